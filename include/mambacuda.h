@@ -1,0 +1,198 @@
+/*
+ * mambacuda.h — C ABI of libmambacuda.so, the B200 (sm_100a) batched MCMC engine that sits
+ * behind Mamba.jl's `Sampler` / `mcmc()` API.
+ *
+ * The reference (jamesonquinn/Mamba.jl, pure Julia) has no FFI for this path; these entry
+ * points are what a Julia `ccall` shim (mamba.jl_b200/julia/MambaCUDA.jl)
+ * binds in place of `mcmc_master!`'s `pmap2(mcmc_worker!, lsts)` (src/model/mcmc.jl:36-59).
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *  - Every pointer is a HOST pointer owned by the caller, read/written only during the call.
+ *  - All floating point data is IEEE double (the reference is Float64 throughout,
+ *    src/Mamba.jl:129-131,152-155,172-177).
+ *  - Host matrices are "one record contiguous": `x[n][D]` in C order == Julia `Array{Float64}(D, n)`.
+ *  - The thinned sample block written by mcu_run is Julia column-major
+ *    `[kept × n_monitor × n_chains]` (iteration fastest), i.e. exactly `ModelChains.value`
+ *    (src/Mamba.jl:172-185, src/output/chains.jl:5-32).
+ *  - Return value 0 = success, negative = error code; text via mcu_last_error().
+ *    Nothing throws or longjmps across the ABI.  Numerical trouble (-Inf / NaN log densities)
+ *    is in-band, as in the reference (src/distributions/distributionstruct.jl:138-140).
+ *  - A handle is bound to ONE CUDA device and is not thread-safe; distinct handles may be used
+ *    from distinct threads/processes.  Chains are sharded across handles by
+ *    (chain_offset, n_chains); the Philox key is the GLOBAL chain id, so results do not depend
+ *    on how chains are sharded.
+ *  - There is no CPU fallback: if no CUDA device is usable every compute entry point fails.
+ */
+#ifndef MAMBACUDA_H
+#define MAMBACUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCU_ABI_VERSION 1
+
+/* ---- error codes -------------------------------------------------------------------------- */
+enum {
+  MCU_OK = 0,
+  MCU_ERR_ARG = -1,        /* ArgumentError in the reference (e.g. src/model/mcmc.jl:22-25)   */
+  MCU_ERR_DIM = -2,        /* DimensionMismatch (src/model/simulation.jl:20-23)               */
+  MCU_ERR_STATE = -3,      /* call order (inputs before inits: src/model/initialization.jl:4) */
+  MCU_ERR_CUDA = -4,       /* CUDA runtime failure / no device                                */
+  MCU_ERR_UNSUPPORTED = -5 /* no device template for the request (no CPU fallback)            */
+};
+
+/* ---- model templates: fixed library compiled to device functions ------- */
+enum {
+  MCU_TPL_LINE = 0,      /* doc/tutorial/line.jl:5-25      nodes: beta[2], s2                 */
+  MCU_TPL_SEEDS = 1,     /* doc/examples/seeds.jl:16-56    nodes: alpha0, alpha1, alpha2, alpha12, s2, b[21] */
+  MCU_TPL_RATS = 2,      /* doc/examples/rats.jl:49-97     nodes: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30] */
+  MCU_TPL_PUMPS = 3,     /* doc/examples/pumps.jl:12-39    nodes: alpha, beta, theta[10]      */
+  MCU_TPL_GLM_LOGIT = 4, /* synthetic Bernoulli-logit GLM  nodes: beta[d]  (no reference file; closest doc/examples/seeds.jl) */
+  MCU_N_TEMPLATES = 5
+};
+
+/* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */
+enum {
+  MCU_AMWG = 0,        /* src/samplers/amwg.jl:47-115  */
+  MCU_SLICE_UNI = 1,   /* src/samplers/slice.jl:66-92  */
+  MCU_SLICE_MULTI = 2, /* src/samplers/slice.jl:95-117 */
+  MCU_RWM = 3,         /* src/samplers/rwm.jl:49-71    */
+  MCU_NUTS = 4,        /* src/samplers/nuts.jl:47-205  */
+  MCU_HMC = 5,         /* src/samplers/hmc.jl:47-111   */
+  MCU_AMM = 6          /* src/samplers/amm.jl:45-108   */
+};
+
+enum { MCU_ADAPT_ALL = 0, MCU_ADAPT_BURNIN = 1, MCU_ADAPT_NONE = 2 }; /* amwg.jl:47-56, amm.jl:45-55 */
+enum { MCU_PROP_NORMAL = 0, MCU_PROP_SYMUNIFORM = 1, MCU_PROP_SYMTRIANGULAR = 2 }; /* rwm.jl:12-13, distributions/extensions.jl:43-53 */
+enum { MCU_GRAD_ANALYTIC = 0, MCU_GRAD_FORWARD = 1, MCU_GRAD_CENTRAL = 2 };       /* nuts.jl:47 dtype; simulation.jl:47-51 */
+enum { MCU_RNG_PHILOX = 0, MCU_RNG_EXTERNAL = 1 };
+enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1 };                                    /* src/output/mcse.jl:3-8 */
+
+/* mcu_run flags */
+#define MCU_RUN_NO_STORE 1u     /* do not keep thinned samples on the device, only streaming moments */
+#define MCU_RUN_FORCE_GENERIC 2u /* never dispatch to a specialised (fused) kernel */
+
+#define MCU_MAX_BLOCK_NODES 8
+
+/*
+ * One sampling block == one `Sampler(params, f, tune)` produced by the reference's sampler
+ * constructors (src/samplers/sampler.jl:20-24).  The Julia shim fills it by inspecting the
+ * Sampler object (type of `tune`, `params`, constructor arguments).
+ */
+typedef struct mcu_block_desc {
+  int32_t kind;                       /* MCU_AMWG ...                                         */
+  int32_t n_nodes;                    /* number of entries in nodes[]                         */
+  int32_t nodes[MCU_MAX_BLOCK_NODES]; /* template node ids, in the order given to the sampler */
+  int32_t transform;                  /* SamplingBlock(model, block, transform): AMWG/RWM/NUTS/HMC/AMM always 1; Slice: kwarg, default 0 (slice.jl:47-50) */
+  int32_t adapt;                      /* MCU_ADAPT_*  (AMWG, AMM)                             */
+  int32_t batchsize;                  /* AMWG, default 50 (amwg.jl:16-19); 0 → default        */
+  int32_t proposal;                   /* RWM: MCU_PROP_*                                      */
+  int32_t L;                          /* HMC: leapfrog steps                                  */
+  int32_t grad;                       /* NUTS/HMC: MCU_GRAD_*                                 */
+  int32_t max_depth;                  /* NUTS tree-depth cap; 0 → 10. (reference: unbounded, nuts.jl:106-124) */
+  int32_t n_scale;                    /* entries behind `scale`: 1 (broadcast) or block dim k; AMM/HMC-with-Sigma: k*k */
+  double target;                      /* AMWG 0.44 (amwg.jl:18) / NUTS 0.6 (nuts.jl:22); 0 → default */
+  double epsilon;                     /* HMC step size; NUTS: <= 0 → nutsepsilon() heuristic (nuts.jl:192-205) */
+  double beta;                        /* AMM mixing weight, default 0.05 (amm.jl:21); 0 → default */
+  double amm_scale;                   /* AMM scale, default 2.38 (amm.jl:22); 0 → default      */
+  const double* scale;                /* AMWG sigma / Slice width / RWM scale; AMM Sigma (k×k, column-major); HMC Sigma or NULL (=I) */
+} mcu_block_desc;
+
+typedef struct mcu_ctx* mcu_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces deepcopy(model) + per-chain ModelState allocation: src/model/mcmc.jl:27-30.       */
+int mcu_create(int template_id, int64_t n_chains, int64_t chain_offset, int device,
+               uint64_t seed, mcu_handle* out);
+int mcu_destroy(mcu_handle h);
+/* Last error text for h (or for the failed mcu_create when h == NULL). */
+const char* mcu_last_error(mcu_handle h);
+int mcu_abi_version(void);
+
+/* ---- model inputs: setinputs!  src/model/initialization.jl:30-40 --------------------------- */
+/* Named input arrays of the template (e.g. "x","y" for line; "r","n","x1","x2" for seeds;
+ * "y","Xm","rat" for rats; "y","t" for pumps; "X" [N×d row-major],"y" for the GLM).
+ * Integer-valued inputs are passed as doubles.  Every template has the reference's dataset as
+ * default, so this is optional except for the GLM.                                            */
+int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, const double* ptr);
+
+/* ---- sampling scheme: setsamplers!  src/model/initialization.jl:42-48 ---------------------- */
+int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks);
+
+/* ---- shapes and names: names(m, true)  src/model/model.jl:231-240 -------------------------- */
+/* D = number of unobserved stochastic elements (state record length); n_monitor = monitored columns. */
+int mcu_dims(mcu_handle h, int* D, int* n_monitor, int* n_nodes);
+/* '\n'-separated names; which = 0 state elements, 1 monitored columns, 2 node names.  Returns needed length if buf too small. */
+int mcu_names(mcu_handle h, int which, char* buf, size_t buflen);
+/* Number of doubles of sampler tune state per chain for the current scheme (sum over blocks). */
+int mcu_tune_size(mcu_handle h, int64_t* n_per_chain);
+
+/* ---- initial values: setinits!  src/model/initialization.jl:3-28 --------------------------- */
+/* x is [n_inits × D] (record contiguous, constrained scale); chain c starts from record
+ * (chain_offset + c) % n_inits.  jitter_sd > 0 adds Philox N(0, jitter_sd²) noise on the
+ * unconstrained scale (stream kind 1; SURVEY.md §8d config 2 "+ jitter").  Resets iter to 0. */
+int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_sd);
+
+/* ---- the engine: mcmc_master!/mcmc_worker!  src/model/mcmc.jl:36-83 ------------------------ */
+/* Advances every chain of the handle by `iters` iterations, continuing from the handle's
+ * iteration counter (0 after mcu_set_inits; restart semantics of mcmc(mc, iters), mcmc.jl:3-16).
+ * Samples with iteration i > burnin and (i - burnin) % thin == 0 are kept (mcmc.jl:76-78).
+ * `out` (may be NULL) receives [kept × n_monitor × n_chains], column-major, where
+ * kept = number of kept iterations inside this call.                                          */
+int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* out, uint32_t flags);
+int64_t mcu_kept(int64_t first_iter, int64_t iters, int64_t burnin, int64_t thin);
+
+/* ---- ModelState round trip (src/Mamba.jl:152-155; mcmc.jl:56,82) --------------------------- */
+/* values [n_chains × D], tune [n_chains × tune_size] (may be NULL), iter = model.iter.        */
+int mcu_get_state(mcu_handle h, double* values, double* tune, int64_t* iter);
+int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_t iter);
+
+/* ---- batched density entry points (parity surface) ----------------------------------------- */
+/* logpdf!(m, x, block, transform)  src/model/simulation.jl:77-90 via src/samplers/sampler.jl:102-104.
+ * state [B × D]: full model state (constrained) for each evaluation; x [B × k] block vector on
+ * the sampler's scale, or NULL to use the block's own values from `state` (unlist, sampler.jl:113-115). */
+int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const double* x, double* lp);
+/* logpdfgrad!(block, x, dtype)  src/samplers/sampler.jl:106-111 (+ analytic mode).  g [B × k]. */
+int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const double* state,
+                   const double* x, double* lp, double* g);
+
+/* ---- diagnostics on the way out ------------------------------------------------------------- */
+/* Cross-chain sums for gelmandiag (src/output/gelmandiag.jl:5-29) over the samples kept since
+ * the last mcu_set_inits, optionally on the link scale (transform, src/output/modelchains.jl:57-76):
+ * sums[p][7] = { m, Σψ̄, Σψ̄², Σs², Σ(s²)², Σs²ψ̄, Σs²ψ̄² } per monitored column, ψ̄/s² = a chain's
+ * mean/variance.  These are what gets all-reduced across GPUs (the ONLY collective).           */
+int mcu_moments(mcu_handle h, int transform, double* sums, int64_t* n_kept);
+/* PSRF and upper CI from (all-reduced) sums: gelmandiag.jl:31-47.  psrf [p × 2] row-major, NOT rounded. */
+int mcu_gelman_from_moments(int64_t n_kept, int p, const double* sums, double alpha, double* psrf);
+/* Convenience single-handle gelmandiag(c; alpha, transform).                                   */
+int mcu_gelman(mcu_handle h, double alpha, int transform, double* psrf);
+/* summarystats(c; etype)  src/output/stats.jl:85-94, mcse.jl:10-33 over the stored samples:
+ * out [p × 5] = mean, SD, naive SE, MCSE, ESS.  Needs stored samples (no MCU_RUN_NO_STORE).    */
+int mcu_summarystats(mcu_handle h, int etype, int batch_size, double* out);
+/* Per-chain streaming batch-means ESS aggregated over chains (for chain counts too large to
+ * store): out [p × 5] = pooled mean, pooled SD, naive SE, MCSE (per-chain batch means pooled), ESS. */
+int mcu_summary_streaming(mcu_handle h, double* out);
+
+/* ---- RNG contract ----------------------------------------------------- */
+/* PHILOX: Philox4x32-10, key = seed, counter = (draw j, iteration, global chain, block|kind<<16).
+ * EXTERNAL: the shim stream of north_star — draws are consumed sequentially from
+ * u[chain][0..n_per_chain) (uniforms in [0,1)); a normal consumes two.                        */
+int mcu_set_rng_mode(mcu_handle h, int mode, const double* u, size_t n_per_chain);
+
+/* ---- device info for the harness ------------------------------------------------------------ */
+int mcu_device_count(void);
+/* Number of kernel launches issued by this handle since creation (bench "gpu_launches").      */
+int64_t mcu_launch_count(mcu_handle h);
+/* Device time in ms of the sampler kernels of the last mcu_run (CUDA events on the launching stream). */
+double mcu_last_kernel_ms(mcu_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMBACUDA_H */

@@ -1,0 +1,285 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rng.hpp header).
+//
+// templates.hpp — the model scripts on the hot path, restated node by node.
+//   line  : doc/tutorial/line.jl:5-25, data :69-73
+//   seeds : doc/examples/seeds.jl:16-56, data :4-12
+//   rats  : doc/examples/rats.jl:49-97, data :4-45
+//   pumps : doc/examples/pumps.jl:12-39, data :4-9
+//   glm   : synthetic Bernoulli-logit regression (no reference file; structure of seeds.jl:18-28
+//           with the prior of line.jl:18)
+// Node order inside each template is a valid topological order and stands in for
+// keys(m, :dependent) (model.jl:112-120), whose exact order in the reference depends on Dict
+// iteration order; it only fixes column order and floating-point summation order.
+// The analytic joint gradients are hand-derived (the reference has none: it differentiates
+// numerically, simulation.jl:47-51) and are validated against the FD gradient in tests.
+#pragma once
+#include "model.hpp"
+
+namespace orc {
+
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4 };
+
+inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
+                      bool observed = false) {
+  Node n; n.name = name; n.stochastic = stochastic; n.len = len; n.scalar = scalar; n.observed = observed;
+  n.value.assign(len, stochastic ? 0.0 : NAN);
+  if (monitored) for (int i = 0; i < len; ++i) n.monitor.push_back(i);  // setmonitor!: dependent.jl:33-51
+  return n;
+}
+
+inline double ig_dlogpdf(double a, double th, double x) { return -(a + 1.0) / x + th / (x * x); }
+
+// ------------------------------------------------------------------------------------------
+inline Model make_line() {
+  Model m; m.template_id = TPL_LINE;
+  m.inputs["x"] = {1, 2, 3, 4, 5};
+  m.inputs["y"] = {1, 3, 3, 3, 5};
+  // beta = Stochastic(1, () -> MvNormal(2, sqrt(1000)))
+  { Node n = make_node("beta", true, 2, false, true);
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::MVNORMAL_ISO; s.distr.mu.assign(2, 0.0); s.distr.sigma = std::sqrt(1000.0); };
+    m.nodes.push_back(n); }
+  // s2 = Stochastic(() -> InverseGamma(0.001, 0.001))
+  { Node n = make_node("s2", true, 1, true, true);
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  // mu = Logical(1, (xmat, beta) -> xmat * beta, false) ; xmat = [ones(5) x]  (line.jl:73)
+  { Node n = make_node("mu", false, 5, false, false);
+    n.sources = {0};
+    n.eval = [](const Model& mm, Node& l) {
+      const auto& x = mm.in("x"); const auto& b = mm.val(0);
+      l.value.resize(x.size());
+      for (size_t i = 0; i < x.size(); ++i) l.value[i] = 1.0 * b[0] + x[i] * b[1];
+    };
+    m.nodes.push_back(n); }
+  // y = Stochastic(1, (mu, s2) -> MvNormal(mu, sqrt(s2)), false)
+  { Node n = make_node("y", true, 5, false, false, true);
+    n.sources = {2, 1};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::MVNORMAL_ISO; s.distr.mu = mm.val(2); s.distr.sigma = std::sqrt(mm.val(1)[0]); };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {
+    const auto& x = mm.in("x"); const auto& y = mm.in("y");
+    const auto& b = mm.val(0); double s2 = mm.val(1)[0];
+    double sr = 0, sxr = 0, srr = 0;
+    for (size_t i = 0; i < x.size(); ++i) { double r = y[i] - b[0] - b[1] * x[i]; sr += r; sxr += x[i] * r; srr += r * r; }
+    g[0] = sr / s2 - b[0] / 1000.0;
+    g[1] = sxr / s2 - b[1] / 1000.0;
+    g[2] = -0.5 * (double)x.size() / s2 + 0.5 * srr / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+inline Model make_seeds() {
+  Model m; m.template_id = TPL_SEEDS;
+  m.inputs["r"] = {10, 23, 23, 26, 17, 5, 53, 55, 32, 46, 10, 8, 10, 8, 23, 0, 3, 22, 15, 32, 3};
+  m.inputs["n"] = {39, 62, 81, 51, 39, 6, 74, 72, 51, 79, 13, 16, 30, 28, 45, 4, 12, 41, 30, 51, 7};
+  m.inputs["x1"] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+  m.inputs["x2"] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1};
+  const char* an[4] = {"alpha0", "alpha1", "alpha2", "alpha12"};
+  for (int k = 0; k < 4; ++k) {   // alpha* = Stochastic(() -> Normal(0, 1000))
+    Node n = make_node(an[k], true, 1, true, true);
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+    m.nodes.push_back(n);
+  }
+  { Node n = make_node("s2", true, 1, true, true);   // InverseGamma(0.001, 0.001)
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b", true, 21, false, false);  // b = Stochastic(1, s2 -> Normal(0, sqrt(s2)), false)
+    n.sources = {4};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(4)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("r", true, 21, false, false, true);  // seeds.jl:18-28
+    n.sources = {0, 1, 2, 3, 5};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& x1 = mm.in("x1"); const auto& x2 = mm.in("x2"); const auto& nn = mm.in("n");
+      double a0 = mm.val(0)[0], a1 = mm.val(1)[0], a2 = mm.val(2)[0], a12 = mm.val(3)[0];
+      const auto& b = mm.val(5);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(nn.size());
+      for (size_t i = 0; i < nn.size(); ++i) {
+        double p = invlogit(a0 + a1 * x1[i] + a2 * x2[i] + a12 * x1[i] * x2[i] + b[i]);
+        s.distr.arr[i] = {D_BINOMIAL, nn[i], p};
+      }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {
+    const auto& x1 = mm.in("x1"); const auto& x2 = mm.in("x2"); const auto& nn = mm.in("n"); const auto& r = mm.in("r");
+    double a0 = mm.val(0)[0], a1 = mm.val(1)[0], a2 = mm.val(2)[0], a12 = mm.val(3)[0], s2 = mm.val(4)[0];
+    const auto& b = mm.val(5);
+    double g0 = 0, g1 = 0, g2 = 0, g12 = 0, sbb = 0;
+    for (size_t i = 0; i < nn.size(); ++i) {
+      double p = invlogit(a0 + a1 * x1[i] + a2 * x2[i] + a12 * x1[i] * x2[i] + b[i]);
+      double de = r[i] - nn[i] * p;
+      g0 += de; g1 += x1[i] * de; g2 += x2[i] * de; g12 += x1[i] * x2[i] * de;
+      g[5 + i] = de - b[i] / s2;
+      sbb += b[i] * b[i];
+    }
+    g[0] = g0 - a0 / 1e6; g[1] = g1 - a1 / 1e6; g[2] = g2 - a2 / 1e6; g[3] = g12 - a12 / 1e6;
+    g[4] = -0.5 * (double)nn.size() / s2 + 0.5 * sbb / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+inline Model make_rats() {
+  Model m; m.template_id = TPL_RATS;
+  static const double Y[150] = {
+    151, 199, 246, 283, 320, 145, 199, 249, 293, 354, 147, 214, 263, 312, 328, 155, 200, 237, 272, 297,
+    135, 188, 230, 280, 323, 159, 210, 252, 298, 331, 141, 189, 231, 275, 305, 159, 201, 248, 297, 338,
+    177, 236, 285, 350, 376, 134, 182, 220, 260, 296, 160, 208, 261, 313, 352, 143, 188, 220, 273, 314,
+    154, 200, 244, 289, 325, 171, 221, 270, 326, 358, 163, 216, 242, 281, 312, 160, 207, 248, 288, 324,
+    142, 187, 234, 280, 316, 156, 203, 243, 283, 317, 157, 212, 259, 307, 336, 152, 203, 246, 286, 321,
+    154, 205, 253, 298, 334, 139, 190, 225, 267, 302, 146, 191, 229, 272, 302, 157, 211, 250, 285, 323,
+    132, 185, 237, 286, 331, 160, 207, 257, 303, 345, 169, 216, 261, 295, 333, 157, 205, 248, 289, 316,
+    137, 180, 219, 258, 291, 153, 200, 244, 286, 324};
+  // rats.jl:38-45: the script's :y is a 30x5 Julia matrix literal written row by row and the
+  // node is a 150-vector; y[k] pairs with rat[k] = div(k-1,5)+1, week[k] = (k-1)%5+1.
+  // (Julia's vec() of that matrix would be column-major; upstream Mamba passes y as the
+  // row-wise flat vector — SURVEY.md §8d config 3 "y flat 150-vector" — which is what is used.)
+  std::vector<double> y(Y, Y + 150), rat(150), Xm(150);
+  const double xs[5] = {8.0, 15.0, 22.0, 29.0, 36.0};
+  double xbar = 22.0;
+  for (int k = 0; k < 150; ++k) { rat[k] = k / 5; Xm[k] = xs[k % 5] - xbar; }
+  m.inputs["y"] = y; m.inputs["rat"] = rat; m.inputs["Xm"] = Xm; m.inputs["xbar"] = {xbar};
+  auto prior_norm = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+  auto prior_ig = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+  { Node n = make_node("mu_alpha", true, 1, true, false); n.eval = prior_norm; m.nodes.push_back(n); }   // 0
+  { Node n = make_node("mu_beta", true, 1, true, true); n.eval = prior_norm; m.nodes.push_back(n); }     // 1
+  { Node n = make_node("alpha0", false, 1, true, true);                                                   // 2
+    n.sources = {0, 1};
+    n.eval = [](const Model& mm, Node& l) { l.value.assign(1, mm.val(0)[0] - mm.in("xbar")[0] * mm.val(1)[0]); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("s2_alpha", true, 1, true, false); n.eval = prior_ig; m.nodes.push_back(n); }     // 3
+  { Node n = make_node("s2_beta", true, 1, true, false); n.eval = prior_ig; m.nodes.push_back(n); }      // 4
+  { Node n = make_node("s2_c", true, 1, true, true); n.eval = prior_ig; m.nodes.push_back(n); }          // 5
+  { Node n = make_node("alpha", true, 30, false, false);                                                 // 6
+    n.sources = {0, 3};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, mm.val(0)[0], std::sqrt(mm.val(3)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("beta", true, 30, false, false);                                                  // 7
+    n.sources = {1, 4};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, mm.val(1)[0], std::sqrt(mm.val(4)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 150, false, false, true);                                              // 8
+    n.sources = {6, 7, 5};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& rat = mm.in("rat"); const auto& Xm = mm.in("Xm");
+      const auto& a = mm.val(6); const auto& b = mm.val(7);
+      s.distr.form = Distr::MVNORMAL_ISO; s.distr.mu.resize(rat.size());
+      for (size_t k = 0; k < rat.size(); ++k) { int i = (int)rat[k]; s.distr.mu[k] = a[i] + b[i] * Xm[k]; }
+      s.distr.sigma = std::sqrt(mm.val(5)[0]);
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {
+    // state record: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30]
+    const auto& rat = mm.in("rat"); const auto& Xm = mm.in("Xm"); const auto& y = mm.in("y");
+    double mua = mm.val(0)[0], mub = mm.val(1)[0], s2a = mm.val(3)[0], s2b = mm.val(4)[0], s2c = mm.val(5)[0];
+    const auto& a = mm.val(6); const auto& b = mm.val(7);
+    for (int i = 0; i < 60; ++i) g[5 + i] = 0.0;
+    double see = 0;
+    for (size_t k = 0; k < rat.size(); ++k) {
+      int i = (int)rat[k]; double e = y[k] - (a[i] + b[i] * Xm[k]);
+      g[5 + i] += e / s2c; g[35 + i] += e * Xm[k] / s2c; see += e * e;
+    }
+    double sa = 0, saa = 0, sb = 0, sbb = 0;
+    for (int i = 0; i < 30; ++i) {
+      double da = a[i] - mua, db = b[i] - mub;
+      g[5 + i] -= da / s2a; g[35 + i] -= db / s2b;
+      sa += da; saa += da * da; sb += db; sbb += db * db;
+    }
+    g[0] = sa / s2a - mua / 1e6;
+    g[1] = sb / s2b - mub / 1e6;
+    g[2] = -15.0 / s2a + 0.5 * saa / (s2a * s2a) + ig_dlogpdf(0.001, 0.001, s2a);
+    g[3] = -15.0 / s2b + 0.5 * sbb / (s2b * s2b) + ig_dlogpdf(0.001, 0.001, s2b);
+    g[4] = -75.0 / s2c + 0.5 * see / (s2c * s2c) + ig_dlogpdf(0.001, 0.001, s2c);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+inline Model make_pumps() {
+  Model m; m.template_id = TPL_PUMPS;
+  m.inputs["y"] = {5, 1, 5, 14, 3, 19, 1, 1, 4, 22};
+  m.inputs["t"] = {94.3, 15.7, 62.9, 126, 5.24, 31.4, 1.05, 1.05, 2.1, 10.5};
+  { Node n = make_node("alpha", true, 1, true, true);   // Exponential(1.0)
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_EXPONENTIAL, 1.0, 0.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("beta", true, 1, true, true);    // Gamma(0.1, 1.0)
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_GAMMA, 0.1, 1.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("theta", true, 10, false, true); // (alpha, beta) -> Gamma(alpha, 1 / beta)
+    n.sources = {0, 1};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_GAMMA, mm.val(0)[0], 1.0 / mm.val(1)[0]}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 10, false, false, true);  // Poisson(theta[i] * t[i])
+    n.sources = {2};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& t = mm.in("t"); const auto& th = mm.val(2);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(t.size());
+      for (size_t i = 0; i < t.size(); ++i) s.distr.arr[i] = {D_POISSON, th[i] * t[i], 0.0};
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {
+    const auto& t = mm.in("t"); const auto& y = mm.in("y");
+    double al = mm.val(0)[0], be = mm.val(1)[0]; const auto& th = mm.val(2);
+    double slog = 0, sth = 0; double N = (double)t.size();
+    for (size_t i = 0; i < t.size(); ++i) {
+      g[2 + i] = y[i] / th[i] - t[i] + (al - 1.0) / th[i] - be;
+      slog += std::log(th[i]); sth += th[i];
+    }
+    g[0] = N * std::log(be) + slog - N * digamma(al) - 1.0;
+    g[1] = N * al / be - sth + (0.1 - 1.0) / be - 1.0;
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  Inputs "X" (N*d,
+// row-major) and "y" must be supplied; d is taken from inputs["d"].
+inline Model make_glm(int d) {
+  Model m; m.template_id = TPL_GLM;
+  m.inputs["d"] = {(double)d};
+  { Node n = make_node("beta", true, d, false, true);
+    n.eval = [d](const Model&, Node& s) { s.distr.form = Distr::MVNORMAL_ISO; s.distr.mu.assign(d, 0.0); s.distr.sigma = std::sqrt(1000.0); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 0, false, false, true);
+    n.sources = {0};
+    n.eval = [d](const Model& mm, Node& s) {
+      const auto& X = mm.in("X"); const auto& be = mm.val(0);
+      size_t N = X.size() / d;
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(N);
+      for (size_t i = 0; i < N; ++i) {
+        double eta = 0; for (int j = 0; j < d; ++j) eta += X[i * d + j] * be[j];
+        s.distr.arr[i] = {D_BERNOULLI, invlogit(eta), 0.0};
+      }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [d](const Model& mm, std::vector<double>& g) {
+    const auto& X = mm.in("X"); const auto& y = mm.in("y"); const auto& be = mm.val(0);
+    size_t N = X.size() / d;
+    for (int j = 0; j < d; ++j) g[j] = -be[j] / 1000.0;
+    for (size_t i = 0; i < N; ++i) {
+      double eta = 0; for (int j = 0; j < d; ++j) eta += X[i * d + j] * be[j];
+      double r = y[i] - invlogit(eta);
+      for (int j = 0; j < d; ++j) g[j] += r * X[i * d + j];
+    }
+  };
+  m.finalize();
+  return m;
+}
+
+inline Model make_template(int id, int glm_d = 0) {
+  switch (id) {
+    case TPL_LINE: return make_line();
+    case TPL_SEEDS: return make_seeds();
+    case TPL_RATS: return make_rats();
+    case TPL_PUMPS: return make_pumps();
+    case TPL_GLM: return make_glm(glm_d > 0 ? glm_d : 1);
+    default: throw std::runtime_error("unknown template");
+  }
+}
+
+}  // namespace orc
