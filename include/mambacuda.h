@@ -163,20 +163,41 @@ int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const doub
                    const double* x, double* lp, double* g);
 
 /* ---- diagnostics on the way out ------------------------------------------------------------- */
-/* Cross-chain sums for gelmandiag (src/output/gelmandiag.jl:5-29) over the samples kept since
- * the last mcu_set_inits, optionally on the link scale (transform, src/output/modelchains.jl:57-76):
- * sums[p][7] = { m, Σψ̄, Σψ̄², Σs², Σ(s²)², Σs²ψ̄, Σs²ψ̄² } per monitored column, ψ̄/s² = a chain's
- * mean/variance.  These are what gets all-reduced across GPUs (the ONLY collective).           */
-int mcu_moments(mcu_handle h, int transform, double* sums, int64_t* n_kept);
-/* PSRF and upper CI from (all-reduced) sums: gelmandiag.jl:31-47.  psrf [p × 2] row-major, NOT rounded. */
-int mcu_gelman_from_moments(int64_t n_kept, int p, const double* sums, double alpha, double* psrf);
+/* All streaming statistics cover the samples kept since the last mcu_set_inits.  They are held
+ * per chain on the device (Welford mean/M2 on the raw and log scale, min/max, batch means of
+ * size 100) and reduced across chains by reduction kernels; what crosses the ABI is O(p).
+ *
+ * link(c) for gelmandiag(transform=true): src/output/modelchains.jl:57-76, src/output/chains.jl:237-246.
+ * codes[p]: 0 identity, 1 log.  Monitored stochastic columns use their node's link; Logical
+ * columns use the reference's data-dependent heuristic (log when every value is > 0), resolved
+ * from minmax[p×2] (pass the all-reduced min/max for multi-GPU, or NULL to use this handle's).  */
+int mcu_minmax(mcu_handle h, double* minmax /* [p × 2] */);
+int mcu_link_codes(mcu_handle h, int transform, const double* minmax, int* codes);
+
+/* Cross-chain sums for gelmandiag (src/output/gelmandiag.jl:12-29).  With psibar_c / s2_c a chain's
+ * mean / variance of column j (on the scale given by codes, NULL = identity) and centres
+ * center[j] = (c1, c2) (NULL = 0):  d = psibar_c - c1, e = s2_c - c2,
+ *   sums[j][7] = { m, Σd, Σd², Σe, Σe², Σe·d, Σe·d² }   (Σ over this handle's chains).
+ * These 7·p doubles are the ONLY thing all-reduced across GPUs.  Two passes (first with
+ * center = NULL to get the means, then centred) keep the variances free of cancellation.       */
+int mcu_moments(mcu_handle h, const int* codes, const double* center, double* sums, int64_t* n_kept);
+/* PSRF and its upper confidence limit from (all-reduced) centred sums: gelmandiag.jl:20-47.
+ * psrf [p × 2] row-major, NOT rounded (the reference rounds to 3 dp at gelmandiag.jl:59).        */
+int mcu_gelman_from_moments(int64_t n_kept, int p, const double* center, const double* sums,
+                            double alpha, double* psrf);
 /* Convenience single-handle gelmandiag(c; alpha, transform).                                   */
 int mcu_gelman(mcu_handle h, double alpha, int transform, double* psrf);
-/* summarystats(c; etype)  src/output/stats.jl:85-94, mcse.jl:10-33 over the stored samples:
- * out [p × 5] = mean, SD, naive SE, MCSE, ESS.  Needs stored samples (no MCU_RUN_NO_STORE).    */
+
+/* summarystats(c; etype)  src/output/stats.jl:85-94, src/output/mcse.jl:10-33 over the samples stored
+ * by the last mcu_run (needs them: no MCU_RUN_NO_STORE): out [p × 5] = mean, SD, naive SE, MCSE, ESS. */
 int mcu_summarystats(mcu_handle h, int etype, int batch_size, double* out);
-/* Per-chain streaming batch-means ESS aggregated over chains (for chain counts too large to
- * store): out [p × 5] = pooled mean, pooled SD, naive SE, MCSE (per-chain batch means pooled), ESS. */
+/* Streaming form for chain counts too large to store: per-column sums
+ *   sums[j][8] = { C, Σ mean_c, Σ M2_c, Σ (mean_c - c1)², Σ nb_c, Σ nb_c·bmean_c, Σ bM2_c, Σ nb_c (bmean_c - c2)² }
+ * (center[j] = (c1, c2) or NULL), all-reducible like mcu_moments; and the single-handle
+ * convenience that returns [p × 5] = mean, SD, naive SE, MCSE (batch means of 100, batches never
+ * straddle chains), ESS = min((SD/MCSE)², kept per chain) (stats.jl:92).                        */
+int mcu_summary_sums(mcu_handle h, const double* center, double* sums);
+int mcu_summary_from_sums(int64_t n_kept, int p, const double* center, const double* sums, double* out);
 int mcu_summary_streaming(mcu_handle h, double* out);
 
 /* ---- RNG contract ----------------------------------------------------- */

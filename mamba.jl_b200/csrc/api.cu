@@ -1,0 +1,796 @@
+// api.cu — the C ABI of libmambacuda.so (include/mambacuda.h): handle, data upload, scheme
+// descriptors, engine launches, state round trip, batched density entry points and the
+// on-device diagnostics.  Host side of what the Julia shim calls instead of
+// mcmc_master!/mcmc_worker! (src/model/mcmc.jl:36-83).
+//
+// There is no CPU fallback anywhere in this file: every compute entry point launches CUDA
+// kernels and fails with MCU_ERR_CUDA when no device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mambacuda.h"
+#include "hostdiag.hpp"
+#include "launch.hpp"
+
+using namespace mcu;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct mcu_ctx_impl;
+
+}  // namespace
+
+struct mcu_ctx {
+  int tpl = -1;
+  long long C = 0, chain_offset = 0;
+  int device = 0;
+  unsigned long long seed = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, std::vector<double>> inputs;
+  std::map<std::string, double*> d_inputs;
+  int* d_rat = nullptr;
+  bool data_dirty = true;
+  int D = 0, P = 0, NN = 0, glm_d = 0;
+  std::vector<int> elink_state;   // link code per state element
+  int* d_elink_state = nullptr;
+  // scheme
+  std::vector<DevBlock> h_blocks;
+  DevBlock* d_blocks = nullptr;
+  std::vector<void*> scheme_allocs;
+  long long tune_size = 0;
+  // chain state
+  double *d_state = nullptr, *d_tune = nullptr, *d_samples = nullptr, *d_mom = nullptr, *d_momn = nullptr;
+  size_t samples_cap = 0; long long samples_kept = 0;
+  long long iter = 0;
+  bool has_inits = false;
+  // rng
+  int rng_mode = MCU_RNG_PHILOX; double* d_ext = nullptr; size_t ext_n = 0; unsigned long long* d_ext_pos = nullptr;
+  // bookkeeping
+  std::string err;
+  long long launches = 0;
+  double last_ms = 0.0;
+  bool seeds_fast_ok = false;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return MCU_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+int fail(mcu_handle h, int code, const std::string& msg) { h->err = msg; return code; }
+
+inline unsigned grid_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- template metadata on the host ---------------------------------------------------------------
+template <class M> struct Host;
+
+std::vector<double> lchoose_vec(const std::vector<double>& n, const std::vector<double>& r) {
+  std::vector<double> lc(n.size());
+  for (size_t i = 0; i < n.size(); ++i) lc[i] = std::lgamma(n[i] + 1.0) - std::lgamma(r[i] + 1.0) - std::lgamma(n[i] - r[i] + 1.0);
+  return lc;
+}
+
+void default_inputs(mcu_ctx* h) {
+  auto& in = h->inputs;
+  switch (h->tpl) {
+    case MCU_TPL_LINE:   // doc/tutorial/line.jl:69-73
+      in["x"] = {1, 2, 3, 4, 5}; in["y"] = {1, 3, 3, 3, 5};
+      break;
+    case MCU_TPL_SEEDS:  // doc/examples/seeds.jl:4-12
+      in["r"] = {10, 23, 23, 26, 17, 5, 53, 55, 32, 46, 10, 8, 10, 8, 23, 0, 3, 22, 15, 32, 3};
+      in["n"] = {39, 62, 81, 51, 39, 6, 74, 72, 51, 79, 13, 16, 30, 28, 45, 4, 12, 41, 30, 51, 7};
+      in["x1"] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+      in["x2"] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1};
+      break;
+    case MCU_TPL_RATS: {  // doc/examples/rats.jl:4-45
+      static const double Y[150] = {
+        151, 199, 246, 283, 320, 145, 199, 249, 293, 354, 147, 214, 263, 312, 328, 155, 200, 237, 272, 297,
+        135, 188, 230, 280, 323, 159, 210, 252, 298, 331, 141, 189, 231, 275, 305, 159, 201, 248, 297, 338,
+        177, 236, 285, 350, 376, 134, 182, 220, 260, 296, 160, 208, 261, 313, 352, 143, 188, 220, 273, 314,
+        154, 200, 244, 289, 325, 171, 221, 270, 326, 358, 163, 216, 242, 281, 312, 160, 207, 248, 288, 324,
+        142, 187, 234, 280, 316, 156, 203, 243, 283, 317, 157, 212, 259, 307, 336, 152, 203, 246, 286, 321,
+        154, 205, 253, 298, 334, 139, 190, 225, 267, 302, 146, 191, 229, 272, 302, 157, 211, 250, 285, 323,
+        132, 185, 237, 286, 331, 160, 207, 257, 303, 345, 169, 216, 261, 295, 333, 157, 205, 248, 289, 316,
+        137, 180, 219, 258, 291, 153, 200, 244, 286, 324};
+      const double xs[5] = {8.0, 15.0, 22.0, 29.0, 36.0};
+      std::vector<double> y(Y, Y + 150), rat(150), Xm(150);
+      for (int k = 0; k < 150; ++k) { rat[k] = k / 5; Xm[k] = xs[k % 5] - 22.0; }
+      in["y"] = y; in["rat"] = rat; in["Xm"] = Xm; in["xbar"] = {22.0};
+      break;
+    }
+    case MCU_TPL_PUMPS:  // doc/examples/pumps.jl:4-9
+      in["y"] = {5, 1, 5, 14, 3, 19, 1, 1, 4, 22};
+      in["t"] = {94.3, 15.7, 62.9, 126, 5.24, 31.4, 1.05, 1.05, 2.1, 10.5};
+      break;
+    default: break;
+  }
+}
+
+int upload_inputs(mcu_ctx* h) {
+  if (!h->data_dirty) return MCU_OK;
+  for (auto& kv : h->d_inputs) cudaFree(kv.second);
+  h->d_inputs.clear();
+  if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
+  auto in = h->inputs;   // derived arrays
+  if (h->tpl == MCU_TPL_SEEDS) in["lc"] = lchoose_vec(in["n"], in["r"]);
+  if (h->tpl == MCU_TPL_PUMPS) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
+  for (auto& kv : in) {
+    if (kv.second.empty()) continue;
+    double* p = nullptr;
+    CK(cudaMalloc(&p, kv.second.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(p, kv.second.data(), kv.second.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->d_inputs[kv.first] = p;
+  }
+  if (h->tpl == MCU_TPL_RATS) {
+    std::vector<int> rat; for (double r : in["rat"]) rat.push_back((int)r);
+    CK(cudaMalloc(&h->d_rat, rat.size() * sizeof(int)));
+    CK(cudaMemcpyAsync(h->d_rat, rat.data(), rat.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->data_dirty = false;
+  return MCU_OK;
+}
+
+template <> struct Host<LineModel> {
+  static LineModel::Data data(mcu_ctx* h) { return {h->d_inputs["x"], h->d_inputs["y"], (int)h->inputs["y"].size()}; }
+};
+template <> struct Host<SeedsModel> {
+  static SeedsModel::Data data(mcu_ctx* h) {
+    return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["x1"], h->d_inputs["x2"], h->d_inputs["lc"], (int)h->inputs["r"].size()};
+  }
+};
+template <> struct Host<RatsModel> {
+  static RatsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["Xm"], h->d_rat, (int)h->inputs["y"].size(), h->inputs["xbar"][0]}; }
+};
+template <> struct Host<PumpsModel> {
+  static PumpsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["t"], h->d_inputs["lgy1"], (int)h->inputs["y"].size()}; }
+};
+template <> struct Host<GlmM> {
+  static GlmM::Data data(mcu_ctx* h) { return {h->d_inputs["X"], h->d_inputs["y"], (int)h->inputs["y"].size(), h->glm_d}; }
+};
+
+#define MCU_DISPATCH(h, BODY)                                                      \
+  switch ((h)->tpl) {                                                              \
+    case MCU_TPL_LINE: { typedef LineModel M; BODY; break; }                       \
+    case MCU_TPL_SEEDS: { typedef SeedsModel M; BODY; break; }                     \
+    case MCU_TPL_RATS: { typedef RatsModel M; BODY; break; }                       \
+    case MCU_TPL_PUMPS: { typedef PumpsModel M; BODY; break; }                     \
+    case MCU_TPL_GLM_LOGIT: { typedef GlmM M; BODY; break; }                       \
+    default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
+  }
+
+struct TplInfo { int D, P, NN; std::vector<int> off, len, link, monlink; std::vector<std::string> node_names; };
+
+template <class M> TplInfo tpl_info_fixed() {
+  TplInfo t; t.D = M::D; t.P = M::P; t.NN = M::NN;
+  for (int n = 0; n < M::NN; ++n) { t.off.push_back(M::node_off(n)); t.len.push_back(M::node_len(n)); t.link.push_back(M::node_link(n)); t.node_names.push_back(M::node_name(n)); }
+  for (int j = 0; j < M::P; ++j) t.monlink.push_back(M::mon_link(j));
+  return t;
+}
+TplInfo tpl_info(const mcu_ctx* h) {
+  switch (h->tpl) {
+    case MCU_TPL_LINE: return tpl_info_fixed<LineModel>();
+    case MCU_TPL_SEEDS: return tpl_info_fixed<SeedsModel>();
+    case MCU_TPL_RATS: return tpl_info_fixed<RatsModel>();
+    case MCU_TPL_PUMPS: return tpl_info_fixed<PumpsModel>();
+    default: {
+      TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
+      t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
+      t.monlink.assign(h->glm_d, LINK_IDENT);
+      return t;
+    }
+  }
+}
+
+std::string names_of(const mcu_ctx* h, int which) {
+  TplInfo t = tpl_info(h);
+  std::string s;
+  auto add = [&](const std::string& x) { if (!s.empty()) s += "\n"; s += x; };
+  if (which == 2) { for (auto& n : t.node_names) add(n); return s; }
+  if (which == 1) {
+    switch (h->tpl) {
+      case MCU_TPL_LINE: return LineModel::monitor_names();
+      case MCU_TPL_SEEDS: return SeedsModel::monitor_names();
+      case MCU_TPL_RATS: return RatsModel::monitor_names();
+      case MCU_TPL_PUMPS: return PumpsModel::monitor_names();
+      default: break;
+    }
+  }
+  for (int n = 0; n < t.NN; ++n) {
+    if (t.len[n] == 1 && h->tpl != MCU_TPL_GLM_LOGIT) add(t.node_names[n]);
+    else for (int e = 0; e < t.len[n]; ++e) add(t.node_names[n] + "[" + std::to_string(e + 1) + "]");
+  }
+  return s;
+}
+
+void free_scheme(mcu_ctx* h) {
+  for (void* p : h->scheme_allocs) cudaFree(p);
+  h->scheme_allocs.clear();
+  if (h->d_blocks) { cudaFree(h->d_blocks); h->d_blocks = nullptr; }
+  h->h_blocks.clear();
+}
+void free_chain_buffers(mcu_ctx* h) {
+  cudaFree(h->d_state); cudaFree(h->d_tune); cudaFree(h->d_samples); cudaFree(h->d_mom); cudaFree(h->d_momn);
+  h->d_state = h->d_tune = h->d_samples = h->d_mom = h->d_momn = nullptr;
+  h->samples_cap = 0; h->samples_kept = 0;
+}
+
+bool chol_lower_host(const std::vector<double>& A, int n, std::vector<double>& L) {
+  L.assign((size_t)n * n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + (size_t)j * n];
+    for (int c = 0; c < j; ++c) d -= L[j + (size_t)c * n] * L[j + (size_t)c * n];
+    if (!(d > 0.0)) return false;
+    const double dj = std::sqrt(d); L[j + (size_t)j * n] = dj;
+    for (int i = j + 1; i < n; ++i) {
+      double a = A[i + (size_t)j * n];
+      for (int c = 0; c < j; ++c) a -= L[i + (size_t)c * n] * L[j + (size_t)c * n];
+      L[i + (size_t)j * n] = a / dj;
+    }
+  }
+  return true;
+}
+
+int ensure_chain_buffers(mcu_ctx* h) {
+  if (h->d_state) return MCU_OK;
+  const size_t C = (size_t)h->C;
+  CK(cudaMalloc(&h->d_state, sizeof(double) * C * std::max(1, h->D)));
+  CK(cudaMalloc(&h->d_tune, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size)));
+  CK(cudaMalloc(&h->d_mom, sizeof(double) * C * (size_t)h->P * kMomPerCol));
+  CK(cudaMalloc(&h->d_momn, sizeof(double) * C * 3));
+  CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size), h->stream));
+  CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
+  CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  return MCU_OK;
+}
+
+bool scheme_is_seeds_fast(const mcu_ctx* h) {
+  // AMWG(alpha0..alpha12) , AMWG(b) , AMWG(s2) — SURVEY.md §8d config 2 scheme A
+  if (h->tpl != MCU_TPL_SEEDS || h->h_blocks.size() != 3) return false;
+  const DevBlock& a = h->h_blocks[0]; const DevBlock& b = h->h_blocks[1]; const DevBlock& c = h->h_blocks[2];
+  if (a.kind != MCU_AMWG || b.kind != MCU_AMWG || c.kind != MCU_AMWG) return false;
+  if (a.n_own != 4 || a.own[0] != 0 || a.own[1] != 1 || a.own[2] != 2 || a.own[3] != 3) return false;
+  if (b.n_own != 1 || b.own[0] != 5) return false;
+  if (c.n_own != 1 || c.own[0] != 4) return false;
+  if ((int)h->inputs.at("r").size() != SeedsModel::NP) return false;
+  return true;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mcu_abi_version(void) { return MCU_ABI_VERSION; }
+
+int mcu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* mcu_last_error(mcu_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int mcu_create(int template_id, int64_t n_chains, int64_t chain_offset, int device, uint64_t seed, mcu_handle* out) {
+  if (!out) { g_create_err = "out is NULL"; return MCU_ERR_ARG; }
+  *out = nullptr;
+  if (template_id < 0 || template_id >= MCU_N_TEMPLATES) { g_create_err = "unknown template id"; return MCU_ERR_ARG; }
+  if (n_chains < 1) { g_create_err = "n_chains must be positive"; return MCU_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libmambacuda has no CPU fallback";
+    return MCU_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return MCU_ERR_ARG; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MCU_ERR_CUDA; }
+  mcu_ctx* h = new mcu_ctx();
+  h->tpl = template_id; h->C = n_chains; h->chain_offset = chain_offset; h->device = device; h->seed = seed;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    g_create_err = "cannot create stream/events"; delete h; return MCU_ERR_CUDA;
+  }
+  default_inputs(h);
+  TplInfo t = tpl_info(h);
+  h->D = t.D; h->P = t.P; h->NN = t.NN;
+  *out = h;
+  return MCU_OK;
+}
+
+int mcu_destroy(mcu_handle h) {
+  if (!h) return MCU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_scheme(h); free_chain_buffers(h);
+  for (auto& kv : h->d_inputs) cudaFree(kv.second);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
+  delete h;
+  return MCU_OK;
+}
+
+int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, const double* ptr) {
+  if (!h || !name || !dims || !ptr || ndim < 1) return h ? fail(h, MCU_ERR_ARG, "bad argument to mcu_set_data") : MCU_ERR_ARG;
+  size_t n = 1; for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i];
+  const std::string nm(name);
+  if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "X") {
+    if (ndim != 2) return fail(h, MCU_ERR_DIM, "X must be [N × d]");
+    if (dims[1] < 1 || dims[1] > kGlmDMax) return fail(h, MCU_ERR_UNSUPPORTED, "GLM template supports 1 <= d <= 128");
+    if (h->glm_d != (int)dims[1]) { free_chain_buffers(h); free_scheme(h); h->has_inits = false; }
+    h->glm_d = (int)dims[1]; h->D = h->glm_d; h->P = h->glm_d;
+  } else if (h->tpl != MCU_TPL_GLM_LOGIT) {
+    if (h->inputs.find(nm) == h->inputs.end()) return fail(h, MCU_ERR_ARG, "template has no input named " + nm);
+    if (h->tpl == MCU_TPL_SEEDS && n != (size_t)SeedsModel::NP) return fail(h, MCU_ERR_DIM, "seeds inputs have 21 entries");
+    if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
+    if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
+  }
+  h->inputs[nm].assign(ptr, ptr + n);
+  h->data_dirty = true;
+  return MCU_OK;
+}
+
+int mcu_dims(mcu_handle h, int* D, int* n_monitor, int* n_nodes) {
+  if (!h) return MCU_ERR_ARG;
+  if (D) *D = h->D;
+  if (n_monitor) *n_monitor = h->P;
+  if (n_nodes) *n_nodes = h->NN;
+  return MCU_OK;
+}
+
+int mcu_names(mcu_handle h, int which, char* buf, size_t buflen) {
+  if (!h) return MCU_ERR_ARG;
+  const std::string s = names_of(h, which);
+  if (!buf || s.size() + 1 > buflen) return (int)s.size() + 1;
+  std::memcpy(buf, s.c_str(), s.size() + 1);
+  return MCU_OK;
+}
+
+int mcu_tune_size(mcu_handle h, int64_t* n) {
+  if (!h || !n) return MCU_ERR_ARG;
+  *n = h->tune_size;
+  return MCU_OK;
+}
+
+int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
+  if (!h || n_blocks < 1 || !blocks) return h ? fail(h, MCU_ERR_ARG, "bad argument to mcu_set_scheme") : MCU_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  if (h->tpl == MCU_TPL_GLM_LOGIT && h->glm_d == 0) return fail(h, MCU_ERR_STATE, "inputs must be set before the scheme (GLM needs X)");
+  TplInfo t = tpl_info(h);
+  free_scheme(h);
+  free_chain_buffers(h);
+  h->has_inits = false;
+  long long toff = 0;
+  std::vector<DevBlock> hb;
+  for (int bi = 0; bi < n_blocks; ++bi) {
+    const mcu_block_desc& d = blocks[bi];
+    if (d.kind < MCU_AMWG || d.kind > MCU_AMM) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
+    if (d.n_nodes < 1 || d.n_nodes > MCU_MAX_BLOCK_NODES) return fail(h, MCU_ERR_ARG, "block must name 1..8 nodes");
+    DevBlock b; std::memset(&b, 0, sizeof(b));
+    b.kind = d.kind;
+    b.transform = (d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI) ? (d.transform != 0) : 1;   // slice.jl:47-50; others sampler files :53
+    b.adapt = d.adapt;
+    if (d.adapt < MCU_ADAPT_ALL || d.adapt > MCU_ADAPT_NONE) return fail(h, MCU_ERR_ARG, "adapt must be one of :all, :burnin, or :none");   // amwg.jl:49-50
+    b.batchsize = d.batchsize > 0 ? d.batchsize : 50;
+    b.proposal = d.proposal; b.L = d.L; b.grad = d.grad; b.max_depth = d.max_depth;
+    b.target = d.target > 0 ? d.target : (d.kind == MCU_NUTS ? 0.6 : 0.44);
+    b.epsilon = d.epsilon; b.beta = d.beta > 0 ? d.beta : 0.05; b.amm_scale = d.amm_scale > 0 ? d.amm_scale : 2.38;
+    std::vector<int> elem, elink;
+    for (int i = 0; i < d.n_nodes; ++i) {
+      const int n = d.nodes[i];
+      if (n < 0 || n >= t.NN) return fail(h, MCU_ERR_ARG, "node id out of range");
+      if (b.mask & (1u << n)) return fail(h, MCU_ERR_ARG, "node listed twice in a block");
+      b.mask |= 1u << n; b.own[i] = n;
+      for (int e = 0; e < t.len[n]; ++e) { elem.push_back(t.off[n] + e); elink.push_back(t.link[n]); }
+    }
+    b.n_own = d.n_nodes; b.k = (int)elem.size();
+    const int k = b.k;
+    // scale: sigma / width / scale  (validate(): amwg.jl:38-43, slice.jl:34-40, rwm.jl:40-46)
+    std::vector<double> sc;
+    const bool needs_scale = d.kind == MCU_AMWG || d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI || d.kind == MCU_RWM;
+    if (needs_scale) {
+      if (!d.scale || (d.n_scale != 1 && d.n_scale != k))
+        return fail(h, MCU_ERR_ARG, "length(scale) differs from variate length " + std::to_string(k));
+      for (int i = 0; i < k; ++i) sc.push_back(d.n_scale == 1 ? d.scale[0] : d.scale[i]);
+    }
+    std::vector<double> SL;
+    if (d.kind == MCU_AMM || (d.kind == MCU_HMC && d.scale)) {
+      if (!d.scale || d.n_scale != k * k) return fail(h, MCU_ERR_ARG, "Sigma dimension differs from variate length " + std::to_string(k));   // amm.jl:36-41, hmc.jl:36-41
+      if (d.kind == MCU_AMM && k > kAmmMaxK) return fail(h, MCU_ERR_UNSUPPORTED, "AMM blocks are limited to 8 elements on the device");
+      std::vector<double> S(d.scale, d.scale + (size_t)k * k);
+      if (!chol_lower_host(S, k, SL)) return fail(h, MCU_ERR_ARG, "Sigma is not positive definite");
+    }
+    if (d.kind == MCU_HMC && (d.L < 1 || !(d.epsilon > 0))) return fail(h, MCU_ERR_ARG, "HMC needs epsilon > 0 and L >= 1");
+    if (d.kind == MCU_RWM && (d.proposal < 0 || d.proposal > 2)) return fail(h, MCU_ERR_UNSUPPORTED, "RWM proposal not available on the device");
+    if (d.grad < 0 || d.grad > 2) return fail(h, MCU_ERR_ARG, "unknown gradient mode");
+    int *de = nullptr, *dl = nullptr; double *ds = nullptr, *dS = nullptr;
+    CK(cudaMalloc(&de, sizeof(int) * k)); h->scheme_allocs.push_back(de);
+    CK(cudaMalloc(&dl, sizeof(int) * k)); h->scheme_allocs.push_back(dl);
+    CK(cudaMemcpy(de, elem.data(), sizeof(int) * k, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dl, elink.data(), sizeof(int) * k, cudaMemcpyHostToDevice));
+    if (!sc.empty()) { CK(cudaMalloc(&ds, sizeof(double) * k)); h->scheme_allocs.push_back(ds); CK(cudaMemcpy(ds, sc.data(), sizeof(double) * k, cudaMemcpyHostToDevice)); }
+    if (!SL.empty()) { CK(cudaMalloc(&dS, sizeof(double) * k * k)); h->scheme_allocs.push_back(dS); CK(cudaMemcpy(dS, SL.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice)); }
+    b.elem = de; b.elink = dl; b.scale = ds; b.SigmaL = dS;
+    b.tune_off = (int)toff;
+    switch (d.kind) {   // tune record layout: see samplers.cuh
+      case MCU_AMWG: toff += 2 + 2 * k; break;
+      case MCU_NUTS: toff += 8; break;
+      case MCU_AMM: toff += 2 + k + 2 * k * k; break;
+      default: break;
+    }
+    hb.push_back(b);
+  }
+  h->h_blocks = hb;
+  h->tune_size = toff;
+  CK(cudaMalloc(&h->d_blocks, sizeof(DevBlock) * hb.size()));
+  CK(cudaMemcpy(h->d_blocks, hb.data(), sizeof(DevBlock) * hb.size(), cudaMemcpyHostToDevice));
+  // link code of every state element (for init jitter)
+  h->elink_state.assign(h->D, LINK_IDENT);
+  for (int n = 0; n < t.NN; ++n) for (int e = 0; e < t.len[n]; ++e) h->elink_state[t.off[n] + e] = t.link[n];
+  cudaFree(h->d_elink_state); h->d_elink_state = nullptr;
+  CK(cudaMalloc(&h->d_elink_state, sizeof(int) * h->D));
+  CK(cudaMemcpy(h->d_elink_state, h->elink_state.data(), sizeof(int) * h->D, cudaMemcpyHostToDevice));
+  h->seeds_fast_ok = scheme_is_seeds_fast(h);
+  return MCU_OK;
+}
+
+int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_sd) {
+  if (!h || !x) return h ? fail(h, MCU_ERR_ARG, "missing initial values") : MCU_ERR_ARG;
+  if (n_inits < 1) return fail(h, MCU_ERR_ARG, "fewer initial values than chains");   // mcmc.jl:24-25
+  if (h->h_blocks.empty()) return fail(h, MCU_ERR_STATE, "set the sampling scheme before the initial values");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  rc = ensure_chain_buffers(h); if (rc) return rc;
+  double* d_in = nullptr;
+  CK(cudaMalloc(&d_in, sizeof(double) * (size_t)n_inits * h->D));
+  CK(cudaMemcpyAsync(d_in, x, sizeof(double) * (size_t)n_inits * h->D, cudaMemcpyHostToDevice, h->stream));
+  launch_init(h->C, h->chain_offset, h->seed, h->D, d_in, n_inits, h->d_elink_state, jitter_sd, h->d_state, h->stream);
+  h->launches++;
+  const size_t C = (size_t)h->C;
+  CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size), h->stream));
+  CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
+  CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_in);
+  CK(cudaGetLastError());
+  h->iter = 0; h->has_inits = true; h->samples_kept = 0;
+  return MCU_OK;
+}
+
+int64_t mcu_kept(int64_t first_iter, int64_t iters, int64_t burnin, int64_t thin) {
+  // number of i in (first_iter, first_iter + iters] with i > burnin and (i - burnin) % thin == 0
+  if (thin < 1) return 0;
+  auto upto = [&](int64_t i) { return i > burnin ? (i - burnin) / thin : 0; };
+  return upto(first_iter + iters) - upto(first_iter);
+}
+
+int mcu_set_rng_mode(mcu_handle h, int mode, const double* u, size_t n_per_chain) {
+  if (!h) return MCU_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  cudaFree(h->d_ext); cudaFree(h->d_ext_pos); h->d_ext = nullptr; h->d_ext_pos = nullptr; h->ext_n = 0;
+  h->rng_mode = MCU_RNG_PHILOX;
+  if (mode == MCU_RNG_PHILOX) return MCU_OK;
+  if (mode != MCU_RNG_EXTERNAL || !u || n_per_chain == 0) return fail(h, MCU_ERR_ARG, "bad RNG mode / stream");
+  CK(cudaMalloc(&h->d_ext, sizeof(double) * (size_t)h->C * n_per_chain));
+  CK(cudaMemcpy(h->d_ext, u, sizeof(double) * (size_t)h->C * n_per_chain, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_ext_pos, sizeof(unsigned long long) * (size_t)h->C));
+  CK(cudaMemset(h->d_ext_pos, 0, sizeof(unsigned long long) * (size_t)h->C));
+  h->ext_n = n_per_chain; h->rng_mode = MCU_RNG_EXTERNAL;
+  return MCU_OK;
+}
+
+int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* out, uint32_t flags) {
+  if (!h) return MCU_ERR_ARG;
+  if (iters < 1) return fail(h, MCU_ERR_ARG, "iters must be positive");
+  if (thin < 1) return fail(h, MCU_ERR_ARG, "thin must be positive");
+  if (h->iter == 0 && iters <= burnin) return fail(h, MCU_ERR_ARG, "burnin is greater than or equal to iters");   // mcmc.jl:22-23
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "initial values must be set before mcu_run");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  const long long kept = mcu_kept(h->iter, iters, burnin, thin);
+  const bool store = out != nullptr || !(flags & MCU_RUN_NO_STORE);
+  const size_t C = (size_t)h->C;
+  if (store && kept > 0) {
+    const size_t need = (size_t)kept * h->P * C;
+    if (need > h->samples_cap) {
+      cudaFree(h->d_samples); h->d_samples = nullptr; h->samples_cap = 0;
+      CK(cudaMalloc(&h->d_samples, sizeof(double) * need));
+      h->samples_cap = need;
+    }
+  }
+  h->samples_kept = store ? kept : 0;
+  RunArgs a;
+  a.n_chains = h->C; a.chain_offset = h->chain_offset; a.seed = h->seed;
+  a.burnin = burnin; a.thin = thin;
+  a.row0 = h->iter > burnin ? (h->iter - burnin) / thin : 0;
+  a.n_blocks = (int)h->h_blocks.size(); a.D = h->D; a.P = h->P; a.blocks = h->d_blocks;
+  a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
+  a.mom = h->d_mom; a.momn = h->d_momn;
+  a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
+  const bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  long long chunk = 256;
+  if (const char* e = std::getenv("MCU_CHUNK_ITERS")) { long long v = std::atoll(e); if (v > 0) chunk = v; }
+  if (fast) chunk = iters;   // the fused kernel keeps everything on chip for the whole call
+  CK(cudaEventRecord(h->ev0, h->stream));
+  long long done = 0;
+  while (done < iters) {
+    const long long n = std::min(chunk, iters - done);
+    a.iter0 = h->iter + done; a.iters = n;
+    if (fast) {
+      rc = seeds_fast_launch(Host<SeedsModel>::data(h), a, h->h_blocks.data(), h->stream);
+      if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
+    } else {
+      MCU_DISPATCH(h, launch_run(Host<M>::data(h), a, h->stream));
+    }
+    h->launches++;
+    done += n;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
+  h->iter += iters;
+  if (out && kept > 0) {
+    double* d_out = nullptr;
+    const size_t total = (size_t)kept * h->P * C;
+    CK(cudaMalloc(&d_out, sizeof(double) * total));
+    launch_samples_to_julia(h->d_samples, d_out, kept, h->P, h->C, h->stream);
+    h->launches++;
+    CK(cudaMemcpyAsync(out, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_out);
+    CK(cudaGetLastError());
+  }
+  return MCU_OK;
+}
+
+int mcu_get_state(mcu_handle h, double* values, double* tune, int64_t* iter) {
+  if (!h) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no chain state yet");
+  CK(cudaSetDevice(h->device));
+  const size_t C = (size_t)h->C;
+  if (values) {
+    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->D));
+    launch_soa_to_records(h->d_state, tmp, h->C, h->D, h->stream); h->launches++;
+    CK(cudaMemcpyAsync(values, tmp, sizeof(double) * C * h->D, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+  }
+  if (tune && h->tune_size > 0) {
+    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->tune_size));
+    launch_soa_to_records(h->d_tune, tmp, h->C, (int)h->tune_size, h->stream); h->launches++;
+    CK(cudaMemcpyAsync(tune, tmp, sizeof(double) * C * h->tune_size, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+  }
+  if (iter) *iter = h->iter;
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+
+int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_t iter) {
+  if (!h || !values) return h ? fail(h, MCU_ERR_ARG, "values is NULL") : MCU_ERR_ARG;
+  if (h->h_blocks.empty()) return fail(h, MCU_ERR_STATE, "set the sampling scheme before the state");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  rc = ensure_chain_buffers(h); if (rc) return rc;
+  const size_t C = (size_t)h->C;
+  {
+    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->D));
+    CK(cudaMemcpyAsync(tmp, values, sizeof(double) * C * h->D, cudaMemcpyHostToDevice, h->stream));
+    launch_records_to_soa(tmp, h->d_state, h->C, h->D, h->stream); h->launches++;
+    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+  }
+  if (tune && h->tune_size > 0) {
+    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->tune_size));
+    CK(cudaMemcpyAsync(tmp, tune, sizeof(double) * C * h->tune_size, cudaMemcpyHostToDevice, h->stream));
+    launch_records_to_soa(tmp, h->d_tune, h->C, (int)h->tune_size, h->stream); h->launches++;
+    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+  }
+  CK(cudaGetLastError());
+  h->iter = iter; h->has_inits = true;
+  return MCU_OK;
+}
+
+static int density_call(mcu_handle h, int block, int grad_mode, int64_t B, const double* state, const double* x, double* lp, double* g) {
+  if (!h || !state || B < 1) return h ? fail(h, MCU_ERR_ARG, "bad argument") : MCU_ERR_ARG;
+  if (block < 0 || block >= (int)h->h_blocks.size()) return fail(h, MCU_ERR_ARG, "block index out of range");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  const int k = h->h_blocks[block].k, D = h->D;
+  double *d_rec = nullptr, *d_state = nullptr, *d_x = nullptr, *d_lp = nullptr, *d_g = nullptr, *d_tmp = nullptr;
+  CK(cudaMalloc(&d_rec, sizeof(double) * B * std::max(D, k)));
+  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
+  CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
+  launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
+  if (x) {
+    CK(cudaMalloc(&d_x, sizeof(double) * B * k));
+    CK(cudaMemcpyAsync(d_rec, x, sizeof(double) * B * k, cudaMemcpyHostToDevice, h->stream));
+    launch_records_to_soa(d_rec, d_x, B, k, h->stream); h->launches++;
+  }
+  CK(cudaMalloc(&d_lp, sizeof(double) * B));
+  if (g) { CK(cudaMalloc(&d_g, sizeof(double) * B * k)); CK(cudaMalloc(&d_tmp, sizeof(double) * B * k)); }
+  MCU_DISPATCH(h, launch_logpdf(Host<M>::data(h), h->d_blocks, block, B, D, d_state, d_x, d_lp, d_g, grad_mode, h->stream));
+  h->launches++;
+  if (lp) CK(cudaMemcpyAsync(lp, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (g) {
+    launch_soa_to_records(d_g, d_tmp, B, k, h->stream); h->launches++;
+    CK(cudaMemcpyAsync(g, d_tmp, sizeof(double) * B * k, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_x); cudaFree(d_lp); cudaFree(d_g); cudaFree(d_tmp);
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+
+int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const double* x, double* lp) {
+  if (!lp) return h ? fail(h, MCU_ERR_ARG, "lp is NULL") : MCU_ERR_ARG;
+  return density_call(h, block, 0, B, state, x, lp, nullptr);
+}
+int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const double* state, const double* x, double* lp, double* g) {
+  if (!g) return h ? fail(h, MCU_ERR_ARG, "g is NULL") : MCU_ERR_ARG;
+  if (grad_mode < 0 || grad_mode > 2) return fail(h, MCU_ERR_ARG, "unknown gradient mode");
+  return density_call(h, block, grad_mode, B, state, x, lp, g);
+}
+
+// ---- diagnostics ----------------------------------------------------------------------------------
+static int reduce_partials(mcu_handle h, double* d_partial, long long nblk, int width, double* host_out) {
+  double* d_out = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * width));
+  launch_fold(d_partial, nblk, width, d_out, h->stream); h->launches++;
+  CK(cudaMemcpyAsync(host_out, d_out, sizeof(double) * width, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_out);
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+
+int mcu_minmax(mcu_handle h, double* minmax) {
+  if (!h || !minmax) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  const long long nblk = grid_for(h->C, 128);
+  double* d_partial = nullptr;
+  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * h->P * 2));
+  launch_minmax_partial(h->d_mom, h->C, h->P, d_partial, h->stream); h->launches++;
+  std::vector<double> part((size_t)nblk * h->P * 2);
+  CK(cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_partial);
+  CK(cudaGetLastError());
+  for (int j = 0; j < h->P; ++j) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (long long b = 0; b < nblk; ++b) { mn = std::fmin(mn, part[((size_t)b * h->P + j) * 2]); mx = std::fmax(mx, part[((size_t)b * h->P + j) * 2 + 1]); }
+    minmax[j * 2] = mn; minmax[j * 2 + 1] = mx;
+  }
+  return MCU_OK;
+}
+
+int mcu_link_codes(mcu_handle h, int transform, const double* minmax, int* codes) {
+  if (!h || !codes) return MCU_ERR_ARG;
+  TplInfo t = tpl_info(h);
+  std::vector<double> mm;
+  for (int j = 0; j < h->P; ++j) {
+    int c = 0;
+    if (transform) {
+      if (t.monlink[j] == LINK_LOG) c = 1;
+      else if (t.monlink[j] == LINK_HEUR) {
+        if (!minmax && mm.empty()) { mm.resize((size_t)h->P * 2); int rc = mcu_minmax(h, mm.data()); if (rc) return rc; }
+        const double* q = minmax ? minmax : mm.data();
+        if (q[j * 2] > 0.0) {
+          if (q[j * 2 + 1] < 1.0) return fail(h, MCU_ERR_UNSUPPORTED, "logit link for a Logical column needs stored samples");
+          c = 1;
+        }
+      }
+    }
+    codes[j] = c;
+  }
+  return MCU_OK;
+}
+
+int mcu_moments(mcu_handle h, const int* codes, const double* center, double* sums, int64_t* n_kept) {
+  if (!h || !sums) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  const int P = h->P;
+  const long long nblk = grid_for(h->C, 128);
+  int* d_codes = nullptr; double* d_center = nullptr; double* d_partial = nullptr;
+  std::vector<int> zc(P, 0);
+  CK(cudaMalloc(&d_codes, sizeof(int) * P));
+  CK(cudaMemcpy(d_codes, codes ? codes : zc.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  if (center) { CK(cudaMalloc(&d_center, sizeof(double) * P * 2)); CK(cudaMemcpy(d_center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice)); }
+  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * P * 7));
+  launch_gelman_partial(h->d_mom, h->d_momn, h->C, P, d_codes, d_center, d_partial, h->stream); h->launches++;
+  int rc = reduce_partials(h, d_partial, nblk, P * 7, sums);
+  cudaFree(d_codes); cudaFree(d_center); cudaFree(d_partial);
+  if (rc) return rc;
+  if (n_kept) { double n0 = 0; CK(cudaMemcpy(&n0, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost)); *n_kept = (int64_t)n0; }
+  return MCU_OK;
+}
+
+int mcu_gelman_from_moments(int64_t n_kept, int p, const double* center, const double* sums, double alpha, double* psrf) {
+  if (!sums || !psrf || p < 1) return MCU_ERR_ARG;
+  for (int j = 0; j < p; ++j) {
+    if (sums[j * 7] < 2.0) return MCU_ERR_ARG;   // "less than 2 chains supplied to gelman diagnostic": gelmandiag.jl:6-7
+    hostdiag::gelman_column((double)n_kept, center ? center[j * 2] : 0.0, center ? center[j * 2 + 1] : 0.0, sums + j * 7, alpha, psrf + j * 2);
+  }
+  return MCU_OK;
+}
+
+int mcu_gelman(mcu_handle h, double alpha, int transform, double* psrf) {
+  if (!h || !psrf) return MCU_ERR_ARG;
+  const int P = h->P;
+  if (h->C < 2) return fail(h, MCU_ERR_ARG, "less than 2 chains supplied to gelman diagnostic");
+  std::vector<int> codes(P); std::vector<double> s0((size_t)P * 7), s1((size_t)P * 7), center((size_t)P * 2);
+  int rc = mcu_link_codes(h, transform, nullptr, codes.data()); if (rc) return rc;
+  int64_t n = 0;
+  rc = mcu_moments(h, codes.data(), nullptr, s0.data(), &n); if (rc) return rc;
+  for (int j = 0; j < P; ++j) { center[j * 2] = s0[j * 7 + 1] / s0[j * 7]; center[j * 2 + 1] = s0[j * 7 + 3] / s0[j * 7]; }
+  rc = mcu_moments(h, codes.data(), center.data(), s1.data(), &n); if (rc) return rc;
+  if (n < 2) return fail(h, MCU_ERR_STATE, "fewer than 2 kept samples per chain");
+  return mcu_gelman_from_moments(n, P, center.data(), s1.data(), alpha, psrf);
+}
+
+int mcu_summary_sums(mcu_handle h, const double* center, double* sums) {
+  if (!h || !sums) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  const int P = h->P;
+  const long long nblk = grid_for(h->C, 128);
+  double* d_center = nullptr; double* d_partial = nullptr;
+  if (center) { CK(cudaMalloc(&d_center, sizeof(double) * P * 2)); CK(cudaMemcpy(d_center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice)); }
+  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * P * 8));
+  launch_summary_partial(h->d_mom, h->d_momn, h->C, P, d_center, d_partial, h->stream); h->launches++;
+  int rc = reduce_partials(h, d_partial, nblk, P * 8, sums);
+  cudaFree(d_center); cudaFree(d_partial);
+  return rc;
+}
+
+int mcu_summary_from_sums(int64_t n_kept, int p, const double* center, const double* sums, double* out) {
+  if (!sums || !out || !center) return MCU_ERR_ARG;
+  for (int j = 0; j < p; ++j) hostdiag::summary_column((double)n_kept, center[j * 2], center[j * 2 + 1], sums + j * 8, out + j * 5);
+  return MCU_OK;
+}
+
+int mcu_summary_streaming(mcu_handle h, double* out) {
+  if (!h || !out) return MCU_ERR_ARG;
+  const int P = h->P;
+  std::vector<double> s0((size_t)P * 8), s1((size_t)P * 8), center((size_t)P * 2);
+  int rc = mcu_summary_sums(h, nullptr, s0.data()); if (rc) return rc;
+  for (int j = 0; j < P; ++j) { center[j * 2] = s0[j * 8 + 1] / s0[j * 8]; center[j * 2 + 1] = s0[j * 8 + 4] > 0 ? s0[j * 8 + 5] / s0[j * 8 + 4] : 0.0; }
+  rc = mcu_summary_sums(h, center.data(), s1.data()); if (rc) return rc;
+  double n0 = 0; CK(cudaMemcpy(&n0, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost));
+  return mcu_summary_from_sums((int64_t)n0, P, center.data(), s1.data(), out);
+}
+
+int mcu_summarystats(mcu_handle h, int etype, int batch_size, double* out) {
+  if (!h || !out) return MCU_ERR_ARG;
+  if (h->samples_kept < 1 || !h->d_samples) return fail(h, MCU_ERR_STATE, "no stored samples (run without MCU_RUN_NO_STORE)");
+  if (etype != MCU_ETYPE_BM && etype != MCU_ETYPE_IMSE) return fail(h, MCU_ERR_ARG, "unsupported mcse method");   // mcse.jl:3-8
+  CK(cudaSetDevice(h->device));
+  const size_t total = (size_t)h->samples_kept * h->P * (size_t)h->C;
+  std::vector<double> smp(total);
+  CK(cudaMemcpy(smp.data(), h->d_samples, sizeof(double) * total, cudaMemcpyDeviceToHost));
+  if (batch_size < 1) batch_size = 100;
+  const int rc = hostdiag::summarystats_soa(smp.data(), h->samples_kept, h->P, h->C, etype, batch_size, out);
+  if (rc) return fail(h, MCU_ERR_ARG, "iterations are < 2 * batch size");   // mcse.jl:13-16
+  return MCU_OK;
+}
+
+int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
+double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// engine.cuh — the generic one-chain-per-thread engine kernels, templated on a model template.
+//
+// Replaces the reference's per-chain interpreter loop mcmc_worker! → sample!(m) → sampler.eval
+// (src/model/mcmc.jl:62-83, src/model/simulation.jl:93-107) by kernels that advance all chains of a
+// handle in lockstep.  Memory layout in HBM (structure of arrays, chain fastest ⇒ every warp-wide
+// access is one coalesced 256-byte request):
+//   state   [D][C]        constrained values of the unobserved stochastic elements
+//   tune    [T][C]        sampler tune slots of every block (layout in samplers.cuh)
+//   samples [kept][P][C]  thinned monitored values (Chains storage, src/output/chains.jl:5-32)
+//   mom     [P*9][C]      streaming per-chain moments for gelmandiag / ESS
+//   momn    [3][C]        kept count, in-batch count, number of complete batches
+#pragma once
+#include "samplers.cuh"
+
+namespace mcu {
+
+constexpr int kMomPerCol = 9;   // mean, M2, lmean, lM2, min, max, bsum, bmean, bM2
+constexpr int kBatch = 100;     // mcse_bm default batch size (src/output/mcse.jl:10)
+
+// logpdf!(block, x) / logpdfgrad!(block, x) for one chain: relist x into the state record
+// (invlink when the block samples on the transformed scale), then sum the block's own prior
+// factors that are not targets followed by the target factors in topological order, stopping at
+// the first non-finite partial sum (src/model/simulation.jl:60-67,77-90).
+template <class M>
+struct BlockTarget {
+  const typename M::Data& d;
+  double* s;
+  const DevBlock& b;
+
+  MCU_D void relist(const double* x) const {
+    for (int i = 0; i < b.k; ++i) s[b.elem[i]] = (b.transform && b.elink[i] == LINK_LOG) ? exp(x[i]) : x[i];
+  }
+  MCU_D void unlist(double* x) const {
+    for (int i = 0; i < b.k; ++i) { const double v = s[b.elem[i]]; x[i] = (b.transform && b.elink[i] == LINK_LOG) ? log(v) : v; }
+  }
+  MCU_NOINL double eval() const {
+    double lp = 0.0;
+    const bool tr = b.transform != 0;
+    for (int o = 0; o < b.n_own; ++o) {
+      const int f = b.own[o];
+      if (M::parents(f) & b.mask) continue;        // it is a target: handled below
+      lp += M::factor(d, s, f, tr);
+      if (!isfinite(lp)) return lp;
+    }
+    for (int f = 0; f < M::NF; ++f) {
+      if (!(M::parents(f) & b.mask)) continue;
+      if (!isfinite(lp)) break;
+      const bool own = f < M::NN && ((b.mask >> f) & 1u);
+      lp += M::factor(d, s, f, tr && own);
+    }
+    return lp;
+  }
+  MCU_D double logf(const double* x) const { relist(x); return eval(); }
+  MCU_NOINL void grad_analytic(const double* x, double* g) const {
+    relist(x);
+    double gj[M::D];
+    M::joint_grad(d, s, gj);
+    for (int i = 0; i < b.k; ++i) {
+      const int e = b.elem[i];
+      g[i] = (b.transform && b.elink[i] == LINK_LOG) ? gj[e] * s[e] + 1.0 : gj[e];
+    }
+  }
+  // Calculus.gradient(f, x, :forward / :central): src/model/simulation.jl:47-51
+  MCU_NOINL void grad_fd(const double* x0, double* g, int mode) const {
+    double x[M::D];
+    for (int i = 0; i < b.k; ++i) x[i] = x0[i];
+    const double EPS = 2.220446049250313e-16;
+    if (mode == 1) {
+      const double f0 = logf(x);
+      for (int i = 0; i < b.k; ++i) {
+        const double h = sqrt(EPS) * fmax(1.0, fabs(x[i]));
+        const double old = x[i]; x[i] = old + h;
+        g[i] = (logf(x) - f0) / h; x[i] = old;
+      }
+    } else {
+      for (int i = 0; i < b.k; ++i) {
+        const double h = cbrt(EPS) * fmax(1.0, fabs(x[i]));
+        const double old = x[i];
+        x[i] = old + h; const double f1 = logf(x);
+        x[i] = old - h; const double f2 = logf(x);
+        g[i] = (f1 - f2) / (2.0 * h); x[i] = old;
+      }
+    }
+  }
+  MCU_NOINL double logfgrad_mode(const double* x, double* g, int mode) const {   // sampler.jl:106-111
+    if (mode == 0) grad_analytic(x, g); else grad_fd(x, g, mode);
+    const double lf = logf(x);
+    for (int i = 0; i < b.k; ++i) if (!isfinite(g[i])) g[i] = 0.0;
+    return lf;
+  }
+  MCU_D double logfgrad(const double* x, double* g) const { return logfgrad_mode(x, g, b.grad); }
+};
+
+struct RunArgs {
+  long long n_chains, chain_offset;
+  unsigned long long seed;
+  long long iter0, iters, burnin, thin;   // this launch advances iterations iter0+1 .. iter0+iters
+  long long row0;                         // kept rows that precede this mcu_run call (global row - row0 = row in `samples`)
+  int n_blocks, D, P;
+  const DevBlock* blocks;
+  double* state; double* tune; double* samples; double* mom; double* momn;
+  const double* ext_u; unsigned long long ext_n; unsigned long long* ext_pos;
+};
+
+static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon) {
+  const double n = momn[0 * C + c] + 1.0; momn[0 * C + c] = n;
+  double bc = momn[1 * C + c] + 1.0;
+  const bool bdone = bc >= (double)kBatch;
+  double nb = momn[2 * C + c];
+  if (bdone) { bc = 0.0; nb += 1.0; momn[2 * C + c] = nb; }
+  momn[1 * C + c] = bc;
+  for (int j = 0; j < P; ++j) {
+    double* q = mom + (size_t)j * kMomPerCol * C + c;
+    const double x = mon[j];
+    double mean = q[0 * C], M2 = q[1 * C];
+    double dl = x - mean; mean += dl / n; M2 += dl * (x - mean);
+    q[0 * C] = mean; q[1 * C] = M2;
+    const double lx = log(x);
+    double lmean = q[2 * C], lM2 = q[3 * C];
+    dl = lx - lmean; lmean += dl / n; lM2 += dl * (lx - lmean);
+    q[2 * C] = lmean; q[3 * C] = lM2;
+    q[4 * C] = n == 1.0 ? x : fmin(q[4 * C], x);
+    q[5 * C] = n == 1.0 ? x : fmax(q[5 * C], x);
+    double bsum = q[6 * C] + x;
+    if (bdone) {
+      const double bm = bsum / (double)kBatch; bsum = 0.0;
+      double bmean = q[7 * C], bM2 = q[8 * C];
+      const double db = bm - bmean; bmean += db / nb; bM2 += db * (bm - bmean);
+      q[7 * C] = bmean; q[8 * C] = bM2;
+    }
+    q[6 * C] = bsum;
+  }
+}
+
+template <class M>
+__global__ void __launch_bounds__(128) run_generic_kernel(typename M::Data data, RunArgs a) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.n_chains) return;
+  const size_t C = (size_t)a.n_chains;
+  double s[M::D];
+  for (int e = 0; e < a.D; ++e) s[e] = a.state[(size_t)e * C + c];
+  Draws rng;
+  rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32);
+  rng.chain = (uint32_t)(a.chain_offset + c);
+  rng.ext = a.ext_u ? a.ext_u + (size_t)c * a.ext_n : nullptr;
+  rng.ext_n = a.ext_n; rng.ext_pos = a.ext_pos ? a.ext_pos + c : nullptr;
+  double v[M::D];
+  double mon[M::P];
+  for (long long it = 1; it <= a.iters; ++it) {
+    const long long iter = a.iter0 + it;                       // m.iter += 1: simulation.jl:94
+    for (int bi = 0; bi < a.n_blocks; ++bi) {
+      const DevBlock& b = a.blocks[bi];
+      BlockTarget<M> tgt{data, s, b};
+      TuneRef tn{a.tune + (size_t)b.tune_off * C + c, C};
+      rng.seek((uint32_t)iter, (uint32_t)bi, 0);
+      tgt.unlist(v);                                           // unlist(block): sampler.jl:113-115
+      const bool fresh = iter == 1;                            // sampler.jl:40-45
+      const bool isadapt = b.adapt == 1 ? iter <= a.burnin : b.adapt == 0;
+      switch (b.kind) {
+        case 0: amwg_sample<M::D>(v, b, tn, tgt, rng, fresh, isadapt); break;
+        case 1: slice_uni_sample<M::D>(v, b, tgt, rng); break;
+        case 2: slice_multi_sample<M::D>(v, b, tgt, rng); break;
+        case 3: rwm_sample<M::D>(v, b, tgt, rng); break;
+        case 4: nuts_sample<M::D>(v, b, tn, tgt, rng, fresh, iter <= a.burnin); break;
+        case 5: hmc_sample<M::D>(v, b, tgt, rng); break;
+        case 6: amm_sample<M::D>(v, b, tn, tgt, rng, fresh, isadapt); break;
+      }
+      tgt.relist(v);                                           // m[sampler.params] = relist(block, v)
+    }
+    if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {  // mcmc.jl:76-78
+      M::monitor(data, s, mon);
+      if (a.samples) {
+        const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;   // iters2inds: src/output/chains.jl:66-87
+        for (int j = 0; j < a.P; ++j) a.samples[((size_t)row * a.P + j) * C + c] = mon[j];
+      }
+      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon);
+    }
+  }
+  for (int e = 0; e < a.D; ++e) a.state[(size_t)e * C + c] = s[e];
+}
+
+// Batched density entry points (mcu_logpdf / mcu_gradlogpdf): one evaluation per thread.
+// state [D][B] chain-fastest; x [k][B] or nullptr (use unlist of state); lp [B]; g [k][B] or nullptr.
+template <class M>
+__global__ void logpdf_kernel(typename M::Data data, const DevBlock* blocks, int block, long long B, int D,
+                              const double* state, const double* x, double* lp, double* g, int grad_mode) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B) return;
+  const DevBlock& b = blocks[block];
+  double s[M::D], v[M::D], gg[M::D];
+  for (int e = 0; e < D; ++e) s[e] = state[(size_t)e * B + c];
+  BlockTarget<M> tgt{data, s, b};
+  if (x) for (int i = 0; i < b.k; ++i) v[i] = x[(size_t)i * B + c]; else tgt.unlist(v);
+  if (g) {
+    const double l = tgt.logfgrad_mode(v, gg, grad_mode);
+    if (lp) lp[c] = l;
+    for (int i = 0; i < b.k; ++i) g[(size_t)i * B + c] = gg[i];
+  } else {
+    lp[c] = tgt.logf(v);
+  }
+}
+
+}  // namespace mcu

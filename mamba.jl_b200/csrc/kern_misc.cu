@@ -1,0 +1,155 @@
+// kern_misc.cu — initialisation, layout transposes and the cross-chain reduction kernels.
+#include "launch.hpp"
+
+namespace mcu {
+
+// setinits! for all chains: state[e][c] = inits[(g % n_inits)][e] (+ jitter on the link scale).
+__global__ void init_kernel(long long n_chains, long long chain_offset, unsigned long long seed, int D,
+                            const double* inits, long long n_inits, const int* elink, double jitter_sd, double* state) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  const long long gidx = chain_offset + c;
+  const double* rec = inits + (size_t)(gidx % n_inits) * D;
+  Draws rng;
+  rng.k0 = (uint32_t)seed; rng.k1 = (uint32_t)(seed >> 32); rng.chain = (uint32_t)gidx; rng.ext = nullptr; rng.ext_pos = nullptr; rng.ext_n = 0;
+  rng.seek(0, 0, 1);
+  for (int e = 0; e < D; ++e) {
+    double v = rec[e];
+    if (jitter_sd > 0.0) {
+      const double z = jitter_sd * rng.normal();
+      v = elink[e] == LINK_LOG ? exp(log(v) + z) : v + z;
+    }
+    state[(size_t)e * n_chains + c] = v;
+  }
+}
+
+// [rows][C] (chain fastest) → out[c][rows] record-contiguous, and the reverse.
+__global__ void soa_to_records(const double* soa, double* rec, long long C, int rows) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int e = 0; e < rows; ++e) rec[(size_t)c * rows + e] = soa[(size_t)e * C + c];
+}
+__global__ void records_to_soa(const double* rec, double* soa, long long C, int rows) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int e = 0; e < rows; ++e) soa[(size_t)e * C + c] = rec[(size_t)c * rows + e];
+}
+// samples [kept][P][C] → Julia column-major [kept × P × C]
+__global__ void samples_to_julia(const double* smp, double* out, long long kept, int P, long long C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over kept*P*C, chain fastest on the read side
+  const long long total = kept * P * C;
+  if (idx >= total) return;
+  const long long c = idx % C; const long long r = idx / C; const long long j = r % P; const long long i = r / P;
+  out[i + kept * (j + (long long)P * c)] = smp[idx];
+}
+
+// ---- cross-chain reductions ---------------------------------------------------------------------
+// Gelman moments (src/output/gelmandiag.jl:12-29): per column j and chain c let psibar = chain mean and
+// s2 = chain variance (on the raw or link scale); with centres (c1, c2):
+//   d = psibar - c1, e = s2 - c2;  sums = { 1, d, d^2, e, e^2, e d, e d^2 } summed over chains.
+// Deterministic two-stage reduction: per-block partials, then one block folds them.
+__global__ void gelman_partial_kernel(const double* mom, const double* momn, long long C, int P, const int* use_log,
+                                      const double* center, double* partial /*[gridDim.x][P][7]*/) {
+  __shared__ double sh[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = 0; j < P; ++j) {
+    double vals[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+      const double n = momn[c];
+      const double* q = mom + (size_t)j * kMomPerCol * C + c;
+      const double psibar = use_log[j] ? q[2 * C] : q[0 * C];
+      const double s2 = (use_log[j] ? q[3 * C] : q[1 * C]) / (n - 1.0);
+      const double d = psibar - (center ? center[j * 2 + 0] : 0.0);
+      const double e = s2 - (center ? center[j * 2 + 1] : 0.0);
+      vals[0] = 1.0; vals[1] = d; vals[2] = d * d; vals[3] = e; vals[4] = e * e; vals[5] = e * d; vals[6] = e * d * d;
+    }
+    for (int q7 = 0; q7 < 7; ++q7) {
+      sh[threadIdx.x] = vals[q7];
+      __syncthreads();
+      for (int off = 64; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+      if (threadIdx.x == 0) partial[((size_t)blockIdx.x * P + j) * 7 + q7] = sh[0];
+      __syncthreads();
+    }
+  }
+}
+// generic fold of per-block partial vectors: out[i] = sum_b partial[b][i]
+__global__ void fold_kernel(const double* partial, long long nblocks, int width, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  double s = 0.0;
+  for (long long b = 0; b < nblocks; ++b) s += partial[(size_t)b * width + i];
+  out[i] = s;
+}
+// min/max of each monitored column over all chains (for the link(c) heuristic, chains.jl:237-246)
+__global__ void minmax_partial_kernel(const double* mom, long long C, int P, double* partial /*[grid][P][2]*/) {
+  __shared__ double shmin[128], shmax[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = 0; j < P; ++j) {
+    const double* q = mom + (size_t)j * kMomPerCol * C + c;
+    shmin[threadIdx.x] = c < C ? q[4 * C] : CUDART_INF;
+    shmax[threadIdx.x] = c < C ? q[5 * C] : -CUDART_INF;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) { shmin[threadIdx.x] = fmin(shmin[threadIdx.x], shmin[threadIdx.x + off]); shmax[threadIdx.x] = fmax(shmax[threadIdx.x], shmax[threadIdx.x + off]); }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[((size_t)blockIdx.x * P + j) * 2 + 0] = shmin[0]; partial[((size_t)blockIdx.x * P + j) * 2 + 1] = shmax[0]; }
+    __syncthreads();
+  }
+}
+// streaming summary sums per column: { C, sum mean_c, sum M2_c, sum (mean_c - ctr)^2, nb_total, sum bmean_c*nb, sum bM2_c, sum nb (bmean_c - bctr)^2 }
+__global__ void summary_partial_kernel(const double* mom, const double* momn, long long C, int P, const double* center /*[P][2] or null*/,
+                                       double* partial /*[grid][P][8]*/) {
+  __shared__ double sh[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = 0; j < P; ++j) {
+    double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+      const double* q = mom + (size_t)j * kMomPerCol * C + c;
+      const double nb = momn[2 * C + c];
+      const double c1 = center ? center[j * 2 + 0] : 0.0, c2 = center ? center[j * 2 + 1] : 0.0;
+      vals[0] = 1.0; vals[1] = q[0 * C]; vals[2] = q[1 * C]; vals[3] = (q[0 * C] - c1) * (q[0 * C] - c1);
+      vals[4] = nb; vals[5] = nb * q[7 * C]; vals[6] = q[8 * C]; vals[7] = nb * (q[7 * C] - c2) * (q[7 * C] - c2);
+    }
+    for (int q8 = 0; q8 < 8; ++q8) {
+      sh[threadIdx.x] = vals[q8];
+      __syncthreads();
+      for (int off = 64; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+      if (threadIdx.x == 0) partial[((size_t)blockIdx.x * P + j) * 8 + q8] = sh[0];
+      __syncthreads();
+    }
+  }
+}
+
+
+static inline unsigned gridf(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+void launch_init(long long n_chains, long long chain_offset, unsigned long long seed, int D, const double* inits,
+                 long long n_inits, const int* elink, double jitter_sd, double* state, cudaStream_t st) {
+  init_kernel<<<gridf(n_chains, 256), 256, 0, st>>>(n_chains, chain_offset, seed, D, inits, n_inits, elink, jitter_sd, state);
+}
+void launch_soa_to_records(const double* soa, double* rec, long long C, int rows, cudaStream_t st) {
+  soa_to_records<<<gridf(C, 256), 256, 0, st>>>(soa, rec, C, rows);
+}
+void launch_records_to_soa(const double* rec, double* soa, long long C, int rows, cudaStream_t st) {
+  records_to_soa<<<gridf(C, 256), 256, 0, st>>>(rec, soa, C, rows);
+}
+void launch_samples_to_julia(const double* smp, double* out, long long kept, int P, long long C, cudaStream_t st) {
+  samples_to_julia<<<gridf(kept * P * C, 256), 256, 0, st>>>(smp, out, kept, P, C);
+}
+void launch_gelman_partial(const double* mom, const double* momn, long long C, int P, const int* use_log,
+                           const double* center, double* partial, cudaStream_t st) {
+  gelman_partial_kernel<<<gridf(C, 128), 128, 0, st>>>(mom, momn, C, P, use_log, center, partial);
+}
+void launch_fold(const double* partial, long long nblocks, int width, double* out, cudaStream_t st) {
+  fold_kernel<<<gridf(width, 128), 128, 0, st>>>(partial, nblocks, width, out);
+}
+void launch_minmax_partial(const double* mom, long long C, int P, double* partial, cudaStream_t st) {
+  minmax_partial_kernel<<<gridf(C, 128), 128, 0, st>>>(mom, C, P, partial);
+}
+void launch_summary_partial(const double* mom, const double* momn, long long C, int P, const double* center,
+                            double* partial, cudaStream_t st) {
+  summary_partial_kernel<<<gridf(C, 128), 128, 0, st>>>(mom, momn, C, P, center, partial);
+}
+
+}  // namespace mcu

@@ -1,0 +1,46 @@
+// launch.hpp — host-callable launch wrappers; each model template's kernels live in their own
+// translation unit (tpl_*.cu) so the library builds in parallel.
+#pragma once
+#include "engine.cuh"
+
+namespace mcu {
+
+constexpr int kGlmDMax = 128;
+typedef GlmModel<kGlmDMax> GlmM;
+
+#define MCU_DECLARE_TPL(M)                                                                                   \
+  void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st);                                      \
+  void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
+                     const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st);
+MCU_DECLARE_TPL(LineModel)
+MCU_DECLARE_TPL(SeedsModel)
+MCU_DECLARE_TPL(RatsModel)
+MCU_DECLARE_TPL(PumpsModel)
+MCU_DECLARE_TPL(GlmM)
+
+#define MCU_DEFINE_TPL(M)                                                                                    \
+  void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st) {                                     \
+    run_generic_kernel<M><<<(unsigned)((a.n_chains + 127) / 128), 128, 0, st>>>(d, a);                       \
+  }                                                                                                          \
+  void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
+                     const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st) { \
+    logpdf_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d, blocks, block, B, D, state, x, lp, g, grad_mode); \
+  }
+
+// misc kernels (kern_misc.cu)
+void launch_init(long long n_chains, long long chain_offset, unsigned long long seed, int D, const double* inits,
+                 long long n_inits, const int* elink, double jitter_sd, double* state, cudaStream_t st);
+void launch_soa_to_records(const double* soa, double* rec, long long C, int rows, cudaStream_t st);
+void launch_records_to_soa(const double* rec, double* soa, long long C, int rows, cudaStream_t st);
+void launch_samples_to_julia(const double* smp, double* out, long long kept, int P, long long C, cudaStream_t st);
+void launch_gelman_partial(const double* mom, const double* momn, long long C, int P, const int* use_log,
+                           const double* center, double* partial, cudaStream_t st);
+void launch_fold(const double* partial, long long nblocks, int width, double* out, cudaStream_t st);
+void launch_minmax_partial(const double* mom, long long C, int P, double* partial, cudaStream_t st);
+void launch_summary_partial(const double* mom, const double* momn, long long C, int P, const double* center,
+                            double* partial, cudaStream_t st);
+
+// fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success
+int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
+
+}  // namespace mcu

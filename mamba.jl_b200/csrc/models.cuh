@@ -1,0 +1,331 @@
+// models.cuh — the fixed library of model templates, compiled to device functions.
+//
+// The reference interprets its density: every logpdf! re-runs node closures that allocate
+// Distribution objects (src/model/dependent.jl:176-179, src/model/simulation.jl:77-90).  Here each
+// template is a struct of static device functions over a flat state record `s[D]` holding the
+// unobserved stochastic elements on the CONSTRAINED scale:
+//
+//   factor(f)      log density of stochastic node f given its parents (logpdf_sub semantics:
+//                  -Inf outside the support, src/distributions/distributionstruct.jl:138-158; plus the
+//                  log-Jacobian of the node's link when `transform`,
+//                  src/distributions/transformdistribution.jl:66-78)
+//   parents(f)     bitmask of the parameter nodes factor f depends on through Logical nodes — the
+//                  transpose of the reference's `targets` (src/model/model.jl:17-25,
+//                  src/model/graph.jl:93-103)
+//   joint_grad     analytic gradient of the sum of all factors w.r.t. every state element
+//                  (replaces Calculus.gradient finite differences, src/model/simulation.jl:47-51)
+//   monitor        unlist(m, true): the monitored columns (src/model/simulation.jl:114-121)
+//
+// Factors 0..NN-1 are the parameter nodes' own densities (factor f belongs to node f); factors
+// NN.. are observed (data) nodes.  Factor order is topological and fixes summation order.
+// Templates: line (doc/tutorial/line.jl:5-25), seeds (doc/examples/seeds.jl:16-56),
+// rats (doc/examples/rats.jl:49-97), pumps (doc/examples/pumps.jl:12-39), glm (synthetic).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace mcu {
+
+#define MCU_HD __host__ __device__ __forceinline__
+#define MCU_D __device__ __forceinline__
+#define MCU_NOINL __device__ __noinline__
+
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+constexpr int LINK_IDENT = 0, LINK_LOG = 1, LINK_HEUR = -1;
+
+MCU_D double neg_inf() { return -CUDART_INF; }
+
+// ---- univariate log densities (Distributions.jl formulas) -------------------
+MCU_D double lp_normal(double x, double mu, double sigma) {
+  if (isnan(x)) return neg_inf();
+  const double z = (x - mu) / sigma;
+  return -(z * z + kLog2Pi) / 2.0 - log(sigma);
+}
+// InverseGamma(shape a, scale th), with lgamma(a) and a*log(th) folded into c0 = a*log(th) - lgamma(a)
+MCU_D double lp_invgamma(double x, double a, double th, double c0, bool transform) {
+  if (!(x >= 0.0)) return neg_inf();
+  const double lx = log(x);
+  double lp = c0 - (a + 1.0) * lx - th / x;
+  if (transform) lp += lx;
+  return lp;
+}
+MCU_D double lp_gamma(double x, double a, double th, bool transform) {   // Gamma(shape a, scale th)
+  if (!(x >= 0.0)) return neg_inf();
+  const double lx = log(x);
+  double lp = -lgamma(a) - a * log(th) + (a - 1.0) * lx - x / th;
+  if (transform) lp += lx;
+  return lp;
+}
+MCU_D double lp_exponential(double x, double th, bool transform) {       // Exponential(scale th)
+  if (!(x >= 0.0)) return neg_inf();
+  const double lambda = 1.0 / th;
+  double lp = log(lambda) - lambda * x;
+  if (transform) lp += log(x);
+  return lp;
+}
+// Binomial(n, p = invlogit(eta)) at integer r, lc = lchoose(n, r) precomputed on the host
+MCU_D double lp_binomial_logit(double r, double n, double lc, double eta) {
+  const double p = 1.0 / (exp(-eta) + 1.0);      // invlogit: src/utils.jl:64
+  const double q = 1.0 - p;
+  if (p == 0.0) return r == 0.0 ? 0.0 : neg_inf();
+  if (q == 0.0) return r == n ? 0.0 : neg_inf();
+  double lp = lc;
+  if (r > 0.0) lp += r * log(p);
+  if (n - r > 0.0) lp += (n - r) * log(q);
+  return lp;
+}
+MCU_D double lp_poisson(double y, double lgy1 /* lgamma(y+1) */, double lam) {
+  if (lam == 0.0) return y == 0.0 ? 0.0 : neg_inf();
+  return y * log(lam) - lam - lgy1;
+}
+MCU_D double lp_bernoulli_logit(double y, double eta) {
+  const double p = 1.0 / (exp(-eta) + 1.0);
+  return y == 0.0 ? log(1.0 - p) : log(p);
+}
+// MvNormal(mu, sigma) isotropic: -(d log 2pi + d log sigma^2)/2 - (|x-mu|^2 / sigma^2)/2
+MCU_D double lp_isonormal(double sq, double d, double sigma) {
+  const double v = sigma * sigma;
+  return -(d * kLog2Pi + d * log(v)) / 2.0 - (sq / v) / 2.0;
+}
+MCU_D double d_invgamma(double x, double a, double th) { return -(a + 1.0) / x + th / (x * x); }
+
+MCU_D double digamma_d(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 +
+                   f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+
+// c0 of InverseGamma(0.001, 0.001): 0.001*log(0.001) - lgamma(0.001)
+MCU_D double ig001_c0() { return 0.001 * log(0.001) - lgamma(0.001); }
+
+// =============================================================================== line
+struct LineModel {
+  static constexpr int D = 3, NN = 2, NF = 3, P = 3, MAXN = 64;
+  struct Data { const double* x; const double* y; int N; };
+  MCU_HD static int node_off(int n) { return n == 0 ? 0 : 2; }
+  MCU_HD static int node_len(int n) { return n == 0 ? 2 : 1; }
+  MCU_HD static int node_link(int n) { return n == 1 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 2 ? 0x3u : 0u; }
+  MCU_HD static int mon_link(int j) { return j == 2 ? LINK_LOG : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"beta", "s2"}; return nm[n]; }
+  static const char* state_names() { return "beta[1]\nbeta[2]\ns2"; }
+  static const char* monitor_names() { return "beta[1]\nbeta[2]\ns2"; }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    switch (f) {
+      case 0: {  // beta ~ MvNormal(2, sqrt(1000))
+        if (!isfinite(s[0]) || !isfinite(s[1])) return neg_inf();
+        return lp_isonormal(s[0] * s[0] + s[1] * s[1], 2.0, sqrt(1000.0));
+      }
+      case 1: return lp_invgamma(s[2], 0.001, 0.001, ig001_c0(), transform);
+      default: {  // y ~ MvNormal(xmat * beta, sqrt(s2))
+        double sq = 0.0;
+        for (int i = 0; i < d.N; ++i) { const double mu = 1.0 * s[0] + d.x[i] * s[1]; const double e = d.y[i] - mu; sq += e * e; }
+        return lp_isonormal(sq, (double)d.N, sqrt(s[2]));
+      }
+    }
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    double sr = 0, sxr = 0, srr = 0;
+    for (int i = 0; i < d.N; ++i) { const double r = d.y[i] - s[0] - s[1] * d.x[i]; sr += r; sxr += d.x[i] * r; srr += r * r; }
+    g[0] = sr / s[2] - s[0] / 1000.0;
+    g[1] = sxr / s[2] - s[1] / 1000.0;
+    g[2] = -0.5 * (double)d.N / s[2] + 0.5 * srr / (s[2] * s[2]) + d_invgamma(s[2], 0.001, 0.001);
+  }
+  MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
+};
+
+// =============================================================================== seeds
+struct SeedsModel {
+  static constexpr int D = 26, NN = 6, NF = 7, P = 5, NP = 21;
+  struct Data { const double* r; const double* n; const double* x1; const double* x2; const double* lc; int N; };
+  MCU_HD static int node_off(int n) { return n <= 4 ? n : 5; }
+  MCU_HD static int node_len(int n) { return n == 5 ? NP : 1; }
+  MCU_HD static int node_link(int n) { return n == 4 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 5 ? 0x10u : f == 6 ? 0x2Fu : 0u; }
+  MCU_HD static int mon_link(int j) { return j == 4 ? LINK_LOG : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"alpha0", "alpha1", "alpha2", "alpha12", "s2", "b"}; return nm[n]; }
+  static const char* state_names() {
+    return "alpha0\nalpha1\nalpha2\nalpha12\ns2\nb[1]\nb[2]\nb[3]\nb[4]\nb[5]\nb[6]\nb[7]\nb[8]\nb[9]\nb[10]\nb[11]\nb[12]\nb[13]\nb[14]\nb[15]\nb[16]\nb[17]\nb[18]\nb[19]\nb[20]\nb[21]";
+  }
+  static const char* monitor_names() { return "alpha0\nalpha1\nalpha2\nalpha12\ns2"; }
+  MCU_D static double eta(const Data& d, const double* s, int i) {
+    return s[0] + s[1] * d.x1[i] + s[2] * d.x2[i] + s[3] * d.x1[i] * d.x2[i] + s[5 + i];
+  }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f < 4) return lp_normal(s[f], 0.0, 1000.0);
+    if (f == 4) return lp_invgamma(s[4], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 5) {  // b ~ Normal(0, sqrt(s2)), one distribution for the 21-vector
+      const double sigma = sqrt(s[4]);
+      double lp = 0.0;
+      for (int i = 0; i < d.N; ++i) lp += lp_normal(s[5 + i], 0.0, sigma);
+      return lp;
+    }
+    double lp = 0.0;  // r[i] ~ Binomial(n[i], invlogit(eta_i))
+    for (int i = 0; i < d.N; ++i) lp += lp_binomial_logit(d.r[i], d.n[i], d.lc[i], eta(d, s, i));
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    double g0 = 0, g1 = 0, g2 = 0, g12 = 0, sbb = 0;
+    const double s2 = s[4];
+    for (int i = 0; i < d.N; ++i) {
+      const double p = 1.0 / (exp(-eta(d, s, i)) + 1.0);
+      const double de = d.r[i] - d.n[i] * p;
+      g0 += de; g1 += d.x1[i] * de; g2 += d.x2[i] * de; g12 += d.x1[i] * d.x2[i] * de;
+      g[5 + i] = de - s[5 + i] / s2;
+      sbb += s[5 + i] * s[5 + i];
+    }
+    g[0] = g0 - s[0] / 1e6; g[1] = g1 - s[1] / 1e6; g[2] = g2 - s[2] / 1e6; g[3] = g12 - s[3] / 1e6;
+    g[4] = -0.5 * (double)d.N / s2 + 0.5 * sbb / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  MCU_D static void monitor(const Data&, const double* s, double* out) {
+    for (int j = 0; j < 5; ++j) out[j] = s[j];
+  }
+};
+
+// =============================================================================== rats
+struct RatsModel {
+  // state: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30]
+  static constexpr int D = 65, NN = 7, NF = 8, P = 3, NR = 30;
+  struct Data { const double* y; const double* Xm; const int* rat; int N; double xbar; };
+  MCU_HD static int node_off(int n) { return n < 5 ? n : (n == 5 ? 5 : 35); }
+  MCU_HD static int node_len(int n) { return n < 5 ? 1 : NR; }
+  MCU_HD static int node_link(int n) { return (n >= 2 && n <= 4) ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) {
+    return f == 5 ? 0x05u /* mu_alpha, s2_alpha */ : f == 6 ? 0x0Au /* mu_beta, s2_beta */ : f == 7 ? 0x70u /* s2_c, alpha, beta */ : 0u;
+  }
+  // monitored: mu_beta (stochastic, identity), alpha0 (Logical → heuristic link), s2_c (log)
+  MCU_HD static int mon_link(int j) { return j == 0 ? LINK_IDENT : j == 1 ? LINK_HEUR : LINK_LOG; }
+  static const char* node_name(int n) { static const char* nm[] = {"mu_alpha", "mu_beta", "s2_alpha", "s2_beta", "s2_c", "alpha", "beta"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }   // generated: scalar nodes + alpha[1..30] + beta[1..30]
+  static const char* monitor_names() { return "mu_beta\nalpha0\ns2_c"; }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f < 2) return lp_normal(s[f], 0.0, 1000.0);
+    if (f < 5) return lp_invgamma(s[f], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 5) { const double sg = sqrt(s[2]); double lp = 0; for (int i = 0; i < NR; ++i) lp += lp_normal(s[5 + i], s[0], sg); return lp; }
+    if (f == 6) { const double sg = sqrt(s[3]); double lp = 0; for (int i = 0; i < NR; ++i) lp += lp_normal(s[35 + i], s[1], sg); return lp; }
+    double sq = 0.0;  // y ~ MvNormal(alpha[rat] + beta[rat] .* Xm, sqrt(s2_c))
+    for (int k = 0; k < d.N; ++k) {
+      const int i = d.rat[k];
+      if (!isfinite(s[5 + i]) || !isfinite(s[35 + i])) { /* mu non-finite: logpdf is NaN/-Inf either way */ }
+      const double mu = s[5 + i] + s[35 + i] * d.Xm[k];
+      const double e = d.y[k] - mu; sq += e * e;
+    }
+    return lp_isonormal(sq, (double)d.N, sqrt(s[4]));
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double mua = s[0], mub = s[1], s2a = s[2], s2b = s[3], s2c = s[4];
+    for (int i = 0; i < 2 * NR; ++i) g[5 + i] = 0.0;
+    double see = 0;
+    for (int k = 0; k < d.N; ++k) {
+      const int i = d.rat[k];
+      const double e = d.y[k] - (s[5 + i] + s[35 + i] * d.Xm[k]);
+      g[5 + i] += e / s2c; g[35 + i] += e * d.Xm[k] / s2c; see += e * e;
+    }
+    double sa = 0, saa = 0, sb = 0, sbb = 0;
+    for (int i = 0; i < NR; ++i) {
+      const double da = s[5 + i] - mua, db = s[35 + i] - mub;
+      g[5 + i] -= da / s2a; g[35 + i] -= db / s2b;
+      sa += da; saa += da * da; sb += db; sbb += db * db;
+    }
+    g[0] = sa / s2a - mua / 1e6;
+    g[1] = sb / s2b - mub / 1e6;
+    g[2] = -0.5 * NR / s2a + 0.5 * saa / (s2a * s2a) + d_invgamma(s2a, 0.001, 0.001);
+    g[3] = -0.5 * NR / s2b + 0.5 * sbb / (s2b * s2b) + d_invgamma(s2b, 0.001, 0.001);
+    g[4] = -0.5 * (double)d.N / s2c + 0.5 * see / (s2c * s2c) + d_invgamma(s2c, 0.001, 0.001);
+  }
+  MCU_D static void monitor(const Data& d, const double* s, double* out) {
+    out[0] = s[1]; out[1] = s[0] - d.xbar * s[1]; out[2] = s[4];   // alpha0 = mu_alpha - xbar * mu_beta (rats.jl:64-66)
+  }
+};
+
+// =============================================================================== pumps
+struct PumpsModel {
+  static constexpr int D = 12, NN = 3, NF = 4, P = 12, NPUMP = 10;
+  struct Data { const double* y; const double* t; const double* lgy1; int N; };
+  MCU_HD static int node_off(int n) { return n; }
+  MCU_HD static int node_len(int n) { return n == 2 ? NPUMP : 1; }
+  MCU_HD static int node_link(int) { return LINK_LOG; }
+  MCU_HD static uint32_t parents(int f) { return f == 2 ? 0x3u : f == 3 ? 0x4u : 0u; }
+  MCU_HD static int mon_link(int) { return LINK_LOG; }
+  static const char* node_name(int n) { static const char* nm[] = {"alpha", "beta", "theta"}; return nm[n]; }
+  static const char* state_names() { return "alpha\nbeta\ntheta[1]\ntheta[2]\ntheta[3]\ntheta[4]\ntheta[5]\ntheta[6]\ntheta[7]\ntheta[8]\ntheta[9]\ntheta[10]"; }
+  static const char* monitor_names() { return state_names(); }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_exponential(s[0], 1.0, transform);
+    if (f == 1) return lp_gamma(s[1], 0.1, 1.0, transform);
+    if (f == 2) {  // theta ~ Gamma(alpha, 1 / beta), one distribution for the 10-vector
+      const double a = s[0], th = 1.0 / s[1];
+      const double c = -lgamma(a) - a * log(th);
+      double lp = 0.0;
+      for (int i = 0; i < d.N; ++i) {
+        const double x = s[2 + i];
+        if (!(x >= 0.0)) { lp += neg_inf(); continue; }
+        const double lx = log(x);
+        double t = c + (a - 1.0) * lx - x / th;
+        if (transform) t += lx;
+        lp += t;
+      }
+      return lp;
+    }
+    double lp = 0.0;  // y[i] ~ Poisson(theta[i] * t[i])
+    for (int i = 0; i < d.N; ++i) lp += lp_poisson(d.y[i], d.lgy1[i], s[2 + i] * d.t[i]);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double al = s[0], be = s[1];
+    double slog = 0, sth = 0; const double N = (double)d.N;
+    for (int i = 0; i < d.N; ++i) {
+      const double th = s[2 + i];
+      g[2 + i] = d.y[i] / th - d.t[i] + (al - 1.0) / th - be;
+      slog += log(th); sth += th;
+    }
+    g[0] = N * log(be) + slog - N * digamma_d(al) - 1.0;
+    g[1] = N * al / be - sth + (0.1 - 1.0) / be - 1.0;
+  }
+  MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 12; ++j) out[j] = s[j]; }
+};
+
+// =============================================================================== glm (CUDA-core form)
+// y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
+// small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.
+template <int DMAX>
+struct GlmModel {
+  static constexpr int D = DMAX, NN = 1, NF = 2, P = DMAX;
+  struct Data { const double* X; const double* y; int N; int d; };
+  MCU_HD static int node_off(int) { return 0; }
+  MCU_HD static int node_len(int) { return DMAX; }
+  MCU_HD static int node_link(int) { return LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 1 ? 0x1u : 0u; }
+  MCU_HD static int mon_link(int) { return LINK_IDENT; }
+  static const char* node_name(int) { return "beta"; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return nullptr; }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool) {
+    if (f == 0) {
+      double sq = 0; for (int j = 0; j < d.d; ++j) { if (!isfinite(s[j])) return neg_inf(); sq += s[j] * s[j]; }
+      return lp_isonormal(sq, (double)d.d, sqrt(1000.0));
+    }
+    double lp = 0.0;
+    for (int i = 0; i < d.N; ++i) {
+      double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
+      lp += lp_bernoulli_logit(d.y[i], eta);
+    }
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    for (int j = 0; j < d.d; ++j) g[j] = -s[j] / 1000.0;
+    for (int i = 0; i < d.N; ++i) {
+      double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
+      const double r = d.y[i] - 1.0 / (exp(-eta) + 1.0);
+      for (int j = 0; j < d.d; ++j) g[j] += r * d.X[(size_t)i * d.d + j];
+    }
+  }
+  MCU_D static void monitor(const Data& d, const double* s, double* out) { for (int j = 0; j < d.d; ++j) out[j] = s[j]; }
+};
+
+}  // namespace mcu

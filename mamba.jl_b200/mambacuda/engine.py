@@ -1,0 +1,243 @@
+"""Engine — one handle of libmambacuda.so: all chains of one model template on one GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BlockDesc, MambaCudaError
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def make_desc(kind, nodes, scale=None, transform=None, adapt="all", batchsize=0, proposal="normal", L=0,
+              grad="analytic", max_depth=0, target=0.0, epsilon=0.0, beta=0.0, amm_scale=0.0):
+    """Fill a mcu_block_desc; returns (desc, keepalive-array)."""
+    d = BlockDesc()
+    d.kind = _lib.KIND[kind] if isinstance(kind, str) else int(kind)
+    nodes = list(nodes)
+    if not 1 <= len(nodes) <= _lib.MAX_BLOCK_NODES:
+        raise ValueError("a sampling block names 1..8 nodes")
+    d.n_nodes = len(nodes)
+    for i, n in enumerate(nodes):
+        d.nodes[i] = int(n)
+    if transform is None:
+        transform = 0 if d.kind in (1, 2) else 1
+    d.transform = int(bool(transform))
+    d.adapt = _lib.ADAPT[adapt] if isinstance(adapt, str) else int(adapt)
+    d.batchsize = int(batchsize)
+    d.proposal = _lib.PROPOSAL[proposal] if isinstance(proposal, str) else int(proposal)
+    d.L = int(L)
+    d.grad = _lib.GRAD[grad] if isinstance(grad, str) else int(grad)
+    d.max_depth = int(max_depth)
+    d.target, d.epsilon, d.beta, d.amm_scale = float(target), float(epsilon), float(beta), float(amm_scale)
+    keep = None
+    if scale is not None:
+        keep = np.ascontiguousarray(np.atleast_1d(np.asarray(scale, dtype=np.float64)).ravel(order="F"))
+        d.n_scale = keep.size
+        d.scale = keep.ctypes.data_as(C.POINTER(C.c_double))
+    return d, keep
+
+
+class Engine:
+    def __init__(self, template, n_chains, seed=123, chain_offset=0, device=0):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        tid = _lib.TPL[template] if isinstance(template, str) else int(template)
+        rc = self.L.mcu_create(tid, int(n_chains), int(chain_offset), int(device), int(seed), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.mcu_last_error(None).decode()
+            self.h = None
+            raise MambaCudaError(rc, msg)
+        self.template = tid
+        self.n_chains = int(n_chains)
+        self.chain_offset = int(chain_offset)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mcu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise MambaCudaError(rc, self.L.mcu_last_error(self.h).decode())
+
+    # ---- model -------------------------------------------------------------------------------
+    def set_data(self, name, arr):
+        a = _f64(np.asarray(arr))
+        dims = (C.c_int64 * max(a.ndim, 1))(*(a.shape if a.ndim else (1,)))
+        self._chk(self.L.mcu_set_data(self.h, name.encode(), max(a.ndim, 1), dims, _dp(a)))
+
+    def set_scheme(self, blocks):
+        arr = (BlockDesc * len(blocks))()
+        self._keep = []
+        for i, b in enumerate(blocks):
+            d, keep = make_desc(**b)
+            arr[i] = d
+            self._keep.append(keep)
+        self._chk(self.L.mcu_set_scheme(self.h, len(blocks), arr))
+        self.n_blocks = len(blocks)
+
+    def dims(self):
+        D, p, nn = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.L.mcu_dims(self.h, C.byref(D), C.byref(p), C.byref(nn)))
+        return D.value, p.value, nn.value
+
+    def names(self, which=1):
+        buf = C.create_string_buffer(1 << 16)
+        self.L.mcu_names(self.h, which, buf, len(buf))
+        return buf.value.decode().split("\n")
+
+    def tune_size(self):
+        n = C.c_int64()
+        self._chk(self.L.mcu_tune_size(self.h, C.byref(n)))
+        return n.value
+
+    # ---- chains ------------------------------------------------------------------------------
+    def set_inits(self, x, jitter_sd=0.0):
+        x = _f64(np.atleast_2d(x))
+        D = self.dims()[0]
+        if x.shape[1] != D:
+            raise ValueError(f"initial values have {x.shape[1]} entries per record, model state has {D}")
+        self._chk(self.L.mcu_set_inits(self.h, _dp(x), x.shape[0], float(jitter_sd)))
+
+    def kept(self, first_iter, iters, burnin, thin):
+        return self.L.mcu_kept(first_iter, iters, burnin, thin)
+
+    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False):
+        """Returns the [kept × p × chains] block (Fortran order) or None when out=False."""
+        _, p, _ = self.dims()
+        it0 = self.iter()
+        kept = self.kept(it0, iters, burnin, thin)
+        flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0)
+        arr = None
+        if out:
+            arr = np.full((kept, p, self.n_chains), np.nan, order="F")
+        self._chk(self.L.mcu_run(self.h, int(iters), int(burnin), int(thin), _dp(arr) if out and kept > 0 else None, flags))
+        return arr
+
+    def iter(self):
+        it = C.c_int64()
+        rc = self.L.mcu_get_state(self.h, None, None, C.byref(it))
+        return it.value if rc == 0 else 0
+
+    def get_state(self):
+        D = self.dims()[0]
+        nt = self.tune_size()
+        v = np.empty((self.n_chains, D))
+        t = np.empty((self.n_chains, max(nt, 1)))
+        it = C.c_int64()
+        self._chk(self.L.mcu_get_state(self.h, _dp(v), _dp(t) if nt else None, C.byref(it)))
+        return v, t[:, :nt], it.value
+
+    def set_state(self, values, tune, it):
+        v = _f64(values)
+        t = _f64(tune) if tune is not None and tune.size else None
+        self._chk(self.L.mcu_set_state(self.h, _dp(v), _dp(t), int(it)))
+
+    def set_external_stream(self, u):
+        if u is None:
+            self._chk(self.L.mcu_set_rng_mode(self.h, 0, None, 0))
+            return
+        u = _f64(np.atleast_2d(u))
+        assert u.shape[0] == self.n_chains
+        self._chk(self.L.mcu_set_rng_mode(self.h, 1, _dp(u), u.shape[1]))
+
+    # ---- densities ---------------------------------------------------------------------------
+    def logpdf(self, block, state, x=None):
+        state = _f64(np.atleast_2d(state))
+        x = _f64(None if x is None else np.atleast_2d(x))
+        lp = np.empty(state.shape[0])
+        self._chk(self.L.mcu_logpdf(self.h, block, state.shape[0], _dp(state), _dp(x), _dp(lp)))
+        return lp
+
+    def gradlogpdf(self, block, state, k, x=None, mode="analytic"):
+        state = _f64(np.atleast_2d(state))
+        x = _f64(None if x is None else np.atleast_2d(x))
+        lp = np.empty(state.shape[0])
+        g = np.empty((state.shape[0], k))
+        m = _lib.GRAD[mode] if isinstance(mode, str) else int(mode)
+        self._chk(self.L.mcu_gradlogpdf(self.h, block, m, state.shape[0], _dp(state), _dp(x), _dp(lp), _dp(g)))
+        return lp, g
+
+    # ---- diagnostics -------------------------------------------------------------------------
+    def minmax(self):
+        p = self.dims()[1]
+        mm = np.empty((p, 2))
+        self._chk(self.L.mcu_minmax(self.h, _dp(mm)))
+        return mm
+
+    def link_codes(self, transform, minmax=None):
+        p = self.dims()[1]
+        codes = (C.c_int * p)()
+        mm = _f64(minmax)
+        self._chk(self.L.mcu_link_codes(self.h, int(bool(transform)), _dp(mm), codes))
+        return np.array(list(codes), dtype=np.int32)
+
+    def moments(self, codes=None, center=None):
+        p = self.dims()[1]
+        sums = np.empty((p, 7))
+        n = C.c_int64()
+        cc = None if codes is None else (C.c_int * p)(*[int(c) for c in codes])
+        ctr = _f64(center)
+        self._chk(self.L.mcu_moments(self.h, cc, _dp(ctr), _dp(sums), C.byref(n)))
+        return sums, n.value
+
+    def gelman_from_moments(self, n_kept, center, sums, alpha=0.05):
+        p = sums.shape[0]
+        psrf = np.empty((p, 2))
+        center = _f64(center); sums = _f64(sums)
+        rc = self.L.mcu_gelman_from_moments(int(n_kept), p, _dp(center), _dp(sums), float(alpha), _dp(psrf))
+        if rc != 0:
+            raise ValueError("less than 2 chains supplied to gelman diagnostic")
+        return psrf
+
+    def gelman(self, alpha=0.05, transform=False):
+        p = self.dims()[1]
+        psrf = np.empty((p, 2))
+        self._chk(self.L.mcu_gelman(self.h, float(alpha), int(bool(transform)), _dp(psrf)))
+        return psrf
+
+    def summarystats(self, etype="bm", batch=100):
+        p = self.dims()[1]
+        out = np.empty((p, 5))
+        self._chk(self.L.mcu_summarystats(self.h, {"bm": 0, "imse": 1}[etype], int(batch), _dp(out)))
+        return out
+
+    def summary_sums(self, center=None):
+        p = self.dims()[1]
+        sums = np.empty((p, 8))
+        ctr = _f64(center)
+        self._chk(self.L.mcu_summary_sums(self.h, _dp(ctr), _dp(sums)))
+        return sums
+
+    def summary_from_sums(self, n_kept, center, sums):
+        p = sums.shape[0]
+        out = np.empty((p, 5))
+        center = _f64(center); sums = _f64(sums)
+        self.L.mcu_summary_from_sums(int(n_kept), p, _dp(center), _dp(sums), _dp(out))
+        return out
+
+    def summary_streaming(self):
+        p = self.dims()[1]
+        out = np.empty((p, 5))
+        self._chk(self.L.mcu_summary_streaming(self.h, _dp(out)))
+        return out
+
+    def launch_count(self):
+        return self.L.mcu_launch_count(self.h)
+
+    def last_kernel_ms(self):
+        return self.L.mcu_last_kernel_ms(self.h)

@@ -1,0 +1,80 @@
+"""Shared fixtures for the parity tests: schemes, initial values and comparison helpers."""
+import numpy as np
+
+# state record layouts (include/mambacuda.h):
+#  line : beta[2], s2                 seeds: alpha0, alpha1, alpha2, alpha12, s2, b[21]
+#  rats : mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30]
+#  pumps: alpha, beta, theta[10]      glm  : beta[d]
+
+SEEDS_INITS = np.zeros((2, 26)); SEEDS_INITS[0, 4] = 0.01; SEEDS_INITS[1, 4] = 1.0   # doc/examples/seeds.jl:60-65
+RATS_INITS = np.array([[150, 10, 1, 1, 1] + [250] * 30 + [6] * 30,                   # doc/examples/rats.jl:100-108
+                       [15, 1, 10, 10, 10] + [20] * 30 + [0.6] * 30], dtype=float)
+LINE_INITS = np.array([[0.3, -0.2, 1.5], [1.0, 0.5, 0.7], [-0.5, 1.2, 3.0]])
+
+
+def pumps_inits(seed=1):
+    rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
+    return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
+
+
+SCHEMES = {
+    # AMWG(beta) + Slice(s2, transform)
+    "line_amwg_slice": ("line", [dict(kind="amwg", nodes=[0], scale=1.0, adapt="burnin"),
+                                 dict(kind="slice_multi", nodes=[1], scale=5.0, transform=1)], LINE_INITS),
+    # doc/tutorial/line.jl:48-49 scheme1
+    "line_nuts_slice": ("line", [dict(kind="nuts", nodes=[0]), dict(kind="slice_multi", nodes=[1], scale=3.0)], LINE_INITS),
+    # doc/tutorial/line.jl:52 scheme2
+    "line_nuts_all": ("line", [dict(kind="nuts", nodes=[0, 1])], LINE_INITS),
+    "line_nuts_fd": ("line", [dict(kind="nuts", nodes=[0, 1], grad="forward")], LINE_INITS),
+    "line_rwm": ("line", [dict(kind="rwm", nodes=[0, 1], scale=[0.5, 0.2, 0.8])], LINE_INITS),
+    "line_rwm_unif": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symuniform")], LINE_INITS),
+    "line_rwm_tri": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symtriangular")], LINE_INITS),
+    "line_hmc": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=8)], LINE_INITS),
+    "line_hmc_sigma": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=5,
+                                     scale=np.array([[1.0, 0.2, 0.0], [0.2, 0.5, 0.1], [0.0, 0.1, 2.0]]))], LINE_INITS),
+    "line_amm": ("line", [dict(kind="amm", nodes=[0, 1], scale=0.05 * np.eye(3))], LINE_INITS),
+    "line_slice_uni": ("line", [dict(kind="slice_uni", nodes=[0, 1], scale=[1.0, 1.0, 2.0], transform=1)], LINE_INITS),
+    # SURVEY.md §8d config 2 scheme A (north_star "AMWG on seeds")
+    "seeds_amwg": ("seeds", [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", nodes=[5], scale=0.01),
+                             dict(kind="amwg", nodes=[4], scale=0.1)], SEEDS_INITS),
+    # doc/examples/seeds.jl:69-71 scheme B (reference-faithful)
+    "seeds_amm": ("seeds", [dict(kind="amm", nodes=[0, 1, 2, 3], scale=0.01 * np.eye(4)), dict(kind="amwg", nodes=[5], scale=0.01),
+                            dict(kind="amwg", nodes=[4], scale=0.1)], SEEDS_INITS),
+    # doc/examples/rats.jl:112-116
+    "rats_slice_amwg": ("rats", [dict(kind="slice_multi", nodes=[4], scale=10.0), dict(kind="amwg", nodes=[5], scale=100.0),
+                                 dict(kind="slice_uni", nodes=[0, 2], scale=[100.0, 10.0]), dict(kind="amwg", nodes=[6], scale=1.0),
+                                 dict(kind="slice_uni", nodes=[1, 3], scale=1.0)], RATS_INITS),
+    # NUTS(alpha, beta, mu_alpha, mu_beta) + Slice(s2_c, s2_alpha, s2_beta; univariate)
+    "rats_nuts_slice": ("rats", [dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], RATS_INITS),
+    # doc/examples/pumps.jl:52-53
+    "pumps_slice": ("pumps", [dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], None),
+    "pumps_amwg_nuts": ("pumps", [dict(kind="amwg", nodes=[0, 1], scale=0.5), dict(kind="nuts", nodes=[2])], None),
+}
+
+
+def oracle_block(b):
+    """helpers scheme dict -> pyoracle.make_desc kwargs (ints instead of names)."""
+    from mambacuda import _lib
+    o = dict(b)
+    if "adapt" in o and isinstance(o["adapt"], str):
+        o["adapt"] = _lib.ADAPT[o["adapt"]]
+    if "proposal" in o and isinstance(o["proposal"], str):
+        o["proposal"] = _lib.PROPOSAL[o["proposal"]]
+    if "grad" in o and isinstance(o["grad"], str):
+        o["grad"] = _lib.GRAD[o["grad"]]
+    return o
+
+
+def scheme(name):
+    tpl, blocks, inits = SCHEMES[name]
+    if inits is None:
+        inits = pumps_inits()
+    return tpl, blocks, np.array(inits, dtype=float)
+
+
+def glm_data(N=200, d=8, seed=1):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(N, d)); X[:, 0] = 1.0
+    beta = rng.normal(size=d) / np.sqrt(d)
+    y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(float)
+    return X, y, beta
