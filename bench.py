@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 batched MCMC engine.
+
+Metric (BASELINE.json): chain-iterations/s of AMWG on the `seeds` random-effects logistic model
+(configs[1]): scheme [AMWG(alpha0..alpha12, 0.1), AMWG(b, 0.01), AMWG(s2, 0.1)],
+125,000 chains per GPU (10^6 chains on 8 GPUs, weak scaling), one step = one mcmc() call of 2,000
+iterations (burn-in 1,000, thin 10) for every chain, followed by the on-device Gelman-Rubin /
+summary reductions (all-reduced over NCCL when N > 1 — the only collective on the path).
+
+  value : chain-iterations/s over all GPUs with the inputs resident in HBM
+  e2e   : the same through the C ABI with HOST buffers: per-chain initial values copied from pinned host
+          memory every step, final chain states + diagnostics read back every step
+  --impl reference : the CPU restatement of the reference's algorithm (oracle/) on all host threads,
+          on a bounded sample of the same workload (the Julia reference cannot run here: no julia).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "mamba.jl_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+CHAINS_PER_GPU = 125_000
+ITERS, BURNIN, THIN = 2000, 1000, 10
+SEED = 123
+# Algorithmic FP64 work of one chain-iteration in the minimal (term-difference) form, DESIGN.md §4:
+# 68 binomial-logit term evaluations x 72 flop + 26 normal draws x 96 flop + 26 MH tests x 20 flop + 60.
+ALGO_FLOP_PER_CHAIN_ITER = 68 * 72 + 26 * 96 + 26 * 20 + 60
+# Algorithmic HBM bytes of one chain-iteration: thinned output only (5 monitored doubles every THIN iterations)
+ALGO_BYTES_PER_CHAIN_ITER = 5 * 8 / THIN
+
+SCHEME = [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", nodes=[5], scale=0.01),
+          dict(kind="amwg", nodes=[4], scale=0.1)]
+
+
+def seeds_inits():
+    x = np.zeros((2, 26)); x[0, 4] = 0.01; x[1, 4] = 1.0   # doc/examples/seeds.jl:60-65
+    return x
+
+
+def per_chain_inits(n, offset):
+    """Host-side initial values for every chain: the two reference init records cycled, plus a deterministic jitter."""
+    base = seeds_inits()
+    idx = (np.arange(n) + offset) % 2
+    x = base[idx].copy()
+    rng = np.random.default_rng(SEED + offset)
+    x[:, :4] += 0.1 * rng.standard_normal((n, 4))
+    x[:, 4] *= np.exp(0.1 * rng.standard_normal(n))
+    x[:, 5:] += 0.1 * rng.standard_normal((n, 21))
+    return x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_oracle_sample(n_chains, iters, burnin, thin, nthreads):
+    import helpers
+    import pyoracle
+    orc = pyoracle.Oracle("seeds")
+    orc.set_scheme([helpers.oracle_block(b) for b in SCHEME])
+    t0 = time.perf_counter()
+    orc.run(n_chains, seeds_inits(), iters, burnin=burnin, thin=thin, seed=SEED, nthreads=nthreads, store=False)
+    dt = time.perf_counter() - t0
+    return n_chains * iters / dt, dt
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path: the oracle port, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_chains = 16 * cores
+    for _ in range(args.warmup):
+        run_oracle_sample(cores, 200, 100, THIN, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_oracle_sample(n_chains, ITERS, BURNIN, THIN, cores)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_chains * ITERS / dt
+    sample = f"{n_chains} chains (16 per host thread) x {ITERS} iterations per step, same model/scheme/burn-in/thinning"
+    line = {
+        "impl": "reference", "metric": "chain_iters_per_sec", "value": value, "unit": "chain-iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "seeds random-effects logistic (21 plates), AMWG x3 blocks, 2000 iters (burnin 1000, thin 10)",
+                   "chains": n_chains, "note": "Julia reference not runnable (no julia in image); CPU restatement of its algorithm (oracle/) timed instead"},
+        "cpu_baseline": {"value": value, "unit": "chain-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "chain-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--iters", type=int, default=ITERS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-generic", action="store_true", help="time the generic engine kernel instead of the fused one")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mambacuda import distributed as mdist
+    from mambacuda.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+
+    C = args.chains_per_gpu
+    iters = args.iters
+    burnin = min(BURNIN, iters // 2)
+    eng = Engine("seeds", C, seed=SEED, chain_offset=rank * C, device=local_rank)
+    eng.set_scheme(SCHEME)
+    inits2 = seeds_inits()
+    peak_fp64 = eng.fp64_peak_tflops()
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        l2_flush.fill_(1)                                  # evict L2 between steps
+        eng.set_inits(inits2, jitter_sd=0.1)               # 2 init records, cycled + Philox jitter on the device
+        eng.run(iters, burnin=burnin, thin=THIN, store=False, out=False, force_generic=args.force_generic)
+        ms = eng.last_kernel_ms()
+        psrf = mdist.global_gelman(eng, 0.05, True, device)
+        return ms, psrf
+
+    # pinned host buffers for the end-to-end arm
+    host_inits = torch.empty((C, 26), dtype=torch.float64).pin_memory()
+    host_inits.numpy()[:] = per_chain_inits(C, rank * C)
+    host_state = torch.empty((C, 26), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        l2_flush.fill_(1)
+        eng.set_inits(host_inits.numpy())                  # H2D: C x 26 doubles from pinned memory
+        eng.run(iters, burnin=burnin, thin=THIN, store=False, out=False, force_generic=args.force_generic)
+        psrf = mdist.global_gelman(eng, 0.05, True, device)
+        summ = mdist.global_summary(eng, device)
+        import ctypes as Ct
+        dp = host_state.numpy().ctypes.data_as(Ct.POINTER(Ct.c_double))
+        it = Ct.c_int64()
+        eng._chk(eng.L.mcu_get_state(eng.h, dp, None, Ct.byref(it)))   # D2H: final states into pinned memory
+        return psrf, summ
+
+    # ---- resident arm ---------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    launches0 = eng.launch_count()
+    t0 = time.perf_counter()
+    kernel_ms = []
+    psrf = None
+    for _ in range(args.steps):
+        ms, psrf = step_resident()
+        kernel_ms.append(ms)
+    sync_all()
+    dt = time.perf_counter() - t0
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    tmax = torch.tensor([dt], dtype=torch.float64, device=device)
+    kmax = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item()); kms = float(kmax.item())
+    value = world * C * iters * args.steps / dt
+
+    # ---- end-to-end arm -------------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        psrf_e, summ_e = step_e2e()
+    sync_all()
+    dte = time.perf_counter() - t0
+    tmax = torch.tensor([dte], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dte = float(tmax.item())
+    e2e_value = world * C * iters * args.steps / dte
+    h2d = C * 26 * 8
+    d2h = C * 26 * 8 + 5 * 2 * 8 + 5 * 5 * 8 + 4 * 5 * 7 * 8
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        kernel_rate = C * iters / (kms * 1e-3)             # chain-iterations/s of the dominant kernel on one GPU
+        achieved_tflops = kernel_rate * ALGO_FLOP_PER_CHAIN_ITER / 1e12
+        kept = (iters - burnin) // THIN
+        hbm_bytes = C * (kept * 5 * 8)                     # algorithmic: the thinned monitored values
+        line = {
+            "metric": "chain_iters_per_sec", "value": value, "unit": "chain-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "seeds random-effects logistic regression (21 plates, doc/examples/seeds.jl), AMWG(alpha0..alpha12)+AMWG(b)+AMWG(s2)",
+                "chains_per_gpu": C, "chains_total": world * C, "iters": iters, "burnin": burnin, "thin": THIN,
+                "kernel": "generic" if args.force_generic else "seeds_fast (fused)",
+                "parallelism": f"chains sharded over {world} GPU(s), no data-path collective; all-reduce of 7p moment sums for PSRF",
+                "l2": "L2 flushed between steps (256 MiB fill); chain state is register/shared-memory resident inside a step",
+                "psrf_max": float(np.max(psrf[:, 0])) if psrf is not None else None,
+            },
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tflops, "peak": peak_fp64, "unit": "TFLOP/s",
+                "frac": achieved_tflops / peak_fp64 if peak_fp64 > 0 else None, "traffic": None,
+                "peak_source": "DFMA microbenchmark run by this process (mcu_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 figure",
+                "kernel": "seeds_fast_kernel<96>" if not args.force_generic else "run_generic_kernel<SeedsModel>",
+                "kernel_ms": kms, "algo_flop_per_chain_iter": ALGO_FLOP_PER_CHAIN_ITER,
+                "note": "CUDA-core FP64 kernel: neither HBM- nor tensor-bound (SURVEY.md §8d); the hbm object shows the memory side is idle",
+                "hbm": {"bound": "hbm", "achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": hbm_bytes / (kms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_source": peak_src},
+            },
+            "e2e": {"value": e2e_value, "unit": "chain-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * dte / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_s = 16 * cores
+            v, secs = run_oracle_sample(n_s, ITERS, BURNIN, THIN, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "chain-iterations/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_s} chains x {ITERS} iterations of the same model/scheme on {cores} host threads ({secs:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

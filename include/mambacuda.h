@@ -208,6 +208,9 @@ int mcu_set_rng_mode(mcu_handle h, int mode, const double* u, size_t n_per_chain
 
 /* ---- device info for the harness ------------------------------------------------------------ */
 int mcu_device_count(void);
+/* Measured FP64 FMA throughput of the handle's device (DFMA microbenchmark, TFLOP/s): the roofline
+ * denominator for the CUDA-core small-model kernels, which MEASURED_PEAKS.json does not carry.       */
+double mcu_fp64_peak_tflops(mcu_handle h);
 /* Number of kernel launches issued by this handle since creation (bench "gpu_launches").      */
 int64_t mcu_launch_count(mcu_handle h);
 /* Device time in ms of the sampler kernels of the last mcu_run (CUDA events on the launching stream). */

@@ -268,6 +268,7 @@ bool scheme_is_seeds_fast(const mcu_ctx* h) {
   if (b.n_own != 1 || b.own[0] != 5) return false;
   if (c.n_own != 1 || c.own[0] != 4) return false;
   if ((int)h->inputs.at("r").size() != SeedsModel::NP) return false;
+  for (const char* nm : {"x1", "x2"}) for (double v : h->inputs.at(nm)) if (v != 0.0 && v != 1.0) return false;   // 0/1 design → 4 group bases
   return true;
 }
 
@@ -790,6 +791,12 @@ int mcu_summarystats(mcu_handle h, int etype, int batch_size, double* out) {
   return MCU_OK;
 }
 
+double mcu_fp64_peak_tflops(mcu_handle h) {
+  if (!h) return -1.0;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+  h->launches += 6;
+  return measure_fp64_peak_tflops(h->stream);
+}
 int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
 double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }
 

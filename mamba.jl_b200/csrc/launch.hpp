@@ -40,6 +40,8 @@ void launch_minmax_partial(const double* mom, long long C, int P, double* partia
 void launch_summary_partial(const double* mom, const double* momn, long long C, int P, const double* center,
                             double* partial, cudaStream_t st);
 
+double measure_fp64_peak_tflops(cudaStream_t st);
+
 // fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success
 int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
 

@@ -46,7 +46,7 @@ SYMBOLS = [
     "mcu_set_state", "mcu_logpdf", "mcu_gradlogpdf", "mcu_minmax", "mcu_link_codes", "mcu_moments",
     "mcu_gelman_from_moments", "mcu_gelman", "mcu_summarystats", "mcu_summary_sums",
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
-    "mcu_launch_count", "mcu_last_kernel_ms",
+    "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
     L.mcu_set_rng_mode.argtypes = [vp, C.c_int, dp, C.c_size_t]
     L.mcu_launch_count.restype = i64
     L.mcu_launch_count.argtypes = [vp]
+    L.mcu_fp64_peak_tflops.restype = C.c_double
+    L.mcu_fp64_peak_tflops.argtypes = [vp]
     L.mcu_last_kernel_ms.restype = C.c_double
     L.mcu_last_kernel_ms.argtypes = [vp]
     _lib = L

@@ -236,6 +236,9 @@ class Engine:
         self._chk(self.L.mcu_summary_streaming(self.h, _dp(out)))
         return out
 
+    def fp64_peak_tflops(self):
+        return self.L.mcu_fp64_peak_tflops(self.h)
+
     def launch_count(self):
         return self.L.mcu_launch_count(self.h)
 

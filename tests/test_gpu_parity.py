@@ -82,10 +82,11 @@ def test_gradient_matches_oracle(oracle, name):
         _, gf_o = orc.gradlogpdf(b, st, mode=1)
         _, gf_g = eng.gradlogpdf(b, st, k, mode="forward")
         scale = 1.0 + np.abs(g_o)
-        assert np.max(np.abs(gf_g - gf_o) / scale) < 1e-4
-        assert np.max(np.abs(gf_g - g_g) / scale) < 1e-3
+        noise = 3e-7 * np.maximum(1.0, np.abs(lp_o))[:, None]    # ~ 20 eps |f| / h with h = sqrt(eps)
+        assert np.all(np.abs(gf_g - gf_o) / scale < noise + 1e-6)
+        assert np.all(np.abs(gf_g - g_g) / scale < noise + 1e-4)  # + O(h f'') truncation
         _, gc_g = eng.gradlogpdf(b, st, k, mode="central")
-        assert np.max(np.abs(gc_g - g_g) / scale) < 1e-5
+        assert np.all(np.abs(gc_g - g_g) / scale < 1e-9 * np.maximum(1.0, np.abs(lp_o))[:, None] + 1e-5)
 
 
 def test_glm_density_and_gradient(oracle):
@@ -114,16 +115,18 @@ def run_pair(oracle, name, n_chains, iters, burnin, thin, seed=99, force_generic
     return (out_g, st_g, tune_g), (out_o, st_o, tune_o), eng, orc
 
 
-def assert_same_run(g, o, rtol=1e-8, min_frac=1.0):
+def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     """Chains that took identical decisions agree to rounding.  `min_frac` < 1 tolerates the rare chain
     whose accept/reject comparison sits within rounding of the threshold (then everything after differs)."""
     out_g, st_g, tune_g = g
     out_o, st_o, tune_o = o
     C = st_g.shape[0]
-    ok = np.array([np.allclose(st_g[c], st_o[c], rtol=rtol, atol=1e-10) and
-                   np.allclose(out_g[:, :, c], out_o[:, :, c], rtol=rtol, atol=1e-10) and
-                   np.allclose(tune_g[c], tune_o[c], rtol=1e-7, atol=1e-10) for c in range(C)])
-    assert ok.mean() >= min_frac, f"only {ok.sum()}/{C} chains reproduce the oracle trajectory"
+    ok_state = np.array([np.allclose(st_g[c], st_o[c], rtol=rtol, atol=1e-10) for c in range(C)])
+    ok_out = np.array([np.allclose(out_g[:, :, c], out_o[:, :, c], rtol=rtol, atol=1e-10) for c in range(C)])
+    ok_tune = np.array([np.allclose(tune_g[c], tune_o[c], rtol=tune_rtol, atol=tune_rtol * 1e-2, equal_nan=True) for c in range(C)])
+    ok = ok_state & ok_out & ok_tune
+    assert ok.mean() >= min_frac, (f"only {ok.sum()}/{C} chains reproduce the oracle trajectory "
+                                   f"(state {ok_state.sum()}, samples {ok_out.sum()}, tune {ok_tune.sum()})")
     assert not np.isnan(out_g).any()
 
 
@@ -143,18 +146,14 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0):
 ])
 def test_trajectories_match_oracle(oracle, name, iters, burnin, thin):
     g, o, _, _ = run_pair(oracle, name, 16, iters, burnin, thin)
-    assert_same_run(g, o, min_frac=0.9)
+    # AMM's SigmaLm comes from Mvv - Mv Mv' (cancellation): its entries agree to fewer digits than the chain does
+    assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4 if "amm" in name else 1e-6)
 
 
-@pytest.mark.parametrize("name,iters,burnin", [
-    ("line_nuts_slice", 300, 150),
-    ("line_nuts_all", 300, 150),
-    ("rats_nuts_slice", 60, 30),
-    ("pumps_amwg_nuts", 150, 75),
-])
-def test_nuts_trajectories_match_oracle(oracle, name, iters, burnin):
-    # the oracle runs the reference's recursive buildtree, the device the unrolled form; both with max_depth 10
-    eng, orc, inits = make_pair(oracle, name, 16, seed=5)
+def nuts_pair(oracle, name, n_chains, iters, burnin, seed):
+    """The oracle runs the reference's recursive buildtree (nuts.jl:139-180), the device the unrolled
+    leaf-by-leaf form; both stop doubling after 10 doublings."""
+    eng, orc, inits = make_pair(oracle, name, n_chains, seed=seed)
     tpl, blocks, _ = helpers.scheme(name)
     ob = [helpers.oracle_block(b) for b in blocks]
     for b in ob:
@@ -164,9 +163,27 @@ def test_nuts_trajectories_match_oracle(oracle, name, iters, burnin):
     eng.set_inits(inits)
     out_g = eng.run(iters, burnin=burnin, thin=1, force_generic=True)
     st_g, tune_g, _ = eng.get_state()
-    out_o, st_o, tune_o = orc.run(16, inits, iters, burnin=burnin, thin=1, seed=5, nthreads=4)
-    # Hamiltonian trajectories amplify rounding; NUTS epsilon adaptation feeds it back: looser tolerance
-    assert_same_run((out_g, st_g, tune_g), (out_o, st_o, tune_o), rtol=1e-6, min_frac=0.75)
+    out_o, st_o, tune_o = orc.run(n_chains, inits, iters, burnin=burnin, thin=1, seed=seed, nthreads=4)
+    return (out_g, st_g, tune_g), (out_o, st_o, tune_o)
+
+
+@pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts"])
+def test_nuts_adaptive_trajectories_match_oracle(oracle, name):
+    # Dual averaging multiplies a perturbation of the acceptance statistic by sqrt(m)/gamma/(m+t0) ~ 2-10x per
+    # adaptive iteration (nuts.jl:70-75), so libm-level rounding differences between two machines grow
+    # exponentially while adapting: step-wise agreement is only observable over a short horizon.
+    # 64 chains x 12 adaptive + 4 non-adaptive iterations exercise trees of several depths and both directions.
+    g, o = nuts_pair(oracle, name, 64, 16, 12, seed=5)
+    assert_same_run(g, o, rtol=1e-5, min_frac=0.9)
+    depth_proxy = g[2][:, -1] if name != "pumps_amwg_nuts" else g[2][:, -1]
+    assert depth_proxy.max() >= 4          # nalpha of the last doubling: trees deeper than one doubling were built
+
+
+@pytest.mark.parametrize("name,iters", [("line_nuts_slice", 150), ("line_nuts_all", 150), ("rats_nuts_slice", 40), ("pumps_amwg_nuts", 100)])
+def test_nuts_fixed_stepsize_trajectories_match_oracle(oracle, name, iters):
+    # burnin = 0: model-based NUTS adapts only while iter <= burnin (nuts.jl:52), epsilon stays at nutsepsilon()
+    g, o = nuts_pair(oracle, name, 16, iters, 0, seed=6)
+    assert_same_run(g, o, rtol=1e-6, min_frac=0.85)
 
 
 def test_nuts_fd_gradient_statistically_equivalent(oracle):
@@ -264,3 +281,52 @@ def test_error_codes(oracle):
     one = Engine(tpl, 1); one.set_scheme(blocks); one.set_inits(inits); one.run(20, burnin=5)
     with pytest.raises(MambaCudaError, match="less than 2 chains"):   # gelmandiag.jl:6-7
         one.gelman()
+
+
+# ---- the fused seeds/AMWG kernel (mamba.jl_b200/csrc/seeds_fast.cu) ------------------------------------
+def test_seeds_fast_matches_oracle_and_generic(oracle):
+    # dispatch happens inside mcu_run when the scheme is [AMWG(alphas), AMWG(b), AMWG(s2)] on the seeds template
+    g, o, eng, _ = run_pair(oracle, "seeds_amwg", 64, 400, 200, 4, seed=21, force_generic=False)
+    assert_same_run(g, o, rtol=1e-8, min_frac=0.95)
+    assert (g[2][:, 0] == 400).all() and (o[2][:, 0] == 400).all()           # m of block 0 (adapt=:all)
+    np.testing.assert_array_equal(g[2][:, 6:10], o[2][:, 6:10])              # alpha accept counters are integers
+    g2, _, _, _ = run_pair(oracle, "seeds_amwg", 64, 400, 200, 4, seed=21, force_generic=True)
+    np.testing.assert_allclose(g[0], g2[0], rtol=1e-9, atol=1e-12)
+
+
+def test_seeds_fast_burnin_adaptation_and_restart(oracle):
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("seeds_amwg")
+    blocks = [dict(b, adapt="burnin") for b in blocks]
+    a = Engine(tpl, 32, seed=9); a.set_scheme(blocks); a.set_inits(inits, jitter_sd=0.1)
+    full = a.run(300, burnin=120, thin=3)
+    b = Engine(tpl, 32, seed=9); b.set_scheme(blocks); b.set_inits(inits, jitter_sd=0.1)
+    p1 = b.run(130, burnin=120, thin=3); p2 = b.run(170, burnin=120, thin=3)
+    assert p1.shape[0] == 3
+    np.testing.assert_array_equal(np.concatenate([p1, p2], axis=0), full)
+    orc = oracle.Oracle(tpl); orc.set_scheme([helpers.oracle_block(x) for x in blocks])
+    out_o, st_o, tune_o = orc.run(32, inits, 300, burnin=120, thin=3, seed=9, jitter_sd=0.1, nthreads=4)
+    st, tune, _ = a.get_state()
+    ok = [np.allclose(full[:, :, c], out_o[:, :, c], rtol=1e-8) and np.allclose(tune[c], tune_o[c], rtol=1e-7) for c in range(32)]
+    assert np.mean(ok) >= 0.95
+    assert (tune[:, 0] == 120).all() and (tune[:, 1] == 0).all()             # adaptation stopped after burn-in
+
+
+def test_seeds_fast_posterior_within_3_mcse_of_reference(oracle):
+    # doc/examples/seeds.rst:37-56 (AMM+AMWG+AMWG, 2 x 12,500, burnin 2,500, thin 2): mean [MCSE]
+    ref = {"alpha0": (-0.556154341, 0.0101730837), "alpha1": (0.088700176, 0.0128300598), "alpha2": (1.310728093, 0.0153996801),
+           "alpha12": (-0.746440855, 0.0251658152), "s2": (0.085705306, 0.0080848189)}
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("seeds_amwg")
+    # same inits, iterations, burn-in and thinning as the reference run, 4096 chains instead of 2 (the chain
+    # mixes slowly — ESS 145 of 10,000 for s2 in the reference — so a shorter burn-in is visibly biased)
+    eng = Engine(tpl, 4096, seed=2024); eng.set_scheme(blocks); eng.set_inits(inits)
+    eng.run(12500, burnin=2500, thin=2, store=False, out=False)
+    ss = eng.summary_streaming()
+    names = eng.names(1)
+    for j, nm in enumerate(names):
+        mean, mcse_ref = ref[nm]
+        tol = 3.0 * np.hypot(mcse_ref, ss[j, 3])
+        assert abs(ss[j, 0] - mean) < tol, (nm, ss[j, 0], mean, tol)
+    psrf = eng.gelman(0.05, True)
+    assert (psrf[:, 0] < 1.2).all()   # doc/tutorial.rst:321 rule of thumb
