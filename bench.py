@@ -129,7 +129,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_chains = 16 * cores
+    n_chains = 64 * cores
     for _ in range(args.warmup):
         run_oracle_sample(cores, 200, 100, THIN, cores)
     t0 = time.perf_counter()
@@ -137,7 +137,7 @@ def reference_arm(args, rank, world):
         run_oracle_sample(n_chains, ITERS, BURNIN, THIN, cores)
     dt = time.perf_counter() - t0
     value = args.steps * n_chains * ITERS / dt
-    sample = f"{n_chains} chains (16 per host thread) x {ITERS} iterations per step, same model/scheme/burn-in/thinning"
+    sample = f"{n_chains} chains (64 per host thread) x {ITERS} iterations per step, same model/scheme/burn-in/thinning"
     line = {
         "impl": "reference", "metric": "chain_iters_per_sec", "value": value, "unit": "chain-iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -301,7 +301,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_s = 16 * cores
+            n_s = 128 * cores    # ~10-20 s of CPU work
             v, secs = run_oracle_sample(n_s, ITERS, BURNIN, THIN, cores)
             line["cpu_baseline"] = {"value": v, "unit": "chain-iterations/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_s} chains x {ITERS} iterations of the same model/scheme on {cores} host threads ({secs:.1f} s)"}

@@ -32,7 +32,10 @@ SCHEMES = {
     "line_hmc": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=8)], LINE_INITS),
     "line_hmc_sigma": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=5,
                                      scale=np.array([[1.0, 0.2, 0.0], [0.2, 0.5, 0.1], [0.0, 0.1, 2.0]]))], LINE_INITS),
-    "line_amm": ("line", [dict(kind="amm", nodes=[0, 1], scale=0.05 * np.eye(3))], LINE_INITS),
+    # small initial proposals: every early move is accepted, so the adapted covariance is full rank by the time it is
+    # first used (m > 2n, amm.jl:75-77); a rank-deficient Sigma makes cholfact(.., Val{true})'s rank decision — and the
+    # trajectory — depend on rounding noise in the reference itself
+    "line_amm": ("line", [dict(kind="amm", nodes=[0, 1], scale=0.0005 * np.eye(3))], LINE_INITS),
     "line_slice_uni": ("line", [dict(kind="slice_uni", nodes=[0, 1], scale=[1.0, 1.0, 2.0], transform=1)], LINE_INITS),
     # SURVEY.md §8d config 2 scheme A (north_star "AMWG on seeds")
     "seeds_amwg": ("seeds", [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", nodes=[5], scale=0.01),

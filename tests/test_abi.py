@@ -1,0 +1,85 @@
+"""CPU tests of the boundary: libmambacuda.so builds for sm_100a, loads, exports every symbol include/mambacuda.h
+declares, fails loudly without a GPU, and the product never touches the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mambacuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for s in ["mcu_create", "mcu_set_data", "mcu_set_scheme", "mcu_set_inits", "mcu_run", "mcu_logpdf", "mcu_gradlogpdf",
+              "mcu_get_state", "mcu_set_state", "mcu_moments", "mcu_gelman", "mcu_summarystats", "mcu_set_rng_mode", "mcu_last_error", "mcu_destroy"]:
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(mcu_built):
+    L = ctypes.CDLL(mcu_built)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    assert not missing, missing
+    from mambacuda import _lib
+    assert sorted(_lib.SYMBOLS) == declared_symbols()
+    assert L.mcu_abi_version() == 1
+
+
+def test_library_contains_sm100a_code(mcu_built):
+    out = subprocess.run(["cuobjdump", "-lelf", mcu_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_block_desc_layout_matches_the_header():
+    from mambacuda._lib import BlockDesc
+    # int32 x 2, int32[8], int32 x 8, (pad), double x 4, pointer  — as laid out by a C compiler for mcu_block_desc
+    assert ctypes.sizeof(BlockDesc) == 4 * 2 + 4 * 8 + 4 * 8 + 8 * 4 + 8
+    assert BlockDesc.target.offset == 72 and BlockDesc.scale.offset == 104
+    src = f'#include <stddef.h>\n#include <stdio.h>\n#include "{ROOT}/include/mambacuda.h"\n' \
+          'int main(){printf("%zu %zu %zu", sizeof(mcu_block_desc), offsetof(mcu_block_desc, target), offsetof(mcu_block_desc, scale));return 0;}'
+    exe = os.path.join(ROOT, "mamba.jl_b200", "build", "abi_probe")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-o", exe], input=src, text=True, check=True)
+    assert subprocess.run([exe], capture_output=True, text=True).stdout.split() == ["112", "72", "104"]
+
+
+def test_no_cpu_fallback_without_a_device(mcu_built):
+    from mambacuda import _lib
+    from mambacuda.engine import Engine, MambaCudaError
+    L = _lib.lib()
+    if L.mcu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(MambaCudaError, match="no usable CUDA device"):
+        Engine("seeds", 4)
+
+
+def test_argument_validation_does_not_need_a_device(mcu_built):
+    from mambacuda import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.mcu_create(99, 4, 0, 0, 1, ctypes.byref(h)) == _lib.ERR_ARG
+    assert b"unknown template" in L.mcu_last_error(None)
+    assert L.mcu_create(1, 0, 0, 0, 1, ctypes.byref(h)) == _lib.ERR_ARG
+    assert L.mcu_kept(0, 2000, 1000, 10) == 100 and L.mcu_kept(0, 50, 11, 4) == 9 and L.mcu_kept(130, 170, 120, 3) == 57
+
+
+def test_product_never_touches_the_oracle():
+    # the oracle is test infrastructure: nothing under mamba.jl_b200/ or include/ may import, link or name it
+    bad = []
+    for base in ("mamba.jl_b200", "include"):
+        for root, _, files in os.walk(os.path.join(ROOT, base)):
+            if os.sep + "build" in root:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".jl")):
+                    txt = open(os.path.join(root, f), errors="ignore").read()
+                    if re.search(r"pyoracle|liboracle|oracle/|orc_[a-z]", txt):
+                        bad.append(os.path.join(root, f))
+    assert not bad, bad
