@@ -1,0 +1,209 @@
+## MambaCUDA.jl — Julia shim that routes Mamba's mcmc() through libmambacuda.so.
+##
+## NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia` (and the reference targets
+## Julia 0.5, src/Mamba.jl:52-185 uses `type` / `immutable` / `typealias`).  The same C ABI is exercised
+## from Python (mamba.jl_b200/mambacuda, tests/) — this file is the binding a Mamba maintainer adds.
+## Syntax follows the reference's Julia 0.5 dialect.
+##
+## What it replaces: mcmc_master!'s `pmap2(mcmc_worker!, lsts)` (src/model/mcmc.jl:36-59).  Everything
+## above that line — Model construction, setsamplers!, argument checks, the ModelChains result — stays
+## Mamba's own code.
+
+module MambaCUDA
+
+using Mamba
+import Mamba: Model, ModelChains, ModelState, Sampler, Chains,
+              AMWGTune, SliceTune, RWMTune, NUTSTune, HMCTune, AMMTune
+
+const libmambacuda = get(ENV, "LIBMAMBACUDA", "libmambacuda.so")
+
+const MCU_MAX_BLOCK_NODES = 8
+
+## mirror of `mcu_block_desc` (include/mambacuda.h); isbits so it can be passed in a Vector
+immutable BlockDesc
+  kind::Int32
+  n_nodes::Int32
+  nodes::NTuple{8, Int32}
+  transform::Int32
+  adapt::Int32
+  batchsize::Int32
+  proposal::Int32
+  L::Int32
+  grad::Int32
+  max_depth::Int32
+  n_scale::Int32
+  target::Float64
+  epsilon::Float64
+  beta::Float64
+  amm_scale::Float64
+  scale::Ptr{Float64}
+end
+
+## template library: node order of the state record (include/mambacuda.h, MCU_TPL_*)
+const TEMPLATES = Dict(
+  0 => [:beta, :s2],                                                      # doc/tutorial/line.jl
+  1 => [:alpha0, :alpha1, :alpha2, :alpha12, :s2, :b],                    # doc/examples/seeds.jl
+  2 => [:mu_alpha, :mu_beta, :s2_alpha, :s2_beta, :s2_c, :alpha, :beta],  # doc/examples/rats.jl
+  3 => [:alpha, :beta, :theta]                                            # doc/examples/pumps.jl
+)
+
+function check(h::Ptr{Void}, rc::Cint)
+  if rc != 0
+    msg = unsafe_string(ccall((:mcu_last_error, libmambacuda), Cstring, (Ptr{Void},), h))
+    rc == -1 ? throw(ArgumentError(msg)) :
+    rc == -2 ? throw(DimensionMismatch(msg)) : error("libmambacuda: $msg")
+  end
+end
+
+## A model matches a template when its unobserved stochastic nodes are exactly the template's nodes.
+## (The node closures themselves cannot be inspected; the caller asserts the template with `template=`
+## when the names alone are ambiguous.)
+function matchtemplate(m::Model)
+  sampled = Symbol[]
+  for s in m.samplers
+    append!(sampled, s.params)
+  end
+  for (id, nodes) in TEMPLATES
+    if Set(sampled) == Set(nodes)
+      return id
+    end
+  end
+  throw(ArgumentError("model does not match a device template (no CPU fallback)"))
+end
+
+adaptcode(a::Symbol) = a == :all ? 0 : a == :burnin ? 1 : 2
+
+## Build one descriptor from a Sampler produced by Mamba's own constructors.  The constructor
+## arguments live in the sampler closure (src/samplers/amwg.jl:52-59 etc.); the shim's versions of the
+## constructors below record them in `shimargs` keyed by the Sampler object.
+const shimargs = ObjectIdDict()
+
+function blockdesc(m::Model, s::Sampler, nodeids::Dict{Symbol, Int}, keep::Vector{Any})
+  a = get(shimargs, s, Dict{Symbol, Any}())
+  kind = isa(s.tune, AMWGTune) ? 0 :
+         isa(s.tune, SliceTune{Univariate}) ? 1 :
+         isa(s.tune, SliceTune{Multivariate}) ? 2 :
+         isa(s.tune, RWMTune) ? 3 :
+         isa(s.tune, NUTSTune) ? 4 :
+         isa(s.tune, HMCTune) ? 5 :
+         isa(s.tune, AMMTune) ? 6 :
+         throw(ArgumentError("sampler $(typeof(s.tune)) has no device implementation (no CPU fallback)"))
+  length(s.params) <= MCU_MAX_BLOCK_NODES || throw(ArgumentError("a block names at most 8 nodes"))
+  nodes = zeros(Int32, 8)
+  for (i, p) in enumerate(s.params)
+    nodes[i] = nodeids[p]
+  end
+  scale = Float64[]
+  if haskey(a, :scale)
+    scale = vec(convert(Array{Float64}, collect(a[:scale])))   # column-major for Sigma matrices
+    push!(keep, scale)
+  end
+  BlockDesc(kind, length(s.params), (nodes...),
+            Int32(get(a, :transform, kind in (1, 2) ? false : true)),
+            Int32(adaptcode(get(a, :adapt, :all))), Int32(get(a, :batchsize, 0)),
+            Int32(get(a, :proposal, 0)), Int32(get(a, :L, 0)),
+            Int32(get(a, :dtype, :analytic) == :forward ? 1 : get(a, :dtype, :analytic) == :central ? 2 : 0),
+            Int32(get(a, :max_depth, 0)), Int32(length(scale)),
+            Float64(get(a, :target, 0.0)), Float64(get(a, :epsilon, 0.0)),
+            Float64(get(a, :beta, 0.0)), Float64(get(a, :amm_scale, 0.0)),
+            isempty(scale) ? Ptr{Float64}(0) : pointer(scale))
+end
+
+## constructor wrappers: call Mamba's constructor, remember the arguments
+function AMWG(params, sigma; adapt::Symbol=:all, batchsize::Integer=50, target::Real=0.44)
+  s = Mamba.AMWG(params, sigma, adapt=adapt, batchsize=batchsize, target=target)
+  shimargs[s] = Dict(:scale => sigma, :adapt => adapt, :batchsize => batchsize, :target => target); s
+end
+function Slice(params, width, F=Multivariate; transform::Bool=false)
+  s = Mamba.Slice(params, width, F, transform=transform)
+  shimargs[s] = Dict(:scale => width, :transform => transform); s
+end
+function RWM(params, scale; proposal=Normal)
+  s = Mamba.RWM(params, scale, proposal=proposal)
+  code = proposal == Normal ? 0 : proposal == SymUniform ? 1 : proposal == SymTriangularDist ? 2 :
+         throw(ArgumentError("proposal $proposal has no device implementation"))
+  shimargs[s] = Dict(:scale => scale, :proposal => code); s
+end
+function NUTS(params; dtype::Symbol=:forward, target::Real=0.6, max_depth::Integer=10)
+  s = Mamba.NUTS(params, dtype=dtype, target=target)
+  shimargs[s] = Dict(:dtype => dtype, :target => target, :max_depth => max_depth); s
+end
+function HMC(params, epsilon::Real, L::Integer, Sigma=nothing; dtype::Symbol=:forward)
+  s = Sigma == nothing ? Mamba.HMC(params, epsilon, L, dtype=dtype) : Mamba.HMC(params, epsilon, L, Sigma, dtype=dtype)
+  d = Dict{Symbol, Any}(:epsilon => epsilon, :L => L, :dtype => dtype)
+  Sigma == nothing || (d[:scale] = Sigma)
+  shimargs[s] = d; s
+end
+function AMM(params, Sigma; adapt::Symbol=:all, beta::Real=0.05, scale::Real=2.38)
+  s = Mamba.AMM(params, Sigma, adapt=adapt, beta=beta, scale=scale)
+  shimargs[s] = Dict(:scale => Sigma, :adapt => adapt, :beta => beta, :amm_scale => scale); s
+end
+
+## mcmc(model, inputs, inits, iters; burnin, thin, chains): same signature, checks and result as
+## src/model/mcmc.jl:19-33; the chains x iterations loop is ONE call into the library.
+function mcmc(m::Model, inputs::Dict{Symbol}, inits::Vector{Dict{Symbol, Any}}, iters::Integer;
+              burnin::Integer=0, thin::Integer=1, chains::Integer=1, verbose::Bool=true,
+              seed::Integer=123, device::Integer=0, template::Integer=-1)
+  iters > burnin || throw(ArgumentError("burnin is greater than or equal to iters"))
+  length(inits) >= chains || throw(ArgumentError("fewer initial values than chains"))
+
+  mm = deepcopy(m)
+  setinputs!(mm, inputs)
+  setinits!(mm, inits[1:chains])          # validates the Dicts exactly as the reference does
+  mm.burnin = burnin
+
+  tid = template >= 0 ? template : matchtemplate(mm)
+  nodes = TEMPLATES[tid]
+  nodeids = Dict{Symbol, Int}([nodes[i] => i - 1 for i in 1:length(nodes)])
+
+  h = Ref{Ptr{Void}}(C_NULL)
+  rc = ccall((:mcu_create, libmambacuda), Cint, (Cint, Int64, Int64, Cint, UInt64, Ptr{Ptr{Void}}),
+             tid, chains, 0, device, seed, h)
+  rc == 0 || error(unsafe_string(ccall((:mcu_last_error, libmambacuda), Cstring, (Ptr{Void},), C_NULL)))
+  try
+    ## inputs (setinputs!, src/model/initialization.jl:30-40); integer data travel as Float64
+    for (key, value) in inputs
+      isa(value, AbstractArray) || continue
+      x = convert(Array{Float64}, value)
+      dims = Int64[size(x)...]
+      check(h[], ccall((:mcu_set_data, libmambacuda), Cint, (Ptr{Void}, Cstring, Cint, Ptr{Int64}, Ptr{Float64}),
+                       h[], string(key), length(dims), dims, x))
+    end
+    keep = Any[]
+    descs = BlockDesc[blockdesc(mm, s, nodeids, keep) for s in mm.samplers]
+    check(h[], ccall((:mcu_set_scheme, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{BlockDesc}), h[], length(descs), descs))
+
+    ## initial values → [D × chains] (record contiguous == column-major D × n)
+    D = Ref{Cint}(0); P = Ref{Cint}(0); NN = Ref{Cint}(0)
+    check(h[], ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), h[], D, P, NN))
+    x0 = Array{Float64}(D[], chains)
+    for k in 1:chains
+      x0[:, k] = vcat([vec(Float64[inits[k][key]...]) for key in nodes]...)
+    end
+    check(h[], ccall((:mcu_set_inits, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Int64, Float64), h[], x0, chains, 0.0))
+
+    kept = ccall((:mcu_kept, libmambacuda), Int64, (Int64, Int64, Int64, Int64), 0, iters, burnin, thin)
+    value = Array{Float64}(kept, P[], chains)          # == ModelChains.value layout, filled in place
+    check(h[], ccall((:mcu_run, libmambacuda), Cint, (Ptr{Void}, Int64, Int64, Int64, Ptr{Float64}, UInt32),
+                     h[], iters, burnin, thin, value, 0))
+
+    ## final ModelStates (mcmc.jl:56,82): values + tune records
+    nt = Ref{Int64}(0)
+    check(h[], ccall((:mcu_tune_size, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), h[], nt))
+    vals = Array{Float64}(D[], chains); tune = Array{Float64}(max(nt[], 1), chains); it = Ref{Int64}(0)
+    check(h[], ccall((:mcu_get_state, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                     h[], vals, tune, it))
+    mm.iter = it[]
+    mm.states = ModelState[ModelState(vals[:, k], Any[tune[:, k]]) for k in 1:chains]
+
+    buf = Vector{UInt8}(1 << 16)
+    ccall((:mcu_names, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{UInt8}, Csize_t), h[], 1, buf, length(buf))
+    pnames = split(unsafe_string(pointer(buf)), '\n')
+    sim = Chains(value, start=burnin + thin, thin=thin, names=AbstractString[pnames...])
+    return ModelChains(sim, mm)
+  finally
+    ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h[])
+  end
+end
+
+end # module

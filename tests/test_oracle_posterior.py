@@ -1,0 +1,71 @@
+"""Statistical pin of the oracle: posterior means of the reference's published runs (doc/*.rst tables; single
+MersenneTwister realisations that cannot be replayed) must be within 3 MCSE, MCSE = sqrt(ref^2 + ours^2)."""
+import numpy as np
+import pytest
+
+import helpers
+
+
+def within_3_mcse(ss, names, ref):
+    for nm, (mean, mcse_ref) in ref.items():
+        j = names.index(nm)
+        tol = 3.0 * np.hypot(mcse_ref, ss[j, 3])
+        assert abs(ss[j, 0] - mean) < tol, (nm, ss[j, 0], mean, tol)
+
+
+def test_line_standalone_amwg_slice(oracle):
+    # doc/examples/line_amwg_slice.jl:35-43, table doc/examples/line_amwg_slice.rst:26-31 (1 x 10,000)
+    ref = {"b0": (0.64401798, 0.060725564), "b1": (0.78985612, 0.017888106), "s2": (1.20785292, 0.062566344)}
+    outs = [oracle.standalone_line(4, 10000, 1000, seed=s) for s in range(8)]
+    c = np.stack(outs, axis=2)
+    ss = oracle.summarystats(c, 0, 100)
+    within_3_mcse(ss, ["b0", "b1", "s2"], ref)
+
+
+def test_line_standalone_nuts_and_slice(oracle):
+    # doc/samplers/nuts.jl:34-43 and doc/samplers/slice.jl:31-40: same posterior as the tutorial table
+    # (doc/tutorial.rst:432-436: beta1 0.5971 [0.0169], beta2 0.8017 [0.0048], s2 1.2204 [0.1018])
+    ref = {"b0": (0.5971183, 0.016925598), "b1": (0.8017036, 0.004793345), "s2": (1.2203777, 0.101798287)}
+    for which, n, burn in ((1, 5000, 1000), (2, 5000, 0), (3, 5000, 0)):
+        c = np.stack([oracle.standalone_line(which, n, burn, seed=s)[burn:] for s in range(4)], axis=2)
+        within_3_mcse(oracle.summarystats(c, 0, 100), ["b0", "b1", "s2"], ref)
+
+
+def test_line_model_based_nuts_slice(oracle):
+    # doc/tutorial/line.jl:48-49,99: scheme1 = [NUTS(:beta), Slice(:s2, 3.0)], 3 x 10,000, burnin 250, thin 2
+    ref = {"beta[1]": (0.5971183, 0.016925598), "beta[2]": (0.8017036, 0.004793345), "s2": (1.2203777, 0.101798287)}
+    tpl, blocks, inits = helpers.scheme("line_nuts_slice")
+    blocks = [dict(b, grad="forward") if b["kind"] == "nuts" else b for b in blocks]   # the reference differentiates numerically
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(6, inits, 10000, burnin=250, thin=2, seed=11, nthreads=6)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
+def test_seeds_reference_scheme(oracle):
+    # doc/examples/seeds.jl:69-75 (AMM + AMWG + AMWG, 2 x 12,500, burnin 2,500, thin 2), table doc/examples/seeds.rst:43-48
+    ref = {"alpha0": (-0.556154341, 0.0101730837), "alpha1": (0.088700176, 0.0128300598), "alpha2": (1.310728093, 0.0153996801),
+           "alpha12": (-0.746440855, 0.0251658152), "s2": (0.085705306, 0.0080848189)}
+    tpl, blocks, inits = helpers.scheme("seeds_amm")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 12500, burnin=2500, thin=2, seed=1, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
+def test_rats_reference_scheme(oracle):
+    # doc/examples/rats.jl:112-116 (intended run 2 x 10,000, burnin 2,500, thin 2), table doc/examples/rats.rst:42-46
+    ref = {"s2_c": (37.2543133, 0.2337982327), "mu_beta": (6.1830663, 0.0017921615), "alpha0": (106.6259925, 0.0526804390)}
+    tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=2, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
+def test_pumps_reference_scheme(oracle):
+    # doc/examples/pumps.jl:52-57 (2 x 10,000, burnin 2,500, thin 2), table doc/examples/pumps.rst:43-56
+    ref = {"beta": (0.93036099, 0.01824153419), "alpha": (0.69679849, 0.00722593007), "theta[1]": (0.05991674, 0.00032725274),
+           "theta[2]": (0.10125873, 0.00129985769), "theta[5]": (0.59971611, 0.00585119652), "theta[7]": (0.86767451, 0.02858200254),
+           "theta[9]": (1.55721556, 0.03109274798), "theta[10]": (1.98475207, 0.00912748779)}
+    tpl, blocks, inits = helpers.scheme("pumps_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=3, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
