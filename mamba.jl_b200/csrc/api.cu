@@ -59,6 +59,10 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  // GLM / NUTS tick engine buffers (glm_nuts.cu)
+  double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
+  int* g_nactive = nullptr; int g_nslab = 0;
+  long long ticks = 0;
 };
 
 namespace {
@@ -224,7 +228,13 @@ void free_scheme(mcu_ctx* h) {
   if (h->d_blocks) { cudaFree(h->d_blocks); h->d_blocks = nullptr; }
   h->h_blocks.clear();
 }
+void free_glm_buffers(mcu_ctx* h) {
+  cudaFree(h->g_sc); cudaFree(h->g_vec); cudaFree(h->g_req); cudaFree(h->g_lp); cudaFree(h->g_grad); cudaFree(h->g_part_lp); cudaFree(h->g_part_g);
+  cudaFree(h->g_nactive);
+  h->g_sc = h->g_vec = h->g_req = h->g_lp = h->g_grad = h->g_part_lp = h->g_part_g = nullptr; h->g_nactive = nullptr;
+}
 void free_chain_buffers(mcu_ctx* h) {
+  free_glm_buffers(h);
   cudaFree(h->d_state); cudaFree(h->d_tune); cudaFree(h->d_samples); cudaFree(h->d_mom); cudaFree(h->d_momn);
   h->d_state = h->d_tune = h->d_samples = h->d_mom = h->d_momn = nullptr;
   h->samples_cap = 0; h->samples_kept = 0;
@@ -270,6 +280,68 @@ bool scheme_is_seeds_fast(const mcu_ctx* h) {
   if ((int)h->inputs.at("r").size() != SeedsModel::NP) return false;
   for (const char* nm : {"x1", "x2"}) for (double v : h->inputs.at(nm)) if (v != 0.0 && v != 1.0) return false;   // 0/1 design → 4 group bases
   return true;
+}
+
+bool scheme_is_glm_tick(const mcu_ctx* h) {
+  if (h->tpl != MCU_TPL_GLM_LOGIT || h->h_blocks.size() != 1) return false;
+  const DevBlock& b = h->h_blocks[0];
+  return b.kind == MCU_NUTS && b.grad == MCU_GRAD_ANALYTIC && b.n_own == 1;
+}
+
+int ensure_glm_buffers(mcu_ctx* h) {
+  if (h->g_sc) return MCU_OK;
+  const size_t C = (size_t)h->C, d = (size_t)h->D;
+  const size_t nsc = glm_tick_scalar_slots(), nv = glm_tick_vector_slots();
+  long long nslab = (148LL * 512 + h->C - 1) / h->C;
+  const long long N = (long long)h->inputs["y"].size();
+  if (nslab > (N + 63) / 64) nslab = (N + 63) / 64;
+  if (nslab < 1) nslab = 1;
+  h->g_nslab = (int)nslab;
+  CK(cudaMalloc(&h->g_sc, sizeof(double) * nsc * C));
+  CK(cudaMalloc(&h->g_vec, sizeof(double) * nv * d * C));
+  CK(cudaMalloc(&h->g_req, sizeof(double) * d * C));
+  CK(cudaMalloc(&h->g_lp, sizeof(double) * C));
+  CK(cudaMalloc(&h->g_grad, sizeof(double) * d * C));
+  CK(cudaMalloc(&h->g_part_lp, sizeof(double) * nslab * C));
+  CK(cudaMalloc(&h->g_part_g, sizeof(double) * nslab * d * C));
+  CK(cudaMalloc(&h->g_nactive, sizeof(int)));
+  CK(cudaMemsetAsync(h->g_sc, 0, sizeof(double) * nsc * C, h->stream));
+  CK(cudaMemsetAsync(h->g_vec, 0, sizeof(double) * nv * d * C, h->stream));
+  CK(cudaMemsetAsync(h->g_req, 0, sizeof(double) * d * C, h->stream));
+  CK(cudaMemsetAsync(h->g_lp, 0, sizeof(double) * C, h->stream));
+  CK(cudaMemsetAsync(h->g_grad, 0, sizeof(double) * d * C, h->stream));
+  // resume point: every chain's own iteration counter starts at the handle's
+  if (h->iter > 0) {
+    std::vector<double> it(C, (double)h->iter);
+    CK(cudaMemcpyAsync(h->g_sc + 1 * C, it.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));   // slot 1 = SL_ITER
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return MCU_OK;
+}
+
+int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, const RunArgs& a) {
+  int rc = ensure_glm_buffers(h); if (rc) return rc;
+  const DevBlock& b = h->h_blocks[0];
+  GlmTick t;
+  t.C = h->C; t.chain_offset = h->chain_offset; t.seed = h->seed; t.target_iter = h->iter + iters; t.burnin = burnin; t.thin = thin;
+  t.row0 = a.row0; t.d = h->D;
+  t.max_depth = b.max_depth > 0 ? (b.max_depth < kMaxDepth ? b.max_depth : kMaxDepth) : kMaxDepth;
+  t.target = b.target; t.eps_desc = b.epsilon;
+  t.state = h->d_state; t.tune = h->d_tune + (size_t)b.tune_off * h->C; t.sc = h->g_sc; t.vec = h->g_vec; t.req = h->g_req;
+  t.lp = h->g_lp; t.grad = h->g_grad; t.samples = a.samples; t.mom = h->d_mom; t.momn = h->d_momn; t.n_active = h->g_nactive;
+  const int N = (int)h->inputs["y"].size();
+  while (true) {
+    CK(cudaMemsetAsync(h->g_nactive, 0, sizeof(int), h->stream));
+    glm_advance(t, h->stream); h->launches++;
+    int active = 0;
+    CK(cudaMemcpyAsync(&active, h->g_nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (active == 0) break;
+    glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
+                       h->g_lp, h->g_grad, h->stream);
+    h->launches += 3; h->ticks++;
+  }
+  return MCU_OK;
 }
 
 }  // namespace
@@ -470,6 +542,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   cudaFree(d_in);
   CK(cudaGetLastError());
   h->iter = 0; h->has_inits = true; h->samples_kept = 0;
+  free_glm_buffers(h);
   return MCU_OK;
 }
 
@@ -524,11 +597,17 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.mom = h->d_mom; a.momn = h->d_momn;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
   const bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   long long chunk = 256;
   if (const char* e = std::getenv("MCU_CHUNK_ITERS")) { long long v = std::atoll(e); if (v > 0) chunk = v; }
   if (fast) chunk = iters;   // the fused kernel keeps everything on chip for the whole call
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
+  if (glm_tick) {
+    rc = run_glm_tick(h, iters, burnin, thin, a);
+    if (rc) return rc;
+    done = iters;
+  }
   while (done < iters) {
     const long long n = std::min(chunk, iters - done);
     a.iter0 = h->iter + done; a.iters = n;
@@ -603,6 +682,7 @@ int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_
   }
   CK(cudaGetLastError());
   h->iter = iter; h->has_inits = true;
+  free_glm_buffers(h);
   return MCU_OK;
 }
 

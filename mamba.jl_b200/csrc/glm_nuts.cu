@@ -1,0 +1,341 @@
+// glm_nuts.cu — NUTS for the Bernoulli-logit GLM template at data sizes where one chain per thread cannot
+// evaluate the density (N = 10^6 rows): the "tick" engine of SURVEY.md §7 step 8.
+//
+// The reference runs, per chain, nuts_sub! → buildtree → leapfrog → logfgrad (src/samplers/nuts.jl:95-180),
+// one gradient after the other.  Here a gradient evaluation is a pass over X shared by ALL chains, so the
+// sampler of every chain is turned into a resumable state machine:
+//
+//     advance kernel (one thread per chain)  ── consumes the (logf, grad) it asked for, runs the NUTS
+//                                               bookkeeping up to its NEXT gradient request, writes the
+//                                               requested position
+//     gradient kernels (all chains at once)  ── logf and grad of the likelihood at every requested position
+//
+// One host-side loop alternates the two ("tick") until every chain has finished its iterations.  A chain
+// requests exactly the gradients the reference's recursion would (same leapfrogs, same uniforms in the same
+// post-order, same dual averaging, same nutsepsilon), so on the same Philox stream it follows the same
+// trajectory as the generic kernel and the oracle; chains sit at different tree depths / iterations in the
+// same tick.
+//
+// Chain-state layout: every vector is [d][C] (chain fastest); the per-level stack is [depth][d][C].
+#include "launch.hpp"
+
+namespace mcu {
+
+namespace {
+
+enum Phase { PH_BEGIN = 0, PH_EPS_INIT = 1, PH_EPS_TRIAL = 2, PH_START = 3, PH_LEAF = 4, PH_DONE = 5 };
+
+// scalar slots per chain (doubles)
+enum Slot {
+  SL_PHASE = 0, SL_ITER, SL_JDRAW, SL_LOGP0, SL_LOGU0, SL_N, SL_TN, SL_TS, SL_ALPHA, SL_NALPHA, SL_J, SL_T, SL_PM,
+  SL_EPS_USE, SL_EPS_TRY, SL_EPS_PM, SL_EPS_LOGF0, SL_EPS_D0, SL_EPS_GUARD, SL_SN0,   // SL_SN0 .. SL_SN0 + kMaxDepth - 1: stack n
+  SL_COUNT = SL_SN0 + kMaxDepth
+};
+// vector slots per chain (each d doubles)
+enum VSlot { V_CX = 0, V_CR, V_CG, V_XM, V_RM, V_GM, V_XP, V_RP, V_GP, V_TXF, V_TRF, V_TXP, V_SXF0,   // then 3 * kMaxDepth stack vectors
+             V_COUNT = V_SXF0 + 3 * kMaxDepth };
+
+struct GlmTickArgs {
+  long long C, chain_offset;
+  unsigned long long seed;
+  long long target_iter, burnin, thin, row0;
+  int d, max_depth;
+  double target, eps_desc;
+  double* state;     // [d][C] current sample v (the handle's state array)
+  double* tune;      // [8][C]  NUTS tune slots (samplers.cuh)
+  double* sc;        // [SL_COUNT][C]
+  double* vec;       // [V_COUNT][d][C]
+  double* req;       // [d][C] requested position
+  const double* lp;  // [C] likelihood logf at the requested position
+  const double* grad;// [d][C] likelihood gradient
+  double* samples; double* mom; double* momn;
+  int* n_active;
+};
+
+__global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const size_t C = (size_t)a.C;
+  const int d = a.d;
+#define SC(s) a.sc[(size_t)(s) * C + c]
+#define VV(v, i) a.vec[((size_t)(v) * d + (i)) * C + c]
+#define ST(i) a.state[(size_t)(i) * C + c]
+#define TN(s) a.tune[(size_t)(s) * C + c]
+#define REQ(i) a.req[(size_t)(i) * C + c]
+  int phase = (int)SC(SL_PHASE);
+  if (phase == PH_DONE && (long long)SC(SL_ITER) >= a.target_iter) { return; }
+  if (phase == PH_DONE) phase = PH_BEGIN;   // a later mcu_run continues the chain
+  Draws rng;
+  rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
+  rng.ext = nullptr; rng.ext_pos = nullptr; rng.ext_n = 0;
+  long long iter = (long long)SC(SL_ITER);
+  rng.seek((uint32_t)iter, 0, 0); rng.j = (uint32_t)SC(SL_JDRAW);
+
+  // pending result: full block density = MvNormal(d, sqrt(1000)) prior + likelihood (glm template, models.cuh)
+  double lp_full = 0.0;
+  auto load_result = [&](int vslot_g) {
+    double sq = 0.0; bool fin = true;
+    for (int i = 0; i < d; ++i) { const double b = REQ(i); sq += b * b; fin = fin && isfinite(b); }
+    const double prior = fin ? lp_isonormal(sq, (double)d, sqrt(1000.0)) : neg_inf();
+    lp_full = prior + a.lp[c];
+    for (int i = 0; i < d; ++i) {
+      double g = a.grad[(size_t)i * C + c] - REQ(i) / 1000.0;
+      if (!isfinite(g)) g = 0.0;                       // logpdfgrad!: sampler.jl:110
+      VV(vslot_g, i) = g;
+    }
+  };
+  auto dotv = [&](int vs) { double s = 0; for (int i = 0; i < d; ++i) { const double x = VV(vs, i); s += x * x; } return s; };
+  auto copyv = [&](int dst, int src) { for (int i = 0; i < d; ++i) VV(dst, i) = VV(src, i); };
+  auto nouturn = [&](int xminus, int xplus, int rminus, int rplus) {
+    double p = 0, q = 0;
+    for (int i = 0; i < d; ++i) { const double df = VV(xplus, i) - VV(xminus, i); p += df * VV(rminus, i); q += df * VV(rplus, i); }
+    return p >= 0 && q >= 0;
+  };
+  auto request_cx = [&]() { for (int i = 0; i < d; ++i) REQ(i) = VV(V_CX, i); };
+  // first half of a leapfrog from (cx, cr, cg): nuts.jl:130-131
+  auto half_step_and_request = [&](double eps) {
+    for (int i = 0; i < d; ++i) { const double r = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); VV(V_CR, i) = r; VV(V_CX, i) = VV(V_CX, i) + eps * r; }
+    request_cx();
+  };
+
+  bool need_grad = false;
+  while (!need_grad) {
+    switch (phase) {
+      case PH_BEGIN: {
+        if (iter >= a.target_iter) { phase = PH_DONE; for (int i = 0; i < d; ++i) REQ(i) = ST(i); need_grad = true; break; }
+        iter += 1; rng.seek((uint32_t)iter, 0, 0);
+        if (iter == 1) {   // NUTSTune(x, nutsepsilon(x, f)): nuts.jl:17-30
+          TN(0) = 0.0; TN(1) = 0.0; TN(3) = 1.0; TN(4) = 0.0; TN(5) = 0.0; TN(6) = CUDART_NAN; TN(7) = 0.0;
+          if (a.eps_desc > 0.0) { TN(2) = a.eps_desc; phase = PH_START; }
+          else {           // nutsepsilon: nuts.jl:192-205 — r0 = randn(n); leapfrog(x, r0, 0, 0)
+            for (int i = 0; i < d; ++i) { VV(V_RM, i) = rng.normal(); VV(V_CX, i) = ST(i); }
+            request_cx(); phase = PH_EPS_INIT; need_grad = true; break;
+          }
+        } else phase = PH_START;
+        if (phase == PH_START) {
+          // sample!(v, f, adapt): nuts.jl:63-81 up to nuts_sub!'s first gradient request
+          const bool adapt = iter <= a.burnin;
+          if (adapt && TN(0) == 0.0) { TN(5) = 0.0; TN(6) = log(10.0 * TN(2)); }
+          TN(0) = adapt ? 1.0 : 0.0;
+          if (adapt) TN(5) = TN(5) + 1.0; else if (TN(5) > 0.0) TN(2) = TN(3);
+          SC(SL_EPS_USE) = TN(2);
+          for (int i = 0; i < d; ++i) { VV(V_CR, i) = rng.normal(); VV(V_CX, i) = ST(i); VV(V_CG, i) = 0.0; }
+          request_cx(); need_grad = true;
+        }
+        break;
+      }
+      case PH_EPS_INIT: {   // (logf0, grad0) at x0 arrived; r0 sits in V_RM, grad0 goes to V_GM
+        load_result(V_GM);
+        SC(SL_EPS_LOGF0) = lp_full; SC(SL_EPS_D0) = dotv(V_RM);
+        SC(SL_EPS_TRY) = 1.0; SC(SL_EPS_PM) = 0.0; SC(SL_EPS_GUARD) = 0.0;
+        for (int i = 0; i < d; ++i) {   // trial leapfrog from (x0, r0, grad0) with eps = 1
+          const double r = VV(V_RM, i) + 0.5 * VV(V_GM, i);
+          VV(V_CR, i) = r; VV(V_CX, i) = ST(i) + 1.0 * r;
+        }
+        request_cx(); phase = PH_EPS_TRIAL; need_grad = true;
+        break;
+      }
+      case PH_EPS_TRIAL: {
+        load_result(V_CG);
+        double eps = SC(SL_EPS_TRY);
+        double dr = 0.0;
+        for (int i = 0; i < d; ++i) { const double r = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); dr += r * r; }
+        const double prob = exp(lp_full - SC(SL_EPS_LOGF0) - 0.5 * (dr - SC(SL_EPS_D0)));
+        double pm = SC(SL_EPS_PM);
+        if (pm == 0.0) { pm = prob > 0.5 ? 1.0 : -1.0; SC(SL_EPS_PM) = pm; }
+        const double guard = SC(SL_EPS_GUARD) + 1.0; SC(SL_EPS_GUARD) = guard;
+        if (pow(prob, pm) > pow(0.5, pm) && guard <= 2000.0) {
+          eps *= pm > 0 ? 2.0 : 0.5; SC(SL_EPS_TRY) = eps;
+          for (int i = 0; i < d; ++i) {
+            const double r = VV(V_RM, i) + (0.5 * eps) * VV(V_GM, i);
+            VV(V_CR, i) = r; VV(V_CX, i) = ST(i) + eps * r;
+          }
+          request_cx(); need_grad = true;
+        } else {
+          TN(2) = eps;
+          const bool adapt = iter <= a.burnin;
+          if (adapt && TN(0) == 0.0) { TN(5) = 0.0; TN(6) = log(10.0 * TN(2)); }
+          TN(0) = adapt ? 1.0 : 0.0;
+          if (adapt) TN(5) = TN(5) + 1.0; else if (TN(5) > 0.0) TN(2) = TN(3);
+          SC(SL_EPS_USE) = TN(2);
+          for (int i = 0; i < d; ++i) { VV(V_CR, i) = rng.normal(); VV(V_CX, i) = ST(i); VV(V_CG, i) = 0.0; }
+          request_cx(); phase = PH_START; need_grad = true;
+        }
+        break;
+      }
+      case PH_START: {   // nuts_sub!: nuts.jl:97-105 after the eps = 0 leapfrog
+        load_result(V_CG);
+        const double logp0 = lp_full - 0.5 * dotv(V_CR);
+        SC(SL_LOGP0) = logp0; SC(SL_LOGU0) = logp0 + log(rng.uniform());
+        copyv(V_XM, V_CX); copyv(V_XP, V_CX); copyv(V_RM, V_CR); copyv(V_RP, V_CR); copyv(V_GM, V_CG); copyv(V_GP, V_CG);
+        SC(SL_J) = 0.0; SC(SL_N) = 1.0;
+        // first doubling
+        const double pm = rng.uniform() > 0.5 ? 1.0 : -1.0;   // both edges equal the start point
+        SC(SL_PM) = pm; SC(SL_T) = 0.0; SC(SL_ALPHA) = 0.0; SC(SL_NALPHA) = 0.0;
+        half_step_and_request(pm * SC(SL_EPS_USE));
+        phase = PH_LEAF; need_grad = true;
+        break;
+      }
+      case PH_LEAF: {    // buildtree leaf (nuts.jl:142-152) + the unrolled merges (samplers.cuh nuts_sub)
+        load_result(V_CG);
+        const double pm = SC(SL_PM), eps = pm * SC(SL_EPS_USE);
+        for (int i = 0; i < d; ++i) VV(V_CR, i) = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i);
+        const double logu0 = SC(SL_LOGU0), logp0 = SC(SL_LOGP0);
+        const double logpp = lp_full - 0.5 * dotv(V_CR);
+        double Tn = logu0 < logpp ? 1.0 : 0.0;
+        bool Ts = logu0 < logpp + 1000.0;
+        SC(SL_ALPHA) = SC(SL_ALPHA) + fmin(1.0, exp(logpp - logp0));
+        SC(SL_NALPHA) = SC(SL_NALPHA) + 1.0;
+        copyv(V_TXF, V_CX); copyv(V_TRF, V_CR); copyv(V_TXP, V_CX);
+        const int j = (int)SC(SL_J); const unsigned t = (unsigned)SC(SL_T);
+        int l = 0;
+        bool parked = false;
+        while (l < j) {
+          const int sxf = V_SXF0 + 3 * l, srf = sxf + 1, sxp = sxf + 2;
+          if ((t >> l) & 1u) {
+            const double u = rng.uniform();
+            const double nA = SC(SL_SN0 + l);
+            if (!(u < Tn / (nA + Tn))) copyv(V_TXP, sxp);
+            Tn = nA + Tn;
+            const bool ok = pm > 0 ? nouturn(sxf, V_CX, srf, V_CR) : nouturn(V_CX, sxf, V_CR, srf);
+            Ts = Ts && ok;
+            copyv(V_TXF, sxf); copyv(V_TRF, srf);
+            ++l;
+          } else if (Ts) {
+            copyv(sxf, V_TXF); copyv(srf, V_TRF); copyv(sxp, V_TXP); SC(SL_SN0 + l) = Tn;
+            parked = true; break;
+          } else {
+            ++l;
+          }
+        }
+        if (parked) {      // build the sibling: next leaf
+          SC(SL_T) = (double)(t + 1);
+          half_step_and_request(eps);
+          need_grad = true;
+          break;
+        }
+        // tree of depth j complete (or failed): nuts.jl:108-123
+        if (pm < 0) { copyv(V_XM, V_CX); copyv(V_RM, V_CR); copyv(V_GM, V_CG); }
+        else { copyv(V_XP, V_CX); copyv(V_RP, V_CR); copyv(V_GP, V_CG); }
+        double n = SC(SL_N);
+        if (Ts) { if (rng.uniform() < Tn / n) for (int i = 0; i < d; ++i) ST(i) = VV(V_TXP, i); }
+        const int jn = j + 1;
+        n += Tn; SC(SL_N) = n; SC(SL_J) = (double)jn;
+        bool s = Ts && nouturn(V_XM, V_XP, V_RM, V_RP);
+        if (jn >= a.max_depth) s = false;
+        TN(1) = SC(SL_ALPHA); TN(7) = SC(SL_NALPHA);
+        if (s) {           // next doubling
+          const double pm2 = rng.uniform() > 0.5 ? 1.0 : -1.0;
+          SC(SL_PM) = pm2; SC(SL_T) = 0.0; SC(SL_ALPHA) = 0.0; SC(SL_NALPHA) = 0.0;
+          if (pm2 < 0) { copyv(V_CX, V_XM); copyv(V_CR, V_RM); copyv(V_CG, V_GM); }
+          else { copyv(V_CX, V_XP); copyv(V_CR, V_RP); copyv(V_CG, V_GP); }
+          half_step_and_request(pm2 * SC(SL_EPS_USE));
+          need_grad = true;
+          break;
+        }
+        // end of the iteration: dual averaging (nuts.jl:70-75), thinning (mcmc.jl:76-78)
+        if (TN(0) != 0.0) {
+          const double m = TN(5);
+          double p = 1.0 / (m + 10.0);
+          const double Hbar = (1.0 - p) * TN(4) + p * (a.target - TN(1) / TN(7));
+          TN(4) = Hbar;
+          const double e2 = exp(TN(6) - sqrt(m) * Hbar / 0.05);
+          TN(2) = e2;
+          p = pow(m, -0.75);
+          TN(3) = exp(p * log(e2) + (1.0 - p) * log(TN(3)));
+        }
+        if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {
+          const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
+          if (a.samples) for (int i = 0; i < d; ++i) a.samples[((size_t)row * d + i) * C + c] = ST(i);
+          // streaming moments, one column at a time (same update as engine.cuh moments_update)
+          const double nk = a.momn[c] + 1.0; a.momn[c] = nk;
+          double bc = a.momn[C + c] + 1.0; const bool bdone = bc >= (double)kBatch; double nb = a.momn[2 * C + c];
+          if (bdone) { bc = 0.0; nb += 1.0; a.momn[2 * C + c] = nb; }
+          a.momn[C + c] = bc;
+          for (int i = 0; i < d; ++i) {
+            double* q = a.mom + (size_t)i * kMomPerCol * C + c;
+            const double x = ST(i);
+            double mean = q[0], M2 = q[C]; double dl = x - mean; mean += dl / nk; M2 += dl * (x - mean); q[0] = mean; q[C] = M2;
+            const double lx = log(x); double lm = q[2 * C], lM2 = q[3 * C]; dl = lx - lm; lm += dl / nk; lM2 += dl * (lx - lm); q[2 * C] = lm; q[3 * C] = lM2;
+            q[4 * C] = nk == 1.0 ? x : fmin(q[4 * C], x); q[5 * C] = nk == 1.0 ? x : fmax(q[5 * C], x);
+            double bsum = q[6 * C] + x;
+            if (bdone) { const double bm = bsum / (double)kBatch; bsum = 0.0; double bmean = q[7 * C], bM2 = q[8 * C]; const double db = bm - bmean; bmean += db / nb; bM2 += db * (bm - bmean); q[7 * C] = bmean; q[8 * C] = bM2; }
+            q[6 * C] = bsum;
+          }
+        }
+        phase = PH_BEGIN;
+        break;
+      }
+      default: need_grad = true; break;
+    }
+  }
+  SC(SL_PHASE) = (double)phase; SC(SL_ITER) = (double)iter; SC(SL_JDRAW) = (double)rng.j;
+  if (phase != PH_DONE) atomicAdd(a.n_active, 1);
+#undef SC
+#undef VV
+#undef ST
+#undef TN
+#undef REQ
+}
+
+// ---- reference gradient kernel (FP64, CUDA cores): thread = (chain, row slab) ---------------------------
+// lik logf = sum_i [y_i log p_i + (1 - y_i) log(1 - p_i)], grad = X' (y - p), p = invlogit(X beta).
+// Deterministic: per-slab partials, then a fold over slabs.  This is the correctness path for the tick
+// engine; the tensor-core kernel (glm_tc.cu) replaces it for large N.
+template <int DMAX>
+__global__ void __launch_bounds__(128) glm_grad_ref_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d,
+                                                           long long C, const double* __restrict__ req, int rows_per_slab,
+                                                           double* __restrict__ part_lp /*[slab][C]*/, double* __restrict__ part_g /*[slab][d][C]*/) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = blockIdx.y;
+  if (c >= C) return;
+  double beta[DMAX], g[DMAX];
+  for (int j = 0; j < d; ++j) { beta[j] = req[(size_t)j * C + c]; g[j] = 0.0; }
+  double lp = 0.0;
+  const int i0 = slab * rows_per_slab, i1 = min(N, i0 + rows_per_slab);
+  for (int i = i0; i < i1; ++i) {
+    const double* xi = X + (size_t)i * d;
+    double eta = 0.0;
+    for (int j = 0; j < d; ++j) eta += xi[j] * beta[j];
+    const double p = 1.0 / (exp(-eta) + 1.0);
+    const double yi = y[i];
+    lp += yi == 0.0 ? log(1.0 - p) : log(p);
+    const double r = yi - p;
+    for (int j = 0; j < d; ++j) g[j] += r * xi[j];
+  }
+  part_lp[(size_t)slab * C + c] = lp;
+  for (int j = 0; j < d; ++j) part_g[((size_t)slab * d + j) * C + c] = g[j];
+}
+// out[i] = sum_s part[s][i]
+__global__ void glm_fold_kernel(const double* __restrict__ part, int nslab, long long width, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  double s = 0.0;
+  for (int k = 0; k < nslab; ++k) s += part[(size_t)k * width + i];
+  out[i] = s;
+}
+
+}  // namespace
+
+size_t glm_tick_scalar_slots() { return SL_COUNT; }
+size_t glm_tick_vector_slots() { return V_COUNT; }
+
+void glm_grad_reference(const double* X, const double* y, int N, int d, long long C, const double* req, int nslab,
+                        double* part_lp, double* part_g, double* lp, double* grad, cudaStream_t st) {
+  const int rows = (N + nslab - 1) / nslab;
+  dim3 grid((unsigned)((C + 127) / 128), (unsigned)nslab);
+  glm_grad_ref_kernel<kGlmDMax><<<grid, 128, 0, st>>>(X, y, N, d, C, req, rows, part_lp, part_g);
+  glm_fold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(part_lp, nslab, C, lp);
+  glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab, (long long)d * C, grad);
+}
+
+void glm_advance(const GlmTick& t, cudaStream_t st) {
+  GlmTickArgs a;
+  a.C = t.C; a.chain_offset = t.chain_offset; a.seed = t.seed; a.target_iter = t.target_iter; a.burnin = t.burnin; a.thin = t.thin;
+  a.row0 = t.row0; a.d = t.d; a.max_depth = t.max_depth; a.target = t.target; a.eps_desc = t.eps_desc;
+  a.state = t.state; a.tune = t.tune; a.sc = t.sc; a.vec = t.vec; a.req = t.req; a.lp = t.lp; a.grad = t.grad;
+  a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active;
+  glm_advance_kernel<<<(unsigned)((t.C + 127) / 128), 128, 0, st>>>(a);
+}
+
+}  // namespace mcu

@@ -45,4 +45,22 @@ double measure_fp64_peak_tflops(cudaStream_t st);
 // fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success
 int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
 
+
+// ---- GLM / NUTS tick engine (glm_nuts.cu) ----------------------------------------------------------------
+struct GlmTick {
+  long long C, chain_offset;
+  unsigned long long seed;
+  long long target_iter, burnin, thin, row0;
+  int d, max_depth;
+  double target, eps_desc;
+  double* state; double* tune; double* sc; double* vec; double* req; const double* lp; const double* grad;
+  double* samples; double* mom; double* momn;
+  int* n_active;
+};
+size_t glm_tick_scalar_slots();
+size_t glm_tick_vector_slots();
+void glm_advance(const GlmTick& t, cudaStream_t st);
+void glm_grad_reference(const double* X, const double* y, int N, int d, long long C, const double* req, int nslab,
+                        double* part_lp, double* part_g, double* lp, double* grad, cudaStream_t st);
+
 }  // namespace mcu

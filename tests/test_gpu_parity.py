@@ -331,3 +331,58 @@ def test_seeds_fast_posterior_within_3_mcse_of_reference(oracle):
         assert abs(ss[j, 0] - mean) < tol, (nm, ss[j, 0], mean, tol)
     psrf = eng.gelman(0.05, True)
     assert (psrf[:, 0] < 1.2).all()   # doc/tutorial.rst:321 rule of thumb
+
+
+# ---- GLM / NUTS tick engine (mamba.jl_b200/csrc/glm_nuts.cu) ------------------------------------------------
+def glm_pair(oracle, N, d, n_chains, seed):
+    from mambacuda.engine import Engine
+    X, y, _ = helpers.glm_data(N=N, d=d, seed=seed)
+    eng = Engine("glm", n_chains, seed=seed)
+    eng.set_data("X", X); eng.set_data("y", y)
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    orc = oracle.Oracle("glm", glm_d=d)
+    orc.set_data("X", X); orc.set_data("y", y)
+    orc.set_scheme([dict(kind=4, nodes=[0], max_depth=10)])
+    inits = 0.1 * np.random.default_rng(seed).normal(size=(n_chains, d))
+    return eng, orc, inits
+
+
+def test_glm_tick_engine_matches_generic_kernel_and_oracle(oracle):
+    # every chain is a resumable state machine fed by a shared gradient pass; it must request exactly the
+    # gradients the reference's recursion does (same draws, same post-order merges, same dual averaging)
+    eng, orc, inits = glm_pair(oracle, 400, 8, 32, seed=13)
+    eng.set_inits(inits)
+    out_t = eng.run(16, burnin=12, thin=1)                       # tick engine
+    st_t, tune_t, _ = eng.get_state()
+    eng.set_inits(inits)
+    out_g = eng.run(16, burnin=12, thin=1, force_generic=True)   # one chain per thread
+    st_g, tune_g, _ = eng.get_state()
+    out_o, st_o, tune_o = orc.run(32, inits, 16, burnin=12, thin=1, seed=13, nthreads=4)
+    assert_same_run((out_t, st_t, tune_t), (out_g, st_g, tune_g), rtol=1e-6, min_frac=0.9)
+    assert_same_run((out_t, st_t, tune_t), (out_o, st_o, tune_o), rtol=1e-5, min_frac=0.9)
+    assert tune_t[:, 7].max() >= 4                               # trees deeper than one doubling
+
+
+def test_glm_tick_engine_fixed_stepsize_and_restart(oracle):
+    eng, orc, inits = glm_pair(oracle, 300, 6, 16, seed=17)
+    eng.set_inits(inits)
+    full = eng.run(40, burnin=0, thin=2)
+    out_o, st_o, tune_o = orc.run(16, inits, 40, burnin=0, thin=2, seed=17, nthreads=4)
+    st, tune, _ = eng.get_state()
+    assert_same_run((full, st, tune), (out_o, st_o, tune_o), rtol=1e-6, min_frac=0.85)
+    eng.set_inits(inits)
+    p1 = eng.run(14, burnin=0, thin=2); p2 = eng.run(26, burnin=0, thin=2)
+    np.testing.assert_allclose(np.concatenate([p1, p2], axis=0), full, rtol=1e-12)
+
+
+def test_glm_posterior_recovers_coefficients(oracle):
+    from mambacuda.engine import Engine
+    X, y, beta = helpers.glm_data(N=4000, d=6, seed=5)
+    eng = Engine("glm", 128, seed=1)
+    eng.set_data("X", X); eng.set_data("y", y)
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    eng.set_inits(np.zeros((1, 6)), jitter_sd=0.1)
+    out = eng.run(300, burnin=150, thin=1)
+    mean = out.mean(axis=(0, 2)); sd = out.std(axis=(0, 2))
+    assert np.all(np.abs(mean - beta) < 5 * sd)
+    assert (eng.gelman(0.05, False)[:, 0] < 1.1).all()
