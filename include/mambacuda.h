@@ -77,6 +77,7 @@ enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1 };                                  
 /* mcu_run flags */
 #define MCU_RUN_NO_STORE 1u     /* do not keep thinned samples on the device, only streaming moments */
 #define MCU_RUN_FORCE_GENERIC 2u /* never dispatch to a specialised (fused) kernel */
+#define MCU_RUN_GLM_REFERENCE 4u /* GLM/NUTS tick engine: use the FP64 CUDA-core gradient kernel instead of the tensor-core one */
 
 #define MCU_MAX_BLOCK_NODES 8
 
@@ -161,6 +162,14 @@ int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const do
 /* logpdfgrad!(block, x, dtype)  src/samplers/sampler.jl:106-111 (+ analytic mode).  g [B × k]. */
 int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const double* state,
                    const double* x, double* lp, double* g);
+
+/* Likelihood part of the GLM block density for ALL chains of the handle in one pass over X (the kernels behind the
+ * GLM/NUTS tick engine): beta [n_chains × d] → lp [n_chains] = Σ_i log Bernoulli(y_i; invlogit(x_i·beta)),
+ * grad [n_chains × d] = X'(y − p).  impl 0 = FP64 CUDA-core reference kernel, 1 = fused tcgen05 tensor-core kernel
+ * (split-fp16 operands, FP32 accumulation; agrees with impl 0 to ~1e-6 relative).  Device time of the pass is
+ * then available from mcu_last_kernel_ms.  (Replaces d+2 interpreted model evaluations per gradient:
+ * src/model/simulation.jl:47-51, src/samplers/sampler.jl:106-111.)                                        */
+int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, double* grad);
 
 /* ---- diagnostics on the way out ------------------------------------------------------------- */
 /* All streaming statistics cover the samples kept since the last mcu_set_inits.  They are held

@@ -62,6 +62,7 @@ struct mcu_ctx {
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
   int* g_nactive = nullptr; int g_nslab = 0;
+  unsigned char* g_blob = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
 };
 
@@ -230,7 +231,7 @@ void free_scheme(mcu_ctx* h) {
 }
 void free_glm_buffers(mcu_ctx* h) {
   cudaFree(h->g_sc); cudaFree(h->g_vec); cudaFree(h->g_req); cudaFree(h->g_lp); cudaFree(h->g_grad); cudaFree(h->g_part_lp); cudaFree(h->g_part_g);
-  cudaFree(h->g_nactive);
+  cudaFree(h->g_nactive); cudaFree(h->g_blob); h->g_blob = nullptr;
   h->g_sc = h->g_vec = h->g_req = h->g_lp = h->g_grad = h->g_part_lp = h->g_part_g = nullptr; h->g_nactive = nullptr;
 }
 void free_chain_buffers(mcu_ctx* h) {
@@ -297,6 +298,14 @@ int ensure_glm_buffers(mcu_ctx* h) {
   if (nslab > (N + 63) / 64) nslab = (N + 63) / 64;
   if (nslab < 1) nslab = 1;
   h->g_nslab = (int)nslab;
+  {
+    const long long groups = (h->C + 127) / 128;
+    long long ns = 148 / groups; if (ns < 1) ns = 1;
+    const long long NT = glm_tc_num_tiles(N); if (ns > NT) ns = NT;
+    h->g_nslab_tc = (int)ns;
+    if (ns > nslab) nslab = ns;
+  }
+  if (const char* e = std::getenv("MCU_GLM_IMPL")) h->glm_impl = std::atoi(e);
   CK(cudaMalloc(&h->g_sc, sizeof(double) * nsc * C));
   CK(cudaMalloc(&h->g_vec, sizeof(double) * nv * d * C));
   CK(cudaMalloc(&h->g_req, sizeof(double) * d * C));
@@ -305,6 +314,11 @@ int ensure_glm_buffers(mcu_ctx* h) {
   CK(cudaMalloc(&h->g_part_lp, sizeof(double) * nslab * C));
   CK(cudaMalloc(&h->g_part_g, sizeof(double) * nslab * d * C));
   CK(cudaMalloc(&h->g_nactive, sizeof(int)));
+  {
+    const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
+    CK(cudaMalloc(&h->g_blob, blob_bytes));
+    glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, h->g_blob, h->stream); h->launches++;
+  }
   CK(cudaMemsetAsync(h->g_sc, 0, sizeof(double) * nsc * C, h->stream));
   CK(cudaMemsetAsync(h->g_vec, 0, sizeof(double) * nv * d * C, h->stream));
   CK(cudaMemsetAsync(h->g_req, 0, sizeof(double) * d * C, h->stream));
@@ -316,6 +330,19 @@ int ensure_glm_buffers(mcu_ctx* h) {
     CK(cudaMemcpyAsync(h->g_sc + 1 * C, it.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));   // slot 1 = SL_ITER
     CK(cudaStreamSynchronize(h->stream));
   }
+  return MCU_OK;
+}
+
+int glm_gradient_dispatch(mcu_ctx* h, int N) {
+  if (h->glm_impl == 1) {
+    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, h->g_part_g, h->stream) != 0)
+      return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
+    glm_fold(h->g_part_lp, h->g_part_g, h->g_nslab_tc, h->D, h->C, h->g_lp, h->g_grad, h->stream);
+  } else {
+    glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
+                       h->g_lp, h->g_grad, h->stream);
+  }
+  h->launches += 3;
   return MCU_OK;
 }
 
@@ -337,9 +364,9 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
     CK(cudaMemcpyAsync(&active, h->g_nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (active == 0) break;
-    glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
-                       h->g_lp, h->g_grad, h->stream);
-    h->launches += 3; h->ticks++;
+    { const int saved = h->glm_impl; if (h->glm_impl_run == 0) h->glm_impl = 0; rc = glm_gradient_dispatch(h, N); h->glm_impl = saved; }
+    if (rc) return rc;
+    h->ticks++;
   }
   return MCU_OK;
 }
@@ -604,6 +631,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   if (glm_tick) {
+    if (flags & MCU_RUN_GLM_REFERENCE) h->glm_impl_run = 0; else h->glm_impl_run = 1;
     rc = run_glm_tick(h, iters, burnin, thin, a);
     if (rc) return rc;
     done = iters;
@@ -877,6 +905,33 @@ double mcu_fp64_peak_tflops(mcu_handle h) {
   h->launches += 6;
   return measure_fp64_peak_tflops(h->stream);
 }
+int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, double* grad) {
+  if (!h || !beta || !lp || !grad) return h ? fail(h, MCU_ERR_ARG, "NULL argument") : MCU_ERR_ARG;
+  if (h->tpl != MCU_TPL_GLM_LOGIT || h->glm_d == 0) return fail(h, MCU_ERR_STATE, "GLM template with inputs X, y required");
+  if (impl != 0 && impl != 1) return fail(h, MCU_ERR_ARG, "impl must be 0 (reference) or 1 (tensor core)");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  rc = ensure_glm_buffers(h); if (rc) return rc;
+  const size_t C = (size_t)h->C; const int d = h->D; const int N = (int)h->inputs["y"].size();
+  double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * d));
+  CK(cudaMemcpyAsync(tmp, beta, sizeof(double) * C * d, cudaMemcpyHostToDevice, h->stream));
+  launch_records_to_soa(tmp, h->g_req, h->C, d, h->stream); h->launches++;
+  const int saved = h->glm_impl; h->glm_impl = impl;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  rc = glm_gradient_dispatch(h, N);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->glm_impl = saved;
+  if (rc) { cudaFree(tmp); return rc; }
+  launch_soa_to_records(h->g_grad, tmp, h->C, d, h->stream); h->launches++;
+  CK(cudaMemcpyAsync(grad, tmp, sizeof(double) * C * d, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(lp, h->g_lp, sizeof(double) * C, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  CK(cudaGetLastError());
+  float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
+  return MCU_OK;
+}
+
 int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
 double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }
 

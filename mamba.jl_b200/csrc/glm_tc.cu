@@ -1,0 +1,325 @@
+// glm_tc.cu — tensor-core likelihood/gradient kernel for the Bernoulli-logit GLM template (sm_100a only).
+//
+// For every chain c of the handle and the requested position beta_c (req [d][C]):
+//     eta = X beta_c,   logf_c = sum_i [y_i eta_i - softplus(eta_i)],   grad_c = X' (y - invlogit(eta))
+// i.e. the likelihood part of logpdf!/gradlogpdf! of the GLM block (the reference would run d+2 interpreted
+// model evaluations per gradient: src/model/simulation.jl:47-51, src/samplers/sampler.jl:106-111).
+//
+// One CTA owns 128 chains (UMMA M = 128) and a slab of 128-row tiles of X, and per tile runs the
+// FlashAttention-shaped chain   S = Theta X_t'  →  elementwise  →  G += R X_t   entirely on chip:
+//   GEMM1  D1[128 chains x 128 rows]  = Theta[128 x d] . X_t'          tcgen05.mma, A and B from shared memory
+//   epilogue (4 warps, thread = chain = TMEM lane): tcgen05.ld D1, p = invlogit(eta), logf += y eta - softplus,
+//            R = y - p written back to TENSOR MEMORY as fp16 (tcgen05.st)
+//   GEMM2  G[128 chains x d]        += R[128 x 128 rows] . X_t         tcgen05.mma, A from TMEM, B = the same
+//            shared-memory tile read MN-major; the accumulator G stays in TMEM across the whole slab
+// eta never leaves the SM; X is read from HBM once per chain group (bulk-copied tile by tile with
+// cp.async.bulk + mbarrier, double buffered).
+//
+// Precision: operands are split fp16 pairs (x = hi + lo, |lo| <= 2^-11 |hi|) and every product is formed
+// as hi*hi + hi*lo + lo*hi with FP32 accumulation (dropped term 2^-22 relative), so eta and the gradient
+// carry ~1e-6 relative error — inside north_star's 1e-5 — at 1/3 of the fp16 tensor peak.
+// Per-slab partials are written as FP64 and folded deterministically (glm_nuts.cu: glm_fold_kernel).
+//
+// Shared-memory operand layout: un-swizzled UMMA "interleave" core matrices (8 rows x 16 bytes, 128 bytes
+// contiguous), core matrices ordered [row-block][col-block].  X is pre-packed in HBM in exactly this order,
+// so a tile is one contiguous bulk copy, and the SAME bytes serve GEMM1 (K-major: SBO = row-block stride,
+// LBO = 128) and GEMM2 (MN-major: SBO = 128, LBO = row-block stride).
+#include <cuda_fp16.h>
+
+#include "launch.hpp"
+
+namespace mcu {
+
+namespace {
+
+constexpr int TM = 128;   // chains per CTA
+constexpr int TR = 128;   // data rows per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// UMMA shared-memory descriptor, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  return d;                 // layout_type (bits 61-63) = 0: no swizzle
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_half2(__half lo, __half hi) {
+  return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+}
+
+// ---- X pre-pack: fp64 [N x d] row-major → per tile [hi | lo | y] ----------------------------------------
+// hi/lo blocks: core matrices (8 rows x 8 cols fp16 = 128 B) ordered [row-block][col-block].
+__global__ void glm_pack_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d, int DP,
+                                unsigned char* __restrict__ blob, size_t tile_bytes) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over tiles * TR * (DP/8) 16-byte chunks
+  const int CB = DP / 8;
+  const long long chunks_per_tile = (long long)TR * CB;
+  const long long NT = (N + TR - 1) / TR;
+  if (idx >= NT * chunks_per_tile) return;
+  const long long t = idx / chunks_per_tile;
+  const int rem = (int)(idx % chunks_per_tile);
+  const int row = rem / CB, cb = rem % CB;
+  const long long grow = t * TR + row;
+  __half hi[8], lo[8];
+  for (int e = 0; e < 8; ++e) {
+    const int col = cb * 8 + e;
+    const float x = (grow < N && col < d) ? (float)X[(size_t)grow * d + col] : 0.0f;
+    hi[e] = __float2half_rn(x);
+    lo[e] = __float2half_rn(x - __half2float(hi[e]));
+  }
+  unsigned char* tile = blob + (size_t)t * tile_bytes;
+  const size_t off = ((size_t)(row / 8) * CB + cb) * 128 + (size_t)(row % 8) * 16;
+  uint4 vh, vl;
+  vh.x = pack_half2(hi[0], hi[1]); vh.y = pack_half2(hi[2], hi[3]); vh.z = pack_half2(hi[4], hi[5]); vh.w = pack_half2(hi[6], hi[7]);
+  vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
+  *reinterpret_cast<uint4*>(tile + off) = vh;
+  *reinterpret_cast<uint4*>(tile + (size_t)TR * DP * 2 + off) = vl;
+  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)y[grow] : -1.0f;   // -1 marks padding rows
+}
+
+struct TcArgs {
+  const unsigned char* blob; size_t tile_bytes;
+  int NT, tiles_per_slab, d, DP;
+  long long C;
+  const double* req;         // [d][C]
+  double* part_lp;           // [nslab][C]
+  double* part_g;            // [nslab][d][C]
+};
+
+__global__ void __launch_bounds__(128, 1) glm_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int DP = a.DP, CB = DP / 8;
+  const uint32_t op_bytes = (uint32_t)TM * DP * 2;          // one 128 x DP fp16 operand block
+  const uint32_t tile_bytes = (uint32_t)a.tile_bytes;       // hi | lo | y
+  unsigned char* xbuf0 = smem;
+  unsigned char* xbuf1 = smem + tile_bytes;
+  unsigned char* th_hi = smem + 2 * tile_bytes;
+  unsigned char* th_lo = th_hi + op_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(th_lo + op_bytes);   // [0],[1]: tile landed; [2]: MMA done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const long long c = (long long)blockIdx.x * TM + tid;     // this thread's chain
+  const int slab = blockIdx.y;
+  const int t0 = slab * a.tiles_per_slab, t1 = min(a.NT, t0 + a.tiles_per_slab);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Theta tile: this thread's chain is row `tid`; split fp16, blocked core-matrix layout, zero padded
+  for (int cb = 0; cb < CB; ++cb) {
+    __half hi[8], lo[8];
+    for (int e = 0; e < 8; ++e) {
+      const int col = cb * 8 + e;
+      const float x = (c < a.C && col < a.d) ? (float)a.req[(size_t)col * a.C + c] : 0.0f;
+      hi[e] = __float2half_rn(x);
+      lo[e] = __float2half_rn(x - __half2float(hi[e]));
+    }
+    const size_t off = ((size_t)(tid / 8) * CB + cb) * 128 + (size_t)(tid % 8) * 16;
+    uint4 vh, vl;
+    vh.x = pack_half2(hi[0], hi[1]); vh.y = pack_half2(hi[2], hi[3]); vh.z = pack_half2(hi[4], hi[5]); vh.w = pack_half2(hi[6], hi[7]);
+    vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(th_hi + off) = vh;
+    *reinterpret_cast<uint4*>(th_lo + off) = vl;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes → visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_d1 = tmem, tm_rh = tmem + 128, tm_rl = tmem + 192, tm_g = tmem + 256;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+  // instruction descriptors (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): F16 x F16 → F32, M = 128
+  const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);                 // N = 128, A/B K-major
+  const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(DP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);     // N = DP, B MN-major
+  const uint32_t rb_stride = (uint32_t)CB * 128;   // bytes between 8-row blocks
+
+  if (tid == 0 && t0 < t1) {
+    mbar_expect_tx(smem_u32(&bars[0]), tile_bytes);
+    bulk_copy_g2s(smem_u32(xbuf0), a.blob + (size_t)t0 * a.tile_bytes, tile_bytes, smem_u32(&bars[0]));
+  }
+  double lp_acc = 0.0;
+  uint32_t mma_phase = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    unsigned char* xb = buf ? xbuf1 : xbuf0;
+    if (tid == 0 && t + 1 < t1) {   // prefetch the next tile into the other buffer (its last reader, GEMM2 of t-1, has completed)
+      mbar_expect_tx(smem_u32(&bars[buf ^ 1]), tile_bytes);
+      bulk_copy_g2s(smem_u32(buf ? xbuf0 : xbuf1), a.blob + (size_t)(t + 1) * a.tile_bytes, tile_bytes, smem_u32(&bars[buf ^ 1]));
+    }
+    mbar_wait(smem_u32(&bars[buf]), (uint32_t)(((t - t0) >> 1) & 1));
+    // ---- GEMM1: D1 = Theta . X_t'  (3 split products per 16-wide K step)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t xh = smem_u32(xb), xl = xh + op_bytes, ah = smem_u32(th_hi), al = smem_u32(th_lo);
+      for (int k = 0; k < DP / 16; ++k) {
+        const uint32_t ko = (uint32_t)k * 256;   // two col-blocks per K step
+        const uint64_t dah = make_desc(ah + ko, 128, rb_stride), dal = make_desc(al + ko, 128, rb_stride);
+        const uint64_t dbh = make_desc(xh + ko, 128, rb_stride), dbl = make_desc(xl + ko, 128, rb_stride);
+        mma_ss(tm_d1, dah, dbh, idesc1, k > 0 ? 1u : 0u);
+        mma_ss(tm_d1, dah, dbl, idesc1, 1u);
+        mma_ss(tm_d1, dal, dbh, idesc1, 1u);
+      }
+      tc_commit(smem_u32(&bars[2]));
+    }
+    mbar_wait(smem_u32(&bars[2]), mma_phase); mma_phase ^= 1u;
+    tc_fence_after();
+    // ---- epilogue: thread = chain (TMEM lane), columns = the tile's 128 data rows
+    const float* ytile = reinterpret_cast<const float*>(xb + 2 * op_bytes);
+    float lp_tile = 0.0f;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[32];
+      tmem_ld32(tm_d1 + lane_off + (uint32_t)q * 32, v);
+      tmem_wait_ld();
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float r2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float eta = __uint_as_float(v[e + u]);
+          const float yv = ytile[q * 32 + e + u];
+          const float ex = __expf(-fabsf(eta));
+          const float s = __fdividef(1.0f, 1.0f + ex);
+          const float p = eta >= 0.0f ? s : ex * s;
+          const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + ex);
+          const bool valid = yv >= 0.0f;
+          lp_tile += valid ? (yv * eta - sp) : 0.0f;
+          r2[u] = valid ? (yv - p) : 0.0f;
+        }
+        const __half h0 = __float2half_rn(r2[0]), h1 = __float2half_rn(r2[1]);
+        ph[e >> 1] = pack_half2(h0, h1);
+        pl[e >> 1] = pack_half2(__float2half_rn(r2[0] - __half2float(h0)), __float2half_rn(r2[1] - __half2float(h1)));
+      }
+      tmem_st16(tm_rh + lane_off + (uint32_t)q * 16, ph);
+      tmem_st16(tm_rl + lane_off + (uint32_t)q * 16, pl);
+    }
+    lp_acc += (double)lp_tile;
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    // ---- GEMM2: G += R . X_t  (A = R from tensor memory, B = the X tile read MN-major)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t xh = smem_u32(xb), xl = xh + op_bytes;
+      for (int kk = 0; kk < TR / 16; ++kk) {
+        const uint32_t ko = (uint32_t)kk * 2 * rb_stride;   // two row-blocks per K step
+        const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
+        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, (t > t0 || kk > 0) ? 1u : 0u);
+        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
+        mma_ts(tm_g, tm_rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
+      }
+      tc_commit(smem_u32(&bars[2]));
+    }
+    mbar_wait(smem_u32(&bars[2]), mma_phase); mma_phase ^= 1u;
+    tc_fence_after();
+  }
+  // ---- write this slab's partials
+  if (c < a.C) a.part_lp[(size_t)slab * a.C + c] = lp_acc;
+  for (int j0 = 0; j0 < DP; j0 += 16) {
+    uint32_t v[16];
+    if (t0 < t1) { tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld(); }
+    else { for (int e = 0; e < 16; ++e) v[e] = 0u; }
+    if (c < a.C)
+      for (int e = 0; e < 16; ++e)
+        if (j0 + e < a.d) a.part_g[((size_t)slab * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+}  // namespace
+
+size_t glm_tc_tile_bytes(int d) { const int DP = (d + 15) / 16 * 16; return (size_t)2 * TR * DP * 2 + TR * sizeof(float); }
+long long glm_tc_num_tiles(long long N) { return (N + TR - 1) / TR; }
+
+void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* blob, cudaStream_t st) {
+  const int DP = (d + 15) / 16 * 16;
+  const long long total = glm_tc_num_tiles(N) * TR * (DP / 8);
+  glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, blob, glm_tc_tile_bytes(d));
+}
+
+// Returns 0 on success.  part_lp [nslab][C], part_g [nslab][d][C] (FP64), to be folded over slabs.
+int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
+                  double* part_lp, double* part_g, cudaStream_t st) {
+  TcArgs a;
+  a.DP = (d + 15) / 16 * 16;
+  a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
+  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 64;
+  if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);
+  glm_tc_kernel<<<grid, 128, smem, st>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mcu

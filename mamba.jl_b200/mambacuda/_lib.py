@@ -16,7 +16,7 @@ KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc":
 ADAPT = {"all": 0, "burnin": 1, "none": 2}
 PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2}
 GRAD = {"analytic": 0, "forward": 1, "central": 2}
-RUN_NO_STORE, RUN_FORCE_GENERIC = 1, 2
+RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE = 1, 2, 4
 
 
 class BlockDesc(C.Structure):
@@ -43,7 +43,7 @@ _lib = None
 SYMBOLS = [
     "mcu_create", "mcu_destroy", "mcu_last_error", "mcu_abi_version", "mcu_set_data", "mcu_set_scheme",
     "mcu_dims", "mcu_names", "mcu_tune_size", "mcu_set_inits", "mcu_run", "mcu_kept", "mcu_get_state",
-    "mcu_set_state", "mcu_logpdf", "mcu_gradlogpdf", "mcu_minmax", "mcu_link_codes", "mcu_moments",
+    "mcu_set_state", "mcu_logpdf", "mcu_gradlogpdf", "mcu_glm_gradient", "mcu_minmax", "mcu_link_codes", "mcu_moments",
     "mcu_gelman_from_moments", "mcu_gelman", "mcu_summarystats", "mcu_summary_sums",
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
@@ -78,6 +78,7 @@ def lib():
     L.mcu_set_state.argtypes = [vp, dp, dp, i64]
     L.mcu_logpdf.argtypes = [vp, C.c_int, i64, dp, dp, dp]
     L.mcu_gradlogpdf.argtypes = [vp, C.c_int, C.c_int, i64, dp, dp, dp, dp]
+    L.mcu_glm_gradient.argtypes = [vp, C.c_int, dp, dp, dp]
     L.mcu_minmax.argtypes = [vp, dp]
     L.mcu_link_codes.argtypes = [vp, C.c_int, dp, ip]
     L.mcu_moments.argtypes = [vp, ip, dp, dp, C.POINTER(i64)]

@@ -116,12 +116,13 @@ class Engine:
     def kept(self, first_iter, iters, burnin, thin):
         return self.L.mcu_kept(first_iter, iters, burnin, thin)
 
-    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False):
+    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False):
         """Returns the [kept × p × chains] block (Fortran order) or None when out=False."""
         _, p, _ = self.dims()
         it0 = self.iter()
         kept = self.kept(it0, iters, burnin, thin)
-        flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0)
+        flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0) | \
+            (_lib.RUN_GLM_REFERENCE if glm_reference else 0)
         arr = None
         if out:
             arr = np.full((kept, p, self.n_chains), np.nan, order="F")
@@ -170,6 +171,14 @@ class Engine:
         g = np.empty((state.shape[0], k))
         m = _lib.GRAD[mode] if isinstance(mode, str) else int(mode)
         self._chk(self.L.mcu_gradlogpdf(self.h, block, m, state.shape[0], _dp(state), _dp(x), _dp(lp), _dp(g)))
+        return lp, g
+
+    def glm_gradient(self, beta, impl=1):
+        """Likelihood logf and gradient of the GLM template for all chains in one pass over X."""
+        beta = _f64(np.atleast_2d(beta))
+        assert beta.shape[0] == self.n_chains
+        lp = np.empty(self.n_chains); g = np.empty_like(beta)
+        self._chk(self.L.mcu_glm_gradient(self.h, int(impl), _dp(beta), _dp(lp), _dp(g)))
         return lp, g
 
     # ---- diagnostics -------------------------------------------------------------------------

@@ -352,7 +352,7 @@ def test_glm_tick_engine_matches_generic_kernel_and_oracle(oracle):
     # gradients the reference's recursion does (same draws, same post-order merges, same dual averaging)
     eng, orc, inits = glm_pair(oracle, 400, 8, 32, seed=13)
     eng.set_inits(inits)
-    out_t = eng.run(16, burnin=12, thin=1)                       # tick engine
+    out_t = eng.run(16, burnin=12, thin=1, glm_reference=True)   # tick engine, FP64 gradient kernel
     st_t, tune_t, _ = eng.get_state()
     eng.set_inits(inits)
     out_g = eng.run(16, burnin=12, thin=1, force_generic=True)   # one chain per thread
@@ -366,12 +366,12 @@ def test_glm_tick_engine_matches_generic_kernel_and_oracle(oracle):
 def test_glm_tick_engine_fixed_stepsize_and_restart(oracle):
     eng, orc, inits = glm_pair(oracle, 300, 6, 16, seed=17)
     eng.set_inits(inits)
-    full = eng.run(40, burnin=0, thin=2)
+    full = eng.run(40, burnin=0, thin=2, glm_reference=True)
     out_o, st_o, tune_o = orc.run(16, inits, 40, burnin=0, thin=2, seed=17, nthreads=4)
     st, tune, _ = eng.get_state()
     assert_same_run((full, st, tune), (out_o, st_o, tune_o), rtol=1e-6, min_frac=0.85)
     eng.set_inits(inits)
-    p1 = eng.run(14, burnin=0, thin=2); p2 = eng.run(26, burnin=0, thin=2)
+    p1 = eng.run(14, burnin=0, thin=2, glm_reference=True); p2 = eng.run(26, burnin=0, thin=2, glm_reference=True)
     np.testing.assert_allclose(np.concatenate([p1, p2], axis=0), full, rtol=1e-12)
 
 
@@ -386,3 +386,41 @@ def test_glm_posterior_recovers_coefficients(oracle):
     mean = out.mean(axis=(0, 2)); sd = out.std(axis=(0, 2))
     assert np.all(np.abs(mean - beta) < 5 * sd)
     assert (eng.gelman(0.05, False)[:, 0] < 1.1).all()
+
+
+@pytest.mark.parametrize("N,d,C", [(1000, 10, 128), (5000, 100, 256), (777, 37, 100)])
+def test_glm_tensor_core_gradient_matches_fp64_kernel(oracle, N, d, C):
+    # north_star: logpdf and gradient within 1e-5 relative of the reference arithmetic (here: the FP64 kernel, which
+    # itself matches the oracle to 1e-12 in test_glm_density_and_gradient)
+    from mambacuda.engine import Engine
+    X, y, _ = helpers.glm_data(N=N, d=d, seed=3)
+    eng = Engine("glm", C, seed=1)
+    eng.set_data("X", X); eng.set_data("y", y)
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    beta = np.random.default_rng(4).normal(scale=0.5 / np.sqrt(d), size=(C, d))
+    lp0, g0 = eng.glm_gradient(beta, impl=0)
+    lp1, g1 = eng.glm_gradient(beta, impl=1)
+    eta = beta @ X.T
+    lp_np = (y * eta - np.logaddexp(0, eta)).sum(axis=1)
+    g_np = (y - 1 / (1 + np.exp(-eta))) @ X
+    np.testing.assert_allclose(lp0, lp_np, rtol=1e-12)
+    np.testing.assert_allclose(g0, g_np, rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(lp1, lp0, rtol=1e-5)
+    gscale = np.abs(g0).max(axis=1, keepdims=True)
+    assert np.max(np.abs(g1 - g0) / gscale) < 1e-5
+
+
+def test_glm_tick_engine_with_tensor_core_gradient_is_statistically_equivalent(oracle):
+    from mambacuda.engine import Engine
+    X, y, beta = helpers.glm_data(N=4000, d=6, seed=5)
+    res = []
+    for ref in (True, False):
+        eng = Engine("glm", 256, seed=1)
+        eng.set_data("X", X); eng.set_data("y", y)
+        eng.set_scheme([dict(kind="nuts", nodes=[0])])
+        eng.set_inits(np.zeros((1, 6)), jitter_sd=0.1)
+        eng.run(300, burnin=150, thin=1, store=False, out=False, glm_reference=ref)
+        res.append(eng.summary_streaming())
+    a, b = res
+    assert np.all(np.abs(a[:, 0] - b[:, 0]) < 4 * np.hypot(a[:, 3], b[:, 3]) + 1e-3)     # means within MCSE
+    np.testing.assert_allclose(a[:, 1], b[:, 1], rtol=0.1)                                # posterior SDs
