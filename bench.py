@@ -151,6 +151,119 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def glm_synthetic(N, d):
+    """X[:,0] = 1, X[:,1:] ~ N(0,1), beta* ~ N(0, I/d), y ~ Bernoulli(invlogit(X beta*))."""
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((N, d)); X[:, 0] = 1.0
+    beta = np.random.default_rng(2).standard_normal(d) / np.sqrt(d)
+    p = 1.0 / (1.0 + np.exp(-(X @ beta)))
+    y = (np.random.default_rng(3).uniform(size=N) < p).astype(np.float64)
+    return X, y, beta
+
+
+def glm_bench(args, rank, local_rank, world):
+    """configs[3]: NUTS on Bayesian logistic regression; reports the gradient-pass rate against the tensor roofline
+    and the chain-iteration / leapfrog rate of a short NUTS run (same JSON contract as the headline line)."""
+    import torch
+    from mambacuda.engine import Engine
+    torch.cuda.set_device(local_rank)
+    N, d, C = args.glm_n, args.glm_d, args.glm_chains
+    X, y, beta_true = glm_synthetic(N, d)
+    eng = Engine("glm", C, seed=SEED, chain_offset=rank * C, device=local_rank)
+    eng.set_data("X", X); eng.set_data("y", y)
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    beta = 0.1 * np.random.default_rng(5).standard_normal((C, d))
+    # gradient pass alone (the dominant kernel): tensor-core kernel vs FP64 reference kernel
+    times = {}
+    for impl, reps in ((1, max(args.steps, 3) + 3), (0, 2)):
+        ms = []
+        for r in range(reps):
+            lp, g = eng.glm_gradient(beta, impl=impl)
+            ms.append(eng.last_kernel_ms())
+        times[impl] = float(np.mean(ms[3:])) if impl == 1 else float(ms[-1])
+        if impl == 1:
+            lp1, g1 = lp, g
+        else:
+            err_lp = float(np.max(np.abs(lp1 - lp) / np.abs(lp)))
+            err_g = float(np.max(np.abs(g1 - g) / np.abs(g).max(axis=1, keepdims=True)))
+    flops = 4.0 * C * N * d
+    peaks, peak_src = measured_peaks()
+    # short NUTS run through the tick engine (adaptation on): leapfrogs = gradient passes ("ticks")
+    eng.set_inits(np.zeros((1, d)), jitter_sd=0.1)
+    sampler = ClockSampler(local_rank); sampler.start()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    launches0 = eng.launch_count()
+    eng.run(args.glm_iters, burnin=args.glm_iters // 2, thin=1, store=False, out=False)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    ticks = (launches - 0) // 4
+    summ = eng.summary_streaming()
+    if rank == 0:
+        ach = flops / (times[1] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        line = {
+            "metric": "chain_iters_per_sec", "value": world * C * args.glm_iters / dt, "unit": "chain-iterations/s", "n_gpus": world,
+            "steps": 1, "warmup": 3, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16x2-split tensor (f32 accumulate) + f64 NUTS state", "data": "synthetic",
+            "config": {"workload": f"Bayesian logistic regression N={N}, d={d}, NUTS(beta), {C} chains/GPU (configs[3])",
+                       "iters": args.glm_iters, "burnin": args.glm_iters // 2, "gradient_passes": int(ticks),
+                       "l2": "X (449 MB packed) exceeds L2; every pass streams it from HBM",
+                       "posterior_mean_abs_err_vs_truth": float(np.mean(np.abs(summ[:, 0] - beta_true)))},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "effective_peak_note": "operands are split fp16 pairs: 3 tensor products per algorithmic product, so the reachable fraction is 1/3",
+                         "traffic": None, "kernel": "glm_tc_kernel", "kernel_ms": times[1], "algo_flops_per_pass": flops,
+                         "peak_source": peak_src + " (sustained bf16; fp16 runs at the same rate)",
+                         "fp64_reference_kernel_ms": times[0], "max_rel_err_logf_vs_fp64": err_lp, "max_rel_err_grad_vs_fp64": err_g,
+                         "hbm": {"achieved": (np.ceil(C / 128) * (N * 112 * 4)) / (times[1] * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s"}},
+            "e2e": {"value": world * C * args.glm_iters / dt, "unit": "chain-iterations/s", "h2d_bytes_per_step": int(d * 8), "d2h_bytes_per_step": int(d * 5 * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def small_model_bench(args, rank, local_rank, world):
+    """The other configurations of BASELINE.json on the generic engine kernel (one chain per thread):
+    configs[0] line (3 chains x 10,000, CPU-scale sanity), configs[2] rats (NUTS + Slice, 65,536 chains),
+    configs[4] pumps (chain sweep with on-device Gelman-Rubin).  One JSON line per run."""
+    import helpers
+    import torch
+    from mambacuda.engine import Engine
+    torch.cuda.set_device(local_rank)
+    runs = []
+    if args.workload == "line":
+        runs = [("line_amwg_slice", 3, 10000, 1000, 1)]
+    elif args.workload == "rats":
+        runs = [("rats_nuts_slice", 65536, 200, 100, 1), ("rats_slice_amwg", 65536, 2000, 1000, 10)]
+    else:
+        runs = [("pumps_slice", n, 2000, 1000, 10) for n in (10**3, 10**4, 10**5, 10**6)]
+    for name, C, iters, burnin, thin in runs:
+        tpl, blocks, inits = helpers.scheme(name)
+        eng = Engine(tpl, C, seed=SEED, chain_offset=rank * C, device=local_rank)
+        eng.set_scheme(blocks)
+        eng.set_inits(inits, jitter_sd=0.05 if C > 16 else 0.0)
+        eng.run(min(iters, 20), burnin=min(burnin, 10), thin=1, store=False, out=False)     # warm-up launch
+        eng.set_inits(inits, jitter_sd=0.05 if C > 16 else 0.0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        eng.run(iters, burnin=burnin, thin=thin, store=False, out=False)
+        kms = eng.last_kernel_ms()
+        psrf = eng.gelman(0.05, True) if C >= 2 else None
+        summ = eng.summary_streaming() if (iters - burnin) // thin >= 200 else None
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        if rank == 0:
+            line = {"metric": "chain_iters_per_sec", "value": world * C * iters / dt, "unit": "chain-iterations/s", "n_gpus": world, "steps": 1,
+                    "warmup": 1, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                    "data": "reference data set", "config": {"workload": name, "chains_per_gpu": C, "iters": iters, "burnin": burnin, "thin": thin,
+                                                             "kernel": "run_generic_kernel", "kernel_ms": kms,
+                                                             "psrf_max": None if psrf is None else float(np.nanmax(psrf[:, 0])),
+                                                             "names": eng.names(1)[:12],
+                                                             "posterior_mean": None if summ is None else [float(v) for v in summ[:12, 0]],
+                                                             "ess_per_sec_min": None if summ is None else float(np.nanmin(summ[:, 4]) * world * C / dt)},
+                    "gpu_launches": int(eng.launch_count())}
+            print(json.dumps(line), flush=True)
+        eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +274,12 @@ def main():
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true", help="time the generic engine kernel instead of the fused one")
+    ap.add_argument("--workload", default="seeds", choices=["seeds", "glm", "rats", "pumps", "line"],
+                    help="seeds = headline (configs[1]); glm = configs[3]: NUTS logistic regression N=1e6, d=100 (tensor-core likelihood)")
+    ap.add_argument("--glm-n", type=int, default=1_000_000)
+    ap.add_argument("--glm-d", type=int, default=100)
+    ap.add_argument("--glm-chains", type=int, default=512, help="chains per GPU (4096 chains on 8 GPUs)")
+    ap.add_argument("--glm-iters", type=int, default=40)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,6 +288,12 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "glm":
+        glm_bench(args, rank, local_rank, world)
+        return
+    if args.workload in ("rats", "pumps", "line"):
+        small_model_bench(args, rank, local_rank, world)
         return
 
     import torch

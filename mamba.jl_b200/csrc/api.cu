@@ -297,13 +297,14 @@ int ensure_glm_buffers(mcu_ctx* h) {
   const long long N = (long long)h->inputs["y"].size();
   if (nslab > (N + 63) / 64) nslab = (N + 63) / 64;
   if (nslab < 1) nslab = 1;
-  h->g_nslab = (int)nslab;
+  const long long nslab_ref = nslab; h->g_nslab = (int)nslab_ref;
   {
     const long long groups = (h->C + 127) / 128;
     long long ns = 148 / groups; if (ns < 1) ns = 1;
     const long long NT = glm_tc_num_tiles(N); if (ns > NT) ns = NT;
     h->g_nslab_tc = (int)ns;
-    if (ns > nslab) nslab = ns;
+    const long long npart = ns * glm_tc_nsub(N, (int)ns);   // FP64 gradient partials: one per (slab, flush interval)
+    if (npart > nslab) nslab = npart;
   }
   if (const char* e = std::getenv("MCU_GLM_IMPL")) h->glm_impl = std::atoi(e);
   CK(cudaMalloc(&h->g_sc, sizeof(double) * nsc * C));
@@ -337,7 +338,7 @@ int glm_gradient_dispatch(mcu_ctx* h, int N) {
   if (h->glm_impl == 1) {
     if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, h->g_part_g, h->stream) != 0)
       return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
-    glm_fold(h->g_part_lp, h->g_part_g, h->g_nslab_tc, h->D, h->C, h->g_lp, h->g_grad, h->stream);
+    glm_fold(h->g_part_lp, h->g_part_g, h->g_nslab_tc, h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc), h->D, h->C, h->g_lp, h->g_grad, h->stream);
   } else {
     glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
                        h->g_lp, h->g_grad, h->stream);

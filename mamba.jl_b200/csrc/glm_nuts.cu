@@ -329,9 +329,9 @@ void glm_grad_reference(const double* X, const double* y, int N, int d, long lon
   glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab, (long long)d * C, grad);
 }
 
-void glm_fold(const double* part_lp, const double* part_g, int nslab, int d, long long C, double* lp, double* grad, cudaStream_t st) {
-  glm_fold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(part_lp, nslab, C, lp);
-  glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab, (long long)d * C, grad);
+void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st) {
+  glm_fold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(part_lp, nslab_lp, C, lp);
+  glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab_g, (long long)d * C, grad);
 }
 
 void glm_advance(const GlmTick& t, cudaStream_t st) {

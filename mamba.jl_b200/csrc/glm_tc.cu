@@ -18,7 +18,10 @@
 // Precision: operands are split fp16 pairs (x = hi + lo, |lo| <= 2^-11 |hi|) and every product is formed
 // as hi*hi + hi*lo + lo*hi with FP32 accumulation (dropped term 2^-22 relative), so eta and the gradient
 // carry ~1e-6 relative error — inside north_star's 1e-5 — at 1/3 of the fp16 tensor peak.
-// Per-slab partials are written as FP64 and folded deterministically (glm_nuts.cu: glm_fold_kernel).
+// The tensor core truncates when it adds into the FP32 accumulator, so a long running sum drifts linearly
+// (measured 1e-4 relative over 27k rows); the gradient accumulator is therefore flushed to FP64 partials every
+// FLUSH = 8 tiles (1,024 rows), which bounds the drift at a few 1e-6.
+// Partials are written as FP64 and folded deterministically (glm_nuts.cu: glm_fold_kernel).
 //
 // Shared-memory operand layout: un-swizzled UMMA "interleave" core matrices (8 rows x 16 bytes, 128 bytes
 // contiguous), core matrices ordered [row-block][col-block].  X is pre-packed in HBM in exactly this order,
@@ -34,6 +37,7 @@ namespace {
 
 constexpr int TM = 128;   // chains per CTA
 constexpr int TR = 128;   // data rows per tile
+constexpr int FLUSH = 8;  // tiles between flushes of the TMEM gradient accumulator (see below)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -144,7 +148,8 @@ struct TcArgs {
   long long C;
   const double* req;         // [d][C]
   double* part_lp;           // [nslab][C]
-  double* part_g;            // [nslab][d][C]
+  double* part_g;            // [nslab * nsub][d][C]
+  int nsub;
 };
 
 __global__ void __launch_bounds__(128, 1) glm_tc_kernel(const TcArgs a) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(128, 1) glm_tc_kernel(const TcArgs a) {
       for (int kk = 0; kk < TR / 16; ++kk) {
         const uint32_t ko = (uint32_t)kk * 2 * rb_stride;   // two row-blocks per K step
         const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
-        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, (t > t0 || kk > 0) ? 1u : 0u);
+        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, (((t - t0) % FLUSH) != 0 || kk > 0) ? 1u : 0u);
         mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
         mma_ts(tm_g, tm_rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
       }
@@ -281,16 +286,26 @@ __global__ void __launch_bounds__(128, 1) glm_tc_kernel(const TcArgs a) {
     }
     mbar_wait(smem_u32(&bars[2]), mma_phase); mma_phase ^= 1u;
     tc_fence_after();
+    // ---- flush the gradient accumulator to this sub-slab's FP64 partial
+    if (((t - t0) % FLUSH) == FLUSH - 1 || t == t1 - 1) {
+      const int sub = (t - t0) / FLUSH;
+      for (int j0 = 0; j0 < DP; j0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
+        if (c < a.C)
+          for (int e = 0; e < 16; ++e)
+            if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+      }
+      tc_fence_before();
+      __syncthreads();   // every lane has read G before the next GEMM2 overwrites it
+    }
   }
-  // ---- write this slab's partials
-  if (c < a.C) a.part_lp[(size_t)slab * a.C + c] = lp_acc;
-  for (int j0 = 0; j0 < DP; j0 += 16) {
-    uint32_t v[16];
-    if (t0 < t1) { tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld(); }
-    else { for (int e = 0; e < 16; ++e) v[e] = 0u; }
-    if (c < a.C)
-      for (int e = 0; e < 16; ++e)
-        if (j0 + e < a.d) a.part_g[((size_t)slab * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+  // ---- this slab's logf partial; sub-slabs this CTA never reached contribute zero
+  if (c < a.C) {
+    a.part_lp[(size_t)slab * a.C + c] = lp_acc;
+    const int used = t1 > t0 ? (t1 - t0 + FLUSH - 1) / FLUSH : 0;
+    for (int sub = used; sub < a.nsub; ++sub)
+      for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -308,13 +323,18 @@ void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* 
   glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, blob, glm_tc_tile_bytes(d));
 }
 
-// Returns 0 on success.  part_lp [nslab][C], part_g [nslab][d][C] (FP64), to be folded over slabs.
+int glm_tc_nsub(long long N, int nslab) {
+  const long long NT = glm_tc_num_tiles(N), tps = (NT + nslab - 1) / nslab;
+  return (int)((tps + FLUSH - 1) / FLUSH);
+}
+
+// Returns 0 on success.  part_lp [nslab][C], part_g [nslab * nsub][d][C] (FP64), to be folded over slabs.
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
                   double* part_lp, double* part_g, cudaStream_t st) {
   TcArgs a;
   a.DP = (d + 15) / 16 * 16;
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
-  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
   const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 64;
   if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);

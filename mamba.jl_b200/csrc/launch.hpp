@@ -66,9 +66,10 @@ void glm_grad_reference(const double* X, const double* y, int N, int d, long lon
 // ---- tensor-core GLM likelihood/gradient kernel (glm_tc.cu) ---------------------------------------------
 size_t glm_tc_tile_bytes(int d);
 long long glm_tc_num_tiles(long long N);
+int glm_tc_nsub(long long N, int nslab);
 void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* blob, cudaStream_t st);
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
                   double* part_lp, double* part_g, cudaStream_t st);
-void glm_fold(const double* part_lp, const double* part_g, int nslab, int d, long long C, double* lp, double* grad, cudaStream_t st);
+void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st);
 
 }  // namespace mcu
