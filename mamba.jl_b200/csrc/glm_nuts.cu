@@ -73,29 +73,71 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
 
   // pending result: full block density = MvNormal(d, sqrt(1000)) prior + likelihood (glm template, models.cuh)
   double lp_full = 0.0;
+  // Global-memory vector helpers.  Loads are staged through registers in chunks of kCh before the stores: a store
+  // to a.vec may alias the next load, so an element-by-element copy would pay one memory latency per element.
+  constexpr int kCh = 10;
   auto load_result = [&](int vslot_g) {
     double sq = 0.0; bool fin = true;
-    for (int i = 0; i < d; ++i) { const double b = REQ(i); sq += b * b; fin = fin && isfinite(b); }
+    for (int i0 = 0; i0 < d; i0 += kCh) {
+      double b[kCh], g[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { b[k] = REQ(i0 + k); g[k] = a.grad[(size_t)(i0 + k) * C + c]; }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) {
+        sq += b[k] * b[k]; fin = fin && isfinite(b[k]);
+        double gg = g[k] - b[k] / 1000.0;
+        if (!isfinite(gg)) gg = 0.0;                     // logpdfgrad!: sampler.jl:110
+        VV(vslot_g, i0 + k) = gg;
+      }
+    }
     const double prior = fin ? lp_isonormal(sq, (double)d, sqrt(1000.0)) : neg_inf();
     lp_full = prior + a.lp[c];
-    for (int i = 0; i < d; ++i) {
-      double g = a.grad[(size_t)i * C + c] - REQ(i) / 1000.0;
-      if (!isfinite(g)) g = 0.0;                       // logpdfgrad!: sampler.jl:110
-      VV(vslot_g, i) = g;
-    }
   };
   auto dotv = [&](int vs) { double s = 0; for (int i = 0; i < d; ++i) { const double x = VV(vs, i); s += x * x; } return s; };
-  auto copyv = [&](int dst, int src) { for (int i = 0; i < d; ++i) VV(dst, i) = VV(src, i); };
+  auto copyv = [&](int dst, int src) {
+    for (int i0 = 0; i0 < d; i0 += kCh) {
+      double t[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) t[k] = VV(src, i0 + k);
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) VV(dst, i0 + k) = t[k];
+    }
+  };
+  auto copyv3 = [&](int d0, int s0, int d1, int s1, int d2, int s2) {   // three independent copies, loads batched
+    for (int i0 = 0; i0 < d; i0 += kCh) {
+      double t0[kCh], t1[kCh], t2[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { t0[k] = VV(s0, i0 + k); t1[k] = VV(s1, i0 + k); t2[k] = VV(s2, i0 + k); }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { VV(d0, i0 + k) = t0[k]; VV(d1, i0 + k) = t1[k]; VV(d2, i0 + k) = t2[k]; }
+    }
+  };
   auto nouturn = [&](int xminus, int xplus, int rminus, int rplus) {
     double p = 0, q = 0;
     for (int i = 0; i < d; ++i) { const double df = VV(xplus, i) - VV(xminus, i); p += df * VV(rminus, i); q += df * VV(rplus, i); }
     return p >= 0 && q >= 0;
   };
-  auto request_cx = [&]() { for (int i = 0; i < d; ++i) REQ(i) = VV(V_CX, i); };
+  auto request_cx = [&]() {
+    for (int i0 = 0; i0 < d; i0 += kCh) {
+      double t[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) t[k] = VV(V_CX, i0 + k);
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) REQ(i0 + k) = t[k];
+    }
+  };
   // first half of a leapfrog from (cx, cr, cg): nuts.jl:130-131
   auto half_step_and_request = [&](double eps) {
-    for (int i = 0; i < d; ++i) { const double r = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); VV(V_CR, i) = r; VV(V_CX, i) = VV(V_CX, i) + eps * r; }
-    request_cx();
+    for (int i0 = 0; i0 < d; i0 += kCh) {
+      double r[kCh], g[kCh], x[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { r[k] = VV(V_CR, i0 + k); g[k] = VV(V_CG, i0 + k); x[k] = VV(V_CX, i0 + k); }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) if (i0 + k < d) {
+        const double rn = r[k] + (0.5 * eps) * g[k]; const double xn = x[k] + eps * rn;
+        VV(V_CR, i0 + k) = rn; VV(V_CX, i0 + k) = xn; REQ(i0 + k) = xn;
+      }
+    }
   };
 
   bool need_grad = false;
@@ -167,7 +209,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
         load_result(V_CG);
         const double logp0 = lp_full - 0.5 * dotv(V_CR);
         SC(SL_LOGP0) = logp0; SC(SL_LOGU0) = logp0 + log(rng.uniform());
-        copyv(V_XM, V_CX); copyv(V_XP, V_CX); copyv(V_RM, V_CR); copyv(V_RP, V_CR); copyv(V_GM, V_CG); copyv(V_GP, V_CG);
+        copyv3(V_XM, V_CX, V_RM, V_CR, V_GM, V_CG); copyv3(V_XP, V_CX, V_RP, V_CR, V_GP, V_CG);
         SC(SL_J) = 0.0; SC(SL_N) = 1.0;
         // first doubling
         const double pm = rng.uniform() > 0.5 ? 1.0 : -1.0;   // both edges equal the start point
@@ -179,14 +221,21 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
       case PH_LEAF: {    // buildtree leaf (nuts.jl:142-152) + the unrolled merges (samplers.cuh nuts_sub)
         load_result(V_CG);
         const double pm = SC(SL_PM), eps = pm * SC(SL_EPS_USE);
-        for (int i = 0; i < d; ++i) VV(V_CR, i) = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i);
+        double dotr = 0.0;
+        for (int i0 = 0; i0 < d; i0 += kCh) {
+          double r[kCh], g[kCh];
+#pragma unroll
+          for (int k = 0; k < kCh; ++k) if (i0 + k < d) { r[k] = VV(V_CR, i0 + k); g[k] = VV(V_CG, i0 + k); }
+#pragma unroll
+          for (int k = 0; k < kCh; ++k) if (i0 + k < d) { const double rn = r[k] + (0.5 * eps) * g[k]; VV(V_CR, i0 + k) = rn; dotr += rn * rn; }
+        }
         const double logu0 = SC(SL_LOGU0), logp0 = SC(SL_LOGP0);
-        const double logpp = lp_full - 0.5 * dotv(V_CR);
+        const double logpp = lp_full - 0.5 * dotr;
         double Tn = logu0 < logpp ? 1.0 : 0.0;
         bool Ts = logu0 < logpp + 1000.0;
         SC(SL_ALPHA) = SC(SL_ALPHA) + fmin(1.0, exp(logpp - logp0));
         SC(SL_NALPHA) = SC(SL_NALPHA) + 1.0;
-        copyv(V_TXF, V_CX); copyv(V_TRF, V_CR); copyv(V_TXP, V_CX);
+        copyv3(V_TXF, V_CX, V_TRF, V_CR, V_TXP, V_CX);
         const int j = (int)SC(SL_J); const unsigned t = (unsigned)SC(SL_T);
         int l = 0;
         bool parked = false;
@@ -202,7 +251,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
             copyv(V_TXF, sxf); copyv(V_TRF, srf);
             ++l;
           } else if (Ts) {
-            copyv(sxf, V_TXF); copyv(srf, V_TRF); copyv(sxp, V_TXP); SC(SL_SN0 + l) = Tn;
+            copyv3(sxf, V_TXF, srf, V_TRF, sxp, V_TXP); SC(SL_SN0 + l) = Tn;
             parked = true; break;
           } else {
             ++l;
@@ -215,8 +264,8 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
           break;
         }
         // tree of depth j complete (or failed): nuts.jl:108-123
-        if (pm < 0) { copyv(V_XM, V_CX); copyv(V_RM, V_CR); copyv(V_GM, V_CG); }
-        else { copyv(V_XP, V_CX); copyv(V_RP, V_CR); copyv(V_GP, V_CG); }
+        if (pm < 0) copyv3(V_XM, V_CX, V_RM, V_CR, V_GM, V_CG);
+        else copyv3(V_XP, V_CX, V_RP, V_CR, V_GP, V_CG);
         double n = SC(SL_N);
         if (Ts) { if (rng.uniform() < Tn / n) for (int i = 0; i < d; ++i) ST(i) = VV(V_TXP, i); }
         const int jn = j + 1;
@@ -227,8 +276,8 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
         if (s) {           // next doubling
           const double pm2 = rng.uniform() > 0.5 ? 1.0 : -1.0;
           SC(SL_PM) = pm2; SC(SL_T) = 0.0; SC(SL_ALPHA) = 0.0; SC(SL_NALPHA) = 0.0;
-          if (pm2 < 0) { copyv(V_CX, V_XM); copyv(V_CR, V_RM); copyv(V_CG, V_GM); }
-          else { copyv(V_CX, V_XP); copyv(V_CR, V_RP); copyv(V_CG, V_GP); }
+          if (pm2 < 0) copyv3(V_CX, V_XM, V_CR, V_RM, V_CG, V_GM);
+          else copyv3(V_CX, V_XP, V_CR, V_RP, V_CG, V_GP);
           half_step_and_request(pm2 * SC(SL_EPS_USE));
           need_grad = true;
           break;

@@ -152,164 +152,220 @@ struct TcArgs {
   int nsub;
 };
 
-__global__ void __launch_bounds__(128, 1) glm_tc_kernel(const TcArgs a) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kEpiThreads = 256;   // 8 epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 and column half w / 4
+constexpr int kTcThreads = kEpiThreads + 32;   // + 1 issuer warp (bulk copies, tcgen05.mma, commits)
+
+// barrier slots in shared memory
+enum { B_FULL0 = 0, B_FULL1, B_D1FULL0, B_D1FULL1, B_D1EMPTY0, B_D1EMPTY1, B_RFULL, B_GDONE, B_GREAD, B_COUNT };
+
+// Warp-specialised pipeline.  Per tile t (buffer b = t & 1):
+//   issuer  : GEMM1(t+1) → D1[b^1]  (runs under epilogue(t))     | waits: tile landed, D1[b^1] drained
+//             GEMM2(t)   → G        (after epilogue(t) stored R)  | waits: R stored, G read back if tile t-1 flushed
+//             bulk copy X(t+2) → buffer b once GEMM2(t) has completed
+//   epilogue: D1[b] → p, logf, R (split fp16) → tensor memory; every FLUSH tiles G → FP64 partial
+// TMEM columns: D1[0] 0-127, D1[1] 128-255, R_hi 256-319, R_lo 320-383, G 384-511.
+__global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int DP = a.DP, CB = DP / 8;
   const uint32_t op_bytes = (uint32_t)TM * DP * 2;          // one 128 x DP fp16 operand block
   const uint32_t tile_bytes = (uint32_t)a.tile_bytes;       // hi | lo | y
-  unsigned char* xbuf0 = smem;
-  unsigned char* xbuf1 = smem + tile_bytes;
+  unsigned char* xbuf[2] = {smem, smem + tile_bytes};
   unsigned char* th_hi = smem + 2 * tile_bytes;
   unsigned char* th_lo = th_hi + op_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(th_lo + op_bytes);   // [0],[1]: tile landed; [2]: MMA done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(th_lo + op_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  double* lp_xchg = reinterpret_cast<double*>(bars + B_COUNT + 2);   // [128]
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
-  const long long c = (long long)blockIdx.x * TM + tid;     // this thread's chain
   const int slab = blockIdx.y;
   const int t0 = slab * a.tiles_per_slab, t1 = min(a.NT, t0 + a.tiles_per_slab);
+  const int T = max(0, t1 - t0);
 
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init(smem_u32(&bars[2]), 1);
+    mbar_init(bar(B_FULL0), 1); mbar_init(bar(B_FULL1), 1);
+    mbar_init(bar(B_D1FULL0), 1); mbar_init(bar(B_D1FULL1), 1);
+    mbar_init(bar(B_D1EMPTY0), kEpiThreads); mbar_init(bar(B_D1EMPTY1), kEpiThreads);
+    mbar_init(bar(B_RFULL), kEpiThreads); mbar_init(bar(B_GDONE), 1); mbar_init(bar(B_GREAD), kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Theta tile: this thread's chain is row `tid`; split fp16, blocked core-matrix layout, zero padded
-  for (int cb = 0; cb < CB; ++cb) {
-    __half hi[8], lo[8];
-    for (int e = 0; e < 8; ++e) {
-      const int col = cb * 8 + e;
-      const float x = (c < a.C && col < a.d) ? (float)a.req[(size_t)col * a.C + c] : 0.0f;
-      hi[e] = __float2half_rn(x);
-      lo[e] = __float2half_rn(x - __half2float(hi[e]));
+  // Theta tile: chain = row (tid % 128); the two column halves are split over tid / 128; split fp16, blocked layout
+  if (tid < kEpiThreads) {
+    const int row = tid & 127, hf = tid >> 7;
+    const long long c = (long long)blockIdx.x * TM + row;
+    for (int cb = hf; cb < CB; cb += 2) {
+      __half hi[8], lo[8];
+      for (int e = 0; e < 8; ++e) {
+        const int col = cb * 8 + e;
+        const float x = (c < a.C && col < a.d) ? (float)a.req[(size_t)col * a.C + c] : 0.0f;
+        hi[e] = __float2half_rn(x);
+        lo[e] = __float2half_rn(x - __half2float(hi[e]));
+      }
+      const size_t off = ((size_t)(row / 8) * CB + cb) * 128 + (size_t)(row % 8) * 16;
+      uint4 vh, vl;
+      vh.x = pack_half2(hi[0], hi[1]); vh.y = pack_half2(hi[2], hi[3]); vh.z = pack_half2(hi[4], hi[5]); vh.w = pack_half2(hi[6], hi[7]);
+      vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
+      *reinterpret_cast<uint4*>(th_hi + off) = vh;
+      *reinterpret_cast<uint4*>(th_lo + off) = vl;
     }
-    const size_t off = ((size_t)(tid / 8) * CB + cb) * 128 + (size_t)(tid % 8) * 16;
-    uint4 vh, vl;
-    vh.x = pack_half2(hi[0], hi[1]); vh.y = pack_half2(hi[2], hi[3]); vh.z = pack_half2(hi[4], hi[5]); vh.w = pack_half2(hi[6], hi[7]);
-    vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
-    *reinterpret_cast<uint4*>(th_hi + off) = vh;
-    *reinterpret_cast<uint4*>(th_lo + off) = vl;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes → visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_d1 = tmem, tm_rh = tmem + 128, tm_rl = tmem + 192, tm_g = tmem + 256;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tm_d1[2] = {tmem, tmem + 128};
+  const uint32_t tm_rh = tmem + 256, tm_rl = tmem + 320, tm_g = tmem + 384;
 
   // instruction descriptors (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): F16 x F16 → F32, M = 128
   const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);                 // N = 128, A/B K-major
   const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(DP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);     // N = DP, B MN-major
   const uint32_t rb_stride = (uint32_t)CB * 128;   // bytes between 8-row blocks
 
-  if (tid == 0 && t0 < t1) {
-    mbar_expect_tx(smem_u32(&bars[0]), tile_bytes);
-    bulk_copy_g2s(smem_u32(xbuf0), a.blob + (size_t)t0 * a.tile_bytes, tile_bytes, smem_u32(&bars[0]));
-  }
-  double lp_acc = 0.0;
-  uint32_t mma_phase = 0;
-  for (int t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    unsigned char* xb = buf ? xbuf1 : xbuf0;
-    if (tid == 0 && t + 1 < t1) {   // prefetch the next tile into the other buffer (its last reader, GEMM2 of t-1, has completed)
-      mbar_expect_tx(smem_u32(&bars[buf ^ 1]), tile_bytes);
-      bulk_copy_g2s(smem_u32(buf ? xbuf0 : xbuf1), a.blob + (size_t)(t + 1) * a.tile_bytes, tile_bytes, smem_u32(&bars[buf ^ 1]));
-    }
-    mbar_wait(smem_u32(&bars[buf]), (uint32_t)(((t - t0) >> 1) & 1));
-    // ---- GEMM1: D1 = Theta . X_t'  (3 split products per 16-wide K step)
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t xh = smem_u32(xb), xl = xh + op_bytes, ah = smem_u32(th_hi), al = smem_u32(th_lo);
-      for (int k = 0; k < DP / 16; ++k) {
-        const uint32_t ko = (uint32_t)k * 256;   // two col-blocks per K step
-        const uint64_t dah = make_desc(ah + ko, 128, rb_stride), dal = make_desc(al + ko, 128, rb_stride);
-        const uint64_t dbh = make_desc(xh + ko, 128, rb_stride), dbl = make_desc(xl + ko, 128, rb_stride);
-        mma_ss(tm_d1, dah, dbh, idesc1, k > 0 ? 1u : 0u);
-        mma_ss(tm_d1, dah, dbl, idesc1, 1u);
-        mma_ss(tm_d1, dal, dbh, idesc1, 1u);
-      }
-      tc_commit(smem_u32(&bars[2]));
-    }
-    mbar_wait(smem_u32(&bars[2]), mma_phase); mma_phase ^= 1u;
-    tc_fence_after();
-    // ---- epilogue: thread = chain (TMEM lane), columns = the tile's 128 data rows
-    const float* ytile = reinterpret_cast<const float*>(xb + 2 * op_bytes);
-    float lp_tile = 0.0f;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      uint32_t v[32];
-      tmem_ld32(tm_d1 + lane_off + (uint32_t)q * 32, v);
-      tmem_wait_ld();
-      uint32_t ph[16], pl[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float r2[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float eta = __uint_as_float(v[e + u]);
-          const float yv = ytile[q * 32 + e + u];
-          const float ex = __expf(-fabsf(eta));
-          const float s = __fdividef(1.0f, 1.0f + ex);
-          const float p = eta >= 0.0f ? s : ex * s;
-          const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + ex);
-          const bool valid = yv >= 0.0f;
-          lp_tile += valid ? (yv * eta - sp) : 0.0f;
-          r2[u] = valid ? (yv - p) : 0.0f;
+  if (warp == 8) {
+    // ======================================================================= issuer (one elected lane)
+    if ((tid & 31) == 0 && T > 0) {
+      auto load_tile = [&](int t) {
+        const int b = t & 1;
+        mbar_expect_tx(bar(B_FULL0 + b), tile_bytes);
+        bulk_copy_g2s(smem_u32(xbuf[b]), a.blob + (size_t)(t0 + t) * a.tile_bytes, tile_bytes, bar(B_FULL0 + b));
+      };
+      auto gemm1 = [&](int t) {   // D1[t&1] = Theta . X_t'  (3 split products per 16-wide K step)
+        const int b = t & 1;
+        const uint32_t xh = smem_u32(xbuf[b]), xl = xh + op_bytes, ah = smem_u32(th_hi), al = smem_u32(th_lo);
+        for (int k = 0; k < DP / 16; ++k) {
+          const uint32_t ko = (uint32_t)k * 256;   // two col-blocks per K step
+          const uint64_t dah = make_desc(ah + ko, 128, rb_stride), dal = make_desc(al + ko, 128, rb_stride);
+          const uint64_t dbh = make_desc(xh + ko, 128, rb_stride), dbl = make_desc(xl + ko, 128, rb_stride);
+          mma_ss(tm_d1[b], dah, dbh, idesc1, k > 0 ? 1u : 0u);
+          mma_ss(tm_d1[b], dah, dbl, idesc1, 1u);
+          mma_ss(tm_d1[b], dal, dbh, idesc1, 1u);
         }
-        const __half h0 = __float2half_rn(r2[0]), h1 = __float2half_rn(r2[1]);
-        ph[e >> 1] = pack_half2(h0, h1);
-        pl[e >> 1] = pack_half2(__float2half_rn(r2[0] - __half2float(h0)), __float2half_rn(r2[1] - __half2float(h1)));
-      }
-      tmem_st16(tm_rh + lane_off + (uint32_t)q * 16, ph);
-      tmem_st16(tm_rl + lane_off + (uint32_t)q * 16, pl);
-    }
-    lp_acc += (double)lp_tile;
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    // ---- GEMM2: G += R . X_t  (A = R from tensor memory, B = the X tile read MN-major)
-    if (tid == 0) {
+        tc_commit(bar(B_D1FULL0 + b));
+      };
+      load_tile(0);
+      if (T > 1) load_tile(1);
+      mbar_wait(bar(B_FULL0), 0);
       tc_fence_after();
-      const uint32_t xh = smem_u32(xb), xl = xh + op_bytes;
-      for (int kk = 0; kk < TR / 16; ++kk) {
-        const uint32_t ko = (uint32_t)kk * 2 * rb_stride;   // two row-blocks per K step
-        const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
-        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, (((t - t0) % FLUSH) != 0 || kk > 0) ? 1u : 0u);
-        mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
-        mma_ts(tm_g, tm_rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
+      gemm1(0);
+      int nflush = 0;          // flushes completed so far (= completions of B_GREAD the issuer has consumed)
+      bool prev_flushed = false;
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        if (t + 1 < T) {
+          mbar_wait(bar(B_FULL0 + (b ^ 1)), (uint32_t)(((t + 1) >> 1) & 1));
+          if (t + 1 >= 2) mbar_wait(bar(B_D1EMPTY0 + (b ^ 1)), (uint32_t)(((t - 1) >> 1) & 1));   // epilogue(t-1) drained D1[b^1]
+          tc_fence_after();
+          gemm1(t + 1);
+        }
+        mbar_wait(bar(B_RFULL), (uint32_t)(t & 1));                 // epilogue(t) stored R
+        if (prev_flushed) { mbar_wait(bar(B_GREAD), (uint32_t)(nflush & 1)); ++nflush; }   // G of the previous interval read back
+        tc_fence_after();
+        {   // GEMM2(t): G += R . X_t  (A = R from tensor memory, B = the X tile read MN-major)
+          const uint32_t xh = smem_u32(xbuf[b]), xl = xh + op_bytes;
+          for (int kk = 0; kk < TR / 16; ++kk) {
+            const uint32_t ko = (uint32_t)kk * 2 * rb_stride;       // two row-blocks per K step
+            const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
+            mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, ((t % FLUSH) != 0 || kk > 0) ? 1u : 0u);
+            mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
+            mma_ts(tm_g, tm_rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
+          }
+          tc_commit(bar(B_GDONE));
+        }
+        prev_flushed = (t % FLUSH) == FLUSH - 1 || t == T - 1;
+        if (t + 2 < T) {
+          mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));               // GEMM2(t) complete → X buffer b is free
+          load_tile(t + 2);
+        }
       }
-      tc_commit(smem_u32(&bars[2]));
     }
-    mbar_wait(smem_u32(&bars[2]), mma_phase); mma_phase ^= 1u;
-    tc_fence_after();
-    // ---- flush the gradient accumulator to this sub-slab's FP64 partial
-    if (((t - t0) % FLUSH) == FLUSH - 1 || t == t1 - 1) {
-      const int sub = (t - t0) / FLUSH;
-      for (int j0 = 0; j0 < DP; j0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
-        if (c < a.C)
-          for (int e = 0; e < 16; ++e)
-            if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+  } else {
+    // ======================================================================= epilogue warps
+    const int q = warp & 3, hf = warp >> 2;
+    const int lane_row = q * 32 + (tid & 31);                       // TMEM lane = chain row of this CTA
+    const long long c = (long long)blockIdx.x * TM + lane_row;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    double lp_acc = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      mbar_wait(bar(B_D1FULL0 + b), (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const float* ytile = reinterpret_cast<const float*>(xbuf[b] + 2 * op_bytes);
+      float lp_tile = 0.0f;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col0 = hf * 64 + ch * 32;
+        uint32_t v[32];
+        tmem_ld32(tm_d1[b] + lane_off + (uint32_t)col0, v);
+        tmem_wait_ld();
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float r2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float eta = __uint_as_float(v[e + u]);
+            const float yv = ytile[col0 + e + u];
+            const float ex = __expf(-fabsf(eta));
+            const float s = __fdividef(1.0f, 1.0f + ex);
+            const float p = eta >= 0.0f ? s : ex * s;
+            const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + ex);
+            const bool valid = yv >= 0.0f;
+            lp_tile += valid ? (yv * eta - sp) : 0.0f;
+            r2[u] = valid ? (yv - p) : 0.0f;
+          }
+          const __half2 h = __floats2half2_rn(r2[0], r2[1]);
+          const float2 hb = __half22float2(h);
+          const __half2 l = __floats2half2_rn(r2[0] - hb.x, r2[1] - hb.y);
+          ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        if (ch == 1) { tc_fence_before(); mbar_arrive(bar(B_D1EMPTY0 + b)); }   // both chunks of D1[b] are in registers: the buffer may be overwritten
+        if (ch == 0 && t > 0) { mbar_wait(bar(B_GDONE), (uint32_t)((t - 1) & 1)); tc_fence_after(); }   // GEMM2(t-1) done: R is free
+        tmem_st16(tm_rh + lane_off + (uint32_t)(col0 >> 1), ph);
+        tmem_st16(tm_rl + lane_off + (uint32_t)(col0 >> 1), pl);
       }
+      lp_acc += (double)lp_tile;
+      tmem_wait_st();
       tc_fence_before();
-      __syncthreads();   // every lane has read G before the next GEMM2 overwrites it
+      mbar_arrive(bar(B_RFULL));
+      if ((t % FLUSH) == FLUSH - 1 || t == T - 1) {
+        // ---- flush the gradient accumulator to this sub-slab's FP64 partial (column halves split over hf)
+        mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));
+        tc_fence_after();
+        const int sub = t / FLUSH;
+        for (int j0 = hf * 16; j0 < DP; j0 += 32) {
+          uint32_t v[16];
+          tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
+          if (c < a.C)
+            for (int e = 0; e < 16; ++e)
+              if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        mbar_arrive(bar(B_GREAD));
+      }
     }
-  }
-  // ---- this slab's logf partial; sub-slabs this CTA never reached contribute zero
-  if (c < a.C) {
-    a.part_lp[(size_t)slab * a.C + c] = lp_acc;
-    const int used = t1 > t0 ? (t1 - t0 + FLUSH - 1) / FLUSH : 0;
-    for (int sub = used; sub < a.nsub; ++sub)
-      for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0;
+    // ---- this slab's logf partial (the two column halves of a chain are combined through shared memory)
+    if (hf == 1) lp_xchg[lane_row] = lp_acc;
+    asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
+    if (hf == 0 && c < a.C) {
+      a.part_lp[(size_t)slab * a.C + c] = lp_acc + lp_xchg[lane_row];
+      const int used = T > 0 ? (T + FLUSH - 1) / FLUSH : 0;
+      for (int sub = used; sub < a.nsub; ++sub)
+        for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -335,10 +391,10 @@ int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const do
   a.DP = (d + 15) / 16 * 16;
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
   a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
-  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 64;
+  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 8 * (B_COUNT + 2) + 128 * sizeof(double);
   if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);
-  glm_tc_kernel<<<grid, 128, smem, st>>>(a);
+  glm_tc_kernel<<<grid, kTcThreads, smem, st>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
