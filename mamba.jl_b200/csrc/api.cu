@@ -62,7 +62,7 @@ struct mcu_ctx {
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
   int* g_nactive = nullptr; int g_nslab = 0;
-  unsigned char* g_blob = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
+  unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
 };
 
@@ -231,7 +231,7 @@ void free_scheme(mcu_ctx* h) {
 }
 void free_glm_buffers(mcu_ctx* h) {
   cudaFree(h->g_sc); cudaFree(h->g_vec); cudaFree(h->g_req); cudaFree(h->g_lp); cudaFree(h->g_grad); cudaFree(h->g_part_lp); cudaFree(h->g_part_g);
-  cudaFree(h->g_nactive); cudaFree(h->g_blob); h->g_blob = nullptr;
+  cudaFree(h->g_nactive); cudaFree(h->g_blob); h->g_blob = nullptr; cudaFree(h->g_xty); h->g_xty = nullptr;
   h->g_sc = h->g_vec = h->g_req = h->g_lp = h->g_grad = h->g_part_lp = h->g_part_g = nullptr; h->g_nactive = nullptr;
 }
 void free_chain_buffers(mcu_ctx* h) {
@@ -314,11 +314,19 @@ int ensure_glm_buffers(mcu_ctx* h) {
   CK(cudaMalloc(&h->g_grad, sizeof(double) * d * C));
   CK(cudaMalloc(&h->g_part_lp, sizeof(double) * nslab * C));
   CK(cudaMalloc(&h->g_part_g, sizeof(double) * nslab * d * C));
-  CK(cudaMalloc(&h->g_nactive, sizeof(int)));
+  CK(cudaMalloc(&h->g_nactive, 2 * sizeof(int)));
+  CK(cudaMemsetAsync(h->g_nactive, 0, 2 * sizeof(int), h->stream));
   {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
     glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, h->g_blob, h->stream); h->launches++;
+    // X'y (FP64, once): sum_i y_i eta_i = beta . (X'y) is added by the fold instead of per element
+    std::vector<double> xty(h->D, 0.0);
+    const std::vector<double>& Xh = h->inputs["X"]; const std::vector<double>& yh = h->inputs["y"];
+    for (long long i = 0; i < N; ++i) { const double yi = yh[i]; if (yi != 0.0) for (int j = 0; j < h->D; ++j) xty[j] += yi * Xh[(size_t)i * h->D + j]; }
+    CK(cudaMalloc(&h->g_xty, sizeof(double) * h->D));
+    CK(cudaMemcpyAsync(h->g_xty, xty.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
   }
   CK(cudaMemsetAsync(h->g_sc, 0, sizeof(double) * nsc * C, h->stream));
   CK(cudaMemsetAsync(h->g_vec, 0, sizeof(double) * nv * d * C, h->stream));
@@ -336,14 +344,16 @@ int ensure_glm_buffers(mcu_ctx* h) {
 
 int glm_gradient_dispatch(mcu_ctx* h, int N) {
   if (h->glm_impl == 1) {
-    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, h->g_part_g, h->stream) != 0)
+    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), h->stream) != 0)
       return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
-    glm_fold(h->g_part_lp, h->g_part_g, h->g_nslab_tc, h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc), h->D, h->C, h->g_lp, h->g_grad, h->stream);
+    glm_fold_tc(h->g_part_lp, reinterpret_cast<const float*>(h->g_part_g), h->g_nslab_tc, h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc), h->D, h->C,
+                h->g_req, h->g_xty, h->g_lp, h->g_grad, h->stream);
   } else {
     glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
                        h->g_lp, h->g_grad, h->stream);
+    h->launches += 1;
   }
-  h->launches += 3;
+  h->launches += 2;
   return MCU_OK;
 }
 
@@ -358,16 +368,24 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
   t.state = h->d_state; t.tune = h->d_tune + (size_t)b.tune_off * h->C; t.sc = h->g_sc; t.vec = h->g_vec; t.req = h->g_req;
   t.lp = h->g_lp; t.grad = h->g_grad; t.samples = a.samples; t.mom = h->d_mom; t.momn = h->d_momn; t.n_active = h->g_nactive;
   const int N = (int)h->inputs["y"].size();
+  // A tick = advance every chain to its next gradient request, then one gradient pass.  The host only looks at
+  // the running-chain counter every kCheck ticks (finished chains idle; at most kCheck - 1 passes are wasted at the end).
+  const int kCheck = 4;
+  int tick = 0;
   while (true) {
-    CK(cudaMemsetAsync(h->g_nactive, 0, sizeof(int), h->stream));
-    glm_advance(t, h->stream); h->launches++;
+    int slot = 0;
+    for (int k = 0; k < kCheck; ++k, ++tick) {
+      t.tick = tick; slot = tick & 1;
+      glm_advance(t, h->stream); h->launches++;
+      const int saved = h->glm_impl; if (h->glm_impl_run == 0) h->glm_impl = 0;
+      rc = glm_gradient_dispatch(h, N); h->glm_impl = saved;
+      if (rc) return rc;
+      h->ticks++;
+    }
     int active = 0;
-    CK(cudaMemcpyAsync(&active, h->g_nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&active, h->g_nactive + slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (active == 0) break;
-    { const int saved = h->glm_impl; if (h->glm_impl_run == 0) h->glm_impl = 0; rc = glm_gradient_dispatch(h, N); h->glm_impl = saved; }
-    if (rc) return rc;
-    h->ticks++;
   }
   return MCU_OK;
 }

@@ -49,11 +49,13 @@ struct GlmTickArgs {
   const double* lp;  // [C] likelihood logf at the requested position
   const double* grad;// [d][C] likelihood gradient
   double* samples; double* mom; double* momn;
-  int* n_active;
+  int* n_active;     // [2] ring: slot (tick & 1) counts chains still running after this tick
+  int tick;
 };
 
 __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) a.n_active[(a.tick + 1) & 1] = 0;   // the other slot was read by the host before this launch
   if (c >= a.C) return;
   const size_t C = (size_t)a.C;
   const int d = a.d;
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
     }
   }
   SC(SL_PHASE) = (double)phase; SC(SL_ITER) = (double)iter; SC(SL_JDRAW) = (double)rng.j;
-  if (phase != PH_DONE) atomicAdd(a.n_active, 1);
+  if (phase != PH_DONE) atomicAdd(&a.n_active[a.tick & 1], 1);
 #undef SC
 #undef VV
 #undef ST
@@ -378,9 +380,57 @@ void glm_grad_reference(const double* X, const double* y, int N, int d, long lon
   glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab, (long long)d * C, grad);
 }
 
+// lp[c] = sum_s part_lp[s][c]  and  grad[j][c] = sum_s part_g[s][j][c]  in one launch
+__global__ void glm_fold2_kernel(const double* __restrict__ part_lp, const double* __restrict__ part_g, int nslab_lp, int nslab_g,
+                                 long long C, long long dC, double* __restrict__ lp, double* __restrict__ grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dC) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= nslab_g; k += 4) {
+      s0 += part_g[(size_t)k * dC + i]; s1 += part_g[(size_t)(k + 1) * dC + i];
+      s2 += part_g[(size_t)(k + 2) * dC + i]; s3 += part_g[(size_t)(k + 3) * dC + i];
+    }
+    for (; k < nslab_g; ++k) s0 += part_g[(size_t)k * dC + i];
+    grad[i] = (s0 + s1) + (s2 + s3);
+  } else if (i < dC + C) {
+    const long long c = i - dC;
+    double s = 0.0;
+    for (int k = 0; k < nslab_lp; ++k) s += part_lp[(size_t)k * C + c];
+    lp[c] = s;
+  }
+}
+// tensor-core path: FP32 gradient partials, logf partials hold -sum softplus(eta); lp[c] = beta_c . (X'y) + sum_s part_lp[s][c]
+__global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const float* __restrict__ part_g, int nslab_lp, int nslab_g,
+                                   long long C, int d, const double* __restrict__ req, const double* __restrict__ xty,
+                                   double* __restrict__ lp, double* __restrict__ grad) {
+  const long long dC = (long long)d * C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dC) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= nslab_g; k += 4) {
+      s0 += (double)part_g[(size_t)k * dC + i]; s1 += (double)part_g[(size_t)(k + 1) * dC + i];
+      s2 += (double)part_g[(size_t)(k + 2) * dC + i]; s3 += (double)part_g[(size_t)(k + 3) * dC + i];
+    }
+    for (; k < nslab_g; ++k) s0 += (double)part_g[(size_t)k * dC + i];
+    grad[i] = (s0 + s1) + (s2 + s3);
+  } else if (i < dC + C) {
+    const long long c = i - dC;
+    double s = 0.0;
+    for (int k = 0; k < nslab_lp; ++k) s += part_lp[(size_t)k * C + c];
+    for (int j = 0; j < d; ++j) s += req[(size_t)j * C + c] * xty[j];
+    lp[c] = s;
+  }
+}
+void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
+                 const double* xty, double* lp, double* grad, cudaStream_t st) {
+  const long long dC = (long long)d * C;
+  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp, grad);
+}
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st) {
-  glm_fold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(part_lp, nslab_lp, C, lp);
-  glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab_g, (long long)d * C, grad);
+  const long long dC = (long long)d * C;
+  glm_fold2_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, dC, lp, grad);
 }
 
 void glm_advance(const GlmTick& t, cudaStream_t st) {
@@ -388,7 +438,7 @@ void glm_advance(const GlmTick& t, cudaStream_t st) {
   a.C = t.C; a.chain_offset = t.chain_offset; a.seed = t.seed; a.target_iter = t.target_iter; a.burnin = t.burnin; a.thin = t.thin;
   a.row0 = t.row0; a.d = t.d; a.max_depth = t.max_depth; a.target = t.target; a.eps_desc = t.eps_desc;
   a.state = t.state; a.tune = t.tune; a.sc = t.sc; a.vec = t.vec; a.req = t.req; a.lp = t.lp; a.grad = t.grad;
-  a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active;
+  a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active; a.tick = t.tick;
   glm_advance_kernel<<<(unsigned)((t.C + 127) / 128), 128, 0, st>>>(a);
 }
 

@@ -105,9 +105,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack_half2(__half lo, __half hi) {
   return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
@@ -139,7 +146,7 @@ __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __re
   vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
   *reinterpret_cast<uint4*>(tile + off) = vh;
   *reinterpret_cast<uint4*>(tile + (size_t)TR * DP * 2 + off) = vl;
-  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)y[grow] : -1.0f;   // -1 marks padding rows
+  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)y[grow] : 0.5f;   // padding rows: X = 0, so eta = 0 and r x = 0; their softplus(0) is added back below
 }
 
 struct TcArgs {
@@ -148,26 +155,29 @@ struct TcArgs {
   long long C;
   const double* req;         // [d][C]
   double* part_lp;           // [nslab][C]
-  double* part_g;            // [nslab * nsub][d][C]
+  float* part_g;             // [nslab * nsub][d][C]  FP32 flushes of the TMEM accumulator (summed in FP64 by the fold)
   int nsub;
+  int n_pad;                 // zero rows appended to the last tile
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-constexpr int kEpiThreads = 256;   // 8 epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 and column half w / 4
+constexpr int kEpiThreads = 512;   // 16 epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 and the 32-column quarter w / 4
 constexpr int kTcThreads = kEpiThreads + 32;   // + 1 issuer warp (bulk copies, tcgen05.mma, commits)
 
 // barrier slots in shared memory
-enum { B_FULL0 = 0, B_FULL1, B_D1FULL0, B_D1FULL1, B_D1EMPTY0, B_D1EMPTY1, B_RFULL, B_GDONE, B_GREAD, B_COUNT };
+enum { B_FULL0 = 0, B_FULL1, B_D1FULL0, B_D1FULL1, B_RFULL, B_GDONE, B_GREAD, B_COUNT };
 
 // Warp-specialised pipeline.  Per tile t (buffer b = t & 1):
-//   issuer  : GEMM1(t+1) → D1[b^1]  (runs under epilogue(t))     | waits: tile landed, D1[b^1] drained
-//             GEMM2(t)   → G        (after epilogue(t) stored R)  | waits: R stored, G read back if tile t-1 flushed
-//             bulk copy X(t+2) → buffer b once GEMM2(t) has completed
-//   epilogue: D1[b] → p, logf, R (split fp16) → tensor memory; every FLUSH tiles G → FP64 partial
-// TMEM columns: D1[0] 0-127, D1[1] 128-255, R_hi 256-319, R_lo 320-383, G 384-511.
+//   issuer  : GEMM2(t)   → G        as soon as epilogue(t) has stored R(t)
+//             bulk copy X(t+2) → buffer b once GEMM2(t) has completed, then GEMM1(t+2) → D1[b]
+//             (the tensor pipe runs GEMM2(t), GEMM1(t+2) while the 16 epilogue warps work on tile t+1)
+//   epilogue: D1[b] → p, logf, R (split fp16) written back INTO D1[b] (R_hi columns 0-63, R_lo 64-127, as
+//             FlashAttention keeps P where S was), so R is double buffered for free; every FLUSH tiles G → FP64 partial
+//             (16 warps = 4 per scheduler; the 4 warps that share a TMEM lane quarter sync before overwriting D1)
+// TMEM columns: D1[0] 0-127, D1[1] 128-255, G 256-383.
 __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -179,29 +189,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   unsigned char* th_lo = th_hi + op_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(th_lo + op_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-  double* lp_xchg = reinterpret_cast<double*>(bars + B_COUNT + 2);   // [128]
+  double* lp_xchg = reinterpret_cast<double*>(bars + B_COUNT + 2);   // [3][128]
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
   const int slab = blockIdx.y;
   const int t0 = slab * a.tiles_per_slab, t1 = min(a.NT, t0 + a.tiles_per_slab);
   const int T = max(0, t1 - t0);
 
-  if (warp == 8) {
+  if (warp == kEpiThreads / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
     mbar_init(bar(B_FULL0), 1); mbar_init(bar(B_FULL1), 1);
     mbar_init(bar(B_D1FULL0), 1); mbar_init(bar(B_D1FULL1), 1);
-    mbar_init(bar(B_D1EMPTY0), kEpiThreads); mbar_init(bar(B_D1EMPTY1), kEpiThreads);
     mbar_init(bar(B_RFULL), kEpiThreads); mbar_init(bar(B_GDONE), 1); mbar_init(bar(B_GREAD), kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // Theta tile: chain = row (tid % 128); the two column halves are split over tid / 128; split fp16, blocked layout
   if (tid < kEpiThreads) {
-    const int row = tid & 127, hf = tid >> 7;
+    const int row = tid & 127, grp = tid >> 7;
     const long long c = (long long)blockIdx.x * TM + row;
-    for (int cb = hf; cb < CB; cb += 2) {
+    for (int cb = grp; cb < CB; cb += kEpiThreads / 128) {
       __half hi[8], lo[8];
       for (int e = 0; e < 8; ++e) {
         const int col = cb * 8 + e;
@@ -223,14 +232,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_d1[2] = {tmem, tmem + 128};
-  const uint32_t tm_rh = tmem + 256, tm_rl = tmem + 320, tm_g = tmem + 384;
+  const uint32_t tm_g = tmem + 256;
 
   // instruction descriptors (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): F16 x F16 → F32, M = 128
   const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);                 // N = 128, A/B K-major
   const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(DP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);     // N = DP, B MN-major
   const uint32_t rb_stride = (uint32_t)CB * 128;   // bytes between 8-row blocks
 
-  if (warp == 8) {
+  if (warp == kEpiThreads / 32) {
     // ======================================================================= issuer (one elected lane)
     if ((tid & 31) == 0 && T > 0) {
       auto load_tile = [&](int t) {
@@ -256,40 +265,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
       mbar_wait(bar(B_FULL0), 0);
       tc_fence_after();
       gemm1(0);
-      int nflush = 0;          // flushes completed so far (= completions of B_GREAD the issuer has consumed)
+      if (T > 1) { mbar_wait(bar(B_FULL1), 0); tc_fence_after(); gemm1(1); }
+      int nflush = 0;          // completions of B_GREAD consumed so far
       bool prev_flushed = false;
       for (int t = 0; t < T; ++t) {
         const int b = t & 1;
-        if (t + 1 < T) {
-          mbar_wait(bar(B_FULL0 + (b ^ 1)), (uint32_t)(((t + 1) >> 1) & 1));
-          if (t + 1 >= 2) mbar_wait(bar(B_D1EMPTY0 + (b ^ 1)), (uint32_t)(((t - 1) >> 1) & 1));   // epilogue(t-1) drained D1[b^1]
-          tc_fence_after();
-          gemm1(t + 1);
-        }
-        mbar_wait(bar(B_RFULL), (uint32_t)(t & 1));                 // epilogue(t) stored R
+        mbar_wait(bar(B_RFULL), (uint32_t)(t & 1));                 // epilogue(t) stored R(t) into D1[b]
         if (prev_flushed) { mbar_wait(bar(B_GREAD), (uint32_t)(nflush & 1)); ++nflush; }   // G of the previous interval read back
         tc_fence_after();
         {   // GEMM2(t): G += R . X_t  (A = R from tensor memory, B = the X tile read MN-major)
           const uint32_t xh = smem_u32(xbuf[b]), xl = xh + op_bytes;
+          const uint32_t rh = tm_d1[b], rl = tm_d1[b] + 64;
           for (int kk = 0; kk < TR / 16; ++kk) {
             const uint32_t ko = (uint32_t)kk * 2 * rb_stride;       // two row-blocks per K step
             const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
-            mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbh, idesc2, ((t % FLUSH) != 0 || kk > 0) ? 1u : 0u);
-            mma_ts(tm_g, tm_rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
-            mma_ts(tm_g, tm_rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
+            mma_ts(tm_g, rh + (uint32_t)kk * 8, dbh, idesc2, ((t % FLUSH) != 0 || kk > 0) ? 1u : 0u);
+            mma_ts(tm_g, rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
+            mma_ts(tm_g, rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
           }
           tc_commit(bar(B_GDONE));
         }
         prev_flushed = (t % FLUSH) == FLUSH - 1 || t == T - 1;
         if (t + 2 < T) {
-          mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));               // GEMM2(t) complete → X buffer b is free
+          mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));               // GEMM2(t) complete → X buffer b and D1[b] are free
           load_tile(t + 2);
+          mbar_wait(bar(B_FULL0 + b), (uint32_t)(((t + 2) >> 1) & 1));
+          tc_fence_after();
+          gemm1(t + 2);
         }
       }
     }
   } else {
     // ======================================================================= epilogue warps
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;                         // lane quarter, column quarter
     const int lane_row = q * 32 + (tid & 31);                       // TMEM lane = chain row of this CTA
     const long long c = (long long)blockIdx.x * TM + lane_row;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -298,74 +306,88 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
       const int b = t & 1;
       mbar_wait(bar(B_D1FULL0 + b), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      const float* ytile = reinterpret_cast<const float*>(xbuf[b] + 2 * op_bytes);
-      float lp_tile = 0.0f;
-#pragma unroll 1
+      // y of this warp's 32 rows (shared memory, written by the bulk copy)
+      const float4* y4 = reinterpret_cast<const float4*>(smem + (size_t)b * tile_bytes + 2 * (size_t)op_bytes) + cq * 8;
+      float sp_sum = 0.0f;
+      // this warp's 32 columns of eta → registers; then the four warps of this lane quarter agree that all of D1[b]
+      // has been read before any of them overwrites it with R
+      uint32_t v0[16], v1[16];
+      tmem_ld16(tm_d1[b] + lane_off + (uint32_t)(cq * 32), v0);
+      tmem_ld16(tm_d1[b] + lane_off + (uint32_t)(cq * 32 + 16), v1);
+      tmem_wait_ld();
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+#pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        const int col0 = hf * 64 + ch * 32;
-        uint32_t v[32];
-        tmem_ld32(tm_d1[b] + lane_off + (uint32_t)col0, v);
-        tmem_wait_ld();
-        uint32_t ph[16], pl[16];
+        const int col0 = cq * 32 + ch * 16;
+        uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float r2[2];
+        for (int e = 0; e < 16; e += 4) {
+          const float4 yq = y4[ch * 4 + (e >> 2)];
+          const float yy[4] = {yq.x, yq.y, yq.z, yq.w};
+          float r4[4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float eta = __uint_as_float(v[e + u]);
-            const float yv = ytile[col0 + e + u];
-            const float ex = __expf(-fabsf(eta));
-            const float s = __fdividef(1.0f, 1.0f + ex);
+          for (int u = 0; u < 4; ++u) {
+            const float eta = __uint_as_float(ch == 0 ? v0[e + u] : v1[e + u]);
+            const float ex = exp2f_approx(-1.4426950408889634f * fabsf(eta));   // exp(-|eta|)
+            const float w = 1.0f + ex;
+            const float s = rcp_approx(w);                                      // invlogit(|eta|)
             const float p = eta >= 0.0f ? s : ex * s;
-            const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + ex);
-            const bool valid = yv >= 0.0f;
-            lp_tile += valid ? (yv * eta - sp) : 0.0f;
-            r2[u] = valid ? (yv - p) : 0.0f;
+            sp_sum += fmaf(lg2_approx(w), 0.6931471805599453f, fmaxf(eta, 0.0f));   // softplus(eta)
+            r4[u] = yy[u] - p;
           }
-          const __half2 h = __floats2half2_rn(r2[0], r2[1]);
-          const float2 hb = __half22float2(h);
-          const __half2 l = __floats2half2_rn(r2[0] - hb.x, r2[1] - hb.y);
-          ph[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          pl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+#pragma unroll
+          for (int u = 0; u < 4; u += 2) {
+            const __half2 h = __floats2half2_rn(r4[u], r4[u + 1]);
+            const float2 hb = __half22float2(h);
+            const __half2 l = __floats2half2_rn(r4[u] - hb.x, r4[u + 1] - hb.y);
+            ph[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            pl[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+          }
         }
-        if (ch == 1) { tc_fence_before(); mbar_arrive(bar(B_D1EMPTY0 + b)); }   // both chunks of D1[b] are in registers: the buffer may be overwritten
-        if (ch == 0 && t > 0) { mbar_wait(bar(B_GDONE), (uint32_t)((t - 1) & 1)); tc_fence_after(); }   // GEMM2(t-1) done: R is free
-        tmem_st16(tm_rh + lane_off + (uint32_t)(col0 >> 1), ph);
-        tmem_st16(tm_rl + lane_off + (uint32_t)(col0 >> 1), pl);
+        tmem_st8(tm_d1[b] + lane_off + (uint32_t)(col0 >> 1), ph);          // R_hi: columns 0-63 of D1[b]
+        tmem_st8(tm_d1[b] + lane_off + (uint32_t)(64 + (col0 >> 1)), pl);   // R_lo: columns 64-127
+      }
+      // logf contribution of the tile: -sum softplus(eta); the sum_i y_i eta_i part is beta . (X'y), added by the fold.
+      // Padding rows of the last tile have eta = 0: give their softplus(0) back.
+      float lp_tile = -sp_sum;
+      if (t0 + t == a.NT - 1 && a.n_pad > 0) {
+        const int first_pad = TR - a.n_pad;
+        const int lo_c = max(first_pad, cq * 32), hi_c = cq * 32 + 32;
+        if (hi_c > lo_c) lp_tile += (float)(hi_c - lo_c) * (lg2_approx(2.0f) * 0.6931471805599453f);
       }
       lp_acc += (double)lp_tile;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar(B_RFULL));
       if ((t % FLUSH) == FLUSH - 1 || t == T - 1) {
-        // ---- flush the gradient accumulator to this sub-slab's FP64 partial (column halves split over hf)
+        // ---- flush the gradient accumulator to this sub-slab's FP64 partial (16-column blocks dealt over cq)
         mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));
         tc_fence_after();
         const int sub = t / FLUSH;
-        for (int j0 = hf * 16; j0 < DP; j0 += 32) {
+        for (int j0 = cq * 16; j0 < DP; j0 += 64) {
           uint32_t v[16];
           tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
           if (c < a.C)
             for (int e = 0; e < 16; ++e)
-              if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = (double)__uint_as_float(v[e]);
+              if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = __uint_as_float(v[e]);
         }
         tc_fence_before();
         mbar_arrive(bar(B_GREAD));
       }
     }
-    // ---- this slab's logf partial (the two column halves of a chain are combined through shared memory)
-    if (hf == 1) lp_xchg[lane_row] = lp_acc;
+    // ---- this slab's logf partial (the four column quarters of a chain are combined through shared memory)
+    if (cq > 0) lp_xchg[(cq - 1) * 128 + lane_row] = lp_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
-    if (hf == 0 && c < a.C) {
-      a.part_lp[(size_t)slab * a.C + c] = lp_acc + lp_xchg[lane_row];
+    if (cq == 0 && c < a.C) {
+      a.part_lp[(size_t)slab * a.C + c] = ((lp_acc + lp_xchg[lane_row]) + lp_xchg[128 + lane_row]) + lp_xchg[256 + lane_row];
       const int used = T > 0 ? (T + FLUSH - 1) / FLUSH : 0;
       for (int sub = used; sub < a.nsub; ++sub)
-        for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0;
+        for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == kEpiThreads / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -384,14 +406,14 @@ int glm_tc_nsub(long long N, int nslab) {
   return (int)((tps + FLUSH - 1) / FLUSH);
 }
 
-// Returns 0 on success.  part_lp [nslab][C], part_g [nslab * nsub][d][C] (FP64), to be folded over slabs.
+// Returns 0 on success.  part_lp [nslab][C] (FP64, = -sum softplus), part_g [nslab * nsub][d][C] (FP32), to be folded over slabs.
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, double* part_g, cudaStream_t st) {
+                  double* part_lp, float* part_g, cudaStream_t st) {
   TcArgs a;
   a.DP = (d + 15) / 16 * 16;
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
-  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
-  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 8 * (B_COUNT + 2) + 128 * sizeof(double);
+  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
   if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);
   glm_tc_kernel<<<grid, kTcThreads, smem, st>>>(a);

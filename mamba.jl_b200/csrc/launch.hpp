@@ -55,7 +55,8 @@ struct GlmTick {
   double target, eps_desc;
   double* state; double* tune; double* sc; double* vec; double* req; const double* lp; const double* grad;
   double* samples; double* mom; double* momn;
-  int* n_active;
+  int* n_active;   // [2]
+  int tick;
 };
 size_t glm_tick_scalar_slots();
 size_t glm_tick_vector_slots();
@@ -69,7 +70,9 @@ long long glm_tc_num_tiles(long long N);
 int glm_tc_nsub(long long N, int nslab);
 void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* blob, cudaStream_t st);
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, double* part_g, cudaStream_t st);
+                  double* part_lp, float* part_g, cudaStream_t st);
+void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
+                 const double* xty, double* lp, double* grad, cudaStream_t st);
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st);
 
 }  // namespace mcu
