@@ -53,214 +53,198 @@ struct GlmTickArgs {
   int tick;
 };
 
+// One WARP per chain: the lanes stride over the d components of every vector (a thread-per-chain version spends its
+// time in d-long chains of dependent global loads/stores), scalars are read by all lanes and written by lane 0, dot
+// products are butterfly-reduced, and lane i draws the normal of component i from its own Philox counter.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) a.n_active[(a.tick + 1) & 1] = 0;   // the other slot was read by the host before this launch
+  const int lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.n_active[(a.tick + 1) & 1] = 0;   // the other slot was read by the host before this launch
   if (c >= a.C) return;
   const size_t C = (size_t)a.C;
   const int d = a.d;
 #define SC(s) a.sc[(size_t)(s) * C + c]
+#define SCW(s, v) do { if (lane == 0) a.sc[(size_t)(s) * C + c] = (v); } while (0)
 #define VV(v, i) a.vec[((size_t)(v) * d + (i)) * C + c]
 #define ST(i) a.state[(size_t)(i) * C + c]
 #define TN(s) a.tune[(size_t)(s) * C + c]
+#define TNW(s, v) do { if (lane == 0) a.tune[(size_t)(s) * C + c] = (v); } while (0)
 #define REQ(i) a.req[(size_t)(i) * C + c]
   int phase = (int)SC(SL_PHASE);
-  if (phase == PH_DONE && (long long)SC(SL_ITER) >= a.target_iter) { return; }
-  if (phase == PH_DONE) phase = PH_BEGIN;   // a later mcu_run continues the chain
-  Draws rng;
-  rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
-  rng.ext = nullptr; rng.ext_pos = nullptr; rng.ext_n = 0;
   long long iter = (long long)SC(SL_ITER);
-  rng.seek((uint32_t)iter, 0, 0); rng.j = (uint32_t)SC(SL_JDRAW);
+  if (phase == PH_DONE && iter >= a.target_iter) return;
+  if (phase == PH_DONE) phase = PH_BEGIN;   // a later mcu_run continues the chain
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), gchain = (uint32_t)(a.chain_offset + c);
+  uint32_t jdraw = (uint32_t)SC(SL_JDRAW);
+  auto words = [&](uint32_t j, uint32_t (&w)[4]) { philox4x32_10(j, (uint32_t)iter, gchain, 0u, k0, k1, w); };
+  auto uniform = [&]() { uint32_t w[4]; words(jdraw, w); ++jdraw; return u53(w[0], w[1]); };            // same value on every lane
+  auto normal_at = [&](uint32_t j) { uint32_t w[4]; words(j, w); return box_muller(u53(w[0], w[1]), u53(w[2], w[3])); };
+
+  // NUTS tune scalars are kept in registers while the chain advances
+  double t_adapt = TN(0), t_alpha = TN(1), t_eps = TN(2), t_epsbar = TN(3), t_Hbar = TN(4), t_m = TN(5), t_mu = TN(6), t_nalpha = TN(7);
 
   // pending result: full block density = MvNormal(d, sqrt(1000)) prior + likelihood (glm template, models.cuh)
   double lp_full = 0.0;
-  // Global-memory vector helpers.  Loads are staged through registers in chunks of kCh before the stores: a store
-  // to a.vec may alias the next load, so an element-by-element copy would pay one memory latency per element.
-  constexpr int kCh = 10;
   auto load_result = [&](int vslot_g) {
-    double sq = 0.0; bool fin = true;
-    for (int i0 = 0; i0 < d; i0 += kCh) {
-      double b[kCh], g[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { b[k] = REQ(i0 + k); g[k] = a.grad[(size_t)(i0 + k) * C + c]; }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) {
-        sq += b[k] * b[k]; fin = fin && isfinite(b[k]);
-        double gg = g[k] - b[k] / 1000.0;
-        if (!isfinite(gg)) gg = 0.0;                     // logpdfgrad!: sampler.jl:110
-        VV(vslot_g, i0 + k) = gg;
-      }
+    double sq = 0.0; int fin = 1;
+    for (int i = lane; i < d; i += 32) {
+      const double b = REQ(i);
+      double g = a.grad[(size_t)i * C + c] - b / 1000.0;
+      sq += b * b; fin &= isfinite(b) ? 1 : 0;
+      if (!isfinite(g)) g = 0.0;                       // logpdfgrad!: sampler.jl:110
+      VV(vslot_g, i) = g;
     }
+    sq = warp_sum(sq);
+    fin = __all_sync(0xffffffffu, fin);
     const double prior = fin ? lp_isonormal(sq, (double)d, sqrt(1000.0)) : neg_inf();
     lp_full = prior + a.lp[c];
   };
-  auto dotv = [&](int vs) { double s = 0; for (int i = 0; i < d; ++i) { const double x = VV(vs, i); s += x * x; } return s; };
-  auto copyv = [&](int dst, int src) {
-    for (int i0 = 0; i0 < d; i0 += kCh) {
-      double t[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) t[k] = VV(src, i0 + k);
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) VV(dst, i0 + k) = t[k];
-    }
-  };
-  auto copyv3 = [&](int d0, int s0, int d1, int s1, int d2, int s2) {   // three independent copies, loads batched
-    for (int i0 = 0; i0 < d; i0 += kCh) {
-      double t0[kCh], t1[kCh], t2[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { t0[k] = VV(s0, i0 + k); t1[k] = VV(s1, i0 + k); t2[k] = VV(s2, i0 + k); }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { VV(d0, i0 + k) = t0[k]; VV(d1, i0 + k) = t1[k]; VV(d2, i0 + k) = t2[k]; }
-    }
+  auto dotv = [&](int vs) { double s = 0; for (int i = lane; i < d; i += 32) { const double x = VV(vs, i); s += x * x; } return warp_sum(s); };
+  auto copyv = [&](int dst, int src) { for (int i = lane; i < d; i += 32) VV(dst, i) = VV(src, i); };
+  auto copyv3 = [&](int d0, int s0, int d1, int s1, int d2, int s2) {
+    for (int i = lane; i < d; i += 32) { const double x0 = VV(s0, i), x1 = VV(s1, i), x2 = VV(s2, i); VV(d0, i) = x0; VV(d1, i) = x1; VV(d2, i) = x2; }
   };
   auto nouturn = [&](int xminus, int xplus, int rminus, int rplus) {
     double p = 0, q = 0;
-    for (int i = 0; i < d; ++i) { const double df = VV(xplus, i) - VV(xminus, i); p += df * VV(rminus, i); q += df * VV(rplus, i); }
+    for (int i = lane; i < d; i += 32) { const double df = VV(xplus, i) - VV(xminus, i); p += df * VV(rminus, i); q += df * VV(rplus, i); }
+    p = warp_sum(p); q = warp_sum(q);
     return p >= 0 && q >= 0;
   };
-  auto request_cx = [&]() {
-    for (int i0 = 0; i0 < d; i0 += kCh) {
-      double t[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) t[k] = VV(V_CX, i0 + k);
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) REQ(i0 + k) = t[k];
-    }
-  };
-  // first half of a leapfrog from (cx, cr, cg): nuts.jl:130-131
+  // first half of a leapfrog from (cx, cr, cg) and the gradient request at the new position: nuts.jl:130-131
   auto half_step_and_request = [&](double eps) {
-    for (int i0 = 0; i0 < d; i0 += kCh) {
-      double r[kCh], g[kCh], x[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) { r[k] = VV(V_CR, i0 + k); g[k] = VV(V_CG, i0 + k); x[k] = VV(V_CX, i0 + k); }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) if (i0 + k < d) {
-        const double rn = r[k] + (0.5 * eps) * g[k]; const double xn = x[k] + eps * rn;
-        VV(V_CR, i0 + k) = rn; VV(V_CX, i0 + k) = xn; REQ(i0 + k) = xn;
-      }
+    for (int i = lane; i < d; i += 32) {
+      const double rn = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); const double xn = VV(V_CX, i) + eps * rn;
+      VV(V_CR, i) = rn; VV(V_CX, i) = xn; REQ(i) = xn;
     }
   };
+  // start of nuts_sub! (nuts.jl:97-98): r = randn(n), gradient request at the current sample
+  auto start_iteration_request = [&]() {
+    const bool adapt = iter <= a.burnin;
+    if (adapt && t_adapt == 0.0) { t_m = 0.0; t_mu = log(10.0 * t_eps); }    // setadapt!: nuts.jl:84-92
+    t_adapt = adapt ? 1.0 : 0.0;
+    if (adapt) t_m += 1.0; else if (t_m > 0.0) t_eps = t_epsbar;
+    SCW(SL_EPS_USE, t_eps);
+    for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_CR, i) = normal_at(jdraw + (uint32_t)i); VV(V_CX, i) = x; VV(V_CG, i) = 0.0; REQ(i) = x; }
+    jdraw += (uint32_t)d;
+  };
+  double eps_use = SC(SL_EPS_USE);
 
   bool need_grad = false;
   while (!need_grad) {
     switch (phase) {
       case PH_BEGIN: {
-        if (iter >= a.target_iter) { phase = PH_DONE; for (int i = 0; i < d; ++i) REQ(i) = ST(i); need_grad = true; break; }
-        iter += 1; rng.seek((uint32_t)iter, 0, 0);
+        if (iter >= a.target_iter) { phase = PH_DONE; for (int i = lane; i < d; i += 32) REQ(i) = ST(i); need_grad = true; break; }
+        iter += 1; jdraw = 0;
         if (iter == 1) {   // NUTSTune(x, nutsepsilon(x, f)): nuts.jl:17-30
-          TN(0) = 0.0; TN(1) = 0.0; TN(3) = 1.0; TN(4) = 0.0; TN(5) = 0.0; TN(6) = CUDART_NAN; TN(7) = 0.0;
-          if (a.eps_desc > 0.0) { TN(2) = a.eps_desc; phase = PH_START; }
+          t_adapt = 0.0; t_alpha = 0.0; t_epsbar = 1.0; t_Hbar = 0.0; t_m = 0.0; t_mu = CUDART_NAN; t_nalpha = 0.0;
+          if (a.eps_desc > 0.0) { t_eps = a.eps_desc; }
           else {           // nutsepsilon: nuts.jl:192-205 — r0 = randn(n); leapfrog(x, r0, 0, 0)
-            for (int i = 0; i < d; ++i) { VV(V_RM, i) = rng.normal(); VV(V_CX, i) = ST(i); }
-            request_cx(); phase = PH_EPS_INIT; need_grad = true; break;
+            for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_RM, i) = normal_at(jdraw + (uint32_t)i); VV(V_CX, i) = x; REQ(i) = x; }
+            jdraw += (uint32_t)d;
+            phase = PH_EPS_INIT; need_grad = true; break;
           }
-        } else phase = PH_START;
-        if (phase == PH_START) {
-          // sample!(v, f, adapt): nuts.jl:63-81 up to nuts_sub!'s first gradient request
-          const bool adapt = iter <= a.burnin;
-          if (adapt && TN(0) == 0.0) { TN(5) = 0.0; TN(6) = log(10.0 * TN(2)); }
-          TN(0) = adapt ? 1.0 : 0.0;
-          if (adapt) TN(5) = TN(5) + 1.0; else if (TN(5) > 0.0) TN(2) = TN(3);
-          SC(SL_EPS_USE) = TN(2);
-          for (int i = 0; i < d; ++i) { VV(V_CR, i) = rng.normal(); VV(V_CX, i) = ST(i); VV(V_CG, i) = 0.0; }
-          request_cx(); need_grad = true;
         }
+        start_iteration_request(); eps_use = t_eps;
+        phase = PH_START; need_grad = true;
         break;
       }
       case PH_EPS_INIT: {   // (logf0, grad0) at x0 arrived; r0 sits in V_RM, grad0 goes to V_GM
         load_result(V_GM);
-        SC(SL_EPS_LOGF0) = lp_full; SC(SL_EPS_D0) = dotv(V_RM);
-        SC(SL_EPS_TRY) = 1.0; SC(SL_EPS_PM) = 0.0; SC(SL_EPS_GUARD) = 0.0;
-        for (int i = 0; i < d; ++i) {   // trial leapfrog from (x0, r0, grad0) with eps = 1
-          const double r = VV(V_RM, i) + 0.5 * VV(V_GM, i);
-          VV(V_CR, i) = r; VV(V_CX, i) = ST(i) + 1.0 * r;
+        SCW(SL_EPS_LOGF0, lp_full); { const double d0 = dotv(V_RM); SCW(SL_EPS_D0, d0); }
+        SCW(SL_EPS_TRY, 1.0); SCW(SL_EPS_PM, 0.0); SCW(SL_EPS_GUARD, 0.0);
+        for (int i = lane; i < d; i += 32) {   // trial leapfrog from (x0, r0, grad0) with eps = 1
+          const double r = VV(V_RM, i) + 0.5 * VV(V_GM, i); const double x = ST(i) + 1.0 * r;
+          VV(V_CR, i) = r; VV(V_CX, i) = x; REQ(i) = x;
         }
-        request_cx(); phase = PH_EPS_TRIAL; need_grad = true;
+        phase = PH_EPS_TRIAL; need_grad = true;
         break;
       }
       case PH_EPS_TRIAL: {
         load_result(V_CG);
         double eps = SC(SL_EPS_TRY);
         double dr = 0.0;
-        for (int i = 0; i < d; ++i) { const double r = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); dr += r * r; }
+        for (int i = lane; i < d; i += 32) { const double r = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); dr += r * r; }
+        dr = warp_sum(dr);
         const double prob = exp(lp_full - SC(SL_EPS_LOGF0) - 0.5 * (dr - SC(SL_EPS_D0)));
         double pm = SC(SL_EPS_PM);
-        if (pm == 0.0) { pm = prob > 0.5 ? 1.0 : -1.0; SC(SL_EPS_PM) = pm; }
-        const double guard = SC(SL_EPS_GUARD) + 1.0; SC(SL_EPS_GUARD) = guard;
+        if (pm == 0.0) { pm = prob > 0.5 ? 1.0 : -1.0; }
+        const double guard = SC(SL_EPS_GUARD) + 1.0;
+        __syncwarp();
+        SCW(SL_EPS_PM, pm); SCW(SL_EPS_GUARD, guard);
         if (pow(prob, pm) > pow(0.5, pm) && guard <= 2000.0) {
-          eps *= pm > 0 ? 2.0 : 0.5; SC(SL_EPS_TRY) = eps;
-          for (int i = 0; i < d; ++i) {
-            const double r = VV(V_RM, i) + (0.5 * eps) * VV(V_GM, i);
-            VV(V_CR, i) = r; VV(V_CX, i) = ST(i) + eps * r;
+          eps *= pm > 0 ? 2.0 : 0.5; SCW(SL_EPS_TRY, eps);
+          for (int i = lane; i < d; i += 32) {
+            const double r = VV(V_RM, i) + (0.5 * eps) * VV(V_GM, i); const double x = ST(i) + eps * r;
+            VV(V_CR, i) = r; VV(V_CX, i) = x; REQ(i) = x;
           }
-          request_cx(); need_grad = true;
+          need_grad = true;
         } else {
-          TN(2) = eps;
-          const bool adapt = iter <= a.burnin;
-          if (adapt && TN(0) == 0.0) { TN(5) = 0.0; TN(6) = log(10.0 * TN(2)); }
-          TN(0) = adapt ? 1.0 : 0.0;
-          if (adapt) TN(5) = TN(5) + 1.0; else if (TN(5) > 0.0) TN(2) = TN(3);
-          SC(SL_EPS_USE) = TN(2);
-          for (int i = 0; i < d; ++i) { VV(V_CR, i) = rng.normal(); VV(V_CX, i) = ST(i); VV(V_CG, i) = 0.0; }
-          request_cx(); phase = PH_START; need_grad = true;
+          t_eps = eps;
+          start_iteration_request(); eps_use = t_eps;
+          phase = PH_START; need_grad = true;
         }
         break;
       }
       case PH_START: {   // nuts_sub!: nuts.jl:97-105 after the eps = 0 leapfrog
         load_result(V_CG);
         const double logp0 = lp_full - 0.5 * dotv(V_CR);
-        SC(SL_LOGP0) = logp0; SC(SL_LOGU0) = logp0 + log(rng.uniform());
+        const double logu0 = logp0 + log(uniform());
+        SCW(SL_LOGP0, logp0); SCW(SL_LOGU0, logu0);
         copyv3(V_XM, V_CX, V_RM, V_CR, V_GM, V_CG); copyv3(V_XP, V_CX, V_RP, V_CR, V_GP, V_CG);
-        SC(SL_J) = 0.0; SC(SL_N) = 1.0;
-        // first doubling
-        const double pm = rng.uniform() > 0.5 ? 1.0 : -1.0;   // both edges equal the start point
-        SC(SL_PM) = pm; SC(SL_T) = 0.0; SC(SL_ALPHA) = 0.0; SC(SL_NALPHA) = 0.0;
-        half_step_and_request(pm * SC(SL_EPS_USE));
+        SCW(SL_J, 0.0); SCW(SL_N, 1.0);
+        const double pm = uniform() > 0.5 ? 1.0 : -1.0;   // first doubling; both edges equal the start point
+        SCW(SL_PM, pm); SCW(SL_T, 0.0); SCW(SL_ALPHA, 0.0); SCW(SL_NALPHA, 0.0);
+        half_step_and_request(pm * eps_use);
         phase = PH_LEAF; need_grad = true;
         break;
       }
       case PH_LEAF: {    // buildtree leaf (nuts.jl:142-152) + the unrolled merges (samplers.cuh nuts_sub)
         load_result(V_CG);
-        const double pm = SC(SL_PM), eps = pm * SC(SL_EPS_USE);
+        const double pm = SC(SL_PM), eps = pm * eps_use;
         double dotr = 0.0;
-        for (int i0 = 0; i0 < d; i0 += kCh) {
-          double r[kCh], g[kCh];
-#pragma unroll
-          for (int k = 0; k < kCh; ++k) if (i0 + k < d) { r[k] = VV(V_CR, i0 + k); g[k] = VV(V_CG, i0 + k); }
-#pragma unroll
-          for (int k = 0; k < kCh; ++k) if (i0 + k < d) { const double rn = r[k] + (0.5 * eps) * g[k]; VV(V_CR, i0 + k) = rn; dotr += rn * rn; }
-        }
+        for (int i = lane; i < d; i += 32) { const double rn = VV(V_CR, i) + (0.5 * eps) * VV(V_CG, i); VV(V_CR, i) = rn; dotr += rn * rn; }
+        dotr = warp_sum(dotr);
         const double logu0 = SC(SL_LOGU0), logp0 = SC(SL_LOGP0);
         const double logpp = lp_full - 0.5 * dotr;
         double Tn = logu0 < logpp ? 1.0 : 0.0;
         bool Ts = logu0 < logpp + 1000.0;
-        SC(SL_ALPHA) = SC(SL_ALPHA) + fmin(1.0, exp(logpp - logp0));
-        SC(SL_NALPHA) = SC(SL_NALPHA) + 1.0;
-        copyv3(V_TXF, V_CX, V_TRF, V_CR, V_TXP, V_CX);
+        const double alpha = SC(SL_ALPHA) + fmin(1.0, exp(logpp - logp0));
+        const double nalpha = SC(SL_NALPHA) + 1.0;
         const int j = (int)SC(SL_J); const unsigned t = (unsigned)SC(SL_T);
+        double n = SC(SL_N);
+        __syncwarp();
+        SCW(SL_ALPHA, alpha); SCW(SL_NALPHA, nalpha);
+        copyv3(V_TXF, V_CX, V_TRF, V_CR, V_TXP, V_CX);
+        __syncwarp();
         int l = 0;
         bool parked = false;
         while (l < j) {
           const int sxf = V_SXF0 + 3 * l, srf = sxf + 1, sxp = sxf + 2;
           if ((t >> l) & 1u) {
-            const double u = rng.uniform();
+            const double u = uniform();
             const double nA = SC(SL_SN0 + l);
             if (!(u < Tn / (nA + Tn))) copyv(V_TXP, sxp);
             Tn = nA + Tn;
             const bool ok = pm > 0 ? nouturn(sxf, V_CX, srf, V_CR) : nouturn(V_CX, sxf, V_CR, srf);
             Ts = Ts && ok;
             copyv(V_TXF, sxf); copyv(V_TRF, srf);
+            __syncwarp();
             ++l;
           } else if (Ts) {
-            copyv3(sxf, V_TXF, srf, V_TRF, sxp, V_TXP); SC(SL_SN0 + l) = Tn;
+            copyv3(sxf, V_TXF, srf, V_TRF, sxp, V_TXP); SCW(SL_SN0 + l, Tn);
             parked = true; break;
           } else {
             ++l;
           }
         }
         if (parked) {      // build the sibling: next leaf
-          SC(SL_T) = (double)(t + 1);
+          SCW(SL_T, (double)(t + 1));
           half_step_and_request(eps);
           need_grad = true;
           break;
@@ -268,42 +252,44 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
         // tree of depth j complete (or failed): nuts.jl:108-123
         if (pm < 0) copyv3(V_XM, V_CX, V_RM, V_CR, V_GM, V_CG);
         else copyv3(V_XP, V_CX, V_RP, V_CR, V_GP, V_CG);
-        double n = SC(SL_N);
-        if (Ts) { if (rng.uniform() < Tn / n) for (int i = 0; i < d; ++i) ST(i) = VV(V_TXP, i); }
+        __syncwarp();
+        if (Ts) { if (uniform() < Tn / n) for (int i = lane; i < d; i += 32) ST(i) = VV(V_TXP, i); }
         const int jn = j + 1;
-        n += Tn; SC(SL_N) = n; SC(SL_J) = (double)jn;
+        n += Tn;
         bool s = Ts && nouturn(V_XM, V_XP, V_RM, V_RP);
         if (jn >= a.max_depth) s = false;
-        TN(1) = SC(SL_ALPHA); TN(7) = SC(SL_NALPHA);
+        t_alpha = alpha; t_nalpha = nalpha;
+        SCW(SL_N, n); SCW(SL_J, (double)jn);
         if (s) {           // next doubling
-          const double pm2 = rng.uniform() > 0.5 ? 1.0 : -1.0;
-          SC(SL_PM) = pm2; SC(SL_T) = 0.0; SC(SL_ALPHA) = 0.0; SC(SL_NALPHA) = 0.0;
+          const double pm2 = uniform() > 0.5 ? 1.0 : -1.0;
+          SCW(SL_PM, pm2); SCW(SL_T, 0.0); SCW(SL_ALPHA, 0.0); SCW(SL_NALPHA, 0.0);
           if (pm2 < 0) copyv3(V_CX, V_XM, V_CR, V_RM, V_CG, V_GM);
           else copyv3(V_CX, V_XP, V_CR, V_RP, V_CG, V_GP);
-          half_step_and_request(pm2 * SC(SL_EPS_USE));
+          __syncwarp();
+          half_step_and_request(pm2 * eps_use);
           need_grad = true;
           break;
         }
         // end of the iteration: dual averaging (nuts.jl:70-75), thinning (mcmc.jl:76-78)
-        if (TN(0) != 0.0) {
-          const double m = TN(5);
+        if (t_adapt != 0.0) {
+          const double m = t_m;
           double p = 1.0 / (m + 10.0);
-          const double Hbar = (1.0 - p) * TN(4) + p * (a.target - TN(1) / TN(7));
-          TN(4) = Hbar;
-          const double e2 = exp(TN(6) - sqrt(m) * Hbar / 0.05);
-          TN(2) = e2;
+          t_Hbar = (1.0 - p) * t_Hbar + p * (a.target - t_alpha / t_nalpha);
+          t_eps = exp(t_mu - sqrt(m) * t_Hbar / 0.05);
           p = pow(m, -0.75);
-          TN(3) = exp(p * log(e2) + (1.0 - p) * log(TN(3)));
+          t_epsbar = exp(p * log(t_eps) + (1.0 - p) * log(t_epsbar));
         }
+        __syncwarp();
         if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {
           const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
-          if (a.samples) for (int i = 0; i < d; ++i) a.samples[((size_t)row * d + i) * C + c] = ST(i);
-          // streaming moments, one column at a time (same update as engine.cuh moments_update)
-          const double nk = a.momn[c] + 1.0; a.momn[c] = nk;
+          if (a.samples) for (int i = lane; i < d; i += 32) a.samples[((size_t)row * d + i) * C + c] = ST(i);
+          // streaming moments, one monitored column per lane step (same update as engine.cuh moments_update)
+          const double nk = a.momn[c] + 1.0;
           double bc = a.momn[C + c] + 1.0; const bool bdone = bc >= (double)kBatch; double nb = a.momn[2 * C + c];
-          if (bdone) { bc = 0.0; nb += 1.0; a.momn[2 * C + c] = nb; }
-          a.momn[C + c] = bc;
-          for (int i = 0; i < d; ++i) {
+          if (bdone) { bc = 0.0; nb += 1.0; }
+          __syncwarp();
+          if (lane == 0) { a.momn[c] = nk; a.momn[C + c] = bc; a.momn[2 * C + c] = nb; }
+          for (int i = lane; i < d; i += 32) {
             double* q = a.mom + (size_t)i * kMomPerCol * C + c;
             const double x = ST(i);
             double mean = q[0], M2 = q[C]; double dl = x - mean; mean += dl / nk; M2 += dl * (x - mean); q[0] = mean; q[C] = M2;
@@ -320,12 +306,19 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
       default: need_grad = true; break;
     }
   }
-  SC(SL_PHASE) = (double)phase; SC(SL_ITER) = (double)iter; SC(SL_JDRAW) = (double)rng.j;
-  if (phase != PH_DONE) atomicAdd(&a.n_active[a.tick & 1], 1);
+  __syncwarp();
+  if (lane == 0) {
+    a.sc[(size_t)SL_PHASE * C + c] = (double)phase; a.sc[(size_t)SL_ITER * C + c] = (double)iter; a.sc[(size_t)SL_JDRAW * C + c] = (double)jdraw;
+    a.tune[0 * C + c] = t_adapt; a.tune[1 * C + c] = t_alpha; a.tune[2 * C + c] = t_eps; a.tune[3 * C + c] = t_epsbar;
+    a.tune[4 * C + c] = t_Hbar; a.tune[5 * C + c] = t_m; a.tune[6 * C + c] = t_mu; a.tune[7 * C + c] = t_nalpha;
+    if (phase != PH_DONE) atomicAdd(&a.n_active[a.tick & 1], 1);
+  }
 #undef SC
+#undef SCW
 #undef VV
 #undef ST
 #undef TN
+#undef TNW
 #undef REQ
 }
 
@@ -439,7 +432,7 @@ void glm_advance(const GlmTick& t, cudaStream_t st) {
   a.row0 = t.row0; a.d = t.d; a.max_depth = t.max_depth; a.target = t.target; a.eps_desc = t.eps_desc;
   a.state = t.state; a.tune = t.tune; a.sc = t.sc; a.vec = t.vec; a.req = t.req; a.lp = t.lp; a.grad = t.grad;
   a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active; a.tick = t.tick;
-  glm_advance_kernel<<<(unsigned)((t.C + 127) / 128), 128, 0, st>>>(a);
+  glm_advance_kernel<<<(unsigned)((t.C + 3) / 4), 128, 0, st>>>(a);   // one warp per chain, 4 chains per block
 }
 
 }  // namespace mcu

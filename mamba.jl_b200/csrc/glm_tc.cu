@@ -414,10 +414,15 @@ int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const do
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
   a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
   const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
-  if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  static thread_local size_t smem_set[64] = {0};   // per device: the attribute call is slow, do it once per size
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || smem_set[dev] != smem) {
+    if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+  }
   dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);
   glm_tc_kernel<<<grid, kTcThreads, smem, st>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return 0;   // launch errors surface at the next synchronisation of the handle's stream
 }
 
 }  // namespace mcu
