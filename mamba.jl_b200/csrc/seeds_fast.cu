@@ -11,14 +11,21 @@
 //     ratio is formed from term differences — 68 term evaluations per iteration instead of 29 x 21;
 //   * the (x1, x2) design has four distinct rows, so eta_i = g[group_i] + b_i with four cached group
 //     bases, evaluated in the reference's summation order;
-//   * the s2 update uses the sufficient statistic sum b_i^2.
+//   * the s2 update uses the sufficient statistic sum b_i^2;
+//   * e_i = exp(eta_i) and L_i = log(1 + e_i) are cached per plate: an alpha proposal shifts every affected eta_i by
+//     the same step z, so e_i' = e_i * exp(z) needs ONE exp per proposal and one log per affected plate
+//     (ll_i' - ll_i = r_i z - n_i (L_i' - L_i)); a b_i proposal recomputes e_i = exp(eta_i) afresh, which also stops
+//     the rounding drift of the multiplicative updates;
+//   * exp / log are own FP64 routines (fdlibm-style reductions, coefficients in __constant__ memory so the DFMAs take
+//     them as constant-bank operands instead of two UMOVs each — 20 % of all issued instructions before).
 // The accept/reject decisions are those of the reference on the same uniform stream: the same draws
 // (Philox counter j = position of the draw inside the block update, rng.cuh), the same proposal, and a
 // log-ratio equal to logf(x') - logf(x) up to rounding (~1e-14; tests/test_gpu_parity.py compares
 // whole trajectories against the oracle and against the generic kernel).
 //
-// Layout: alpha, log s2 and their tune state live in registers; b, the term caches, sigma_b and the
-// b accept counters live in shared memory as [element][thread] (conflict-free 8-byte lanes); plate
+// Layout: alpha, log s2 and their tune state live in registers; b, e, L and the proposed L live in shared memory
+// as [element][thread] (conflict-free 8-byte lanes); sigma_b and the b accept counters stay in the (L2-resident)
+// tune array and are touched once per plate per iteration; plate
 // constants sit in the kernel-parameter constant bank and are read with warp-uniform indices.
 // FP64 throughout (the reference is Float64; a decision taken in FP32 would flip ~1e-7 of the time).
 #include "launch.hpp"
@@ -31,6 +38,7 @@ constexpr int NPL = SeedsModel::NP;   // 21 plates
 
 struct FastCfg {
   double r[NPL], n[NPL];
+  double rsum[4];                     // sum of r_i over the plates that depend on alpha_j
   unsigned char grp[NPL];             // 0:(x1=0,x2=0) 1:(0,1) 2:(1,0) 3:(1,1)
   unsigned amask[4];                  // plates whose eta depends on alpha_j
   unsigned gmask[4];                  // groups whose base depends on alpha_j
@@ -50,6 +58,52 @@ MCU_D double draw_normal(const RunArgs& a, uint32_t chain, uint32_t iter, uint32
   return box_muller(u53(w[0], w[1]), u53(w[2], w[3]));
 }
 
+// ---- FP64 exp / log with constant-bank coefficients ------------------------------------------------------
+__constant__ double kExpC[12] = {   // 1/n!, n = 13 .. 2 (Horner order); |r| <= ln2/2 ⇒ truncation < 5e-18
+  1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.755731922398589e-06,
+  2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
+  1.6666666666666666e-01, 0.5};
+__constant__ double kLogC[7] = {   // fdlibm e_log.c Lg7 .. Lg1
+  1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01, 2.222219843214978396e-01,
+  2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01};
+
+// exp(x) for |x| < 700 (callers clamp): x = k ln2 + r, exp(r) by a degree-13 Taylor polynomial, 2^k through the exponent field
+MCU_D double fast_exp(double x) {
+  const double kf = rint(x * 1.4426950408889634074);
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
+  p = fma(p * r, r, r) + 1.0;                           // 1 + r + r^2 (1/2 + r (1/6 + ...))
+  const int k = (int)kf;
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+// log(x) for normal positive x (fdlibm e_log.c): x = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m - 1, s = f / (2 + f)
+MCU_D double fast_log(double x) {
+  int hx = __double2hiint(x);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int adj = (hx + 0x95f64) & 0x100000;            // mantissa above sqrt(2): halve m, k += 1
+  k += adj >> 20;
+  const double m = __hiloint2double(hx | (adj ^ 0x3ff00000), __double2loint(x));
+  const double f = m - 1.0;
+  const double dnm = 2.0 + f;
+  double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(dnm));
+  y = fma(fma(-dnm, y, 1.0), y, y);
+  y = fma(fma(-dnm, y, 1.0), y, y);                     // 1 / (2 + f) to full precision
+  const double sq = f * y;
+  const double z = sq * sq;
+  double R = kLogC[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) R = fma(R, z, kLogC[i]);
+  R *= z;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)k;
+  // log(1+f) = f - (hfsq - s (hfsq + R));  result = k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
+  return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+}
+
 // r log p + (n - r) log(1 - p) with p = invlogit(eta), written as r eta - n softplus(eta)
 MCU_D double binlogit_term(double r, double n, double eta) {
   const double e = exp(-fabs(eta));
@@ -58,7 +112,8 @@ MCU_D double binlogit_term(double r, double n, double eta) {
 
 MCU_D bool mh_accept(double u, double delta) {   // rand() < exp(logfprime - logf0): amwg.jl:107
   if (delta >= 0.0) return true;                  // u < 1 <= exp(delta)
-  return u < exp(delta);
+  if (!(delta > -700.0)) return false;            // exp underflows (or delta is NaN): u < 0 never holds
+  return u < fast_exp(delta);
 }
 
 struct Bases { double g0, g1, g2, g3; };
@@ -83,20 +138,20 @@ template <int BS>
 __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   double* sb = smem;                        // b[i]
-  double* sll = smem + NPL * BS;            // ll[i]
-  double* sln = smem + 2 * NPL * BS;        // proposed ll[i]
-  double* ssg = smem + 3 * NPL * BS;        // sigma_b[i]
-  int* sac = reinterpret_cast<int*>(smem + 4 * NPL * BS);   // accept_b[i]
+  double* se = smem + NPL * BS;             // e[i] = exp(eta_i)
+  double* sll = smem + 2 * NPL * BS;        // L[i] = log(1 + e[i])
+  double* sln = smem + 3 * NPL * BS;        // proposed L[i]
   const int tid = threadIdx.x;
   const long long c = (long long)blockIdx.x * BS + tid;
   if (c >= a.n_chains) return;
   const size_t C = (size_t)a.n_chains;
   const uint32_t chain = (uint32_t)(a.chain_offset + c);
 #define SB(i) sb[(i) * BS + tid]
+#define SE(i) se[(i) * BS + tid]
 #define SLL(i) sll[(i) * BS + tid]
 #define SLN(i) sln[(i) * BS + tid]
-#define SSG(i) ssg[(i) * BS + tid]
-#define SAC(i) sac[(i) * BS + tid]
+#define SSG(i) TUNE(1, 2 + (i))
+#define SAC(i) TUNE(1, 2 + NPL + (i))
 #define TUNE(blk, slot) a.tune[(size_t)(cfg.tune_off[blk] + (slot)) * C + c]
 
   // ---- load chain state -------------------------------------------------------------------------
@@ -109,11 +164,10 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
   bool ad0 = TUNE(0, 1) != 0.0, ad1 = TUNE(1, 1) != 0.0, ad2 = TUNE(2, 1) != 0.0;
   double sg0 = TUNE(0, 2), sg1 = TUNE(0, 3), sg2 = TUNE(0, 4), sg3 = TUNE(0, 5);
   int ac0 = (int)TUNE(0, 6), ac1 = (int)TUNE(0, 7), ac2 = (int)TUNE(0, 8), ac3 = (int)TUNE(0, 9);
-  for (int i = 0; i < NPL; ++i) { SSG(i) = TUNE(1, 2 + i); SAC(i) = (int)TUNE(1, 2 + NPL + i); }
   double sgs = TUNE(2, 2); int acs = (int)TUNE(2, 3);
 
   Bases g = group_bases(al0, al1, al2, al3);
-  for (int i = 0; i < NPL; ++i) SLL(i) = binlogit_term(cfg.r[i], cfg.n[i], pick(g, cfg.grp[i]) + SB(i));
+  for (int i = 0; i < NPL; ++i) { const double e = fast_exp(pick(g, cfg.grp[i]) + SB(i)); SE(i) = e; SLL(i) = fast_log(1.0 + e); }
 
   double mon[SeedsModel::P];
   for (long long it = 1; it <= a.iters; ++it) {
@@ -123,7 +177,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       m0 = m1 = m2 = 0.0; ad0 = ad1 = ad2 = false;
       sg0 = cfg.scale_a[0]; sg1 = cfg.scale_a[1]; sg2 = cfg.scale_a[2]; sg3 = cfg.scale_a[3];
       ac0 = ac1 = ac2 = ac3 = 0;
-      for (int i = 0; i < NPL; ++i) { SSG(i) = cfg.scale_b[i]; SAC(i) = 0; }
+      for (int i = 0; i < NPL; ++i) { SSG(i) = cfg.scale_b[i]; SAC(i) = 0.0; }
       sgs = cfg.scale_s; acs = 0;
     }
     // ================================================================== block 0: AMWG(alpha0..alpha12)
@@ -144,13 +198,16 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
         const double q2 = j == 0 ? al2 : (j == 1 ? al1 : (j == 2 ? anew : al3));
         const double q3 = j == 0 ? al3 : (j == 1 ? al2 : (j == 2 ? al1 : anew));
         const Bases gn = group_bases(q0, q1, q2, q3);
-        double delta = 0.0;
+        // every affected plate moves by the same step: e_i' = e_i exp(z); ll_i' - ll_i = r_i z - n_i (L_i' - L_i)
+        const double E = fast_exp(z);
+        double dL = 0.0;
         for (int i = 0; i < NPL; ++i) {
           if (!((pm >> i) & 1u)) continue;
-          const double ln = binlogit_term(cfg.r[i], cfg.n[i], pick(gn, cfg.grp[i]) + SB(i));
+          const double ln = fast_log(fma(SE(i), E, 1.0));
           SLN(i) = ln;
-          delta += ln - SLL(i);
+          dL = fma(cfg.n[i], ln - SLL(i), dL);
         }
+        double delta = fma(cfg.rsum[j], z, -dL);
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
           const double zo = al0 / 1000.0, zn = anew / 1000.0;
           delta += -(zn * zn - zo * zo) / 2.0;
@@ -159,7 +216,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
         if (mh_accept(u, delta)) {
           al0 = anew;
           g = gn;   // bases of groups that do not contain alpha_j are recomputed to the same value
-          for (int i = 0; i < NPL; ++i) if ((pm >> i) & 1u) SLL(i) = SLN(i);
+          for (int i = 0; i < NPL; ++i) if ((pm >> i) & 1u) { SLL(i) = SLN(i); SE(i) = SE(i) * E; }
           if (adapt) ac0 += 1;
         }
         // rotate (alpha, sigma, accept) so the next component sits in slot 0
@@ -178,24 +235,26 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
     // ================================================================== block 1: AMWG(b)
     {
       const bool adapt = cfg.adapt[1] == 1 ? iter <= a.burnin : cfg.adapt[1] == 0;
-      if (adapt && !ad1) { for (int i = 0; i < NPL; ++i) SAC(i) = 0; m1 = 0.0; }
+      if (adapt && !ad1) { for (int i = 0; i < NPL; ++i) SAC(i) = 0.0; m1 = 0.0; }
       ad1 = adapt;
       if (adapt) m1 += 1.0;
       const double sigma = sqrt(s2);                                      // b ~ Normal(0, sqrt(s2)): seeds.jl:31-32
 #pragma unroll 1
       for (int i = 0; i < NPL; ++i) {
+        const double sg = SSG(i);                                          // global (L2) load, issued ahead of its use
         const double bi = SB(i);
-        const double bn = bi + SSG(i) * draw_normal(a, chain, it32, 1, i);
-        const double ln = binlogit_term(cfg.r[i], cfg.n[i], pick(g, cfg.grp[i]) + bn);
+        const double bn = bi + sg * draw_normal(a, chain, it32, 1, i);
+        const double en = fast_exp(pick(g, cfg.grp[i]) + bn);            // fresh e_i: also resets the drift of the alpha updates
+        const double ln = fast_log(1.0 + en);
         const double zo = bi / sigma, zn = bn / sigma;
-        const double delta = (ln - SLL(i)) + (-(zn * zn - zo * zo) / 2.0);
+        const double delta = fma(cfg.r[i], bn - bi, -cfg.n[i] * (ln - SLL(i))) + (-(zn * zn - zo * zo) / 2.0);
         const double u = draw_uniform(a, chain, it32, 1, NPL + i);
-        if (mh_accept(u, delta)) { SB(i) = bn; SLL(i) = ln; if (adapt) SAC(i) += 1; }
+        if (mh_accept(u, delta)) { SB(i) = bn; SE(i) = en; SLL(i) = ln; if (adapt) SAC(i) = SAC(i) + 1.0; }
       }
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
         const double dl = amwg_delta(m1, cfg.batchsize[1]);
         const double up = exp(dl), dn = exp(-dl);
-        for (int i = 0; i < NPL; ++i) SSG(i) *= ((double)SAC(i) / m1 < cfg.target[1]) ? dn : up;
+        for (int i = 0; i < NPL; ++i) SSG(i) = SSG(i) * ((SAC(i) / m1 < cfg.target[1]) ? dn : up);
       }
     }
     // ================================================================== block 2: AMWG(s2) on x = log s2
@@ -207,7 +266,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
       const double xn = x + sgs * draw_normal(a, chain, it32, 2, 0);
-      const double s2n = exp(xn);
+      const double s2n = (xn > -700.0 && xn < 700.0) ? fast_exp(xn) : exp(xn);
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
       //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double dx = xn - x;
@@ -238,9 +297,9 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
   TUNE(0, 2) = sg0; TUNE(0, 3) = sg1; TUNE(0, 4) = sg2; TUNE(0, 5) = sg3;
   TUNE(0, 6) = ac0; TUNE(0, 7) = ac1; TUNE(0, 8) = ac2; TUNE(0, 9) = ac3;
   TUNE(1, 0) = m1; TUNE(1, 1) = ad1 ? 1.0 : 0.0;
-  for (int i = 0; i < NPL; ++i) { TUNE(1, 2 + i) = SSG(i); TUNE(1, 2 + NPL + i) = SAC(i); }
   TUNE(2, 0) = m2; TUNE(2, 1) = ad2 ? 1.0 : 0.0; TUNE(2, 2) = sgs; TUNE(2, 3) = acs;
 #undef SB
+#undef SE
 #undef SLL
 #undef SLN
 #undef SSG
@@ -250,7 +309,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
 
 template <int BS>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)BS * (4 * NPL * sizeof(double) + NPL * sizeof(int));
+  const size_t smem = (size_t)BS * 4 * NPL * sizeof(double);
   if (cudaFuncSetAttribute(seeds_fast_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)((a.n_chains + BS - 1) / BS);
   seeds_fast_kernel<BS><<<grid, BS, smem, st>>>(cfg, a);
@@ -285,6 +344,7 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
     if (x2[i] != 0.0) cfg.amask[2] |= 1u << i;
     if (x1[i] != 0.0 && x2[i] != 0.0) cfg.amask[3] |= 1u << i;
   }
+  for (int j = 0; j < 4; ++j) { cfg.rsum[j] = 0.0; for (int i = 0; i < NPL; ++i) if ((cfg.amask[j] >> i) & 1u) cfg.rsum[j] += r[i]; }
   cfg.gmask[0] = 0xFu; cfg.gmask[1] = 0xCu; cfg.gmask[2] = 0xAu; cfg.gmask[3] = 0x8u;
   cfg.scale_s = ss[0];
   for (int b = 0; b < 3; ++b) {
