@@ -59,6 +59,7 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  void* d_stage = nullptr; size_t stage_cap = 0;   // reusable device staging buffer (no cudaMalloc/cudaFree on the hot API calls)
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
   int* g_nactive = nullptr; int g_nslab = 0;
@@ -78,6 +79,19 @@ namespace {
   } while (0)
 
 int fail(mcu_handle h, int code, const std::string& msg) { h->err = msg; return code; }
+
+// Returns a device buffer of at least `bytes` that lives as long as the handle; contents are scratch.
+int stage(mcu_ctx* h, size_t bytes, void** out) {
+  if (bytes > h->stage_cap) {
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr; h->stage_cap = 0;
+    cudaError_t e = cudaMalloc(&h->d_stage, bytes);
+    if (e != cudaSuccess) { h->err = std::string("cudaMalloc(stage): ") + cudaGetErrorString(e); return MCU_ERR_CUDA; }
+    h->stage_cap = bytes;
+  }
+  *out = h->d_stage;
+  return MCU_OK;
+}
 
 inline unsigned grid_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -437,7 +451,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
-  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
   return MCU_OK;
@@ -575,7 +589,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   int rc = upload_inputs(h); if (rc) return rc;
   rc = ensure_chain_buffers(h); if (rc) return rc;
   double* d_in = nullptr;
-  CK(cudaMalloc(&d_in, sizeof(double) * (size_t)n_inits * h->D));
+  rc = stage(h, sizeof(double) * (size_t)n_inits * h->D, (void**)&d_in); if (rc) return rc;
   CK(cudaMemcpyAsync(d_in, x, sizeof(double) * (size_t)n_inits * h->D, cudaMemcpyHostToDevice, h->stream));
   launch_init(h->C, h->chain_offset, h->seed, h->D, d_in, n_inits, h->d_elink_state, jitter_sd, h->d_state, h->stream);
   h->launches++;
@@ -585,7 +599,6 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
   if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_in);
   CK(cudaGetLastError());
   h->iter = 0; h->has_inits = true; h->samples_kept = 0;
   free_glm_buffers(h);
@@ -692,16 +705,16 @@ int mcu_get_state(mcu_handle h, double* values, double* tune, int64_t* iter) {
   CK(cudaSetDevice(h->device));
   const size_t C = (size_t)h->C;
   if (values) {
-    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->D));
+    double* tmp = nullptr; int rc = stage(h, sizeof(double) * C * h->D, (void**)&tmp); if (rc) return rc;
     launch_soa_to_records(h->d_state, tmp, h->C, h->D, h->stream); h->launches++;
     CK(cudaMemcpyAsync(values, tmp, sizeof(double) * C * h->D, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+    CK(cudaStreamSynchronize(h->stream));
   }
   if (tune && h->tune_size > 0) {
-    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->tune_size));
+    double* tmp = nullptr; int rc = stage(h, sizeof(double) * C * h->tune_size, (void**)&tmp); if (rc) return rc;
     launch_soa_to_records(h->d_tune, tmp, h->C, (int)h->tune_size, h->stream); h->launches++;
     CK(cudaMemcpyAsync(tune, tmp, sizeof(double) * C * h->tune_size, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+    CK(cudaStreamSynchronize(h->stream));
   }
   if (iter) *iter = h->iter;
   CK(cudaGetLastError());

@@ -52,10 +52,13 @@ MCU_D double draw_uniform(const RunArgs& a, uint32_t chain, uint32_t iter, uint3
   philox4x32_10(j, iter, chain, block, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
   return u53(w[0], w[1]);
 }
+MCU_D double fast_log(double x);
+MCU_D double fast_cos2pi(double u);
+// same map as rng.cuh box_muller — sqrt(-2 log(1 - ua)) cos(2 pi ub) — with the kernel's own log / cos
 MCU_D double draw_normal(const RunArgs& a, uint32_t chain, uint32_t iter, uint32_t block, uint32_t j) {
   uint32_t w[4];
   philox4x32_10(j, iter, chain, block, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
-  return box_muller(u53(w[0], w[1]), u53(w[2], w[3]));
+  return sqrt(-2.0 * fast_log(1.0 - u53(w[0], w[1]))) * fast_cos2pi(u53(w[2], w[3]));
 }
 
 // ---- FP64 exp / log with constant-bank coefficients ------------------------------------------------------
@@ -102,6 +105,26 @@ MCU_D double fast_log(double x) {
   const double dk = (double)k;
   // log(1+f) = f - (hfsq - s (hfsq + R));  result = k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
   return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+}
+
+// cos(2 pi u), u in [0, 1): quadrant reduction is exact (u - q/4), then fdlibm's sin/cos kernels on |x| <= pi/4
+__constant__ double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+__constant__ double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+MCU_D double fast_cos2pi(double u) {
+  const double qf = rint(4.0 * u);
+  const int q = (int)qf & 3;
+  const double x = 6.283185307179586476925286766559 * fma(qf, -0.25, u);   // |x| <= pi/4
+  const double z = x * x;
+  double sp = kSinC[0], cp = kCosC[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) { sp = fma(sp, z, kSinC[i]); cp = fma(cp, z, kCosC[i]); }
+  const double sn = fma(x * z, sp, x);
+  const double cs = fma(z * z, cp, fma(z, -0.5, 1.0));
+  // cos(x + q pi/2): q = 0 → cos, 1 → -sin, 2 → -cos, 3 → sin
+  const double v = (q & 1) ? sn : cs;
+  return ((q + 1) & 2) ? -v : v;
 }
 
 // r log p + (n - r) log(1 - p) with p = invlogit(eta), written as r eta - n softplus(eta)
