@@ -210,9 +210,12 @@ int mcu_summary_from_sums(int64_t n_kept, int p, const double* center, const dou
 int mcu_summary_streaming(mcu_handle h, double* out);
 
 /* ---- RNG contract ----------------------------------------------------- */
-/* PHILOX: Philox4x32-10, key = seed, counter = (draw j, iteration, global chain, block|kind<<16).
+/* PHILOX: Philox4x32-10, key = seed, counter = (k >> 1, iteration, global chain, block | kind << 16 | stream << 24).
+ * Every block update of every chain owns two streams (0 = rand(), 1 = randn()); k counts the draws of a stream in
+ * the order the reference consumes them; one Philox block yields two draws (uniforms: words (0,1) / (2,3) as 53-bit
+ * fractions; normals: both Box-Muller branches rad·cos / rad·sin).  Full definition: mamba.jl_b200/csrc/rng.cuh.
  * EXTERNAL: the shim stream of north_star — draws are consumed sequentially from
- * u[chain][0..n_per_chain) (uniforms in [0,1)); a normal consumes two.                        */
+ * u[chain][0..n_per_chain) (uniforms in [0,1)); a normal consumes two (cosine branch).            */
 int mcu_set_rng_mode(mcu_handle h, int mode, const double* u, size_t n_per_chain);
 
 /* ---- device info for the harness ------------------------------------------------------------ */

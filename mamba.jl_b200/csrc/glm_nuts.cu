@@ -27,7 +27,7 @@ enum Phase { PH_BEGIN = 0, PH_EPS_INIT = 1, PH_EPS_TRIAL = 2, PH_START = 3, PH_L
 
 // scalar slots per chain (doubles)
 enum Slot {
-  SL_PHASE = 0, SL_ITER, SL_JDRAW, SL_LOGP0, SL_LOGU0, SL_N, SL_TN, SL_TS, SL_ALPHA, SL_NALPHA, SL_J, SL_T, SL_PM,
+  SL_PHASE = 0, SL_ITER, SL_JDRAW /* uniforms drawn */, SL_KN /* normals drawn */, SL_LOGP0, SL_LOGU0, SL_N, SL_TN, SL_TS, SL_ALPHA, SL_NALPHA, SL_J, SL_T, SL_PM,
   SL_EPS_USE, SL_EPS_TRY, SL_EPS_PM, SL_EPS_LOGF0, SL_EPS_D0, SL_EPS_GUARD, SL_SN0,   // SL_SN0 .. SL_SN0 + kMaxDepth - 1: stack n
   SL_COUNT = SL_SN0 + kMaxDepth
 };
@@ -81,10 +81,19 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
   if (phase == PH_DONE && iter >= a.target_iter) return;
   if (phase == PH_DONE) phase = PH_BEGIN;   // a later mcu_run continues the chain
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), gchain = (uint32_t)(a.chain_offset + c);
-  uint32_t jdraw = (uint32_t)SC(SL_JDRAW);
-  auto words = [&](uint32_t j, uint32_t (&w)[4]) { philox4x32_10(j, (uint32_t)iter, gchain, 0u, k0, k1, w); };
-  auto uniform = [&]() { uint32_t w[4]; words(jdraw, w); ++jdraw; return u53(w[0], w[1]); };            // same value on every lane
-  auto normal_at = [&](uint32_t j) { uint32_t w[4]; words(j, w); return box_muller(u53(w[0], w[1]), u53(w[2], w[3])); };
+  uint32_t jdraw = (uint32_t)SC(SL_JDRAW), kn = (uint32_t)SC(SL_KN);
+  // rng.cuh contract: stream 0 = uniforms, stream 1 = normals, two draws per Philox block (block 0, kind 0)
+  auto words = [&](uint32_t k, uint32_t stream, uint32_t (&w)[4]) { philox4x32_10(k >> 1, (uint32_t)iter, gchain, stream << 24, k0, k1, w); };
+  auto uniform = [&]() {   // same value on every lane
+    uint32_t w[4]; words(jdraw, 0u, w);
+    const double u = (jdraw & 1u) ? u53(w[2], w[3]) : u53(w[0], w[1]);
+    ++jdraw; return u;
+  };
+  auto normal_at = [&](uint32_t k) {
+    uint32_t w[4]; words(k, 1u, w);
+    const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
+    return (k & 1u) ? box_muller_sin(ua, ub) : box_muller(ua, ub);
+  };
 
   // NUTS tune scalars are kept in registers while the chain advances
   double t_adapt = TN(0), t_alpha = TN(1), t_eps = TN(2), t_epsbar = TN(3), t_Hbar = TN(4), t_m = TN(5), t_mu = TN(6), t_nalpha = TN(7);
@@ -130,8 +139,8 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
     t_adapt = adapt ? 1.0 : 0.0;
     if (adapt) t_m += 1.0; else if (t_m > 0.0) t_eps = t_epsbar;
     SCW(SL_EPS_USE, t_eps);
-    for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_CR, i) = normal_at(jdraw + (uint32_t)i); VV(V_CX, i) = x; VV(V_CG, i) = 0.0; REQ(i) = x; }
-    jdraw += (uint32_t)d;
+    for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_CR, i) = normal_at(kn + (uint32_t)i); VV(V_CX, i) = x; VV(V_CG, i) = 0.0; REQ(i) = x; }
+    kn += (uint32_t)d;
   };
   double eps_use = SC(SL_EPS_USE);
 
@@ -140,13 +149,13 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
     switch (phase) {
       case PH_BEGIN: {
         if (iter >= a.target_iter) { phase = PH_DONE; for (int i = lane; i < d; i += 32) REQ(i) = ST(i); need_grad = true; break; }
-        iter += 1; jdraw = 0;
+        iter += 1; jdraw = 0; kn = 0;
         if (iter == 1) {   // NUTSTune(x, nutsepsilon(x, f)): nuts.jl:17-30
           t_adapt = 0.0; t_alpha = 0.0; t_epsbar = 1.0; t_Hbar = 0.0; t_m = 0.0; t_mu = CUDART_NAN; t_nalpha = 0.0;
           if (a.eps_desc > 0.0) { t_eps = a.eps_desc; }
           else {           // nutsepsilon: nuts.jl:192-205 — r0 = randn(n); leapfrog(x, r0, 0, 0)
-            for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_RM, i) = normal_at(jdraw + (uint32_t)i); VV(V_CX, i) = x; REQ(i) = x; }
-            jdraw += (uint32_t)d;
+            for (int i = lane; i < d; i += 32) { const double x = ST(i); VV(V_RM, i) = normal_at(kn + (uint32_t)i); VV(V_CX, i) = x; REQ(i) = x; }
+            kn += (uint32_t)d;
             phase = PH_EPS_INIT; need_grad = true; break;
           }
         }
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
   }
   __syncwarp();
   if (lane == 0) {
-    a.sc[(size_t)SL_PHASE * C + c] = (double)phase; a.sc[(size_t)SL_ITER * C + c] = (double)iter; a.sc[(size_t)SL_JDRAW * C + c] = (double)jdraw;
+    a.sc[(size_t)SL_PHASE * C + c] = (double)phase; a.sc[(size_t)SL_ITER * C + c] = (double)iter; a.sc[(size_t)SL_JDRAW * C + c] = (double)jdraw; a.sc[(size_t)SL_KN * C + c] = (double)kn;
     a.tune[0 * C + c] = t_adapt; a.tune[1 * C + c] = t_alpha; a.tune[2 * C + c] = t_eps; a.tune[3 * C + c] = t_epsbar;
     a.tune[4 * C + c] = t_Hbar; a.tune[5 * C + c] = t_m; a.tune[6 * C + c] = t_mu; a.tune[7 * C + c] = t_nalpha;
     if (phase != PH_DONE) atomicAdd(&a.n_active[a.tick & 1], 1);

@@ -4,13 +4,15 @@
 // the engine replaces it by a counter-based stream so that thousands of chains advance in
 // lockstep with no RNG state in memory and with results independent of the chain→GPU mapping:
 //
-//   Philox4x32-10, key = (seed_lo, seed_hi), counter = (j, iter, chain, block | kind << 16)
-//   uniform  u = (w0 * 2^21 + (w1 >> 11)) * 2^-53                 in [0,1)
-//   normal   z = sqrt(-2 log(1 - u(w0,w1))) * cos(2 pi u(w2,w3))
-//
-// j counts draws inside one block update in the order the reference consumes them
-// (SURVEY.md App. A).  EXTERNAL mode reads uniforms sequentially from a caller-supplied stream
-// (the north_star "shim" stream); a normal consumes two.
+//   Philox4x32-10, key = (seed_lo, seed_hi), counter = (k >> 1, iter, chain, block | kind << 16 | stream << 24)
+//   Two independent streams per block update: stream 0 feeds rand(), stream 1 feeds randn(); k counts the
+//   draws of a stream in the order the reference consumes them.  One Philox block
+//   gives two draws:
+//     uniform k : u53(w0, w1) for even k, u53(w2, w3) for odd k;  u53(hi, lo) = (hi * 2^21 + (lo >> 11)) * 2^-53 in [0,1)
+//     normal  k : rad = sqrt(-2 log(1 - u53(w0,w1))), ang = 2 pi u53(w2,w3);  rad cos(ang) for even k, rad sin(ang) for odd k
+//   (both Box-Muller branches are used, so 26 normals cost 13 Philox blocks, logs and square roots).
+// EXTERNAL mode reads uniforms sequentially from a caller-supplied stream (the north_star "shim"
+// stream); a normal consumes two entries and uses the cosine branch.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,14 +42,18 @@ __device__ __forceinline__ double box_muller(double ua, double ub) {
   return sqrt(-2.0 * log(1.0 - ua)) * cos(6.283185307179586476925286766559 * ub);
 }
 
+__device__ __forceinline__ double box_muller_sin(double ua, double ub) {
+  return sqrt(-2.0 * log(1.0 - ua)) * sin(6.283185307179586476925286766559 * ub);
+}
+
 struct Draws {
-  uint32_t k0, k1, chain, iter, blockkind, j;
+  uint32_t k0, k1, chain, iter, blockkind, ku, kn;
   const double* ext;          // EXTERNAL mode: this chain's stream, or nullptr
   unsigned long long ext_n;
   unsigned long long* ext_pos;  // this chain's cursor (persists across block updates and launches)
 
   __device__ __forceinline__ void seek(uint32_t it, uint32_t block, uint32_t kind) {
-    iter = it; blockkind = block | (kind << 16); j = 0;
+    iter = it; blockkind = block | (kind << 16); ku = 0; kn = 0;
   }
   __device__ __forceinline__ double next_ext() {
     unsigned long long p = *ext_pos;
@@ -58,16 +64,19 @@ struct Draws {
   __device__ __noinline__ double uniform() {
     if (ext) return next_ext();
     uint32_t w[4];
-    philox4x32_10(j, iter, chain, blockkind, k0, k1, w);
-    ++j;
-    return u53(w[0], w[1]);
+    philox4x32_10(ku >> 1, iter, chain, blockkind, k0, k1, w);
+    const double u = (ku & 1u) ? u53(w[2], w[3]) : u53(w[0], w[1]);
+    ++ku;
+    return u;
   }
   __device__ __noinline__ double normal() {
     if (ext) { const double a = next_ext(); const double b = next_ext(); return box_muller(a, b); }
     uint32_t w[4];
-    philox4x32_10(j, iter, chain, blockkind, k0, k1, w);
-    ++j;
-    return box_muller(u53(w[0], w[1]), u53(w[2], w[3]));
+    philox4x32_10(kn >> 1, iter, chain, blockkind | (1u << 24), k0, k1, w);
+    const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
+    const double z = (kn & 1u) ? box_muller_sin(ua, ub) : box_muller(ua, ub);
+    ++kn;
+    return z;
   }
 };
 

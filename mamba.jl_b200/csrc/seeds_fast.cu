@@ -47,18 +47,22 @@ struct FastCfg {
   double scale_a[4], scale_b[NPL], scale_s;
 };
 
-MCU_D double draw_uniform(const RunArgs& a, uint32_t chain, uint32_t iter, uint32_t block, uint32_t j) {
-  uint32_t w[4];
-  philox4x32_10(j, iter, chain, block, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
-  return u53(w[0], w[1]);
-}
+// rng.cuh contract: stream 0 = uniforms, stream 1 = normals, TWO draws per Philox block: draw k of a stream comes from
+// block k >> 1 (first/second half for uniforms, cosine/sine branch of Box-Muller for normals).
+struct Pair { double a, b; };
 MCU_D double fast_log(double x);
-MCU_D double fast_cos2pi(double u);
-// same map as rng.cuh box_muller — sqrt(-2 log(1 - ua)) cos(2 pi ub) — with the kernel's own log / cos
-MCU_D double draw_normal(const RunArgs& a, uint32_t chain, uint32_t iter, uint32_t block, uint32_t j) {
+MCU_D Pair fast_sincos2pi(double u);
+MCU_D Pair draw_uniform_pair(const RunArgs& a, uint32_t chain, uint32_t iter, uint32_t block, uint32_t kpair) {
   uint32_t w[4];
-  philox4x32_10(j, iter, chain, block, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
-  return sqrt(-2.0 * fast_log(1.0 - u53(w[0], w[1]))) * fast_cos2pi(u53(w[2], w[3]));
+  philox4x32_10(kpair, iter, chain, block, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
+  return {u53(w[0], w[1]), u53(w[2], w[3])};
+}
+MCU_D Pair draw_normal_pair(const RunArgs& a, uint32_t chain, uint32_t iter, uint32_t block, uint32_t kpair) {
+  uint32_t w[4];
+  philox4x32_10(kpair, iter, chain, block | (1u << 24), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
+  const double rad = sqrt(-2.0 * fast_log(1.0 - u53(w[0], w[1])));
+  const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
+  return {rad * sc.b, rad * sc.a};   // (rad cos, rad sin)
 }
 
 // ---- FP64 exp / log with constant-bank coefficients ------------------------------------------------------
@@ -107,12 +111,12 @@ MCU_D double fast_log(double x) {
   return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
 }
 
-// cos(2 pi u), u in [0, 1): quadrant reduction is exact (u - q/4), then fdlibm's sin/cos kernels on |x| <= pi/4
+// sin and cos of 2 pi u, u in [0, 1): quadrant reduction is exact (u - q/4), then fdlibm's sin/cos kernels on |x| <= pi/4
 __constant__ double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
                                 -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
 __constant__ double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
                                 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
-MCU_D double fast_cos2pi(double u) {
+MCU_D Pair fast_sincos2pi(double u) {   // returns (sin, cos) of 2 pi u
   const double qf = rint(4.0 * u);
   const int q = (int)qf & 3;
   const double x = 6.283185307179586476925286766559 * fma(qf, -0.25, u);   // |x| <= pi/4
@@ -122,9 +126,9 @@ MCU_D double fast_cos2pi(double u) {
   for (int i = 1; i < 6; ++i) { sp = fma(sp, z, kSinC[i]); cp = fma(cp, z, kCosC[i]); }
   const double sn = fma(x * z, sp, x);
   const double cs = fma(z * z, cp, fma(z, -0.5, 1.0));
-  // cos(x + q pi/2): q = 0 → cos, 1 → -sin, 2 → -cos, 3 → sin
-  const double v = (q & 1) ? sn : cs;
-  return ((q + 1) & 2) ? -v : v;
+  // angle x + q pi/2:  cos: q = 0 → cos, 1 → -sin, 2 → -cos, 3 → sin ;  sin: q = 0 → sin, 1 → cos, 2 → -sin, 3 → -cos
+  const double cv = (q & 1) ? sn : cs, sv = (q & 1) ? cs : sn;
+  return {(q & 2) ? -sv : sv, ((q + 1) & 2) ? -cv : cv};
 }
 
 // r log p + (n - r) log(1 - p) with p = invlogit(eta), written as r eta - n softplus(eta)
@@ -210,9 +214,12 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       ad0 = adapt;
       if (adapt) m0 += 1.0;
       // components are rotated through slot 0 so the loop stays rolled with everything in registers
+      double zc = 0.0, uc = 0.0;   // second draw of the current Philox pair
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-        const double z = sg0 * draw_normal(a, chain, it32, 0, j);         // z = sigma .* randn(n), drawn up front
+        double zn01;
+        if ((j & 1) == 0) { const Pair pr = draw_normal_pair(a, chain, it32, 0, j >> 1); zn01 = pr.a; zc = pr.b; } else zn01 = zc;
+        const double z = sg0 * zn01;                                      // z = sigma .* randn(n): normal j of the block
         const double anew = al0 + z;
         const unsigned pm = cfg.amask[j];
         // proposed group bases, again in the reference's summation order (slot s holds alpha_{(j+s)%4})
@@ -235,7 +242,8 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
           const double zo = al0 / 1000.0, zn = anew / 1000.0;
           delta += -(zn * zn - zo * zo) / 2.0;
         }
-        const double u = draw_uniform(a, chain, it32, 0, 4 + j);
+        double u;                                                         // uniform j of the block
+        if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); u = pr.a; uc = pr.b; } else u = uc;
         if (mh_accept(u, delta)) {
           al0 = anew;
           g = gn;   // bases of groups that do not contain alpha_j are recomputed to the same value
@@ -263,15 +271,20 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       if (adapt) m1 += 1.0;
       const double sigma = sqrt(s2);                                      // b ~ Normal(0, sqrt(s2)): seeds.jl:31-32
 #pragma unroll 1
+      double zc = 0.0, uc = 0.0;
       for (int i = 0; i < NPL; ++i) {
         const double sg = SSG(i);                                          // global (L2) load, issued ahead of its use
         const double bi = SB(i);
-        const double bn = bi + sg * draw_normal(a, chain, it32, 1, i);
+        double zn01, u;
+        if ((i & 1) == 0) {
+          const Pair pz = draw_normal_pair(a, chain, it32, 1, i >> 1); zn01 = pz.a; zc = pz.b;
+          const Pair pu = draw_uniform_pair(a, chain, it32, 1, i >> 1); u = pu.a; uc = pu.b;
+        } else { zn01 = zc; u = uc; }
+        const double bn = bi + sg * zn01;
         const double en = fast_exp(pick(g, cfg.grp[i]) + bn);            // fresh e_i: also resets the drift of the alpha updates
         const double ln = fast_log(1.0 + en);
         const double zo = bi / sigma, zn = bn / sigma;
         const double delta = fma(cfg.r[i], bn - bi, -cfg.n[i] * (ln - SLL(i))) + (-(zn * zn - zo * zo) / 2.0);
-        const double u = draw_uniform(a, chain, it32, 1, NPL + i);
         if (mh_accept(u, delta)) { SB(i) = bn; SE(i) = en; SLL(i) = ln; if (adapt) SAC(i) = SAC(i) + 1.0; }
       }
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
@@ -288,14 +301,14 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       if (adapt) m2 += 1.0;
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
-      const double xn = x + sgs * draw_normal(a, chain, it32, 2, 0);
+      const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
       const double s2n = (xn > -700.0 && xn < 700.0) ? fast_exp(xn) : exp(xn);
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
       //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double dx = xn - x;
       const double delta = -(0.001 + 1.0) * dx - 0.001 * (1.0 / s2n - 1.0 / s2) + dx
                            - (S / s2n - S / s2) / 2.0 - (double)NPL * 0.5 * dx;
-      const double u = draw_uniform(a, chain, it32, 2, 1);
+      const double u = draw_uniform_pair(a, chain, it32, 2, 0).a;
       if (mh_accept(u, delta)) { x = xn; s2 = s2n; if (adapt) acs += 1; }
       if (adapt && ((long long)m2 % cfg.batchsize[2]) == 0) {
         const double dl = amwg_delta(m2, cfg.batchsize[2]);

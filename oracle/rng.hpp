@@ -9,14 +9,16 @@
 // counter-based stream that a Julia shim can also produce:
 //
 //   Philox4x32-10 (Salmon et al., SC'11 — Random123), key = (seed_lo, seed_hi),
-//   counter = (j, iter, chain, block | kind << 16)
-//     j     : index of the draw inside one block update, in the order the reference consumes
-//             draws; a vector draw randn(n) takes n consecutive j
+//   counter = (k >> 1, iter, chain, block | kind << 16 | stream << 24)
+//     Every block update of every chain owns two independent streams: stream 0 feeds rand(),
+//     stream 1 feeds randn().  k is the index of the draw inside its stream, in the order the
+//     reference consumes draws; a vector draw randn(n) takes n consecutive k.
+//     One Philox block (4 words) yields TWO draws:
+//       uniform k : u53(w0, w1) if k is even, u53(w2, w3) if k is odd,  u53(hi, lo) = (hi * 2^21 + (lo >> 11)) * 2^-53 in [0,1)
+//       normal  k : rad = sqrt(-2 log(1 - u53(w0,w1))), ang = 2 pi u53(w2,w3): rad cos(ang) if k is even, rad sin(ang) if odd
 //     iter  : model.iter (1-based, src/model/simulation.jl:94)
 //     chain : GLOBAL chain id
 //     block : sampler index (0-based); kind 0 = sampler draws, 1 = init jitter
-//   uniform  u = (w0 * 2^21 + (w1 >> 11)) * 2^-53                in [0,1)
-//   normal   z = sqrt(-2 log(1 - u(w0,w1))) * cos(2*pi*u(w2,w3))  (Box-Muller, cosine branch only)
 //
 // EXTERNAL mode: draws are read sequentially from a caller-supplied uniform stream; a normal
 // consumes two entries (ua, ub) with the same Box-Muller map.
@@ -51,6 +53,10 @@ inline double box_muller(double ua, double ub) {
   const double TWO_PI = 6.283185307179586476925286766559;
   return std::sqrt(-2.0 * std::log(1.0 - ua)) * std::cos(TWO_PI * ub);
 }
+inline double box_muller_sin(double ua, double ub) {
+  const double TWO_PI = 6.283185307179586476925286766559;
+  return std::sqrt(-2.0 * std::log(1.0 - ua)) * std::sin(TWO_PI * ub);
+}
 
 struct Rng {
   virtual ~Rng() {}
@@ -61,22 +67,29 @@ struct Rng {
 
 struct PhiloxRng : Rng {
   uint32_t key[2];
-  uint32_t chain, iter = 0, blockkind = 0, j = 0;
+  uint32_t chain, iter = 0, blockkind = 0, ku = 0, kn = 0;
   PhiloxRng(uint64_t seed, uint32_t chain_) : chain(chain_) {
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
   }
   void seek(uint32_t it, uint32_t block, uint32_t kind) override {
-    iter = it; blockkind = block | (kind << 16); j = 0;
+    iter = it; blockkind = block | (kind << 16); ku = 0; kn = 0;
   }
-  void words(uint32_t w[4]) {
-    uint32_t ctr[4] = {j, iter, chain, blockkind};
+  void words(uint32_t k, uint32_t stream, uint32_t w[4]) const {
+    uint32_t ctr[4] = {k >> 1, iter, chain, blockkind | (stream << 24)};
     philox4x32_10(ctr, key, w);
-    ++j;
   }
-  double uniform() override { uint32_t w[4]; words(w); return u53(w[0], w[1]); }
+  double uniform() override {
+    uint32_t w[4]; words(ku, 0, w);
+    const double u = (ku & 1u) ? u53(w[2], w[3]) : u53(w[0], w[1]);
+    ++ku;
+    return u;
+  }
   double normal() override {
-    uint32_t w[4]; words(w);
-    return box_muller(u53(w[0], w[1]), u53(w[2], w[3]));
+    uint32_t w[4]; words(kn, 1, w);
+    const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
+    const double z = (kn & 1u) ? box_muller_sin(ua, ub) : box_muller(ua, ub);
+    ++kn;
+    return z;
   }
 };
 

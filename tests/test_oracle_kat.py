@@ -19,19 +19,25 @@ def test_philox_known_answers(oracle):
 
 
 def test_stream_contract(oracle):
-    # uniform = (w0 * 2^21 + (w1 >> 11)) * 2^-53 ; normal = sqrt(-2 log(1 - ua)) cos(2 pi ub); counter = (j, iter, chain, block | kind << 16)
+    # two streams per block update (0 = rand, 1 = randn), counter = (k >> 1, iter, chain, block | kind << 16 | stream << 24);
+    # one Philox block gives two draws: uniforms (w0,w1) / (w2,w3), normals rad cos(ang) / rad sin(ang)
     seed, chain, it, block = 0x123456789, 7, 3, 2
-    d = oracle.draws(seed, chain, it, block, [0, 1, 0])
     key = [seed & 0xffffffff, seed >> 32]
-    w = oracle.philox([0, it, chain, block], key)
-    assert d[0] == ((w[0] << 21) | (w[1] >> 11)) * 2.0 ** -53
-    w = oracle.philox([1, it, chain, block], key)
-    ua = ((w[0] << 21) | (w[1] >> 11)) * 2.0 ** -53; ub = ((w[2] << 21) | (w[3] >> 11)) * 2.0 ** -53
-    assert d[1] == pytest.approx(np.sqrt(-2 * np.log(1 - ua)) * np.cos(2 * np.pi * ub), rel=1e-15)
+    u53 = lambda hi, lo: ((hi << 21) | (lo >> 11)) * 2.0 ** -53
+    d = oracle.draws(seed, chain, it, block, [0, 1, 0, 0, 1, 1])    # u0 n0 u1 u2 n1 n2 — interleaving does not matter
+    wu0 = oracle.philox([0, it, chain, block], key); wu1 = oracle.philox([1, it, chain, block], key)
+    wn0 = oracle.philox([0, it, chain, block | (1 << 24)], key); wn1 = oracle.philox([1, it, chain, block | (1 << 24)], key)
+    assert d[0] == u53(wu0[0], wu0[1]) and d[2] == u53(wu0[2], wu0[3]) and d[3] == u53(wu1[0], wu1[1])
+    rad0 = np.sqrt(-2 * np.log(1 - u53(wn0[0], wn0[1]))); ang0 = 2 * np.pi * u53(wn0[2], wn0[3])
+    rad1 = np.sqrt(-2 * np.log(1 - u53(wn1[0], wn1[1]))); ang1 = 2 * np.pi * u53(wn1[2], wn1[3])
+    assert d[1] == pytest.approx(rad0 * np.cos(ang0), rel=1e-14, abs=1e-15)
+    assert d[4] == pytest.approx(rad0 * np.sin(ang0), rel=1e-14, abs=1e-15)
+    assert d[5] == pytest.approx(rad1 * np.cos(ang1), rel=1e-14, abs=1e-15)
     u = oracle.draws(1, 0, 1, 0, [0] * 20000)
     z = oracle.draws(1, 0, 1, 0, [1] * 20000)
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
     assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03 and st.kstest(z, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 0.03 and abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.03
 
 
 def test_line_closed_form_known_answers(oracle):
