@@ -31,9 +31,10 @@ import numpy as np  # noqa: E402
 CHAINS_PER_GPU = 125_000
 ITERS, BURNIN, THIN = 2000, 1000, 10
 SEED = 123
-# Algorithmic FP64 work of one chain-iteration in the minimal (term-difference) form, DESIGN.md §4:
-# 68 binomial-logit term evaluations x 72 flop + 26 normal draws x 96 flop + 26 MH tests x 20 flop + 60.
-ALGO_FLOP_PER_CHAIN_ITER = 68 * 72 + 26 * 96 + 26 * 20 + 60
+# Algorithmic FP64 work of one chain-iteration in the minimal form the fused kernel implements, DESIGN.md §4:
+# 25 exp (one per alpha proposal + one per b_i) x 28 flop + 68 plate terms x (log 40 + 8) flop
+# + 13 Box-Muller pairs x 110 flop (log, sqrt, sincos) + 26 MH tests x 20 flop + 26 x 2 + 60.
+ALGO_FLOP_PER_CHAIN_ITER = 25 * 28 + 68 * 48 + 13 * 110 + 26 * 20 + 26 * 2 + 60
 # Algorithmic HBM bytes of one chain-iteration: thinned output only (5 monitored doubles every THIN iterations)
 ALGO_BYTES_PER_CHAIN_ITER = 5 * 8 / THIN
 

@@ -239,8 +239,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
         }
         double delta = fma(cfg.rsum[j], z, -dL);
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
-          const double zo = al0 / 1000.0, zn = anew / 1000.0;
-          delta += -(zn * zn - zo * zo) / 2.0;
+          delta = fma(-0.5e-6, fma(anew, anew, -al0 * al0), delta);   // (x / 1000)^2 / 2 without the divisions
         }
         double u;                                                         // uniform j of the block
         if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); u = pr.a; uc = pr.b; } else u = uc;
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       if (adapt && !ad1) { for (int i = 0; i < NPL; ++i) SAC(i) = 0.0; m1 = 0.0; }
       ad1 = adapt;
       if (adapt) m1 += 1.0;
-      const double sigma = sqrt(s2);                                      // b ~ Normal(0, sqrt(s2)): seeds.jl:31-32
+      const double half_inv_s2 = 0.5 / s2;                                // b ~ Normal(0, sqrt(s2)): -(b/sigma)^2 / 2 = -b^2 / (2 s2)
 #pragma unroll 1
       double zc = 0.0, uc = 0.0;
       for (int i = 0; i < NPL; ++i) {
@@ -283,8 +282,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
         const double bn = bi + sg * zn01;
         const double en = fast_exp(pick(g, cfg.grp[i]) + bn);            // fresh e_i: also resets the drift of the alpha updates
         const double ln = fast_log(1.0 + en);
-        const double zo = bi / sigma, zn = bn / sigma;
-        const double delta = fma(cfg.r[i], bn - bi, -cfg.n[i] * (ln - SLL(i))) + (-(zn * zn - zo * zo) / 2.0);
+        const double delta = fma(cfg.r[i], bn - bi, -cfg.n[i] * (ln - SLL(i))) - half_inv_s2 * fma(bn, bn, -bi * bi);
         if (mh_accept(u, delta)) { SB(i) = bn; SE(i) = en; SLL(i) = ln; if (adapt) SAC(i) = SAC(i) + 1.0; }
       }
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
@@ -306,8 +304,8 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
       //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double dx = xn - x;
-      const double delta = -(0.001 + 1.0) * dx - 0.001 * (1.0 / s2n - 1.0 / s2) + dx
-                           - (S / s2n - S / s2) / 2.0 - (double)NPL * 0.5 * dx;
+      const double dinv = 1.0 / s2n - 1.0 / s2;
+      const double delta = -(0.001 + 1.0) * dx - 0.001 * dinv + dx - 0.5 * S * dinv - (double)NPL * 0.5 * dx;
       const double u = draw_uniform_pair(a, chain, it32, 2, 0).a;
       if (mh_accept(u, delta)) { x = xn; s2 = s2n; if (adapt) acs += 1; }
       if (adapt && ((long long)m2 % cfg.batchsize[2]) == 0) {
