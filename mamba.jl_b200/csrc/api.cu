@@ -334,10 +334,11 @@ int ensure_glm_buffers(mcu_ctx* h) {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
     glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, h->g_blob, h->stream); h->launches++;
-    // X'y (FP64, once): sum_i y_i eta_i = beta . (X'y) is added by the fold instead of per element
+    // X'(y - 1/2) (FP64, once): sum_i (y_i - 1/2) eta_i = beta . X'(y - 1/2) is the part of the log-likelihood that is linear in
+    // beta (y eta from the Bernoulli term, -eta/2 from softplus(eta) = eta/2 + |eta|/2 + log(1 + e^-|eta|)); the fold adds it
     std::vector<double> xty(h->D, 0.0);
     const std::vector<double>& Xh = h->inputs["X"]; const std::vector<double>& yh = h->inputs["y"];
-    for (long long i = 0; i < N; ++i) { const double yi = yh[i]; if (yi != 0.0) for (int j = 0; j < h->D; ++j) xty[j] += yi * Xh[(size_t)i * h->D + j]; }
+    for (long long i = 0; i < N; ++i) { const double yi = yh[i] - 0.5; for (int j = 0; j < h->D; ++j) xty[j] += yi * Xh[(size_t)i * h->D + j]; }
     CK(cudaMalloc(&h->g_xty, sizeof(double) * h->D));
     CK(cudaMemcpyAsync(h->g_xty, xty.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));

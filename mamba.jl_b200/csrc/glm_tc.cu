@@ -63,6 +63,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp (the warp keeps running converged: descriptors and addresses stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] . B[smem desc]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -146,7 +152,7 @@ __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __re
   vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
   *reinterpret_cast<uint4*>(tile + off) = vh;
   *reinterpret_cast<uint4*>(tile + (size_t)TR * DP * 2 + off) = vl;
-  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)y[grow] : 0.5f;   // padding rows: X = 0, so eta = 0 and r x = 0; their softplus(0) is added back below
+  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)(y[grow] - 0.5) : 0.0f;   // y - 1/2; padding rows: X = 0, so eta = 0 and r = 0; their softplus(0) is taken back in the kernel
 }
 
 struct TcArgs {
@@ -154,9 +160,8 @@ struct TcArgs {
   int NT, tiles_per_slab, d, DP;
   long long C;
   const double* req;         // [d][C]
-  double* part_lp;           // [nslab][C]
-  float* part_g;             // [nslab * nsub][d][C]  FP32 flushes of the TMEM accumulator (summed in FP64 by the fold)
-  int nsub;
+  double* part_lp;           // [nslab][C]   -ln2 * sum_i [ |s_i| / 2 + log2(1 + 2^-|s_i|) ],  s = eta * log2(e)
+  float* part_g;             // [nslab][d][C]  FP32 running sum of the TMEM accumulator flushes (folded over slabs in FP64)
   int n_pad;                 // zero rows appended to the last tile
 };
 
@@ -166,28 +171,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 constexpr int kEpiThreads = 512;   // 16 epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. +31 and the 32-column quarter w / 4
 constexpr int kTcThreads = kEpiThreads + 32;   // + 1 issuer warp (bulk copies, tcgen05.mma, commits)
+constexpr int kStages = 3;         // X tiles in flight in shared memory
 
 // barrier slots in shared memory
-enum { B_FULL0 = 0, B_FULL1, B_D1FULL0, B_D1FULL1, B_RFULL, B_GDONE, B_GREAD, B_COUNT };
+enum { B_FULL0 = 0, B_D1FULL0 = B_FULL0 + kStages, B_RFULL0 = B_D1FULL0 + 2, B_GDONE0 = B_RFULL0 + 2, B_GREAD = B_GDONE0 + 2, B_COUNT };
 
-// Warp-specialised pipeline.  Per tile t (buffer b = t & 1):
-//   issuer  : GEMM2(t)   → G        as soon as epilogue(t) has stored R(t)
-//             bulk copy X(t+2) → buffer b once GEMM2(t) has completed, then GEMM1(t+2) → D1[b]
-//             (the tensor pipe runs GEMM2(t), GEMM1(t+2) while the 16 epilogue warps work on tile t+1)
-//   epilogue: D1[b] → p, logf, R (split fp16) written back INTO D1[b] (R_hi columns 0-63, R_lo 64-127, as
-//             FlashAttention keeps P where S was), so R is double buffered for free; every FLUSH tiles G → FP64 partial
-//             (16 warps = 4 per scheduler; the 4 warps that share a TMEM lane quarter sync before overwriting D1)
-// TMEM columns: D1[0] 0-127, D1[1] 128-255, G 256-383.
+// Warp-specialised pipeline.  Tile t uses X stage t % 3 and D1 / barrier slot b = t & 1.
+//   issuer  : tensor-pipe order  ... G2(t-1), G1(t+1), G2(t), G1(t+2) ...  — GEMM1(t+2) is queued right behind GEMM2(t)
+//             (tcgen05.mma of one CTA execute in issue order), so the pipe has GEMM1(t+2) to run while the epilogue warps
+//             are busy with tile t+1; X(t+3) is bulk-copied into the stage GEMM2(t) has finished reading.
+//   epilogue: D1[b] → sigmoid, softplus sums, R = y - p (split fp16) written back INTO THE SAME 32 COLUMNS the warp read
+//             (R_hi in the first 16, R_lo in the last 16: as FlashAttention keeps P where S was), so no warp ever writes
+//             columns another warp reads and the epilogue needs no CTA-level synchronisation.
+//             Every FLUSH tiles the gradient accumulator G is added into the slab's FP32 partial (L2 resident), one tile
+//             late, so that the read never waits for GEMM2.
+// Theta (the 128 requested positions, pre-scaled by log2 e, split fp16) lives in TENSOR MEMORY for the whole kernel: both GEMMs
+// take A from TMEM, shared memory holds nothing but X tiles.
+// TMEM columns: D1[0] 0-127, D1[1] 128-255, G 256-(256+DP), Theta_hi 384-(384+DP/2), Theta_lo 448-(448+DP/2).
 __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int DP = a.DP, CB = DP / 8;
-  const uint32_t op_bytes = (uint32_t)TM * DP * 2;          // one 128 x DP fp16 operand block
-  const uint32_t tile_bytes = (uint32_t)a.tile_bytes;       // hi | lo | y
-  unsigned char* xbuf[2] = {smem, smem + tile_bytes};
-  unsigned char* th_hi = smem + 2 * tile_bytes;
-  unsigned char* th_lo = th_hi + op_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(th_lo + op_bytes);
+  const uint32_t op_bytes = (uint32_t)TR * DP * 2;          // one 128 x DP fp16 operand block
+  const uint32_t tile_bytes = (uint32_t)a.tile_bytes;       // hi | lo | y - 1/2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * tile_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
   double* lp_xchg = reinterpret_cast<double*>(bars + B_COUNT + 2);   // [3][128]
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
@@ -201,38 +208,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(bar(B_FULL0), 1); mbar_init(bar(B_FULL1), 1);
-    mbar_init(bar(B_D1FULL0), 1); mbar_init(bar(B_D1FULL1), 1);
-    mbar_init(bar(B_RFULL), kEpiThreads); mbar_init(bar(B_GDONE), 1); mbar_init(bar(B_GREAD), kEpiThreads);
+    for (int i = 0; i < kStages; ++i) mbar_init(bar(B_FULL0 + i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_D1FULL0 + i), 1); mbar_init(bar(B_RFULL0 + i), kEpiThreads / 32); mbar_init(bar(B_GDONE0 + i), 1); }
+    mbar_init(bar(B_GREAD), kEpiThreads / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // Theta tile: chain = row (tid % 128); the two column halves are split over tid / 128; split fp16, blocked layout
-  if (tid < kEpiThreads) {
-    const int row = tid & 127, grp = tid >> 7;
-    const long long c = (long long)blockIdx.x * TM + row;
-    for (int cb = grp; cb < CB; cb += kEpiThreads / 128) {
-      __half hi[8], lo[8];
-      for (int e = 0; e < 8; ++e) {
-        const int col = cb * 8 + e;
-        const float x = (c < a.C && col < a.d) ? (float)a.req[(size_t)col * a.C + c] : 0.0f;
-        hi[e] = __float2half_rn(x);
-        lo[e] = __float2half_rn(x - __half2float(hi[e]));
-      }
-      const size_t off = ((size_t)(row / 8) * CB + cb) * 128 + (size_t)(row % 8) * 16;
-      uint4 vh, vl;
-      vh.x = pack_half2(hi[0], hi[1]); vh.y = pack_half2(hi[2], hi[3]); vh.z = pack_half2(hi[4], hi[5]); vh.w = pack_half2(hi[6], hi[7]);
-      vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
-      *reinterpret_cast<uint4*>(th_hi + off) = vh;
-      *reinterpret_cast<uint4*>(th_lo + off) = vl;
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes → visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_d1[2] = {tmem, tmem + 128};
-  const uint32_t tm_g = tmem + 256;
+  const uint32_t tm_g = tmem + 256, tm_th = tmem + 384, tm_tl = tmem + 448;
+
+  // Theta → tensor memory: thread = (chain lane, 16-value chunk); column j of the A operand holds values 2j, 2j+1
+  if (tid < kEpiThreads) {
+    const int q = warp & 3, cq = warp >> 2;
+    const long long c = (long long)blockIdx.x * TM + q * 32 + (tid & 31);
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int ck = cq; ck < DP / 16; ck += 4) {
+      uint32_t vh[8], vl[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float x[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = ck * 16 + e + u;
+          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.C + c] * 1.4426950408889634) : 0.0f;
+        }
+        const __half2 h = __floats2half2_rn(x[0], x[1]);
+        const float2 hb = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x[0] - hb.x, x[1] - hb.y);
+        vh[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        vl[e >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      tmem_st8(tm_th + lane_off + (uint32_t)(ck * 8), vh);
+      tmem_st8(tm_tl + lane_off + (uint32_t)(ck * 8), vl);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   // instruction descriptors (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): F16 x F16 → F32, M = 128
   const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TR >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);                 // N = 128, A/B K-major
@@ -240,100 +256,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   const uint32_t rb_stride = (uint32_t)CB * 128;   // bytes between 8-row blocks
 
   if (warp == kEpiThreads / 32) {
-    // ======================================================================= issuer (one elected lane)
-    if ((tid & 31) == 0 && T > 0) {
+    // ======================================================================= issuer warp (converged; one elected lane issues)
+    if (T > 0) {
+      const uint32_t smem_base = smem_u32(smem);
       auto load_tile = [&](int t) {
-        const int b = t & 1;
-        mbar_expect_tx(bar(B_FULL0 + b), tile_bytes);
-        bulk_copy_g2s(smem_u32(xbuf[b]), a.blob + (size_t)(t0 + t) * a.tile_bytes, tile_bytes, bar(B_FULL0 + b));
-      };
-      auto gemm1 = [&](int t) {   // D1[t&1] = Theta . X_t'  (3 split products per 16-wide K step)
-        const int b = t & 1;
-        const uint32_t xh = smem_u32(xbuf[b]), xl = xh + op_bytes, ah = smem_u32(th_hi), al = smem_u32(th_lo);
-        for (int k = 0; k < DP / 16; ++k) {
-          const uint32_t ko = (uint32_t)k * 256;   // two col-blocks per K step
-          const uint64_t dah = make_desc(ah + ko, 128, rb_stride), dal = make_desc(al + ko, 128, rb_stride);
-          const uint64_t dbh = make_desc(xh + ko, 128, rb_stride), dbl = make_desc(xl + ko, 128, rb_stride);
-          mma_ss(tm_d1[b], dah, dbh, idesc1, k > 0 ? 1u : 0u);
-          mma_ss(tm_d1[b], dah, dbl, idesc1, 1u);
-          mma_ss(tm_d1[b], dal, dbh, idesc1, 1u);
+        const int s = t % kStages;
+        if (elect_one()) {
+          mbar_expect_tx(bar(B_FULL0 + s), tile_bytes);
+          bulk_copy_g2s(smem_base + (uint32_t)s * tile_bytes, a.blob + (size_t)(t0 + t) * a.tile_bytes, tile_bytes, bar(B_FULL0 + s));
         }
-        tc_commit(bar(B_D1FULL0 + b));
+        __syncwarp();
       };
-      load_tile(0);
-      if (T > 1) load_tile(1);
-      mbar_wait(bar(B_FULL0), 0);
-      tc_fence_after();
+      auto gemm1 = [&](int t) {   // D1[t&1] = Theta . X_t'  (3 split products per 16-wide K step; A from tensor memory)
+        const int b = t & 1, s = t % kStages;
+        mbar_wait(bar(B_FULL0 + s), (uint32_t)((t / kStages) & 1));
+        tc_fence_after();
+        const uint32_t xh = smem_base + (uint32_t)s * tile_bytes;
+        const uint64_t dh0 = make_desc(xh, 128, rb_stride), dl0 = make_desc(xh + op_bytes, 128, rb_stride);
+        const uint32_t d1 = tm_d1[b];
+        if (elect_one()) {
+#pragma unroll 1
+          for (int k = 0; k < DP / 16; ++k) {
+            const uint64_t dbh = dh0 + (uint64_t)(k * 16), dbl = dl0 + (uint64_t)(k * 16);   // two col-blocks (256 B) per K step
+            mma_ts(d1, tm_th + (uint32_t)k * 8, dbh, idesc1, k > 0 ? 1u : 0u);
+            mma_ts(d1, tm_th + (uint32_t)k * 8, dbl, idesc1, 1u);
+            mma_ts(d1, tm_tl + (uint32_t)k * 8, dbh, idesc1, 1u);
+          }
+          tc_commit(bar(B_D1FULL0 + b));
+        }
+        __syncwarp();
+      };
+      for (int t = 0; t < kStages && t < T; ++t) load_tile(t);
       gemm1(0);
-      if (T > 1) { mbar_wait(bar(B_FULL1), 0); tc_fence_after(); gemm1(1); }
+      if (T > 1) gemm1(1);
       int nflush = 0;          // completions of B_GREAD consumed so far
-      bool prev_flushed = false;
       for (int t = 0; t < T; ++t) {
-        const int b = t & 1;
-        mbar_wait(bar(B_RFULL), (uint32_t)(t & 1));                 // epilogue(t) stored R(t) into D1[b]
-        if (prev_flushed) { mbar_wait(bar(B_GREAD), (uint32_t)(nflush & 1)); ++nflush; }   // G of the previous interval read back
+        const int b = t & 1, s = t % kStages;
+        mbar_wait(bar(B_RFULL0 + b), (uint32_t)((t >> 1) & 1));       // epilogue(t) stored R(t) into D1[b]
+        if (t > 0 && (t % FLUSH) == 0) { mbar_wait(bar(B_GREAD), (uint32_t)(nflush & 1)); ++nflush; }   // G of the previous interval read back
         tc_fence_after();
         {   // GEMM2(t): G += R . X_t  (A = R from tensor memory, B = the X tile read MN-major)
-          const uint32_t xh = smem_u32(xbuf[b]), xl = xh + op_bytes;
-          const uint32_t rh = tm_d1[b], rl = tm_d1[b] + 64;
-          for (int kk = 0; kk < TR / 16; ++kk) {
-            const uint32_t ko = (uint32_t)kk * 2 * rb_stride;       // two row-blocks per K step
-            const uint64_t dbh = make_desc(xh + ko, rb_stride, 128), dbl = make_desc(xl + ko, rb_stride, 128);
-            mma_ts(tm_g, rh + (uint32_t)kk * 8, dbh, idesc2, ((t % FLUSH) != 0 || kk > 0) ? 1u : 0u);
-            mma_ts(tm_g, rh + (uint32_t)kk * 8, dbl, idesc2, 1u);
-            mma_ts(tm_g, rl + (uint32_t)kk * 8, dbh, idesc2, 1u);
+          const uint32_t xh = smem_base + (uint32_t)s * tile_bytes;
+          const uint64_t dh0 = make_desc(xh, rb_stride, 128), dl0 = make_desc(xh + op_bytes, rb_stride, 128);
+          const uint32_t step = (2 * rb_stride) >> 4;                  // two row-blocks per K step
+          const uint32_t d1 = tm_d1[b];
+          const uint32_t acc0 = (t % FLUSH) != 0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll 1
+            for (int kk = 0; kk < TR / 16; ++kk) {
+              const uint64_t dbh = dh0 + (uint64_t)(kk * step), dbl = dl0 + (uint64_t)(kk * step);
+              const uint32_t rh = d1 + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), rl = rh + 16;
+              mma_ts(tm_g, rh, dbh, idesc2, kk > 0 ? 1u : acc0);
+              mma_ts(tm_g, rh, dbl, idesc2, 1u);
+              mma_ts(tm_g, rl, dbh, idesc2, 1u);
+            }
+            tc_commit(bar(B_GDONE0 + b));
           }
-          tc_commit(bar(B_GDONE));
+          __syncwarp();
         }
-        prev_flushed = (t % FLUSH) == FLUSH - 1 || t == T - 1;
         if (t + 2 < T) {
-          mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));               // GEMM2(t) complete → X buffer b and D1[b] are free
-          load_tile(t + 2);
-          mbar_wait(bar(B_FULL0 + b), (uint32_t)(((t + 2) >> 1) & 1));
-          tc_fence_after();
+#if MCU_GLM_TC_CONSERVATIVE
+          mbar_wait(bar(B_GDONE0 + b), (uint32_t)((t >> 1) & 1));     // GEMM2(t) complete before D1[b] is overwritten
+#endif
           gemm1(t + 2);
+        }
+        if (t + kStages < T) {
+          mbar_wait(bar(B_GDONE0 + b), (uint32_t)((t >> 1) & 1));     // GEMM2(t) complete → X stage s is free
+          load_tile(t + kStages);
         }
       }
     }
   } else {
     // ======================================================================= epilogue warps
     const int q = warp & 3, cq = warp >> 2;                         // lane quarter, column quarter
-    const int lane_row = q * 32 + (tid & 31);                       // TMEM lane = chain row of this CTA
+    const int lane = tid & 31;
+    const int lane_row = q * 32 + lane;                             // TMEM lane = chain row of this CTA
     const long long c = (long long)blockIdx.x * TM + lane_row;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     double lp_acc = 0.0;
+    int pending = -1;                                               // tile whose flush interval has ended and is still to be read
+    auto flush = [&](int te) {
+      // add the gradient accumulator of the interval ending at tile te into this slab's FP32 partial (16-column blocks dealt over cq)
+      mbar_wait(bar(B_GDONE0 + (te & 1)), (uint32_t)((te >> 1) & 1));
+      tc_fence_after();
+      const bool first = te < FLUSH;
+      for (int j0 = cq * 16; j0 < DP; j0 += 64) {
+        uint32_t v[16];
+        tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
+        if (c < a.C) {
+          float* dst = a.part_g + ((size_t)slab * a.d + j0) * a.C + c;
+          float old[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) old[e] = (!first && j0 + e < a.d) ? dst[(size_t)e * a.C] : 0.0f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (j0 + e < a.d) dst[(size_t)e * a.C] = old[e] + __uint_as_float(v[e]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_GREAD));
+    };
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       mbar_wait(bar(B_D1FULL0 + b), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      // y of this warp's 32 rows (shared memory, written by the bulk copy)
-      const float4* y4 = reinterpret_cast<const float4*>(smem + (size_t)b * tile_bytes + 2 * (size_t)op_bytes) + cq * 8;
-      float sp_sum = 0.0f;
-      // this warp's 32 columns of eta → registers; then the four warps of this lane quarter agree that all of D1[b]
-      // has been read before any of them overwrites it with R
-      uint32_t v0[16], v1[16];
-      tmem_ld16(tm_d1[b] + lane_off + (uint32_t)(cq * 32), v0);
-      tmem_ld16(tm_d1[b] + lane_off + (uint32_t)(cq * 32 + 16), v1);
+      // y - 1/2 of this warp's 32 rows (shared memory, written by the bulk copy)
+      const float4* y4 = reinterpret_cast<const float4*>(smem + (size_t)(t % kStages) * tile_bytes + 2 * (size_t)op_bytes) + cq * 8;
+      const uint32_t tcol = tm_d1[b] + lane_off + (uint32_t)(cq * 32);
+      uint32_t v[32];
+      tmem_ld32(tcol, v);
       tmem_wait_ld();
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      float abs_sum = 0.0f, lg_sum = 0.0f;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        const int col0 = cq * 32 + ch * 16;
         uint32_t ph[8], pl[8];
+        float prod = 1.0f;
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           const float4 yq = y4[ch * 4 + (e >> 2)];
-          const float yy[4] = {yq.x, yq.y, yq.z, yq.w};
+          const float ym[4] = {yq.x, yq.y, yq.z, yq.w};
           float r4[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float eta = __uint_as_float(ch == 0 ? v0[e + u] : v1[e + u]);
-            const float ex = exp2f_approx(-1.4426950408889634f * fabsf(eta));   // exp(-|eta|)
-            const float w = 1.0f + ex;
-            const float s = rcp_approx(w);                                      // invlogit(|eta|)
-            const float p = eta >= 0.0f ? s : ex * s;
-            sp_sum += fmaf(lg2_approx(w), 0.6931471805599453f, fmaxf(eta, 0.0f));   // softplus(eta)
-            r4[u] = yy[u] - p;
+          for (int u = 0; u < 4; u += 2) {
+            const uint32_t b0 = v[ch * 16 + e + u], b1 = v[ch * 16 + e + u + 1];
+            const float s0 = __uint_as_float(b0), s1 = __uint_as_float(b1);   // eta * log2(e)
+            const float w0 = 1.0f + exp2f_approx(-fabsf(s0)), w1 = 1.0f + exp2f_approx(-fabsf(s1));
+            const float ww = w0 * w1;
+            const float rr = rcp_approx(ww);                  // one reciprocal for the pair
+            const float h0 = fmaf(rr, w1, -0.5f), h1 = fmaf(rr, w0, -0.5f);   // invlogit(|eta|) - 1/2  in [0, 1/2)
+            prod *= ww;
+            abs_sum += fabsf(s0); abs_sum += fabsf(s1);
+            // r = y - p,  p = 1/2 + copysign(h, eta)
+            r4[u] = ym[u] - __uint_as_float(__float_as_uint(h0) | (b0 & 0x80000000u));
+            r4[u + 1] = ym[u + 1] - __uint_as_float(__float_as_uint(h1) | (b1 & 0x80000000u));
           }
 #pragma unroll
           for (int u = 0; u < 4; u += 2) {
@@ -344,45 +400,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
             pl[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&l);
           }
         }
-        tmem_st8(tm_d1[b] + lane_off + (uint32_t)(col0 >> 1), ph);          // R_hi: columns 0-63 of D1[b]
-        tmem_st8(tm_d1[b] + lane_off + (uint32_t)(64 + (col0 >> 1)), pl);   // R_lo: columns 64-127
+        lg_sum += lg2_approx(prod);                           // sum_16 log2(1 + 2^-|s|) = log2 of the product (<= 2^16)
+        tmem_st8(tcol + (uint32_t)(ch * 8), ph);              // R_hi: first 16 of the warp's 32 columns
+        tmem_st8(tcol + (uint32_t)(16 + ch * 8), pl);         // R_lo: last 16
       }
-      // logf contribution of the tile: -sum softplus(eta); the sum_i y_i eta_i part is beta . (X'y), added by the fold.
-      // Padding rows of the last tile have eta = 0: give their softplus(0) back.
-      float lp_tile = -sp_sum;
+      // softplus(eta) = ln2 * (s/2 + |s|/2 + log2(1 + 2^-|s|)); the s/2 part is linear in beta and, like sum y eta, is added by the
+      // fold as beta . X'(y - 1/2).  Padding rows of the last tile have s = 0: take their log2(2) = 1 back.
+      float tile_sum = fmaf(0.5f, abs_sum, lg_sum);
       if (t0 + t == a.NT - 1 && a.n_pad > 0) {
         const int first_pad = TR - a.n_pad;
         const int lo_c = max(first_pad, cq * 32), hi_c = cq * 32 + 32;
-        if (hi_c > lo_c) lp_tile += (float)(hi_c - lo_c) * (lg2_approx(2.0f) * 0.6931471805599453f);
+        if (hi_c > lo_c) tile_sum -= (float)(hi_c - lo_c);
       }
-      lp_acc += (double)lp_tile;
+      lp_acc += (double)tile_sum;
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(bar(B_RFULL));
-      if ((t % FLUSH) == FLUSH - 1 || t == T - 1) {
-        // ---- flush the gradient accumulator to this sub-slab's FP64 partial (16-column blocks dealt over cq)
-        mbar_wait(bar(B_GDONE), (uint32_t)(t & 1));
-        tc_fence_after();
-        const int sub = t / FLUSH;
-        for (int j0 = cq * 16; j0 < DP; j0 += 64) {
-          uint32_t v[16];
-          tmem_ld16(tm_g + lane_off + (uint32_t)j0, v); tmem_wait_ld();
-          if (c < a.C)
-            for (int e = 0; e < 16; ++e)
-              if (j0 + e < a.d) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + (j0 + e)) * a.C + c] = __uint_as_float(v[e]);
-        }
-        tc_fence_before();
-        mbar_arrive(bar(B_GREAD));
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_RFULL0 + b));
+      if (pending >= 0) { flush(pending); pending = -1; }
+      if ((t % FLUSH) == FLUSH - 1 || t == T - 1) pending = t;
     }
+    if (pending >= 0) flush(pending);
     // ---- this slab's logf partial (the four column quarters of a chain are combined through shared memory)
     if (cq > 0) lp_xchg[(cq - 1) * 128 + lane_row] = lp_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
     if (cq == 0 && c < a.C) {
-      a.part_lp[(size_t)slab * a.C + c] = ((lp_acc + lp_xchg[lane_row]) + lp_xchg[128 + lane_row]) + lp_xchg[256 + lane_row];
-      const int used = T > 0 ? (T + FLUSH - 1) / FLUSH : 0;
-      for (int sub = used; sub < a.nsub; ++sub)
-        for (int j = 0; j < a.d; ++j) a.part_g[(((size_t)slab * a.nsub + sub) * a.d + j) * a.C + c] = 0.0f;
+      a.part_lp[(size_t)slab * a.C + c] = -0.6931471805599453 * (((lp_acc + lp_xchg[lane_row]) + lp_xchg[128 + lane_row]) + lp_xchg[256 + lane_row]);
+      if (T == 0)
+        for (int j = 0; j < a.d; ++j) a.part_g[((size_t)slab * a.d + j) * a.C + c] = 0.0f;
     }
   }
   tc_fence_before();
@@ -401,19 +446,17 @@ void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* 
   glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, blob, glm_tc_tile_bytes(d));
 }
 
-int glm_tc_nsub(long long N, int nslab) {
-  const long long NT = glm_tc_num_tiles(N), tps = (NT + nslab - 1) / nslab;
-  return (int)((tps + FLUSH - 1) / FLUSH);
-}
+int glm_tc_nsub(long long, int) { return 1; }   // one FP32 gradient partial per slab (the flush intervals are summed in place)
 
-// Returns 0 on success.  part_lp [nslab][C] (FP64, = -sum softplus), part_g [nslab * nsub][d][C] (FP32), to be folded over slabs.
+// Returns 0 on success.  part_lp [nslab][C] (FP64), part_g [nslab][d][C] (FP32), to be folded over slabs (glm_fold_tc).
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
                   double* part_lp, float* part_g, cudaStream_t st) {
   TcArgs a;
   a.DP = (d + 15) / 16 * 16;
+  if (a.DP > 128) return -2;   // TMEM budget: G (DP columns) + Theta hi/lo (DP/2 each) next to the two D1 buffers
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
-  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.nsub = glm_tc_nsub(N, nslab); a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
-  const size_t smem = 2 * a.tile_bytes + 2 * (size_t)TM * a.DP * 2 + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
+  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  const size_t smem = kStages * a.tile_bytes + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
   static thread_local size_t smem_set[64] = {0};   // per device: the attribute call is slow, do it once per size
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || smem_set[dev] != smem) {
