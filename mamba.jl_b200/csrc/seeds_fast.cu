@@ -36,8 +36,12 @@ namespace {
 
 constexpr int NPL = SeedsModel::NP;   // 21 plates
 
+constexpr int NSL = NPL + 1;          // shared-memory slots per array: 21 plates + one dummy (e = 0, L = 0, n = 0) that pads the plate lists
+
 struct FastCfg {
-  double r[NPL], n[NPL];
+  double r[NPL], n[NSL];
+  unsigned char alist[4][24];         // plates whose eta depends on alpha_j, padded with the dummy slot to a multiple of 3
+  int atriples[4];
   double rsum[4];                     // sum of r_i over the plates that depend on alpha_j
   unsigned char grp[NPL];             // 0:(x1=0,x2=0) 1:(0,1) 2:(1,0) 3:(1,1)
   unsigned amask[4];                  // plates whose eta depends on alpha_j
@@ -142,6 +146,12 @@ MCU_D bool mh_accept(double u, double delta) {   // rand() < exp(logfprime - log
   if (!(delta > -700.0)) return false;            // exp underflows (or delta is NaN): u < 0 never holds
   return u < fast_exp(delta);
 }
+// the same decision without branches (the exp is always evaluated), so that two or three independent updates can be
+// scheduled into each other's dependency stalls
+MCU_D bool mh_accept_nb(double u, double delta) {
+  const double ex = fast_exp(fmax(fmin(delta, 0.0), -700.0));
+  return delta >= 0.0 ? true : (delta > -700.0 && u < ex);
+}
 
 struct Bases { double g0, g1, g2, g3; };
 MCU_D Bases group_bases(double a0, double a1, double a2, double a12) {
@@ -165,9 +175,9 @@ template <int BS>
 __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   double* sb = smem;                        // b[i]
-  double* se = smem + NPL * BS;             // e[i] = exp(eta_i)
-  double* sll = smem + 2 * NPL * BS;        // L[i] = log(1 + e[i])
-  double* sln = smem + 3 * NPL * BS;        // proposed L[i]
+  double* se = smem + NSL * BS;             // e[i] = exp(eta_i)
+  double* sll = smem + 2 * NSL * BS;        // L[i] = log(1 + e[i])
+  double* sln = smem + 3 * NSL * BS;        // proposed L[i]
   const int tid = threadIdx.x;
   const long long c = (long long)blockIdx.x * BS + tid;
   if (c >= a.n_chains) return;
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
 
   Bases g = group_bases(al0, al1, al2, al3);
   for (int i = 0; i < NPL; ++i) { const double e = fast_exp(pick(g, cfg.grp[i]) + SB(i)); SE(i) = e; SLL(i) = fast_log(1.0 + e); }
+  SB(NPL) = 0.0; SE(NPL) = 0.0; SLL(NPL) = 0.0; SLN(NPL) = 0.0;   // dummy slot: log(1 + 0 * E) = 0, n = 0
 
   double mon[SeedsModel::P];
   for (long long it = 1; it <= a.iters; ++it) {
@@ -230,14 +241,19 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
         const Bases gn = group_bases(q0, q1, q2, q3);
         // every affected plate moves by the same step: e_i' = e_i exp(z); ll_i' - ll_i = r_i z - n_i (L_i' - L_i)
         const double E = fast_exp(z);
-        double dL = 0.0;
-        for (int i = 0; i < NPL; ++i) {
-          if (!((pm >> i) & 1u)) continue;
-          const double ln = fast_log(fma(SE(i), E, 1.0));
-          SLN(i) = ln;
-          dL = fma(cfg.n[i], ln - SLL(i), dL);
+        // three plates per trip: their logs are independent, so the scheduler fills one chain's DFMA latency with the others
+        double dLa = 0.0, dLb = 0.0, dLc = 0.0;
+        const int nt = cfg.atriples[j];
+#pragma unroll 1
+        for (int k = 0; k < nt; ++k) {
+          const int ia = cfg.alist[j][3 * k], ib = cfg.alist[j][3 * k + 1], ic = cfg.alist[j][3 * k + 2];
+          const double la = fast_log(fma(SE(ia), E, 1.0)), lb = fast_log(fma(SE(ib), E, 1.0)), lc = fast_log(fma(SE(ic), E, 1.0));
+          SLN(ia) = la; SLN(ib) = lb; SLN(ic) = lc;
+          dLa = fma(cfg.n[ia], la - SLL(ia), dLa);
+          dLb = fma(cfg.n[ib], lb - SLL(ib), dLb);
+          dLc = fma(cfg.n[ic], lc - SLL(ic), dLc);
         }
-        double delta = fma(cfg.rsum[j], z, -dL);
+        double delta = fma(cfg.rsum[j], z, -((dLa + dLb) + dLc));
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
           delta = fma(-0.5e-6, fma(anew, anew, -al0 * al0), delta);   // (x / 1000)^2 / 2 without the divisions
         }
@@ -269,21 +285,26 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       ad1 = adapt;
       if (adapt) m1 += 1.0;
       const double half_inv_s2 = 0.5 / s2;                                // b ~ Normal(0, sqrt(s2)): -(b/sigma)^2 / 2 = -b^2 / (2 s2)
+      // The b_i are conditionally independent given alpha and s2, so two plates (the two draws of one Philox pair) are
+      // updated per trip in straight-line code: two independent exp → log → exp chains for the scheduler to interleave.
 #pragma unroll 1
-      double zc = 0.0, uc = 0.0;
-      for (int i = 0; i < NPL; ++i) {
-        const double sg = SSG(i);                                          // global (L2) load, issued ahead of its use
-        const double bi = SB(i);
-        double zn01, u;
-        if ((i & 1) == 0) {
-          const Pair pz = draw_normal_pair(a, chain, it32, 1, i >> 1); zn01 = pz.a; zc = pz.b;
-          const Pair pu = draw_uniform_pair(a, chain, it32, 1, i >> 1); u = pu.a; uc = pu.b;
-        } else { zn01 = zc; u = uc; }
-        const double bn = bi + sg * zn01;
-        const double en = fast_exp(pick(g, cfg.grp[i]) + bn);            // fresh e_i: also resets the drift of the alpha updates
-        const double ln = fast_log(1.0 + en);
-        const double delta = fma(cfg.r[i], bn - bi, -cfg.n[i] * (ln - SLL(i))) - half_inv_s2 * fma(bn, bn, -bi * bi);
-        if (mh_accept(u, delta)) { SB(i) = bn; SE(i) = en; SLL(i) = ln; if (adapt) SAC(i) = SAC(i) + 1.0; }
+      for (int ip = 0; ip < (NPL + 1) / 2; ++ip) {
+        const int i0 = 2 * ip;
+        const bool two = i0 + 1 < NPL;
+        const int i1 = two ? i0 + 1 : NPL;                                 // odd plate count: the last trip pairs with the dummy slot
+        const double sga = SSG(i0), sgb = two ? SSG(i1) : 0.0;             // global (L2) loads, issued ahead of their use
+        const double bia = SB(i0), bib = SB(i1);
+        const Pair pz = draw_normal_pair(a, chain, it32, 1, ip);
+        const Pair pu = draw_uniform_pair(a, chain, it32, 1, ip);
+        const double bna = bia + sga * pz.a, bnb = bib + sgb * pz.b;
+        const double ena = fast_exp(pick(g, cfg.grp[i0]) + bna);           // fresh e_i: also resets the drift of the alpha updates
+        const double enb = fast_exp(pick(g, cfg.grp[two ? i1 : i0]) + bnb);
+        const double lna = fast_log(1.0 + ena), lnb = fast_log(1.0 + enb);
+        const double da = fma(cfg.r[i0], bna - bia, -cfg.n[i0] * (lna - SLL(i0))) - half_inv_s2 * fma(bna, bna, -bia * bia);
+        const double db = fma(cfg.r[two ? i1 : i0], bnb - bib, -cfg.n[i1] * (lnb - SLL(i1))) - half_inv_s2 * fma(bnb, bnb, -bib * bib);
+        const bool acca = mh_accept_nb(pu.a, da), accb = two && mh_accept_nb(pu.b, db);
+        if (acca) { SB(i0) = bna; SE(i0) = ena; SLL(i0) = lna; if (adapt) SAC(i0) = SAC(i0) + 1.0; }
+        if (accb) { SB(i1) = bnb; SE(i1) = enb; SLL(i1) = lnb; if (adapt) SAC(i1) = SAC(i1) + 1.0; }
       }
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
         const double dl = amwg_delta(m1, cfg.batchsize[1]);
@@ -343,7 +364,7 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
 
 template <int BS>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)BS * 4 * NPL * sizeof(double);
+  const size_t smem = (size_t)BS * 4 * NSL * sizeof(double);
   if (cudaFuncSetAttribute(seeds_fast_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)((a.n_chains + BS - 1) / BS);
   seeds_fast_kernel<BS><<<grid, BS, smem, st>>>(cfg, a);
@@ -379,6 +400,14 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
     if (x1[i] != 0.0 && x2[i] != 0.0) cfg.amask[3] |= 1u << i;
   }
   for (int j = 0; j < 4; ++j) { cfg.rsum[j] = 0.0; for (int i = 0; i < NPL; ++i) if ((cfg.amask[j] >> i) & 1u) cfg.rsum[j] += r[i]; }
+  cfg.n[NPL] = 0.0;
+  for (int j = 0; j < 4; ++j) {
+    int cnt = 0;
+    for (int i = 0; i < NPL; ++i) if ((cfg.amask[j] >> i) & 1u) cfg.alist[j][cnt++] = (unsigned char)i;
+    while (cnt % 3) cfg.alist[j][cnt++] = (unsigned char)NPL;
+    cfg.atriples[j] = cnt / 3;
+    for (int k = cnt; k < 24; ++k) cfg.alist[j][k] = (unsigned char)NPL;
+  }
   cfg.gmask[0] = 0xFu; cfg.gmask[1] = 0xCu; cfg.gmask[2] = 0xAu; cfg.gmask[3] = 0x8u;
   cfg.scale_s = ss[0];
   for (int b = 0; b < 3; ++b) {
