@@ -28,7 +28,22 @@
 // tune array and are touched once per plate per iteration; plate
 // constants sit in the kernel-parameter constant bank and are read with warp-uniform indices.
 // FP64 throughout (the reference is Float64; a decision taken in FP32 would flip ~1e-7 of the time).
+#include <type_traits>
+
 #include "launch.hpp"
+
+#ifndef MCU_SEEDS_BW
+#define MCU_SEEDS_BW 2      // plates per trip in the b block (even)
+#endif
+#ifndef MCU_SEEDS_ESTRIN
+#define MCU_SEEDS_ESTRIN 0
+#endif
+#ifndef MCU_SEEDS_BS
+#define MCU_SEEDS_BS 96
+#endif
+#ifndef MCU_SEEDS_MINB
+#define MCU_SEEDS_MINB 3
+#endif
 
 namespace mcu {
 
@@ -83,10 +98,20 @@ MCU_D double fast_exp(double x) {
   const double kf = rint(x * 1.4426950408889634074);
   double r = fma(kf, -6.93147180369123816490e-01, x);
   r = fma(kf, -1.90821492927058770002e-10, r);
+#if MCU_SEEDS_ESTRIN
+  // Estrin's scheme: dependency depth 6 instead of 12 (kExpC[11 - i] is the coefficient of r^i)
+  const double r2 = r * r, r4 = r2 * r2;
+  const double b0 = fma(kExpC[10], r, kExpC[11]), b1 = fma(kExpC[8], r, kExpC[9]), b2 = fma(kExpC[6], r, kExpC[7]);
+  const double b3 = fma(kExpC[4], r, kExpC[5]), b4 = fma(kExpC[2], r, kExpC[3]), b5 = fma(kExpC[0], r, kExpC[1]);
+  const double c0 = fma(b1, r2, b0), c1 = fma(b3, r2, b2), c2 = fma(b5, r2, b4);
+  double p = fma(fma(c2, r4, c1), r4, c0);
+  p = fma(p, r2, r) + 1.0;                              // 1 + r + r^2 (1/2 + r (1/6 + ...))
+#else
   double p = kExpC[0];
 #pragma unroll
   for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
   p = fma(p * r, r, r) + 1.0;                           // 1 + r + r^2 (1/2 + r (1/6 + ...))
+#endif
   const int k = (int)kf;
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
@@ -105,10 +130,18 @@ MCU_D double fast_log(double x) {
   y = fma(fma(-dnm, y, 1.0), y, y);                     // 1 / (2 + f) to full precision
   const double sq = f * y;
   const double z = sq * sq;
+#if MCU_SEEDS_ESTRIN
+  // fdlibm's own even/odd split (kLogC[7 - i] = Lg_i): two chains of depth 3-4 instead of one of depth 7
+  const double w = z * z;
+  const double t1 = w * fma(w, fma(w, kLogC[1], kLogC[3]), kLogC[5]);                      // w (Lg2 + w (Lg4 + w Lg6))
+  const double t2 = z * fma(w, fma(w, fma(w, kLogC[0], kLogC[2]), kLogC[4]), kLogC[6]);    // z (Lg1 + w (Lg3 + w (Lg5 + w Lg7)))
+  const double R = t2 + t1;
+#else
   double R = kLogC[0];
 #pragma unroll
   for (int i = 1; i < 7; ++i) R = fma(R, z, kLogC[i]);
   R *= z;
+#endif
   const double hfsq = 0.5 * f * f;
   const double dk = (double)k;
   // log(1+f) = f - (hfsq - s (hfsq + R));  result = k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
@@ -172,7 +205,7 @@ MCU_D double pick(const Bases& g, unsigned grp) {   // warp-uniform select, keep
 MCU_D double amwg_delta(double m, int batchsize) { return fmin(0.01, pow(m / (double)batchsize, -0.5)); }
 
 template <int BS>
-__global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
+__global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   double* sb = smem;                        // b[i]
   double* se = smem + NSL * BS;             // e[i] = exp(eta_i)
@@ -285,26 +318,46 @@ __global__ void __launch_bounds__(BS, 3) seeds_fast_kernel(const __grid_constant
       ad1 = adapt;
       if (adapt) m1 += 1.0;
       const double half_inv_s2 = 0.5 / s2;                                // b ~ Normal(0, sqrt(s2)): -(b/sigma)^2 / 2 = -b^2 / (2 s2)
-      // The b_i are conditionally independent given alpha and s2, so two plates (the two draws of one Philox pair) are
-      // updated per trip in straight-line code: two independent exp → log → exp chains for the scheduler to interleave.
+      // The b_i are conditionally independent given alpha and s2, so W plates (the draws of W / 2 Philox pairs) are updated
+      // per trip in straight-line code: W independent exp → log → exp chains for the scheduler to interleave.
+      auto b_trip = [&](auto Wc, int i0) {
+        constexpr int W = decltype(Wc)::value;
+        int ix[W]; double sg[W], bi[W], zn[W], uu[W], ac[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const bool real = i0 + w < NPL;
+          ix[w] = real ? i0 + w : NPL;                                     // past the last plate: the dummy slot (never accepted)
+          sg[w] = real ? SSG(ix[w]) : 0.0;                                 // global (L2) loads, issued a whole trip ahead of their use
+          ac[w] = (real && adapt) ? SAC(ix[w]) : 0.0;
+          bi[w] = SB(ix[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < W; w += 2) {
+          const Pair pz = draw_normal_pair(a, chain, it32, 1, (i0 + w) >> 1);
+          const Pair pu = draw_uniform_pair(a, chain, it32, 1, (i0 + w) >> 1);
+          zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = pu.a; uu[w + 1] = pu.b;
+        }
+        double bn[W], en[W], ln[W]; bool acc[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const int ir = i0 + w < NPL ? i0 + w : 0;                        // constants of a real plate for the dummy chain
+          bn[w] = bi[w] + sg[w] * zn[w];
+          en[w] = fast_exp(pick(g, cfg.grp[ir]) + bn[w]);                  // fresh e_i: also resets the drift of the alpha updates
+          ln[w] = fast_log(1.0 + en[w]);
+          const double dl = fma(cfg.r[ir], bn[w] - bi[w], -cfg.n[ix[w]] * (ln[w] - SLL(ix[w]))) - half_inv_s2 * fma(bn[w], bn[w], -bi[w] * bi[w]);
+          acc[w] = i0 + w < NPL && mh_accept_nb(uu[w], dl);
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) SAC(ix[w]) = ac[w] + 1.0; }
+      };
+      {
+        constexpr int W = MCU_SEEDS_BW;
+        int i0 = 0;
 #pragma unroll 1
-      for (int ip = 0; ip < (NPL + 1) / 2; ++ip) {
-        const int i0 = 2 * ip;
-        const bool two = i0 + 1 < NPL;
-        const int i1 = two ? i0 + 1 : NPL;                                 // odd plate count: the last trip pairs with the dummy slot
-        const double sga = SSG(i0), sgb = two ? SSG(i1) : 0.0;             // global (L2) loads, issued ahead of their use
-        const double bia = SB(i0), bib = SB(i1);
-        const Pair pz = draw_normal_pair(a, chain, it32, 1, ip);
-        const Pair pu = draw_uniform_pair(a, chain, it32, 1, ip);
-        const double bna = bia + sga * pz.a, bnb = bib + sgb * pz.b;
-        const double ena = fast_exp(pick(g, cfg.grp[i0]) + bna);           // fresh e_i: also resets the drift of the alpha updates
-        const double enb = fast_exp(pick(g, cfg.grp[two ? i1 : i0]) + bnb);
-        const double lna = fast_log(1.0 + ena), lnb = fast_log(1.0 + enb);
-        const double da = fma(cfg.r[i0], bna - bia, -cfg.n[i0] * (lna - SLL(i0))) - half_inv_s2 * fma(bna, bna, -bia * bia);
-        const double db = fma(cfg.r[two ? i1 : i0], bnb - bib, -cfg.n[i1] * (lnb - SLL(i1))) - half_inv_s2 * fma(bnb, bnb, -bib * bib);
-        const bool acca = mh_accept_nb(pu.a, da), accb = two && mh_accept_nb(pu.b, db);
-        if (acca) { SB(i0) = bna; SE(i0) = ena; SLL(i0) = lna; if (adapt) SAC(i0) = SAC(i0) + 1.0; }
-        if (accb) { SB(i1) = bnb; SE(i1) = enb; SLL(i1) = lnb; if (adapt) SAC(i1) = SAC(i1) + 1.0; }
+        for (; i0 + W <= NPL; i0 += W) b_trip(std::integral_constant<int, W>{}, i0);
+#pragma unroll 1
+        for (; i0 < NPL; i0 += 2) b_trip(std::integral_constant<int, 2>{}, i0);
       }
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
         const double dl = amwg_delta(m1, cfg.batchsize[1]);
@@ -415,7 +468,7 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
     cfg.target[b] = h_blocks[b].target;
   }
   // 96 threads x 3 blocks/SM = 288 resident chains/SM: 125,000 chains/GPU fit in 3 even rounds
-  return launch_bs<96>(cfg, a, st);
+  return launch_bs<MCU_SEEDS_BS>(cfg, a, st);
 }
 
 }  // namespace mcu

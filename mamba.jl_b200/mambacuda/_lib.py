@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmambacuda.so")
+LIB_PATH = os.environ.get("MCU_LIB_PATH") or os.path.join(_HERE, "libmambacuda.so")   # override: kernel-variant experiments only
 MAX_BLOCK_NODES = 8
 
 OK, ERR_ARG, ERR_DIM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
