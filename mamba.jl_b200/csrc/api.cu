@@ -59,6 +59,8 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
+  std::vector<std::vector<double>> h_scales;                                // host mirror of every block's expanded scale
   void* d_stage = nullptr; size_t stage_cap = 0;   // reusable device staging buffer (no cudaMalloc/cudaFree on the hot API calls)
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
@@ -297,6 +299,16 @@ bool scheme_is_seeds_fast(const mcu_ctx* h) {
   return true;
 }
 
+bool scheme_is_rats_warp(const mcu_ctx* h) {
+  // NUTS(alpha, beta, mu_alpha, mu_beta) , Slice(s2_c, s2_alpha, s2_beta; univariate, constrained) — SURVEY.md §8d config 3
+  if (h->tpl != MCU_TPL_RATS || h->h_blocks.size() != 2) return false;
+  const DevBlock& a = h->h_blocks[0]; const DevBlock& b = h->h_blocks[1];
+  if (a.kind != MCU_NUTS || a.grad != MCU_GRAD_ANALYTIC || b.kind != MCU_SLICE_UNI || b.transform != 0) return false;
+  if (a.n_own != 4 || a.own[0] != 5 || a.own[1] != 6 || a.own[2] != 0 || a.own[3] != 1) return false;
+  if (b.n_own != 3 || b.own[0] != 4 || b.own[1] != 2 || b.own[2] != 3) return false;
+  return true;
+}
+
 bool scheme_is_glm_tick(const mcu_ctx* h) {
   if (h->tpl != MCU_TPL_GLM_LOGIT || h->h_blocks.size() != 1) return false;
   const DevBlock& b = h->h_blocks[0];
@@ -452,7 +464,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
-  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->r_scratch);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
   return MCU_OK;
@@ -510,6 +522,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   h->has_inits = false;
   long long toff = 0;
   std::vector<DevBlock> hb;
+  std::vector<std::vector<double>> h_scales;
   for (int bi = 0; bi < n_blocks; ++bi) {
     const mcu_block_desc& d = blocks[bi];
     if (d.kind < MCU_AMWG || d.kind > MCU_AMM) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
@@ -559,6 +572,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
     if (!sc.empty()) { CK(cudaMalloc(&ds, sizeof(double) * k)); h->scheme_allocs.push_back(ds); CK(cudaMemcpy(ds, sc.data(), sizeof(double) * k, cudaMemcpyHostToDevice)); }
     if (!SL.empty()) { CK(cudaMalloc(&dS, sizeof(double) * k * k)); h->scheme_allocs.push_back(dS); CK(cudaMemcpy(dS, SL.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice)); }
     b.elem = de; b.elink = dl; b.scale = ds; b.SigmaL = dS;
+    h_scales.push_back(sc);
     b.tune_off = (int)toff;
     switch (d.kind) {   // tune record layout: see samplers.cuh
       case MCU_AMWG: toff += 2 + 2 * k; break;
@@ -578,7 +592,9 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   cudaFree(h->d_elink_state); h->d_elink_state = nullptr;
   CK(cudaMalloc(&h->d_elink_state, sizeof(int) * h->D));
   CK(cudaMemcpy(h->d_elink_state, h->elink_state.data(), sizeof(int) * h->D, cudaMemcpyHostToDevice));
+  h->h_scales = h_scales;
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
+  h->rats_warp_ok = scheme_is_rats_warp(h);
   return MCU_OK;
 }
 
@@ -660,7 +676,14 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   long long chunk = 256;
   if (const char* e = std::getenv("MCU_CHUNK_ITERS")) { long long v = std::atoll(e); if (v > 0) chunk = v; }
-  if (fast) chunk = iters;   // the fused kernel keeps everything on chip for the whole call
+  bool rats_warp = h->rats_warp_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  if (rats_warp && h->r_grid == 0) {
+    const int g = rats_warp_grid(h->C);
+    if (g < 1) return fail(h, MCU_ERR_CUDA, "rats_warp_kernel: cannot size the grid");
+    CK(cudaMalloc(&h->r_scratch, rats_warp_scratch_bytes(g)));
+    h->r_grid = g;
+  }
+  if (fast || rats_warp) chunk = iters;   // the fused kernels keep everything on chip for the whole call
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   if (glm_tick) {
@@ -675,6 +698,11 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     if (fast) {
       rc = seeds_fast_launch(Host<SeedsModel>::data(h), a, h->h_blocks.data(), h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
+    } else if (rats_warp) {
+      rc = rats_warp_launch(h->inputs["y"].data(), h->inputs["Xm"].data(), h->inputs["rat"].data(), (int)h->inputs["y"].size(),
+                            h->inputs["xbar"][0], a, h->h_blocks.data(), h->h_scales[1].data(), h->r_grid, h->r_scratch, h->stream);
+      if (rc == -2) { rats_warp = false; chunk = 256; continue; }   // data are not 5 observations per rat: the generic kernel takes over
+      if (rc) return fail(h, MCU_ERR_CUDA, "rats_warp launch failed");
     } else {
       MCU_DISPATCH(h, launch_run(Host<M>::data(h), a, h->stream));
     }

@@ -46,6 +46,12 @@ double measure_fp64_peak_tflops(cudaStream_t st);
 int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
 
 
+// warp-per-chain rats kernel, NUTS + Slice (rats_warp.cu); launch returns 0 on success
+int rats_warp_grid(long long n_chains);
+size_t rats_warp_scratch_bytes(int grid);
+int rats_warp_launch(const double* y, const double* Xm, const double* rat, int N, double xbar, const RunArgs& a, const DevBlock* h_blocks,
+                     const double* h_width, int grid, double* scratch, cudaStream_t st);
+
 // ---- GLM / NUTS tick engine (glm_nuts.cu) ----------------------------------------------------------------
 struct GlmTick {
   long long C, chain_offset;

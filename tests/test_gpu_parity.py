@@ -150,7 +150,7 @@ def test_trajectories_match_oracle(oracle, name, iters, burnin, thin):
     assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4 if "amm" in name else 1e-6)
 
 
-def nuts_pair(oracle, name, n_chains, iters, burnin, seed):
+def nuts_pair(oracle, name, n_chains, iters, burnin, seed, force_generic=True):
     """The oracle runs the reference's recursive buildtree (nuts.jl:139-180), the device the unrolled
     leaf-by-leaf form; both stop doubling after 10 doublings."""
     eng, orc, inits = make_pair(oracle, name, n_chains, seed=seed)
@@ -161,7 +161,7 @@ def nuts_pair(oracle, name, n_chains, iters, burnin, seed):
             b["max_depth"] = 10
     orc.set_scheme(ob)
     eng.set_inits(inits)
-    out_g = eng.run(iters, burnin=burnin, thin=1, force_generic=True)
+    out_g = eng.run(iters, burnin=burnin, thin=1, force_generic=force_generic)
     st_g, tune_g, _ = eng.get_state()
     out_o, st_o, tune_o = orc.run(n_chains, inits, iters, burnin=burnin, thin=1, seed=seed, nthreads=4)
     return (out_g, st_g, tune_g), (out_o, st_o, tune_o)
@@ -185,6 +185,45 @@ def test_nuts_fixed_stepsize_trajectories_match_oracle(oracle, name, iters):
     g, o = nuts_pair(oracle, name, 16, iters, 0, seed=6)
     # long Hamiltonian trajectories in the (beta, log s2) funnel amplify rounding: allow a few chains to flip a decision
     assert_same_run(g, o, rtol=1e-6, min_frac=0.75)
+
+
+# ---- warp-per-chain rats kernel (mamba.jl_b200/csrc/rats_warp.cu) ------------------------------------------
+@pytest.mark.parametrize("iters,burnin,min_frac", [(16, 12, 0.9), (40, 0, 0.75)])
+def test_rats_warp_kernel_trajectories_match_oracle(oracle, iters, burnin, min_frac):
+    # the same draws in the same order as the reference's recursion: adaptive (dual averaging + nutsepsilon) and fixed step size
+    g, o = nuts_pair(oracle, "rats_nuts_slice", 64, iters, burnin, seed=5, force_generic=False)
+    assert_same_run(g, o, rtol=1e-5, min_frac=min_frac)
+    assert g[2][:, -1].max() >= 4
+
+
+def test_rats_warp_kernel_matches_generic_kernel_and_restarts(oracle):
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("rats_nuts_slice")
+    outs = []
+    for generic in (True, False):
+        eng = Engine(tpl, 96, seed=21)
+        eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+        if generic:
+            outs.append(eng.run(30, burnin=10, thin=2, force_generic=True))
+        else:   # 12 + 18 iterations in two calls = mcmc(mc, iters) restart (mcmc.jl:3-16) through the warp kernel
+            a = eng.run(12, burnin=10, thin=2); b = eng.run(18, burnin=10, thin=2)
+            outs.append(np.concatenate([a, b], axis=0))
+    ok = np.array([np.allclose(outs[0][:, :, c], outs[1][:, :, c], rtol=1e-5, atol=1e-9) for c in range(96)])
+    assert ok.mean() >= 0.85, f"{ok.sum()}/96 chains agree between the warp kernel and the generic kernel"
+
+
+def test_rats_warp_kernel_posterior_matches_published_table(oracle):
+    # doc/examples/rats.rst:42-46 (Slice+AMWG run of the reference): mu_beta 6.1831 (0.108), alpha0 106.626 (3.459), s2_c 37.254 (6.027)
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("rats_nuts_slice")
+    eng = Engine(tpl, 512, seed=4)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(1500, burnin=750, thin=1, store=False, out=False)
+    summ = eng.summary_streaming()   # rows: mu_beta, alpha0, s2_c ; columns: mean, sd, naive se, mcse, ess
+    ref = np.array([6.1831, 106.626, 37.254]); ref_mcse = np.array([0.0018, 0.0527, 0.234]); ref_sd = np.array([0.108, 3.459, 6.027])
+    assert np.all(np.abs(summ[:, 0] - ref) < 3 * np.hypot(ref_mcse, summ[:, 3]) + 0.02 * ref_sd)
+    np.testing.assert_allclose(summ[:, 1], ref_sd, rtol=0.08)
+    assert (eng.gelman(0.05, True)[:, 0] < 1.05).all()
 
 
 def test_nuts_fd_gradient_statistically_equivalent(oracle):
