@@ -104,9 +104,19 @@ struct WRng {
 
 struct Chain {
   double y[NOBS], xo[NOBS];
-  double s2a, s2b, s2c;              // fixed during the NUTS block
+  // constants of the NUTS block density while s2_alpha, s2_beta, s2_c are held fixed (set_variances): reciprocals for the
+  // gradient, half-reciprocals of sigma^2 for the quadratic forms, and every term of the log-density that does not depend on x
+  double is2a, is2b, is2c, qa, qb, qc, lpc;
   int lane;
 
+  MCU_D void set_variances(double s2a, double s2b, double s2c) {
+    is2a = 1.0 / s2a; is2b = 1.0 / s2b; is2c = 1.0 / s2c;
+    const double sga = sqrt(s2a), sgb = sqrt(s2b), sgc = sqrt(s2c);
+    qa = 0.5 / (sga * sga); qb = 0.5 / (sgb * sgb); qc = 0.5 / (sgc * sgc);
+    // lp_normal(mu, 0, 1000) x 2, sum_i lp_normal(alpha_i | mu_alpha, sga), sum_i lp_normal(beta_i | ...), lp_isonormal(y): models.cuh
+    lpc = -2.0 * (0.5 * kLog2Pi + log(1000.0)) - (double)NR * (0.5 * kLog2Pi + log(sga)) - (double)NR * (0.5 * kLog2Pi + log(sgb))
+          - ((double)(NR * NOBS) * kLog2Pi + (double)(NR * NOBS) * log(sgc * sgc)) / 2.0;
+  }
   // logpdfgrad!(block, x) for the NUTS block: value of the block density and its analytic gradient (models.cuh:
   // RatsModel::factor / joint_grad, engine.cuh: BlockTarget::logfgrad_mode), non-finite gradient entries zeroed (sampler.jl:110)
   MCU_D double logfgrad(const V4& x, V4& g) const {
@@ -114,32 +124,22 @@ struct Chain {
     double se = 0.0, sxe = 0.0, see = 0.0;
 #pragma unroll
     for (int k = 0; k < NOBS; ++k) {
-      const double e = y[k] - (x.a + x.b * xo[k]);
-      se += e; sxe += e * xo[k]; see += e * e;
+      const double e = y[k] - (x.a + x.b * xo[k]);   // padding lanes: y = x = 0 and x.a = x.b = 0, so e = 0
+      se += e; sxe = fma(e, xo[k], sxe); see = fma(e, e, see);
     }
-    if (!act) { se = 0.0; sxe = 0.0; see = 0.0; }
     const double da = act ? x.a - x.ma : 0.0, db = act ? x.b - x.mb : 0.0;
-    g.a = se / s2c - da / s2a;
-    g.b = sxe / s2c - db / s2b;
+    g.a = se * is2c - da * is2a;
+    g.b = sxe * is2c - db * is2b;
     const double sa = wsum(da), saa = wsum(da * da), sb = wsum(db), sbb = wsum(db * db), SEE = wsum(see);
-    g.ma = sa / s2a - x.ma / 1e6;
-    g.mb = sb / s2b - x.mb / 1e6;
+    g.ma = sa * is2a - x.ma * 1e-6;
+    g.mb = sb * is2b - x.mb * 1e-6;
     if (!isfinite(g.a)) g.a = 0.0;
     if (!isfinite(g.b)) g.b = 0.0;
     if (!isfinite(g.ma)) g.ma = 0.0;
     if (!isfinite(g.mb)) g.mb = 0.0;
-    // own priors that are not targets (mu_alpha, mu_beta), then the targets alpha, beta, y in topological order
-    double lp = lp_normal(x.ma, 0.0, 1000.0) + lp_normal(x.mb, 0.0, 1000.0);
-    if (!isfinite(lp)) return lp;
-    const double sga = sqrt(s2a), sgb = sqrt(s2b);
-    lp += -(saa / (sga * sga) + (double)NR * kLog2Pi) / 2.0 - (double)NR * log(sga);
-    if (!isfinite(lp)) return lp;
-    lp += -(sbb / (sgb * sgb) + (double)NR * kLog2Pi) / 2.0 - (double)NR * log(sgb);
-    if (!isfinite(lp)) return lp;
-    lp += lp_isonormal(SEE, (double)(NR * NOBS), sqrt(s2c));
-    return lp;
+    return lpc - 0.5e-6 * (x.ma * x.ma + x.mb * x.mb) - qa * saa - qb * sbb - qc * SEE;
   }
-  MCU_NOINL double leapfrog(V4& x, V4& r, V4& g, double eps) const {   // nuts.jl:129-136 (in place)
+  MCU_D double leapfrog_inl(V4& x, V4& r, V4& g, double eps) const {   // nuts.jl:129-136 (in place)
     const double h = 0.5 * eps;
     r.a += h * g.a; r.b += h * g.b; r.ma += h * g.ma; r.mb += h * g.mb;
     x.a += eps * r.a; x.b += eps * r.b; x.ma += eps * r.ma; x.mb += eps * r.mb;
@@ -147,6 +147,7 @@ struct Chain {
     r.a += h * g.a; r.b += h * g.b; r.ma += h * g.ma; r.mb += h * g.mb;
     return lf;
   }
+  MCU_NOINL double leapfrog(V4& x, V4& r, V4& g, double eps) const { return leapfrog_inl(x, r, g, eps); }   // cold call sites
 };
 
 MCU_NOINL bool nouturn4(const V4& xminus, const V4& xplus, const V4& rminus, const V4& rplus) {   // nuts.jl:183-187
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
       const long long iter = a.iter0 + it;
       // ================================================================ block 0: NUTS(alpha, beta, mu_alpha, mu_beta)
       rng.seek((uint32_t)iter, 0);
-      ch.s2a = s2a; ch.s2b = s2b; ch.s2c = s2c;
+      ch.set_variances(s2a, s2b, s2c);
       const bool adapt = iter <= a.burnin;                       // nuts.jl:52
       if (iter == 1) {                                           // NUTSTune(x, nutsepsilon(x, f)): nuts.jl:17-30 via sampler.jl:40-45
         t_adapt = 0.0; t_alpha = 0.0; t_epsbar = 1.0; t_Hbar = 0.0; t_m = 0.0; t_mu = CUDART_NAN; t_nalpha = 0.0;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
           int xp_src = -1;                                       // where the subtree's proposal lives: -1 = the current leaf, else stack level
           alpha = 0.0; nalpha = 0.0;
           for (unsigned t = 0; t < nleaf; ++t) {
-            const double logf = ch.leapfrog(cx, cr, cg, pm * eps);
+            const double logf = ch.leapfrog_inl(cx, cr, cg, pm * eps);
             const double logpp = logf - 0.5 * dot_self4(cr);
             Tn = logu0 < logpp ? 1.0 : 0.0;
             Ts = logu0 < logpp + 1000.0;
