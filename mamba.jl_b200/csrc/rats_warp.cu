@@ -16,8 +16,14 @@
 //   * dual averaging, nutsepsilon (nuts.jl:63-92,192-205) and the whole Slice block (slice.jl:66-92, on the
 //     sufficient statistics sum e^2, sum (alpha-mu_alpha)^2, sum (beta-mu_beta)^2) are warp-uniform scalar code.
 // Warps never synchronise with each other: chains sit at different tree depths at the same time.
+// The kernel is instruction-fetch bound (ncu: stall_no_instruction dominates once the leaf loop exceeds the ~6 KB L0
+// instruction cache: 4 warps per scheduler at different program counters), so the leaf is written for few instructions:
+// only logp = logf - r.r/2 is needed per leaf, so its lane parts go through ONE butterfly (3 reductions per leaf with the two
+// for the mu gradient), the merge uniforms come from a lane-parallel Philox batch (64 per refill), no FP64 division.
 // RNG: the engine's Philox contract (rng.cuh) — normal k of the block update is element k of r = randn(n), so lane l
 // evaluates Philox block l (both Box-Muller branches) and the 62 momenta are dealt out by shuffle.
+#include <cstdlib>
+
 #include "launch.hpp"
 
 namespace mcu {
@@ -66,30 +72,30 @@ MCU_D void vcopy(double* dst, const double* src, int lane) {
   dst[lane] = t0; dst[32 + lane] = t1;
   __syncwarp();
 }
-MCU_D double dot_self4(const V4& r) { return wsum(r.a * r.a + r.b * r.b) + r.ma * r.ma + r.mb * r.mb; }
 
 struct WRng {
-  uint32_t k0, k1, chain, iter, block, ku, kn, c2, c3;
-  MCU_D void seek(uint32_t it, uint32_t blk) { iter = it; block = blk; ku = 0; kn = 0; }
-  MCU_NOINL double uniform() {       // warp-uniform: every lane evaluates the same counter
-    double u;
-    if (!(ku & 1u)) {
-      uint32_t w[4];
-      philox4x32_10(ku >> 1, iter, chain, block, k0, k1, w);
-      c2 = w[2]; c3 = w[3];
-      u = u53(w[0], w[1]);
-    } else {
-      u = u53(c2, c3);
-    }
+  uint32_t k0, k1, chain, iter, block, ku, kn, ubase;
+  double ua, ub;                       // this lane's two uniforms of the current batch: draws ubase + 2 lane, ubase + 2 lane + 1
+  MCU_D void seek(uint32_t it, uint32_t blk) { iter = it; block = blk; ku = 0; kn = 0; ubase = 0xffffff00u; }
+  MCU_NOINL void refill() {            // lane l evaluates Philox block (ku >> 1) + l: 64 uniforms per batch
+    uint32_t w[4];
+    ubase = ku & ~1u;
+    philox4x32_10((ubase >> 1) + (uint32_t)(threadIdx.x & 31), iter, chain, block, k0, k1, w);
+    ua = u53(w[0], w[1]); ub = u53(w[2], w[3]);
+  }
+  MCU_D double uniform() {             // draw ku of the block update, warp-uniform
+    if (ku - ubase >= 64u) refill();
+    const uint32_t idx = ku - ubase;
+    const double mine = (idx & 1u) ? ub : ua;
     ++ku;
-    return u;
+    return __shfl_sync(FULL, mine, (int)(idx >> 1));
   }
   // r = randn(62): element e is normal kn + e of the block update; lane l evaluates Philox block (kn >> 1) + l
   MCU_NOINL V4 normals62(int lane) {
     uint32_t w[4];
     philox4x32_10((kn >> 1) + (uint32_t)lane, iter, chain, block | (1u << 24), k0, k1, w);
-    const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
-    const double zc = box_muller(ua, ub), zs = box_muller_sin(ua, ub);
+    const double ua_ = u53(w[0], w[1]), ub_ = u53(w[2], w[3]);
+    const double zc = box_muller(ua_, ub_), zs = box_muller_sin(ua_, ub_);
     V4 r;
     const int sa = lane >> 1, sb = 15 + (lane >> 1);
     const double ac = __shfl_sync(FULL, zc, sa), as = __shfl_sync(FULL, zs, sa);
@@ -102,11 +108,26 @@ struct WRng {
   }
 };
 
+// exp(x) for x <= 0 (acceptance statistic): x = k ln2 + r, degree-11 Taylor polynomial, 2^k through the exponent field
+MCU_D double exp_nonpos(double x) {
+  x = fmax(x, -700.0);
+  const double kf = rint(x * 1.4426950408889634074);
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double p = 2.505210838544172e-08;
+  p = fma(p, r, 2.755731922398589e-07); p = fma(p, r, 2.755731922398589e-06); p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 1.984126984126984e-04); p = fma(p, r, 1.388888888888889e-03); p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02); p = fma(p, r, 1.6666666666666666e-01); p = fma(p, r, 0.5);
+  p = fma(p * r, r, r) + 1.0;
+  return __hiloint2double(__double2hiint(p) + ((int)kf << 20), __double2loint(p));
+}
+
 struct Chain {
   double y[NOBS], xo[NOBS];
   // constants of the NUTS block density while s2_alpha, s2_beta, s2_c are held fixed (set_variances): reciprocals for the
   // gradient, half-reciprocals of sigma^2 for the quadratic forms, and every term of the log-density that does not depend on x
   double is2a, is2b, is2c, qa, qb, qc, lpc;
+  double nw;                           // -1 on the 30 rat lanes, 0 on the two padding lanes
   int lane;
 
   MCU_D void set_variances(double s2a, double s2b, double s2c) {
@@ -117,37 +138,38 @@ struct Chain {
     lpc = -2.0 * (0.5 * kLog2Pi + log(1000.0)) - (double)NR * (0.5 * kLog2Pi + log(sga)) - (double)NR * (0.5 * kLog2Pi + log(sgb))
           - ((double)(NR * NOBS) * kLog2Pi + (double)(NR * NOBS) * log(sgc * sgc)) / 2.0;
   }
-  // logpdfgrad!(block, x) for the NUTS block: value of the block density and its analytic gradient (models.cuh:
-  // RatsModel::factor / joint_grad, engine.cuh: BlockTarget::logfgrad_mode), non-finite gradient entries zeroed (sampler.jl:110)
-  MCU_D double logfgrad(const V4& x, V4& g) const {
-    const bool act = lane < NR;
+  // One leapfrog step (nuts.jl:129-136, in place) of size eps on the NUTS block density — logpdfgrad!(block, x) is the block density
+  // and its analytic gradient (models.cuh: RatsModel::factor / joint_grad; non-finite gradient entries zeroed, sampler.jl:110).
+  // Returns logp = logf(x') - r'.r'/2, the only combination buildtree uses (nuts.jl:144-150); its lane parts share one butterfly.
+  MCU_D double leapfrog_inl(V4& x, V4& r, V4& g, double eps) const {
+    const double h = 0.5 * eps;
+    r.a = fma(h, g.a, r.a); r.b = fma(h, g.b, r.b); r.ma = fma(h, g.ma, r.ma); r.mb = fma(h, g.mb, r.mb);
+    x.a = fma(eps, r.a, x.a); x.b = fma(eps, r.b, x.b); x.ma = fma(eps, r.ma, x.ma); x.mb = fma(eps, r.mb, x.mb);
     double se = 0.0, sxe = 0.0, see = 0.0;
 #pragma unroll
     for (int k = 0; k < NOBS; ++k) {
-      const double e = y[k] - (x.a + x.b * xo[k]);   // padding lanes: y = x = 0 and x.a = x.b = 0, so e = 0
+      const double e = y[k] - fma(x.b, xo[k], x.a);   // padding lanes: y = xo = 0 and x.a = x.b = 0, so e = 0
       se += e; sxe = fma(e, xo[k], sxe); see = fma(e, e, see);
     }
-    const double da = act ? x.a - x.ma : 0.0, db = act ? x.b - x.mb : 0.0;
-    g.a = se * is2c - da * is2a;
-    g.b = sxe * is2c - db * is2b;
-    const double sa = wsum(da), saa = wsum(da * da), sb = wsum(db), sbb = wsum(db * db), SEE = wsum(see);
-    g.ma = sa * is2a - x.ma * 1e-6;
-    g.mb = sb * is2b - x.mb * 1e-6;
-    if (!isfinite(g.a)) g.a = 0.0;
-    if (!isfinite(g.b)) g.b = 0.0;
-    if (!isfinite(g.ma)) g.ma = 0.0;
-    if (!isfinite(g.mb)) g.mb = 0.0;
-    return lpc - 0.5e-6 * (x.ma * x.ma + x.mb * x.mb) - qa * saa - qb * sbb - qc * SEE;
+    const double da = fma(nw, x.ma, x.a), db = fma(nw, x.mb, x.b);   // alpha_i - mu_alpha, beta_i - mu_beta; 0 on padding lanes
+    double ga = fma(se, is2c, -da * is2a), gb = fma(sxe, is2c, -db * is2b);
+    const double sa = wsum(da), sb = wsum(db);
+    double gma = fma(sa, is2a, -x.ma * 1e-6), gmb = fma(sb, is2b, -x.mb * 1e-6);
+    if (!isfinite((ga + gb) + (gma + gmb))) {          // rare: zero the non-finite entries one by one
+      if (!isfinite(ga)) ga = 0.0;
+      if (!isfinite(gb)) gb = 0.0;
+      if (!isfinite(gma)) gma = 0.0;
+      if (!isfinite(gmb)) gmb = 0.0;
+    }
+    g.a = ga; g.b = gb; g.ma = gma; g.mb = gmb;
+    r.a = fma(h, ga, r.a); r.b = fma(h, gb, r.b); r.ma = fma(h, gma, r.ma); r.mb = fma(h, gmb, r.mb);
+    double hl = -qa * da * da;
+    hl = fma(-qb * db, db, hl); hl = fma(-qc, see, hl); hl = fma(-0.5 * r.a, r.a, hl); hl = fma(-0.5 * r.b, r.b, hl);
+    double H = wsum(hl) + lpc;
+    H = fma(-0.5e-6 * x.ma, x.ma, H); H = fma(-0.5e-6 * x.mb, x.mb, H);
+    H = fma(-0.5 * r.ma, r.ma, H); H = fma(-0.5 * r.mb, r.mb, H);
+    return H;
   }
-  MCU_D double leapfrog_inl(V4& x, V4& r, V4& g, double eps) const {   // nuts.jl:129-136 (in place)
-    const double h = 0.5 * eps;
-    r.a += h * g.a; r.b += h * g.b; r.ma += h * g.ma; r.mb += h * g.mb;
-    x.a += eps * r.a; x.b += eps * r.b; x.ma += eps * r.ma; x.mb += eps * r.mb;
-    const double lf = logfgrad(x, g);
-    r.a += h * g.a; r.b += h * g.b; r.ma += h * g.ma; r.mb += h * g.mb;
-    return lf;
-  }
-  MCU_NOINL double leapfrog(V4& x, V4& r, V4& g, double eps) const { return leapfrog_inl(x, r, g, eps); }   // cold call sites
 };
 
 MCU_NOINL bool nouturn4(const V4& xminus, const V4& xplus, const V4& rminus, const V4& rplus) {   // nuts.jl:183-187
@@ -157,7 +179,7 @@ MCU_NOINL bool nouturn4(const V4& xminus, const V4& xplus, const V4& rminus, con
   return a >= 0 && c >= 0;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const __grid_constant__ WarpCfg cfg, const __grid_constant__ RunArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) rats_warp_kernel(const __grid_constant__ WarpCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * kWarpDoubles;
@@ -174,14 +196,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
   const double ig_c0 = ig001_c0();
 
   Chain ch;
-  ch.lane = lane;
+  ch.lane = lane; ch.nw = lane < NR ? -1.0 : 0.0;
 #pragma unroll
   for (int k = 0; k < NOBS; ++k) { ch.y[k] = cfg.y[k][lane]; ch.xo[k] = cfg.x[k][lane]; }
 
   for (long long c = gw; c < a.n_chains; c += GW) {
     WRng rng;
     rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
-    rng.c2 = rng.c3 = 0;
     // ---- chain state: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30]
     V4 x;
     x.ma = a.state[0 * C + c]; x.mb = a.state[1 * C + c];
@@ -205,14 +226,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
         } else {                                                 // nutsepsilon: nuts.jl:192-205
           V4 r0 = rng.normals62(lane), x0 = x, g0 = {0.0, 0.0, 0.0, 0.0};
           V4 xx = x0;
-          const double logf0 = ch.leapfrog(xx, r0, g0, 0.0);
-          const double d0 = dot_self4(r0);
+          const double logp_0 = ch.leapfrog_inl(xx, r0, g0, 0.0);   // logf(x0) - r0.r0/2
           vst(e_xm, x0, lane); vst(e_rm, r0, lane); vst(e_gm, g0, lane);
           double eps = 1.0;
           auto trial = [&](double e) {
             V4 tx = vld(e_xm, lane), tr = vld(e_rm, lane), tg = vld(e_gm, lane);
-            const double lf = ch.leapfrog(tx, tr, tg, e);
-            return exp(lf - logf0 - 0.5 * (dot_self4(tr) - d0));
+            return exp(ch.leapfrog_inl(tx, tr, tg, e) - logp_0);
           };
           double prob = trial(eps);
           const int pm = prob > 0.5 ? 1 : -1;
@@ -233,8 +252,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
         // ------------------------------------------------------------ nuts_sub!: nuts.jl:95-126
         const double eps = t_eps;
         V4 cr = rng.normals62(lane), cx = x, cg = {0.0, 0.0, 0.0, 0.0};
-        const double logf_init = ch.leapfrog(cx, cr, cg, 0.0);
-        const double logp0 = logf_init - 0.5 * dot_self4(cr);
+        const double logp0 = ch.leapfrog_inl(cx, cr, cg, 0.0);
         const double logu0 = logp0 + log(rng.uniform());
         vst(e_xm, cx, lane); vst(e_xp, cx, lane); vst(e_rm, cr, lane); vst(e_rp, cr, lane); vst(e_gm, cg, lane); vst(e_gp, cg, lane);
         vst(e_v, x, lane);
@@ -250,11 +268,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
           int xp_src = -1;                                       // where the subtree's proposal lives: -1 = the current leaf, else stack level
           alpha = 0.0; nalpha = 0.0;
           for (unsigned t = 0; t < nleaf; ++t) {
-            const double logf = ch.leapfrog_inl(cx, cr, cg, pm * eps);
-            const double logpp = logf - 0.5 * dot_self4(cr);
+            const double logpp = ch.leapfrog_inl(cx, cr, cg, pm * eps);
             Tn = logu0 < logpp ? 1.0 : 0.0;
             Ts = logu0 < logpp + 1000.0;
-            alpha += fmin(1.0, exp(logpp - logp0));
+            alpha += exp_nonpos(fmin(logpp - logp0, 0.0));                   // min(1, exp(logp' - logp0))
             nalpha += 1.0;
             xp_src = -1;
             int l = 0;
@@ -262,10 +279,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
               if ((t >> l) & 1u) {   // this subtree is a second half: merge with the pending first half
                 const double u = rng.uniform();
                 const double nA = Sn[l];
-                if (!(u < Tn / (nA + Tn))) xp_src = l;           // keep the first half's proposal
+                if (!(u * (nA + Tn) < Tn)) xp_src = l;           // rand() < n''/(n' + n'') fails: keep the first half's proposal
                 Tn = nA + Tn;
+                // nouturn between the subtree's first leaf (stack) and the current leaf; one code path for both directions:
+                // pm = +1: (x - xf).rf >= 0 && (x - xf).r >= 0;  pm = -1: (xf - x).r >= 0 && (xf - x).rf >= 0
                 const V4 fx = vld(slot(l, 0), lane), fr = vld(slot(l, 1), lane);
-                const bool ok = pm == 1 ? nouturn4(fx, cx, fr, cr) : nouturn4(cx, fx, cr, fr);
+                const double da = cx.a - fx.a, db = cx.b - fx.b, dma = cx.ma - fx.ma, dmb = cx.mb - fx.mb;
+                const double p1 = wsum(fma(da, fr.a, db * fr.b)) + fma(dma, fr.ma, dmb * fr.mb);
+                const double p2 = wsum(fma(da, cr.a, db * cr.b)) + fma(dma, cr.ma, dmb * cr.mb);
+                const double sg = (double)pm;
+                const bool ok = sg * p1 >= 0 && sg * p2 >= 0;
                 Ts = Ts && ok;
                 ++l;
               } else if (Ts) {       // a good first half: park it and build its sibling
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
           if (pm == -1) { vst(e_xm, cx, lane); vst(e_rm, cr, lane); vst(e_gm, cg, lane); }
           else { vst(e_xp, cx, lane); vst(e_rp, cr, lane); vst(e_gp, cg, lane); }
           if (Ts) {
-            if (rng.uniform() < Tn / n) { if (xp_src < 0) vst(e_v, cx, lane); else vcopy(e_v, slot(xp_src, 2), lane); }
+            if (rng.uniform() * n < Tn) { if (xp_src < 0) vst(e_v, cx, lane); else vcopy(e_v, slot(xp_src, 2), lane); }
           }
           j += 1;
           n += Tn;
@@ -315,41 +338,39 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rats_warp_kernel(const
         for (int k = 0; k < NOBS; ++k) { const double e = ch.y[k] - (x.a + x.b * ch.xo[k]); see += e * e; }
         const double da = act ? x.a - x.ma : 0.0, db = act ? x.b - x.mb : 0.0;
         const double SEE = wsum(act ? see : 0.0), saa = wsum(da * da), sbb = wsum(db * db);
-        // logpdf!(block, v): the three InverseGamma priors in block order, then alpha | s2_alpha, beta | s2_beta, y | s2_c,
-        // stopping at the first non-finite partial sum (simulation.jl:60-67,77-90)
-        auto logf = [&](const double* v) {
-          double lp = lp_invgamma(v[0], 0.001, 0.001, ig_c0, false);
-          if (!isfinite(lp)) return lp;
-          lp += lp_invgamma(v[1], 0.001, 0.001, ig_c0, false);
-          if (!isfinite(lp)) return lp;
-          lp += lp_invgamma(v[2], 0.001, 0.001, ig_c0, false);
-          if (!isfinite(lp)) return lp;
-          const double sga = sqrt(v[1]), sgb = sqrt(v[2]);
-          lp += -(saa / (sga * sga) + (double)NR * kLog2Pi) / 2.0 - (double)NR * log(sga);
-          if (!isfinite(lp)) return lp;
-          lp += -(sbb / (sgb * sgb) + (double)NR * kLog2Pi) / 2.0 - (double)NR * log(sgb);
-          if (!isfinite(lp)) return lp;
-          lp += lp_isonormal(SEE, (double)(NR * NOBS), sqrt(v[0]));
-          return lp;
+        // logpdf!(block, v) = IG(s2_c) + IG(s2_alpha) + IG(s2_beta) + sum_i N(alpha_i | mu_alpha, s2_alpha) + sum_i N(beta_i | ..) +
+        // N(y | .., s2_c) (simulation.jl:60-67,77-90); with the sufficient statistics fixed it separates into one term per component,
+        //   term(x; n, S) = c0 - (1.001 + n/2) log x - (0.001 + S/2) / x - n log(2 pi)/2,   -Inf outside the support,
+        // so a univariate update re-evaluates one log and one reciprocal.
+        auto term = [&](double xv, double nn, double S) {
+          if (!(xv >= 0.0)) return neg_inf();
+          return ig_c0 - (1.001 + 0.5 * nn) * log(xv) - (0.001 + 0.5 * S) / xv - 0.5 * nn * kLog2Pi;
         };
-        double v[3] = {s2c, s2a, s2b}, lower[3], upper[3];
-        double logf0 = logf(v);
+        const double cn[3] = {(double)(NR * NOBS), (double)NR, (double)NR}, cS[3] = {SEE, saa, sbb};
+        double v[3] = {s2c, s2a, s2b}, lower[3], upper[3], tv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tv[i] = term(v[i], cn[i], cS[i]);
+        double logf0 = (tv[0] + tv[1]) + tv[2];
 #pragma unroll
         for (int i = 0; i < 3; ++i) lower[i] = v[i] - cfg.width[i] * rng.uniform();
 #pragma unroll
         for (int i = 0; i < 3; ++i) upper[i] = lower[i] + cfg.width[i];
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 3; ++i) {
           const double p0 = logf0 + log(rng.uniform());
           const double xv = v[i];
-          v[i] = lower[i] + (upper[i] - lower[i]) * rng.uniform();
+          const double others = i == 0 ? tv[1] + tv[2] : (i == 1 ? tv[0] + tv[2] : tv[0] + tv[1]);
+          const double nn = i == 0 ? cn[0] : cn[1], S = i == 0 ? cS[0] : (i == 1 ? cS[1] : cS[2]);
+          double lo = i == 0 ? lower[0] : (i == 1 ? lower[1] : lower[2]), up = i == 0 ? upper[0] : (i == 1 ? upper[1] : upper[2]);
+          double cur = lo + (up - lo) * rng.uniform(), tc;
           while (true) {
-            logf0 = logf(v);
+            tc = term(cur, nn, S);
+            logf0 = others + tc;
             if (!(logf0 < p0)) break;
-            const double value = v[i];
-            if (value < xv) lower[i] = value; else upper[i] = value;
-            v[i] = lower[i] + (upper[i] - lower[i]) * rng.uniform();
+            if (cur < xv) lo = cur; else up = cur;
+            cur = lo + (up - lo) * rng.uniform();
           }
+          if (i == 0) { v[0] = cur; tv[0] = tc; } else if (i == 1) { v[1] = cur; tv[1] = tc; } else { v[2] = cur; tv[2] = tc; }
         }
         s2c = v[0]; s2a = v[1]; s2b = v[2];
       }
@@ -390,7 +411,8 @@ int rats_warp_grid(long long n_chains) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long want = (n_chains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const long long cap = (long long)sms * per_sm;
+  long long cap = (long long)sms * per_sm;
+  if (const char* e = std::getenv("MCU_RATS_BLOCKS_PER_SM")) { const long long v = std::atoll(e); if (v > 0 && v < per_sm) cap = (long long)sms * v; }   // occupancy experiments
   return (int)(want < cap ? want : cap);
 }
 size_t rats_warp_scratch_bytes(int grid) { return (size_t)grid * kWarpsPerBlock * (kMaxDepth - LS) * 3 * VEC * sizeof(double); }

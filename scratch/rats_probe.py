@@ -7,7 +7,7 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 eng = Engine(tpl, C, seed=1)
 eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
 tot = 0
-for (n, b) in [(10, 5), (90, 200), (100, 200), (100, 200)]:
+for (n, b) in [(10, 5), (90, 200), (100, 200)]:
     eng.run(n, burnin=b, thin=1, store=False, out=False)
     ms = eng.last_kernel_ms()
     st, tune, it = eng.get_state()
