@@ -24,6 +24,10 @@
 // evaluates Philox block l (both Box-Muller branches) and the 62 momenta are dealt out by shuffle.
 #include <cstdlib>
 
+#ifndef MCU_RATS_MINB
+#define MCU_RATS_MINB 3   // resident blocks per SM the register allocation aims for
+#endif
+
 #include "launch.hpp"
 
 namespace mcu {
@@ -153,19 +157,24 @@ struct Chain {
     }
     const double da = fma(nw, x.ma, x.a), db = fma(nw, x.mb, x.b);   // alpha_i - mu_alpha, beta_i - mu_beta; 0 on padding lanes
     double ga = fma(se, is2c, -da * is2a), gb = fma(sxe, is2c, -db * is2b);
-    const double sa = wsum(da), sb = wsum(db);
-    double gma = fma(sa, is2a, -x.ma * 1e-6), gmb = fma(sb, is2b, -x.mb * 1e-6);
-    if (!isfinite((ga + gb) + (gma + gmb))) {          // rare: zero the non-finite entries one by one
-      if (!isfinite(ga)) ga = 0.0;
-      if (!isfinite(gb)) gb = 0.0;
-      if (!isfinite(gma)) gma = 0.0;
-      if (!isfinite(gmb)) gmb = 0.0;
-    }
-    g.a = ga; g.b = gb; g.ma = gma; g.mb = gmb;
-    r.a = fma(h, ga, r.a); r.b = fma(h, gb, r.b); r.ma = fma(h, gma, r.ma); r.mb = fma(h, gmb, r.mb);
+    // second half-kick of the lane parts and the lane part of logp first: the three butterflies (sum da, sum db, logp) are
+    // independent, so they run interleaved and the leaf pays one shuffle-chain latency instead of two
+    if (!isfinite(ga + gb)) { if (!isfinite(ga)) ga = 0.0; if (!isfinite(gb)) gb = 0.0; }   // rare: zero non-finite gradient entries
+    g.a = ga; g.b = gb;
+    r.a = fma(h, ga, r.a); r.b = fma(h, gb, r.b);
     double hl = -qa * da * da;
     hl = fma(-qb * db, db, hl); hl = fma(-qc, see, hl); hl = fma(-0.5 * r.a, r.a, hl); hl = fma(-0.5 * r.b, r.b, hl);
-    double H = wsum(hl) + lpc;
+    double sa = da, sb = db;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t0 = __shfl_xor_sync(FULL, sa, o), t1 = __shfl_xor_sync(FULL, sb, o), t2 = __shfl_xor_sync(FULL, hl, o);
+      sa += t0; sb += t1; hl += t2;
+    }
+    double gma = fma(sa, is2a, -x.ma * 1e-6), gmb = fma(sb, is2b, -x.mb * 1e-6);
+    if (!isfinite(gma + gmb)) { if (!isfinite(gma)) gma = 0.0; if (!isfinite(gmb)) gmb = 0.0; }
+    g.ma = gma; g.mb = gmb;
+    r.ma = fma(h, gma, r.ma); r.mb = fma(h, gmb, r.mb);
+    double H = hl + lpc;
     H = fma(-0.5e-6 * x.ma, x.ma, H); H = fma(-0.5e-6 * x.mb, x.mb, H);
     H = fma(-0.5 * r.ma, r.ma, H); H = fma(-0.5 * r.mb, r.mb, H);
     return H;
@@ -179,7 +188,7 @@ MCU_NOINL bool nouturn4(const V4& xminus, const V4& xplus, const V4& rminus, con
   return a >= 0 && c >= 0;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) rats_warp_kernel(const __grid_constant__ WarpCfg cfg, const __grid_constant__ RunArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_kernel(const __grid_constant__ WarpCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* ws = smem + (size_t)warp * kWarpDoubles;
