@@ -42,6 +42,11 @@ SCHEME = [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", no
           dict(kind="amwg", nodes=[4], scale=0.1)]
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one seeds_fast_kernel launch (ncu --set full capture of this command,
+# profiles/r1_seeds_fast_summary.md), keyed by (chains per GPU, iterations per launch)
+SEEDS_KERNEL_DRAM_BYTES = {(125000, 2000): 85.83e6 + 125.20e6}
+
+
 def seeds_inits():
     x = np.zeros((2, 26)); x[0, 4] = 0.01; x[1, 4] = 1.0   # doc/examples/seeds.jl:60-65
     return x
@@ -235,7 +240,7 @@ def small_model_bench(args, rank, local_rank, world):
     if args.workload == "line":
         runs = [("line_amwg_slice", 3, 10000, 1000, 1)]
     elif args.workload == "rats":
-        runs = [("rats_nuts_slice", 65536, 200, 100, 1), ("rats_slice_amwg", 65536, 2000, 1000, 10)]
+        runs = [("rats_nuts_slice", 65536, 2000, 1000, 5), ("rats_slice_amwg", 65536, 2000, 1000, 10)]
     else:
         runs = [("pumps_slice", n, 2000, 1000, 10) for n in (10**3, 10**4, 10**5, 10**6)]
     for name, C, iters, burnin, thin in runs:
@@ -425,6 +430,17 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        # ESS/s (BASELINE.json metric, second half): summarystats' ESS is (SD / MCSE)^2 with batch-means MCSE over the draws of
+        # ALL chains (src/output/stats.jl:85-94, mcse.jl:10-19); the reference then caps it at the per-chain draw count, which
+        # is meaningless at 10^6 chains, so the uncapped value over all chains is reported, per second of the end-to-end step
+        ess_all = (summ_e[:, 1] / summ_e[:, 3]) ** 2
+        line["ess"] = {"ess_per_sec_min": float(np.nanmin(ess_all) / (dte / args.steps)), "ess_min": float(np.nanmin(ess_all)),
+                       "kept_draws": int(world * C * kept), "names": ["alpha0", "alpha1", "alpha2", "alpha12", "s2"],
+                       "ess_per_param": [float(v) for v in ess_all],
+                       "definition": "(SD/MCSE_bm)^2 over the kept draws of all chains, batch size 100, uncapped; per second of one end-to-end step"}
+        line["roofline"]["traffic"] = SEEDS_KERNEL_DRAM_BYTES.get((C, iters))
+        line["roofline"]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one seeds_fast_kernel launch, ncu --set full "
+                                              "(profiles/r1_seeds_fast_summary.md); null for other chain / iteration counts")
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_s = 128 * cores    # ~10-20 s of CPU work
