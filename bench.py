@@ -242,7 +242,8 @@ def small_model_bench(args, rank, local_rank, world):
     elif args.workload == "rats":
         runs = [("rats_nuts_slice", 65536, 2000, 1000, 5), ("rats_slice_amwg", 65536, 2000, 1000, 10)]
     else:
-        runs = [("pumps_slice", n, 2000, 1000, 10) for n in (10**3, 10**4, 10**5, 10**6)]
+        # BASELINE.json configs[4]: Gibbs + AMWG, chain sweep 10^3 .. 10^7 with on-device Gelman-Rubin; the reference's own Slice scheme beside it
+        runs = [("pumps_gibbs_amwg", n, 2000, 1000, 10) for n in (10**3, 10**4, 10**5, 10**6, 10**7)] + [("pumps_slice", 10**6, 2000, 1000, 10)]
     for name, C, iters, burnin, thin in runs:
         tpl, blocks, inits = helpers.scheme(name)
         eng = Engine(tpl, C, seed=SEED, chain_offset=rank * C, device=local_rank)

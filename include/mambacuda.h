@@ -65,7 +65,14 @@ enum {
   MCU_RWM = 3,         /* src/samplers/rwm.jl:49-71    */
   MCU_NUTS = 4,        /* src/samplers/nuts.jl:47-205  */
   MCU_HMC = 5,         /* src/samplers/hmc.jl:47-111   */
-  MCU_AMM = 6          /* src/samplers/amm.jl:45-108   */
+  MCU_AMM = 6,         /* src/samplers/amm.jl:45-108   */
+  MCU_GIBBS = 7        /* exact draw from the block's full conditional, where the template has a conjugate form — the device
+                          counterpart of a user-defined Gibbs sampler Sampler([:theta], (theta, ...) -> rand(...))
+                          (src/samplers/sampler.jl:20-24, doc/mcmc/sampler.rst; the tutorial's Gibbs_beta / Gibbs_s2 are of this kind).
+                          pumps: nodes = [theta]: theta_i ~ Gamma(alpha + y_i, 1/(beta + t_i)); nodes = [beta]:
+                          beta ~ Gamma(0.1 + N alpha, 1/(1 + sum theta)).  Gamma variates: Marsaglia-Tsang on the block's
+                          Philox streams (for shape < 1: one uniform first, then per attempt normals until 1 + c x > 0 and
+                          one uniform).  Other templates / node sets: MCU_ERR_UNSUPPORTED.                                    */
 };
 
 enum { MCU_ADAPT_ALL = 0, MCU_ADAPT_BURNIN = 1, MCU_ADAPT_NONE = 2 }; /* amwg.jl:47-56, amm.jl:45-55 */

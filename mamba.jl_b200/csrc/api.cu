@@ -525,11 +525,16 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   std::vector<std::vector<double>> h_scales;
   for (int bi = 0; bi < n_blocks; ++bi) {
     const mcu_block_desc& d = blocks[bi];
-    if (d.kind < MCU_AMWG || d.kind > MCU_AMM) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
+    if (d.kind < MCU_AMWG || d.kind > MCU_GIBBS) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
+    if (d.kind == MCU_GIBBS) {
+      bool ok = false;
+      if (d.n_nodes == 1) { MCU_DISPATCH(h, ok = M::has_gibbs(d.nodes[0])); }
+      if (!ok) return fail(h, MCU_ERR_UNSUPPORTED, "no conjugate full conditional for this node on the device (user-defined samplers have no device equivalent)");
+    }
     if (d.n_nodes < 1 || d.n_nodes > MCU_MAX_BLOCK_NODES) return fail(h, MCU_ERR_ARG, "block must name 1..8 nodes");
     DevBlock b; std::memset(&b, 0, sizeof(b));
     b.kind = d.kind;
-    b.transform = (d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI) ? (d.transform != 0) : 1;   // slice.jl:47-50; others sampler files :53
+    b.transform = (d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI) ? (d.transform != 0) : (d.kind == MCU_GIBBS ? 0 : 1);   // slice.jl:47-50; others sampler files :53
     b.adapt = d.adapt;
     if (d.adapt < MCU_ADAPT_ALL || d.adapt > MCU_ADAPT_NONE) return fail(h, MCU_ERR_ARG, "adapt must be one of :all, :burnin, or :none");   // amwg.jl:49-50
     b.batchsize = d.batchsize > 0 ? d.batchsize : 50;

@@ -136,6 +136,8 @@ struct LineModel {
     g[1] = sxr / s[2] - s[1] / 1000.0;
     g[2] = -0.5 * (double)d.N / s[2] + 0.5 * srr / (s[2] * s[2]) + d_invgamma(s[2], 0.001, 0.001);
   }
+  MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
 };
 
@@ -182,6 +184,8 @@ struct SeedsModel {
     g[0] = g0 - s[0] / 1e6; g[1] = g1 - s[1] / 1e6; g[2] = g2 - s[2] / 1e6; g[3] = g12 - s[3] / 1e6;
     g[4] = -0.5 * (double)d.N / s2 + 0.5 * sbb / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
   }
+  MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) {
     for (int j = 0; j < 5; ++j) out[j] = s[j];
   }
@@ -238,6 +242,8 @@ struct RatsModel {
     g[3] = -0.5 * NR / s2b + 0.5 * sbb / (s2b * s2b) + d_invgamma(s2b, 0.001, 0.001);
     g[4] = -0.5 * (double)d.N / s2c + 0.5 * see / (s2c * s2c) + d_invgamma(s2c, 0.001, 0.001);
   }
+  MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
     out[0] = s[1]; out[1] = s[0] - d.xbar * s[1]; out[2] = s[4];   // alpha0 = mu_alpha - xbar * mu_beta (rats.jl:64-66)
   }
@@ -288,6 +294,18 @@ struct PumpsModel {
     g[1] = N * al / be - sth + (0.1 - 1.0) / be - 1.0;
   }
   MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 12; ++j) out[j] = s[j]; }
+  // conjugate full conditionals (MCU_GIBBS): theta_i | . ~ Gamma(alpha + y_i, 1/(beta + t_i)); beta | . ~ Gamma(0.1 + N alpha, 1/(1 + sum theta))
+  MCU_HD static bool has_gibbs(int node) { return node == 1 || node == 2; }
+  template <class R, class G>
+  MCU_D static void gibbs(const Data& d, double* s, int node, R& rng, G rgamma) {
+    if (node == 2) {
+      for (int i = 0; i < d.N; ++i) s[2 + i] = rgamma(s[0] + d.y[i], rng) / (s[1] + d.t[i]);
+    } else {
+      double sth = 0.0;
+      for (int i = 0; i < d.N; ++i) sth += s[2 + i];
+      s[1] = rgamma(0.1 + (double)d.N * s[0], rng) / (1.0 + sth);
+    }
+  }
 };
 
 // =============================================================================== glm (CUDA-core form)
@@ -325,6 +343,8 @@ struct GlmModel {
       for (int j = 0; j < d.d; ++j) g[j] += r * d.X[(size_t)i * d.d + j];
     }
   }
+  MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) { for (int j = 0; j < d.d; ++j) out[j] = s[j]; }
 };
 

@@ -121,6 +121,23 @@ MCU_NOINL void slice_multi_sample(double* v, const DevBlock& b, T& tgt, Draws& r
   for (int i = 0; i < k; ++i) v[i] = x[i];
 }
 
+// -------------------------------------------------------------------------------- Gibbs
+// Gamma(shape a, scale 1), Marsaglia & Tsang (2000); draw order: include/mambacuda.h, MCU_GIBBS
+static MCU_NOINL double rgamma_mt(double a, Draws& rng) {
+  double boost = 1.0;
+  if (a < 1.0) { boost = pow(rng.uniform(), 1.0 / a); a += 1.0; }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    double x, v;
+    do { x = rng.normal(); v = 1.0 + c * x; } while (v <= 0.0);
+    v = v * v * v;
+    const double u = rng.uniform();
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+  }
+}
+
 // -------------------------------------------------------------------------------- RWM
 template <int K, class T>
 MCU_NOINL void rwm_sample(double* v, const DevBlock& b, T& tgt, Draws& rng) {   // rwm.jl:65-71

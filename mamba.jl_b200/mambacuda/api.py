@@ -102,6 +102,13 @@ def AMM(params, Sigma, adapt="all", beta=0.05, scale=2.38):        # src/sampler
     return Sampler(params, "amm", scale=np.asarray(Sigma, dtype=float), adapt=adapt, beta=beta, amm_scale=scale)
 
 
+def Gibbs(params):
+    """The device counterpart of a user-defined Gibbs sampler `Sampler(params, (args...) -> rand(full conditional))`
+    (src/samplers/sampler.jl:20-24; tutorial's Gibbs_beta / Gibbs_s2): an exact draw from the block's full conditional, for the
+    node sets the template registers a conjugate form for (pumps: [:theta], [:beta]); anything else raises at setsamplers time."""
+    return Sampler(params, "gibbs")
+
+
 class ModelState:
     """src/Mamba.jl:152-155"""
 

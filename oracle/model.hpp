@@ -38,7 +38,7 @@ struct Node {
   std::vector<int> targets;         // model.jl:17-25
 };
 
-enum SamplerKind { S_AMWG = 0, S_SLICE_UNI, S_SLICE_MULTI, S_RWM, S_NUTS, S_HMC, S_AMM };
+enum SamplerKind { S_AMWG = 0, S_SLICE_UNI, S_SLICE_MULTI, S_RWM, S_NUTS, S_HMC, S_AMM, S_GIBBS };
 
 struct Tune {  // union of the reference's *Tune types (amwg.jl:5-21, slice.jl:7-26, rwm.jl:5-22, nuts.jl:5-27, hmc.jl:5-28, amm.jl:5-24)
   bool init = false;
@@ -79,6 +79,9 @@ struct Model {
   // analytic gradient of the joint log density w.r.t. every unobserved stochastic element
   // (constrained scale), written to g[state offset].  Hand-derived per template (templates.hpp).
   std::function<void(const Model&, std::vector<double>&)> joint_grad;
+  // user-defined Gibbs samplers of the template (Sampler(params, f) closures, sampler.jl:20-24): draws the node's value from
+  // its full conditional; returns false when the template has no conjugate form for that node
+  std::function<bool(Model&, int /*node*/, struct Rng&)> gibbs;
 
   int idx(const std::string& s) const {
     for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].name == s) return (int)i;

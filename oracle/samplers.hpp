@@ -69,6 +69,24 @@ inline void amwg_sample(Vec& v, Tune& t, const LogF& logf, bool adapt, Rng& rng)
 // rand(Uniform(a, b)) = a + (b - a) * rand()   (Distributions.jl)
 inline double runif(double a, double b, Rng& rng) { return a + (b - a) * rng.uniform(); }
 
+// Gamma(shape a, scale 1) by Marsaglia & Tsang (2000) — stands in for Distributions.jl's rand(Gamma(...)) inside a user-defined
+// Gibbs sampler; draw order (the engine's RNG contract): for a < 1 one uniform first (boost U^(1/a)), then per attempt normals
+// until 1 + c x > 0, then one uniform
+inline double rgamma_mt(double a, Rng& rng) {
+  double boost = 1.0;
+  if (a < 1.0) { boost = std::pow(rng.uniform(), 1.0 / a); a += 1.0; }
+  const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+  for (;;) {
+    double x, v;
+    do { x = rng.normal(); v = 1.0 + c * x; } while (v <= 0.0);
+    v = v * v * v;
+    const double u = rng.uniform();
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+    if (std::log(u) < 0.5 * x2 + d * (1.0 - v + std::log(v))) return boost * d * v;
+  }
+}
+
 inline void slice_uni_sample(Vec& v, const Vec& width, const LogF& logf, Rng& rng) {   // slice.jl:66-92
   double logf0 = logf(v);
   size_t n = v.size();

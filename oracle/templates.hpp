@@ -232,6 +232,22 @@ inline Model make_pumps() {
     g[0] = N * std::log(be) + slog - N * digamma(al) - 1.0;
     g[1] = N * al / be - sth + (0.1 - 1.0) / be - 1.0;
   };
+  // conjugate full conditionals (BASELINE.json configs[4] "Gibbs + AMWG"):
+  //   theta_i | . ~ Gamma(alpha + y_i, 1 / (beta + t_i)),   beta | . ~ Gamma(0.1 + N alpha, 1 / (1 + sum_i theta_i))
+  m.gibbs = [](Model& mm, int node, Rng& rng) {
+    const auto& t = mm.in("t"); const auto& y = mm.in("y");
+    const double al = mm.val(0)[0], be = mm.val(1)[0];
+    if (node == 2) {
+      for (size_t i = 0; i < t.size(); ++i) mm.nodes[2].value[i] = rgamma_mt(al + y[i], rng) / (be + t[i]);
+      return true;
+    }
+    if (node == 1) {
+      double sth = 0; for (double v : mm.val(2)) sth += v;
+      mm.nodes[1].value[0] = rgamma_mt(0.1 + (double)t.size() * al, rng) / (1.0 + sth);
+      return true;
+    }
+    return false;
+  };
   m.finalize();
   return m;
 }

@@ -52,6 +52,8 @@ SCHEMES = {
     # doc/examples/pumps.jl:52-53
     "pumps_slice": ("pumps", [dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], None),
     "pumps_amwg_nuts": ("pumps", [dict(kind="amwg", nodes=[0, 1], scale=0.5), dict(kind="nuts", nodes=[2])], None),
+    # BASELINE.json configs[4] / SURVEY.md §8d config 5: Gibbs(theta), Gibbs(beta), AMWG(alpha)
+    "pumps_gibbs_amwg": ("pumps", [dict(kind="gibbs", nodes=[2]), dict(kind="gibbs", nodes=[1]), dict(kind="amwg", nodes=[0], scale=1.0)], None),
 }
 
 

@@ -60,6 +60,16 @@ def test_rats_reference_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_pumps_gibbs_amwg_scheme(oracle):
+    # BASELINE.json configs[4]: Gibbs(theta) + Gibbs(beta) + AMWG(alpha) targets the same posterior as the reference's Slice scheme
+    ref = {"beta": (0.93036099, 0.01824153419), "alpha": (0.69679849, 0.00722593007), "theta[1]": (0.05991674, 0.00032725274),
+           "theta[2]": (0.10125873, 0.00129985769), "theta[5]": (0.59971611, 0.00585119652), "theta[10]": (1.98475207, 0.00912748779)}
+    tpl, blocks, inits = helpers.scheme("pumps_gibbs_amwg")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=3, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_pumps_reference_scheme(oracle):
     # doc/examples/pumps.jl:52-57 (2 x 10,000, burnin 2,500, thin 2), table doc/examples/pumps.rst:43-56
     ref = {"beta": (0.93036099, 0.01824153419), "alpha": (0.69679849, 0.00722593007), "theta[1]": (0.05991674, 0.00032725274),
