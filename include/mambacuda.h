@@ -216,6 +216,22 @@ int mcu_summary_sums(mcu_handle h, const double* center, double* sums);
 int mcu_summary_from_sums(int64_t n_kept, int p, const double* center, const double* sums, double* out);
 int mcu_summary_streaming(mcu_handle h, double* out);
 
+/* ---- post-processing of a materialised ModelChains.value (host arrays; no handle, no device) ----------------------
+ * value: [n iterations × p parameters × m chains], column-major (iteration fastest) — the array mcu_run returns.
+ * The Julia shim keeps describe() / gelmandiag(mpsrf = true) / hpd / autocor / changerate on engine output.
+ *   mcu_chains_quantile   quantile(c; q)        src/output/stats.jl:74-83     out [p × nq] row-major
+ *   mcu_chains_hpd        hpd(c; alpha)         src/output/stats.jl:52-72     out [p × 2]
+ *   mcu_chains_autocor    autocor(c; lags, relative)  stats.jl:3-13; lags = index lags on the stored series (× thinning step when
+ *                         relative = true, exactly as the reference does); out [p × nlags × m] column-major
+ *   mcu_chains_changerate changerate(c)         stats.jl:19-39                out [p + 1] (last = multivariate), NOT rounded
+ *   mcu_chains_gelman     gelmandiag(c; alpha, mpsrf, transform)  src/output/gelmandiag.jl:3-60; codes[j] = 1 → log scale (link(c));
+ *                         out [(p + mpsrf) × 2] row-major, NOT rounded; multivariate row = (MPSRF, NaN); returns MCU_ERR_ARG for m < 2 */
+int mcu_chains_quantile(const double* value, int64_t n, int p, int64_t m, const double* q, int nq, double* out);
+int mcu_chains_hpd(const double* value, int64_t n, int p, int64_t m, double alpha, double* out);
+int mcu_chains_autocor(const double* value, int64_t n, int p, int64_t m, const int64_t* lags, int nlags, double* out);
+int mcu_chains_changerate(const double* value, int64_t n, int p, int64_t m, double* out);
+int mcu_chains_gelman(const double* value, int64_t n, int p, int64_t m, double alpha, const int* codes, int mpsrf, double* out);
+
 /* ---- RNG contract ----------------------------------------------------- */
 /* PHILOX: Philox4x32-10, key = seed, counter = (k >> 1, iteration, global chain, block | kind << 16 | stream << 24).
  * Every block update of every chain owns two streams (0 = rand(), 1 = randn()); k counts the draws of a stream in

@@ -965,6 +965,32 @@ int mcu_summarystats(mcu_handle h, int etype, int batch_size, double* out) {
   return MCU_OK;
 }
 
+int mcu_chains_quantile(const double* value, int64_t n, int p, int64_t m, const double* q, int nq, double* out) {
+  if (!value || !q || !out || n < 1 || p < 1 || m < 1 || nq < 1) return MCU_ERR_ARG;
+  hostdiag::chains_quantile(value, n, p, m, q, nq, out);
+  return MCU_OK;
+}
+int mcu_chains_hpd(const double* value, int64_t n, int p, int64_t m, double alpha, double* out) {
+  if (!value || !out || n < 1 || p < 1 || m < 1 || !(alpha > 0.0 && alpha < 1.0)) return MCU_ERR_ARG;
+  hostdiag::chains_hpd(value, n, p, m, alpha, out);
+  return MCU_OK;
+}
+int mcu_chains_autocor(const double* value, int64_t n, int p, int64_t m, const int64_t* lags, int nlags, double* out) {
+  if (!value || !lags || !out || n < 2 || p < 1 || m < 1 || nlags < 1) return MCU_ERR_ARG;
+  std::vector<long long> lg(lags, lags + nlags);
+  hostdiag::chains_autocor(value, n, p, m, lg.data(), nlags, out);
+  return MCU_OK;
+}
+int mcu_chains_changerate(const double* value, int64_t n, int p, int64_t m, double* out) {
+  if (!value || !out || n < 2 || p < 1 || m < 1) return MCU_ERR_ARG;
+  hostdiag::chains_changerate(value, n, p, m, out);
+  return MCU_OK;
+}
+int mcu_chains_gelman(const double* value, int64_t n, int p, int64_t m, double alpha, const int* codes, int mpsrf, double* out) {
+  if (!value || !out || n < 2 || p < 1) return MCU_ERR_ARG;
+  return hostdiag::chains_gelman(value, n, p, m, alpha, codes, mpsrf != 0, out) ? MCU_ERR_ARG : MCU_OK;   // "less than 2 chains": gelmandiag.jl:6-7
+}
+
 double mcu_fp64_peak_tflops(mcu_handle h) {
   if (!h) return -1.0;
   if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;

@@ -9,6 +9,7 @@
 //   f_quantile         quantile(FDist(d1, d2), p) (gelmandiag.jl:43) — hypergeometric series for the
 //                      regularised incomplete beta / gamma functions + bisection
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -143,6 +144,137 @@ inline int summarystats_soa(const double* smp, long long kept, int P, long long 
     const double r = sd / mc;
     out[j * 5 + 0] = mu; out[j * 5 + 1] = sd; out[j * 5 + 2] = sd / std::sqrt((double)N); out[j * 5 + 3] = mc;
     out[j * 5 + 4] = std::fmin(r * r, (double)kept);
+  }
+  return 0;
+}
+
+
+// ---- post-processing of a materialised chain array (ModelChains.value: [n iterations x p parameters x m chains], column-major,
+//      iteration fastest) — src/output/stats.jl:3-83 and the multivariate PSRF of src/output/gelmandiag.jl:49-55 -----------------
+inline double at(const double* v, long long n, int p, long long i, int j, long long k) { return v[(size_t)i + (size_t)n * ((size_t)j + (size_t)p * (size_t)k)]; }
+
+// quantile(c; q): stats.jl:74-83 — Julia's quantile(vec(x), q) (linear interpolation between order statistics, "type 7")
+inline void chains_quantile(const double* v, long long n, int p, long long m, const double* q, int nq, double* out) {
+  const size_t N = (size_t)n * (size_t)m;
+  std::vector<double> x(N);
+  for (int j = 0; j < p; ++j) {
+    for (long long k = 0; k < m; ++k) for (long long i = 0; i < n; ++i) x[(size_t)k * n + i] = at(v, n, p, i, j, k);
+    std::sort(x.begin(), x.end());
+    for (int a = 0; a < nq; ++a) {
+      const double h = (double)(N - 1) * q[a];
+      const size_t lo = (size_t)std::floor(h);
+      const size_t hi = lo + 1 < N ? lo + 1 : lo;
+      out[(size_t)j * nq + a] = x[lo] + (h - (double)lo) * (x[hi] - x[lo]);
+    }
+  }
+}
+// hpd(c; alpha): stats.jl:52-72 — shortest of the intervals [y_i, y_(n-m+i)], m = max(1, ceil(alpha n)), first minimum
+inline void chains_hpd(const double* v, long long n, int p, long long m, double alpha, double* out) {
+  const size_t N = (size_t)n * (size_t)m;
+  std::vector<double> x(N);
+  for (int j = 0; j < p; ++j) {
+    for (long long k = 0; k < m; ++k) for (long long i = 0; i < n; ++i) x[(size_t)k * n + i] = at(v, n, p, i, j, k);
+    std::sort(x.begin(), x.end());
+    size_t mm = (size_t)std::ceil(alpha * (double)N); if (mm < 1) mm = 1; if (mm > N) mm = N;
+    size_t best = 0; double bw = x[N - mm] - x[0];
+    for (size_t i = 1; i < mm; ++i) { const double w = x[N - mm + i] - x[i]; if (w < bw) { bw = w; best = i; } }
+    out[j * 2 + 0] = x[best]; out[j * 2 + 1] = x[N - mm + best];
+  }
+}
+// autocor(c; lags, relative): stats.jl:3-13 over StatsBase.autocor (demeaned, normalised by the lag-0 sum); `lags` are the
+// index lags actually applied to the stored series (the caller multiplies by the thinning step when relative = true, as the
+// reference does).  out [p x nlags x m], column-major like the reference's ChainSummary value.
+inline void chains_autocor(const double* v, long long n, int p, long long m, const long long* lags, int nlags, double* out) {
+  std::vector<double> z((size_t)n);
+  for (long long k = 0; k < m; ++k)
+    for (int j = 0; j < p; ++j) {
+      double mu = 0; for (long long i = 0; i < n; ++i) mu += at(v, n, p, i, j, k); mu /= (double)n;
+      double s0 = 0; for (long long i = 0; i < n; ++i) { z[i] = at(v, n, p, i, j, k) - mu; s0 += z[i] * z[i]; }
+      for (int a = 0; a < nlags; ++a) {
+        const long long lag = lags[a];
+        double s = 0;
+        if (lag >= 0 && lag < n) for (long long t = 0; t + lag < n; ++t) s += z[t] * z[t + lag];
+        out[(size_t)j + (size_t)p * ((size_t)a + (size_t)nlags * (size_t)k)] = (lag >= 0 && lag < n) ? s / s0 : NAN;
+      }
+    }
+}
+// changerate(c): stats.jl:19-39 — per-parameter and multivariate fraction of iterations whose value changed; NOT rounded
+inline void chains_changerate(const double* v, long long n, int p, long long m, double* out) {
+  std::vector<double> r((size_t)p, 0.0); double rmv = 0.0;
+  for (long long k = 0; k < m; ++k)
+    for (long long i = 1; i < n; ++i) {
+      bool any = false;
+      for (int j = 0; j < p; ++j) { const bool dx = at(v, n, p, i, j, k) != at(v, n, p, i - 1, j, k); r[j] += dx; any = any || dx; }
+      rmv += any;
+    }
+  const double den = (double)m * (double)(n - 1);
+  for (int j = 0; j < p; ++j) out[j] = r[j] / den;
+  out[p] = rmv / den;
+}
+// largest eigenvalue of a symmetric matrix (cyclic Jacobi; p is a handful of monitored parameters)
+inline double sym_eigmax(std::vector<double> A, int p) {
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0; for (int a = 0; a < p; ++a) for (int b = a + 1; b < p; ++b) off += A[a * p + b] * A[a * p + b];
+    if (off < 1e-300) break;
+    for (int a = 0; a < p; ++a)
+      for (int b = a + 1; b < p; ++b) {
+        if (A[a * p + b] == 0.0) continue;
+        const double th = (A[b * p + b] - A[a * p + a]) / (2.0 * A[a * p + b]);
+        const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < p; ++k) { const double ka = A[k * p + a], kb = A[k * p + b]; A[k * p + a] = c * ka - s * kb; A[k * p + b] = s * ka + c * kb; }
+        for (int k = 0; k < p; ++k) { const double ak = A[a * p + k], bk = A[b * p + k]; A[a * p + k] = c * ak - s * bk; A[b * p + k] = s * ak + c * bk; }
+      }
+  }
+  double mx = A[0]; for (int a = 1; a < p; ++a) mx = std::fmax(mx, A[a * p + a]);
+  return mx;
+}
+// gelmandiag(c; alpha, mpsrf, transform) on a materialised array: gelmandiag.jl:3-60.  codes[j] = 1: log scale (link(c)).
+// out [(p + mpsrf) x 2] row-major, NOT rounded; the multivariate row is (R_fixed + R_random_scale eigmax(W^-1 B), NaN), NaN when W is
+// not positive definite.  Returns 1 for fewer than 2 chains.
+inline int chains_gelman(const double* v, long long n, int p, long long m, double alpha, const int* codes, int mpsrf, double* out) {
+  if (m < 2) return 1;
+  auto val = [&](long long i, int j, long long k) { const double x = at(v, n, p, i, j, k); return (codes && codes[j] == 1) ? std::log(x) : x; };
+  std::vector<double> mean((size_t)m * p), W((size_t)p * p, 0.0), s2((size_t)m * p);
+  for (long long k = 0; k < m; ++k) {
+    for (int j = 0; j < p; ++j) { double s = 0; for (long long i = 0; i < n; ++i) s += val(i, j, k); mean[k * p + j] = s / (double)n; }
+    for (int a = 0; a < p; ++a)
+      for (int b = a; b < p; ++b) {
+        double s = 0; for (long long i = 0; i < n; ++i) s += (val(i, a, k) - mean[k * p + a]) * (val(i, b, k) - mean[k * p + b]);
+        s /= (double)(n - 1);
+        W[a * p + b] += s / (double)m; if (b != a) W[b * p + a] += s / (double)m;
+        if (a == b) s2[k * p + a] = s;
+      }
+  }
+  std::vector<double> gm((size_t)p, 0.0), B((size_t)p * p, 0.0);
+  for (int j = 0; j < p; ++j) { for (long long k = 0; k < m; ++k) gm[j] += mean[k * p + j]; gm[j] /= (double)m; }
+  for (int a = 0; a < p; ++a) for (int b = 0; b < p; ++b) {
+    double s = 0; for (long long k = 0; k < m; ++k) s += (mean[k * p + a] - gm[a]) * (mean[k * p + b] - gm[b]);
+    B[a * p + b] = (double)n * s / (double)(m - 1);
+  }
+  for (int j = 0; j < p; ++j) {   // the univariate columns through the same centred sums as the device path
+    double c2 = 0; for (long long k = 0; k < m; ++k) c2 += s2[k * p + j]; c2 /= (double)m;
+    double s[7] = {(double)m, 0, 0, 0, 0, 0, 0};
+    for (long long k = 0; k < m; ++k) { const double d = mean[k * p + j] - gm[j], e = s2[k * p + j] - c2; s[1] += d; s[2] += d * d; s[3] += e; s[4] += e * e; s[5] += e * d; s[6] += e * d * d; }
+    gelman_column((double)n, gm[j], c2, s, alpha, out + 2 * j);
+  }
+  if (mpsrf) {
+    // isposdef(W) ? R_fixed + R_random_scale * eigmax(inv(cholfact(W)) * B) : NaN — W^-1 B is similar to L^-1 B L^-T (W = L L')
+    std::vector<double> L((size_t)p * p, 0.0); bool pd = true;
+    for (int a = 0; a < p && pd; ++a)
+      for (int b = 0; b <= a; ++b) {
+        double s = W[a * p + b]; for (int k = 0; k < b; ++k) s -= L[a * p + k] * L[b * p + k];
+        if (a == b) { if (!(s > 0)) { pd = false; break; } L[a * p + a] = std::sqrt(s); } else L[a * p + b] = s / L[b * p + b];
+      }
+    double x = NAN;
+    if (pd) {
+      std::vector<double> Y((size_t)p * p), S((size_t)p * p);
+      for (int c = 0; c < p; ++c) for (int a = 0; a < p; ++a) { double s = B[a * p + c]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * Y[k * p + c]; Y[a * p + c] = s / L[a * p + a]; }   // Y = L^-1 B
+      for (int r = 0; r < p; ++r) for (int a = 0; a < p; ++a) { double s = Y[r * p + a]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * S[r * p + k]; S[r * p + a] = s / L[a * p + a]; }   // S = Y L^-T
+      for (int a = 0; a < p; ++a) for (int b = a + 1; b < p; ++b) { const double t = 0.5 * (S[a * p + b] + S[b * p + a]); S[a * p + b] = S[b * p + a] = t; }
+      x = (double)(n - 1) / (double)n + (double)(m + 1) / ((double)m * (double)n) * sym_eigmax(S, p);
+    }
+    out[2 * p] = x; out[2 * p + 1] = NAN;
   }
   return 0;
 }

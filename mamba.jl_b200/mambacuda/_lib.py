@@ -47,6 +47,7 @@ SYMBOLS = [
     "mcu_gelman_from_moments", "mcu_gelman", "mcu_summarystats", "mcu_summary_sums",
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
+    "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
 ]
 
 
@@ -95,5 +96,10 @@ def lib():
     L.mcu_fp64_peak_tflops.argtypes = [vp]
     L.mcu_last_kernel_ms.restype = C.c_double
     L.mcu_last_kernel_ms.argtypes = [vp]
+    L.mcu_chains_quantile.argtypes = [dp, i64, C.c_int, i64, dp, C.c_int, dp]
+    L.mcu_chains_hpd.argtypes = [dp, i64, C.c_int, i64, C.c_double, dp]
+    L.mcu_chains_autocor.argtypes = [dp, i64, C.c_int, i64, C.POINTER(i64), C.c_int, dp]
+    L.mcu_chains_changerate.argtypes = [dp, i64, C.c_int, i64, dp]
+    L.mcu_chains_gelman.argtypes = [dp, i64, C.c_int, i64, C.c_double, ip, C.c_int, dp]
     _lib = L
     return L

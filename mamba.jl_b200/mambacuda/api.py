@@ -302,10 +302,79 @@ def gelmandiag(c, alpha=0.05, mpsrf=False, transform=False):
     """gelmandiag(c; alpha, mpsrf, transform): src/output/gelmandiag.jl:3-60 (PSRF and 97.5% columns, rounded to 3 dp)."""
     if len(c.chains) < 2:
         raise ArgumentError("less than 2 chains supplied to gelman diagnostic")   # gelmandiag.jl:6-7
-    if mpsrf:
-        raise ArgumentError("the multivariate PSRF is not computed on the device (SURVEY.md §8f)")
+    if mpsrf:   # needs the p x p within / between covariances: computed on the materialised array (mcu_chains_gelman)
+        codes = c.engine.link_codes(transform) if (transform and getattr(c, "engine", None) is not None) else None
+        psrf = _chains_gelman(c.value, alpha, codes, True)
+        return np.round(psrf, 3), c.names + ["Multivariate"], ["PSRF", f"{100 * (1 - alpha / 2)}%"]
     psrf = c.engine.gelman(alpha, transform)
     return np.round(psrf, 3), c.names, ["PSRF", f"{100 * (1 - alpha / 2)}%"]
+
+
+def _value_f(c):
+    v = np.asfortranarray(c.value if isinstance(c, Chains) else c, dtype=np.float64)
+    if v.ndim != 3:
+        raise DimensionMismatch("value must be iterations x parameters x chains")
+    return v
+
+
+def _dp(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _chains_gelman(value, alpha, codes, mpsrf):
+    import ctypes as C
+    v = _value_f(value); n, p, m = v.shape
+    out = np.empty((p + int(mpsrf), 2))
+    cc = None if codes is None else (C.c_int * p)(*[int(x) for x in codes])
+    if _lib.lib().mcu_chains_gelman(_dp(v), n, p, m, float(alpha), cc, int(mpsrf), _dp(out)) != 0:
+        raise ArgumentError("less than 2 chains supplied to gelman diagnostic")
+    return out
+
+
+def quantile(c, q=(0.025, 0.25, 0.5, 0.75, 0.975)):
+    """quantile(c; q): src/output/stats.jl:74-83 → [p × length(q)]"""
+    v = _value_f(c); n, p, m = v.shape
+    qq = np.ascontiguousarray(q, dtype=np.float64); out = np.empty((p, qq.size))
+    _lib.lib().mcu_chains_quantile(_dp(v), n, p, m, _dp(qq), qq.size, _dp(out))
+    return out, c.names, [f"{100 * x}%" for x in qq]
+
+
+def hpd(c, alpha=0.05):
+    """hpd(c; alpha): src/output/stats.jl:52-72 → [p × 2]"""
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, 2))
+    if _lib.lib().mcu_chains_hpd(_dp(v), n, p, m, float(alpha), _dp(out)) != 0:
+        raise ArgumentError("alpha must be in (0, 1)")
+    return out, c.names, [f"{100 * (1 - alpha)}% Lower", f"{100 * (1 - alpha)}% Upper"]
+
+
+def autocor(c, lags=(1, 5, 10, 50), relative=True):
+    """autocor(c; lags, relative): src/output/stats.jl:3-13 → [p × length(lags) × chains]"""
+    import ctypes as C
+    lags = np.asarray(lags, dtype=np.int64)
+    if relative:
+        lags = lags * c.step
+    elif np.any(lags % c.step != 0):
+        raise ArgumentError("lags do not correspond to thinning interval")
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, lags.size, m), order="F")
+    lg = np.ascontiguousarray(lags)
+    _lib.lib().mcu_chains_autocor(_dp(v), n, p, m, lg.ctypes.data_as(C.POINTER(C.c_int64)), lags.size, _dp(out))
+    return out, c.names, [f"Lag {x}" for x in lags]
+
+
+def changerate(c):
+    """changerate(c): src/output/stats.jl:19-39 → [p + 1] rounded to 3 dp, last row "Multivariate"."""
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty(p + 1)
+    _lib.lib().mcu_chains_changerate(_dp(v), n, p, m, _dp(out))
+    return np.round(out, 3), c.names + ["Multivariate"], ["Change Rate"]
+
+
+def describe(c, q=(0.025, 0.25, 0.5, 0.75, 0.975), etype="bm"):
+    """describe(c): src/output/stats.jl:41-52 — summarystats + quantiles."""
+    return summarystats(c, etype=etype), quantile(c, q=q)
 
 
 def summarystats(c, etype="bm", batch=100):

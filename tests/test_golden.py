@@ -180,3 +180,63 @@ def test_gpu_diagnostics_match_the_golden_formulas_on_sampled_chains():
     ref = mg.summarystats(out)
     np.testing.assert_allclose(eng.summarystats("bm", 100), ref, rtol=1e-9)
     np.testing.assert_allclose(eng.summary_streaming(), ref, rtol=1e-8)   # 100 | 400: streaming batches = the reference's
+
+
+# ------------------------------------------------------------------------- chain post-processing behind the C ABI (CPU)
+def _np_hpd(x, alpha):
+    x = np.sort(x); n = x.size; m = max(1, int(np.ceil(alpha * n)))
+    a, b = x[:m], x[n - m:]
+    i = int(np.argmin(b - a))
+    return a[i], b[i]
+
+
+def _np_autocor(x, lag):
+    z = x - x.mean()
+    return float((z[:x.size - lag] * z[lag:]).sum() / (z * z).sum())
+
+
+def _np_mpsrf(c):
+    n, p, m = c.shape
+    W = np.mean([np.cov(c[:, :, k], rowvar=False) for k in range(m)], axis=0)
+    B = n * np.cov(c.mean(axis=0).T, rowvar=False)
+    lam = np.max(np.linalg.eigvals(np.linalg.solve(W, B)).real)
+    return (n - 1) / n + (m + 1) / (m * n) * lam
+
+
+def test_abi_chain_postprocessing_matches_numpy(mcu_built, gold_diag):
+    # quantile / hpd / autocor / changerate / gelmandiag(mpsrf = true) of src/output/stats.jl and gelmandiag.jl:49-55 through the
+    # host-array entry points (mcu_chains_*), against numpy restatements of the same formulas
+    from mambacuda import api
+    c = np.array(gold_diag["chains"])
+    n, p, m = c.shape
+    ch = api.Chains(c, start=3, thin=2, names=["a", "b", "c"])
+    q, names, labels = api.quantile(ch)
+    ref = np.array([np.quantile(c[:, j, :].reshape(-1), [0.025, 0.25, 0.5, 0.75, 0.975]) for j in range(p)])   # numpy default = Julia's type 7
+    np.testing.assert_allclose(q, ref, rtol=1e-13)
+    assert labels[0] == "2.5%" and names == ["a", "b", "c"]
+    h, _, _ = api.hpd(ch, alpha=0.05)
+    np.testing.assert_allclose(h, [_np_hpd(c[:, j, :].T.reshape(-1), 0.05) for j in range(p)], rtol=1e-13)
+    ac, _, lab = api.autocor(ch, lags=[1, 5], relative=True)       # index lags 2, 10 on the stored series (stats.jl:5-6)
+    assert lab == ["Lag 2", "Lag 10"] and ac.shape == (p, 2, m)
+    for j in range(p):
+        for k in range(m):
+            np.testing.assert_allclose(ac[j, :, k], [_np_autocor(c[:, j, k], 2), _np_autocor(c[:, j, k], 10)], rtol=1e-11)
+    with pytest.raises(api.ArgumentError):
+        api.autocor(ch, lags=[1, 3], relative=False)                # "lags do not correspond to thinning interval"
+    # changerate: a chain array with repeated values
+    rng = np.random.default_rng(0)
+    z = np.cumsum(rng.integers(0, 2, size=(50, 2, 3)), axis=0).astype(float)
+    cr, nm, _ = api.changerate(api.Chains(z))
+    d = np.diff(z, axis=0) != 0
+    np.testing.assert_allclose(cr, np.round(np.append(d.mean(axis=(0, 2)), d.any(axis=1).mean()), 3))
+    assert nm[-1] == "Multivariate"
+    # gelmandiag on the materialised array incl. the multivariate PSRF
+    g = api._chains_gelman(c, 0.05, None, True)
+    np.testing.assert_allclose(g[:p], gold_diag["gelmandiag_alpha_0.05"], rtol=1e-9)
+    assert g[p, 0] == pytest.approx(_np_mpsrf(c), rel=1e-9) and np.isnan(g[p, 1])
+    g2 = api._chains_gelman(c, 0.05, [0, 0, 1], True)
+    np.testing.assert_allclose(g2[:p], gold_diag["gelmandiag_log_last_column"], rtol=1e-9)
+    cl = c.copy(); cl[:, 2, :] = np.log(cl[:, 2, :])
+    assert g2[p, 0] == pytest.approx(_np_mpsrf(cl), rel=1e-9)
+    with pytest.raises(api.ArgumentError):
+        api._chains_gelman(c[:, :, :1], 0.05, None, False)          # less than 2 chains
