@@ -66,6 +66,7 @@ enum {
   MCU_NUTS = 4,        /* src/samplers/nuts.jl:47-205  */
   MCU_HMC = 5,         /* src/samplers/hmc.jl:47-111   */
   MCU_AMM = 6,         /* src/samplers/amm.jl:45-108   */
+  MCU_MALA = 8,        /* src/samplers/mala.jl:43-86 (epsilon, optional Sigma in scale[k*k]; dtype in grad)   */
   MCU_GIBBS = 7        /* exact draw from the block's full conditional, where the template has a conjugate form — the device
                           counterpart of a user-defined Gibbs sampler Sampler([:theta], (theta, ...) -> rand(...))
                           (src/samplers/sampler.jl:20-24, doc/mcmc/sampler.rst; the tutorial's Gibbs_beta / Gibbs_s2 are of this kind).

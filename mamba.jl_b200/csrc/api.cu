@@ -525,7 +525,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   std::vector<std::vector<double>> h_scales;
   for (int bi = 0; bi < n_blocks; ++bi) {
     const mcu_block_desc& d = blocks[bi];
-    if (d.kind < MCU_AMWG || d.kind > MCU_GIBBS) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
+    if (d.kind < MCU_AMWG || d.kind > MCU_MALA) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
     if (d.kind == MCU_GIBBS) {
       bool ok = false;
       if (d.n_nodes == 1) { MCU_DISPATCH(h, ok = M::has_gibbs(d.nodes[0])); }
@@ -560,13 +560,14 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
       for (int i = 0; i < k; ++i) sc.push_back(d.n_scale == 1 ? d.scale[0] : d.scale[i]);
     }
     std::vector<double> SL;
-    if (d.kind == MCU_AMM || (d.kind == MCU_HMC && d.scale)) {
+    if (d.kind == MCU_AMM || ((d.kind == MCU_HMC || d.kind == MCU_MALA) && d.scale)) {
       if (!d.scale || d.n_scale != k * k) return fail(h, MCU_ERR_ARG, "Sigma dimension differs from variate length " + std::to_string(k));   // amm.jl:36-41, hmc.jl:36-41
       if (d.kind == MCU_AMM && k > kAmmMaxK) return fail(h, MCU_ERR_UNSUPPORTED, "AMM blocks are limited to 8 elements on the device");
       std::vector<double> S(d.scale, d.scale + (size_t)k * k);
       if (!chol_lower_host(S, k, SL)) return fail(h, MCU_ERR_ARG, "Sigma is not positive definite");
     }
     if (d.kind == MCU_HMC && (d.L < 1 || !(d.epsilon > 0))) return fail(h, MCU_ERR_ARG, "HMC needs epsilon > 0 and L >= 1");
+    if (d.kind == MCU_MALA && !(d.epsilon > 0)) return fail(h, MCU_ERR_ARG, "MALA needs epsilon > 0");
     if (d.kind == MCU_RWM && (d.proposal < 0 || d.proposal > 2)) return fail(h, MCU_ERR_UNSUPPORTED, "RWM proposal not available on the device");
     if (d.grad < 0 || d.grad > 2) return fail(h, MCU_ERR_ARG, "unknown gradient mode");
     int *de = nullptr, *dl = nullptr; double *ds = nullptr, *dS = nullptr;

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(128) run_generic_kernel(typename M::Data data,
         case 4: nuts_sample<M::D>(v, b, tn, tgt, rng, fresh, iter <= a.burnin); break;
         case 5: hmc_sample<M::D>(v, b, tgt, rng); break;
         case 6: amm_sample<M::D>(v, b, tn, tgt, rng, fresh, isadapt); break;
+        case 8: mala_sample<M::D>(v, b, tgt, rng); break;
         case 7: M::gibbs(data, s, b.own[0], rng, [](double shape, Draws& r) { return rgamma_mt(shape, r); }); tgt.unlist(v); break;   // MCU_GIBBS
       }
       tgt.relist(v);                                           // m[sampler.params] = relist(block, v)

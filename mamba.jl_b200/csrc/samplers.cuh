@@ -286,6 +286,43 @@ MCU_NOINL void nuts_sample(double* v, const DevBlock& b, TuneRef tn, T& tgt, Dra
   }
 }
 
+// -------------------------------------------------------------------------------- MALA
+template <int K, class T>
+MCU_NOINL void mala_sample(double* v, const DevBlock& b, T& tgt, Draws& rng) {   // mala.jl:67-86
+  const int k = b.k;
+  const double se = sqrt(b.epsilon);
+  const double* SL = b.SigmaL;               // nullptr = identity; else column-major lower Cholesky factor of Sigma
+  double g0[K], g1[K], y[K], m0[K], m1[K], t[K], w[K];
+  auto Lmul = [&](const double* z, double* r) {    // r = L z, L = sqrt(epsilon) SigmaL
+    if (!SL) { for (int i = 0; i < k; ++i) r[i] = se * z[i]; return; }
+    for (int i = 0; i < k; ++i) { double s = 0; for (int c = 0; c <= i; ++c) s += SL[i + c * k] * z[c]; r[i] = se * s; }
+  };
+  auto Ltmul = [&](const double* z, double* r) {   // r = L' z
+    if (!SL) { for (int i = 0; i < k; ++i) r[i] = se * z[i]; return; }
+    for (int i = 0; i < k; ++i) { double s = 0; for (int c = i; c < k; ++c) s += SL[c + i * k] * z[c]; r[i] = se * s; }
+  };
+  auto half_sq_Linv = [&](const double* x) {       // |inv(L) x|^2 / 2
+    double acc = 0;
+    if (!SL) { for (int i = 0; i < k; ++i) { const double r = x[i] / se; acc += r * r; } return 0.5 * acc; }
+    for (int i = 0; i < k; ++i) { double s = x[i]; for (int c = 0; c < i; ++c) s -= se * SL[i + c * k] * t[c]; t[i] = s / (se * SL[i + i * k]); acc += t[i] * t[i]; }
+    return 0.5 * acc;
+  };
+  const double logf0 = tgt.logfgrad(v, g0);
+  for (int i = 0; i < k; ++i) w[i] = rng.normal();
+  Ltmul(g0, t); Lmul(t, m0);                       // M2 grad0 = 0.5 L L' grad0
+  for (int i = 0; i < k; ++i) m0[i] *= 0.5;
+  Lmul(w, t);
+  for (int i = 0; i < k; ++i) y[i] = v[i] + m0[i] + t[i];
+  const double logf1 = tgt.logfgrad(y, g1);
+  Ltmul(g1, t); Lmul(t, m1);
+  for (int i = 0; i < k; ++i) m1[i] *= 0.5;
+  for (int i = 0; i < k; ++i) w[i] = v[i] - y[i] - m1[i];
+  const double q0 = -half_sq_Linv(w);
+  for (int i = 0; i < k; ++i) w[i] = y[i] - v[i] - m0[i];
+  const double q1 = -half_sq_Linv(w);
+  if (rng.uniform() < exp((logf1 - q1) - (logf0 - q0))) copyv(v, y, k);
+}
+
 // -------------------------------------------------------------------------------- HMC
 template <int K, class T>
 MCU_NOINL void hmc_sample(double* v, const DevBlock& b, T& tgt, Draws& rng) {   // hmc.jl:72-111

@@ -97,6 +97,15 @@ def HMC(params, epsilon, L, Sigma=None, dtype="analytic"):         # src/sampler
     return Sampler(params, "hmc", **d)
 
 
+def MALA(params, epsilon, Sigma=None, dtype="analytic"):            # src/samplers/mala.jl:43-65
+    if dtype not in _lib.GRAD:
+        raise ArgumentError("dtype must be :forward, :central or :analytic")
+    d = dict(epsilon=epsilon, grad=dtype)
+    if Sigma is not None:
+        d["scale"] = np.asarray(Sigma, dtype=float)
+    return Sampler(params, "mala", **d)
+
+
 def AMM(params, Sigma, adapt="all", beta=0.05, scale=2.38):        # src/samplers/amm.jl:45-59
     _check_adapt(adapt)
     return Sampler(params, "amm", scale=np.asarray(Sigma, dtype=float), adapt=adapt, beta=beta, amm_scale=scale)

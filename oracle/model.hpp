@@ -38,7 +38,7 @@ struct Node {
   std::vector<int> targets;         // model.jl:17-25
 };
 
-enum SamplerKind { S_AMWG = 0, S_SLICE_UNI, S_SLICE_MULTI, S_RWM, S_NUTS, S_HMC, S_AMM, S_GIBBS };
+enum SamplerKind { S_AMWG = 0, S_SLICE_UNI, S_SLICE_MULTI, S_RWM, S_NUTS, S_HMC, S_AMM, S_GIBBS, S_MALA };
 
 struct Tune {  // union of the reference's *Tune types (amwg.jl:5-21, slice.jl:7-26, rwm.jl:5-22, nuts.jl:5-27, hmc.jl:5-28, amm.jl:5-24)
   bool init = false;

@@ -75,6 +75,12 @@ void block_update(Model& m, int b, Rng& rng) {
       hmc_sample(v, sp.epsilon, sp.L, SL, logfgrad, rng);
       break;
     }
+    case S_MALA: {
+      Vec SL;
+      if (!sp.scale.empty() && sp.scale.size() == k * k) { if (!chol_lower(sp.scale, k, SL)) SL.clear(); }   // MALA(params, epsilon, Sigma): mala.jl:17-23
+      mala_sample(v, sp.epsilon, SL, logfgrad, rng);
+      break;
+    }
     case S_GIBBS: {   // user-defined sampler: f(model) returns the new value of its node, written back below like any other (simulation.jl:99-103)
       if (!m.gibbs || sp.params.size() != 1 || !m.gibbs(m, sp.params[0], rng)) throw std::runtime_error("no Gibbs full conditional for this node");
       v = m.unlist_block(b, tr);
@@ -115,7 +121,7 @@ SamplerSpec spec_from_desc(const Model& m, const mcu_block_desc& d) {
     if (d.nodes[i] < 0 || d.nodes[i] >= (int)sn.size()) throw std::runtime_error("bad node id");
     s.params.push_back(sn[d.nodes[i]]); k += m.nodes[sn[d.nodes[i]]].len;
   }
-  s.transform = d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI ? d.transform != 0 : d.kind != MCU_GIBBS;
+  s.transform = d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI ? d.transform != 0 : d.kind != MCU_GIBBS;   // MALA, like NUTS / HMC / AMWG / AMM: SamplingBlock(model, block, true)
   s.adapt = d.adapt; s.batchsize = d.batchsize; s.proposal = d.proposal; s.L = d.L; s.grad = d.grad;
   s.max_depth = d.max_depth; s.target = d.target; s.epsilon = d.epsilon;
   s.beta = d.beta; s.amm_scale = d.amm_scale;

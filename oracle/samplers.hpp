@@ -262,6 +262,44 @@ inline void nuts_sample(Vec& v, Tune& t, const LogFGrad& f, bool adapt, Rng& rng
   }
 }
 
+// ---------------------------------------------------------------------------- MALA
+// SigmaL: empty = identity (UniformScaling), else k×k lower-triangular Cholesky factor, column-major.
+inline void mala_sample(Vec& v, double epsilon, const Vec& SigmaL, const LogFGrad& f, Rng& rng) {   // mala.jl:67-86
+  const size_t n = v.size();
+  const double se = std::sqrt(epsilon);
+  auto Lmul = [&](const Vec& z) {            // L z, L = sqrt(epsilon) SigmaL
+    Vec r(n);
+    if (SigmaL.empty()) { for (size_t i = 0; i < n; ++i) r[i] = se * z[i]; return r; }
+    for (size_t i = 0; i < n; ++i) { double s = 0; for (size_t k = 0; k <= i; ++k) s += SigmaL[i + k * n] * z[k]; r[i] = se * s; }
+    return r;
+  };
+  auto Ltmul = [&](const Vec& z) {           // L' z
+    Vec r(n);
+    if (SigmaL.empty()) { for (size_t i = 0; i < n; ++i) r[i] = se * z[i]; return r; }
+    for (size_t i = 0; i < n; ++i) { double s = 0; for (size_t k = i; k < n; ++k) s += SigmaL[k + i * n] * z[k]; r[i] = se * s; }
+    return r;
+  };
+  auto Linv = [&](const Vec& w) {            // inv(L) w by forward substitution
+    Vec r(n);
+    if (SigmaL.empty()) { for (size_t i = 0; i < n; ++i) r[i] = w[i] / se; return r; }
+    for (size_t i = 0; i < n; ++i) { double s = w[i]; for (size_t k = 0; k < i; ++k) s -= se * SigmaL[i + k * n] * r[k]; r[i] = s / (se * SigmaL[i + i * n]); }
+    return r;
+  };
+  auto M2mul = [&](const Vec& g) { Vec t = Lmul(Ltmul(g)); for (double& x : t) x *= 0.5; return t; };   // M2 = 0.5 L L'
+  Vec grad0, grad1, z(n), y(n), w(n);
+  const double logf0 = f(v, grad0);
+  for (size_t i = 0; i < n; ++i) z[i] = rng.normal();
+  const Vec m0 = M2mul(grad0), lz = Lmul(z);
+  for (size_t i = 0; i < n; ++i) y[i] = v[i] + m0[i] + lz[i];
+  const double logf1 = f(y, grad1);
+  const Vec m1 = M2mul(grad1);
+  for (size_t i = 0; i < n; ++i) w[i] = v[i] - y[i] - m1[i];
+  const double q0 = -0.5 * dotv(Linv(w));
+  for (size_t i = 0; i < n; ++i) w[i] = y[i] - v[i] - m0[i];
+  const double q1 = -0.5 * dotv(Linv(w));
+  if (rng.uniform() < std::exp((logf1 - q1) - (logf0 - q0))) v = y;
+}
+
 // ---------------------------------------------------------------------------- HMC
 // SigmaL: empty = identity (UniformScaling), else k×k lower-triangular Cholesky factor, column-major.
 inline void hmc_sample(Vec& v, double epsilon, int L, const Vec& SigmaL, const LogFGrad& f, Rng& rng) {   // hmc.jl:72-111

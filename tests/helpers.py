@@ -29,6 +29,9 @@ SCHEMES = {
     "line_rwm": ("line", [dict(kind="rwm", nodes=[0, 1], scale=[0.5, 0.2, 0.8])], LINE_INITS),
     "line_rwm_unif": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symuniform")], LINE_INITS),
     "line_rwm_tri": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symtriangular")], LINE_INITS),
+    "line_mala": ("line", [dict(kind="mala", nodes=[0, 1], epsilon=0.08)], LINE_INITS),
+    "line_mala_sigma": ("line", [dict(kind="mala", nodes=[0, 1], epsilon=0.08,
+                                      scale=np.array([[1.0, 0.2, 0.0], [0.2, 0.5, 0.1], [0.0, 0.1, 2.0]]))], LINE_INITS),
     "line_hmc": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=8)], LINE_INITS),
     "line_hmc_sigma": ("line", [dict(kind="hmc", nodes=[0, 1], epsilon=0.05, L=5,
                                      scale=np.array([[1.0, 0.2, 0.0], [0.2, 0.5, 0.1], [0.0, 0.1, 2.0]]))], LINE_INITS),

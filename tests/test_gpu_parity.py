@@ -151,6 +151,25 @@ def test_trajectories_match_oracle(oracle, name, iters, burnin, thin):
     assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4 if "amm" in name else 1e-6)
 
 
+@pytest.mark.parametrize("name", ["line_mala", "line_mala_sigma"])
+def test_mala_trajectories_match_oracle(oracle, name):
+    # The Langevin drift x + (epsilon/2) Sigma grad has Jacobian I + (epsilon/2) Sigma H; in the small-s2 region of the line model
+    # |epsilon H / 2| ~ 10, so rounding differences between the two machines grow ~10x per accepted step (first differences of
+    # 1e-8 appear after 100-300 iterations): step-wise agreement is observable over a short horizon, as for NUTS.
+    g, o, _, _ = run_pair(oracle, name, 32, 60, 0, 1)
+    assert_same_run(g, o, rtol=1e-5, min_frac=0.8)
+
+
+def test_mala_is_statistically_equivalent_to_the_published_posterior(oracle):
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("line_mala")
+    eng = Engine(tpl, 256, seed=2)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(6000, burnin=1000, thin=1, store=False, out=False, force_generic=True)
+    summ = eng.summary_streaming()
+    assert abs(summ[0, 0] - 0.5971) < 0.05 and abs(summ[1, 0] - 0.8017) < 0.02   # doc/tutorial.rst:432-436
+
+
 def nuts_pair(oracle, name, n_chains, iters, burnin, seed, force_generic=True):
     """The oracle runs the reference's recursive buildtree (nuts.jl:139-180), the device the unrolled
     leaf-by-leaf form; both stop doubling after 10 doublings."""

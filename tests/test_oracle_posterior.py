@@ -60,6 +60,15 @@ def test_rats_reference_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_line_mala_scheme(oracle):
+    # MALA(:beta, :s2 jointly on the transformed scale; mala.jl:67-86) targets the tutorial posterior (doc/tutorial.rst:432-436)
+    ref = {"beta[1]": (0.5971183, 0.016925598), "beta[2]": (0.8017036, 0.004793345)}
+    tpl, blocks, inits = helpers.scheme("line_mala_sigma")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 30000, burnin=2000, thin=2, seed=5, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_pumps_gibbs_amwg_scheme(oracle):
     # BASELINE.json configs[4]: Gibbs(theta) + Gibbs(beta) + AMWG(alpha) targets the same posterior as the reference's Slice scheme
     ref = {"beta": (0.93036099, 0.01824153419), "alpha": (0.69679849, 0.00722593007), "theta[1]": (0.05991674, 0.00032725274),
