@@ -13,7 +13,7 @@ module MambaCUDA
 
 using Mamba
 import Mamba: Model, ModelChains, ModelState, Sampler, Chains,
-              AMWGTune, SliceTune, RWMTune, NUTSTune, HMCTune, AMMTune
+              AMWGTune, SliceTune, RWMTune, NUTSTune, HMCTune, AMMTune, MALATune
 
 const libmambacuda = get(ENV, "LIBMAMBACUDA", "libmambacuda.so")
 
@@ -87,6 +87,8 @@ function blockdesc(m::Model, s::Sampler, nodeids::Dict{Symbol, Int}, keep::Vecto
          isa(s.tune, NUTSTune) ? 4 :
          isa(s.tune, HMCTune) ? 5 :
          isa(s.tune, AMMTune) ? 6 :
+         isa(s.tune, MALATune) ? 8 :
+         get(a, :gibbs, false) ? 7 :    # user-defined sampler registered through Gibbs(...) below
          throw(ArgumentError("sampler $(typeof(s.tune)) has no device implementation (no CPU fallback)"))
   length(s.params) <= MCU_MAX_BLOCK_NODES || throw(ArgumentError("a block names at most 8 nodes"))
   nodes = zeros(Int32, 8)
@@ -133,6 +135,19 @@ function HMC(params, epsilon::Real, L::Integer, Sigma=nothing; dtype::Symbol=:fo
   d = Dict{Symbol, Any}(:epsilon => epsilon, :L => L, :dtype => dtype)
   Sigma == nothing || (d[:scale] = Sigma)
   shimargs[s] = d; s
+end
+function MALA(params, epsilon::Real, Sigma=nothing; dtype::Symbol=:forward)
+  s = Sigma == nothing ? Mamba.MALA(params, epsilon, dtype=dtype) : Mamba.MALA(params, epsilon, Sigma, dtype=dtype)
+  d = Dict{Symbol, Any}(:epsilon => epsilon, :dtype => dtype)
+  Sigma == nothing || (d[:scale] = Sigma)
+  shimargs[s] = d; s
+end
+## A user-defined Gibbs sampler Sampler(params, f) has no device equivalent in general (f is a Julia closure); for the
+## node sets a template registers a conjugate full conditional for (pumps: [:theta], [:beta]) the shim tags the sampler so
+## that the block runs as MCU_GIBBS; `f` stays attached for the CPU path of stock Mamba.
+function Gibbs(params, f::Function)
+  s = Mamba.Sampler(params, f)
+  shimargs[s] = Dict{Symbol, Any}(:gibbs => true, :transform => false); s
 end
 function AMM(params, Sigma; adapt::Symbol=:all, beta::Real=0.05, scale::Real=2.38)
   s = Mamba.AMM(params, Sigma, adapt=adapt, beta=beta, scale=scale)
