@@ -157,13 +157,20 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def glm_synthetic(N, d):
-    """X[:,0] = 1, X[:,1:] ~ N(0,1), beta* ~ N(0, I/d), y ~ Bernoulli(invlogit(X beta*))."""
+def glm_synthetic(N, d, family="logit"):
+    """SURVEY.md §8d config 4: X[:,0] = 1, X[:,1:] ~ N(0,1), beta* ~ N(0, I/d), y ~ Bernoulli(invlogit(X beta*));
+    the other members of the GLM family: y ~ Poisson(exp(X beta*)), y ~ Normal(X beta*, 1)."""
     rng = np.random.default_rng(1)
     X = rng.standard_normal((N, d)); X[:, 0] = 1.0
     beta = np.random.default_rng(2).standard_normal(d) / np.sqrt(d)
-    p = 1.0 / (1.0 + np.exp(-(X @ beta)))
-    y = (np.random.default_rng(3).uniform(size=N) < p).astype(np.float64)
+    eta = X @ beta
+    r3 = np.random.default_rng(3)
+    if family == "poisson":
+        y = r3.poisson(np.exp(np.clip(eta, -20, 5))).astype(np.float64)
+    elif family == "normal":
+        y = eta + r3.standard_normal(N)
+    else:
+        y = (r3.uniform(size=N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
     return X, y, beta
 
 
@@ -174,9 +181,10 @@ def glm_bench(args, rank, local_rank, world):
     from mambacuda.engine import Engine
     torch.cuda.set_device(local_rank)
     N, d, C = args.glm_n, args.glm_d, args.glm_chains
-    X, y, beta_true = glm_synthetic(N, d)
+    X, y, beta_true = glm_synthetic(N, d, args.glm_family)
     eng = Engine("glm", C, seed=SEED, chain_offset=rank * C, device=local_rank)
     eng.set_data("X", X); eng.set_data("y", y)
+    eng.set_data("family", np.array([{"logit": 0.0, "poisson": 1.0, "normal": 2.0}[args.glm_family]]))
     eng.set_scheme([dict(kind="nuts", nodes=[0])])
     beta = 0.1 * np.random.default_rng(5).standard_normal((C, d))
     # gradient pass alone (the dominant kernel): tensor-core kernel vs FP64 reference kernel
@@ -212,7 +220,7 @@ def glm_bench(args, rank, local_rank, world):
             "metric": "chain_iters_per_sec", "value": world * C * args.glm_iters / dt, "unit": "chain-iterations/s", "n_gpus": world,
             "steps": 1, "warmup": 3, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16x2-split tensor (f32 accumulate) + f64 NUTS state", "data": "synthetic",
-            "config": {"workload": f"Bayesian logistic regression N={N}, d={d}, NUTS(beta), {C} chains/GPU (configs[3])",
+            "config": {"workload": f"Bayesian {args.glm_family} regression N={N}, d={d}, NUTS(beta), {C} chains/GPU (configs[3])",
                        "iters": args.glm_iters, "burnin": args.glm_iters // 2, "gradient_passes": int(ticks),
                        "l2": "X (449 MB packed) exceeds L2; every pass streams it from HBM",
                        "posterior_mean_abs_err_vs_truth": float(np.mean(np.abs(summ[:, 0] - beta_true)))},
@@ -305,6 +313,7 @@ def main():
     ap.add_argument("--glm-d", type=int, default=100)
     ap.add_argument("--glm-chains", type=int, default=512, help="chains per GPU (4096 chains on 8 GPUs)")
     ap.add_argument("--glm-iters", type=int, default=40)
+    ap.add_argument("--glm-family", default="logit", choices=["logit", "poisson", "normal"], help="member of the GLM family (tensor-core epilogue)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -65,6 +65,7 @@ struct mcu_ctx {
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
   int* g_nactive = nullptr; int g_nslab = 0;
+  double g_lp_const = 0.0;
   unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
 };
@@ -181,8 +182,10 @@ template <> struct Host<RatsModel> {
 template <> struct Host<PumpsModel> {
   static PumpsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["t"], h->d_inputs["lgy1"], (int)h->inputs["y"].size()}; }
 };
+inline int glm_family(mcu_ctx* h) { auto it = h->inputs.find("family"); return it == h->inputs.end() || it->second.empty() ? 0 : (int)it->second[0]; }
+inline double glm_sigma(mcu_ctx* h) { auto it = h->inputs.find("sigma"); return it == h->inputs.end() || it->second.empty() ? 1.0 : it->second[0]; }
 template <> struct Host<GlmM> {
-  static GlmM::Data data(mcu_ctx* h) { return {h->d_inputs["X"], h->d_inputs["y"], (int)h->inputs["y"].size(), h->glm_d}; }
+  static GlmM::Data data(mcu_ctx* h) { return {h->d_inputs["X"], h->d_inputs["y"], (int)h->inputs["y"].size(), h->glm_d, glm_family(h), glm_sigma(h)}; }
 };
 
 #define MCU_DISPATCH(h, BODY)                                                      \
@@ -345,12 +348,18 @@ int ensure_glm_buffers(mcu_ctx* h) {
   {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
-    glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, h->g_blob, h->stream); h->launches++;
+    const int fam = glm_family(h);
+    glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, fam, h->g_blob, h->stream); h->launches++;
     // X'(y - 1/2) (FP64, once): sum_i (y_i - 1/2) eta_i = beta . X'(y - 1/2) is the part of the log-likelihood that is linear in
     // beta (y eta from the Bernoulli term, -eta/2 from softplus(eta) = eta/2 + |eta|/2 + log(1 + e^-|eta|)); the fold adds it
     std::vector<double> xty(h->D, 0.0);
     const std::vector<double>& Xh = h->inputs["X"]; const std::vector<double>& yh = h->inputs["y"];
-    for (long long i = 0; i < N; ++i) { const double yi = yh[i] - 0.5; for (int j = 0; j < h->D; ++j) xty[j] += yi * Xh[(size_t)i * h->D + j]; }
+    // Bernoulli: X'(y - 1/2) (see above); Poisson: X'y, constant -sum lgamma(y + 1); Normal: the kernel forms the whole quadratic,
+    // constant -N (log sigma + log(2 pi) / 2)
+    h->g_lp_const = 0.0;
+    if (fam != 2) for (long long i = 0; i < N; ++i) { const double yi = fam == 0 ? yh[i] - 0.5 : yh[i]; for (int j = 0; j < h->D; ++j) xty[j] += yi * Xh[(size_t)i * h->D + j]; }
+    if (fam == 1) for (long long i = 0; i < N; ++i) h->g_lp_const -= std::lgamma(yh[i] + 1.0);
+    if (fam == 2) h->g_lp_const = -(double)N * (std::log(glm_sigma(h)) + 0.5 * 1.8378770664093454835606594728112);
     CK(cudaMalloc(&h->g_xty, sizeof(double) * h->D));
     CK(cudaMemcpyAsync(h->g_xty, xty.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -371,13 +380,13 @@ int ensure_glm_buffers(mcu_ctx* h) {
 
 int glm_gradient_dispatch(mcu_ctx* h, int N) {
   if (h->glm_impl == 1) {
-    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), h->stream) != 0)
+    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), glm_family(h), glm_sigma(h), h->stream) != 0)
       return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
     glm_fold_tc(h->g_part_lp, reinterpret_cast<const float*>(h->g_part_g), h->g_nslab_tc, h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc), h->D, h->C,
-                h->g_req, h->g_xty, h->g_lp, h->g_grad, h->stream);
+                h->g_req, h->g_xty, h->g_lp_const, h->g_lp, h->g_grad, h->stream);
   } else {
     glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
-                       h->g_lp, h->g_grad, h->stream);
+                       h->g_lp, h->g_grad, glm_family(h), glm_sigma(h), h->stream);
     h->launches += 1;
   }
   h->launches += 2;
@@ -485,6 +494,10 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
   }
+  if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))
+    return fail(h, MCU_ERR_ARG, "family must be 0 (Bernoulli / logit), 1 (Poisson / log) or 2 (Normal / identity)");
+  if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "sigma" && (n != 1 || !(ptr[0] > 0.0))) return fail(h, MCU_ERR_ARG, "sigma must be positive");
+  if (h->tpl == MCU_TPL_GLM_LOGIT) free_glm_buffers(h);   // packed X / y, X'y and the constants depend on the data
   h->inputs[nm].assign(ptr, ptr + n);
   h->data_dirty = true;
   return MCU_OK;

@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
 template <int DMAX>
 __global__ void __launch_bounds__(128) glm_grad_ref_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d,
                                                            long long C, const double* __restrict__ req, int rows_per_slab,
-                                                           double* __restrict__ part_lp /*[slab][C]*/, double* __restrict__ part_g /*[slab][d][C]*/) {
+                                                           double* __restrict__ part_lp /*[slab][C]*/, double* __restrict__ part_g /*[slab][d][C]*/,
+                                                           int family, double sigma) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int slab = blockIdx.y;
   if (c >= C) return;
@@ -350,10 +351,20 @@ __global__ void __launch_bounds__(128) glm_grad_ref_kernel(const double* __restr
     const double* xi = X + (size_t)i * d;
     double eta = 0.0;
     for (int j = 0; j < d; ++j) eta += xi[j] * beta[j];
-    const double p = 1.0 / (exp(-eta) + 1.0);
     const double yi = y[i];
-    lp += yi == 0.0 ? log(1.0 - p) : log(p);
-    const double r = yi - p;
+    double r;
+    if (family == 1) {          // Poisson / log link
+      const double lam = exp(eta);
+      lp += lp_poisson(yi, lgamma(yi + 1.0), lam);
+      r = yi - lam;
+    } else if (family == 2) {   // Normal / identity link, known sd
+      lp += lp_normal(yi, eta, sigma);
+      r = (yi - eta) / (sigma * sigma);
+    } else {                    // Bernoulli / logit link
+      const double p = 1.0 / (exp(-eta) + 1.0);
+      lp += yi == 0.0 ? log(1.0 - p) : log(p);
+      r = yi - p;
+    }
     for (int j = 0; j < d; ++j) g[j] += r * xi[j];
   }
   part_lp[(size_t)slab * C + c] = lp;
@@ -374,10 +385,10 @@ size_t glm_tick_scalar_slots() { return SL_COUNT; }
 size_t glm_tick_vector_slots() { return V_COUNT; }
 
 void glm_grad_reference(const double* X, const double* y, int N, int d, long long C, const double* req, int nslab,
-                        double* part_lp, double* part_g, double* lp, double* grad, cudaStream_t st) {
+                        double* part_lp, double* part_g, double* lp, double* grad, int family, double sigma, cudaStream_t st) {
   const int rows = (N + nslab - 1) / nslab;
   dim3 grid((unsigned)((C + 127) / 128), (unsigned)nslab);
-  glm_grad_ref_kernel<kGlmDMax><<<grid, 128, 0, st>>>(X, y, N, d, C, req, rows, part_lp, part_g);
+  glm_grad_ref_kernel<kGlmDMax><<<grid, 128, 0, st>>>(X, y, N, d, C, req, rows, part_lp, part_g, family, sigma);
   glm_fold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(part_lp, nslab, C, lp);
   glm_fold_kernel<<<(unsigned)(((long long)d * C + 255) / 256), 256, 0, st>>>(part_g, nslab, (long long)d * C, grad);
 }
@@ -402,9 +413,9 @@ __global__ void glm_fold2_kernel(const double* __restrict__ part_lp, const doubl
     lp[c] = s;
   }
 }
-// tensor-core path: FP32 gradient partials, logf partials hold -sum softplus(eta); lp[c] = beta_c . (X'y) + sum_s part_lp[s][c]
+// tensor-core path: FP32 gradient partials; lp[c] = lp_const + beta_c . xty + sum_s part_lp[s][c] (xty, lp_const: the family's linear / constant part)
 __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const float* __restrict__ part_g, int nslab_lp, int nslab_g,
-                                   long long C, int d, const double* __restrict__ req, const double* __restrict__ xty,
+                                   long long C, int d, const double* __restrict__ req, const double* __restrict__ xty, double lp_const,
                                    double* __restrict__ lp, double* __restrict__ grad) {
   const long long dC = (long long)d * C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -419,16 +430,16 @@ __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const flo
     grad[i] = (s0 + s1) + (s2 + s3);
   } else if (i < dC + C) {
     const long long c = i - dC;
-    double s = 0.0;
+    double s = lp_const;
     for (int k = 0; k < nslab_lp; ++k) s += part_lp[(size_t)k * C + c];
     for (int j = 0; j < d; ++j) s += req[(size_t)j * C + c] * xty[j];
     lp[c] = s;
   }
 }
 void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
-                 const double* xty, double* lp, double* grad, cudaStream_t st) {
+                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st) {
   const long long dC = (long long)d * C;
-  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp, grad);
+  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp_const, lp, grad);
 }
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st) {
   const long long dC = (long long)d * C;

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t pack_half2(__half lo, __half hi) {
 
 // ---- X pre-pack: fp64 [N x d] row-major → per tile [hi | lo | y] ----------------------------------------
 // hi/lo blocks: core matrices (8 rows x 8 cols fp16 = 128 B) ordered [row-block][col-block].
-__global__ void glm_pack_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d, int DP,
+__global__ void glm_pack_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d, int DP, int family,
                                 unsigned char* __restrict__ blob, size_t tile_bytes) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over tiles * TR * (DP/8) 16-byte chunks
   const int CB = DP / 8;
@@ -152,7 +152,7 @@ __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __re
   vl.x = pack_half2(lo[0], lo[1]); vl.y = pack_half2(lo[2], lo[3]); vl.z = pack_half2(lo[4], lo[5]); vl.w = pack_half2(lo[6], lo[7]);
   *reinterpret_cast<uint4*>(tile + off) = vh;
   *reinterpret_cast<uint4*>(tile + (size_t)TR * DP * 2 + off) = vl;
-  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)(y[grow] - 0.5) : 0.0f;   // y - 1/2; padding rows: X = 0, so eta = 0 and r = 0; their softplus(0) is taken back in the kernel
+  if (cb == 0) reinterpret_cast<float*>(tile + (size_t)2 * TR * DP * 2)[row] = grow < N ? (float)(family == 0 ? y[grow] - 0.5 : y[grow]) : 0.0f;   // Bernoulli: y - 1/2, else y; padding rows: X = 0, so eta = 0; their residual meets X = 0 and their logf term is taken back in the kernel
 }
 
 struct TcArgs {
@@ -163,6 +163,8 @@ struct TcArgs {
   double* part_lp;           // [nslab][C]   -ln2 * sum_i [ |s_i| / 2 + log2(1 + 2^-|s_i|) ],  s = eta * log2(e)
   float* part_g;             // [nslab][d][C]  FP32 running sum of the TMEM accumulator flushes (folded over slabs in FP64)
   int n_pad;                 // zero rows appended to the last tile
+  double theta_scale;        // log2(e) for the logit / log links (eta arrives as an exponent of 2), 1 for the identity link
+  float r_scale;             // Normal: 1 / sigma^2
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -188,6 +190,8 @@ enum { B_FULL0 = 0, B_D1FULL0 = B_FULL0 + kStages, B_RFULL0 = B_D1FULL0 + 2, B_G
 // Theta (the 128 requested positions, pre-scaled by log2 e, split fp16) lives in TENSOR MEMORY for the whole kernel: both GEMMs
 // take A from TMEM, shared memory holds nothing but X tiles.
 // TMEM columns: D1[0] 0-127, D1[1] 128-255, G 256-(256+DP), Theta_hi 384-(384+DP/2), Theta_lo 448-(448+DP/2).
+// FAM: 0 Bernoulli / logit, 1 Poisson / log, 2 Normal / identity (known sd) — the GLM family of north_star; only the epilogue differs.
+template <int FAM>
 __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int col = ck * 16 + e + u;
-          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.C + c] * 1.4426950408889634) : 0.0f;
+          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.C + c] * a.theta_scale) : 0.0f;
         }
         const __half2 h = __floats2half2_rn(x[0], x[1]);
         const float2 hb = __half22float2(h);
@@ -367,50 +371,89 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
       uint32_t v[32];
       tmem_ld32(tcol, v);
       tmem_wait_ld();
-      float abs_sum = 0.0f, lg_sum = 0.0f;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t ph[8], pl[8];
-        float prod = 1.0f;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 yq = y4[ch * 4 + (e >> 2)];
-          const float ym[4] = {yq.x, yq.y, yq.z, yq.w};
-          float r4[4];
-#pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-            const uint32_t b0 = v[ch * 16 + e + u], b1 = v[ch * 16 + e + u + 1];
-            const float s0 = __uint_as_float(b0), s1 = __uint_as_float(b1);   // eta * log2(e)
-            const float w0 = 1.0f + exp2f_approx(-fabsf(s0)), w1 = 1.0f + exp2f_approx(-fabsf(s1));
-            const float ww = w0 * w1;
-            const float rr = rcp_approx(ww);                  // one reciprocal for the pair
-            const float h0 = fmaf(rr, w1, -0.5f), h1 = fmaf(rr, w0, -0.5f);   // invlogit(|eta|) - 1/2  in [0, 1/2)
-            prod *= ww;
-            abs_sum += fabsf(s0); abs_sum += fabsf(s1);
-            // r = y - p,  p = 1/2 + copysign(h, eta)
-            r4[u] = ym[u] - __uint_as_float(__float_as_uint(h0) | (b0 & 0x80000000u));
-            r4[u + 1] = ym[u + 1] - __uint_as_float(__float_as_uint(h1) | (b1 & 0x80000000u));
+      float tile_sum;
+      if (FAM == 0) {
+        float abs_sum = 0.0f, lg_sum = 0.0f;
+  #pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t ph[8], pl[8];
+          float prod = 1.0f;
+  #pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 yq = y4[ch * 4 + (e >> 2)];
+            const float ym[4] = {yq.x, yq.y, yq.z, yq.w};
+            float r4[4];
+  #pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const uint32_t b0 = v[ch * 16 + e + u], b1 = v[ch * 16 + e + u + 1];
+              const float s0 = __uint_as_float(b0), s1 = __uint_as_float(b1);   // eta * log2(e)
+              const float w0 = 1.0f + exp2f_approx(-fabsf(s0)), w1 = 1.0f + exp2f_approx(-fabsf(s1));
+              const float ww = w0 * w1;
+              const float rr = rcp_approx(ww);                  // one reciprocal for the pair
+              const float h0 = fmaf(rr, w1, -0.5f), h1 = fmaf(rr, w0, -0.5f);   // invlogit(|eta|) - 1/2  in [0, 1/2)
+              prod *= ww;
+              abs_sum += fabsf(s0); abs_sum += fabsf(s1);
+              // r = y - p,  p = 1/2 + copysign(h, eta)
+              r4[u] = ym[u] - __uint_as_float(__float_as_uint(h0) | (b0 & 0x80000000u));
+              r4[u + 1] = ym[u + 1] - __uint_as_float(__float_as_uint(h1) | (b1 & 0x80000000u));
+            }
+  #pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const __half2 h = __floats2half2_rn(r4[u], r4[u + 1]);
+              const float2 hb = __half22float2(h);
+              const __half2 l = __floats2half2_rn(r4[u] - hb.x, r4[u + 1] - hb.y);
+              ph[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              pl[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-            const __half2 h = __floats2half2_rn(r4[u], r4[u + 1]);
-            const float2 hb = __half22float2(h);
-            const __half2 l = __floats2half2_rn(r4[u] - hb.x, r4[u + 1] - hb.y);
-            ph[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            pl[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&l);
-          }
+          lg_sum += lg2_approx(prod);                           // sum_16 log2(1 + 2^-|s|) = log2 of the product (<= 2^16)
+          tmem_st8(tcol + (uint32_t)(ch * 8), ph);              // R_hi: first 16 of the warp's 32 columns
+          tmem_st8(tcol + (uint32_t)(16 + ch * 8), pl);         // R_lo: last 16
         }
-        lg_sum += lg2_approx(prod);                           // sum_16 log2(1 + 2^-|s|) = log2 of the product (<= 2^16)
-        tmem_st8(tcol + (uint32_t)(ch * 8), ph);              // R_hi: first 16 of the warp's 32 columns
-        tmem_st8(tcol + (uint32_t)(16 + ch * 8), pl);         // R_lo: last 16
-      }
-      // softplus(eta) = ln2 * (s/2 + |s|/2 + log2(1 + 2^-|s|)); the s/2 part is linear in beta and, like sum y eta, is added by the
-      // fold as beta . X'(y - 1/2).  Padding rows of the last tile have s = 0: take their log2(2) = 1 back.
-      float tile_sum = fmaf(0.5f, abs_sum, lg_sum);
-      if (t0 + t == a.NT - 1 && a.n_pad > 0) {
-        const int first_pad = TR - a.n_pad;
-        const int lo_c = max(first_pad, cq * 32), hi_c = cq * 32 + 32;
-        if (hi_c > lo_c) tile_sum -= (float)(hi_c - lo_c);
+        // softplus(eta) = ln2 * (s/2 + |s|/2 + log2(1 + 2^-|s|)); the s/2 part is linear in beta and, like sum y eta, is added by the
+        // fold as beta . X'(y - 1/2).  Padding rows of the last tile have s = 0: take their log2(2) = 1 back.
+        tile_sum = fmaf(0.5f, abs_sum, lg_sum);
+        if (t0 + t == a.NT - 1 && a.n_pad > 0) {
+          const int first_pad = TR - a.n_pad;
+          const int lo_c = max(first_pad, cq * 32), hi_c = cq * 32 + 32;
+          if (hi_c > lo_c) tile_sum -= (float)(hi_c - lo_c);
+        }
+      } else {
+        // Poisson / log:  logf_i = y eta - e^eta (- lgamma(y + 1)),  r = y - e^eta;   Normal / identity:  logf_i = -(y - eta)^2 / (2 sigma^2),
+        // r = (y - eta) / sigma^2.  The y eta term of the Poisson family goes through beta . X'y in the fold, like the Bernoulli one.
+        float acc = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t ph[8], pl[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 yq = y4[ch * 4 + (e >> 2)];
+            const float ym[4] = {yq.x, yq.y, yq.z, yq.w};
+            float r4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float s = __uint_as_float(v[ch * 16 + e + u]);
+              if (FAM == 1) { const float lam = exp2f_approx(s); acc += lam; r4[u] = ym[u] - lam; }
+              else { const float d = ym[u] - s; acc = fmaf(d, d, acc); r4[u] = d * a.r_scale; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const __half2 h = __floats2half2_rn(r4[u], r4[u + 1]);
+              const float2 hb = __half22float2(h);
+              const __half2 l = __floats2half2_rn(r4[u] - hb.x, r4[u + 1] - hb.y);
+              ph[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              pl[(e + u) >> 1] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+          }
+          tmem_st8(tcol + (uint32_t)(ch * 8), ph);
+          tmem_st8(tcol + (uint32_t)(16 + ch * 8), pl);
+        }
+        tile_sum = acc;
+        if (FAM == 1 && t0 + t == a.NT - 1 && a.n_pad > 0) {   // padding rows: eta = 0, e^0 = 1 each
+          const int first_pad = TR - a.n_pad;
+          const int lo_c = max(first_pad, cq * 32), hi_c = cq * 32 + 32;
+          if (hi_c > lo_c) tile_sum -= (float)(hi_c - lo_c);
+        }
       }
       lp_acc += (double)tile_sum;
       tmem_wait_st();
@@ -425,7 +468,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
     if (cq > 0) lp_xchg[(cq - 1) * 128 + lane_row] = lp_acc;
     asm volatile("bar.sync 1, %0;" ::"r"(kEpiThreads) : "memory");
     if (cq == 0 && c < a.C) {
-      a.part_lp[(size_t)slab * a.C + c] = -0.6931471805599453 * (((lp_acc + lp_xchg[lane_row]) + lp_xchg[128 + lane_row]) + lp_xchg[256 + lane_row]);
+      const double lp_scale = FAM == 0 ? -0.6931471805599453 : (FAM == 1 ? -1.0 : -0.5 * (double)a.r_scale);
+      a.part_lp[(size_t)slab * a.C + c] = lp_scale * (((lp_acc + lp_xchg[lane_row]) + lp_xchg[128 + lane_row]) + lp_xchg[256 + lane_row]);
       if (T == 0)
         for (int j = 0; j < a.d; ++j) a.part_g[((size_t)slab * a.d + j) * a.C + c] = 0.0f;
     }
@@ -440,31 +484,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
 size_t glm_tc_tile_bytes(int d) { const int DP = (d + 15) / 16 * 16; return (size_t)2 * TR * DP * 2 + TR * sizeof(float); }
 long long glm_tc_num_tiles(long long N) { return (N + TR - 1) / TR; }
 
-void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* blob, cudaStream_t st) {
+void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st) {
   const int DP = (d + 15) / 16 * 16;
   const long long total = glm_tc_num_tiles(N) * TR * (DP / 8);
-  glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, blob, glm_tc_tile_bytes(d));
+  glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, family, blob, glm_tc_tile_bytes(d));
 }
 
 int glm_tc_nsub(long long, int) { return 1; }   // one FP32 gradient partial per slab (the flush intervals are summed in place)
 
 // Returns 0 on success.  part_lp [nslab][C] (FP64), part_g [nslab][d][C] (FP32), to be folded over slabs (glm_fold_tc).
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, float* part_g, cudaStream_t st) {
+                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st) {
   TcArgs a;
   a.DP = (d + 15) / 16 * 16;
   if (a.DP > 128) return -2;   // TMEM budget: G (DP columns) + Theta hi/lo (DP/2 each) next to the two D1 buffers
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
   a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  a.theta_scale = family == 2 ? 1.0 : 1.4426950408889634; a.r_scale = (float)(1.0 / (sigma * sigma));
   const size_t smem = kStages * a.tile_bytes + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
-  static thread_local size_t smem_set[64] = {0};   // per device: the attribute call is slow, do it once per size
+  static thread_local size_t smem_set[3][64] = {{0}};   // per family and device: the attribute call is slow, do it once per size
   int dev = 0; cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || smem_set[dev] != smem) {
-    if (cudaFuncSetAttribute(glm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+  if (family < 0 || family > 2) return -3;
+  const void* fn = family == 0 ? (const void*)glm_tc_kernel<0> : family == 1 ? (const void*)glm_tc_kernel<1> : (const void*)glm_tc_kernel<2>;
+  if (dev < 0 || dev >= 64 || smem_set[family][dev] != smem) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64) smem_set[family][dev] = smem;
   }
   dim3 grid((unsigned)((C + TM - 1) / TM), (unsigned)nslab);
-  glm_tc_kernel<<<grid, kTcThreads, smem, st>>>(a);
+  if (family == 0) glm_tc_kernel<0><<<grid, kTcThreads, smem, st>>>(a);
+  else if (family == 1) glm_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(a);
+  else glm_tc_kernel<2><<<grid, kTcThreads, smem, st>>>(a);
   return 0;   // launch errors surface at the next synchronisation of the handle's stream
 }
 

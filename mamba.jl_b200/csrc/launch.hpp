@@ -68,17 +68,17 @@ size_t glm_tick_scalar_slots();
 size_t glm_tick_vector_slots();
 void glm_advance(const GlmTick& t, cudaStream_t st);
 void glm_grad_reference(const double* X, const double* y, int N, int d, long long C, const double* req, int nslab,
-                        double* part_lp, double* part_g, double* lp, double* grad, cudaStream_t st);
+                        double* part_lp, double* part_g, double* lp, double* grad, int family, double sigma, cudaStream_t st);
 
 // ---- tensor-core GLM likelihood/gradient kernel (glm_tc.cu) ---------------------------------------------
 size_t glm_tc_tile_bytes(int d);
 long long glm_tc_num_tiles(long long N);
 int glm_tc_nsub(long long N, int nslab);
-void glm_tc_pack(const double* X, const double* y, int N, int d, unsigned char* blob, cudaStream_t st);
+void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st);
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, float* part_g, cudaStream_t st);
+                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st);
 void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
-                 const double* xty, double* lp, double* grad, cudaStream_t st);
+                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st);
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st);
 
 }  // namespace mcu

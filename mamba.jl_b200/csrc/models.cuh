@@ -314,7 +314,8 @@ struct PumpsModel {
 template <int DMAX>
 struct GlmModel {
   static constexpr int D = DMAX, NN = 1, NF = 2, P = DMAX;
-  struct Data { const double* X; const double* y; int N; int d; };
+  // family: 0 Bernoulli / logit, 1 Poisson / log, 2 Normal / identity with known sd sigma
+  struct Data { const double* X; const double* y; int N; int d; int family; double sigma; };
   MCU_HD static int node_off(int) { return 0; }
   MCU_HD static int node_len(int) { return DMAX; }
   MCU_HD static int node_link(int) { return LINK_IDENT; }
@@ -331,7 +332,7 @@ struct GlmModel {
     double lp = 0.0;
     for (int i = 0; i < d.N; ++i) {
       double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
-      lp += lp_bernoulli_logit(d.y[i], eta);
+      lp += d.family == 1 ? lp_poisson(d.y[i], lgamma(d.y[i] + 1.0), exp(eta)) : d.family == 2 ? lp_normal(d.y[i], eta, d.sigma) : lp_bernoulli_logit(d.y[i], eta);
     }
     return lp;
   }
@@ -339,7 +340,7 @@ struct GlmModel {
     for (int j = 0; j < d.d; ++j) g[j] = -s[j] / 1000.0;
     for (int i = 0; i < d.N; ++i) {
       double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
-      const double r = d.y[i] - 1.0 / (exp(-eta) + 1.0);
+      const double r = d.family == 1 ? d.y[i] - exp(eta) : d.family == 2 ? (d.y[i] - eta) / (d.sigma * d.sigma) : d.y[i] - 1.0 / (exp(-eta) + 1.0);
       for (int j = 0; j < d.d; ++j) g[j] += r * d.X[(size_t)i * d.d + j];
     }
   }

@@ -267,9 +267,15 @@ inline Model make_glm(int d) {
       const auto& X = mm.in("X"); const auto& be = mm.val(0);
       size_t N = X.size() / d;
       s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(N);
+      // GLM family (north_star "a GLM family"): inputs["family"] 0 = Bernoulli / logit (default), 1 = Poisson / log,
+      // 2 = Normal / identity with known sd inputs["sigma"] (default 1)
+      const int fam = mm.inputs.count("family") ? (int)mm.in("family")[0] : 0;
+      const double sg = mm.inputs.count("sigma") ? mm.in("sigma")[0] : 1.0;
       for (size_t i = 0; i < N; ++i) {
         double eta = 0; for (int j = 0; j < d; ++j) eta += X[i * d + j] * be[j];
-        s.distr.arr[i] = {D_BERNOULLI, invlogit(eta), 0.0};
+        if (fam == 1) s.distr.arr[i] = {D_POISSON, std::exp(eta), 0.0};
+        else if (fam == 2) s.distr.arr[i] = {D_NORMAL, eta, sg};
+        else s.distr.arr[i] = {D_BERNOULLI, invlogit(eta), 0.0};
       }
     };
     m.nodes.push_back(n); }
@@ -279,7 +285,9 @@ inline Model make_glm(int d) {
     for (int j = 0; j < d; ++j) g[j] = -be[j] / 1000.0;
     for (size_t i = 0; i < N; ++i) {
       double eta = 0; for (int j = 0; j < d; ++j) eta += X[i * d + j] * be[j];
-      double r = y[i] - invlogit(eta);
+      const int fam = mm.inputs.count("family") ? (int)mm.in("family")[0] : 0;
+      const double sg = mm.inputs.count("sigma") ? mm.in("sigma")[0] : 1.0;
+      double r = fam == 1 ? y[i] - std::exp(eta) : fam == 2 ? (y[i] - eta) / (sg * sg) : y[i] - invlogit(eta);
       for (int j = 0; j < d; ++j) g[j] += r * X[i * d + j];
     }
   };

@@ -109,6 +109,15 @@ def glm_block(X, y, beta):
     return normal(beta, 0, np.sqrt(1000.0)).sum() + lik, X.T @ (y - p) - beta / 1000.0
 
 
+def glm_family_block(X, y, beta, family, sigma=1.0):
+    """The GLM family of north_star: 1 = Poisson / log link, 2 = Normal / identity link with known sd."""
+    eta = X @ beta
+    prior = normal(beta, 0, np.sqrt(1000.0)).sum()
+    if family == 1:
+        return prior + st.poisson.logpmf(y, np.exp(eta)).sum(), X.T @ (y - np.exp(eta)) - beta / 1000.0
+    return prior + normal(y, eta, sigma).sum(), X.T @ ((y - eta) / sigma ** 2) - beta / 1000.0
+
+
 def states(rng, tpl, n):
     if tpl == "line":
         return np.column_stack([rng.normal(0.5, 1, n), rng.normal(0.8, 0.5, n), rng.gamma(2, 0.7, n)])
@@ -195,8 +204,22 @@ def main():
                             "logpdf": {"beta": [float(v[0]) for v in lg]}, "grad": {"beta": [v[1].tolist() for v in lg]}}
     with open(os.path.join(HERE, "block_logpdf.json"), "w") as f:
         json.dump(out, f)
-    # diagnostics
+    # diagnostics (drawn before the GLM-family fixtures below so that adding fixtures leaves earlier files unchanged)
     c = ar1_chains(rng, 400, 3, 4)
+    # GLM family: Poisson / log and Normal / identity on small synthetic designs
+    fam = {"_about": "GLM family golden vectors (scipy.stats), see make_golden.py"}
+    N, d = 96, 6
+    Xf = rng.normal(scale=0.5, size=(N, d)); Xf[:, 0] = 1.0
+    bt = rng.normal(size=d) / np.sqrt(d)
+    yp = rng.poisson(np.exp(Xf @ bt)).astype(float)
+    yn = Xf @ bt + 0.7 * rng.normal(size=N)
+    Bf = rng.normal(scale=0.4, size=(12, d))
+    for name, family, yy, sg in (("poisson", 1, yp, 1.0), ("normal", 2, yn, 0.7)):
+        lg = [glm_family_block(Xf, yy, b, family, sg) for b in Bf]
+        fam[name] = {"family": family, "sigma": sg, "X": Xf.tolist(), "y": yy.tolist(), "states": Bf.tolist(),
+                     "logpdf": [float(v[0]) for v in lg], "grad": [v[1].tolist() for v in lg]}
+    with open(os.path.join(HERE, "glm_family.json"), "w") as f:
+        json.dump(fam, f)
     diag = {"_about": "gelmandiag / summarystats golden values from the formulas of src/output/{gelmandiag,stats,mcse}.jl; see make_golden.py",
             "chains_shape": list(c.shape), "chains": c.tolist(), "gelmandiag_alpha_0.05": gelmandiag(c).tolist(),
             "gelmandiag_log_last_column": gelmandiag(np.concatenate([c[:, :2, :], np.log(c[:, 2:, :])], axis=1)).tolist(),

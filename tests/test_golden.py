@@ -83,6 +83,24 @@ def test_oracle_glm_density_and_gradient_match_golden(oracle, gold):
     np.testing.assert_allclose(gr, g["grad"]["beta"], rtol=1e-10, atol=1e-10)
 
 
+@pytest.fixture(scope="module")
+def gold_fam():
+    with open(os.path.join(GOLD, "glm_family.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["poisson", "normal"])
+def test_oracle_glm_family_matches_golden(oracle, gold_fam, name):
+    g = gold_fam[name]
+    X, y, B = np.array(g["X"]), np.array(g["y"]), np.array(g["states"])
+    o = oracle.Oracle("glm", glm_d=X.shape[1])
+    o.set_data("X", X); o.set_data("y", y); o.set_data("family", np.array([float(g["family"])])); o.set_data("sigma", np.array([g["sigma"]]))
+    o.set_scheme([dict(kind=4, nodes=[0])])
+    lp, gr = o.gradlogpdf(0, B, mode=0)
+    np.testing.assert_allclose(lp, g["logpdf"], rtol=1e-12)
+    np.testing.assert_allclose(gr, g["grad"], rtol=1e-10, atol=1e-10)
+
+
 def test_oracle_diagnostics_match_golden(oracle, gold_diag):
     c = np.array(gold_diag["chains"])
     np.testing.assert_allclose(oracle.gelmandiag(c), gold_diag["gelmandiag_alpha_0.05"], rtol=1e-9)
@@ -161,6 +179,47 @@ def test_gpu_glm_density_and_gradient_match_golden(gold):
     np.testing.assert_allclose(lp_tc + prior, g["logpdf"]["beta"], rtol=1e-5)
     gl = np.array(g["grad"]["beta"]) + B / 1000.0
     assert np.max(np.abs(g_tc - gl) / np.abs(gl).max(axis=1, keepdims=True)) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["poisson", "normal"])
+def test_gpu_glm_family_matches_golden(gold_fam, name):
+    # CUDA-core FP64 path to 1e-12, tensor-core path (Poisson / Normal epilogues of glm_tc_kernel) to north_star's 1e-5
+    from mambacuda.engine import Engine
+    g = gold_fam[name]
+    X, y, B = np.array(g["X"]), np.array(g["y"]), np.array(g["states"])
+    d = X.shape[1]
+    eng = Engine("glm", 12)
+    eng.set_data("X", X); eng.set_data("y", y); eng.set_data("family", np.array([float(g["family"])])); eng.set_data("sigma", np.array([g["sigma"]]))
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    lp, gr = eng.gradlogpdf(0, B, d)
+    np.testing.assert_allclose(lp, g["logpdf"], rtol=1e-12)
+    np.testing.assert_allclose(gr, g["grad"], rtol=1e-10, atol=1e-10)
+    prior = -0.5 * (B ** 2).sum(axis=1) / 1000.0 - 0.5 * d * np.log(2 * np.pi * 1000.0)
+    gl = np.array(g["grad"]) + B / 1000.0
+    for impl in (0, 1):
+        lp_k, g_k = eng.glm_gradient(B, impl=impl)
+        np.testing.assert_allclose(lp_k + prior, g["logpdf"], rtol=1e-12 if impl == 0 else 1e-5)
+        assert np.max(np.abs(g_k - gl) / np.abs(gl).max(axis=1, keepdims=True)) < (1e-10 if impl == 0 else 1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_poisson_glm_nuts_recovers_coefficients():
+    # NUTS through the tick engine with the tensor-core Poisson epilogue
+    from mambacuda.engine import Engine
+    rng = np.random.default_rng(12)
+    N, d = 5000, 5
+    X = rng.normal(scale=0.5, size=(N, d)); X[:, 0] = 1.0
+    beta = np.array([0.3, -0.5, 0.8, 0.2, -0.1])
+    y = rng.poisson(np.exp(X @ beta)).astype(float)
+    eng = Engine("glm", 128, seed=3)
+    eng.set_data("X", X); eng.set_data("y", y); eng.set_data("family", np.array([1.0]))
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    eng.set_inits(np.zeros((1, d)), jitter_sd=0.1)
+    eng.run(300, burnin=150, thin=1, store=False, out=False)
+    summ = eng.summary_streaming()
+    assert np.all(np.abs(summ[:, 0] - beta) < 5 * summ[:, 1] + 0.01)
+    assert (eng.gelman(0.05, False)[:, 0] < 1.1).all()
 
 
 @pytest.mark.gpu
