@@ -248,9 +248,14 @@ void free_scheme(mcu_ctx* h) {
   if (h->d_blocks) { cudaFree(h->d_blocks); h->d_blocks = nullptr; }
   h->h_blocks.clear();
 }
+// packed X / y tiles, X'y and the family constants: depend on the data only (they survive mcu_set_inits / mcu_set_state)
+void free_glm_data(mcu_ctx* h) {
+  cudaFree(h->g_blob); h->g_blob = nullptr; cudaFree(h->g_xty); h->g_xty = nullptr;
+}
+// tick-engine state of the chains
 void free_glm_buffers(mcu_ctx* h) {
   cudaFree(h->g_sc); cudaFree(h->g_vec); cudaFree(h->g_req); cudaFree(h->g_lp); cudaFree(h->g_grad); cudaFree(h->g_part_lp); cudaFree(h->g_part_g);
-  cudaFree(h->g_nactive); cudaFree(h->g_blob); h->g_blob = nullptr; cudaFree(h->g_xty); h->g_xty = nullptr;
+  cudaFree(h->g_nactive);
   h->g_sc = h->g_vec = h->g_req = h->g_lp = h->g_grad = h->g_part_lp = h->g_part_g = nullptr; h->g_nactive = nullptr;
 }
 void free_chain_buffers(mcu_ctx* h) {
@@ -328,9 +333,18 @@ int ensure_glm_buffers(mcu_ctx* h) {
   if (nslab < 1) nslab = 1;
   const long long nslab_ref = nslab; h->g_nslab = (int)nslab_ref;
   {
+    // one CTA per SM (tensor memory and shared memory are both fully used): pick the number of row slabs that minimises
+    // waves x tiles-per-slab, i.e. the idle SMs of the last wave (4,096 chains = 32 groups: 9 slabs = 288 CTAs = 1.95 waves
+    // instead of 4 slabs = 128 CTAs on 148 SMs)
     const long long groups = (h->C + 127) / 128;
-    long long ns = 148 / groups; if (ns < 1) ns = 1;
-    const long long NT = glm_tc_num_tiles(N); if (ns > NT) ns = NT;
+    const long long NT = glm_tc_num_tiles(N);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    long long ns = 1; double best = 1e300;
+    for (long long cand = 1; cand <= NT && cand * groups <= 8LL * sms; ++cand) {
+      const long long waves = (cand * groups + sms - 1) / sms, tps = (NT + cand - 1) / cand;
+      const double cost = (double)waves * ((double)tps + 6.0);   // + ~6 tiles of prologue / epilogue per CTA
+      if (cost < best - 1e-9) { best = cost; ns = cand; }
+    }
     h->g_nslab_tc = (int)ns;
     const long long npart = ns * glm_tc_nsub(N, (int)ns);   // FP64 gradient partials: one per (slab, flush interval)
     if (npart > nslab) nslab = npart;
@@ -345,7 +359,7 @@ int ensure_glm_buffers(mcu_ctx* h) {
   CK(cudaMalloc(&h->g_part_g, sizeof(double) * nslab * d * C));
   CK(cudaMalloc(&h->g_nactive, 2 * sizeof(int)));
   CK(cudaMemsetAsync(h->g_nactive, 0, 2 * sizeof(int), h->stream));
-  {
+  if (!h->g_blob) {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
     const int fam = glm_family(h);
@@ -406,7 +420,8 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
   const int N = (int)h->inputs["y"].size();
   // A tick = advance every chain to its next gradient request, then one gradient pass.  The host only looks at
   // the running-chain counter every kCheck ticks (finished chains idle; at most kCheck - 1 passes are wasted at the end).
-  const int kCheck = 4;
+  int kCheck = 8;
+  if (const char* e = std::getenv("MCU_GLM_CHECK")) { const int v = std::atoi(e); if (v > 0) kCheck = v; }
   int tick = 0;
   while (true) {
     int slot = 0;
@@ -473,7 +488,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
-  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->r_scratch);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->r_scratch); free_glm_data(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
   return MCU_OK;
@@ -497,7 +512,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))
     return fail(h, MCU_ERR_ARG, "family must be 0 (Bernoulli / logit), 1 (Poisson / log) or 2 (Normal / identity)");
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "sigma" && (n != 1 || !(ptr[0] > 0.0))) return fail(h, MCU_ERR_ARG, "sigma must be positive");
-  if (h->tpl == MCU_TPL_GLM_LOGIT) free_glm_buffers(h);   // packed X / y, X'y and the constants depend on the data
+  if (h->tpl == MCU_TPL_GLM_LOGIT) { free_glm_buffers(h); free_glm_data(h); }   // packed X / y, X'y and the constants depend on the data
   h->inputs[nm].assign(ptr, ptr + n);
   h->data_dirty = true;
   return MCU_OK;

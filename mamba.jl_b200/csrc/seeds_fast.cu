@@ -35,6 +35,9 @@
 #ifndef MCU_SEEDS_BW
 #define MCU_SEEDS_BW 2      // plates per trip in the b block (even)
 #endif
+#ifndef MCU_SEEDS_LOGU
+#define MCU_SEEDS_LOGU 1   // MH test on the log scale (log u evaluated off the critical path)
+#endif
 #ifndef MCU_SEEDS_ESTRIN
 #define MCU_SEEDS_ESTRIN 0
 #endif
@@ -179,6 +182,11 @@ MCU_D bool mh_accept(double u, double delta) {   // rand() < exp(logfprime - log
   if (!(delta > -700.0)) return false;            // exp underflows (or delta is NaN): u < 0 never holds
   return u < fast_exp(delta);
 }
+#if MCU_SEEDS_LOGU
+// rand() < exp(delta)  <=>  log(rand()) < delta: the log of the uniform does not depend on the proposal, so it is evaluated next to the
+// draw, off the exp -> log -> delta critical path of the update (same decision up to rounding of the comparison)
+MCU_D double log_uniform(double u) { return u > 0.0 ? fast_log(u) : -CUDART_INF; }
+#endif
 // the same decision without branches (the exp is always evaluated), so that two or three independent updates can be
 // scheduled into each other's dependency stalls
 MCU_D bool mh_accept_nb(double u, double delta) {
@@ -263,6 +271,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       for (int j = 0; j < 4; ++j) {
         double zn01;
         if ((j & 1) == 0) { const Pair pr = draw_normal_pair(a, chain, it32, 0, j >> 1); zn01 = pr.a; zc = pr.b; } else zn01 = zc;
+#if MCU_SEEDS_LOGU
+        double lu;                                                        // log of uniform j of the block, off the critical path
+        if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); lu = log_uniform(pr.a); uc = log_uniform(pr.b); } else lu = uc;
+#endif
         const double z = sg0 * zn01;                                      // z = sigma .* randn(n): normal j of the block
         const double anew = al0 + z;
         const unsigned pm = cfg.amask[j];
@@ -290,9 +302,13 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
           delta = fma(-0.5e-6, fma(anew, anew, -al0 * al0), delta);   // (x / 1000)^2 / 2 without the divisions
         }
+#if MCU_SEEDS_LOGU
+        if (lu < delta) {                                                 // rand() < exp(delta) on the log scale; lu was formed next to the draw
+#else
         double u;                                                         // uniform j of the block
         if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); u = pr.a; uc = pr.b; } else u = uc;
         if (mh_accept(u, delta)) {
+#endif
           al0 = anew;
           g = gn;   // bases of groups that do not contain alpha_j are recomputed to the same value
           for (int i = 0; i < NPL; ++i) if ((pm >> i) & 1u) { SLL(i) = SLN(i); SE(i) = SE(i) * E; }
@@ -335,7 +351,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; w += 2) {
           const Pair pz = draw_normal_pair(a, chain, it32, 1, (i0 + w) >> 1);
           const Pair pu = draw_uniform_pair(a, chain, it32, 1, (i0 + w) >> 1);
+#if MCU_SEEDS_LOGU
+          zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = log_uniform(pu.a); uu[w + 1] = log_uniform(pu.b);
+#else
           zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = pu.a; uu[w + 1] = pu.b;
+#endif
         }
         double bn[W], en[W], ln[W]; bool acc[W];
 #pragma unroll
@@ -345,7 +365,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
           en[w] = fast_exp(pick(g, cfg.grp[ir]) + bn[w]);                  // fresh e_i: also resets the drift of the alpha updates
           ln[w] = fast_log(1.0 + en[w]);
           const double dl = fma(cfg.r[ir], bn[w] - bi[w], -cfg.n[ix[w]] * (ln[w] - SLL(ix[w]))) - half_inv_s2 * fma(bn[w], bn[w], -bi[w] * bi[w]);
+#if MCU_SEEDS_LOGU
+          acc[w] = i0 + w < NPL && uu[w] < dl;
+#else
           acc[w] = i0 + w < NPL && mh_accept_nb(uu[w], dl);
+#endif
         }
 #pragma unroll
         for (int w = 0; w < W; ++w)
@@ -373,6 +397,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       if (adapt) m2 += 1.0;
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
+#if MCU_SEEDS_LOGU
+      const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
+#endif
       const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
       const double s2n = (xn > -700.0 && xn < 700.0) ? fast_exp(xn) : exp(xn);
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
@@ -380,8 +407,12 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       const double dx = xn - x;
       const double dinv = 1.0 / s2n - 1.0 / s2;
       const double delta = -(0.001 + 1.0) * dx - 0.001 * dinv + dx - 0.5 * S * dinv - (double)NPL * 0.5 * dx;
+#if MCU_SEEDS_LOGU
+      if (lus < delta) { x = xn; s2 = s2n; if (adapt) acs += 1; }
+#else
       const double u = draw_uniform_pair(a, chain, it32, 2, 0).a;
       if (mh_accept(u, delta)) { x = xn; s2 = s2n; if (adapt) acs += 1; }
+#endif
       if (adapt && ((long long)m2 % cfg.batchsize[2]) == 0) {
         const double dl = amwg_delta(m2, cfg.batchsize[2]);
         sgs *= exp((double)acs / m2 < cfg.target[2] ? -dl : dl);
