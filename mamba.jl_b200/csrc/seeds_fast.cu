@@ -38,6 +38,9 @@
 #ifndef MCU_SEEDS_LOGU
 #define MCU_SEEDS_LOGU 1   // MH test on the log scale (log u evaluated off the critical path)
 #endif
+#ifndef MCU_SEEDS_PIPE
+#define MCU_SEEDS_PIPE 0   // b block: draws of trip t + 1 generated during trip t — measured 10 % SLOWER (profiles/r1_seeds_fast_summary.md), kept for the record
+#endif
 #ifndef MCU_SEEDS_ESTRIN
 #define MCU_SEEDS_ESTRIN 0
 #endif
@@ -375,6 +378,37 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; ++w)
           if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) SAC(ix[w]) = ac[w] + 1.0; }
       };
+#if MCU_SEEDS_PIPE && MCU_SEEDS_LOGU
+      // Software-pipelined form (two plates per trip): the normals and log-uniforms of trip t + 1 depend on nothing but the counters, so
+      // they are generated DURING trip t — four independent dependency chains (two updates, Philox + Box-Muller, Philox + two logs) for
+      // the scheduler to interleave, and the exp -> log -> compare chain of a trip no longer waits for its own draws.
+      {
+        Pair pz = draw_normal_pair(a, chain, it32, 1, 0);
+        Pair lu; { const Pair pu = draw_uniform_pair(a, chain, it32, 1, 0); lu.a = log_uniform(pu.a); lu.b = log_uniform(pu.b); }
+#pragma unroll 1
+        for (int ip = 0; ip < (NPL + 1) / 2; ++ip) {
+          const int i0 = 2 * ip;
+          const bool two = i0 + 1 < NPL;
+          const int i1 = two ? i0 + 1 : NPL, r1 = two ? i0 + 1 : i0;           // odd plate count: the last trip pairs with the dummy slot
+          const double sga = SSG(i0), sgb = two ? SSG(i1) : 0.0;               // global (L2) loads, issued a whole trip ahead of their use
+          const double aca = adapt ? SAC(i0) : 0.0, acb = (adapt && two) ? SAC(i1) : 0.0;
+          const double bia = SB(i0), bib = SB(i1);
+          const double za = pz.a, zb = pz.b, lua = lu.a, lub = lu.b;
+          // draws of the next trip (one trip past the end is harmless: nothing consumes it)
+          pz = draw_normal_pair(a, chain, it32, 1, ip + 1);
+          { const Pair pu = draw_uniform_pair(a, chain, it32, 1, ip + 1); lu.a = log_uniform(pu.a); lu.b = log_uniform(pu.b); }
+          const double bna = bia + sga * za, bnb = bib + sgb * zb;
+          const double ena = fast_exp(pick(g, cfg.grp[i0]) + bna);             // fresh e_i: also resets the drift of the alpha updates
+          const double enb = fast_exp(pick(g, cfg.grp[r1]) + bnb);
+          const double lna = fast_log(1.0 + ena), lnb = fast_log(1.0 + enb);
+          const double da = fma(cfg.r[i0], bna - bia, -cfg.n[i0] * (lna - SLL(i0))) - half_inv_s2 * fma(bna, bna, -bia * bia);
+          const double db = fma(cfg.r[r1], bnb - bib, -cfg.n[i1] * (lnb - SLL(i1))) - half_inv_s2 * fma(bnb, bnb, -bib * bib);
+          const bool acca = lua < da, accb = two && lub < db;
+          if (acca) { SB(i0) = bna; SE(i0) = ena; SLL(i0) = lna; if (adapt) SAC(i0) = aca + 1.0; }
+          if (accb) { SB(i1) = bnb; SE(i1) = enb; SLL(i1) = lnb; if (adapt) SAC(i1) = acb + 1.0; }
+        }
+      }
+#else
       {
         constexpr int W = MCU_SEEDS_BW;
         int i0 = 0;
@@ -383,6 +417,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #pragma unroll 1
         for (; i0 < NPL; i0 += 2) b_trip(std::integral_constant<int, 2>{}, i0);
       }
+#endif
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
         const double dl = amwg_delta(m1, cfg.batchsize[1]);
         const double up = exp(dl), dn = exp(-dl);
