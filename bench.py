@@ -44,7 +44,7 @@ SCHEME = [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", no
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one seeds_fast_kernel launch (ncu --set full capture of this command,
 # profiles/r1_seeds_fast_summary.md), keyed by (chains per GPU, iterations per launch)
-SEEDS_KERNEL_DRAM_BYTES = {(125000, 2000): 85.83e6 + 125.20e6}
+SEEDS_KERNEL_DRAM_BYTES = {(125000, 2000): 86.63e6 + 117.40e6}
 
 
 def seeds_inits():
