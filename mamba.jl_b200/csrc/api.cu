@@ -61,6 +61,7 @@ struct mcu_ctx {
   bool seeds_fast_ok = false;
   bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
   std::vector<std::vector<double>> h_scales;                                // host mirror of every block's expanded scale
+  void* d_diag = nullptr; size_t diag_cap = 0;     // persistent scratch of the diagnostics reductions (partials | folded sums | codes | centres)
   void* d_stage = nullptr; size_t stage_cap = 0;   // reusable device staging buffer (no cudaMalloc/cudaFree on the hot API calls)
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
@@ -488,7 +489,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
-  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->r_scratch); free_glm_data(h);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->d_diag); cudaFree(h->r_scratch); free_glm_data(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
   return MCU_OK;
@@ -851,13 +852,27 @@ int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const doub
 }
 
 // ---- diagnostics ----------------------------------------------------------------------------------
-static int reduce_partials(mcu_handle h, double* d_partial, long long nblk, int width, double* host_out) {
-  double* d_out = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(double) * width));
-  launch_fold(d_partial, nblk, width, d_out, h->stream); h->launches++;
-  CK(cudaMemcpyAsync(host_out, d_out, sizeof(double) * width, cudaMemcpyDeviceToHost, h->stream));
+// Diagnostics scratch that lives as long as the handle (no cudaMalloc / cudaFree — each a device-wide sync — on the per-step calls):
+// layout [partials: nblk * width doubles | folded sums: width doubles | centres: 2 P doubles | codes: P ints]
+struct DiagScratch { double* partial; double* out; double* center; int* codes; };
+static int diag_scratch(mcu_ctx* h, long long nblk, int width, DiagScratch* s) {
+  const size_t need = sizeof(double) * ((size_t)nblk * width + width + 2 * (size_t)h->P) + sizeof(int) * (size_t)h->P + 64;
+  if (need > h->diag_cap) {
+    if (h->d_diag) cudaFree(h->d_diag);
+    h->d_diag = nullptr; h->diag_cap = 0;
+    if (cudaMalloc(&h->d_diag, need) != cudaSuccess) return fail(h, MCU_ERR_CUDA, "cudaMalloc(diagnostics scratch) failed");
+    h->diag_cap = need;
+  }
+  s->partial = static_cast<double*>(h->d_diag);
+  s->out = s->partial + (size_t)nblk * width;
+  s->center = s->out + width;
+  s->codes = reinterpret_cast<int*>(s->center + 2 * (size_t)h->P);
+  return MCU_OK;
+}
+static int reduce_partials(mcu_handle h, const DiagScratch& s, long long nblk, int width, double* host_out) {
+  launch_fold(s.partial, nblk, width, s.out, h->stream); h->launches++;
+  CK(cudaMemcpyAsync(host_out, s.out, sizeof(double) * width, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_out);
   CK(cudaGetLastError());
   return MCU_OK;
 }
@@ -867,13 +882,11 @@ int mcu_minmax(mcu_handle h, double* minmax) {
   if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
   CK(cudaSetDevice(h->device));
   const long long nblk = grid_for(h->C, 128);
-  double* d_partial = nullptr;
-  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * h->P * 2));
-  launch_minmax_partial(h->d_mom, h->C, h->P, d_partial, h->stream); h->launches++;
+  DiagScratch ds; int rc0 = diag_scratch(h, nblk, h->P * 2, &ds); if (rc0) return rc0;
+  launch_minmax_partial(h->d_mom, h->C, h->P, ds.partial, h->stream); h->launches++;
   std::vector<double> part((size_t)nblk * h->P * 2);
-  CK(cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(part.data(), ds.partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_partial);
   CK(cudaGetLastError());
   for (int j = 0; j < h->P; ++j) {
     double mn = INFINITY, mx = -INFINITY;
@@ -911,17 +924,16 @@ int mcu_moments(mcu_handle h, const int* codes, const double* center, double* su
   CK(cudaSetDevice(h->device));
   const int P = h->P;
   const long long nblk = grid_for(h->C, 128);
-  int* d_codes = nullptr; double* d_center = nullptr; double* d_partial = nullptr;
+  DiagScratch ds; int rc = diag_scratch(h, nblk, P * 7, &ds); if (rc) return rc;
   std::vector<int> zc(P, 0);
-  CK(cudaMalloc(&d_codes, sizeof(int) * P));
-  CK(cudaMemcpy(d_codes, codes ? codes : zc.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-  if (center) { CK(cudaMalloc(&d_center, sizeof(double) * P * 2)); CK(cudaMemcpy(d_center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice)); }
-  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * P * 7));
-  launch_gelman_partial(h->d_mom, h->d_momn, h->C, P, d_codes, d_center, d_partial, h->stream); h->launches++;
-  int rc = reduce_partials(h, d_partial, nblk, P * 7, sums);
-  cudaFree(d_codes); cudaFree(d_center); cudaFree(d_partial);
+  CK(cudaMemcpyAsync(ds.codes, codes ? codes : zc.data(), sizeof(int) * P, cudaMemcpyHostToDevice, h->stream));
+  if (center) CK(cudaMemcpyAsync(ds.center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice, h->stream));
+  launch_gelman_partial(h->d_mom, h->d_momn, h->C, P, ds.codes, center ? ds.center : nullptr, ds.partial, h->stream); h->launches++;
+  double n0 = 0;
+  if (n_kept) CK(cudaMemcpyAsync(&n0, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost, h->stream));   // completes with the sync below
+  rc = reduce_partials(h, ds, nblk, P * 7, sums);
   if (rc) return rc;
-  if (n_kept) { double n0 = 0; CK(cudaMemcpy(&n0, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost)); *n_kept = (int64_t)n0; }
+  if (n_kept) *n_kept = (int64_t)n0;
   return MCU_OK;
 }
 
@@ -954,13 +966,10 @@ int mcu_summary_sums(mcu_handle h, const double* center, double* sums) {
   CK(cudaSetDevice(h->device));
   const int P = h->P;
   const long long nblk = grid_for(h->C, 128);
-  double* d_center = nullptr; double* d_partial = nullptr;
-  if (center) { CK(cudaMalloc(&d_center, sizeof(double) * P * 2)); CK(cudaMemcpy(d_center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice)); }
-  CK(cudaMalloc(&d_partial, sizeof(double) * nblk * P * 8));
-  launch_summary_partial(h->d_mom, h->d_momn, h->C, P, d_center, d_partial, h->stream); h->launches++;
-  int rc = reduce_partials(h, d_partial, nblk, P * 8, sums);
-  cudaFree(d_center); cudaFree(d_partial);
-  return rc;
+  DiagScratch ds; int rc = diag_scratch(h, nblk, P * 8, &ds); if (rc) return rc;
+  if (center) CK(cudaMemcpyAsync(ds.center, center, sizeof(double) * P * 2, cudaMemcpyHostToDevice, h->stream));
+  launch_summary_partial(h->d_mom, h->d_momn, h->C, P, center ? ds.center : nullptr, ds.partial, h->stream); h->launches++;
+  return reduce_partials(h, ds, nblk, P * 8, sums);
 }
 
 int mcu_summary_from_sums(int64_t n_kept, int p, const double* center, const double* sums, double* out) {

@@ -50,16 +50,29 @@ inline double f_cdf(double q, double d1, double d2) {
   if (std::isinf(d2)) return igamma_series(0.5 * d1, 0.5 * d1 * q);
   return ibeta_series(0.5 * d1, 0.5 * d2, d1 * q / (d1 * q + d2));
 }
+// log density of F(d1, d2) (d2 = inf: chi-square(d1) / d1)
+inline double f_logpdf(double q, double d1, double d2) {
+  if (std::isinf(d2)) return std::log(d1) + (0.5 * d1 - 1.0) * std::log(d1 * q) - 0.5 * d1 * q - 0.5 * d1 * std::log(2.0) - lgam(0.5 * d1);
+  return 0.5 * (d1 * std::log(d1 * q) + d2 * std::log(d2) - (d1 + d2) * std::log(d1 * q + d2)) - std::log(q) -
+         (lgam(0.5 * d1) + lgam(0.5 * d2) - lgam(0.5 * (d1 + d2)));
+}
+// quantile(FDist(d1, d2), p): bracketed Newton on the CDF (a CDF evaluation is a series of O(sqrt(d)) terms, and with one chain per GPU
+// thread d1 = chains - 1 is ~1e5-1e7: plain bisection cost 10 ms per gelmandiag call), bisection whenever a Newton step leaves the bracket
 inline double f_quantile(double p, double d1, double d2) {
   if (!(d1 > 0.0) || !(d2 > 0.0) || std::isnan(d1) || std::isnan(d2)) return NAN;
   double lo = 0.0, hi = 1.0;
-  for (int g = 0; g < 1100 && f_cdf(hi, d1, d2) < p; ++g) hi *= 2.0;
+  for (int g = 0; g < 1100 && f_cdf(hi, d1, d2) < p; ++g) { lo = hi; hi *= 2.0; }
+  double q = 0.5 * (lo + hi);
   for (int it = 0; it < 200; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (mid <= lo || mid >= hi) break;
-    if (f_cdf(mid, d1, d2) < p) lo = mid; else hi = mid;
+    const double F = f_cdf(q, d1, d2);
+    if (F < p) lo = q; else hi = q;
+    const double dens = std::exp(f_logpdf(q, d1, d2));
+    double qn = (dens > 0.0 && std::isfinite(dens)) ? q - (F - p) / dens : NAN;
+    if (!(qn > lo && qn < hi)) qn = 0.5 * (lo + hi);
+    if (std::fabs(qn - q) <= 4e-16 * q || !(hi > lo)) { q = qn; break; }
+    q = qn;
   }
-  return 0.5 * (lo + hi);
+  return q;
 }
 
 // sums = { m, Σd, Σd², Σe, Σe², Σe·d, Σe·d² } with d = psibar - c1, e = s2 - c2 over chains.
