@@ -53,8 +53,9 @@ enum {
   MCU_TPL_SEEDS = 1,     /* doc/examples/seeds.jl:16-56    nodes: alpha0, alpha1, alpha2, alpha12, s2, b[21] */
   MCU_TPL_RATS = 2,      /* doc/examples/rats.jl:49-97     nodes: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30] */
   MCU_TPL_PUMPS = 3,     /* doc/examples/pumps.jl:12-39    nodes: alpha, beta, theta[10]      */
-  MCU_TPL_GLM_LOGIT = 4, /* synthetic Bernoulli-logit GLM  nodes: beta[d]  (no reference file; closest doc/examples/seeds.jl) */
-  MCU_N_TEMPLATES = 5
+  MCU_TPL_GLM_LOGIT = 4, /* synthetic GLM family (inputs X, y, family, sigma)  nodes: beta[d]  (no reference file; closest doc/examples/seeds.jl) */
+  MCU_TPL_SURGICAL = 5,  /* doc/examples/surgical.jl:11-43 nodes: mu, s2, b[12]; monitored mu, pop_mean, s2, p[12] */
+  MCU_N_TEMPLATES = 6
 };
 
 /* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */

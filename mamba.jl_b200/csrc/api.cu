@@ -136,6 +136,10 @@ void default_inputs(mcu_ctx* h) {
       in["y"] = y; in["rat"] = rat; in["Xm"] = Xm; in["xbar"] = {22.0};
       break;
     }
+    case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
+      in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
+      in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
+      break;
     case MCU_TPL_PUMPS:  // doc/examples/pumps.jl:4-9
       in["y"] = {5, 1, 5, 14, 3, 19, 1, 1, 4, 22};
       in["t"] = {94.3, 15.7, 62.9, 126, 5.24, 31.4, 1.05, 1.05, 2.1, 10.5};
@@ -150,7 +154,7 @@ int upload_inputs(mcu_ctx* h) {
   h->d_inputs.clear();
   if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
   auto in = h->inputs;   // derived arrays
-  if (h->tpl == MCU_TPL_SEEDS) in["lc"] = lchoose_vec(in["n"], in["r"]);
+  if (h->tpl == MCU_TPL_SEEDS || h->tpl == MCU_TPL_SURGICAL) in["lc"] = lchoose_vec(in["n"], in["r"]);
   if (h->tpl == MCU_TPL_PUMPS) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
     if (kv.second.empty()) continue;
@@ -180,6 +184,9 @@ template <> struct Host<SeedsModel> {
 template <> struct Host<RatsModel> {
   static RatsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["Xm"], h->d_rat, (int)h->inputs["y"].size(), h->inputs["xbar"][0]}; }
 };
+template <> struct Host<SurgicalModel> {
+  static SurgicalModel::Data data(mcu_ctx* h) { return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["lc"], (int)h->inputs["r"].size()}; }
+};
 template <> struct Host<PumpsModel> {
   static PumpsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["t"], h->d_inputs["lgy1"], (int)h->inputs["y"].size()}; }
 };
@@ -196,6 +203,7 @@ template <> struct Host<GlmM> {
     case MCU_TPL_RATS: { typedef RatsModel M; BODY; break; }                       \
     case MCU_TPL_PUMPS: { typedef PumpsModel M; BODY; break; }                     \
     case MCU_TPL_GLM_LOGIT: { typedef GlmM M; BODY; break; }                       \
+    case MCU_TPL_SURGICAL: { typedef SurgicalModel M; BODY; break; }               \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
 
@@ -213,6 +221,7 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_SEEDS: return tpl_info_fixed<SeedsModel>();
     case MCU_TPL_RATS: return tpl_info_fixed<RatsModel>();
     case MCU_TPL_PUMPS: return tpl_info_fixed<PumpsModel>();
+    case MCU_TPL_SURGICAL: return tpl_info_fixed<SurgicalModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
       t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
@@ -233,6 +242,7 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_SEEDS: return SeedsModel::monitor_names();
       case MCU_TPL_RATS: return RatsModel::monitor_names();
       case MCU_TPL_PUMPS: return PumpsModel::monitor_names();
+      case MCU_TPL_SURGICAL: return SurgicalModel::monitor_names();
       default: break;
     }
   }
@@ -508,6 +518,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->inputs.find(nm) == h->inputs.end()) return fail(h, MCU_ERR_ARG, "template has no input named " + nm);
     if (h->tpl == MCU_TPL_SEEDS && n != (size_t)SeedsModel::NP) return fail(h, MCU_ERR_DIM, "seeds inputs have 21 entries");
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
+    if (h->tpl == MCU_TPL_SURGICAL && n != (size_t)SurgicalModel::NH) return fail(h, MCU_ERR_DIM, "surgical inputs have 12 entries");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
   }
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))

@@ -17,6 +17,7 @@ MCU_DECLARE_TPL(SeedsModel)
 MCU_DECLARE_TPL(RatsModel)
 MCU_DECLARE_TPL(PumpsModel)
 MCU_DECLARE_TPL(GlmM)
+MCU_DECLARE_TPL(SurgicalModel)
 
 #define MCU_DEFINE_TPL(M)                                                                                    \
   void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st) {                                     \

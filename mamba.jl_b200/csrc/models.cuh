@@ -308,6 +308,53 @@ struct PumpsModel {
   }
 };
 
+// =============================================================================== surgical
+// doc/examples/surgical.jl:11-43: r_i ~ Binomial(n_i, invlogit(b_i)), b_i ~ Normal(mu, sqrt(s2)), mu ~ Normal(0, 1000),
+// s2 ~ InverseGamma(0.001, 0.001); Logical p = invlogit(b), pop_mean = invlogit(mu).  State: mu, s2, b[12].
+struct SurgicalModel {
+  static constexpr int D = 14, NN = 3, NF = 4, P = 15, NH = 12;
+  struct Data { const double* r; const double* n; const double* lc; int N; };
+  MCU_HD static int node_off(int n) { return n; }
+  MCU_HD static int node_len(int n) { return n == 2 ? NH : 1; }
+  MCU_HD static int node_link(int n) { return n == 1 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 2 ? 0x3u /* mu, s2 */ : f == 3 ? 0x4u /* b */ : 0u; }
+  // monitored: mu (stochastic, identity), pop_mean (Logical), s2 (log), p[12] (Logical)
+  MCU_HD static int mon_link(int j) { return j == 0 ? LINK_IDENT : j == 2 ? LINK_LOG : LINK_HEUR; }
+  static const char* node_name(int n) { static const char* nm[] = {"mu", "s2", "b"}; return nm[n]; }
+  static const char* state_names() { return "mu\ns2\nb[1]\nb[2]\nb[3]\nb[4]\nb[5]\nb[6]\nb[7]\nb[8]\nb[9]\nb[10]\nb[11]\nb[12]"; }
+  static const char* monitor_names() { return "mu\npop_mean\ns2\np[1]\np[2]\np[3]\np[4]\np[5]\np[6]\np[7]\np[8]\np[9]\np[10]\np[11]\np[12]"; }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_normal(s[0], 0.0, 1000.0);
+    if (f == 1) return lp_invgamma(s[1], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 2) {   // b ~ Normal(mu, sqrt(s2)), one distribution for the 12-vector
+      const double sigma = sqrt(s[1]);
+      double lp = 0.0;
+      for (int i = 0; i < d.N; ++i) lp += lp_normal(s[2 + i], s[0], sigma);
+      return lp;
+    }
+    double lp = 0.0;   // r[i] ~ Binomial(n[i], invlogit(b[i]))
+    for (int i = 0; i < d.N; ++i) lp += lp_binomial_logit(d.r[i], d.n[i], d.lc[i], s[2 + i]);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double mu = s[0], s2 = s[1];
+    double sd = 0.0, sdd = 0.0;
+    for (int i = 0; i < d.N; ++i) {
+      const double p = 1.0 / (exp(-s[2 + i]) + 1.0), db = s[2 + i] - mu;
+      g[2 + i] = (d.r[i] - d.n[i] * p) - db / s2;
+      sd += db; sdd += db * db;
+    }
+    g[0] = sd / s2 - mu / 1e6;
+    g[1] = -0.5 * (double)d.N / s2 + 0.5 * sdd / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data& d, const double* s, double* out) {
+    out[0] = s[0]; out[1] = 1.0 / (exp(-s[0]) + 1.0); out[2] = s[1];   // pop_mean = invlogit(mu): surgical.jl:34-36
+    for (int i = 0; i < d.N; ++i) out[3 + i] = 1.0 / (exp(-s[2 + i]) + 1.0);   // p = invlogit(b): surgical.jl:19-21
+  }
+};
+
 // =============================================================================== glm (CUDA-core form)
 // y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
 // small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.

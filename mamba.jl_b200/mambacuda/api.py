@@ -41,6 +41,7 @@ _TEMPLATES = {
     "rats": dict(nodes=[("mu_alpha", 1), ("mu_beta", 1), ("s2_alpha", 1), ("s2_beta", 1), ("s2_c", 1), ("alpha", 30), ("beta", 30)],
                  inputs=["y", "rat", "Xm", "xbar"]),
     "pumps": dict(nodes=[("alpha", 1), ("beta", 1), ("theta", 10)], inputs=["y", "t"]),
+    "surgical": dict(nodes=[("mu", 1), ("s2", 1), ("b", 12)], inputs=["r", "n"]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"]),
 }
 

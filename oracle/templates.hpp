@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -295,6 +295,54 @@ inline Model make_glm(int d) {
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// surgical: doc/examples/surgical.jl:11-43 (data :4-8).  Node order = topological order: mu, pop_mean, s2, b, p, r.
+inline Model make_surgical() {
+  Model m; m.template_id = TPL_SURGICAL;
+  m.inputs["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
+  m.inputs["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
+  { Node n = make_node("mu", true, 1, true, true);                        // 0: Normal(0, 1000)
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("pop_mean", false, 1, true, true);                 // 1: Logical, invlogit(mu)
+    n.sources = {0};
+    n.eval = [](const Model& mm, Node& l) { l.value.assign(1, invlogit(mm.val(0)[0])); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("s2", true, 1, true, true);                        // 2: InverseGamma(0.001, 0.001)
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b", true, 12, false, false);                      // 3: Normal(mu, sqrt(s2))
+    n.sources = {0, 2};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, mm.val(0)[0], std::sqrt(mm.val(2)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("p", false, 12, false, true);                      // 4: Logical, invlogit(b)
+    n.sources = {3};
+    n.eval = [](const Model& mm, Node& l) { const auto& b = mm.val(3); l.value.resize(b.size()); for (size_t i = 0; i < b.size(); ++i) l.value[i] = invlogit(b[i]); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("r", true, 12, false, false, true);                // 5: Binomial(n[i], p[i])
+    n.sources = {4};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& nn = mm.in("n"); const auto& p = mm.val(4);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(nn.size());
+      for (size_t i = 0; i < nn.size(); ++i) s.distr.arr[i] = {D_BINOMIAL, nn[i], p[i]};
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: mu, s2, b[12]
+    const auto& nn = mm.in("n"); const auto& r = mm.in("r"); const auto& b = mm.val(3);
+    const double mu = mm.val(0)[0], s2 = mm.val(2)[0];
+    double sd = 0, sdd = 0;
+    for (size_t i = 0; i < nn.size(); ++i) {
+      const double p = invlogit(b[i]), db = b[i] - mu;
+      g[2 + i] = (r[i] - nn[i] * p) - db / s2;
+      sd += db; sdd += db * db;
+    }
+    g[0] = sd / s2 - mu / 1e6;
+    g[1] = -0.5 * (double)nn.size() / s2 + 0.5 * sdd / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
 inline Model make_template(int id, int glm_d = 0) {
   switch (id) {
     case TPL_LINE: return make_line();
@@ -302,6 +350,7 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_RATS: return make_rats();
     case TPL_PUMPS: return make_pumps();
     case TPL_GLM: return make_glm(glm_d > 0 ? glm_d : 1);
+    case TPL_SURGICAL: return make_surgical();
     default: throw std::runtime_error("unknown template");
   }
 }

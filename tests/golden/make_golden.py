@@ -41,10 +41,12 @@ def reference_data():
     pumps = open(f"{REF}/doc/examples/pumps.jl").read()
     rats = open(f"{REF}/doc/examples/rats.jl").read()
     line = open(f"{REF}/doc/tutorial/line.jl").read()
+    surgical = open(f"{REF}/doc/examples/surgical.jl").read()
     d = {
         "seeds": {k: _field(seeds, k) for k in ("r", "n", "x1", "x2")},
         "pumps": {k: _field(pumps, k) for k in ("y", "t")},
         "line": {k: _field(line, k) for k in ("x", "y")},
+        "surgical": {k: _field(surgical, k) for k in ("r", "n")},
     }
     y = _field(rats, "y"); x = _field(rats, "x")
     assert y.size == 150 and x.size == 5
@@ -102,6 +104,14 @@ def pumps_blocks(D, s):
             "alpha_beta_transformed": pa + pb + np.log(a) + np.log(b) + pth, "theta_transformed": pth + np.log(th).sum() + lik}
 
 
+def surgical_blocks(D, s):
+    mu, s2, b = s[0], s[1], s[2:]
+    lik = st.binom.logpmf(D["r"], D["n"], invlogit(b)).sum()
+    pb = normal(b, mu, np.sqrt(s2)).sum()
+    pmu = normal(mu, 0, 1000.0); ps2 = invgamma(s2, 0.001, 0.001)
+    return {"b": pb + lik, "mu_s2_constrained": pmu + ps2 + pb, "mu_s2_transformed": pmu + ps2 + np.log(s2) + pb}
+
+
 def glm_block(X, y, beta):
     eta = X @ beta
     p = invlogit(eta)
@@ -128,6 +138,8 @@ def states(rng, tpl, n):
                                 rng.normal(240, 15, (n, 30)), rng.normal(6, 0.6, (n, 30))])
     if tpl == "pumps":
         return np.column_stack([rng.gamma(2, 0.5, n), rng.gamma(2, 0.5, n), rng.gamma(1.5, 0.6, (n, 10))])
+    if tpl == "surgical":
+        return np.column_stack([rng.normal(-2.5, 0.3, n), rng.gamma(2, 0.1, n), rng.normal(-2.5, 0.5, (n, 12))])
     raise ValueError(tpl)
 
 
@@ -188,7 +200,7 @@ def main():
     D = reference_data()
     rng = np.random.default_rng(20261018)
     out = {"_about": "formula-level golden vectors (scipy.stats restatement of logpdf! per block); see make_golden.py",
-           "data": {k: {kk: np.asarray(vv).tolist() for kk, vv in v.items()} for k, v in D.items()}, "blocks": {}}
+           "data": {k: {kk: np.asarray(vv).tolist() for kk, vv in v.items()} for k, v in D.items() if k != "surgical"}, "blocks": {}}
     fn = {"line": line_blocks, "seeds": seeds_blocks, "rats": rats_blocks, "pumps": pumps_blocks}
     for tpl in ("line", "seeds", "rats", "pumps"):
         S = states(rng, tpl, 12)
@@ -220,6 +232,15 @@ def main():
                      "logpdf": [float(v[0]) for v in lg], "grad": [v[1].tolist() for v in lg]}
     with open(os.path.join(HERE, "glm_family.json"), "w") as f:
         json.dump(fam, f)
+    # templates added after the first fixture files (own RNG stream, so earlier files do not change)
+    rng2 = np.random.default_rng(20261019)
+    extra = {"_about": "block_logpdf fixtures of templates added later; same construction as block_logpdf.json",
+             "data": {"surgical": {k: v.tolist() for k, v in D["surgical"].items()}}, "blocks": {}}
+    S = states(rng2, "surgical", 12)
+    vals = [surgical_blocks(D["surgical"], s) for s in S]
+    extra["blocks"]["surgical"] = {"states": S.tolist(), "logpdf": {k: [float(v[k]) for v in vals] for k in vals[0]}}
+    with open(os.path.join(HERE, "block_logpdf_extra.json"), "w") as f:
+        json.dump(extra, f)
     diag = {"_about": "gelmandiag / summarystats golden values from the formulas of src/output/{gelmandiag,stats,mcse}.jl; see make_golden.py",
             "chains_shape": list(c.shape), "chains": c.tolist(), "gelmandiag_alpha_0.05": gelmandiag(c).tolist(),
             "gelmandiag_log_last_column": gelmandiag(np.concatenate([c[:, :2, :], np.log(c[:, 2:, :])], axis=1)).tolist(),

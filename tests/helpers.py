@@ -12,6 +12,9 @@ RATS_INITS = np.array([[150, 10, 1, 1, 1] + [250] * 30 + [6] * 30,              
 LINE_INITS = np.array([[0.3, -0.2, 1.5], [1.0, 0.5, 0.7], [-0.5, 1.2, 3.0]])
 
 
+SURGICAL_INITS = np.array([[0.0, 1.0] + [0.1] * 12, [1.0, 10.0] + [0.5] * 12])                       # doc/examples/surgical.jl:47-50
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -52,6 +55,9 @@ SCHEMES = {
                                  dict(kind="slice_uni", nodes=[1, 3], scale=1.0)], RATS_INITS),
     # NUTS(alpha, beta, mu_alpha, mu_beta) + Slice(s2_c, s2_alpha, s2_beta; univariate)
     "rats_nuts_slice": ("rats", [dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], RATS_INITS),
+    # doc/examples/surgical.jl:54-55: NUTS(:b), Slice([:mu, :s2], 1.0)
+    "surgical_nuts_slice": ("surgical", [dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], SURGICAL_INITS),
+    "surgical_amwg": ("surgical", [dict(kind="amwg", nodes=[2], scale=0.3), dict(kind="amwg", nodes=[0, 1], scale=0.3)], SURGICAL_INITS),
     # doc/examples/pumps.jl:52-53
     "pumps_slice": ("pumps", [dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], None),
     "pumps_amwg_nuts": ("pumps", [dict(kind="amwg", nodes=[0, 1], scale=0.5), dict(kind="nuts", nodes=[2])], None),

@@ -32,6 +32,11 @@ BLOCKS = {
         "nuts_alpha_beta_mu": ([dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], 0),
         "slice_s2c_s2a_s2b": ([dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], 1),
     },
+    "surgical": {
+        "b": ([dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], 0),
+        "mu_s2_constrained": ([dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], 1),
+        "mu_s2_transformed": ([dict(kind="amwg", nodes=[0, 1], scale=0.3)], 0),
+    },
     "pumps": {
         "alpha_beta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 0),
         "theta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 1),
@@ -44,6 +49,12 @@ BLOCKS = {
 @pytest.fixture(scope="module")
 def gold():
     with open(os.path.join(GOLD, "block_logpdf.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def gold_extra():
+    with open(os.path.join(GOLD, "block_logpdf_extra.json")) as f:
         return json.load(f)
 
 
@@ -70,6 +81,14 @@ def test_oracle_block_densities_match_golden(oracle, gold, tpl):
         o = oracle.Oracle(tpl)
         o.set_scheme(_oracle_blocks(blocks))
         np.testing.assert_allclose(o.logpdf(bi, S), gold["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=f"{tpl}/{key}")
+
+
+def test_oracle_surgical_block_densities_match_golden(oracle, gold_extra):
+    S = np.array(gold_extra["blocks"]["surgical"]["states"])
+    for key, (blocks, bi) in BLOCKS["surgical"].items():
+        o = oracle.Oracle("surgical")
+        o.set_scheme(_oracle_blocks(blocks))
+        np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"]["surgical"]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
 
 
 def test_oracle_glm_density_and_gradient_match_golden(oracle, gold):
@@ -156,6 +175,17 @@ def test_gpu_block_densities_match_golden(gold, tpl):
         eng = Engine(tpl, 4)
         eng.set_scheme(blocks)
         np.testing.assert_allclose(eng.logpdf(bi, S), gold["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=f"{tpl}/{key}")
+        eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_surgical_block_densities_match_golden(gold_extra):
+    from mambacuda.engine import Engine
+    S = np.array(gold_extra["blocks"]["surgical"]["states"])
+    for key, (blocks, bi) in BLOCKS["surgical"].items():
+        eng = Engine("surgical", 4)
+        eng.set_scheme(blocks)
+        np.testing.assert_allclose(eng.logpdf(bi, S), gold_extra["blocks"]["surgical"]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
         eng.close()
 
 

@@ -34,11 +34,11 @@ def random_states(inits, B, rng, D_pos):
     return st
 
 
-POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12))}
+POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}}
 
 
 @pytest.mark.parametrize("name", ["line_amwg_slice", "line_nuts_all", "seeds_amwg", "seeds_amm", "rats_slice_amwg",
-                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts"])
+                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg"])
 def test_logpdf_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -137,6 +137,7 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("rats_slice_amwg", 200, 100, 2),
     ("pumps_slice", 300, 100, 2),
     ("pumps_gibbs_amwg", 300, 100, 2),
+    ("surgical_amwg", 300, 150, 2),
     ("line_rwm", 500, 0, 1),
     ("line_rwm_unif", 500, 0, 1),
     ("line_rwm_tri", 500, 0, 1),
@@ -187,7 +188,7 @@ def nuts_pair(oracle, name, n_chains, iters, burnin, seed, force_generic=True):
     return (out_g, st_g, tune_g), (out_o, st_o, tune_o)
 
 
-@pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts"])
+@pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts", "surgical_nuts_slice"])
 def test_nuts_adaptive_trajectories_match_oracle(oracle, name):
     # Dual averaging multiplies a perturbation of the acceptance statistic by sqrt(m)/gamma/(m+t0) ~ 2-10x per
     # adaptive iteration (nuts.jl:70-75), so libm-level rounding differences between two machines grow
@@ -244,6 +245,25 @@ def test_rats_warp_kernel_posterior_matches_published_table(oracle):
     assert np.all(np.abs(summ[:, 0] - ref) < 3 * np.hypot(ref_mcse, summ[:, 3]) + 0.02 * ref_sd)
     np.testing.assert_allclose(summ[:, 1], ref_sd, rtol=0.08)
     assert (eng.gelman(0.05, True)[:, 0] < 1.05).all()
+
+
+def test_surgical_posterior_matches_published_table(oracle):
+    # doc/examples/surgical.rst: mu -2.5503 (0.152), pop_mean 0.07306 (0.0101), s2 0.1831 (0.161), p[4] 0.05986, p[8] 0.12230
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("surgical_nuts_slice")
+    eng = Engine(tpl, 1024, seed=6)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(3000, burnin=1500, thin=1, store=False, out=False)
+    summ = eng.summary_streaming()
+    names = eng.names(1)
+    ref = {"mu": (-2.550263247, 0.0035, 0.1518), "pop_mean": (0.073062651, 0.00023, 0.0101), "s2": (0.183080212, 0.0063, 0.1612),
+           "p[4]": (0.059863573, 0.00033, 0.0082), "p[8]": (0.122296440, 0.00086, 0.0233)}
+    for nm, (mean, mcse_ref, sd) in ref.items():
+        j = names.index(nm)
+        assert abs(summ[j, 0] - mean) < 3 * np.hypot(mcse_ref, summ[j, 3]) + 0.02 * sd, (nm, summ[j, 0], mean)
+    # pop_mean and p[i] are Logical columns in (0, 1): link(c) would take their logit, which the streaming moments do not carry
+    # (raw and log scale only) — the untransformed PSRF is used here, the transformed one needs stored samples
+    assert (eng.gelman(0.05, False)[:, 0] < 1.05).all()
 
 
 def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):

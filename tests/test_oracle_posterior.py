@@ -69,6 +69,18 @@ def test_line_mala_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_surgical_reference_scheme(oracle):
+    # doc/examples/surgical.jl:54-60 (NUTS(b) + Slice([mu, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/surgical.rst
+    ref = {"mu": (-2.550263247, 0.00352027397), "pop_mean": (0.073062651, 0.00022880854), "s2": (0.183080212, 0.00629499754),
+           "p[1]": (0.053571675, 0.00059140521), "p[4]": (0.059863573, 0.00033190971), "p[8]": (0.122296440, 0.00086456417),
+           "p[12]": (0.068534503, 0.00015162331)}
+    tpl, blocks, inits = helpers.scheme("surgical_nuts_slice")
+    ob = [helpers.oracle_block(b) for b in blocks]; ob[0]["max_depth"] = 10
+    o = oracle.Oracle(tpl); o.set_scheme(ob)
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=4, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_pumps_gibbs_amwg_scheme(oracle):
     # BASELINE.json configs[4]: Gibbs(theta) + Gibbs(beta) + AMWG(alpha) targets the same posterior as the reference's Slice scheme
     ref = {"beta": (0.93036099, 0.01824153419), "alpha": (0.69679849, 0.00722593007), "theta[1]": (0.05991674, 0.00032725274),
