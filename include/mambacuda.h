@@ -81,7 +81,7 @@ enum { MCU_ADAPT_ALL = 0, MCU_ADAPT_BURNIN = 1, MCU_ADAPT_NONE = 2 }; /* amwg.jl
 enum { MCU_PROP_NORMAL = 0, MCU_PROP_SYMUNIFORM = 1, MCU_PROP_SYMTRIANGULAR = 2 }; /* rwm.jl:12-13, distributions/extensions.jl:43-53 */
 enum { MCU_GRAD_ANALYTIC = 0, MCU_GRAD_FORWARD = 1, MCU_GRAD_CENTRAL = 2 };       /* nuts.jl:47 dtype; simulation.jl:47-51 */
 enum { MCU_RNG_PHILOX = 0, MCU_RNG_EXTERNAL = 1 };
-enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1 };                                    /* src/output/mcse.jl:3-8 */
+enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1, MCU_ETYPE_IPSE = 2 };                                    /* src/output/mcse.jl:3-8 */
 
 /* mcu_run flags */
 #define MCU_RUN_NO_STORE 1u     /* do not keep thinned samples on the device, only streaming moments */
@@ -233,6 +233,16 @@ int mcu_chains_hpd(const double* value, int64_t n, int p, int64_t m, double alph
 int mcu_chains_autocor(const double* value, int64_t n, int p, int64_t m, const int64_t* lags, int nlags, double* out);
 int mcu_chains_changerate(const double* value, int64_t n, int p, int64_t m, double* out);
 int mcu_chains_gelman(const double* value, int64_t n, int p, int64_t m, double alpha, const int* codes, int mpsrf, double* out);
+/* Per-series convergence diagnostics, one row per (parameter, chain); out [p × K × m] column-major, NOT rounded; etype: MCU_ETYPE_*
+ * (batch_size only for MCU_ETYPE_BM).  Return MCU_ERR_ARG where the reference throws (window fractions, too few iterations for mcse_bm).
+ *   mcu_chains_geweke   gewekediag(c; first, last, etype)        src/output/gewekediag.jl:3-31   K = 2: Z-score, p-value
+ *   mcu_chains_heidel   heideldiag(c; alpha, eps, etype)          src/output/heideldiag.jl:3-41   K = 6: burn-in, stationarity, p-value, mean, halfwidth, test
+ *                       (start = first(c.range), heideldiag.jl:33)
+ *   mcu_chains_raftery  rafterydiag(c; q, r, s, eps)              src/output/rafterydiag.jl:3-61  K = 5: thinning, burn-in, total, nmin, dependence factor
+ *                       (range_start, range_step = first(c.range), step(c.range))                                                         */
+int mcu_chains_geweke(const double* value, int64_t n, int p, int64_t m, double first, double last, int etype, int batch_size, double* out);
+int mcu_chains_heidel(const double* value, int64_t n, int p, int64_t m, double alpha, double eps, int etype, int batch_size, int64_t start, double* out);
+int mcu_chains_raftery(const double* value, int64_t n, int p, int64_t m, double q, double r, double s, double eps, int64_t range_start, int64_t range_step, double* out);
 
 /* ---- RNG contract ----------------------------------------------------- */
 /* PHILOX: Philox4x32-10, key = seed, counter = (k >> 1, iteration, global chain, block | kind << 16 | stream << 24).

@@ -1040,6 +1040,22 @@ int mcu_chains_gelman(const double* value, int64_t n, int p, int64_t m, double a
   return hostdiag::chains_gelman(value, n, p, m, alpha, codes, mpsrf != 0, out) ? MCU_ERR_ARG : MCU_OK;   // "less than 2 chains": gelmandiag.jl:6-7
 }
 
+int mcu_chains_geweke(const double* value, int64_t n, int p, int64_t m, double first, double last, int etype, int batch_size, double* out) {
+  if (!value || !out || n < 4 || p < 1 || m < 1 || etype < 0 || etype > 2) return MCU_ERR_ARG;
+  if (!(first > 0.0 && first < 1.0) || !(last > 0.0 && last < 1.0) || first + last > 1.0) return MCU_ERR_ARG;   // gewekediag.jl:5-11
+  if (batch_size < 1) batch_size = 100;
+  return hostdiag::chains_series(value, n, p, m, 2, out, [&](const double* x, double* r) { return hostdiag::geweke_vec(x, n, first, last, etype, batch_size, r); }) ? MCU_ERR_ARG : MCU_OK;
+}
+int mcu_chains_heidel(const double* value, int64_t n, int p, int64_t m, double alpha, double eps, int etype, int batch_size, int64_t start, double* out) {
+  if (!value || !out || n < 4 || p < 1 || m < 1 || etype < 0 || etype > 2 || !(alpha > 0.0 && alpha < 1.0)) return MCU_ERR_ARG;
+  if (batch_size < 1) batch_size = 100;
+  return hostdiag::chains_series(value, n, p, m, 6, out, [&](const double* x, double* r) { return hostdiag::heidel_vec(x, n, alpha, eps, etype, batch_size, start, r); }) ? MCU_ERR_ARG : MCU_OK;
+}
+int mcu_chains_raftery(const double* value, int64_t n, int p, int64_t m, double q, double r, double s, double eps, int64_t range_start, int64_t range_step, double* out) {
+  if (!value || !out || n < 3 || p < 1 || m < 1 || !(q > 0.0 && q < 1.0) || !(r > 0.0) || !(s > 0.0 && s < 1.0) || range_step < 1) return MCU_ERR_ARG;
+  return hostdiag::chains_series(value, n, p, m, 5, out, [&](const double* x, double* rr) { hostdiag::raftery_vec(x, n, q, r, s, eps, range_start, range_step, rr); return 0; }) ? MCU_ERR_ARG : MCU_OK;
+}
+
 double mcu_fp64_peak_tflops(mcu_handle h) {
   if (!h) return -1.0;
   if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;

@@ -162,9 +162,164 @@ inline int summarystats_soa(const double* smp, long long kept, int P, long long 
 }
 
 
+// element (iteration i, parameter j, chain k) of a ModelChains.value array [n x p x m], column-major
+inline double at(const double* v, long long n, int p, long long i, int j, long long k) { return v[(size_t)i + (size_t)n * ((size_t)j + (size_t)p * (size_t)k)]; }
+
+// ---- per-series pieces shared by the convergence diagnostics ------------------------------------------------------------
+// mcse(x, method): src/output/mcse.jl:3-46; etype 0 = :bm (batch size `batch`), 1 = :imse, 2 = :ipse.  Returns nonzero where the
+// reference throws ("iterations are < 2 * size ...").
+inline int mcse_vec(const double* x, size_t N, int etype, int batch, double* out) {
+  if (etype == 0) {
+    const size_t nb = N / (size_t)batch;
+    if (nb < 2) return 1;
+    std::vector<double> mbar(nb);
+    for (size_t q = 0; q < nb; ++q) mbar[q] = mean_v(x + q * batch, batch);
+    *out = sd_v(mbar.data(), nb) / std::sqrt((double)nb);
+    return 0;
+  }
+  const double mu = mean_v(x, N);
+  std::vector<double> z(N);
+  for (size_t i = 0; i < N; ++i) z[i] = x[i] - mu;
+  auto acov = [&](size_t lag) { double s = 0; for (size_t t = 0; t + lag < N; ++t) s += z[t] * z[t + lag]; return s / (double)N; };   // StatsBase.autocov
+  const double g0 = acov(0), g1 = acov(1);
+  const long long mm = ((long long)N - 2) / 2;
+  double value;
+  if (etype == 1) {          // initial monotone sequence estimator
+    double Ghat = g0 + g1;
+    value = -g0 + 2.0 * Ghat;
+    for (long long i = 1; i <= mm; ++i) {
+      Ghat = std::fmin(Ghat, acov(2 * i) + acov(2 * i + 1));
+      if (!(Ghat > 0)) break;
+      value += 2.0 * Ghat;
+    }
+  } else {                   // initial positive sequence estimator
+    value = g0 + 2.0 * g1;
+    for (long long i = 1; i <= mm; ++i) {
+      const double Ghat = acov(2 * i) + acov(2 * i + 1);
+      if (!(Ghat > 0)) break;
+      value += 2.0 * Ghat;
+    }
+  }
+  *out = std::sqrt(value / (double)N);
+  return 0;
+}
+inline double erfinv_d(double y) {   // inverse error function: Newton on erf from a logarithmic starting value
+  if (!(y > -1.0 && y < 1.0)) return y == 1.0 ? INFINITY : y == -1.0 ? -INFINITY : NAN;
+  const double a = 0.147, ln = std::log(1.0 - y * y), t = 2.0 / (M_PI * a) + 0.5 * ln;
+  double x = (y < 0 ? -1.0 : 1.0) * std::sqrt(std::sqrt(t * t - ln / a) - t);
+  for (int it = 0; it < 4; ++it) x -= (std::erf(x) - y) / (2.0 / std::sqrt(M_PI) * std::exp(-x * x));
+  return x;
+}
+// CDF of the Cramer-von Mises statistic, 4-term series: src/utils.jl:73-81
+inline double pcramer(double q) {
+  double p = 0.0;
+  const double fact[4] = {1.0, 1.0, 2.0, 6.0};
+  for (int k = 0; k < 4; ++k) {
+    const double c1 = 4.0 * k + 1.0, c2 = c1 * c1 / (16.0 * q);
+    p += std::tgamma(k + 0.5) / fact[k] * std::sqrt(c1) * std::exp(-c2) * std::cyl_bessel_k(0.25, c2);
+  }
+  return p / (std::pow(M_PI, 1.5) * std::sqrt(q));
+}
+inline long long jround(double v) { return (long long)std::llround(v); }   // Julia 0.5 round(Int, x): ties away from zero
+// gewekediag(x; first, last, etype): src/output/gewekediag.jl:3-19 → (z, p), NOT rounded
+inline int geweke_vec(const double* x, long long n, double first, double last, int etype, int batch, double* out) {
+  const long long n1 = jround(first * (double)n), s2 = jround((double)n - last * (double)n + 1.0);   // x[1:n1], x[s2:n]
+  if (n1 < 1 || s2 < 1 || s2 > n) return 1;
+  double m1, m2;
+  if (mcse_vec(x, (size_t)n1, etype, batch, &m1) || mcse_vec(x + (s2 - 1), (size_t)(n - s2 + 1), etype, batch, &m2)) return 1;
+  const double z = (mean_v(x, (size_t)n1) - mean_v(x + (s2 - 1), (size_t)(n - s2 + 1))) / std::sqrt(m1 * m1 + m2 * m2);
+  out[0] = z; out[1] = 1.0 - std::erf(std::fabs(z) / std::sqrt(2.0));
+  return 0;
+}
+// heideldiag(x; alpha, eps, etype, start): src/output/heideldiag.jl:3-27 → (burn-in, stationarity, p-value, mean, halfwidth, test)
+inline int heidel_vec(const double* x, long long n, double alpha, double eps, int etype, int batch, long long start, double* out) {
+  const long long delta = (long long)(0.10 * (double)n);
+  const long long h0 = (long long)((double)n / 2.0);              // y = x[trunc(Int, n / 2):end]
+  if (h0 < 1) return 1;
+  double mc;
+  if (mcse_vec(x + (h0 - 1), (size_t)(n - h0 + 1), etype, batch, &mc)) return 1;
+  const double S0 = (double)(n - h0 + 1) * mc * mc;
+  long long i = 1; double pvalue = 1.0, ybar = NAN; bool converged = false;
+  long long ylen = n - h0 + 1, yoff = h0 - 1;                      // the series the halfwidth is computed on (last y of the loop)
+  while ((double)i < (double)n / 2.0) {
+    const double* y = x + (i - 1); const long long m = n - i + 1;
+    yoff = i - 1; ylen = m;
+    ybar = mean_v(y, (size_t)m);
+    double cs = 0.0, I = 0.0;
+    for (long long t = 0; t < m; ++t) { cs += y[t]; const double B = cs - ybar * (double)(t + 1); I += B * B / ((double)m * S0); }
+    I /= (double)m;
+    pvalue = 1.0 - pcramer(I);
+    converged = pvalue > alpha;
+    if (converged || delta < 1) break;
+    i += delta;
+  }
+  if (mcse_vec(x + yoff, (size_t)ylen, etype, batch, &mc)) return 1;
+  const double halfwidth = std::sqrt(2.0) * erfinv_d(1.0 - alpha) * mc;
+  out[0] = (double)(i + start - 2); out[1] = converged ? 1.0 : 0.0; out[2] = pvalue; out[3] = ybar; out[4] = halfwidth;
+  out[5] = (halfwidth / std::fabs(ybar) <= eps) ? 1.0 : 0.0;
+  return 0;
+}
+// rafterydiag(x; q, r, s, eps, range): src/output/rafterydiag.jl:3-46 → (thinning, burn-in, total, nmin, dependence factor)
+inline void raftery_vec(const double* x, long long nx, double q, double r, double s, double eps, long long rstart, long long rstep, double* out) {
+  const double phi = std::sqrt(2.0) * erfinv_d(s);
+  const double nmin = std::ceil(q * (1.0 - q) * (phi / r) * (phi / r));
+  out[3] = nmin;
+  if (nmin > (double)nx) { out[0] = out[1] = out[2] = out[4] = NAN; return; }
+  std::vector<double> srt(x, x + nx);
+  std::sort(srt.begin(), srt.end());
+  const double h = (double)(nx - 1) * q; const size_t lo = (size_t)std::floor(h), hi = lo + 1 < (size_t)nx ? lo + 1 : lo;
+  const double cut = srt[lo] + (h - (double)lo) * (srt[hi] - srt[lo]);
+  std::vector<int> dich((size_t)nx);
+  for (long long i = 0; i < nx; ++i) dich[i] = x[i] <= cut ? 1 : 0;
+  long long kthin = 0; double bic = 1.0;
+  std::vector<int> test;
+  while (bic >= 0.0) {
+    ++kthin;
+    test.clear();
+    for (long long i = 0; i < nx; i += kthin) test.push_back(dich[i]);
+    const long long nt = (long long)test.size();
+    if (nt < 3) break;
+    double tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = 0; i + 2 < nt; ++i) tr[test[i] + 2 * test[i + 1] + 4 * test[i + 2]] += 1.0;   // reshape(counts, 2, 2, 2): [i1, i2, i3]
+    double g2 = 0.0;
+    for (int i1 = 0; i1 < 2; ++i1) for (int i2 = 0; i2 < 2; ++i2) for (int i3 = 0; i3 < 2; ++i3) {
+      const double tt = tr[i1 + 2 * i2 + 4 * i3];
+      if (tt > 0) {
+        const double a = tr[0 + 2 * i2 + 4 * i3] + tr[1 + 2 * i2 + 4 * i3];
+        const double b = tr[i1 + 2 * i2] + tr[i1 + 2 * i2 + 4];
+        const double c = tr[2 * i2] + tr[1 + 2 * i2] + tr[2 * i2 + 4] + tr[1 + 2 * i2 + 4];
+        g2 += 2.0 * tt * std::log(tt / (a * b / c));
+      }
+    }
+    bic = g2 - 2.0 * std::log((double)nt - 2.0);
+  }
+  const long long nt = (long long)test.size();
+  double tf[4] = {0, 0, 0, 0};
+  for (long long i = 0; i + 1 < nt; ++i) tf[test[i] + 2 * test[i + 1]] += 1.0;
+  const double alpha = tf[2] / (tf[0] + tf[2]), beta = tf[1] / (tf[1] + tf[3]);
+  const double kt = (double)(kthin * rstep);
+  const double m = std::log(eps * (alpha + beta) / std::fmax(alpha, beta)) / std::log(std::fabs(1.0 - alpha - beta));
+  const double burnin = kt * std::ceil(m) + (double)rstart - 1.0;
+  const double nn = ((2.0 - alpha - beta) * alpha * beta * phi * phi) / (r * r * std::pow(alpha + beta, 3.0));
+  const double total = burnin + kt * std::ceil(nn);
+  out[0] = kt; out[1] = burnin; out[2] = total; out[4] = total / nmin;
+}
+// the three diagnostics over every (parameter, chain) series of a ModelChains.value; out [p x K x m] column-major (K = 2, 6, 5)
+template <class F>
+inline int chains_series(const double* v, long long n, int p, long long m, int K, double* out, F f) {
+  std::vector<double> x((size_t)n);
+  for (long long k = 0; k < m; ++k)
+    for (int j = 0; j < p; ++j) {
+      for (long long i = 0; i < n; ++i) x[i] = at(v, n, p, i, j, k);
+      double r[8];
+      if (f(x.data(), r)) return 1;
+      for (int c = 0; c < K; ++c) out[(size_t)j + (size_t)p * ((size_t)c + (size_t)K * (size_t)k)] = r[c];
+    }
+  return 0;
+}
+
 // ---- post-processing of a materialised chain array (ModelChains.value: [n iterations x p parameters x m chains], column-major,
 //      iteration fastest) — src/output/stats.jl:3-83 and the multivariate PSRF of src/output/gelmandiag.jl:49-55 -----------------
-inline double at(const double* v, long long n, int p, long long i, int j, long long k) { return v[(size_t)i + (size_t)n * ((size_t)j + (size_t)p * (size_t)k)]; }
 
 // quantile(c; q): stats.jl:74-83 — Julia's quantile(vec(x), q) (linear interpolation between order statistics, "type 7")
 inline void chains_quantile(const double* v, long long n, int p, long long m, const double* q, int nq, double* out) {

@@ -48,6 +48,7 @@ SYMBOLS = [
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
     "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
+    "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery",
 ]
 
 
@@ -101,5 +102,8 @@ def lib():
     L.mcu_chains_autocor.argtypes = [dp, i64, C.c_int, i64, C.POINTER(i64), C.c_int, dp]
     L.mcu_chains_changerate.argtypes = [dp, i64, C.c_int, i64, dp]
     L.mcu_chains_gelman.argtypes = [dp, i64, C.c_int, i64, C.c_double, ip, C.c_int, dp]
+    L.mcu_chains_geweke.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp]
+    L.mcu_chains_heidel.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_int, i64, dp]
+    L.mcu_chains_raftery.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_double, C.c_double, i64, i64, dp]
     _lib = L
     return L

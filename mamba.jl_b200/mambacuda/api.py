@@ -382,6 +382,48 @@ def changerate(c):
     return np.round(out, 3), c.names + ["Multivariate"], ["Change Rate"]
 
 
+_ETYPE = {"bm": 0, "imse": 1, "ipse": 2}
+
+
+def gewekediag(c, first=0.1, last=0.5, etype="imse", size=100):
+    """gewekediag(c; first, last, etype): src/output/gewekediag.jl:3-31 → [p × 2 × chains] (Z-score rounded to 3 dp, p-value to 4)."""
+    if not 0.0 < first < 1.0:
+        raise ArgumentError("first is not in (0, 1)")
+    if not 0.0 < last < 1.0:
+        raise ArgumentError("last is not in (0, 1)")
+    if first + last > 1.0:
+        raise ArgumentError("first and last proportions overlap")
+    if etype not in _ETYPE:
+        raise ArgumentError(f"unsupported mcse method {etype}")
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, 2, m), order="F")
+    if _lib.lib().mcu_chains_geweke(_dp(v), n, p, m, float(first), float(last), _ETYPE[etype], int(size), _dp(out)) != 0:
+        raise ArgumentError(f"iterations are < {2 * size} and batch size is > {n // 2}")
+    out[:, 0, :] = np.round(out[:, 0, :], 3); out[:, 1, :] = np.round(out[:, 1, :], 4)
+    return out, c.names, ["Z-score", "p-value"]
+
+
+def heideldiag(c, alpha=0.05, eps=0.1, etype="imse", size=100):
+    """heideldiag(c; alpha, eps, etype): src/output/heideldiag.jl:3-41 → [p × 6 × chains]."""
+    if etype not in _ETYPE:
+        raise ArgumentError(f"unsupported mcse method {etype}")
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, 6, m), order="F")
+    if _lib.lib().mcu_chains_heidel(_dp(v), n, p, m, float(alpha), float(eps), _ETYPE[etype], int(size), int(c.first), _dp(out)) != 0:
+        raise ArgumentError(f"iterations are < {2 * size} and batch size is > {n // 2}")
+    out[:, 2, :] = np.round(out[:, 2, :], 4)
+    return out, c.names, ["Burn-in", "Stationarity", "p-value", "Mean", "Halfwidth", "Test"]
+
+
+def rafterydiag(c, q=0.025, r=0.005, s=0.95, eps=0.001):
+    """rafterydiag(c; q, r, s, eps): src/output/rafterydiag.jl:3-61 → [p × 5 × chains]."""
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, 5, m), order="F")
+    if _lib.lib().mcu_chains_raftery(_dp(v), n, p, m, float(q), float(r), float(s), float(eps), int(c.first), int(c.step), _dp(out)) != 0:
+        raise ArgumentError("q and s must be in (0, 1), r positive")
+    return out, c.names, ["Thinning", "Burn-in", "Total", "Nmin", "Dependence Factor"]
+
+
 def describe(c, q=(0.025, 0.25, 0.5, 0.75, 0.975), etype="bm"):
     """describe(c): src/output/stats.jl:41-52 — summarystats + quantiles."""
     return summarystats(c, etype=etype), quantile(c, q=q)

@@ -329,3 +329,122 @@ def test_abi_chain_postprocessing_matches_numpy(mcu_built, gold_diag):
     assert g2[p, 0] == pytest.approx(_np_mpsrf(cl), rel=1e-9)
     with pytest.raises(api.ArgumentError):
         api._chains_gelman(c[:, :, :1], 0.05, None, False)          # less than 2 chains
+
+
+# ------------------------------------------------------------------------- geweke / heidel / raftery behind the C ABI (CPU)
+def _np_mcse_imse(x):
+    n = x.size; z = x - x.mean()
+    ac = lambda k: float((z[:n - k] * z[k:]).sum() / n)
+    Ghat = ac(0) + ac(1); value = -ac(0) + 2 * Ghat
+    for i in range(1, (n - 2) // 2 + 1):
+        Ghat = min(Ghat, ac(2 * i) + ac(2 * i + 1))
+        if not Ghat > 0:
+            break
+        value += 2 * Ghat
+    return np.sqrt(value / n)
+
+
+def _np_geweke(x, first=0.1, last=0.5):
+    from scipy.special import erf
+    n = x.size
+    rnd = lambda v: int(np.floor(v + 0.5))
+    x1 = x[:rnd(first * n)]; x2 = x[rnd(n - last * n + 1) - 1:]
+    z = (x1.mean() - x2.mean()) / np.sqrt(_np_mcse_imse(x1) ** 2 + _np_mcse_imse(x2) ** 2)
+    return z, 1 - erf(abs(z) / np.sqrt(2))
+
+
+def _np_pcramer(q):
+    from scipy.special import kv, gamma
+    from math import factorial
+    p = 0.0
+    for k in range(4):
+        c1 = 4.0 * k + 1.0; c2 = c1 ** 2 / (16.0 * q)
+        p += gamma(k + 0.5) / factorial(k) * np.sqrt(c1) * np.exp(-c2) * kv(0.25, c2)
+    return p / (np.pi ** 1.5 * np.sqrt(q))
+
+
+def _np_heidel(x, alpha=0.05, eps=0.1, start=1):
+    from scipy.special import erfinv
+    n = x.size; delta = int(0.10 * n)
+    y = x[int(n / 2) - 1:]
+    S0 = y.size * _np_mcse_imse(y) ** 2
+    i, pvalue, converged, ybar = 1, 1.0, False, np.nan
+    while i < n / 2:
+        y = x[i - 1:]; m = y.size; ybar = y.mean()
+        B = np.cumsum(y) - ybar * np.arange(1, m + 1)
+        I = ((B * B) / (m * S0)).sum() / m
+        pvalue = 1 - _np_pcramer(I); converged = pvalue > alpha
+        if converged:
+            break
+        i += delta
+    hw = np.sqrt(2) * erfinv(1 - alpha) * _np_mcse_imse(y)
+    return [i + start - 2, float(converged), pvalue, ybar, hw, float(hw / abs(ybar) <= eps)]
+
+
+def _np_raftery(x, q=0.025, r=0.005, s=0.95, eps=0.001, start=1, step=1):
+    from scipy.special import erfinv
+    nx = x.size; phi = np.sqrt(2) * erfinv(s)
+    nmin = int(np.ceil(q * (1 - q) * (phi / r) ** 2))
+    if nmin > nx:
+        return [np.nan, np.nan, np.nan, nmin, np.nan]
+    dichot = (x <= np.quantile(x, q)).astype(int)
+    kthin, bic = 0, 1.0
+    while bic >= 0:
+        kthin += 1
+        test = dichot[::kthin]; nt = test.size
+        temp = test[:nt - 2] + 2 * test[1:nt - 1] + 4 * test[2:]
+        tr = np.bincount(temp, minlength=8).reshape(2, 2, 2, order="F").astype(float)
+        g2 = 0.0
+        for i1 in range(2):
+            for i2 in range(2):
+                for i3 in range(2):
+                    tt = tr[i1, i2, i3]
+                    if tt > 0:
+                        fitted = tr[:, i2, i3].sum() * tr[i1, i2, :].sum() / tr[:, i2, :].sum()
+                        g2 += 2 * tt * np.log(tt / fitted)
+        bic = g2 - 2 * np.log(nt - 2.0)
+    tf = np.bincount(test[:nt - 1] + 2 * test[1:], minlength=4).astype(float)
+    al = tf[2] / (tf[0] + tf[2]); be = tf[1] / (tf[1] + tf[3])
+    kt = kthin * step
+    m = np.log(eps * (al + be) / max(al, be)) / np.log(abs(1 - al - be))
+    burnin = kt * np.ceil(m) + start - 1
+    nn = ((2 - al - be) * al * be * phi ** 2) / (r ** 2 * (al + be) ** 3)
+    total = burnin + kt * np.ceil(nn)
+    return [kt, burnin, total, nmin, total / nmin]
+
+
+def test_abi_convergence_diagnostics_match_numpy(mcu_built, gold_diag):
+    # gewekediag / heideldiag / rafterydiag (src/output/{gewekediag,heideldiag,rafterydiag}.jl) through mcu_chains_geweke / _heidel /
+    # _raftery against numpy / scipy.special restatements (besselk, erfinv from scipy)
+    from mambacuda import api
+    c = np.array(gold_diag["chains"])
+    n, p, m = c.shape
+    ch = api.Chains(c, start=251, thin=2, names=["a", "b", "c"])
+    g, _, lab = api.gewekediag(ch)
+    assert lab == ["Z-score", "p-value"] and g.shape == (p, 2, m)
+    h, _, _ = api.heideldiag(ch)
+    for j in range(p):
+        for k in range(m):
+            z, pv = _np_geweke(c[:, j, k])
+            assert g[j, 0, k] == pytest.approx(round(z, 3), abs=1.1e-3) and g[j, 1, k] == pytest.approx(pv, abs=2e-4)
+            ref = _np_heidel(c[:, j, k], start=251)
+            np.testing.assert_allclose(h[j, [0, 1, 3, 4, 5], k], np.array(ref)[[0, 1, 3, 4, 5]], rtol=1e-9)
+            assert h[j, 2, k] == pytest.approx(ref[2], abs=1e-4)
+    with pytest.raises(api.ArgumentError, match="overlap"):
+        api.gewekediag(ch, first=0.6, last=0.5)
+    # raftery needs long chains (nmin = 3746 at the defaults): AR(1) series with thinning-dependent dichotomised dependence
+    rng = np.random.default_rng(5)
+    L = 6000
+    z = np.zeros((L, 2, 2))
+    e = rng.normal(size=(L, 2, 2))
+    for t in range(1, L):
+        z[t] = np.array([0.2, 0.85])[None, :, None] * z[t - 1] + e[t]
+    zc = api.Chains(z, start=1001, thin=3)
+    r, _, lab = api.rafterydiag(zc)
+    assert lab[0] == "Thinning" and r.shape == (2, 5, 2)
+    for j in range(2):
+        for k in range(2):
+            np.testing.assert_allclose(r[j, :, k], _np_raftery(z[:, j, k], start=1001, step=3), rtol=1e-9)
+    assert r[1, 0, 0] >= r[0, 0, 0]                       # the strongly autocorrelated column needs more thinning
+    short, _, _ = api.rafterydiag(api.Chains(z[:500]))     # fewer than nmin samples: NaN rows, nmin reported
+    assert np.isnan(short[0, 0, 0]) and short[0, 3, 0] == 3746
