@@ -132,8 +132,14 @@ static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t
   }
 }
 
+// MCU_GENERIC_MINB (set per template in tpl_*.cu): resident blocks per SM the register allocation aims for; undefined = ptxas' choice
+#ifdef MCU_GENERIC_MINB
+#define MCU_GENERIC_BOUNDS __launch_bounds__(128, MCU_GENERIC_MINB)
+#else
+#define MCU_GENERIC_BOUNDS __launch_bounds__(128)
+#endif
 template <class M>
-__global__ void __launch_bounds__(128) run_generic_kernel(typename M::Data data, RunArgs a) {
+__global__ void MCU_GENERIC_BOUNDS run_generic_kernel(typename M::Data data, RunArgs a) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_chains) return;
   const size_t C = (size_t)a.n_chains;

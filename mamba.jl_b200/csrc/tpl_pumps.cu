@@ -1,4 +1,7 @@
 // tpl_pumps.cu — instantiates the generic engine kernels for the `pumps` model template.
+// Resident blocks per SM the register allocation aims for (measured on B200, 128-thread blocks, profiles/r1_generic_kernel_occupancy.md):
+// small state records want full occupancy (latency hiding beats spills), large ones (rats) want registers.
+#define MCU_GENERIC_MINB 16
 #include "launch.hpp"
 namespace mcu {
 MCU_DEFINE_TPL(PumpsModel)
