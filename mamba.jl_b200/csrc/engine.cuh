@@ -132,14 +132,9 @@ static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t
   }
 }
 
-// MCU_GENERIC_MINB (set per template in tpl_*.cu): resident blocks per SM the register allocation aims for; undefined = ptxas' choice
-#ifdef MCU_GENERIC_MINB
-#define MCU_GENERIC_BOUNDS __launch_bounds__(128, MCU_GENERIC_MINB)
-#else
-#define MCU_GENERIC_BOUNDS __launch_bounds__(128)
-#endif
+// The body of the generic kernel; instantiated behind two __global__ wrappers with different launch bounds (below).
 template <class M>
-__global__ void MCU_GENERIC_BOUNDS run_generic_kernel(typename M::Data data, RunArgs a) {
+__device__ __forceinline__ void generic_kernel_body(const typename M::Data& data, const RunArgs& a) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_chains) return;
   const size_t C = (size_t)a.n_chains;
@@ -186,6 +181,16 @@ __global__ void MCU_GENERIC_BOUNDS run_generic_kernel(typename M::Data data, Run
   }
   for (int e = 0; e < a.D; ++e) a.state[(size_t)e * C + c] = s[e];
 }
+
+// Two instantiations per template: ptxas' own register choice (128) for chain counts that do not fill the device — the latency of a
+// single chain matters there and nothing spills — and the template's tuned MCU_GENERIC_MINB (tpl_*.cu: resident blocks per SM the
+// register allocation aims for) for large chain counts (profiles/r1_generic_kernel_occupancy.md).
+template <class M>
+__global__ void __launch_bounds__(128) run_generic_kernel(typename M::Data data, RunArgs a) { generic_kernel_body<M>(data, a); }
+#ifdef MCU_GENERIC_MINB
+template <class M>
+__global__ void __launch_bounds__(128, MCU_GENERIC_MINB) run_generic_kernel_dense(typename M::Data data, RunArgs a) { generic_kernel_body<M>(data, a); }
+#endif
 
 // Batched density entry points (mcu_logpdf / mcu_gradlogpdf): one evaluation per thread.
 // state [D][B] chain-fastest; x [k][B] or nullptr (use unlist of state); lp [B]; g [k][B] or nullptr.

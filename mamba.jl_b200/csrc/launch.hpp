@@ -1,27 +1,12 @@
 // launch.hpp — host-callable launch wrappers; each model template's kernels live in their own
 // translation unit (tpl_*.cu) so the library builds in parallel.
 #pragma once
-#include <cstdlib>
-
 #include "engine.cuh"
-
-#ifndef MCU_GENERIC_BLOCKS_PER_SM_DEFAULT
-#define MCU_GENERIC_BLOCKS_PER_SM_DEFAULT 0   // 0 = whatever registers allow (4 blocks of 128 threads)
-#endif
 
 namespace mcu {
 
 constexpr int kGlmDMax = 128;
 typedef GlmModel<kGlmDMax> GlmM;
-
-// The generic kernels are large (every sampler x every factor of a template inlined): with 4 warps per scheduler the L0 instruction
-// cache thrashes (ncu: stall_no_instruction 7.9 warps per issue on pumps).  Unused dynamic shared memory caps the resident blocks per SM.
-inline size_t generic_occupancy_smem() {
-  static int blocks = -1;
-  if (blocks < 0) { const char* e = std::getenv("MCU_GENERIC_BLOCKS_PER_SM"); blocks = e ? std::atoi(e) : MCU_GENERIC_BLOCKS_PER_SM_DEFAULT; }
-  if (blocks < 1 || blocks > 15) return 0;
-  return (size_t)(232448 / blocks) - 1024 - 1024 * (size_t)(blocks > 8);
-}
 
 #define MCU_DECLARE_TPL(M)                                                                                   \
   void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st);                                      \
@@ -34,11 +19,19 @@ MCU_DECLARE_TPL(PumpsModel)
 MCU_DECLARE_TPL(GlmM)
 MCU_DECLARE_TPL(SurgicalModel)
 
+// fewer chains than one wave at the default occupancy (148 SMs x 4 blocks x 128 threads): the low-latency instantiation
+#ifdef MCU_GENERIC_MINB
+#define MCU_LAUNCH_GENERIC(M)                                                                                \
+    const unsigned grid_ = (unsigned)((a.n_chains + 127) / 128);                                             \
+    if (a.n_chains >= 148LL * 4 * 128) run_generic_kernel_dense<M><<<grid_, 128, 0, st>>>(d, a);             \
+    else run_generic_kernel<M><<<grid_, 128, 0, st>>>(d, a);
+#else
+#define MCU_LAUNCH_GENERIC(M) run_generic_kernel<M><<<(unsigned)((a.n_chains + 127) / 128), 128, 0, st>>>(d, a);
+#endif
+
 #define MCU_DEFINE_TPL(M)                                                                                    \
   void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st) {                                     \
-    const size_t smem = generic_occupancy_smem();                                                            \
-    if (smem) cudaFuncSetAttribute(run_generic_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    run_generic_kernel<M><<<(unsigned)((a.n_chains + 127) / 128), 128, smem, st>>>(d, a);                    \
+    MCU_LAUNCH_GENERIC(M)                                                                                    \
   }                                                                                                          \
   void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
                      const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st) { \
