@@ -59,6 +59,7 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  bool rats_fast_ok = false;                                                // fused rats Slice + AMWG kernel (rats_fast.cu)
   bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
   std::vector<std::vector<double>> h_scales;                                // host mirror of every block's expanded scale
   void* d_diag = nullptr; size_t diag_cap = 0;     // persistent scratch of the diagnostics reductions (partials | folded sums | codes | centres)
@@ -316,6 +317,17 @@ bool scheme_is_seeds_fast(const mcu_ctx* h) {
   if ((int)h->inputs.at("r").size() != SeedsModel::NP) return false;
   for (const char* nm : {"x1", "x2"}) for (double v : h->inputs.at(nm)) if (v != 0.0 && v != 1.0) return false;   // 0/1 design → 4 group bases
   return true;
+}
+
+bool scheme_is_rats_fast(const mcu_ctx* h) {
+  // Slice(s2_c), AMWG(alpha), Slice([mu_alpha, s2_alpha]; univariate), AMWG(beta), Slice([mu_beta, s2_beta]; univariate): doc/examples/rats.jl:112-116
+  if (h->tpl != MCU_TPL_RATS || h->h_blocks.size() != 5) return false;
+  const DevBlock* b = h->h_blocks.data();
+  auto own1 = [&](int k, int n0) { return b[k].n_own == 1 && b[k].own[0] == n0; };
+  auto own2 = [&](int k, int n0, int n1) { return b[k].n_own == 2 && b[k].own[0] == n0 && b[k].own[1] == n1; };
+  return b[0].kind == MCU_SLICE_MULTI && b[0].transform == 0 && own1(0, 4) && b[1].kind == MCU_AMWG && own1(1, 5) &&
+         b[2].kind == MCU_SLICE_UNI && b[2].transform == 0 && own2(2, 0, 2) && b[3].kind == MCU_AMWG && own1(3, 6) &&
+         b[4].kind == MCU_SLICE_UNI && b[4].transform == 0 && own2(4, 1, 3);
 }
 
 bool scheme_is_rats_warp(const mcu_ctx* h) {
@@ -641,6 +653,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   h->h_scales = h_scales;
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
   h->rats_warp_ok = scheme_is_rats_warp(h);
+  h->rats_fast_ok = scheme_is_rats_fast(h);
   return MCU_OK;
 }
 
@@ -729,7 +742,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     CK(cudaMalloc(&h->r_scratch, rats_warp_scratch_bytes(g)));
     h->r_grid = g;
   }
-  if (fast || rats_warp) chunk = iters;   // the fused kernels keep everything on chip for the whole call
+  bool rats_fast = h->rats_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  if (fast || rats_warp || rats_fast) chunk = iters;   // the fused kernels keep everything on chip for the whole call
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   if (glm_tick) {
@@ -744,6 +758,11 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     if (fast) {
       rc = seeds_fast_launch(Host<SeedsModel>::data(h), a, h->h_blocks.data(), h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
+    } else if (rats_fast) {
+      rc = rats_fast_launch(h->inputs["y"].data(), h->inputs["Xm"].data(), h->inputs["rat"].data(), (int)h->inputs["y"].size(),
+                            h->inputs["xbar"][0], a, h->h_blocks.data(), h->h_scales, h->stream);
+      if (rc == -2) { rats_fast = false; chunk = 256; continue; }   // data are not 5 observations per rat: the generic kernel takes over
+      if (rc) return fail(h, MCU_ERR_CUDA, "rats_fast launch failed");
     } else if (rats_warp) {
       rc = rats_warp_launch(h->inputs["y"].data(), h->inputs["Xm"].data(), h->inputs["rat"].data(), (int)h->inputs["y"].size(),
                             h->inputs["xbar"][0], a, h->h_blocks.data(), h->h_scales[1].data(), h->r_grid, h->r_scratch, h->stream);

@@ -1,6 +1,8 @@
 // launch.hpp — host-callable launch wrappers; each model template's kernels live in their own
 // translation unit (tpl_*.cu) so the library builds in parallel.
 #pragma once
+#include <vector>
+
 #include "engine.cuh"
 
 namespace mcu {
@@ -56,6 +58,10 @@ double measure_fp64_peak_tflops(cudaStream_t st);
 // fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success
 int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
 
+
+// fused rats kernel for the reference's Slice + AMWG scheme (rats_fast.cu); returns 0 on success, -2 if the data layout is not 30 x 5
+int rats_fast_launch(const double* y, const double* Xm, const double* rat, int N, double xbar, const RunArgs& a, const DevBlock* h_blocks,
+                     const std::vector<std::vector<double>>& h_scales, cudaStream_t st);
 
 // warp-per-chain rats kernel, NUTS + Slice (rats_warp.cu); launch returns 0 on success
 int rats_warp_grid(long long n_chains);

@@ -208,6 +208,38 @@ def test_nuts_fixed_stepsize_trajectories_match_oracle(oracle, name, iters):
     assert_same_run(g, o, rtol=1e-6, min_frac=0.75)
 
 
+# ---- fused rats Slice + AMWG kernel (mamba.jl_b200/csrc/rats_fast.cu) -------------------------------------
+def test_rats_fast_kernel_trajectories_match_oracle_and_generic(oracle):
+    g, o, eng, _ = run_pair(oracle, "rats_slice_amwg", 32, 200, 100, 2, force_generic=False)
+    assert_same_run(g, o, min_frac=0.9)
+    tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
+    eng2 = Engine_(tpl, 32, blocks, inits, seed=99)
+    out_gen = eng2.run(200, burnin=100, thin=2, force_generic=True)
+    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
+    assert ok.mean() >= 0.9
+
+
+def test_rats_fast_kernel_restart_and_posterior(oracle):
+    # mcmc(mc, iters) restart through the fused kernel, and the published table doc/examples/rats.rst:42-46
+    tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
+    e1 = Engine_(tpl, 16, blocks, inits, seed=3); full = e1.run(60, burnin=20, thin=2)
+    e2 = Engine_(tpl, 16, blocks, inits, seed=3); a = e2.run(24, burnin=20, thin=2); b = e2.run(36, burnin=20, thin=2)
+    np.testing.assert_allclose(np.concatenate([a, b], axis=0), full, rtol=1e-12)
+    from mambacuda.engine import Engine
+    eng = Engine(tpl, 512, seed=4); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(6000, burnin=3000, thin=1, store=False, out=False)
+    summ = eng.summary_streaming()
+    ref = np.array([6.1831, 106.626, 37.254]); ref_mcse = np.array([0.0018, 0.0527, 0.234]); ref_sd = np.array([0.108, 3.459, 6.027])
+    assert np.all(np.abs(summ[:, 0] - ref) < 3 * np.hypot(ref_mcse, summ[:, 3]) + 0.03 * ref_sd)
+    np.testing.assert_allclose(summ[:, 1], ref_sd, rtol=0.1)
+
+
+def Engine_(tpl, n, blocks, inits, seed):
+    from mambacuda.engine import Engine
+    e = Engine(tpl, n, seed=seed); e.set_scheme(blocks); e.set_inits(inits)
+    return e
+
+
 # ---- warp-per-chain rats kernel (mamba.jl_b200/csrc/rats_warp.cu) ------------------------------------------
 @pytest.mark.parametrize("iters,burnin,min_frac", [(16, 12, 0.9), (40, 0, 0.75)])
 def test_rats_warp_kernel_trajectories_match_oracle(oracle, iters, burnin, min_frac):
