@@ -248,7 +248,7 @@ def small_model_bench(args, rank, local_rank, world):
     if args.workload == "line":
         runs = [("line_amwg_slice", 3, 10000, 1000, 1)]
     elif args.workload == "rats":
-        runs = [("rats_nuts_slice", 65536, 2000, 1000, 5), ("rats_slice_amwg", 65536, 2000, 1000, 10)]
+        runs = [("rats_nuts_slice", 65536, 2000, 1000, 5), ("rats_slice_amwg", 65536, 2000, 1000, 5)]
     else:
         # BASELINE.json configs[4]: Gibbs + AMWG, chain sweep 10^3 .. 10^7 with on-device Gelman-Rubin; the reference's own Slice scheme beside it
         runs = [("pumps_gibbs_amwg", n, 2000, 1000, 10) for n in (10**3, 10**4, 10**5, 10**6, 10**7)] + [("pumps_slice", 10**6, 2000, 1000, 10)]
