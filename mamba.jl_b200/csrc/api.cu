@@ -307,10 +307,11 @@ int ensure_chain_buffers(mcu_ctx* h) {
 }
 
 bool scheme_is_seeds_fast(const mcu_ctx* h) {
-  // AMWG(alpha0..alpha12) , AMWG(b) , AMWG(s2) — SURVEY.md §8d config 2 scheme A
+  // AMWG(alpha0..alpha12) , AMWG(b) , AMWG(s2) — SURVEY.md §8d config 2 scheme A — or the reference's scheme B with AMM(alpha0..alpha12)
+  // as the first block (doc/examples/seeds.jl:69-71)
   if (h->tpl != MCU_TPL_SEEDS || h->h_blocks.size() != 3) return false;
   const DevBlock& a = h->h_blocks[0]; const DevBlock& b = h->h_blocks[1]; const DevBlock& c = h->h_blocks[2];
-  if (a.kind != MCU_AMWG || b.kind != MCU_AMWG || c.kind != MCU_AMWG) return false;
+  if ((a.kind != MCU_AMWG && a.kind != MCU_AMM) || b.kind != MCU_AMWG || c.kind != MCU_AMWG) return false;
   if (a.n_own != 4 || a.own[0] != 0 || a.own[1] != 1 || a.own[2] != 2 || a.own[3] != 3) return false;
   if (b.n_own != 1 || b.own[0] != 5) return false;
   if (c.n_own != 1 || c.own[0] != 4) return false;

@@ -73,6 +73,8 @@ struct FastCfg {
   int adapt[3], batchsize[3], tune_off[3];
   double target[3];
   double scale_a[4], scale_b[NPL], scale_s;
+  // block 0 = AMM(alpha0..alpha12) (doc/examples/seeds.jl:69): lower Cholesky factor of the initial Sigma (column-major), beta, scale
+  double amm_SL[16], amm_beta, amm_scale;
 };
 
 // r log p + (n - r) log(1 - p) with p = invlogit(eta), written as r eta - n softplus(eta)
@@ -108,7 +110,8 @@ MCU_D double pick(const Bases& g, unsigned grp) {   // warp-uniform select, keep
   return (grp & 2u) ? hi : lo;
 }
 
-template <int BS>
+// AMM0: block 0 is AMM(alpha0, alpha1, alpha2, alpha12) (the reference's scheme, doc/examples/seeds.jl:69-71) instead of AMWG
+template <int BS, bool AMM0>
 __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   double* sb = smem;                        // b[i]
@@ -134,10 +137,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   double x = log(s2);
   for (int i = 0; i < NPL; ++i) SB(i) = a.state[(size_t)(5 + i) * C + c];
   // tune: block 0 [m, adapt, sigma[4], accept[4]]; block 1 [m, adapt, sigma[21], accept[21]]; block 2 [m, adapt, sigma, accept]
-  double m0 = TUNE(0, 0), m1 = TUNE(1, 0), m2 = TUNE(2, 0);
-  bool ad0 = TUNE(0, 1) != 0.0, ad1 = TUNE(1, 1) != 0.0, ad2 = TUNE(2, 1) != 0.0;
-  double sg0 = TUNE(0, 2), sg1 = TUNE(0, 3), sg2 = TUNE(0, 4), sg3 = TUNE(0, 5);
-  int ac0 = (int)TUNE(0, 6), ac1 = (int)TUNE(0, 7), ac2 = (int)TUNE(0, 8), ac3 = (int)TUNE(0, 9);
+  // AMM tune record of block 0 (samplers.cuh): [adapt, m, Mv[4], Mvv[16], SigmaLm[16]] — it stays in the L2-resident tune array
+  double m0 = AMM0 ? 0.0 : TUNE(0, 0), m1 = TUNE(1, 0), m2 = TUNE(2, 0);
+  bool ad0 = AMM0 ? false : TUNE(0, 1) != 0.0, ad1 = TUNE(1, 1) != 0.0, ad2 = TUNE(2, 1) != 0.0;
+  double sg0 = AMM0 ? 0.0 : TUNE(0, 2), sg1 = AMM0 ? 0.0 : TUNE(0, 3), sg2 = AMM0 ? 0.0 : TUNE(0, 4), sg3 = AMM0 ? 0.0 : TUNE(0, 5);
+  int ac0 = AMM0 ? 0 : (int)TUNE(0, 6), ac1 = AMM0 ? 0 : (int)TUNE(0, 7), ac2 = AMM0 ? 0 : (int)TUNE(0, 8), ac3 = AMM0 ? 0 : (int)TUNE(0, 9);
   double sgs = TUNE(2, 2); int acs = (int)TUNE(2, 3);
 
   Bases g = group_bases(al0, al1, al2, al3);
@@ -154,9 +158,86 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       ac0 = ac1 = ac2 = ac3 = 0;
       for (int i = 0; i < NPL; ++i) { SSG(i) = cfg.scale_b[i]; SAC(i) = 0.0; }
       sgs = cfg.scale_s; acs = 0;
+      if (AMM0) for (int i = 0; i < 38; ++i) TUNE(0, i) = 0.0;   // AMMTune(x, Sigma): amm.jl:14-24
+    }
+    // ================================================================== block 0, AMM form (amm.jl:66-108; device generic form: samplers.cuh amm_sample)
+    if (AMM0) {
+      const bool adapt = cfg.adapt[0] == 1 ? iter <= a.burnin : cfg.adapt[0] == 0;
+      const bool was = TUNE(0, 0) != 0.0;
+      double v[4] = {al0, al1, al2, al3};
+      if (adapt && !was) {   // setadapt!: amm.jl:97-108
+        TUNE(0, 1) = 0.0;
+        for (int i = 0; i < 4; ++i) TUNE(0, 2 + i) = v[i];
+        for (int i = 0; i < 4; ++i) for (int cc = 0; cc < 4; ++cc) TUNE(0, 6 + i + cc * 4) = v[i] * v[cc];
+        for (int i = 0; i < 16; ++i) TUNE(0, 22 + i) = 0.0;
+      }
+      TUNE(0, 0) = adapt ? 1.0 : 0.0;
+      double m = TUNE(0, 1);
+      // x = SigmaL randn(4) [mixed with the adapted factor once m > 2n] + v: normals 0..3 (and 4..7) of the block, then one uniform
+      const Pair z01 = draw_normal_pair(a, chain, it32, 0, 0), z23 = draw_normal_pair(a, chain, it32, 0, 1);
+      const double z[4] = {z01.a, z01.b, z23.a, z23.b};
+      double xp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { double acc = 0.0; for (int cc = 0; cc <= i; ++cc) acc += cfg.amm_SL[i + cc * 4] * z[cc]; xp[i] = acc; }
+      if (m > 8.0) {
+        const Pair y01 = draw_normal_pair(a, chain, it32, 0, 2), y23 = draw_normal_pair(a, chain, it32, 0, 3);
+        const double z2[4] = {y01.a, y01.b, y23.a, y23.b};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double acc = 0.0; for (int cc = 0; cc < 4; ++cc) acc += TUNE(0, 22 + i + cc * 4) * z2[cc];
+          xp[i] = cfg.amm_beta * xp[i] + (1.0 - cfg.amm_beta) * acc;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xp[i] += v[i];
+      const double lu = log_uniform(draw_uniform_pair(a, chain, it32, 0, 0).a);
+      // logf(x) - logf(v): every plate of group q moves by dg[q]; e_i' = e_i exp(dg[grp_i]) (4 exps, 21 logs), priors Normal(0, 1000)
+      const Bases gn = group_bases(xp[0], xp[1], xp[2], xp[3]);
+      const double dg0 = gn.g0 - g.g0, dg1 = gn.g1 - g.g1, dg2 = gn.g2 - g.g2, dg3 = gn.g3 - g.g3;
+      const double E0 = fast_exp(dg0), E1 = fast_exp(dg1), E2 = fast_exp(dg2), E3 = fast_exp(dg3);
+      double delta = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) delta = fma(-0.5e-6, fma(xp[i], xp[i], -v[i] * v[i]), delta);
+      double dLa = 0.0, dLb = 0.0, dLc = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < NPL; i += 3) {   // 21 plates = 7 trips of three independent logs
+        const unsigned q0 = cfg.grp[i], q1 = cfg.grp[i + 1], q2 = cfg.grp[i + 2];
+        const double Ea = (q0 & 2u) ? ((q0 & 1u) ? E3 : E2) : ((q0 & 1u) ? E1 : E0), da_ = (q0 & 2u) ? ((q0 & 1u) ? dg3 : dg2) : ((q0 & 1u) ? dg1 : dg0);
+        const double Eb = (q1 & 2u) ? ((q1 & 1u) ? E3 : E2) : ((q1 & 1u) ? E1 : E0), db_ = (q1 & 2u) ? ((q1 & 1u) ? dg3 : dg2) : ((q1 & 1u) ? dg1 : dg0);
+        const double Ec = (q2 & 2u) ? ((q2 & 1u) ? E3 : E2) : ((q2 & 1u) ? E1 : E0), dc_ = (q2 & 2u) ? ((q2 & 1u) ? dg3 : dg2) : ((q2 & 1u) ? dg1 : dg0);
+        const double la = fast_log(fma(SE(i), Ea, 1.0)), lb = fast_log(fma(SE(i + 1), Eb, 1.0)), lc = fast_log(fma(SE(i + 2), Ec, 1.0));
+        SLN(i) = la; SLN(i + 1) = lb; SLN(i + 2) = lc;
+        dLa += fma(cfg.r[i], da_, -cfg.n[i] * (la - SLL(i)));
+        dLb += fma(cfg.r[i + 1], db_, -cfg.n[i + 1] * (lb - SLL(i + 1)));
+        dLc += fma(cfg.r[i + 2], dc_, -cfg.n[i + 2] * (lc - SLL(i + 2)));
+      }
+      delta += (dLa + dLb) + dLc;
+      if (lu < delta) {   // rand() < exp(logf(x) - logf(v)): amm.jl:80
+        al0 = xp[0]; al1 = xp[1]; al2 = xp[2]; al3 = xp[3];
+        v[0] = xp[0]; v[1] = xp[1]; v[2] = xp[2]; v[3] = xp[3];
+        g = gn;
+        for (int i = 0; i < NPL; ++i) {
+          const unsigned q = cfg.grp[i];
+          SLL(i) = SLN(i);
+          SE(i) = SE(i) * ((q & 2u) ? ((q & 1u) ? E3 : E2) : ((q & 1u) ? E1 : E0));
+        }
+      }
+      if (adapt) {   // running mean / second moment, Sigma = (scale^2 / n / p)(Mvv - Mv Mv'), pivoted Cholesky: amm.jl:83-91
+        m += 1.0; TUNE(0, 1) = m;
+        const double p = m / (m + 1.0);
+        double Sigma[16], PL[16], Mv[4];
+        for (int i = 0; i < 4; ++i) { Mv[i] = p * TUNE(0, 2 + i) + (1.0 - p) * v[i]; TUNE(0, 2 + i) = Mv[i]; }
+        const double c0 = cfg.amm_scale * cfg.amm_scale / 4.0 / p;
+        for (int i = 0; i < 4; ++i) for (int cc = 0; cc < 4; ++cc) {
+          const double mvv = p * TUNE(0, 6 + i + cc * 4) + (1.0 - p) * v[i] * v[cc];
+          TUNE(0, 6 + i + cc * 4) = mvv;
+          Sigma[i + cc * 4] = c0 * (mvv - Mv[i] * Mv[cc]);
+        }
+        if (pivoted_chol_PL(Sigma, 4, PL) == 4) for (int i = 0; i < 16; ++i) TUNE(0, 22 + i) = PL[i];
+      }
     }
     // ================================================================== block 0: AMWG(alpha0..alpha12)
-    {
+    if (!AMM0) {
       const bool adapt = cfg.adapt[0] == 1 ? iter <= a.burnin : cfg.adapt[0] == 0;
       if (adapt && !ad0) { ac0 = ac1 = ac2 = ac3 = 0; m0 = 0.0; }   // setadapt!: amwg.jl:88-96
       ad0 = adapt;
@@ -360,9 +441,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   a.state[0 * C + c] = al0; a.state[1 * C + c] = al1; a.state[2 * C + c] = al2; a.state[3 * C + c] = al3;
   a.state[4 * C + c] = s2;
   for (int i = 0; i < NPL; ++i) a.state[(size_t)(5 + i) * C + c] = SB(i);
-  TUNE(0, 0) = m0; TUNE(0, 1) = ad0 ? 1.0 : 0.0;
-  TUNE(0, 2) = sg0; TUNE(0, 3) = sg1; TUNE(0, 4) = sg2; TUNE(0, 5) = sg3;
-  TUNE(0, 6) = ac0; TUNE(0, 7) = ac1; TUNE(0, 8) = ac2; TUNE(0, 9) = ac3;
+  if (!AMM0) {
+    TUNE(0, 0) = m0; TUNE(0, 1) = ad0 ? 1.0 : 0.0;
+    TUNE(0, 2) = sg0; TUNE(0, 3) = sg1; TUNE(0, 4) = sg2; TUNE(0, 5) = sg3;
+    TUNE(0, 6) = ac0; TUNE(0, 7) = ac1; TUNE(0, 8) = ac2; TUNE(0, 9) = ac3;
+  }
   TUNE(1, 0) = m1; TUNE(1, 1) = ad1 ? 1.0 : 0.0;
   TUNE(2, 0) = m2; TUNE(2, 1) = ad2 ? 1.0 : 0.0; TUNE(2, 2) = sgs; TUNE(2, 3) = acs;
 #undef SB
@@ -374,12 +457,12 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #undef TUNE
 }
 
-template <int BS>
+template <int BS, bool AMM0>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)BS * 4 * NSL * sizeof(double);
-  if (cudaFuncSetAttribute(seeds_fast_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(seeds_fast_kernel<BS, AMM0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   const unsigned grid = (unsigned)((a.n_chains + BS - 1) / BS);
-  seeds_fast_kernel<BS><<<grid, BS, smem, st>>>(cfg, a);
+  seeds_fast_kernel<BS, AMM0><<<grid, BS, smem, st>>>(cfg, a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -397,7 +480,8 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
   if (cudaMemcpy(n, d.n, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   if (cudaMemcpy(x1, d.x1, sizeof(x1), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   if (cudaMemcpy(x2, d.x2, sizeof(x2), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(sa, h_blocks[0].scale, sizeof(sa), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (h_blocks[0].kind == 6) { for (double& v : sa) v = 0.0; }   // AMM: no per-component sigma
+  else if (cudaMemcpy(sa, h_blocks[0].scale, sizeof(sa), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   if (cudaMemcpy(sb, h_blocks[1].scale, sizeof(sb), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   if (cudaMemcpy(ss, h_blocks[2].scale, sizeof(ss), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   for (int j = 0; j < 4; ++j) { cfg.amask[j] = 0; cfg.gmask[j] = 0; cfg.scale_a[j] = sa[j]; }
@@ -427,7 +511,13 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
     cfg.target[b] = h_blocks[b].target;
   }
   // 96 threads x 3 blocks/SM = 288 resident chains/SM: 125,000 chains/GPU fit in 3 even rounds
-  return launch_bs<MCU_SEEDS_BS>(cfg, a, st);
+  const bool amm0 = h_blocks[0].kind == 6;   // MCU_AMM
+  if (amm0) {
+    if (cudaMemcpy(cfg.amm_SL, h_blocks[0].SigmaL, sizeof(cfg.amm_SL), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    cfg.amm_beta = h_blocks[0].beta; cfg.amm_scale = h_blocks[0].amm_scale;
+    return launch_bs<MCU_SEEDS_BS, true>(cfg, a, st);
+  }
+  return launch_bs<MCU_SEEDS_BS, false>(cfg, a, st);
 }
 
 }  // namespace mcu

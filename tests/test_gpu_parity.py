@@ -208,6 +208,21 @@ def test_nuts_fixed_stepsize_trajectories_match_oracle(oracle, name, iters):
     assert_same_run(g, o, rtol=1e-6, min_frac=0.75)
 
 
+def test_seeds_fast_kernel_with_amm_block_matches_oracle_and_generic(oracle):
+    # the reference's own seeds scheme (AMM + AMWG + AMWG, doc/examples/seeds.jl:69-71) through the fused kernel
+    g, o, eng, _ = run_pair(oracle, "seeds_amm", 32, 300, 150, 3, force_generic=False)
+    assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4)
+    tpl, blocks, inits = helpers.scheme("seeds_amm")
+    e2 = Engine_(tpl, 32, blocks, inits, seed=99)
+    out_gen = e2.run(300, burnin=150, thin=3, force_generic=True)
+    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
+    assert ok.mean() >= 0.9
+    # restart through the fused kernel
+    e3 = Engine_(tpl, 8, blocks, inits, seed=5); full = e3.run(90, burnin=30, thin=3)
+    e4 = Engine_(tpl, 8, blocks, inits, seed=5); a = e4.run(45, burnin=30, thin=3); b = e4.run(45, burnin=30, thin=3)
+    np.testing.assert_allclose(np.concatenate([a, b], axis=0), full, rtol=1e-12)
+
+
 # ---- fused rats Slice + AMWG kernel (mamba.jl_b200/csrc/rats_fast.cu) -------------------------------------
 def test_rats_fast_kernel_trajectories_match_oracle_and_generic(oracle):
     g, o, eng, _ = run_pair(oracle, "rats_slice_amwg", 32, 200, 100, 2, force_generic=False)
