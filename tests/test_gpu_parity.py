@@ -65,7 +65,7 @@ def test_logpdf_out_of_support_is_minus_inf(oracle):
     assert np.all(np.isneginf(eng2.logpdf(0, in2, x))) and np.all(np.isneginf(orc2.logpdf(0, in2, x)))
 
 
-@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg"])
+@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice"])
 def test_gradient_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
