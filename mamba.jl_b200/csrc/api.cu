@@ -59,6 +59,7 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  bool pumps_fast_ok = false;                                               // fused pumps Slice kernel (pumps_fast.cu)
   bool rats_fast_ok = false;                                                // fused rats Slice + AMWG kernel (rats_fast.cu)
   bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
   std::vector<std::vector<double>> h_scales;                                // host mirror of every block's expanded scale
@@ -318,6 +319,14 @@ bool scheme_is_seeds_fast(const mcu_ctx* h) {
   if ((int)h->inputs.at("r").size() != SeedsModel::NP) return false;
   for (const char* nm : {"x1", "x2"}) for (double v : h->inputs.at(nm)) if (v != 0.0 && v != 1.0) return false;   // 0/1 design → 4 group bases
   return true;
+}
+
+bool scheme_is_pumps_fast(const mcu_ctx* h) {
+  // Slice([alpha, beta], 1.0, Univariate), Slice(theta, 1.0, Univariate) on the constrained scale: doc/examples/pumps.jl:52-53
+  if (h->tpl != MCU_TPL_PUMPS || h->h_blocks.size() != 2) return false;
+  const DevBlock& a = h->h_blocks[0]; const DevBlock& b = h->h_blocks[1];
+  return a.kind == MCU_SLICE_UNI && a.transform == 0 && a.n_own == 2 && a.own[0] == 0 && a.own[1] == 1 &&
+         b.kind == MCU_SLICE_UNI && b.transform == 0 && b.n_own == 1 && b.own[0] == 2;
 }
 
 bool scheme_is_rats_fast(const mcu_ctx* h) {
@@ -655,6 +664,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
   h->rats_warp_ok = scheme_is_rats_warp(h);
   h->rats_fast_ok = scheme_is_rats_fast(h);
+  h->pumps_fast_ok = scheme_is_pumps_fast(h);
   return MCU_OK;
 }
 
@@ -744,7 +754,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     h->r_grid = g;
   }
   bool rats_fast = h->rats_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
-  if (fast || rats_warp || rats_fast) chunk = iters;   // the fused kernels keep everything on chip for the whole call
+  const bool pumps_fast = h->pumps_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  if (fast || rats_warp || rats_fast || pumps_fast) chunk = iters;   // the fused kernels keep everything on chip for the whole call
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   if (glm_tick) {
@@ -759,6 +770,9 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     if (fast) {
       rc = seeds_fast_launch(Host<SeedsModel>::data(h), a, h->h_blocks.data(), h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
+    } else if (pumps_fast) {
+      rc = pumps_fast_launch(h->inputs["y"].data(), h->inputs["t"].data(), (int)h->inputs["y"].size(), a, h->h_scales, h->stream);
+      if (rc) return fail(h, MCU_ERR_CUDA, "pumps_fast launch failed");
     } else if (rats_fast) {
       rc = rats_fast_launch(h->inputs["y"].data(), h->inputs["Xm"].data(), h->inputs["rat"].data(), (int)h->inputs["y"].size(),
                             h->inputs["xbar"][0], a, h->h_blocks.data(), h->h_scales, h->stream);

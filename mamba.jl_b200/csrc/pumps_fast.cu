@@ -1,0 +1,152 @@
+// pumps_fast.cu — fused kernel for the reference's own sampling scheme of the `pumps` model (doc/examples/pumps.jl:52-53):
+//     [Slice([alpha, beta], 1.0, Univariate), Slice(theta, 1.0, Univariate)]          (constrained scale: slice.jl:47-50)
+// One chain per thread, every iteration of an mcu_run call inside ONE launch (as seeds_fast.cu / rats_fast.cu).
+//
+// What the reference does per shrinkage step: a full block-density evaluation (10 Gamma + 10 Poisson terms, src/model/simulation.jl:77-90).
+// What this kernel does:
+//   * block (alpha, beta): the ten Gamma(theta_i | alpha, 1/beta) terms enter through SL = sum log theta_i and ST = sum theta_i:
+//       logf(alpha, beta) = -alpha + (0.1 - 1) log beta - beta + 10 (alpha log beta - lgamma(alpha)) + (alpha - 1) SL - beta ST + const;
+//   * block theta: a move of theta_i changes two terms only,
+//       g_i(t) = (alpha - 1 + y_i) log t - t (beta + t_i)      (Gamma prior term + Poisson(y_i | t t_i) term, constants dropped),
+//     and the slice test logf(v') >= logf0 + log u is taken on the difference g_i(t') - g_i(t) + (running difference), so an evaluation is
+//     one log;
+//   * slice.jl:70-71 places ALL interval ends before any coordinate moves (lower = v - width .* rand(n)): with a counter-based stream
+//     draw i can be regenerated when component i is reached, so no per-thread arrays are needed.
+// Decisions are those of the reference on the same Philox stream up to rounding of the comparisons (tests/test_gpu_parity.py).
+#include "fastmath.cuh"
+
+namespace mcu {
+
+namespace {
+
+constexpr int NP = PumpsModel::NPUMP;   // 10 pumps
+
+struct PumpsFastCfg {
+  double y[NP], t[NP];
+  double w_ab[2], w_th[NP];
+};
+
+struct UStreamP {
+  const RunArgs& a; uint32_t chain, iter, block, k; Pair cur;
+  MCU_D double next() {
+    if (!(k & 1u)) cur = draw_uniform_pair(a, chain, iter, block, k >> 1);
+    const double u = (k & 1u) ? cur.b : cur.a;
+    ++k;
+    return u;
+  }
+  MCU_D double at(uint32_t idx) const {   // random access to draw idx of the block (does not move the cursor)
+    const Pair p = draw_uniform_pair(a, chain, iter, block, idx >> 1);
+    return (idx & 1u) ? p.b : p.a;
+  }
+};
+
+template <int BS>
+__global__ void __launch_bounds__(BS, 8) pumps_fast_kernel(const __grid_constant__ PumpsFastCfg cfg, const __grid_constant__ RunArgs a) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const long long c = (long long)blockIdx.x * BS + tid;
+  if (c >= a.n_chains) return;
+  const size_t C = (size_t)a.n_chains;
+  const uint32_t chain = (uint32_t)(a.chain_offset + c);
+#define TH(i) smem[(i) * BS + tid]
+  double al = a.state[0 * C + c], be = a.state[1 * C + c];
+  for (int i = 0; i < NP; ++i) TH(i) = a.state[(size_t)(2 + i) * C + c];
+
+  for (long long it = 1; it <= a.iters; ++it) {
+    const long long iter = a.iter0 + it;
+    const uint32_t it32 = (uint32_t)iter;
+    // ================================================================== block 0: Slice([alpha, beta], 1.0, Univariate)
+    {
+      double SL = 0.0, ST = 0.0;
+      for (int i = 0; i < NP; ++i) { const double th = TH(i); SL += fast_log(th); ST += th; }
+      // Exponential(1)(alpha) + Gamma(0.1, 1)(beta) + sum_i Gamma(alpha, 1/beta)(theta_i), -Inf outside the supports
+      // (src/model/simulation.jl:60-67: own priors first, early exit on a non-finite partial sum)
+      auto logf = [&](double va, double vb) {
+        if (!(va >= 0.0) || !(vb >= 0.0)) return -CUDART_INF;
+        const double lb = fast_log(vb);
+        return -va - 0.9 * lb - vb + (double)NP * (va * lb - lgamma(va)) + (va - 1.0) * SL - vb * ST;
+      };
+      UStreamP us{a, chain, it32, 0, 0, {0.0, 0.0}};
+      double logf0 = logf(al, be);
+      double lo0 = al - cfg.w_ab[0] * us.next(), lo1 = be - cfg.w_ab[1] * us.next();
+      double up0 = lo0 + cfg.w_ab[0], up1 = lo1 + cfg.w_ab[1];
+      {
+        const double p0 = logf0 + log_uniform(us.next());
+        const double x0 = al;
+        double cur = lo0 + (up0 - lo0) * us.next();
+        while (true) {
+          logf0 = logf(cur, be);
+          if (!(logf0 < p0)) break;
+          if (cur < x0) lo0 = cur; else up0 = cur;
+          cur = lo0 + (up0 - lo0) * us.next();
+        }
+        al = cur;
+      }
+      {
+        const double p0 = logf0 + log_uniform(us.next());
+        const double x0 = be;
+        double cur = lo1 + (up1 - lo1) * us.next();
+        while (true) {
+          logf0 = logf(al, cur);
+          if (!(logf0 < p0)) break;
+          if (cur < x0) lo1 = cur; else up1 = cur;
+          cur = lo1 + (up1 - lo1) * us.next();
+        }
+        be = cur;
+      }
+    }
+    // ================================================================== block 1: Slice(theta, 1.0, Univariate)
+    {
+      UStreamP us{a, chain, it32, 1, (uint32_t)NP, {0.0, 0.0}};   // draws 0 .. 9 place the intervals (regenerated below), the cursor starts at 10
+      double dcur = 0.0;   // logf(v) - logf(v at the start of the block): the slice levels are differences, the common part cancels
+#pragma unroll 1
+      for (int i = 0; i < NP; ++i) {
+        const double x0 = TH(i);
+        double lo = x0 - cfg.w_th[i] * us.at((uint32_t)i), up = lo + cfg.w_th[i];
+        const double ca = al - 1.0 + cfg.y[i], cb = be + cfg.t[i];
+        const double g0 = ca * fast_log(x0) - x0 * cb;                   // this component's two terms at its current value
+        const double base = dcur - g0;                                   // logf(v with theta_i = t) - logf(start) = base + g_i(t)
+        const double p0 = dcur + log_uniform(us.next());
+        double cur = lo + (up - lo) * us.next();
+        double lf;
+        while (true) {
+          lf = (cur >= 0.0) ? base + (ca * fast_log(cur) - cur * cb) : -CUDART_INF;   // Gamma / Poisson support: theta >= 0
+          if (cur == 0.0) lf = -CUDART_INF;
+          if (!(lf < p0)) break;
+          if (cur < x0) lo = cur; else up = cur;
+          cur = lo + (up - lo) * us.next();
+        }
+        TH(i) = cur; dcur = lf;
+      }
+    }
+    // ================================================================== thinning + streaming moments (mcmc.jl:76-78)
+    if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {
+      double mon[PumpsModel::P];
+      mon[0] = al; mon[1] = be;
+      for (int i = 0; i < NP; ++i) mon[2 + i] = TH(i);
+      if (a.samples) {
+        const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
+        for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
+      }
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
+    }
+  }
+  a.state[0 * C + c] = al; a.state[1 * C + c] = be;
+  for (int i = 0; i < NP; ++i) a.state[(size_t)(2 + i) * C + c] = TH(i);
+#undef TH
+}
+
+}  // namespace
+
+int pumps_fast_launch(const double* y, const double* t, int N, const RunArgs& a, const std::vector<std::vector<double>>& h_scales, cudaStream_t st) {
+  if (N != NP) return -2;
+  PumpsFastCfg cfg;
+  for (int i = 0; i < NP; ++i) { cfg.y[i] = y[i]; cfg.t[i] = t[i]; cfg.w_th[i] = h_scales[1][i]; }
+  cfg.w_ab[0] = h_scales[0][0]; cfg.w_ab[1] = h_scales[0][1];
+  constexpr int BS = 128;
+  const size_t smem = (size_t)BS * NP * sizeof(double);
+  pumps_fast_kernel<BS><<<(unsigned)((a.n_chains + BS - 1) / BS), BS, smem, st>>>(cfg, a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace mcu

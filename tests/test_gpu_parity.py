@@ -223,6 +223,23 @@ def test_seeds_fast_kernel_with_amm_block_matches_oracle_and_generic(oracle):
     np.testing.assert_allclose(np.concatenate([a, b], axis=0), full, rtol=1e-12)
 
 
+# ---- fused pumps Slice kernel (mamba.jl_b200/csrc/pumps_fast.cu) ---------------------------------------------
+def test_pumps_fast_kernel_matches_oracle_generic_and_published_table(oracle):
+    g, o, _, _ = run_pair(oracle, "pumps_slice", 32, 300, 100, 2, force_generic=False)
+    assert_same_run(g, o, min_frac=0.9)
+    tpl, blocks, inits = helpers.scheme("pumps_slice")
+    e2 = Engine_(tpl, 32, blocks, inits, seed=99)
+    out_gen = e2.run(300, burnin=100, thin=2, force_generic=True)
+    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
+    assert ok.mean() >= 0.9
+    from mambacuda.engine import Engine
+    eng = Engine(tpl, 2048, seed=8); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(3000, burnin=1500, thin=1, store=False, out=False)
+    summ = eng.summary_streaming()
+    ref = np.array([0.6968, 0.9304, 0.0599, 0.1013, 0.0891, 0.1153, 0.5997, 0.6097, 0.8677, 0.8545, 1.5572, 1.9848])   # doc/examples/pumps.rst:43-56
+    np.testing.assert_allclose(summ[:, 0], ref, rtol=0.05)
+
+
 # ---- fused rats Slice + AMWG kernel (mamba.jl_b200/csrc/rats_fast.cu) -------------------------------------
 def test_rats_fast_kernel_trajectories_match_oracle_and_generic(oracle):
     g, o, eng, _ = run_pair(oracle, "rats_slice_amwg", 32, 200, 100, 2, force_generic=False)
