@@ -442,6 +442,9 @@ def main():
                 "parallelism": f"chains sharded over {world} GPU(s), no data-path collective; all-reduce of 7p moment sums for PSRF",
                 "l2": "L2 flushed between steps (256 MiB fill); chain state is register/shared-memory resident inside a step",
                 "psrf_max": float(np.max(psrf[:, 0])) if psrf is not None else None,
+                "psrf_note": "SURVEY.md §8d config 2 runs 2,000 iterations from the reference's two dispersed initial records (s2 = 0.01 / 1): "
+                             "not yet mixed in s2 (the reference runs 12,500); the converged check against doc/examples/seeds.rst is "
+                             "tests/test_gpu_parity.py::test_seeds_fast_posterior_within_3_mcse_of_reference",
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": peak_fp64, "unit": "TFLOP/s",
