@@ -55,7 +55,8 @@ enum {
   MCU_TPL_PUMPS = 3,     /* doc/examples/pumps.jl:12-39    nodes: alpha, beta, theta[10]      */
   MCU_TPL_GLM_LOGIT = 4, /* synthetic GLM family (inputs X, y, family, sigma)  nodes: beta[d]  (no reference file; closest doc/examples/seeds.jl) */
   MCU_TPL_SURGICAL = 5,  /* doc/examples/surgical.jl:11-43 nodes: mu, s2, b[12]; monitored mu, pop_mean, s2, p[12] */
-  MCU_N_TEMPLATES = 6
+  MCU_TPL_DYES = 6,      /* doc/examples/dyes.jl:22-47     nodes: s2_between, theta, s2_within, mu[6] (all monitored) */
+  MCU_N_TEMPLATES = 7
 };
 
 /* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */

@@ -138,6 +138,13 @@ void default_inputs(mcu_ctx* h) {
       in["y"] = y; in["rat"] = rat; in["Xm"] = Xm; in["xbar"] = {22.0};
       break;
     }
+    case MCU_TPL_DYES: {  // doc/examples/dyes.jl:4-17
+      in["y"] = {1545, 1440, 1440, 1520, 1580, 1540, 1555, 1490, 1560, 1495, 1595, 1550, 1605, 1510, 1560,
+                 1445, 1440, 1595, 1465, 1545, 1595, 1630, 1515, 1635, 1625, 1520, 1455, 1450, 1480, 1445};
+      std::vector<double> batch(30); for (int k = 0; k < 30; ++k) batch[k] = k / 5;
+      in["batch"] = batch;
+      break;
+    }
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -165,6 +172,11 @@ int upload_inputs(mcu_ctx* h) {
     CK(cudaMemcpyAsync(p, kv.second.data(), kv.second.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->d_inputs[kv.first] = p;
   }
+  if (h->tpl == MCU_TPL_DYES) {
+    std::vector<int> bt; for (double r : in["batch"]) bt.push_back((int)r);
+    CK(cudaMalloc(&h->d_rat, bt.size() * sizeof(int)));
+    CK(cudaMemcpyAsync(h->d_rat, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
   if (h->tpl == MCU_TPL_RATS) {
     std::vector<int> rat; for (double r : in["rat"]) rat.push_back((int)r);
     CK(cudaMalloc(&h->d_rat, rat.size() * sizeof(int)));
@@ -186,6 +198,9 @@ template <> struct Host<SeedsModel> {
 template <> struct Host<RatsModel> {
   static RatsModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["Xm"], h->d_rat, (int)h->inputs["y"].size(), h->inputs["xbar"][0]}; }
 };
+template <> struct Host<DyesModel> {
+  static DyesModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_rat, (int)h->inputs["y"].size()}; }
+};
 template <> struct Host<SurgicalModel> {
   static SurgicalModel::Data data(mcu_ctx* h) { return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["lc"], (int)h->inputs["r"].size()}; }
 };
@@ -206,6 +221,7 @@ template <> struct Host<GlmM> {
     case MCU_TPL_PUMPS: { typedef PumpsModel M; BODY; break; }                     \
     case MCU_TPL_GLM_LOGIT: { typedef GlmM M; BODY; break; }                       \
     case MCU_TPL_SURGICAL: { typedef SurgicalModel M; BODY; break; }               \
+    case MCU_TPL_DYES: { typedef DyesModel M; BODY; break; }                       \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
 
@@ -224,6 +240,7 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_RATS: return tpl_info_fixed<RatsModel>();
     case MCU_TPL_PUMPS: return tpl_info_fixed<PumpsModel>();
     case MCU_TPL_SURGICAL: return tpl_info_fixed<SurgicalModel>();
+    case MCU_TPL_DYES: return tpl_info_fixed<DyesModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
       t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
@@ -245,6 +262,7 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_RATS: return RatsModel::monitor_names();
       case MCU_TPL_PUMPS: return PumpsModel::monitor_names();
       case MCU_TPL_SURGICAL: return SurgicalModel::monitor_names();
+      case MCU_TPL_DYES: return DyesModel::monitor_names();
       default: break;
     }
   }
@@ -541,6 +559,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_SEEDS && n != (size_t)SeedsModel::NP) return fail(h, MCU_ERR_DIM, "seeds inputs have 21 entries");
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
     if (h->tpl == MCU_TPL_SURGICAL && n != (size_t)SurgicalModel::NH) return fail(h, MCU_ERR_DIM, "surgical inputs have 12 entries");
+    if (h->tpl == MCU_TPL_DYES && n != 30) return fail(h, MCU_ERR_DIM, "dyes inputs have 30 entries");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
   }
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))

@@ -355,6 +355,46 @@ struct SurgicalModel {
   }
 };
 
+// =============================================================================== dyes
+// doc/examples/dyes.jl:22-47: y_k ~ MvNormal(mu[batch_k], sqrt(s2_within)) (30-dim iso), mu_i ~ Normal(theta, sqrt(s2_between)) (6 batches),
+// theta ~ Normal(0, 1000), s2_within, s2_between ~ InverseGamma(0.001, 0.001).  State / monitors (order of doc/examples/dyes.rst):
+// s2_between, theta, s2_within, mu[6].
+struct DyesModel {
+  static constexpr int D = 9, NN = 4, NF = 5, P = 9, NB = 6;
+  struct Data { const double* y; const int* batch; int N; };
+  MCU_HD static int node_off(int n) { return n; }
+  MCU_HD static int node_len(int n) { return n == 3 ? NB : 1; }
+  MCU_HD static int node_link(int n) { return (n == 0 || n == 2) ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 3 ? 0x3u /* s2_between, theta */ : f == 4 ? 0xCu /* s2_within, mu */ : 0u; }
+  MCU_HD static int mon_link(int j) { return (j == 0 || j == 2) ? LINK_LOG : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"s2_between", "theta", "s2_within", "mu"}; return nm[n]; }
+  static const char* state_names() { return "s2_between\ntheta\ns2_within\nmu[1]\nmu[2]\nmu[3]\nmu[4]\nmu[5]\nmu[6]"; }
+  static const char* monitor_names() { return state_names(); }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_invgamma(s[0], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 1) return lp_normal(s[1], 0.0, 1000.0);
+    if (f == 2) return lp_invgamma(s[2], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 3) { const double sg = sqrt(s[0]); double lp = 0.0; for (int i = 0; i < NB; ++i) lp += lp_normal(s[3 + i], s[1], sg); return lp; }
+    double sq = 0.0;
+    for (int k = 0; k < d.N; ++k) { const double e = d.y[k] - s[3 + d.batch[k]]; sq += e * e; }
+    return lp_isonormal(sq, (double)d.N, sqrt(s[2]));
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double s2b = s[0], th = s[1], s2w = s[2];
+    for (int i = 0; i < NB; ++i) g[3 + i] = 0.0;
+    double see = 0.0;
+    for (int k = 0; k < d.N; ++k) { const int i = d.batch[k]; const double e = d.y[k] - s[3 + i]; g[3 + i] += e / s2w; see += e * e; }
+    double sd = 0.0, sdd = 0.0;
+    for (int i = 0; i < NB; ++i) { const double dm = s[3 + i] - th; g[3 + i] -= dm / s2b; sd += dm; sdd += dm * dm; }
+    g[1] = sd / s2b - th / 1e6;
+    g[0] = -0.5 * NB / s2b + 0.5 * sdd / (s2b * s2b) + d_invgamma(s2b, 0.001, 0.001);
+    g[2] = -0.5 * (double)d.N / s2w + 0.5 * see / (s2w * s2w) + d_invgamma(s2w, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 9; ++j) out[j] = s[j]; }
+};
+
 // =============================================================================== glm (CUDA-core form)
 // y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
 // small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.

@@ -42,6 +42,7 @@ _TEMPLATES = {
                  inputs=["y", "rat", "Xm", "xbar"]),
     "pumps": dict(nodes=[("alpha", 1), ("beta", 1), ("theta", 10)], inputs=["y", "t"]),
     "surgical": dict(nodes=[("mu", 1), ("s2", 1), ("b", 12)], inputs=["r", "n"]),
+    "dyes": dict(nodes=[("s2_between", 1), ("theta", 1), ("s2_within", 1), ("mu", 6)], inputs=["y", "batch"]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"]),
 }
 

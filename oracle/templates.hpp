@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -343,6 +343,49 @@ inline Model make_surgical() {
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// dyes: doc/examples/dyes.jl:22-47 (data :4-17).  Node order: s2_between, theta, s2_within, mu, y (a valid topological order; the
+// monitored columns come out in the order of doc/examples/dyes.rst).
+inline Model make_dyes() {
+  Model m; m.template_id = TPL_DYES;
+  m.inputs["y"] = {1545, 1440, 1440, 1520, 1580, 1540, 1555, 1490, 1560, 1495, 1595, 1550, 1605, 1510, 1560,
+                   1445, 1440, 1595, 1465, 1545, 1595, 1630, 1515, 1635, 1625, 1520, 1455, 1450, 1480, 1445};
+  { std::vector<double> b(30); for (int k = 0; k < 30; ++k) b[k] = k / 5; m.inputs["batch"] = b; }
+  auto prior_ig = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+  { Node n = make_node("s2_between", true, 1, true, true); n.eval = prior_ig; m.nodes.push_back(n); }          // 0
+  { Node n = make_node("theta", true, 1, true, true);                                                          // 1
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("s2_within", true, 1, true, true); n.eval = prior_ig; m.nodes.push_back(n); }           // 2
+  { Node n = make_node("mu", true, 6, false, true);                                                            // 3
+    n.sources = {1, 0};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, mm.val(1)[0], std::sqrt(mm.val(0)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 30, false, false, true);                                                     // 4: MvNormal(mu[batch], sqrt(s2_within))
+    n.sources = {3, 2};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& b = mm.in("batch"); const auto& mu = mm.val(3);
+      s.distr.form = Distr::MVNORMAL_ISO; s.distr.mu.resize(b.size());
+      for (size_t k = 0; k < b.size(); ++k) s.distr.mu[k] = mu[(size_t)b[k]];
+      s.distr.sigma = std::sqrt(mm.val(2)[0]);
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: s2_between, theta, s2_within, mu[6]
+    const auto& y = mm.in("y"); const auto& b = mm.in("batch"); const auto& mu = mm.val(3);
+    const double s2b = mm.val(0)[0], th = mm.val(1)[0], s2w = mm.val(2)[0];
+    for (int i = 0; i < 6; ++i) g[3 + i] = 0.0;
+    double see = 0;
+    for (size_t k = 0; k < y.size(); ++k) { const size_t i = (size_t)b[k]; const double e = y[k] - mu[i]; g[3 + i] += e / s2w; see += e * e; }
+    double sd = 0, sdd = 0;
+    for (int i = 0; i < 6; ++i) { const double dm = mu[i] - th; g[3 + i] -= dm / s2b; sd += dm; sdd += dm * dm; }
+    g[1] = sd / s2b - th / 1e6;
+    g[0] = -3.0 / s2b + 0.5 * sdd / (s2b * s2b) + ig_dlogpdf(0.001, 0.001, s2b);
+    g[2] = -0.5 * (double)y.size() / s2w + 0.5 * see / (s2w * s2w) + ig_dlogpdf(0.001, 0.001, s2w);
+  };
+  m.finalize();
+  return m;
+}
+
 inline Model make_template(int id, int glm_d = 0) {
   switch (id) {
     case TPL_LINE: return make_line();
@@ -351,6 +394,7 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_PUMPS: return make_pumps();
     case TPL_GLM: return make_glm(glm_d > 0 ? glm_d : 1);
     case TPL_SURGICAL: return make_surgical();
+    case TPL_DYES: return make_dyes();
     default: throw std::runtime_error("unknown template");
   }
 }

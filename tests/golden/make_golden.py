@@ -42,11 +42,13 @@ def reference_data():
     rats = open(f"{REF}/doc/examples/rats.jl").read()
     line = open(f"{REF}/doc/tutorial/line.jl").read()
     surgical = open(f"{REF}/doc/examples/surgical.jl").read()
+    dyes = open(f"{REF}/doc/examples/dyes.jl").read()
     d = {
         "seeds": {k: _field(seeds, k) for k in ("r", "n", "x1", "x2")},
         "pumps": {k: _field(pumps, k) for k in ("y", "t")},
         "line": {k: _field(line, k) for k in ("x", "y")},
         "surgical": {k: _field(surgical, k) for k in ("r", "n")},
+        "dyes": {"y": _field(dyes, "y"), "batch": np.repeat(np.arange(6), 5)},                                # dyes.jl:16
     }
     y = _field(rats, "y"); x = _field(rats, "x")
     assert y.size == 150 and x.size == 5
@@ -112,6 +114,14 @@ def surgical_blocks(D, s):
     return {"b": pb + lik, "mu_s2_constrained": pmu + ps2 + pb, "mu_s2_transformed": pmu + ps2 + np.log(s2) + pb}
 
 
+def dyes_blocks(D, s):
+    s2b, th, s2w, mu = s[0], s[1], s[2], s[3:]
+    lik = normal(D["y"], mu[D["batch"]], np.sqrt(s2w)).sum()
+    pmu = normal(mu, th, np.sqrt(s2b)).sum()
+    pth = normal(th, 0, 1000.0); ig = lambda v: invgamma(v, 0.001, 0.001)
+    return {"nuts_mu_theta": pth + pmu + lik, "slice_s2w_s2b": ig(s2w) + ig(s2b) + pmu + lik, "theta": pth + pmu, "mu": pmu + lik}
+
+
 def glm_block(X, y, beta):
     eta = X @ beta
     p = invlogit(eta)
@@ -138,6 +148,8 @@ def states(rng, tpl, n):
                                 rng.normal(240, 15, (n, 30)), rng.normal(6, 0.6, (n, 30))])
     if tpl == "pumps":
         return np.column_stack([rng.gamma(2, 0.5, n), rng.gamma(2, 0.5, n), rng.gamma(1.5, 0.6, (n, 10))])
+    if tpl == "dyes":
+        return np.column_stack([rng.gamma(2, 1500, n), rng.normal(1525, 20, n), rng.gamma(3, 900, n), rng.normal(1525, 40, (n, 6))])
     if tpl == "surgical":
         return np.column_stack([rng.normal(-2.5, 0.3, n), rng.gamma(2, 0.1, n), rng.normal(-2.5, 0.5, (n, 12))])
     raise ValueError(tpl)
@@ -200,7 +212,7 @@ def main():
     D = reference_data()
     rng = np.random.default_rng(20261018)
     out = {"_about": "formula-level golden vectors (scipy.stats restatement of logpdf! per block); see make_golden.py",
-           "data": {k: {kk: np.asarray(vv).tolist() for kk, vv in v.items()} for k, v in D.items() if k != "surgical"}, "blocks": {}}
+           "data": {k: {kk: np.asarray(vv).tolist() for kk, vv in v.items()} for k, v in D.items() if k not in ("surgical", "dyes")}, "blocks": {}}
     fn = {"line": line_blocks, "seeds": seeds_blocks, "rats": rats_blocks, "pumps": pumps_blocks}
     for tpl in ("line", "seeds", "rats", "pumps"):
         S = states(rng, tpl, 12)
@@ -239,6 +251,10 @@ def main():
     S = states(rng2, "surgical", 12)
     vals = [surgical_blocks(D["surgical"], s) for s in S]
     extra["blocks"]["surgical"] = {"states": S.tolist(), "logpdf": {k: [float(v[k]) for v in vals] for k in vals[0]}}
+    extra["data"]["dyes"] = {k: np.asarray(v).tolist() for k, v in D["dyes"].items()}
+    S = states(rng2, "dyes", 12)
+    vals = [dyes_blocks(D["dyes"], s) for s in S]
+    extra["blocks"]["dyes"] = {"states": S.tolist(), "logpdf": {k: [float(v[k]) for v in vals] for k in vals[0]}}
     with open(os.path.join(HERE, "block_logpdf_extra.json"), "w") as f:
         json.dump(extra, f)
     diag = {"_about": "gelmandiag / summarystats golden values from the formulas of src/output/{gelmandiag,stats,mcse}.jl; see make_golden.py",

@@ -15,6 +15,9 @@ LINE_INITS = np.array([[0.3, -0.2, 1.5], [1.0, 0.5, 0.7], [-0.5, 1.2, 3.0]])
 SURGICAL_INITS = np.array([[0.0, 1.0] + [0.1] * 12, [1.0, 10.0] + [0.5] * 12])                       # doc/examples/surgical.jl:47-50
 
 
+DYES_INITS = np.array([[1.0, 1500.0, 1.0] + [1500.0] * 6, [10.0, 3000.0, 10.0] + [3000.0] * 6])       # doc/examples/dyes.jl:51-56 (state order s2_between, theta, s2_within, mu)
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -55,6 +58,14 @@ SCHEMES = {
                                  dict(kind="slice_uni", nodes=[1, 3], scale=1.0)], RATS_INITS),
     # NUTS(alpha, beta, mu_alpha, mu_beta) + Slice(s2_c, s2_alpha, s2_beta; univariate)
     "rats_nuts_slice": ("rats", [dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], RATS_INITS),
+    # doc/examples/dyes.jl:60-73: four schemes on one model (scheme4's Cosine proposal has no device implementation: Normal is used)
+    "dyes_nuts_slice": ("dyes", [dict(kind="nuts", nodes=[3, 1]), dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
+    "dyes_mala_slice": ("dyes", [dict(kind="mala", nodes=[1], epsilon=50.0), dict(kind="mala", nodes=[3], epsilon=50.0, scale=np.eye(6)),
+                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
+    "dyes_hmc_slice": ("dyes", [dict(kind="hmc", nodes=[1], epsilon=10.0, L=5), dict(kind="hmc", nodes=[3], epsilon=10.0, L=5, scale=np.eye(6)),
+                                dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
+    "dyes_rwm_slice": ("dyes", [dict(kind="rwm", nodes=[1], scale=50.0), dict(kind="rwm", nodes=[3], scale=50.0),
+                                dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     # doc/examples/surgical.jl:54-55: NUTS(:b), Slice([:mu, :s2], 1.0)
     "surgical_nuts_slice": ("surgical", [dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], SURGICAL_INITS),
     "surgical_amwg": ("surgical", [dict(kind="amwg", nodes=[2], scale=0.3), dict(kind="amwg", nodes=[0, 1], scale=0.3)], SURGICAL_INITS),

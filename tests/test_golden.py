@@ -37,6 +37,12 @@ BLOCKS = {
         "mu_s2_constrained": ([dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], 1),
         "mu_s2_transformed": ([dict(kind="amwg", nodes=[0, 1], scale=0.3)], 0),
     },
+    "dyes": {
+        "nuts_mu_theta": ([dict(kind="nuts", nodes=[3, 1]), dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], 0),
+        "slice_s2w_s2b": ([dict(kind="nuts", nodes=[3, 1]), dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], 1),
+        "theta": ([dict(kind="mala", nodes=[1], epsilon=50.0)], 0),
+        "mu": ([dict(kind="hmc", nodes=[3], epsilon=10.0, L=5)], 0),
+    },
     "pumps": {
         "alpha_beta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 0),
         "theta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 1),
@@ -83,12 +89,13 @@ def test_oracle_block_densities_match_golden(oracle, gold, tpl):
         np.testing.assert_allclose(o.logpdf(bi, S), gold["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=f"{tpl}/{key}")
 
 
-def test_oracle_surgical_block_densities_match_golden(oracle, gold_extra):
-    S = np.array(gold_extra["blocks"]["surgical"]["states"])
-    for key, (blocks, bi) in BLOCKS["surgical"].items():
-        o = oracle.Oracle("surgical")
+@pytest.mark.parametrize("tpl", ["surgical", "dyes"])
+def test_oracle_extra_template_block_densities_match_golden(oracle, gold_extra, tpl):
+    S = np.array(gold_extra["blocks"][tpl]["states"])
+    for key, (blocks, bi) in BLOCKS[tpl].items():
+        o = oracle.Oracle(tpl)
         o.set_scheme(_oracle_blocks(blocks))
-        np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"]["surgical"]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
 
 
 def test_oracle_glm_density_and_gradient_match_golden(oracle, gold):
@@ -179,13 +186,14 @@ def test_gpu_block_densities_match_golden(gold, tpl):
 
 
 @pytest.mark.gpu
-def test_gpu_surgical_block_densities_match_golden(gold_extra):
+@pytest.mark.parametrize("tpl", ["surgical", "dyes"])
+def test_gpu_extra_template_block_densities_match_golden(gold_extra, tpl):
     from mambacuda.engine import Engine
-    S = np.array(gold_extra["blocks"]["surgical"]["states"])
-    for key, (blocks, bi) in BLOCKS["surgical"].items():
-        eng = Engine("surgical", 4)
+    S = np.array(gold_extra["blocks"][tpl]["states"])
+    for key, (blocks, bi) in BLOCKS[tpl].items():
+        eng = Engine(tpl, 4)
         eng.set_scheme(blocks)
-        np.testing.assert_allclose(eng.logpdf(bi, S), gold_extra["blocks"]["surgical"]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        np.testing.assert_allclose(eng.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
         eng.close()
 
 

@@ -34,11 +34,11 @@ def random_states(inits, B, rng, D_pos):
     return st
 
 
-POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}}
+POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}}
 
 
 @pytest.mark.parametrize("name", ["line_amwg_slice", "line_nuts_all", "seeds_amwg", "seeds_amm", "rats_slice_amwg",
-                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg"])
+                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg", "dyes_nuts_slice", "dyes_mala_slice", "dyes_hmc_slice"])
 def test_logpdf_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -65,7 +65,7 @@ def test_logpdf_out_of_support_is_minus_inf(oracle):
     assert np.all(np.isneginf(eng2.logpdf(0, in2, x))) and np.all(np.isneginf(orc2.logpdf(0, in2, x)))
 
 
-@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice"])
+@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice"])
 def test_gradient_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -138,6 +138,8 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("pumps_slice", 300, 100, 2),
     ("pumps_gibbs_amwg", 300, 100, 2),
     ("surgical_amwg", 300, 150, 2),
+    ("dyes_rwm_slice", 300, 0, 1),
+    ("dyes_hmc_slice", 100, 0, 1),
     ("line_rwm", 500, 0, 1),
     ("line_rwm_unif", 500, 0, 1),
     ("line_rwm_tri", 500, 0, 1),
@@ -309,6 +311,23 @@ def test_rats_warp_kernel_posterior_matches_published_table(oracle):
     assert np.all(np.abs(summ[:, 0] - ref) < 3 * np.hypot(ref_mcse, summ[:, 3]) + 0.02 * ref_sd)
     np.testing.assert_allclose(summ[:, 1], ref_sd, rtol=0.08)
     assert (eng.gelman(0.05, True)[:, 0] < 1.05).all()
+
+
+@pytest.mark.parametrize("name", ["dyes_nuts_slice", "dyes_hmc_slice", "dyes_mala_slice"])
+def test_dyes_schemes_match_published_table(oracle, name):
+    # doc/examples/dyes.rst (scheme 1): theta 1526.72 (24.5), s2_within 2887.6 (1075), mu[1] 1511.48, mu[5] 1578.66, mu[6] 1487.19;
+    # the other schemes of the script (MALA, HMC on theta / mu with Sigma = I) target the same posterior
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme(name)
+    eng = Engine(tpl, 1024, seed=6)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.01)
+    eng.run(5000, burnin=2500, thin=1, store=False, out=False)
+    summ = eng.summary_streaming(); names = eng.names(1)
+    ref = {"theta": (1526.7186, 0.377, 24.55), "s2_within": (2887.5853, 76.9, 1075.2), "mu[1]": (1511.4798, 0.52, 20.8),
+           "mu[5]": (1578.6636, 1.29, 25.5), "mu[6]": (1487.1934, 1.24, 24.7)}
+    for nm, (mean, mcse_ref, sd) in ref.items():
+        j = names.index(nm)
+        assert abs(summ[j, 0] - mean) < 3 * np.hypot(mcse_ref, summ[j, 3]) + 0.05 * sd, (name, nm, summ[j, 0], mean)
 
 
 def test_surgical_posterior_matches_published_table(oracle):

@@ -69,6 +69,17 @@ def test_line_mala_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_dyes_reference_scheme(oracle):
+    # doc/examples/dyes.jl:60-61 (NUTS([mu, theta]) + Slice([s2_within, s2_between], 1000), 2 x 10,000, burnin 2,500, thin 2), doc/examples/dyes.rst
+    ref = {"theta": (1526.7186, 0.37724897), "s2_within": (2887.5853, 76.89117959), "mu[1]": (1511.4798, 0.52158448),
+           "mu[3]": (1552.6742, 0.70276515), "mu[5]": (1578.6636, 1.29216105), "mu[6]": (1487.1934, 1.23710390)}
+    tpl, blocks, inits = helpers.scheme("dyes_nuts_slice")
+    ob = [helpers.oracle_block(b) for b in blocks]; ob[0]["max_depth"] = 10
+    o = oracle.Oracle(tpl); o.set_scheme(ob)
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=4, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_surgical_reference_scheme(oracle):
     # doc/examples/surgical.jl:54-60 (NUTS(b) + Slice([mu, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/surgical.rst
     ref = {"mu": (-2.550263247, 0.00352027397), "pop_mean": (0.073062651, 0.00022880854), "s2": (0.183080212, 0.00629499754),
