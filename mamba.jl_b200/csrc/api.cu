@@ -63,6 +63,7 @@ struct mcu_ctx {
   bool rats_fast_ok = false;                                                // fused rats Slice + AMWG kernel (rats_fast.cu)
   bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
   std::vector<std::vector<double>> h_scales;                                // host mirror of every block's expanded scale
+  std::vector<std::vector<double>> h_SigmaL;                                // host mirror of every block's lower Cholesky factor (HMC / MALA / AMM)
   void* d_diag = nullptr; size_t diag_cap = 0;     // persistent scratch of the diagnostics reductions (partials | folded sums | codes | centres)
   void* d_stage = nullptr; size_t stage_cap = 0;   // reusable device staging buffer (no cudaMalloc/cudaFree on the hot API calls)
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
@@ -603,7 +604,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   h->has_inits = false;
   long long toff = 0;
   std::vector<DevBlock> hb;
-  std::vector<std::vector<double>> h_scales;
+  std::vector<std::vector<double>> h_scales, h_SigmaL;
   for (int bi = 0; bi < n_blocks; ++bi) {
     const mcu_block_desc& d = blocks[bi];
     if (d.kind < MCU_AMWG || d.kind > MCU_MALA) return fail(h, MCU_ERR_ARG, "unknown sampler kind");
@@ -660,6 +661,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
     if (!SL.empty()) { CK(cudaMalloc(&dS, sizeof(double) * k * k)); h->scheme_allocs.push_back(dS); CK(cudaMemcpy(dS, SL.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice)); }
     b.elem = de; b.elink = dl; b.scale = ds; b.SigmaL = dS;
     h_scales.push_back(sc);
+    h_SigmaL.push_back(SL);
     b.tune_off = (int)toff;
     switch (d.kind) {   // tune record layout: see samplers.cuh
       case MCU_AMWG: toff += 2 + 2 * k; break;
@@ -679,7 +681,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   cudaFree(h->d_elink_state); h->d_elink_state = nullptr;
   CK(cudaMalloc(&h->d_elink_state, sizeof(int) * h->D));
   CK(cudaMemcpy(h->d_elink_state, h->elink_state.data(), sizeof(int) * h->D, cudaMemcpyHostToDevice));
-  h->h_scales = h_scales;
+  h->h_scales = h_scales; h->h_SigmaL = h_SigmaL;
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
   h->rats_warp_ok = scheme_is_rats_warp(h);
   h->rats_fast_ok = scheme_is_rats_fast(h);
@@ -787,7 +789,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     const long long n = std::min(chunk, iters - done);
     a.iter0 = h->iter + done; a.iters = n;
     if (fast) {
-      rc = seeds_fast_launch(Host<SeedsModel>::data(h), a, h->h_blocks.data(), h->stream);
+      rc = seeds_fast_launch(h->inputs["r"].data(), h->inputs["n"].data(), h->inputs["x1"].data(), h->inputs["x2"].data(), a, h->h_blocks.data(),
+                             h->h_scales, h->h_SigmaL.empty() || h->h_SigmaL[0].empty() ? nullptr : h->h_SigmaL[0].data(), h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
     } else if (pumps_fast) {
       rc = pumps_fast_launch(h->inputs["y"].data(), h->inputs["t"].data(), (int)h->inputs["y"].size(), a, h->h_scales, h->stream);

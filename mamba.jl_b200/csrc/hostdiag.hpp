@@ -6,8 +6,8 @@
 //   summary_column     mean / SD / naive SE / batch-means MCSE / ESS from streaming sums (src/output/stats.jl:85-94)
 //   summarystats_soa   the reference's exact summarystats over materialised samples
 //                      (src/output/stats.jl:85-94, src/output/mcse.jl:10-33; StatsBase autocov/sem)
-//   f_quantile         quantile(FDist(d1, d2), p) (gelmandiag.jl:43) — hypergeometric series for the
-//                      regularised incomplete beta / gamma functions + bisection
+//   f_quantile         quantile(FDist(d1, d2), p) (gelmandiag.jl:43) — continued fraction / series for the
+//                      regularised incomplete beta / gamma functions + bracketed Newton
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -17,20 +17,35 @@ namespace hostdiag {
 
 inline double lgam(double x) { int s; return ::lgamma_r(x, &s); }
 
-// I_x(a,b) = x^a (1-x)^b / (a B(a,b)) * [1 + sum_{n>=0} prod_{i=0..n} x (a+b+i)/(a+1+i)]   (DLMF 8.17.8 form)
+// Regularised incomplete beta function I_x(a, b): continued fraction (DLMF 8.17.22) evaluated with the modified Lentz algorithm on the
+// side where it converges in O(sqrt(max(a, b))) steps (x < (a + 1) / (a + b + 2), else 1 - I_{1-x}(b, a)).  With one chain per GPU
+// thread a = (chains - 1) / 2 is 1e5 - 1e7: the power series needs up to ~1e6 terms near the mode, the fraction a few hundred.
 inline double ibeta_series(double a, double b, double x) {
   if (x <= 0.0) return 0.0;
   if (x >= 1.0) return 1.0;
   const bool flip = x > (a + 1.0) / (a + b + 2.0);
   const double aa = flip ? b : a, bb = flip ? a : b, xx = flip ? 1.0 - x : x;
-  double term = 1.0, sum = 1.0;
-  for (int n = 0; n < 2000000; ++n) {
-    term *= xx * (aa + bb + n) / (aa + 1.0 + n);
-    sum += term;
-    if (term < sum * 1e-17) break;
+  const double tiny = 1e-300, qab = aa + bb, qap = aa + 1.0, qam = aa - 1.0;
+  double c = 1.0, d = 1.0 - qab * xx / qap;
+  if (std::fabs(d) < tiny) d = tiny;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m < 200000; ++m) {
+    const double m2 = 2.0 * m;
+    double an = m * (bb - m) * xx / ((qam + m2) * (aa + m2));
+    d = 1.0 + an * d; if (std::fabs(d) < tiny) d = tiny;
+    c = 1.0 + an / c; if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d; h *= d * c;
+    an = -(aa + m) * (qab + m) * xx / ((aa + m2) * (qap + m2));
+    d = 1.0 + an * d; if (std::fabs(d) < tiny) d = tiny;
+    c = 1.0 + an / c; if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 2e-16) break;
   }
   const double logpre = aa * std::log(xx) + bb * std::log1p(-xx) - std::log(aa) - (lgam(aa) + lgam(bb) - lgam(aa + bb));
-  const double v = std::exp(logpre) * sum;
+  const double v = std::exp(logpre) * h;
   return flip ? 1.0 - v : v;
 }
 // P(a, x) = x^a e^-x / Gamma(a+1) * sum_{n>=0} x^n / ((a+1)...(a+n))

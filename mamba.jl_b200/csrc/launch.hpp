@@ -57,7 +57,8 @@ void launch_summary_partial(const double* mom, const double* momn, long long C, 
 double measure_fp64_peak_tflops(cudaStream_t st);
 
 // fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success
-int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st);
+int seeds_fast_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
+                      const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st);
 
 
 // fused pumps kernel for the reference's Slice scheme (pumps_fast.cu); returns 0 on success

@@ -460,7 +460,12 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 template <int BS, bool AMM0>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)BS * 4 * NSL * sizeof(double);
-  if (cudaFuncSetAttribute(seeds_fast_kernel<BS, AMM0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  static thread_local int attr_dev = -1;   // the attribute call is slow: once per device
+  int dev = 0; cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    if (cudaFuncSetAttribute(seeds_fast_kernel<BS, AMM0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    attr_dev = dev;
+  }
   const unsigned grid = (unsigned)((a.n_chains + BS - 1) / BS);
   seeds_fast_kernel<BS, AMM0><<<grid, BS, smem, st>>>(cfg, a);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -470,20 +475,15 @@ int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
 
 // h_blocks: host copies of the three DevBlocks (scale pointers are device pointers; the scales are
 // re-read from the host-side scale mirror passed in cfg by the caller).
-int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBlock* h_blocks, cudaStream_t st) {
-  (void)d;
+int seeds_fast_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
+                      const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st) {
   FastCfg cfg;
-  // plate constants and scales come down from the device copies the generic path uses, so both
-  // paths see identical inputs
-  double r[NPL], n[NPL], x1[NPL], x2[NPL], sa[4], sb[NPL], ss[1];
-  if (cudaMemcpy(r, d.r, sizeof(r), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(n, d.n, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(x1, d.x1, sizeof(x1), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(x2, d.x2, sizeof(x2), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (h_blocks[0].kind == 6) { for (double& v : sa) v = 0.0; }   // AMM: no per-component sigma
-  else if (cudaMemcpy(sa, h_blocks[0].scale, sizeof(sa), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(sb, h_blocks[1].scale, sizeof(sb), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (cudaMemcpy(ss, h_blocks[2].scale, sizeof(ss), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  // plate constants, scales and (AMM) the Cholesky factor come from the handle's host-side copies of what the generic path uses
+  const bool amm0 = h_blocks[0].kind == 6;   // MCU_AMM
+  double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[NPL], ss[1];
+  if (!amm0) for (int j = 0; j < 4; ++j) sa[j] = h_scales[0][j];
+  for (int i = 0; i < NPL; ++i) sb[i] = h_scales[1][i];
+  ss[0] = h_scales[2][0];
   for (int j = 0; j < 4; ++j) { cfg.amask[j] = 0; cfg.gmask[j] = 0; cfg.scale_a[j] = sa[j]; }
   for (int i = 0; i < NPL; ++i) {
     if ((x1[i] != 0.0 && x1[i] != 1.0) || (x2[i] != 0.0 && x2[i] != 1.0)) return -2;   // design must be 0/1 indicators
@@ -511,9 +511,9 @@ int seeds_fast_launch(const SeedsModel::Data& d, const RunArgs& a, const DevBloc
     cfg.target[b] = h_blocks[b].target;
   }
   // 96 threads x 3 blocks/SM = 288 resident chains/SM: 125,000 chains/GPU fit in 3 even rounds
-  const bool amm0 = h_blocks[0].kind == 6;   // MCU_AMM
   if (amm0) {
-    if (cudaMemcpy(cfg.amm_SL, h_blocks[0].SigmaL, sizeof(cfg.amm_SL), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (!h_SigmaL) return -1;
+    for (int i = 0; i < 16; ++i) cfg.amm_SL[i] = h_SigmaL[i];
     cfg.amm_beta = h_blocks[0].beta; cfg.amm_scale = h_blocks[0].amm_scale;
     return launch_bs<MCU_SEEDS_BS, true>(cfg, a, st);
   }
