@@ -169,6 +169,14 @@ int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_
  * state [B × D]: full model state (constrained) for each evaluation; x [B × k] block vector on
  * the sampler's scale, or NULL to use the block's own values from `state` (unlist, sampler.jl:113-115). */
 int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const double* x, double* lp);
+/* logpdf(mc::ModelChains, nodekeys)  src/output/modelstats.jl:16-58 (the kernel of dic(mc), modelstats.jl:3-13): the sum of the
+ * selected stochastic nodes' log densities (constrained scale, no Jacobian) at B full states [B × D].  Bit f of factor_mask selects
+ * factor f: 0 .. n_param_nodes-1 are the unobserved stochastic nodes in mcu_names(h, 2) order, n_param_nodes .. n_factors-1 the
+ * observed ones (keys(m, :output)).  mcu_factor_parents gives, as a bitmask over parameter nodes, the nodes factor f reads through
+ * Logical nodes (what getsimkeys, modelstats.jl:102-127, finds by walking the graph).                                              */
+int mcu_factor_counts(mcu_handle h, int* n_param_nodes, int* n_factors);
+int mcu_factor_parents(mcu_handle h, int factor, uint32_t* parent_nodes);
+int mcu_logpdf_nodes(mcu_handle h, uint32_t factor_mask, int64_t B, const double* state, double* lp);
 /* logpdfgrad!(block, x, dtype)  src/samplers/sampler.jl:106-111 (+ analytic mode).  g [B × k]. */
 int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const double* state,
                    const double* x, double* lp, double* g);
@@ -187,8 +195,9 @@ int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, dou
  * size 100) and reduced across chains by reduction kernels; what crosses the ABI is O(p).
  *
  * link(c) for gelmandiag(transform=true): src/output/modelchains.jl:57-76, src/output/chains.jl:237-246.
- * codes[p]: 0 identity, 1 log.  Monitored stochastic columns use their node's link; Logical
- * columns use the reference's data-dependent heuristic (log when every value is > 0), resolved
+ * codes[p]: 0 identity, 1 log, 2 logit.  Monitored stochastic columns use their node's link; Logical
+ * columns use the reference's data-dependent heuristic (log when every value is > 0, logit when every
+ * value is also < 1 — logit moments are kept for Logical columns among the first 64), resolved
  * from minmax[p×2] (pass the all-reduced min/max for multi-GPU, or NULL to use this handle's).  */
 int mcu_minmax(mcu_handle h, double* minmax /* [p × 2] */);
 int mcu_link_codes(mcu_handle h, int transform, const double* minmax, int* codes);
@@ -227,13 +236,16 @@ int mcu_summary_streaming(mcu_handle h, double* out);
  *   mcu_chains_autocor    autocor(c; lags, relative)  stats.jl:3-13; lags = index lags on the stored series (× thinning step when
  *                         relative = true, exactly as the reference does); out [p × nlags × m] column-major
  *   mcu_chains_changerate changerate(c)         stats.jl:19-39                out [p + 1] (last = multivariate), NOT rounded
- *   mcu_chains_gelman     gelmandiag(c; alpha, mpsrf, transform)  src/output/gelmandiag.jl:3-60; codes[j] = 1 → log scale (link(c));
+ *   mcu_chains_summarystats  summarystats(c; etype)  src/output/stats.jl:85-94, src/output/mcse.jl:3-46   out [p × 5] row-major: mean, SD, naive SE,
+ *                         MCSE, ESS; MCU_ERR_ARG where mcse_bm throws (fewer than 2 batches)
+ *   mcu_chains_gelman     gelmandiag(c; alpha, mpsrf, transform)  src/output/gelmandiag.jl:3-60; codes[j] = 1 → log scale, 2 → logit scale (link(c));
  *                         out [(p + mpsrf) × 2] row-major, NOT rounded; multivariate row = (MPSRF, NaN); returns MCU_ERR_ARG for m < 2 */
 int mcu_chains_quantile(const double* value, int64_t n, int p, int64_t m, const double* q, int nq, double* out);
 int mcu_chains_hpd(const double* value, int64_t n, int p, int64_t m, double alpha, double* out);
 int mcu_chains_autocor(const double* value, int64_t n, int p, int64_t m, const int64_t* lags, int nlags, double* out);
 int mcu_chains_changerate(const double* value, int64_t n, int p, int64_t m, double* out);
 int mcu_chains_gelman(const double* value, int64_t n, int p, int64_t m, double alpha, const int* codes, int mpsrf, double* out);
+int mcu_chains_summarystats(const double* value, int64_t n, int p, int64_t m, int etype, int batch_size, double* out);
 /* Per-series convergence diagnostics, one row per (parameter, chain); out [p × K × m] column-major, NOT rounded; etype: MCU_ETYPE_*
  * (batch_size only for MCU_ETYPE_BM).  Return MCU_ERR_ARG where the reference throws (window fractions, too few iterations for mcse_bm).
  *   mcu_chains_geweke   gewekediag(c; first, last, etype)        src/output/gewekediag.jl:3-31   K = 2: Z-score, p-value

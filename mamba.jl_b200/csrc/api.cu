@@ -762,6 +762,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.n_blocks = (int)h->h_blocks.size(); a.D = h->D; a.P = h->P; a.blocks = h->d_blocks;
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
+  a.logit_mask = 0ull;
+  { const TplInfo ti = tpl_info(h); for (int j = 0; j < h->P && j < 64; ++j) if (ti.monlink[j] == LINK_HEUR) a.logit_mask |= 1ull << j; }
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
   const bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
@@ -908,6 +910,44 @@ static int density_call(mcu_handle h, int block, int grad_mode, int64_t B, const
   return MCU_OK;
 }
 
+int mcu_factor_counts(mcu_handle h, int* n_param_nodes, int* n_factors) {
+  if (!h) return MCU_ERR_ARG;
+  int nf = 0;
+  MCU_DISPATCH(h, nf = M::NF);
+  if (n_param_nodes) *n_param_nodes = tpl_info(h).NN;
+  if (n_factors) *n_factors = nf;
+  return MCU_OK;
+}
+
+int mcu_factor_parents(mcu_handle h, int factor, uint32_t* parent_nodes) {
+  if (!h || !parent_nodes) return MCU_ERR_ARG;
+  int nf = 0; uint32_t m = 0;
+  MCU_DISPATCH(h, nf = M::NF; if (factor >= 0 && factor < nf) m = M::parents(factor));
+  if (factor < 0 || factor >= nf) return fail(h, MCU_ERR_ARG, "factor index out of range");
+  *parent_nodes = m;
+  return MCU_OK;
+}
+
+int mcu_logpdf_nodes(mcu_handle h, uint32_t factor_mask, int64_t B, const double* state, double* lp) {
+  if (!h || !state || !lp || B < 1) return h ? fail(h, MCU_ERR_ARG, "bad argument") : MCU_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  const int D = h->D;
+  double *d_rec = nullptr, *d_state = nullptr, *d_lp = nullptr;
+  CK(cudaMalloc(&d_rec, sizeof(double) * B * D));
+  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
+  CK(cudaMalloc(&d_lp, sizeof(double) * B));
+  CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
+  launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
+  MCU_DISPATCH(h, launch_factors(Host<M>::data(h), factor_mask, B, D, d_state, d_lp, h->stream));
+  h->launches++;
+  CK(cudaMemcpyAsync(lp, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_lp);
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+
 int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const double* x, double* lp) {
   if (!lp) return h ? fail(h, MCU_ERR_ARG, "lp is NULL") : MCU_ERR_ARG;
   return density_call(h, block, 0, B, state, x, lp, nullptr);
@@ -975,8 +1015,11 @@ int mcu_link_codes(mcu_handle h, int transform, const double* minmax, int* codes
         if (!minmax && mm.empty()) { mm.resize((size_t)h->P * 2); int rc = mcu_minmax(h, mm.data()); if (rc) return rc; }
         const double* q = minmax ? minmax : mm.data();
         if (q[j * 2] > 0.0) {
-          if (q[j * 2 + 1] < 1.0) return fail(h, MCU_ERR_UNSUPPORTED, "logit link for a Logical column needs stored samples");
           c = 1;
+          if (q[j * 2 + 1] < 1.0) {   // all values in (0, 1): logit (chains.jl:241-243); the streaming record keeps logit moments for the first 64 columns
+            if (j >= 64) return fail(h, MCU_ERR_UNSUPPORTED, "logit link beyond monitored column 64 needs stored samples");
+            c = 2;
+          }
         }
       }
     }
@@ -1110,6 +1153,12 @@ int mcu_chains_heidel(const double* value, int64_t n, int p, int64_t m, double a
 int mcu_chains_raftery(const double* value, int64_t n, int p, int64_t m, double q, double r, double s, double eps, int64_t range_start, int64_t range_step, double* out) {
   if (!value || !out || n < 3 || p < 1 || m < 1 || !(q > 0.0 && q < 1.0) || !(r > 0.0) || !(s > 0.0 && s < 1.0) || range_step < 1) return MCU_ERR_ARG;
   return hostdiag::chains_series(value, n, p, m, 5, out, [&](const double* x, double* rr) { hostdiag::raftery_vec(x, n, q, r, s, eps, range_start, range_step, rr); return 0; }) ? MCU_ERR_ARG : MCU_OK;
+}
+
+int mcu_chains_summarystats(const double* value, int64_t n, int p, int64_t m, int etype, int batch_size, double* out) {
+  if (!value || !out || n < 1 || p < 1 || m < 1 || etype < MCU_ETYPE_BM || etype > MCU_ETYPE_IPSE) return MCU_ERR_ARG;
+  if (batch_size < 1) batch_size = 100;
+  return hostdiag::chains_summarystats(value, n, p, m, etype, batch_size, out) ? MCU_ERR_ARG : MCU_OK;
 }
 
 double mcu_fp64_peak_tflops(mcu_handle h) {

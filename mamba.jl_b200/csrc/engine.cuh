@@ -14,7 +14,7 @@
 
 namespace mcu {
 
-constexpr int kMomPerCol = 9;   // mean, M2, lmean, lM2, min, max, bsum, bmean, bM2
+constexpr int kMomPerCol = 11;  // mean, M2, lmean, lM2, min, max, bsum, bmean, bM2, logit mean, logit M2 (Logical columns only)
 constexpr int kBatch = 100;     // mcse_bm default batch size (src/output/mcse.jl:10)
 
 // logpdf!(block, x) / logpdfgrad!(block, x) for one chain: relist x into the state record
@@ -100,9 +100,10 @@ struct RunArgs {
   const DevBlock* blocks;
   double* state; double* tune; double* samples; double* mom; double* momn;
   const double* ext_u; unsigned long long ext_n; unsigned long long* ext_pos;
+  unsigned long long logit_mask;          // monitored columns (bit j) whose link(c) may be the logit: Logical nodes in (0, 1), chains.jl:237-246
 };
 
-static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon) {
+static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon, unsigned long long logit_mask = 0ull) {
   const double n = momn[0 * C + c] + 1.0; momn[0 * C + c] = n;
   double bc = momn[1 * C + c] + 1.0;
   const bool bdone = bc >= (double)kBatch;
@@ -121,6 +122,12 @@ static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t
     q[2 * C] = lmean; q[3 * C] = lM2;
     q[4 * C] = n == 1.0 ? x : fmin(q[4 * C], x);
     q[5 * C] = n == 1.0 ? x : fmax(q[5 * C], x);
+    if (j < 64 && ((logit_mask >> j) & 1ull)) {
+      const double gx = log(x / (1.0 - x));   // logit: src/utils.jl:66
+      double gmean = q[9 * C], gM2 = q[10 * C];
+      dl = gx - gmean; gmean += dl / n; gM2 += dl * (gx - gmean);
+      q[9 * C] = gmean; q[10 * C] = gM2;
+    }
     double bsum = q[6 * C] + x;
     if (bdone) {
       const double bm = bsum / (double)kBatch; bsum = 0.0;
@@ -176,7 +183,7 @@ __device__ __forceinline__ void generic_kernel_body(const typename M::Data& data
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;   // iters2inds: src/output/chains.jl:66-87
         for (int j = 0; j < a.P; ++j) a.samples[((size_t)row * a.P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon);
+      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon, a.logit_mask);
     }
   }
   for (int e = 0; e < a.D; ++e) a.state[(size_t)e * C + c] = s[e];
@@ -211,6 +218,20 @@ __global__ void logpdf_kernel(typename M::Data data, const DevBlock* blocks, int
   } else {
     lp[c] = tgt.logf(v);
   }
+}
+
+
+// logpdf(mc, nodekeys) (src/output/modelstats.jl:16-58): sum of the selected factors (node densities on the constrained scale) at B
+// states, one per thread; bit f of `mask` = factor f (0 .. NN-1 parameter nodes, NN .. NF-1 observed nodes, i.e. keys(m, :output)).
+template <class M>
+__global__ void factors_kernel(typename M::Data data, unsigned mask, long long B, int D, const double* state, double* lp) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B) return;
+  double s[M::D];
+  for (int e = 0; e < D; ++e) s[e] = state[(size_t)e * B + c];
+  double sum = 0.0;
+  for (int f = 0; f < M::NF; ++f) if ((mask >> f) & 1u) sum += M::factor(data, s, f, false);
+  lp[c] = sum;
 }
 
 }  // namespace mcu

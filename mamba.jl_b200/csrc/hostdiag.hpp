@@ -320,6 +320,24 @@ inline void raftery_vec(const double* x, long long nx, double q, double r, doubl
   out[0] = kt; out[1] = burnin; out[2] = total; out[4] = total / nmin;
 }
 // the three diagnostics over every (parameter, chain) series of a ModelChains.value; out [p x K x m] column-major (K = 2, 6, 5)
+// summarystats(c; etype) on a materialised array: src/output/stats.jl:85-94 — each column pooled over chains in vec(x[:, j, :]) order
+// (chain-major), ESS = min((SD / MCSE)^2, iterations).  out [p x 5]: mean, SD, naive SE, MCSE, ESS.
+inline int chains_summarystats(const double* v, long long n, int p, long long m, int etype, int batch, double* out) {
+  const size_t N = (size_t)n * (size_t)m;
+  std::vector<double> x(N);
+  for (int j = 0; j < p; ++j) {
+    for (long long k = 0; k < m; ++k)
+      for (long long i = 0; i < n; ++i) x[(size_t)k * n + i] = at(v, n, p, i, j, k);
+    const double mu = mean_v(x.data(), N), sd = sd_v(x.data(), N);
+    double mc;
+    if (mcse_vec(x.data(), N, etype, batch, &mc)) return 1;
+    const double r = sd / mc;
+    out[j * 5 + 0] = mu; out[j * 5 + 1] = sd; out[j * 5 + 2] = sd / std::sqrt((double)N); out[j * 5 + 3] = mc;
+    out[j * 5 + 4] = std::fmin(r * r, (double)n);
+  }
+  return 0;
+}
+
 template <class F>
 inline int chains_series(const double* v, long long n, int p, long long m, int K, double* out, F f) {
   std::vector<double> x((size_t)n);
@@ -412,12 +430,12 @@ inline double sym_eigmax(std::vector<double> A, int p) {
   double mx = A[0]; for (int a = 1; a < p; ++a) mx = std::fmax(mx, A[a * p + a]);
   return mx;
 }
-// gelmandiag(c; alpha, mpsrf, transform) on a materialised array: gelmandiag.jl:3-60.  codes[j] = 1: log scale (link(c)).
+// gelmandiag(c; alpha, mpsrf, transform) on a materialised array: gelmandiag.jl:3-60.  codes[j] = 1: log scale, 2: logit scale (link(c)).
 // out [(p + mpsrf) x 2] row-major, NOT rounded; the multivariate row is (R_fixed + R_random_scale eigmax(W^-1 B), NaN), NaN when W is
 // not positive definite.  Returns 1 for fewer than 2 chains.
 inline int chains_gelman(const double* v, long long n, int p, long long m, double alpha, const int* codes, int mpsrf, double* out) {
   if (m < 2) return 1;
-  auto val = [&](long long i, int j, long long k) { const double x = at(v, n, p, i, j, k); return (codes && codes[j] == 1) ? std::log(x) : x; };
+  auto val = [&](long long i, int j, long long k) { const double x = at(v, n, p, i, j, k); return (codes && codes[j] == 1) ? std::log(x) : (codes && codes[j] == 2) ? std::log(x / (1.0 - x)) : x; };
   std::vector<double> mean((size_t)m * p), W((size_t)p * p, 0.0), s2((size_t)m * p);
   for (long long k = 0; k < m; ++k) {
     for (int j = 0; j < p; ++j) { double s = 0; for (long long i = 0; i < n; ++i) s += val(i, j, k); mean[k * p + j] = s / (double)n; }

@@ -57,8 +57,9 @@ __global__ void gelman_partial_kernel(const double* mom, const double* momn, lon
     if (c < C) {
       const double n = momn[c];
       const double* q = mom + (size_t)j * kMomPerCol * C + c;
-      const double psibar = use_log[j] ? q[2 * C] : q[0 * C];
-      const double s2 = (use_log[j] ? q[3 * C] : q[1 * C]) / (n - 1.0);
+      const int code = use_log[j];   // 0 identity, 1 log, 2 logit
+      const double psibar = code == 2 ? q[9 * C] : code == 1 ? q[2 * C] : q[0 * C];
+      const double s2 = (code == 2 ? q[10 * C] : code == 1 ? q[3 * C] : q[1 * C]) / (n - 1.0);
       const double d = psibar - (center ? center[j * 2 + 0] : 0.0);
       const double e = s2 - (center ? center[j * 2 + 1] : 0.0);
       vals[0] = 1.0; vals[1] = d; vals[2] = d * d; vals[3] = e; vals[4] = e * e; vals[5] = e * d; vals[6] = e * d * d;

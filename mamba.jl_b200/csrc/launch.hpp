@@ -13,7 +13,8 @@ typedef GlmModel<kGlmDMax> GlmM;
 #define MCU_DECLARE_TPL(M)                                                                                   \
   void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st);                                      \
   void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
-                     const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st);
+                     const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st);   \
+  void launch_factors(const M::Data& d, unsigned mask, long long B, int D, const double* state, double* lp, cudaStream_t st);
 MCU_DECLARE_TPL(LineModel)
 MCU_DECLARE_TPL(SeedsModel)
 MCU_DECLARE_TPL(RatsModel)
@@ -39,6 +40,9 @@ MCU_DECLARE_TPL(DyesModel)
   void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
                      const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st) { \
     logpdf_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d, blocks, block, B, D, state, x, lp, g, grad_mode); \
+  }                                                                                                          \
+  void launch_factors(const M::Data& d, unsigned mask, long long B, int D, const double* state, double* lp, cudaStream_t st) { \
+    factors_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d, mask, B, D, state, lp);               \
   }
 
 // misc kernels (kern_misc.cu)

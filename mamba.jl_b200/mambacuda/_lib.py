@@ -48,7 +48,7 @@ SYMBOLS = [
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
     "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
-    "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery",
+    "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery", "mcu_chains_summarystats", "mcu_factor_counts", "mcu_factor_parents", "mcu_logpdf_nodes",
 ]
 
 
@@ -105,5 +105,9 @@ def lib():
     L.mcu_chains_geweke.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_int, dp]
     L.mcu_chains_heidel.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_int, C.c_int, i64, dp]
     L.mcu_chains_raftery.argtypes = [dp, i64, C.c_int, i64, C.c_double, C.c_double, C.c_double, C.c_double, i64, i64, dp]
+    L.mcu_factor_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mcu_factor_parents.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
+    L.mcu_logpdf_nodes.argtypes = [C.c_void_p, C.c_uint32, i64, dp, dp]
+    L.mcu_chains_summarystats.argtypes = [dp, i64, C.c_int, i64, C.c_int, C.c_int, dp]
     _lib = L
     return L

@@ -36,14 +36,14 @@ class DimensionMismatch(ValueError):
 
 # node tables of the device templates: name -> (node id, length, monitored)
 _TEMPLATES = {
-    "line": dict(nodes=[("beta", 2), ("s2", 1)], inputs=["x", "y"]),
-    "seeds": dict(nodes=[("alpha0", 1), ("alpha1", 1), ("alpha2", 1), ("alpha12", 1), ("s2", 1), ("b", 21)], inputs=["r", "n", "x1", "x2"]),
+    "line": dict(nodes=[("beta", 2), ("s2", 1)], inputs=["x", "y"], outputs=["y"]),
+    "seeds": dict(nodes=[("alpha0", 1), ("alpha1", 1), ("alpha2", 1), ("alpha12", 1), ("s2", 1), ("b", 21)], inputs=["r", "n", "x1", "x2"], outputs=["r"]),
     "rats": dict(nodes=[("mu_alpha", 1), ("mu_beta", 1), ("s2_alpha", 1), ("s2_beta", 1), ("s2_c", 1), ("alpha", 30), ("beta", 30)],
-                 inputs=["y", "rat", "Xm", "xbar"]),
-    "pumps": dict(nodes=[("alpha", 1), ("beta", 1), ("theta", 10)], inputs=["y", "t"]),
-    "surgical": dict(nodes=[("mu", 1), ("s2", 1), ("b", 12)], inputs=["r", "n"]),
-    "dyes": dict(nodes=[("s2_between", 1), ("theta", 1), ("s2_within", 1), ("mu", 6)], inputs=["y", "batch"]),
-    "glm": dict(nodes=[("beta", None)], inputs=["X", "y"]),
+                 inputs=["y", "rat", "Xm", "xbar"], outputs=["y"]),
+    "pumps": dict(nodes=[("alpha", 1), ("beta", 1), ("theta", 10)], inputs=["y", "t"], outputs=["y"]),
+    "surgical": dict(nodes=[("mu", 1), ("s2", 1), ("b", 12)], inputs=["r", "n"], outputs=["r"]),
+    "dyes": dict(nodes=[("s2_between", 1), ("theta", 1), ("s2_within", 1), ("mu", 6)], inputs=["y", "batch"], outputs=["y"]),
+    "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 
 
@@ -254,14 +254,308 @@ class Chains:
     def last(self):
         return self.range[-1] if len(self.range) else self.range.start - self.range.step
 
+    # ---- indexing: c[window, names, chains] (src/output/chains.jl:51-99) ------------------------------------
+    def _window2inds(self, window):
+        """window2inds (chains.jl:73-80): an ITERATION range first:step:last → 0-based row slice of value."""
+        n = self.value.shape[0]
+        if window is None or window == slice(None):
+            return 0, 1, n
+        if isinstance(window, slice):    # iteration numbers, stop inclusive like a Julia range
+            window = range(window.start if window.start is not None else self.first,
+                           (window.stop if window.stop is not None else self.last) + 1, window.step or 1)
+        if not isinstance(window, range):
+            raise ArgumentError(f"{type(window).__name__} iteration indexing is unsupported")          # chains.jl:70-71
+        if len(window) == 0:
+            return 0, window.step, 0
+        lo = (window[0] - self.first) / self.step + 1.0                                                 # @mapiters, chains.jl:64-68
+        hi = (window[-1] - self.first) / self.step + 1.0
+        a = max(int(np.ceil(lo)), 1)
+        b = min(int(np.floor(hi)), n)
+        return a - 1, window.step, b
+
+    def _names2inds(self, names):
+        """names2inds (chains.jl:91-98): integers (1-based like the reference), strings, booleans, or None for all."""
+        p = self.value.shape[1]
+        if names is None or (isinstance(names, slice) and names == slice(None)):
+            return list(range(p))
+        if isinstance(names, (str, int, np.integer)):
+            names = [names]
+        names = list(names)
+        if names and all(isinstance(x, (bool, np.bool_)) for x in names):
+            return [j for j, keep in enumerate(names) if keep]
+        out = []
+        for x in names:
+            if isinstance(x, str):
+                if x not in self.names:
+                    raise KeyError(x)
+                out.append(self.names.index(x))
+            else:
+                out.append(int(x) - 1)
+        return out
+
+    def _chains2inds(self, chains):
+        m = self.value.shape[2]
+        if chains is None or (isinstance(chains, slice) and chains == slice(None)):
+            return list(range(m))
+        if isinstance(chains, (int, np.integer)):
+            chains = [chains]
+        chains = list(chains)
+        if chains and all(isinstance(x, (bool, np.bool_)) for x in chains):
+            return [k for k, keep in enumerate(chains) if keep]
+        return [int(k) - 1 for k in chains]
+
+    def _subset(self, key):
+        if not isinstance(key, tuple) or len(key) != 3:
+            raise ArgumentError("chains are indexed as c[window, names, chains]")
+        a, stride, b = self._window2inds(key[0])
+        j = self._names2inds(key[1]); k = self._chains2inds(key[2])
+        value = self.value[a:b:stride][:, j][:, :, k]
+        return value, dict(start=self.first + a * self.step, thin=stride * self.step, names=[self.names[x] for x in j],
+                           chains=[self.chains[x] for x in k])
+
+    def __getitem__(self, key):                                         # getindex(c::Chains, window, names, chains): chains.jl:51-58
+        value, kw = self._subset(key)
+        return Chains(value, **kw)
+
+    def __setitem__(self, key, value):                                  # setindex!: chains.jl:60-62 (iterations by number)
+        iters, names, chains = key
+        a, stride, b = self._window2inds(iters if not isinstance(iters, (int, np.integer)) else range(iters, iters + 1))
+        j = self._names2inds(names); k = self._chains2inds(chains)
+        self.value[np.ix_(range(a, b, stride), j, k)] = value
+
+    def keys(self):                                                     # chains.jl:171-173
+        return self.names
+
+    def size(self, ind=None):                                           # chains.jl:181-188: (last iteration, parameters, chains)
+        dims = (self.last, self.value.shape[1], self.value.shape[2])
+        return dims if ind is None else dims[ind - 1]
+
+    def header(self):                                                   # chains.jl:211-218
+        return (f"Iterations = {self.first}:{self.last}\nThinning interval = {self.step}\n"
+                f"Chains = {','.join(str(k) for k in self.chains)}\nSamples per chain = {len(self.range)}\n")
+
+    def combine(self):                                                  # chains.jl:197-209: rows ordered iteration-major, chain fastest
+        n, p, m = self.value.shape
+        return np.ascontiguousarray(self.value.transpose(0, 2, 1).reshape(n * m, p))
+
+    def link_codes(self):
+        """link(c::AbstractChains) (chains.jl:237-246) as codes: log if every value of a column is > 0, logit if also < 1."""
+        mn = self.value.min(axis=(0, 2)); mx = self.value.max(axis=(0, 2))
+        return np.where(mn > 0.0, np.where(mx < 1.0, 2, 1), 0).astype(np.int32)
+
+    def link(self):
+        cc = self.value.copy()
+        for j, code in enumerate(self.link_codes()):
+            if code == 2:
+                cc[:, j, :] = np.log(cc[:, j, :] / (1.0 - cc[:, j, :]))
+            elif code == 1:
+                cc[:, j, :] = np.log(cc[:, j, :])
+        return cc
+
+    def indiscretesupport(self, bounds=(0, np.inf)):                    # chains.jl:220-235
+        v = self.value
+        ok = (v == np.round(v)) & (v >= bounds[0]) & (v <= bounds[1])
+        return ok.all(axis=(0, 2))
+
+
+def cat(dim, c1, *args):
+    """cat(dim, c1, args...) for chains (src/output/chains.jl:102-163): 1 = iterations, 2 = parameters, 3 = chains."""
+    cs = (c1,) + args
+    if dim == 1:
+        rng = c1.range
+        for c in args:
+            if rng[-1] + rng.step != c.first:
+                raise ArgumentError("noncontiguous chain iterations")
+            if rng.step != c.step:
+                raise ArgumentError("chain thinning differs")
+            rng = range(rng.start, c.last + 1, rng.step)
+        if not all(c.names == c1.names for c in args):
+            raise ArgumentError("chain names differ")
+        if not all(c.chains == c1.chains for c in args):
+            raise ArgumentError("sets of chains differ")
+        return Chains(np.concatenate([c.value for c in cs], axis=0), start=rng.start, thin=rng.step, names=c1.names, chains=c1.chains)
+    if dim == 2:
+        if not all(c.range == c1.range for c in args):
+            raise ArgumentError("chain ranges differ")
+        names = list(c1.names)
+        for c in args:
+            if set(names) & set(c.names):
+                raise ArgumentError("non-unique chain names")
+            names += c.names
+        if not all(c.chains == c1.chains for c in args):
+            raise ArgumentError("sets of chains differ")
+        return Chains(np.concatenate([c.value for c in cs], axis=1), start=c1.first, thin=c1.step, names=names, chains=c1.chains)
+    if dim == 3:
+        if not all(c.range == c1.range for c in args):
+            raise ArgumentError("chain ranges differ")
+        if not all(c.names == c1.names for c in args):
+            raise ArgumentError("chain names differ")
+        return Chains(np.concatenate([c.value for c in cs], axis=2), start=c1.first, thin=c1.step, names=c1.names)   # chains renumbered 1..m
+    raise ArgumentError(f"cannot concatenate along dimension {dim}")
+
+
+def hcat(c1, *args):
+    return cat(2, c1, *args)
+
+
+def vcat(c1, *args):
+    return cat(1, c1, *args)
+
+
+def readcoda(output, index):
+    """readcoda(output, index) (src/output/fileio.jl:15-40): CODA files as written by OpenBUGS.  `index` rows are
+    (name, first row, last row) into `output`, whose rows are (iteration, value); only the iterations at which every
+    parameter was monitored are kept."""
+    out = np.loadtxt(output, dtype=np.float64, ndmin=2)
+    names, firstind, lastind = [], [], []
+    with open(index) as f:
+        for line in f:
+            t = line.split()
+            if t:
+                names.append(t[0]); firstind.append(int(t[1])); lastind.append(int(t[2]))
+    firstind = np.array(firstind); lastind = np.array(lastind)
+    firstiter = out[firstind - 1, 0]; lastiter = out[lastind - 1, 0]
+    thin = int((lastiter[0] - firstiter[0]) / (lastind[0] - firstind[0]))
+    w0, w1 = int(firstiter.max()), int(lastiter.min())
+    window = range(w0, w1 + 1, thin)
+    startind = firstind + (window[0] - firstiter) / thin
+    stopind = lastind - (lastiter - window[-1]) / thin
+    value = np.empty((len(window), len(names)))
+    for i in range(len(names)):
+        value[:, i] = out[int(startind[i]) - 1:int(stopind[i]), 1]
+    return Chains(value[:, :, None], start=window[0], thin=thin, names=names)
+
+
+def writecoda(output, index, c, chain=1):
+    """The inverse of readcoda for one chain (the reference only reads the format): rows (iteration, value) per
+    parameter, index rows (name, first, last)."""
+    k = c.chains.index(chain)
+    row = 1
+    with open(output, "w") as fo, open(index, "w") as fi:
+        for j, nm in enumerate(c.names):
+            for it, v in zip(c.range, c.value[:, j, k]):
+                fo.write(f"{it}\t{float(v)!r}\n")
+            fi.write(f"{nm}\t{row}\t{row + len(c.range) - 1}\n")
+            row += len(c.range)
+
+
+def _jsonable(x):
+    if isinstance(x, np.ndarray):
+        return {"__ndarray__": x.tolist()}
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    if isinstance(x, (np.floating,)):
+        return float(x)
+    if isinstance(x, dict):
+        return {k: _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    return x
+
+
+def _unjson(x):
+    if isinstance(x, dict):
+        if "__ndarray__" in x:
+            return np.asarray(x["__ndarray__"], dtype=float)
+        return {k: _unjson(v) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_unjson(v) for v in x]
+    return x
+
+
+def write(name, c):
+    """write(name, c) (src/output/fileio.jl:9-11).  The reference serialises the Julia object; the engine-side format is a
+    NumPy .npz archive (no pickled objects) with the same fields (value, range, names, chains) plus, for ModelChains, what
+    mcmc(mc, iters) needs to restart: template, inputs, sampler records, burnin, iteration count, seed and every chain's
+    ModelState (value + tune)."""
+    import json
+    d = dict(kind=np.array("ModelChains" if isinstance(c, ModelChains) else "Chains"), value=c.value, start=np.int64(c.first),
+             thin=np.int64(c.step), names=np.array(c.names), chains=np.array(c.chains, dtype=np.int64))
+    if isinstance(c, ModelChains):
+        m = c.model
+        seed = c.engine.seed if c.engine is not None else getattr(c, "_seed", 123)
+        d["model"] = np.array(json.dumps(dict(template=m.template, iter=int(m.iter), burnin=int(m.burnin), seed=int(seed),
+                                              samplers=[_jsonable([s.params, s.kind, s.desc]) for s in m.samplers])))
+        for k, v in m.inputs.items():
+            d["input_" + k] = np.asarray(v)
+        if c._nodelinks is not None:
+            d["nodelinks"] = c._nodelinks
+        if m.states:
+            d["state_value"] = np.stack([st.value for st in m.states])
+            d["state_tune"] = np.stack([st.tune for st in m.states])
+    with open(name, "wb") as f:
+        np.savez(f, **d)
+
+
+def read(name, T=None):
+    """read(name, T) (src/output/fileio.jl:3-7): TypeError when the stored object is not a T.  A ModelChains read back has no
+    live device handle; mcmc(mc, iters) builds one from the stored template, inputs, scheme and ModelStates and continues
+    the same chains (same Philox streams: the counter is the iteration number)."""
+    import json
+    z = np.load(name, allow_pickle=False)
+    kw = dict(start=int(z["start"]), thin=int(z["thin"]), names=[str(x) for x in z["names"]], chains=[int(k) for k in z["chains"]])
+    if str(z["kind"]) == "ModelChains":
+        md = json.loads(str(z["model"]))
+        m = Model(md["template"], iter=md["iter"], burnin=md["burnin"])
+        m.samplers = [Sampler(p, k, **_unjson(d)) for p, k, d in md["samplers"]]
+        setinputs(m, {k[len("input_"):]: z[k] for k in z.files if k.startswith("input_")})
+        if "state_value" in z.files:
+            m.states = [ModelState(v.copy(), t.copy()) for v, t in zip(z["state_value"], z["state_tune"])]
+        m.hasinits = bool(m.states)
+        c = ModelChains(z["value"], m, engine=None, nodelinks=z["nodelinks"] if "nodelinks" in z.files else None, **kw)
+        c._seed = md["seed"]
+    else:
+        c = Chains(z["value"], **kw)
+    if T is not None and not isinstance(c, T):
+        raise TypeError(f'read("{name}", {T.__name__}): stored object is a {type(c).__name__}')
+    return c
+
 
 class ModelChains(Chains):
     """src/Mamba.jl:179-185"""
 
-    def __init__(self, value, model, engine=None, **kw):
+    def __init__(self, value, model, engine=None, nodelinks=None, streaming=True, **kw):
         super().__init__(value, **kw)
         self.model = model
-        self.engine = engine
+        self.engine = engine          # live device handle (restart continues on it)
+        self._streaming = bool(streaming) and engine is not None   # its streaming moments describe exactly these draws
+        self._nodelinks = None if nodelinks is None else np.asarray(nodelinks, dtype=np.int32)
+
+    def _names2inds(self, names):     # names2inds(mc, nodekeys): modelchains.jl:24-40 — a node key selects all of its elements
+        if isinstance(names, str):
+            names = [names]
+        if isinstance(names, (list, tuple)) and names and all(isinstance(x, str) for x in names):
+            inds, missing = [], []
+            nodes = set(self.model.keys("dependent"))
+            for key in names:
+                if key in self.names:
+                    inds.append(self.names.index(key))
+                elif key in nodes:
+                    found = [j for j, nm in enumerate(self.names) if nm.startswith(key + "[")]
+                    if found:
+                        inds += found
+                    else:
+                        missing.append(key)
+                else:
+                    missing.append(key)
+            if missing:
+                raise ArgumentError("chain values are missing for nodes : " + ", ".join(missing))
+            return inds
+        return super()._names2inds(names)
+
+    def __getitem__(self, key):       # getindex(mc::ModelChains, …): modelchains.jl:19-22
+        value, kw = self._subset(key)
+        j = self._names2inds(key[1])
+        nl = None if self._nodelinks is None else self._nodelinks[j]
+        mc = ModelChains(value, self.model, engine=None, nodelinks=nl, **kw)
+        mc._seed = getattr(self, "_seed", self.engine.seed if self.engine is not None else 123)
+        return mc
+
+    def link_codes(self):             # link(c::ModelChains): node links for stochastic nodes, the heuristic for the rest
+        h = super().link_codes()
+        if self._nodelinks is None:
+            return h
+        return np.where(self._nodelinks >= 0, self._nodelinks, h).astype(np.int32)
 
 
 def mcmc(model, *args, burnin=0, thin=1, chains=1, verbose=False, seed=123, device=0, store=True):
@@ -286,7 +580,9 @@ def mcmc(model, *args, burnin=0, thin=1, chains=1, verbose=False, seed=123, devi
     eng.set_scheme(_block_descs(mm))
     eng.set_inits(x)
     mm.burnin = burnin
-    value = eng.run(iters, burnin=burnin, thin=thin, store=store)
+    value = eng.run(iters, burnin=burnin, thin=thin, store=store, out=store)
+    if value is None:   # store=False: only the streaming moments exist (what 1e6 chains allow); diagnostics use them
+        value = np.empty((0, eng.dims()[1], chains))
     return _wrap(mm, eng, value, burnin + thin, thin, chains)
 
 
@@ -295,7 +591,8 @@ def _wrap(mm, eng, value, start, thin, chains):
     mm.iter = it
     mm.states = [ModelState(vals[k].copy(), tune[k].copy()) for k in range(chains)]    # mcmc.jl:56,82
     mm.hasinits = True
-    return ModelChains(value, mm, engine=eng, start=start, thin=thin, names=eng.names(1), chains=list(range(1, chains + 1)))
+    return ModelChains(value, mm, engine=eng, nodelinks=eng.node_links(), start=start, thin=thin, names=eng.names(1),
+                       chains=list(range(1, chains + 1)))
 
 
 def _restart(mc, iters):
@@ -303,21 +600,34 @@ def _restart(mc, iters):
     if mc.last != (mc.model.iter // thin) * thin:
         raise ArgumentError("chain is missing its last iteration")          # mcmc.jl:5-6
     eng = mc.engine
+    streaming = eng is not None and getattr(mc, "_streaming", False)
+    if eng is None:   # a ModelChains that came back from read(): rebuild the device handle at the stored ModelStates
+        mm = mc.model
+        if not mm.states:
+            raise ArgumentError("chain is missing its last iteration")
+        eng = Engine(mm.template, len(mc.chains), seed=getattr(mc, "_seed", 123))
+        for k, v in mm.inputs.items():
+            eng.set_data(k, v)
+        eng.set_scheme(_block_descs(mm))
+        eng.set_state(np.stack([st.value for st in mm.states]), np.stack([st.tune for st in mm.states]), mm.iter)
     value = eng.run(iters, burnin=mc.model.burnin, thin=thin)
     mc2 = _wrap(mc.model, eng, value, mc.last + thin, thin, len(mc.chains))
-    return ModelChains(np.concatenate([mc.value, mc2.value], axis=0), mc2.model, engine=eng, start=mc.first, thin=thin,
-                       names=mc.names, chains=mc.chains)
+    return ModelChains(np.concatenate([mc.value, mc2.value], axis=0), mc2.model, engine=eng, nodelinks=mc2._nodelinks, streaming=streaming,
+                       start=mc.first, thin=thin, names=mc.names, chains=mc.chains)
 
 
 def gelmandiag(c, alpha=0.05, mpsrf=False, transform=False):
     """gelmandiag(c; alpha, mpsrf, transform): src/output/gelmandiag.jl:3-60 (PSRF and 97.5% columns, rounded to 3 dp)."""
     if len(c.chains) < 2:
         raise ArgumentError("less than 2 chains supplied to gelman diagnostic")   # gelmandiag.jl:6-7
-    if mpsrf:   # needs the p x p within / between covariances: computed on the materialised array (mcu_chains_gelman)
-        codes = c.engine.link_codes(transform) if (transform and getattr(c, "engine", None) is not None) else None
-        psrf = _chains_gelman(c.value, alpha, codes, True)
-        return np.round(psrf, 3), c.names + ["Multivariate"], ["PSRF", f"{100 * (1 - alpha / 2)}%"]
-    psrf = c.engine.gelman(alpha, transform)
+    eng = getattr(c, "engine", None) if getattr(c, "_streaming", False) else None
+    if mpsrf or eng is None:   # MPSRF needs the p x p within / between covariances; subsets / files have no device moments:
+        codes = None           # both are computed on the materialised array (mcu_chains_gelman)
+        if transform:
+            codes = eng.link_codes(True) if eng is not None else c.link_codes()
+        psrf = _chains_gelman(c.value, alpha, codes, bool(mpsrf))
+        return np.round(psrf, 3), c.names + (["Multivariate"] if mpsrf else []), ["PSRF", f"{100 * (1 - alpha / 2)}%"]
+    psrf = eng.gelman(alpha, transform)
     return np.round(psrf, 3), c.names, ["PSRF", f"{100 * (1 - alpha / 2)}%"]
 
 
@@ -373,6 +683,97 @@ def autocor(c, lags=(1, 5, 10, 50), relative=True):
     lg = np.ascontiguousarray(lags)
     _lib.lib().mcu_chains_autocor(_dp(v), n, p, m, lg.ctypes.data_as(C.POINTER(C.c_int64)), lags.size, _dp(out))
     return out, c.names, [f"Lag {x}" for x in lags]
+
+
+def cor(c):
+    """cor(c): src/output/stats.jl:14-16 — correlation matrix of the pooled draws (combine(c))."""
+    return np.corrcoef(c.combine(), rowvar=False), c.names, c.names
+
+
+def _device_for(mc):
+    """A live handle for model-based post-processing: the one the chain was sampled on, or one rebuilt from the stored model."""
+    if mc.engine is not None:
+        return mc.engine
+    mm = mc.model
+    eng = Engine(mm.template, 1, seed=getattr(mc, "_seed", 123))
+    for k, v in mm.inputs.items():
+        eng.set_data(k, v)
+    return eng
+
+
+def _factor_mask(mc, eng, nodekeys):
+    """nodekeys → (factor bitmask, state-element names the selected densities read).  The second item is what getsimkeys
+    (src/output/modelstats.jl:102-127) collects as relistkeys: the stochastic nodes on a path to the selected nodes."""
+    m = mc.model
+    nn, nf = eng.factor_counts()
+    pnodes = [n for n, _ in _TEMPLATES[m.template]["nodes"]]
+    outputs = _TEMPLATES[m.template]["outputs"]
+    if nodekeys is None:
+        nodekeys = pnodes + outputs                        # keys(mc.model, :stochastic): modelstats.jl:28-29
+    if isinstance(nodekeys, str):
+        nodekeys = [nodekeys]
+    mask, need = 0, set()
+    for key in nodekeys:
+        if key in pnodes:
+            f = pnodes.index(key)
+        elif key in outputs:
+            f = nn + outputs.index(key)
+        else:
+            raise KeyError(key)
+        mask |= 1 << f
+        par = eng.factor_parents(f) | ((1 << f) if f < nn else 0)
+        need |= {pnodes[q] for q in range(nn) if (par >> q) & 1}
+    return mask, [n for n in pnodes if n in need]
+
+
+def _states_from_chains(mc, eng, neednodes):
+    """Full state records [n * m x D] (chain-major rows, as vec(value[:, j, :])) with the needed nodes' elements taken from the
+    monitored columns; raises the reference's error when a needed node was not monitored (modelchains.jl:31-37)."""
+    snames = eng.names(0)
+    n, _, m = mc.value.shape
+    D = len(snames)
+    base = mc.model.states[0].value if mc.model.states else np.ones(D)
+    st = np.tile(np.asarray(base, dtype=float), (n * m, 1))
+    missing, cols = [], []
+    for node in neednodes:
+        el = [e for e, nm in enumerate(snames) if nm == node or nm.startswith(node + "[")]
+        if all(snames[e] in mc.names for e in el):
+            cols += [(e, mc.names.index(snames[e])) for e in el]
+        else:
+            missing.append(node)
+    if missing:
+        raise ArgumentError("chain values are missing for nodes : " + ", ".join(missing))
+    for e, j in cols:
+        st[:, e] = mc.value[:, j, :].T.reshape(-1)
+    return st, cols
+
+
+def logpdf(mc, nodekeys=None):
+    """logpdf(mc::ModelChains, nodekeys = keys(mc.model, :stochastic)): src/output/modelstats.jl:28-58 — the summed log density of
+    the named stochastic nodes at every kept draw → a one-column ModelChains named "logpdf".  Evaluated on the device."""
+    eng = _device_for(mc)
+    mask, need = _factor_mask(mc, eng, nodekeys)
+    st, _ = _states_from_chains(mc, eng, need)
+    n, _, m = mc.value.shape
+    lp = eng.logpdf_nodes(mask, st).reshape(m, n).T
+    out = ModelChains(lp[:, None, :], mc.model, engine=None, start=mc.first, thin=mc.step, names=["logpdf"], chains=mc.chains)
+    return out
+
+
+def dic(mc):
+    """dic(mc): src/output/modelstats.jl:3-13 → [[DIC_pD, pD], [DIC_pV, pV]] with rows ("pD", "pV") and columns
+    ("DIC", "Effective Parameters"); the deviance is -2 logpdf of the observed nodes (keys(m, :output))."""
+    eng = _device_for(mc)
+    outputs = _TEMPLATES[mc.model.template]["outputs"]
+    mask, need = _factor_mask(mc, eng, outputs)
+    st, cols = _states_from_chains(mc, eng, need)
+    Dev = -2.0 * eng.logpdf_nodes(mask, st)
+    mean_state = st[:1].copy()
+    for e, j in cols:
+        mean_state[0, e] = mc.value[:, j, :].mean()                       # logpdf(mc, mean, nodekeys): modelstats.jl:16-25
+    Dhat = -2.0 * eng.logpdf_nodes(mask, mean_state)[0]
+    p = np.array([Dev.mean() - Dhat, 0.5 * Dev.var(ddof=1)])
+    return np.column_stack([Dhat + 2.0 * p, p]), ["pD", "pV"], ["DIC", "Effective Parameters"]
 
 
 def changerate(c):
@@ -432,6 +833,16 @@ def describe(c, q=(0.025, 0.25, 0.5, 0.75, 0.975), etype="bm"):
 
 def summarystats(c, etype="bm", batch=100):
     """summarystats(c; etype): src/output/stats.jl:85-94 → [p × 5] Mean, SD, Naive SE, MCSE, ESS."""
-    if etype not in ("bm", "imse"):
+    if etype not in _ETYPE:
         raise ArgumentError(f"unsupported mcse method {etype}")                   # mcse.jl:3-8
-    return c.engine.summarystats(etype, batch), c.names, ["Mean", "SD", "Naive SE", "MCSE", "ESS"]
+    cols = ["Mean", "SD", "Naive SE", "MCSE", "ESS"]
+    eng = getattr(c, "engine", None) if getattr(c, "_streaming", False) else None
+    if c.value.shape[0] == 0:   # run with store=False: batch means of size 100 accumulated on the device
+        if eng is None or etype != "bm":
+            raise ArgumentError("no stored samples: only the streaming batch-means summary is available")
+        return eng.summary_streaming(), c.names, cols
+    v = _value_f(c); n, p, m = v.shape
+    out = np.empty((p, 5))
+    if _lib.lib().mcu_chains_summarystats(_dp(v), n, p, m, _ETYPE[etype], int(batch), _dp(out)) != 0:
+        raise ArgumentError(f"iterations are < {2 * batch} and batch size is > {n * m // 2}")     # mcse.jl:13-16
+    return out, c.names, cols

@@ -56,6 +56,7 @@ class Engine:
             raise MambaCudaError(rc, msg)
         self.template = tid
         self.n_chains = int(n_chains)
+        self.seed = int(seed)
         self.chain_offset = int(chain_offset)
         self._keep = []
 
@@ -164,6 +165,23 @@ class Engine:
         self._chk(self.L.mcu_logpdf(self.h, block, state.shape[0], _dp(state), _dp(x), _dp(lp)))
         return lp
 
+    def factor_counts(self):
+        nn, nf = C.c_int(), C.c_int()
+        self._chk(self.L.mcu_factor_counts(self.h, C.byref(nn), C.byref(nf)))
+        return nn.value, nf.value
+
+    def factor_parents(self, f):
+        m = C.c_uint32()
+        self._chk(self.L.mcu_factor_parents(self.h, int(f), C.byref(m)))
+        return m.value
+
+    def logpdf_nodes(self, mask, state):
+        """logpdf(mc, nodekeys): src/output/modelstats.jl:16-58 — sum of the selected node densities at each state record."""
+        state = _f64(np.atleast_2d(state))
+        lp = np.empty(state.shape[0])
+        self._chk(self.L.mcu_logpdf_nodes(self.h, int(mask), state.shape[0], _dp(state), _dp(lp)))
+        return lp
+
     def gradlogpdf(self, block, state, k, x=None, mode="analytic"):
         state = _f64(np.atleast_2d(state))
         x = _f64(None if x is None else np.atleast_2d(x))
@@ -194,6 +212,13 @@ class Engine:
         mm = _f64(minmax)
         self._chk(self.L.mcu_link_codes(self.h, int(bool(transform)), _dp(mm), codes))
         return np.array(list(codes), dtype=np.int32)
+
+    def node_links(self):
+        """Static part of link(c::ModelChains) (modelchains.jl:57-76) per monitored column: 0 identity, 1 log (the node's own
+        link), -1 = not a stochastic node: the data-dependent heuristic of chains.jl:237-246 applies."""
+        p = self.dims()[1]
+        codes = self.link_codes(True, minmax=np.tile([0.5, 0.6], (p, 1)))
+        return np.where(codes == 2, -1, codes).astype(np.int32)
 
     def moments(self, codes=None, center=None):
         p = self.dims()[1]

@@ -193,6 +193,25 @@ int orc_logpdf(void* h, int block, int64_t B, const double* state, const double*
     return 0;
   } catch (std::exception& e) { c->err = e.what(); return -1; }
 }
+// logpdf(mc, nodekeys) / logpdf(m, nodekeys) (src/output/modelstats.jl:16-58, src/model/simulation.jl:60-67 without the early exit):
+// sum of the selected stochastic nodes' log densities (constrained scale) at B states.  Bit f of `mask` selects the f-th
+// unobserved stochastic node in state-record order, bits from the number of such nodes upwards the observed ones (keys(m, :output)).
+int orc_logpdf_nodes(void* h, uint32_t mask, int64_t B, const double* state, double* lp) {
+  Ctx* c = (Ctx*)h;
+  try {
+    Model m = c->model;
+    const int D = m.state_dim();
+    std::vector<int> order = m.state_nodes();
+    for (size_t i = 0; i < m.nodes.size(); ++i) if (m.nodes[i].stochastic && m.nodes[i].observed) order.push_back((int)i);
+    for (int64_t i = 0; i < B; ++i) {
+      m.setinits(state + i * D);
+      double s = 0.0;
+      for (size_t f = 0; f < order.size(); ++f) if ((mask >> f) & 1u) s += m.node_logpdf(order[f], false);
+      lp[i] = s;
+    }
+    return 0;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
 int orc_gradlogpdf(void* h, int block, int grad_mode, int64_t B, const double* state, const double* x, double* lp, double* g) {
   Ctx* c = (Ctx*)h;
   try {

@@ -75,6 +75,7 @@ def lib():
         L.orc_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_names.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
         L.orc_logpdf.argtypes = [C.c_void_p, C.c_int, C.c_int64, dp, dp, dp]
+        L.orc_logpdf_nodes.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, dp, dp]
         L.orc_gradlogpdf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, dp, dp, dp, dp]
         L.orc_unlist.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.orc_tune_size.restype = C.c_int64
@@ -154,6 +155,12 @@ class Oracle:
         state = _f64(np.atleast_2d(state)); x = _f64(None if x is None else np.atleast_2d(x))
         lp = np.empty(state.shape[0])
         self._chk(self.L.orc_logpdf(self.h, block, state.shape[0], _dp(state), _dp(x), _dp(lp)))
+        return lp
+
+    def logpdf_nodes(self, mask, state):
+        state = _f64(np.atleast_2d(state))
+        lp = np.empty(state.shape[0])
+        self._chk(self.L.orc_logpdf_nodes(self.h, C.c_uint32(int(mask)), C.c_int64(state.shape[0]), _dp(state), _dp(lp)))
         return lp
 
     def gradlogpdf(self, block, state, x=None, mode=0):

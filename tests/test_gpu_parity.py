@@ -344,9 +344,41 @@ def test_surgical_posterior_matches_published_table(oracle):
     for nm, (mean, mcse_ref, sd) in ref.items():
         j = names.index(nm)
         assert abs(summ[j, 0] - mean) < 3 * np.hypot(mcse_ref, summ[j, 3]) + 0.02 * sd, (nm, summ[j, 0], mean)
-    # pop_mean and p[i] are Logical columns in (0, 1): link(c) would take their logit, which the streaming moments do not carry
-    # (raw and log scale only) — the untransformed PSRF is used here, the transformed one needs stored samples
+    # pop_mean and p[i] are Logical columns in (0, 1): link(c) takes their logit (chains.jl:241-243)
     assert (eng.gelman(0.05, False)[:, 0] < 1.05).all()
+    assert (eng.gelman(0.05, True)[:, 0] < 1.05).all()
+
+
+def test_gelman_logit_link_for_logical_columns_in_the_unit_interval(oracle):
+    # link(c::ModelChains) (modelchains.jl:57-76): mu identity, s2 log, pop_mean and p[1..12] Logical with every value in (0, 1) -> logit
+    g, o, eng, orc = run_pair(oracle, "surgical_amwg", 8, 700, 100, 2)
+    out_g = g[0]
+    codes = eng.link_codes(True)
+    names = eng.names(1)
+    assert codes[names.index("s2")] == 1 and codes[names.index("mu")] == 0 and codes[names.index("pop_mean")] == 2 and codes[names.index("p[3]")] == 2
+    psrf_g = eng.gelman(0.05, True)
+    psrf_o = oracle.gelmandiag(out_g, 0.05, [{0: 0, 1: 1, 2: -1}[int(c)] for c in codes])
+    np.testing.assert_allclose(psrf_g, psrf_o, rtol=1e-7)
+    # the same through the host-array entry point on the materialised draws
+    from mambacuda import api
+    psrf_h = api._chains_gelman(out_g, 0.05, codes, False)
+    np.testing.assert_allclose(psrf_h, psrf_o, rtol=1e-7)
+
+
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice"])
+def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
+    # logpdf(mc, nodekeys) (modelstats.jl:16-58): observed nodes only (the deviance of dic), every stochastic node, one parameter node
+    eng, orc, inits = make_pair(oracle, tpl_scheme, 4)
+    tpl = helpers.scheme(tpl_scheme)[0]
+    st = random_states(inits, 24, np.random.default_rng(8), POS[tpl])
+    nn, nf = eng.factor_counts()
+    assert nf == nn + 1
+    for mask in (1 << nn, (1 << nf) - 1, 1, 1 << (nn - 1)):
+        np.testing.assert_allclose(eng.logpdf_nodes(mask, st), orc.logpdf_nodes(mask, st), rtol=RTOL_LP, atol=1e-12)
+    # the block density is the sum of the block's own node densities and its targets': for a block holding every parameter node
+    # this is the joint (simulation.jl:77-90)
+    joint = eng.logpdf_nodes((1 << nf) - 1, st)
+    assert np.isfinite(joint).all()
 
 
 def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):

@@ -282,3 +282,29 @@ def test_engine_bookkeeping(oracle):
     np.testing.assert_array_equal(a[:, :, 2:], b)
     c, _, _ = o.run(4, inits, 30, seed=9, nthreads=3)
     np.testing.assert_array_equal(a, c)
+
+
+def test_node_logpdf_is_the_sum_of_scipy_densities(oracle):
+    """logpdf(m, nodekeys) (src/model/simulation.jl:60-67, used by dic / logpdf(mc, ...) in src/output/modelstats.jl): the observed
+    node of the line model (y ~ MvNormal(xmat * beta, sqrt(s2)), doc/tutorial/line.jl:6-12) and of pumps (y[i] ~ Poisson(theta[i] t[i]),
+    doc/examples/pumps.jl:14-20), and every node of pumps, against scipy.stats."""
+    import helpers
+    import scipy.stats as st
+    rng = np.random.default_rng(11)
+    tpl, blocks, inits = helpers.scheme("line_amwg_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    S = np.column_stack([rng.normal(size=(6, 2)), rng.gamma(2.0, 1.0, size=6)])
+    x = np.arange(1.0, 6.0); y = np.array([1.0, 3, 3, 3, 5])
+    want_y = np.array([st.norm.logpdf(y, s[0] + s[1] * x, np.sqrt(s[2])).sum() for s in S])
+    np.testing.assert_allclose(o.logpdf_nodes(0b100, S), want_y, rtol=1e-12)
+    want_all = want_y + np.array([st.norm.logpdf(s[:2], 0, np.sqrt(1000.0)).sum() + st.invgamma.logpdf(s[2], 0.001, scale=0.001) for s in S])
+    np.testing.assert_allclose(o.logpdf_nodes(0b111, S), want_all, rtol=1e-11)
+    tpl, blocks, inits = helpers.scheme("pumps_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    yp = np.array([5, 1, 5, 14, 3, 19, 1, 1, 4, 22.0]); t = np.array([94.3, 15.7, 62.9, 126, 5.24, 31.4, 1.05, 1.05, 2.1, 10.5])   # pumps.jl:4-9
+    S = np.column_stack([rng.gamma(2.0, 0.5, size=5), rng.gamma(2.0, 0.5, size=5), rng.gamma(2.0, 0.3, size=(5, 10))])
+    want_y = np.array([st.poisson.logpmf(yp, s[2:] * t).sum() for s in S])
+    np.testing.assert_allclose(o.logpdf_nodes(0b1000, S), want_y, rtol=1e-12)
+    want_all = want_y + np.array([st.expon.logpdf(s[0], scale=1.0) + st.gamma.logpdf(s[1], 0.1, scale=1.0)
+                                  + st.gamma.logpdf(s[2:], s[0], scale=1.0 / s[1]).sum() for s in S])
+    np.testing.assert_allclose(o.logpdf_nodes(0b1111, S), want_all, rtol=1e-11)
