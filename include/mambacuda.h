@@ -177,6 +177,11 @@ int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const do
 int mcu_factor_counts(mcu_handle h, int* n_param_nodes, int* n_factors);
 int mcu_factor_parents(mcu_handle h, int factor, uint32_t* parent_nodes);
 int mcu_logpdf_nodes(mcu_handle h, uint32_t factor_mask, int64_t B, const double* state, double* lp);
+/* predict(mc::ModelChains, nodekeys = keys(m, :output))  src/output/modelstats.jl:63-96: one draw from the distribution of every
+ * observed node element at each of B full states [B × D] → out [B × n_out] (pass out = NULL to query n_out, the length of the
+ * observed node).  Philox stream (seed of the handle, chain = stream_id, iteration = record index, block 0, kind 15): a Normal
+ * element takes one normal draw, a Binomial / Poisson / Bernoulli element one uniform (CDF inversion by sequential search).   */
+int mcu_predict(mcu_handle h, int64_t B, const double* state, uint32_t stream_id, double* out, int64_t* n_out);
 /* logpdfgrad!(block, x, dtype)  src/samplers/sampler.jl:106-111 (+ analytic mode).  g [B × k]. */
 int mcu_gradlogpdf(mcu_handle h, int block, int grad_mode, int64_t B, const double* state,
                    const double* x, double* lp, double* g);

@@ -948,6 +948,33 @@ int mcu_logpdf_nodes(mcu_handle h, uint32_t factor_mask, int64_t B, const double
   return MCU_OK;
 }
 
+int mcu_predict(mcu_handle h, int64_t B, const double* state, uint32_t stream_id, double* out, int64_t* n_out) {
+  if (!h) return MCU_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc = upload_inputs(h); if (rc) return rc;
+  int L = 0;
+  MCU_DISPATCH(h, L = launch_predict(Host<M>::data(h), 0, h->D, nullptr, 0ull, 0u, nullptr, h->stream));
+  if (n_out) *n_out = L;
+  if (!out) return MCU_OK;   // size query
+  if (!state || B < 1) return fail(h, MCU_ERR_ARG, "bad argument");
+  const int D = h->D;
+  double *d_rec = nullptr, *d_state = nullptr, *d_out = nullptr, *d_tmp = nullptr;
+  CK(cudaMalloc(&d_rec, sizeof(double) * B * D));
+  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
+  CK(cudaMalloc(&d_out, sizeof(double) * B * L));
+  CK(cudaMalloc(&d_tmp, sizeof(double) * B * L));
+  CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
+  launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
+  MCU_DISPATCH(h, launch_predict(Host<M>::data(h), B, D, d_state, h->seed, stream_id, d_out, h->stream));
+  h->launches++;
+  launch_soa_to_records(d_out, d_tmp, B, L, h->stream); h->launches++;
+  CK(cudaMemcpyAsync(out, d_tmp, sizeof(double) * B * L, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_out); cudaFree(d_tmp);
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+
 int mcu_logpdf(mcu_handle h, int block, int64_t B, const double* state, const double* x, double* lp) {
   if (!lp) return h ? fail(h, MCU_ERR_ARG, "lp is NULL") : MCU_ERR_ARG;
   return density_call(h, block, 0, B, state, x, lp, nullptr);

@@ -221,6 +221,47 @@ __global__ void logpdf_kernel(typename M::Data data, const DevBlock* blocks, int
 }
 
 
+// rand(m[key]) for an observed node element (predict, src/output/modelstats.jl:63-96).  The reference calls Distributions.rand on
+// the global RNG; here a Normal takes one draw of the normal stream, the discrete families ONE uniform and invert the CDF by
+// sequential search from 0 (pmf recurrences; exact in the same arithmetic as the oracle's, so the integer draws coincide).
+static MCU_NOINL double rand_out(int kind, double a, double b, Draws& rng) {
+  if (kind == OUT_NORMAL) return a + b * rng.normal();
+  const double u = rng.uniform();
+  if (kind == OUT_BERNOULLI) return u < a ? 1.0 : 0.0;
+  if (kind == OUT_BINOMIAL) {
+    const double n = a, p = b, q = 1.0 - p;
+    if (!(p > 0.0)) return 0.0;
+    if (!(q > 0.0)) return n;
+    const double ratio = p / q;
+    double pmf = exp(n * log(q)), cdf = pmf, k = 0.0;
+    while (u >= cdf && k < n) { pmf *= (n - k) / (k + 1.0) * ratio; k += 1.0; cdf += pmf; }
+    return k;
+  }
+  double pmf = exp(-a), cdf = pmf, k = 0.0;   // Poisson(a)
+  while (u >= cdf && k < 100000.0) { k += 1.0; pmf *= a / k; cdf += pmf; }
+  return k;
+}
+
+// predict(mc, nodekeys): one draw of every observed element at each of B state records; stream = (seed, chain = stream_id,
+// iteration = record index, block 0, kind 15), element i takes the next draw(s) of the record's stream.  out [L][B].
+template <class M>
+__global__ void predict_kernel(typename M::Data data, long long B, int D, const double* state, unsigned long long seed, unsigned stream_id,
+                               double* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B) return;
+  double s[M::D];
+  for (int e = 0; e < D; ++e) s[e] = state[(size_t)e * B + c];
+  Draws rng;
+  rng.k0 = (uint32_t)seed; rng.k1 = (uint32_t)(seed >> 32); rng.chain = stream_id; rng.ext = nullptr; rng.ext_pos = nullptr; rng.ext_n = 0;
+  rng.seek((uint32_t)c, 0, 15);
+  const int L = M::out_len(data);
+  for (int i = 0; i < L; ++i) {
+    double a, b;
+    const int kind = M::out_dist(data, s, i, a, b);
+    out[(size_t)i * B + c] = rand_out(kind, a, b, rng);
+  }
+}
+
 // logpdf(mc, nodekeys) (src/output/modelstats.jl:16-58): sum of the selected factors (node densities on the constrained scale) at B
 // states, one per thread; bit f of `mask` = factor f (0 .. NN-1 parameter nodes, NN .. NF-1 observed nodes, i.e. keys(m, :output)).
 template <class M>

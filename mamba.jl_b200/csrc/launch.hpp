@@ -14,7 +14,9 @@ typedef GlmModel<kGlmDMax> GlmM;
   void launch_run(const M::Data& d, const RunArgs& a, cudaStream_t st);                                      \
   void launch_logpdf(const M::Data& d, const DevBlock* blocks, int block, long long B, int D,                \
                      const double* state, const double* x, double* lp, double* g, int grad_mode, cudaStream_t st);   \
-  void launch_factors(const M::Data& d, unsigned mask, long long B, int D, const double* state, double* lp, cudaStream_t st);
+  void launch_factors(const M::Data& d, unsigned mask, long long B, int D, const double* state, double* lp, cudaStream_t st); \
+  int launch_predict(const M::Data& d, long long B, int D, const double* state, unsigned long long seed, unsigned stream_id,   \
+                     double* out, cudaStream_t st);
 MCU_DECLARE_TPL(LineModel)
 MCU_DECLARE_TPL(SeedsModel)
 MCU_DECLARE_TPL(RatsModel)
@@ -43,6 +45,11 @@ MCU_DECLARE_TPL(DyesModel)
   }                                                                                                          \
   void launch_factors(const M::Data& d, unsigned mask, long long B, int D, const double* state, double* lp, cudaStream_t st) { \
     factors_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d, mask, B, D, state, lp);               \
+  }                                                                                                          \
+  int launch_predict(const M::Data& d, long long B, int D, const double* state, unsigned long long seed, unsigned stream_id,   \
+                     double* out, cudaStream_t st) {                                                         \
+    if (out) predict_kernel<M><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d, B, D, state, seed, stream_id, out); \
+    return M::out_len(d);                                                                                    \
   }
 
 // misc kernels (kern_misc.cu)

@@ -34,6 +34,7 @@ namespace mcu {
 
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 constexpr int LINK_IDENT = 0, LINK_LOG = 1, LINK_HEUR = -1;
+constexpr int OUT_NORMAL = 0, OUT_BINOMIAL = 1, OUT_POISSON = 2, OUT_BERNOULLI = 3;
 
 MCU_D double neg_inf() { return -CUDART_INF; }
 
@@ -139,6 +140,10 @@ struct LineModel {
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
+  // distribution of observed element i given the state (predict, src/output/modelstats.jl:63-96):
+  // returns OUT_NORMAL (a = mean, b = sd), OUT_BINOMIAL (a = n, b = p), OUT_POISSON (a = rate) or OUT_BERNOULLI (a = p)
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = 1.0 * s[0] + d.x[i] * s[1]; b = sqrt(s[2]); return OUT_NORMAL; }
 };
 
 // =============================================================================== seeds
@@ -189,6 +194,8 @@ struct SeedsModel {
   MCU_D static void monitor(const Data&, const double* s, double* out) {
     for (int j = 0; j < 5; ++j) out[j] = s[j];
   }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (exp(-eta(d, s, i)) + 1.0); return OUT_BINOMIAL; }
 };
 
 // =============================================================================== rats
@@ -247,6 +254,8 @@ struct RatsModel {
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
     out[0] = s[1]; out[1] = s[0] - d.xbar * s[1]; out[2] = s[4];   // alpha0 = mu_alpha - xbar * mu_beta (rats.jl:64-66)
   }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int k, double& a, double& b) { const int i = d.rat[k]; a = s[5 + i] + s[35 + i] * d.Xm[k]; b = sqrt(s[4]); return OUT_NORMAL; }
 };
 
 // =============================================================================== pumps
@@ -306,6 +315,8 @@ struct PumpsModel {
       s[1] = rgamma(0.1 + (double)d.N * s[0], rng) / (1.0 + sth);
     }
   }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = s[2 + i] * d.t[i]; b = 0.0; return OUT_POISSON; }
 };
 
 // =============================================================================== surgical
@@ -353,6 +364,8 @@ struct SurgicalModel {
     out[0] = s[0]; out[1] = 1.0 / (exp(-s[0]) + 1.0); out[2] = s[1];   // pop_mean = invlogit(mu): surgical.jl:34-36
     for (int i = 0; i < d.N; ++i) out[3 + i] = 1.0 / (exp(-s[2 + i]) + 1.0);   // p = invlogit(b): surgical.jl:19-21
   }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (exp(-s[2 + i]) + 1.0); return OUT_BINOMIAL; }
 };
 
 // =============================================================================== dyes
@@ -393,6 +406,8 @@ struct DyesModel {
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 9; ++j) out[j] = s[j]; }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int k, double& a, double& b) { a = s[3 + d.batch[k]]; b = sqrt(s[2]); return OUT_NORMAL; }
 };
 
 // =============================================================================== glm (CUDA-core form)
@@ -434,6 +449,13 @@ struct GlmModel {
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) { for (int j = 0; j < d.d; ++j) out[j] = s[j]; }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) {
+    double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
+    if (d.family == 1) { a = exp(eta); b = 0.0; return OUT_POISSON; }
+    if (d.family == 2) { a = eta; b = d.sigma; return OUT_NORMAL; }
+    a = 1.0 / (exp(-eta) + 1.0); b = 0.0; return OUT_BERNOULLI;
+  }
 };
 
 }  // namespace mcu

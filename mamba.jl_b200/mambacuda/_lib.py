@@ -48,7 +48,7 @@ SYMBOLS = [
     "mcu_summary_from_sums", "mcu_summary_streaming", "mcu_set_rng_mode", "mcu_device_count",
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
     "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
-    "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery", "mcu_chains_summarystats", "mcu_factor_counts", "mcu_factor_parents", "mcu_logpdf_nodes",
+    "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery", "mcu_chains_summarystats", "mcu_factor_counts", "mcu_factor_parents", "mcu_logpdf_nodes", "mcu_predict",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
     L.mcu_factor_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.mcu_factor_parents.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
     L.mcu_logpdf_nodes.argtypes = [C.c_void_p, C.c_uint32, i64, dp, dp]
+    L.mcu_predict.argtypes = [C.c_void_p, i64, dp, C.c_uint32, dp, C.POINTER(i64)]
     L.mcu_chains_summarystats.argtypes = [dp, i64, C.c_int, i64, C.c_int, C.c_int, dp]
     _lib = L
     return L

@@ -776,6 +776,27 @@ def dic(mc):
     return np.column_stack([Dhat + 2.0 * p, p]), ["pD", "pV"], ["DIC", "Effective Parameters"]
 
 
+def predict(mc, nodekeys=None, stream_id=0):
+    """predict(mc, nodekeys = keys(m, :output)): src/output/modelstats.jl:61-96 — posterior predictive draws of the observed nodes,
+    one per kept draw and chain → ModelChains named y[1], y[2], …  Drawn on the device."""
+    outputs = _TEMPLATES[mc.model.template]["outputs"]
+    if nodekeys is None:
+        nodekeys = outputs
+    if isinstance(nodekeys, str):
+        nodekeys = [nodekeys]
+    if not all(k in outputs for k in nodekeys):
+        raise ArgumentError("nodekeys are not all observed Stochastic nodess : " + ", ".join(outputs))     # modelstats.jl:69-73 (sic)
+    eng = _device_for(mc)
+    _, need = _factor_mask(mc, eng, nodekeys)
+    st, _ = _states_from_chains(mc, eng, need)
+    n, _, m = mc.value.shape
+    draws = eng.predict(st, stream_id)                                   # [n * m x L], rows chain-major
+    L = draws.shape[1]
+    value = draws.reshape(m, n, L).transpose(1, 2, 0)
+    names = [f"{nodekeys[0]}[{i + 1}]" for i in range(L)]
+    return ModelChains(value, mc.model, engine=None, start=mc.first, thin=mc.step, names=names, chains=mc.chains)
+
+
 def changerate(c):
     """changerate(c): src/output/stats.jl:19-39 → [p + 1] rounded to 3 dp, last row "Multivariate"."""
     v = _value_f(c); n, p, m = v.shape

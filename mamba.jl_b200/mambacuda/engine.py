@@ -182,6 +182,15 @@ class Engine:
         self._chk(self.L.mcu_logpdf_nodes(self.h, int(mask), state.shape[0], _dp(state), _dp(lp)))
         return lp
 
+    def predict(self, state, stream_id=0):
+        """predict(mc): src/output/modelstats.jl:63-96 — one draw of the observed node at each state record → [B × len(y)]."""
+        state = _f64(np.atleast_2d(state))
+        n = C.c_int64()
+        self._chk(self.L.mcu_predict(self.h, 0, None, 0, None, C.byref(n)))
+        out = np.empty((state.shape[0], n.value))
+        self._chk(self.L.mcu_predict(self.h, state.shape[0], _dp(state), int(stream_id), _dp(out), C.byref(n)))
+        return out
+
     def gradlogpdf(self, block, state, k, x=None, mode="analytic"):
         state = _f64(np.atleast_2d(state))
         x = _f64(None if x is None else np.atleast_2d(x))

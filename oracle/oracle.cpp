@@ -212,6 +212,58 @@ int orc_logpdf_nodes(void* h, uint32_t mask, int64_t B, const double* state, dou
     return 0;
   } catch (std::exception& e) { c->err = e.what(); return -1; }
 }
+// predict(mc, nodekeys = keys(m, :output)) (src/output/modelstats.jl:63-96): rand(m[key]) for every element of the observed nodes at
+// B states.  Engine RNG contract for this call: stream (seed, chain = stream_id, iteration = record index, block 0, kind 15); a Normal
+// element takes one normal draw, a discrete element one uniform and inverts the CDF by sequential search from 0.
+static double rand_udist(const UDist& d, Rng& rng) {
+  if (d.k == D_NORMAL) return d.a + d.b * rng.normal();
+  const double u = rng.uniform();
+  if (d.k == D_BERNOULLI) return u < d.a ? 1.0 : 0.0;
+  if (d.k == D_BINOMIAL) {
+    const double n = d.a, p = d.b, q = 1.0 - p;
+    if (!(p > 0.0)) return 0.0;
+    if (!(q > 0.0)) return n;
+    const double ratio = p / q;
+    double pmf = std::exp(n * std::log(q)), cdf = pmf, k = 0.0;
+    while (u >= cdf && k < n) { pmf *= (n - k) / (k + 1.0) * ratio; k += 1.0; cdf += pmf; }
+    return k;
+  }
+  if (d.k == D_POISSON) {
+    double pmf = std::exp(-d.a), cdf = pmf, k = 0.0;
+    while (u >= cdf && k < 100000.0) { k += 1.0; pmf *= d.a / k; cdf += pmf; }
+    return k;
+  }
+  throw std::runtime_error("predict: no sampler for this observed distribution");
+}
+int orc_predict(void* h, uint64_t seed, uint32_t stream_id, int64_t B, const double* state, double* out, int64_t* n_out) {
+  Ctx* c = (Ctx*)h;
+  try {
+    Model m = c->model;
+    const int D = m.state_dim();
+    std::vector<int> obs;
+    int64_t L = 0;
+    for (size_t i = 0; i < m.nodes.size(); ++i) if (m.nodes[i].stochastic && m.nodes[i].observed) { obs.push_back((int)i); L += m.nodes[i].len; }
+    if (n_out) *n_out = L;
+    if (!out) return 0;
+    for (int64_t i = 0; i < B; ++i) {
+      m.setinits(state + i * D);
+      PhiloxRng rng(seed, stream_id); rng.seek((uint32_t)i, 0, 15);
+      int64_t o = 0;
+      for (int q : obs) {
+        const Node& n = m.nodes[q];
+        for (int e = 0; e < n.len; ++e) {
+          double v;
+          if (n.distr.form == Distr::UNI) v = rand_udist(n.distr.u, rng);
+          else if (n.distr.form == Distr::UNI_ARRAY) v = rand_udist(n.distr.arr[e], rng);
+          else if (n.distr.form == Distr::MVNORMAL_ISO) v = n.distr.mu[e] + n.distr.sigma * rng.normal();
+          else throw std::runtime_error("predict: node without a distribution");
+          out[i * L + o++] = v;
+        }
+      }
+    }
+    return 0;
+  } catch (std::exception& e) { c->err = e.what(); return -1; }
+}
 int orc_gradlogpdf(void* h, int block, int grad_mode, int64_t B, const double* state, const double* x, double* lp, double* g) {
   Ctx* c = (Ctx*)h;
   try {

@@ -76,6 +76,7 @@ def lib():
         L.orc_names.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
         L.orc_logpdf.argtypes = [C.c_void_p, C.c_int, C.c_int64, dp, dp, dp]
         L.orc_logpdf_nodes.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, dp, dp]
+        L.orc_predict.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, dp, dp, C.POINTER(C.c_int64)]
         L.orc_gradlogpdf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, dp, dp, dp, dp]
         L.orc_unlist.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.orc_tune_size.restype = C.c_int64
@@ -162,6 +163,14 @@ class Oracle:
         lp = np.empty(state.shape[0])
         self._chk(self.L.orc_logpdf_nodes(self.h, C.c_uint32(int(mask)), C.c_int64(state.shape[0]), _dp(state), _dp(lp)))
         return lp
+
+    def predict(self, state, seed, stream_id=0):
+        state = _f64(np.atleast_2d(state))
+        n = C.c_int64()
+        self._chk(self.L.orc_predict(self.h, seed, stream_id, 0, None, None, C.byref(n)))
+        out = np.empty((state.shape[0], n.value))
+        self._chk(self.L.orc_predict(self.h, seed, stream_id, state.shape[0], _dp(state), _dp(out), C.byref(n)))
+        return out
 
     def gradlogpdf(self, block, state, x=None, mode=0):
         state = _f64(np.atleast_2d(state)); x = _f64(None if x is None else np.atleast_2d(x))

@@ -381,6 +381,41 @@ def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     assert np.isfinite(joint).all()
 
 
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice"])
+def test_predict_matches_oracle(oracle, tpl_scheme):
+    # predict(mc) (modelstats.jl:63-96): rand of the observed node at each state, same Philox stream on both sides
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme(tpl_scheme)
+    eng = Engine(tpl, 4, seed=31); eng.set_scheme(blocks)
+    orc = oracle.Oracle(tpl); orc.set_scheme([helpers.oracle_block(b) for b in blocks])
+    st = random_states(inits, 40, np.random.default_rng(9), POS[tpl])
+    g = eng.predict(st, stream_id=5); o = orc.predict(st, 31, stream_id=5)
+    assert g.shape == o.shape and g.shape[0] == 40
+    if tpl in ("seeds", "pumps", "surgical"):    # counts: identical integers
+        assert (g == np.round(g)).all() and (g >= 0).all()
+        assert (g == o).mean() > 0.999           # a uniform within rounding of a CDF step may fall on either side
+    else:
+        np.testing.assert_allclose(g, o, rtol=1e-10, atol=1e-10)
+    assert not np.array_equal(g, eng.predict(st, stream_id=6))
+
+
+def test_predict_glm_families():
+    # the three GLM families draw Bernoulli / Poisson / Normal observations with the right means
+    from mambacuda.engine import Engine
+    rng = np.random.default_rng(3)
+    X = np.column_stack([np.ones(400), rng.normal(size=(400, 2))]); beta = np.array([0.3, -0.5, 0.8])
+    eta = X @ beta
+    for family, mean in ((0, 1 / (1 + np.exp(-eta))), (1, np.exp(eta)), (2, eta)):
+        eng = Engine("glm", 2, seed=1); eng.set_data("X", X); eng.set_data("y", np.zeros(400))
+        eng.set_data("family", np.array([float(family)])); eng.set_data("sigma", np.array([0.5]))
+        d = eng.predict(np.tile(beta, (2000, 1)))
+        assert d.shape == (2000, 400)
+        sd = np.sqrt(mean * (1 - mean)) if family == 0 else np.sqrt(mean) if family == 1 else np.full(400, 0.5)
+        assert (np.abs(d.mean(axis=0) - mean) < 5 * sd / np.sqrt(2000)).all()
+        if family == 2:
+            np.testing.assert_allclose(d.std(axis=0), 0.5, rtol=0.1)
+
+
 def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):
     from mambacuda.engine import Engine
     from mambacuda._lib import MambaCudaError

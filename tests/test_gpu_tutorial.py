@@ -81,6 +81,20 @@ def test_tutorial_deviance_matches_the_closed_form(sim1):
     np.testing.assert_allclose(lp.value[:, 0, :], want, rtol=1e-12)
 
 
+def test_posterior_predictive_draws(sim1):
+    # predict(sim1) (src/output/modelstats.jl:63-96): y_rep[i] ~ Normal(beta1 + beta2 x_i, sqrt(s2)) at every kept draw
+    from mambacuda import api
+    pp = api.predict(sim1)
+    assert pp.names == ["y[1]", "y[2]", "y[3]", "y[4]", "y[5]"] and pp.value.shape == (4875, 5, 3) and pp.header() == sim1.header()
+    x = np.array(LINE["x"], float)
+    mu = sim1.value[:, 0, :][:, None, :] + sim1.value[:, 1, :][:, None, :] * x[None, :, None]
+    z = (pp.value - mu) / np.sqrt(sim1.value[:, 2, :])[:, None, :]          # standard normal if the draws are right
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert np.abs(np.median(pp.value, axis=(0, 2)) - (0.6 + 0.8 * x)).max() < 0.15   # posterior predictive centre = fitted line
+    with pytest.raises(api.ArgumentError, match="nodekeys are not all observed"):
+        api.predict(sim1, "beta")
+
+
 def test_tutorial_subsetting(sim1):
     from mambacuda import api
     sim = sim1[range(1000, 5001), ["beta[1]", "beta[2]"], None]              # line.jl:143, tutorial.rst:509-512
