@@ -56,7 +56,9 @@ enum {
   MCU_TPL_GLM_LOGIT = 4, /* synthetic GLM family (inputs X, y, family, sigma)  nodes: beta[d]  (no reference file; closest doc/examples/seeds.jl) */
   MCU_TPL_SURGICAL = 5,  /* doc/examples/surgical.jl:11-43 nodes: mu, s2, b[12]; monitored mu, pop_mean, s2, p[12] */
   MCU_TPL_DYES = 6,      /* doc/examples/dyes.jl:22-47     nodes: s2_between, theta, s2_within, mu[6] (all monitored) */
-  MCU_N_TEMPLATES = 7
+  MCU_TPL_SALM = 7,      /* doc/examples/salm.jl:16-53     nodes: s2, gamma, beta, alpha, lambda[3x6]; monitored s2, gamma, beta, alpha */
+  MCU_TPL_EQUIV = 8,     /* doc/examples/equiv.jl:25-75    nodes: s2_2, s2_1, pi, phi, mu, delta[10x2]; monitored s2_2, s2_1, pi, phi, theta, equiv, mu */
+  MCU_N_TEMPLATES = 9
 };
 
 /* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */

@@ -146,6 +146,14 @@ void default_inputs(mcu_ctx* h) {
       in["batch"] = batch;
       break;
     }
+    case MCU_TPL_SALM:   // doc/examples/salm.jl:4-11 (y is reshape(..., 3, 6): column-major, plate fastest)
+      in["y"] = {15, 21, 29, 16, 18, 21, 16, 26, 33, 27, 41, 60, 33, 38, 41, 20, 27, 42};
+      in["x"] = {0, 10, 33, 100, 333, 1000};
+      break;
+    case MCU_TPL_EQUIV:  // doc/examples/equiv.jl:4-17 (y is a 10 x 2 matrix literal: flattened column-major, subject fastest)
+      in["group"] = {1, 1, 2, 2, 2, 1, 1, 1, 2, 2};
+      in["y"] = {1.40, 1.64, 1.44, 1.36, 1.65, 1.08, 1.09, 1.25, 1.25, 1.30, 1.65, 1.57, 1.58, 1.68, 1.69, 1.31, 1.43, 1.44, 1.39, 1.52};
+      break;
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -165,7 +173,7 @@ int upload_inputs(mcu_ctx* h) {
   if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
   auto in = h->inputs;   // derived arrays
   if (h->tpl == MCU_TPL_SEEDS || h->tpl == MCU_TPL_SURGICAL) in["lc"] = lchoose_vec(in["n"], in["r"]);
-  if (h->tpl == MCU_TPL_PUMPS) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
+  if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
     if (kv.second.empty()) continue;
     double* p = nullptr;
@@ -202,6 +210,12 @@ template <> struct Host<RatsModel> {
 template <> struct Host<DyesModel> {
   static DyesModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_rat, (int)h->inputs["y"].size()}; }
 };
+template <> struct Host<SalmModel> {
+  static SalmModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["x"], h->d_inputs["lgy1"], (int)h->inputs["y"].size()}; }
+};
+template <> struct Host<EquivModel> {
+  static EquivModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["group"], (int)h->inputs["group"].size()}; }
+};
 template <> struct Host<SurgicalModel> {
   static SurgicalModel::Data data(mcu_ctx* h) { return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["lc"], (int)h->inputs["r"].size()}; }
 };
@@ -223,6 +237,8 @@ template <> struct Host<GlmM> {
     case MCU_TPL_GLM_LOGIT: { typedef GlmM M; BODY; break; }                       \
     case MCU_TPL_SURGICAL: { typedef SurgicalModel M; BODY; break; }               \
     case MCU_TPL_DYES: { typedef DyesModel M; BODY; break; }                       \
+    case MCU_TPL_SALM: { typedef SalmModel M; BODY; break; }                       \
+    case MCU_TPL_EQUIV: { typedef EquivModel M; BODY; break; }                     \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
 
@@ -242,6 +258,8 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_PUMPS: return tpl_info_fixed<PumpsModel>();
     case MCU_TPL_SURGICAL: return tpl_info_fixed<SurgicalModel>();
     case MCU_TPL_DYES: return tpl_info_fixed<DyesModel>();
+    case MCU_TPL_SALM: return tpl_info_fixed<SalmModel>();
+    case MCU_TPL_EQUIV: return tpl_info_fixed<EquivModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
       t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
@@ -264,6 +282,8 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_PUMPS: return PumpsModel::monitor_names();
       case MCU_TPL_SURGICAL: return SurgicalModel::monitor_names();
       case MCU_TPL_DYES: return DyesModel::monitor_names();
+      case MCU_TPL_SALM: return SalmModel::monitor_names();
+      case MCU_TPL_EQUIV: return EquivModel::monitor_names();
       default: break;
     }
   }
@@ -561,6 +581,8 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
     if (h->tpl == MCU_TPL_SURGICAL && n != (size_t)SurgicalModel::NH) return fail(h, MCU_ERR_DIM, "surgical inputs have 12 entries");
     if (h->tpl == MCU_TPL_DYES && n != 30) return fail(h, MCU_ERR_DIM, "dyes inputs have 30 entries");
+    if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
+    if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
   }
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))

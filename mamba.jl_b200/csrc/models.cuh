@@ -410,6 +410,114 @@ struct DyesModel {
   MCU_D static int out_dist(const Data& d, const double* s, int k, double& a, double& b) { a = s[3 + d.batch[k]]; b = sqrt(s[2]); return OUT_NORMAL; }
 };
 
+// =============================================================================== salm
+// doc/examples/salm.jl:16-53 (data :4-11): 3 plates x 6 doses of a mutagenicity assay, Poisson counts with a log-linear dose
+// response and an extra-Poisson random effect per plate/dose.  Matrices are flattened column-major (e = plate + 3 dose), as unlist
+// does (src/model/dependent.jl:192-195).  State: s2, gamma, beta, alpha, lambda[18] (the first four are the monitored columns, in the
+// order of doc/examples/salm.rst).
+struct SalmModel {
+  static constexpr int D = 22, NN = 5, NF = 6, P = 4, NY = 18, NPLATE = 3;
+  struct Data { const double* y; const double* x; const double* lgy1; int N; };
+  MCU_HD static int node_off(int n) { return n; }
+  MCU_HD static int node_len(int n) { return n == 4 ? NY : 1; }
+  MCU_HD static int node_link(int n) { return n == 0 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 4 ? 0x1u /* s2 */ : f == 5 ? 0x1Eu /* gamma, beta, alpha, lambda */ : 0u; }
+  MCU_HD static int mon_link(int j) { return j == 0 ? LINK_LOG : LINK_IDENT; }   // lambda and y are declared with monitor = false
+  static const char* node_name(int n) { static const char* nm[] = {"s2", "gamma", "beta", "alpha", "lambda"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "s2\ngamma\nbeta\nalpha"; }
+  MCU_D static double mu(const Data& d, const double* s, int e) {   // exp(alpha + beta log(x_j + 10) + gamma x_j + lambda_ij): salm.jl:22
+    const double x = d.x[e / NPLATE];
+    return exp(s[3] + s[2] * log(x + 10.0) + s[1] * x + s[4 + e]);
+  }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_invgamma(s[0], 0.001, 0.001, ig001_c0(), transform);
+    if (f < 4) return lp_normal(s[f], 0.0, 1000.0);
+    if (f == 4) {   // lambda ~ Normal(0, sqrt(s2)), one distribution for the 3 x 6 matrix
+      const double sigma = sqrt(s[0]);
+      double lp = 0.0;
+      for (int e = 0; e < NY; ++e) lp += lp_normal(s[4 + e], 0.0, sigma);
+      return lp;
+    }
+    double lp = 0.0;   // y[i, j] ~ Poisson(mu_ij)
+    for (int e = 0; e < NY; ++e) lp += lp_poisson(d.y[e], d.lgy1[e], mu(d, s, e));
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    double ga = 0, gb = 0, gg = 0, sll = 0;
+    const double s2 = s[0];
+    for (int e = 0; e < NY; ++e) {
+      const double x = d.x[e / NPLATE];
+      const double r = d.y[e] - mu(d, s, e);
+      ga += r; gb += r * log(x + 10.0); gg += r * x;
+      g[4 + e] = r - s[4 + e] / s2;
+      sll += s[4 + e] * s[4 + e];
+    }
+    g[3] = ga - s[3] / 1e6; g[2] = gb - s[2] / 1e6; g[1] = gg - s[1] / 1e6;
+    g[0] = -0.5 * (double)NY / s2 + 0.5 * sll / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 4; ++j) out[j] = s[j]; }
+  MCU_HD static int out_len(const Data&) { return NY; }
+  MCU_D static int out_dist(const Data& d, const double* s, int e, double& a, double& b) { a = mu(d, s, e); b = 0.0; return OUT_POISSON; }
+};
+
+// =============================================================================== equiv
+// doc/examples/equiv.jl:25-75 (data :4-22): two-period crossover bioequivalence trial, 10 subjects x 2 periods, Normal responses with
+// treatment (phi), period (pi) and subject-by-period (delta) effects; theta = exp(phi) and equiv = 1{0.8 < theta < 1.2} are Logical.
+// Matrices column-major (e = subject + 10 period).  State: s2_2, s2_1, pi, phi, mu, delta[20]; monitored s2_2, s2_1, pi, phi, theta,
+// equiv, mu (the order of doc/examples/equiv.rst).
+struct EquivModel {
+  static constexpr int D = 25, NN = 6, NF = 7, P = 7, NS = 10, NY = 20;
+  struct Data { const double* y; const double* group; int N; };
+  MCU_HD static int node_off(int n) { return n; }
+  MCU_HD static int node_len(int n) { return n == 5 ? NY : 1; }
+  MCU_HD static int node_link(int n) { return n < 2 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 5 ? 0x1u /* s2_2 */ : f == 6 ? 0x3Eu /* s2_1, pi, phi, mu, delta */ : 0u; }
+  MCU_HD static int mon_link(int j) { return j < 2 ? LINK_LOG : (j == 4 || j == 5) ? LINK_HEUR : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"s2_2", "s2_1", "pi", "phi", "mu", "delta"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "s2_2\ns2_1\npi\nphi\ntheta\nequiv\nmu"; }
+  // m_ij = mu + (-1)^(T[i,j] - 1) phi / 2 + (-1)^(j - 1) pi / 2 + delta[i,j],  T = [group  3 - group]  (equiv.jl:22, 33-34)
+  MCU_D static double sphi(const Data& d, int e) { const int i = e % NS, j = e / NS; const double T = j == 0 ? d.group[i] : 3.0 - d.group[i]; return T == 1.0 ? 1.0 : -1.0; }
+  MCU_D static double mean(const Data& d, const double* s, int e) {
+    const double spi = e < NS ? 1.0 : -1.0;
+    return s[4] + sphi(d, e) * s[3] / 2.0 + spi * s[2] / 2.0 + s[5 + e];
+  }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f < 2) return lp_invgamma(s[f], 0.001, 0.001, ig001_c0(), transform);
+    if (f < 5) return lp_normal(s[f], 0.0, 1000.0);
+    if (f == 5) { const double sg = sqrt(s[0]); double lp = 0.0; for (int e = 0; e < NY; ++e) lp += lp_normal(s[5 + e], 0.0, sg); return lp; }
+    const double sg = sqrt(s[1]);
+    double lp = 0.0;
+    for (int e = 0; e < NY; ++e) lp += lp_normal(d.y[e], mean(d, s, e), sg);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double s22 = s[0], s21 = s[1];
+    double gm = 0, gp = 0, gq = 0, see = 0, sdd = 0;
+    for (int e = 0; e < NY; ++e) {
+      const double res = d.y[e] - mean(d, s, e);
+      const double r = res / s21;
+      gm += r; gp += r * sphi(d, e) / 2.0; gq += r * (e < NS ? 0.5 : -0.5);
+      g[5 + e] = r - s[5 + e] / s22;
+      see += res * res; sdd += s[5 + e] * s[5 + e];
+    }
+    g[4] = gm - s[4] / 1e6; g[3] = gp - s[3] / 1e6; g[2] = gq - s[2] / 1e6;
+    g[1] = -0.5 * (double)NY / s21 + 0.5 * see / (s21 * s21) + d_invgamma(s21, 0.001, 0.001);
+    g[0] = -0.5 * (double)NY / s22 + 0.5 * sdd / (s22 * s22) + d_invgamma(s22, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data&, const double* s, double* out) {
+    const double theta = exp(s[3]);
+    out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; out[4] = theta; out[5] = (0.8 < theta && theta < 1.2) ? 1.0 : 0.0; out[6] = s[4];
+  }
+  MCU_HD static int out_len(const Data&) { return NY; }
+  MCU_D static int out_dist(const Data& d, const double* s, int e, double& a, double& b) { a = mean(d, s, e); b = sqrt(s[1]); return OUT_NORMAL; }
+};
+
 // =============================================================================== glm (CUDA-core form)
 // y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
 // small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.

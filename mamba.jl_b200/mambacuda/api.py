@@ -43,6 +43,8 @@ _TEMPLATES = {
     "pumps": dict(nodes=[("alpha", 1), ("beta", 1), ("theta", 10)], inputs=["y", "t"], outputs=["y"]),
     "surgical": dict(nodes=[("mu", 1), ("s2", 1), ("b", 12)], inputs=["r", "n"], outputs=["r"]),
     "dyes": dict(nodes=[("s2_between", 1), ("theta", 1), ("s2_within", 1), ("mu", 6)], inputs=["y", "batch"], outputs=["y"]),
+    "salm": dict(nodes=[("s2", 1), ("gamma", 1), ("beta", 1), ("alpha", 1), ("lambda", 18)], inputs=["y", "x"], outputs=["y"]),
+    "equiv": dict(nodes=[("s2_2", 1), ("s2_1", 1), ("pi", 1), ("phi", 1), ("mu", 1), ("delta", 20)], inputs=["y", "group"], outputs=["y"]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 

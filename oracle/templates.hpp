@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -386,6 +386,111 @@ inline Model make_dyes() {
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// salm: doc/examples/salm.jl:16-53 (data :4-11).  Node order s2, gamma, beta, alpha, lambda, y: a valid topological order that puts
+// the monitored columns in the order of doc/examples/salm.rst.  The 3 x 6 matrices are flattened column-major (plate fastest).
+inline Model make_salm() {
+  Model m; m.template_id = TPL_SALM;
+  m.inputs["y"] = {15, 21, 29, 16, 18, 21, 16, 26, 33, 27, 41, 60, 33, 38, 41, 20, 27, 42};
+  m.inputs["x"] = {0, 10, 33, 100, 333, 1000};
+  auto prior_n = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+  { Node n = make_node("s2", true, 1, true, true);                                                             // 0
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("gamma", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                // 1
+  { Node n = make_node("beta", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                 // 2
+  { Node n = make_node("alpha", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                // 3
+  { Node n = make_node("lambda", true, 18, false, false);                                                      // 4: Normal(0, sqrt(s2))
+    n.sources = {0};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(0)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 18, false, false, true);                                                     // 5: Poisson(mu_ij)
+    n.sources = {3, 2, 1, 4};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& x = mm.in("x"); const auto& lam = mm.val(4);
+      const double alpha = mm.val(3)[0], beta = mm.val(2)[0], gamma = mm.val(1)[0];
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(18);
+      for (int e = 0; e < 18; ++e) { const double xj = x[e / 3]; s.distr.arr[e] = {D_POISSON, std::exp(alpha + beta * std::log(xj + 10.0) + gamma * xj + lam[e]), 0.0}; }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: s2, gamma, beta, alpha, lambda[18]
+    const auto& x = mm.in("x"); const auto& y = mm.in("y"); const auto& lam = mm.val(4);
+    const double s2 = mm.val(0)[0], gamma = mm.val(1)[0], beta = mm.val(2)[0], alpha = mm.val(3)[0];
+    double ga = 0, gb = 0, gg = 0, sll = 0;
+    for (int e = 0; e < 18; ++e) {
+      const double xj = x[e / 3];
+      const double r = y[e] - std::exp(alpha + beta * std::log(xj + 10.0) + gamma * xj + lam[e]);
+      ga += r; gb += r * std::log(xj + 10.0); gg += r * xj;
+      g[4 + e] = r - lam[e] / s2; sll += lam[e] * lam[e];
+    }
+    g[3] = ga - alpha / 1e6; g[2] = gb - beta / 1e6; g[1] = gg - gamma / 1e6;
+    g[0] = -9.0 / s2 + 0.5 * sll / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// equiv: doc/examples/equiv.jl:25-75 (data :4-22).  Node order s2_2, s2_1, pi, phi, theta, equiv, mu, delta, y (topological; the
+// monitored columns come out in the order of doc/examples/equiv.rst).  10 x 2 matrices flattened column-major (subject fastest).
+inline Model make_equiv() {
+  Model m; m.template_id = TPL_EQUIV;
+  m.inputs["group"] = {1, 1, 2, 2, 2, 1, 1, 1, 2, 2};
+  m.inputs["y"] = {1.40, 1.64, 1.44, 1.36, 1.65, 1.08, 1.09, 1.25, 1.25, 1.30, 1.65, 1.57, 1.58, 1.68, 1.69, 1.31, 1.43, 1.44, 1.39, 1.52};
+  auto prior_n = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+  auto prior_ig = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+  { Node n = make_node("s2_2", true, 1, true, true); n.eval = prior_ig; m.nodes.push_back(n); }               // 0
+  { Node n = make_node("s2_1", true, 1, true, true); n.eval = prior_ig; m.nodes.push_back(n); }               // 1
+  { Node n = make_node("pi", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                   // 2
+  { Node n = make_node("phi", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                  // 3
+  { Node n = make_node("theta", false, 1, true, true);                                                         // 4: Logical, exp(phi)
+    n.sources = {3};
+    n.eval = [](const Model& mm, Node& l) { l.value.assign(1, std::exp(mm.val(3)[0])); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("equiv", false, 1, true, true);                                                         // 5: Logical, Int(0.8 < theta < 1.2)
+    n.sources = {4};
+    n.eval = [](const Model& mm, Node& l) { const double th = mm.val(4)[0]; l.value.assign(1, (0.8 < th && th < 1.2) ? 1.0 : 0.0); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("mu", true, 1, true, true); n.eval = prior_n; m.nodes.push_back(n); }                   // 6
+  { Node n = make_node("delta", true, 20, false, false);                                                       // 7: Normal(0, sqrt(s2_2))
+    n.sources = {0};
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(0)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 20, false, false, true);                                                     // 8: Normal(m_ij, sqrt(s2_1))
+    n.sources = {7, 6, 3, 2, 1};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& grp = mm.in("group"); const auto& dl = mm.val(7);
+      const double mu = mm.val(6)[0], phi = mm.val(3)[0], pi = mm.val(2)[0], sigma = std::sqrt(mm.val(1)[0]);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(20);
+      for (int e = 0; e < 20; ++e) {
+        const int i = e % 10, j = e / 10;
+        const double T = j == 0 ? grp[i] : 3.0 - grp[i];
+        const double mean = mu + (T == 1.0 ? 1.0 : -1.0) * phi / 2.0 + (j == 0 ? 1.0 : -1.0) * pi / 2.0 + dl[e];
+        s.distr.arr[e] = {D_NORMAL, mean, sigma};
+      }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: s2_2, s2_1, pi, phi, mu, delta[20]
+    const auto& grp = mm.in("group"); const auto& y = mm.in("y"); const auto& dl = mm.val(7);
+    const double s22 = mm.val(0)[0], s21 = mm.val(1)[0], pi = mm.val(2)[0], phi = mm.val(3)[0], mu = mm.val(6)[0];
+    double gm = 0, gp = 0, gq = 0, see = 0, sdd = 0;
+    for (int e = 0; e < 20; ++e) {
+      const int i = e % 10, j = e / 10;
+      const double T = j == 0 ? grp[i] : 3.0 - grp[i];
+      const double sp = T == 1.0 ? 1.0 : -1.0, sq = j == 0 ? 1.0 : -1.0;
+      const double res = y[e] - (mu + sp * phi / 2.0 + sq * pi / 2.0 + dl[e]);
+      const double r = res / s21;
+      gm += r; gp += r * sp / 2.0; gq += r * sq / 2.0;
+      g[5 + e] = r - dl[e] / s22; see += res * res; sdd += dl[e] * dl[e];
+    }
+    g[4] = gm - mu / 1e6; g[3] = gp - phi / 1e6; g[2] = gq - pi / 1e6;
+    g[1] = -10.0 / s21 + 0.5 * see / (s21 * s21) + ig_dlogpdf(0.001, 0.001, s21);
+    g[0] = -10.0 / s22 + 0.5 * sdd / (s22 * s22) + ig_dlogpdf(0.001, 0.001, s22);
+  };
+  m.finalize();
+  return m;
+}
+
 inline Model make_template(int id, int glm_d = 0) {
   switch (id) {
     case TPL_LINE: return make_line();
@@ -395,6 +500,8 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_GLM: return make_glm(glm_d > 0 ? glm_d : 1);
     case TPL_SURGICAL: return make_surgical();
     case TPL_DYES: return make_dyes();
+    case TPL_SALM: return make_salm();
+    case TPL_EQUIV: return make_equiv();
     default: throw std::runtime_error("unknown template");
   }
 }

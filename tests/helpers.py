@@ -18,6 +18,10 @@ SURGICAL_INITS = np.array([[0.0, 1.0] + [0.1] * 12, [1.0, 10.0] + [0.5] * 12])  
 DYES_INITS = np.array([[1.0, 1500.0, 1.0] + [1500.0] * 6, [10.0, 3000.0, 10.0] + [3000.0] * 6])       # doc/examples/dyes.jl:51-56 (state order s2_between, theta, s2_within, mu)
 
 
+SALM_INITS = np.array([[10.0, 0.0, 0.0, 0.0] + [0.0] * 18, [1.0, 0.01, 1.0, 1.0] + [0.0] * 18])          # doc/examples/salm.jl:56-61 (state order s2, gamma, beta, alpha, lambda)
+EQUIV_INITS = np.array([[1.0, 1.0, 0.0, 0.0, 0.0] + [0.0] * 20, [10.0, 10.0, 10.0, 10.0, 10.0] + [0.0] * 20])   # doc/examples/equiv.jl:79-84 (s2_2, s2_1, pi, phi, mu, delta)
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -66,6 +70,12 @@ SCHEMES = {
                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     "dyes_rwm_slice": ("dyes", [dict(kind="rwm", nodes=[1], scale=50.0), dict(kind="rwm", nodes=[3], scale=50.0),
                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
+    # doc/examples/salm.jl:63-64: Slice([:alpha, :beta, :gamma], [1.0, 1.0, 0.1]), AMWG([:lambda, :s2], 0.1)
+    "salm_slice_amwg": ("salm", [dict(kind="slice_multi", nodes=[3, 2, 1], scale=[1.0, 1.0, 0.1]), dict(kind="amwg", nodes=[4, 0], scale=0.1)], SALM_INITS),
+    # doc/examples/equiv.jl:89-91: NUTS(:delta), Slice([:mu, :phi, :pi], 1.0), Slice([:s2_1, :s2_2], 1.0, Univariate)
+    "equiv_nuts_slice": ("equiv", [dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0),
+                                   dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], EQUIV_INITS),
+    "equiv_amwg": ("equiv", [dict(kind="amwg", nodes=[5], scale=0.1), dict(kind="amwg", nodes=[4, 3, 2], scale=0.1), dict(kind="amwg", nodes=[1, 0], scale=0.5)], EQUIV_INITS),
     # doc/examples/surgical.jl:54-55: NUTS(:b), Slice([:mu, :s2], 1.0)
     "surgical_nuts_slice": ("surgical", [dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], SURGICAL_INITS),
     "surgical_amwg": ("surgical", [dict(kind="amwg", nodes=[2], scale=0.3), dict(kind="amwg", nodes=[0, 1], scale=0.3)], SURGICAL_INITS),

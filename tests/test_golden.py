@@ -43,6 +43,15 @@ BLOCKS = {
         "theta": ([dict(kind="mala", nodes=[1], epsilon=50.0)], 0),
         "mu": ([dict(kind="hmc", nodes=[3], epsilon=10.0, L=5)], 0),
     },
+    "salm": {
+        "slice_alpha_beta_gamma": ([dict(kind="slice_multi", nodes=[3, 2, 1], scale=[1.0, 1.0, 0.1]), dict(kind="amwg", nodes=[4, 0], scale=0.1)], 0),
+        "amwg_lambda_s2_transformed": ([dict(kind="slice_multi", nodes=[3, 2, 1], scale=[1.0, 1.0, 0.1]), dict(kind="amwg", nodes=[4, 0], scale=0.1)], 1),
+    },
+    "equiv": {
+        "nuts_delta": ([dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0), dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], 0),
+        "slice_mu_phi_pi": ([dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0), dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], 1),
+        "slice_s2_1_s2_2": ([dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0), dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], 2),
+    },
     "pumps": {
         "alpha_beta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 0),
         "theta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 1),
@@ -65,6 +74,12 @@ def gold_extra():
 
 
 @pytest.fixture(scope="module")
+def gold_more():
+    with open(os.path.join(GOLD, "block_logpdf_more.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
 def gold_diag():
     with open(os.path.join(GOLD, "diagnostics.json")) as f:
         return json.load(f)
@@ -76,7 +91,7 @@ def _oracle_blocks(blocks):
 
 
 def test_golden_files_are_committed_with_their_generator():
-    for f in ("block_logpdf.json", "diagnostics.json", "make_golden.py"):
+    for f in ("block_logpdf.json", "diagnostics.json", "make_golden.py", "block_logpdf_more.json", "make_golden_more.py", "coda.json", "make_coda_golden.py"):
         assert os.path.exists(os.path.join(GOLD, f))
 
 
@@ -96,6 +111,24 @@ def test_oracle_extra_template_block_densities_match_golden(oracle, gold_extra, 
         o = oracle.Oracle(tpl)
         o.set_scheme(_oracle_blocks(blocks))
         np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+
+
+@pytest.mark.parametrize("tpl", ["salm", "equiv"])
+def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
+    S = np.array(gold_more["blocks"][tpl]["states"])
+    for key, (blocks, bi) in BLOCKS[tpl].items():
+        o = oracle.Oracle(tpl)
+        o.set_scheme(_oracle_blocks(blocks))
+        np.testing.assert_allclose(o.logpdf(bi, S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+    o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(next(iter(BLOCKS[tpl].values()))[0]))
+    nn = {"salm": 5, "equiv": 6}[tpl]
+    np.testing.assert_allclose(o.logpdf_nodes(1 << nn, S), gold_more["blocks"][tpl]["logpdf"]["y"], rtol=1e-11)   # observed node only
+    # analytic gradient of the joint against central differences of the block density that holds every parameter node
+    allb = [dict(kind="nuts", nodes=list(range(nn)))]
+    o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(allb))
+    lp_a, g_a = o.gradlogpdf(0, S, mode=0)
+    lp_c, g_c = o.gradlogpdf(0, S, mode=2)
+    np.testing.assert_allclose(g_a, g_c, rtol=2e-5, atol=1e-4 * np.abs(g_c).max())
 
 
 def test_oracle_glm_density_and_gradient_match_golden(oracle, gold):
@@ -194,6 +227,20 @@ def test_gpu_extra_template_block_densities_match_golden(gold_extra, tpl):
         eng = Engine(tpl, 4)
         eng.set_scheme(blocks)
         np.testing.assert_allclose(eng.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tpl", ["salm", "equiv"])
+def test_gpu_salm_equiv_block_densities_match_golden(gold_more, tpl):
+    from mambacuda.engine import Engine
+    S = np.array(gold_more["blocks"][tpl]["states"])
+    for key, (blocks, bi) in BLOCKS[tpl].items():
+        eng = Engine(tpl, 4)
+        eng.set_scheme(blocks)
+        np.testing.assert_allclose(eng.logpdf(bi, S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        nn, nf = eng.factor_counts()
+        np.testing.assert_allclose(eng.logpdf_nodes(1 << nn, S), gold_more["blocks"][tpl]["logpdf"]["y"], rtol=1e-11)
         eng.close()
 
 

@@ -34,11 +34,12 @@ def random_states(inits, B, rng, D_pos):
     return st
 
 
-POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}}
+POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}, "salm": {0}, "equiv": {0, 1}}
 
 
 @pytest.mark.parametrize("name", ["line_amwg_slice", "line_nuts_all", "seeds_amwg", "seeds_amm", "rats_slice_amwg",
-                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg", "dyes_nuts_slice", "dyes_mala_slice", "dyes_hmc_slice"])
+                                  "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg", "dyes_nuts_slice", "dyes_mala_slice", "dyes_hmc_slice",
+                                  "salm_slice_amwg", "equiv_nuts_slice", "equiv_amwg"])
 def test_logpdf_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -65,7 +66,7 @@ def test_logpdf_out_of_support_is_minus_inf(oracle):
     assert np.all(np.isneginf(eng2.logpdf(0, in2, x))) and np.all(np.isneginf(orc2.logpdf(0, in2, x)))
 
 
-@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice"])
+@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice", "equiv_nuts_slice"])
 def test_gradient_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -138,6 +139,8 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("pumps_slice", 300, 100, 2),
     ("pumps_gibbs_amwg", 300, 100, 2),
     ("surgical_amwg", 300, 150, 2),
+    ("salm_slice_amwg", 300, 150, 2),
+    ("equiv_amwg", 300, 150, 2),
     ("dyes_rwm_slice", 300, 0, 1),
     ("dyes_hmc_slice", 100, 0, 1),
     ("line_rwm", 500, 0, 1),
@@ -190,7 +193,7 @@ def nuts_pair(oracle, name, n_chains, iters, burnin, seed, force_generic=True):
     return (out_g, st_g, tune_g), (out_o, st_o, tune_o)
 
 
-@pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts", "surgical_nuts_slice"])
+@pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "equiv_nuts_slice"])
 def test_nuts_adaptive_trajectories_match_oracle(oracle, name):
     # Dual averaging multiplies a perturbation of the acceptance statistic by sqrt(m)/gamma/(m+t0) ~ 2-10x per
     # adaptive iteration (nuts.jl:70-75), so libm-level rounding differences between two machines grow
@@ -365,7 +368,7 @@ def test_gelman_logit_link_for_logical_columns_in_the_unit_interval(oracle):
     np.testing.assert_allclose(psrf_h, psrf_o, rtol=1e-7)
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg"])
 def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     # logpdf(mc, nodekeys) (modelstats.jl:16-58): observed nodes only (the deviance of dic), every stochastic node, one parameter node
     eng, orc, inits = make_pair(oracle, tpl_scheme, 4)
@@ -381,7 +384,7 @@ def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     assert np.isfinite(joint).all()
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg"])
 def test_predict_matches_oracle(oracle, tpl_scheme):
     # predict(mc) (modelstats.jl:63-96): rand of the observed node at each state, same Philox stream on both sides
     from mambacuda.engine import Engine
@@ -391,7 +394,7 @@ def test_predict_matches_oracle(oracle, tpl_scheme):
     st = random_states(inits, 40, np.random.default_rng(9), POS[tpl])
     g = eng.predict(st, stream_id=5); o = orc.predict(st, 31, stream_id=5)
     assert g.shape == o.shape and g.shape[0] == 40
-    if tpl in ("seeds", "pumps", "surgical"):    # counts: identical integers
+    if tpl in ("seeds", "pumps", "surgical", "salm"):    # counts: identical integers
         assert (g == np.round(g)).all() and (g >= 0).all()
         assert (g == o).mean() > 0.999           # a uniform within rounding of a CDF step may fall on either side
     else:
@@ -414,6 +417,45 @@ def test_predict_glm_families():
         assert (np.abs(d.mean(axis=0) - mean) < 5 * sd / np.sqrt(2000)).all()
         if family == 2:
             np.testing.assert_allclose(d.std(axis=0), 0.5, rtol=0.1)
+
+
+def test_equiv_posterior_matches_published_table(oracle):
+    # doc/examples/equiv.rst:43-50 (NUTS(delta) + Slice([mu, phi, pi]) + Slice([s2_1, s2_2], Univariate)): mean (MCSE, SD)
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("equiv_nuts_slice")
+    eng = Engine(tpl, 1024, seed=12)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(5000, burnin=2500, thin=1, store=False, out=False)
+    summ = eng.summary_streaming(); names = eng.names(1)
+    ref = {"s2_2": (0.0173121833, 0.0007329722, 0.014549568), "s2_1": (0.0184397014, 0.0005689492, 0.013837972),
+           "pi": (-0.1874240524, 0.0032257037, 0.086420302), "phi": (-0.0035569545, 0.0035141650, 0.087590520),
+           "theta": (1.0002921934, 0.0036227671, 0.088250458), "equiv": (0.9751, 0.0036666529, 0.155828169), "mu": (1.4387396416, 0.0013735876, 0.042269208)}
+    for nm, (mean, mcse_ref, sd) in ref.items():
+        j = names.index(nm)
+        assert abs(summ[j, 0] - mean) < 3 * np.hypot(mcse_ref, summ[j, 3]) + 0.02 * sd, (nm, summ[j, 0], mean)
+    psrf = eng.gelman(0.05, True)      # theta is a Logical column > 0 (log link); equiv is a 0/1 indicator (identity: min > 0 fails)
+    codes = eng.link_codes(True)
+    assert codes[names.index("theta")] == 1 and codes[names.index("equiv")] == 0
+    assert (psrf[2:, 0] < 1.03).all() and (psrf[:2, 0] < 1.15).all()   # the variances mix slowly under the constrained-scale slice (published ESS 394 / 592 of 10,000)
+
+
+def test_salm_posterior(oracle):
+    # doc/examples/salm.rst:43-47.  The reference's own run mixes slowly in the multivariate slice block (ESS 93-185), so its table is
+    # matched within 0.75 of the published SD; the long-run values this scheme converges to (CPU oracle, 8 x 100,000 iterations:
+    # alpha 2.176, beta 0.311, gamma -9.7e-4, s2 0.074) are matched within Monte Carlo error.
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("salm_slice_amwg")
+    eng = Engine(tpl, 2048, seed=13)
+    eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.02)
+    eng.run(12000, burnin=4000, thin=1, store=False, out=False)
+    summ = eng.summary_streaming(); names = eng.names(1)
+    pub = {"s2": (0.0690769709, 0.04304237136), "gamma": (-0.0011250515, 0.00034536546), "beta": (0.3543443166, 0.07160779229), "alpha": (2.0100584321, 0.26156942610)}
+    longrun = {"s2": (0.0740, 0.047), "gamma": (-0.000973, 0.00045), "beta": (0.3106, 0.1031), "alpha": (2.176, 0.379)}
+    for nm in pub:
+        j = names.index(nm)
+        assert abs(summ[j, 0] - pub[nm][0]) < 0.75 * pub[nm][1], (nm, summ[j, 0])
+        assert abs(summ[j, 0] - longrun[nm][0]) < 0.06 * longrun[nm][1] + 3 * summ[j, 3], (nm, summ[j, 0], summ[j, 3])
+    assert (eng.gelman(0.05, True)[:, 0] < 1.1).all()
 
 
 def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):
