@@ -36,7 +36,8 @@
 #define MCU_SEEDS_BW 2      // plates per trip in the b block (even)
 #endif
 #ifndef MCU_SEEDS_LOGU
-#define MCU_SEEDS_LOGU 1   // MH test on the log scale (log u evaluated off the critical path)
+#define MCU_SEEDS_LOGU 1   // MH test on the log scale (log u evaluated off the critical path); 2 = float bracket + FP64 log inside the
+                           // rounding band only (same decisions; measured 3-7 % slower, profiles/r1_seeds_fast_summary.md)
 #endif
 #ifndef MCU_SEEDS_PIPE
 #define MCU_SEEDS_PIPE 0   // b block: draws of trip t + 1 generated during trip t — measured 10 % SLOWER (profiles/r1_seeds_fast_summary.md), kept for the record
@@ -248,7 +249,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       for (int j = 0; j < 4; ++j) {
         double zn01;
         if ((j & 1) == 0) { const Pair pr = draw_normal_pair(a, chain, it32, 0, j >> 1); zn01 = pr.a; zc = pr.b; } else zn01 = zc;
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+        LogU lu;                                                          // bracket of log(uniform j), off the critical path
+        if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); lu = logu_bracket(pr.a); uc = pr.b; } else lu = logu_bracket(uc);
+#elif MCU_SEEDS_LOGU
         double lu;                                                        // log of uniform j of the block, off the critical path
         if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); lu = log_uniform(pr.a); uc = log_uniform(pr.b); } else lu = uc;
 #endif
@@ -279,7 +283,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
           delta = fma(-0.5e-6, fma(anew, anew, -al0 * al0), delta);   // (x / 1000)^2 / 2 without the divisions
         }
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+        if (logu_less(lu, delta)) {                                       // rand() < exp(delta): float bracket, FP64 log only inside the rounding band
+#elif MCU_SEEDS_LOGU
         if (lu < delta) {                                                 // rand() < exp(delta) on the log scale; lu was formed next to the draw
 #else
         double u;                                                         // uniform j of the block
@@ -316,6 +322,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       auto b_trip = [&](auto Wc, int i0) {
         constexpr int W = decltype(Wc)::value;
         int ix[W]; double sg[W], bi[W], zn[W], uu[W], ac[W];
+#if MCU_SEEDS_LOGU == 2
+        LogU lb[W];
+#endif
 #pragma unroll
         for (int w = 0; w < W; ++w) {
           const bool real = i0 + w < NPL;
@@ -328,7 +337,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; w += 2) {
           const Pair pz = draw_normal_pair(a, chain, it32, 1, (i0 + w) >> 1);
           const Pair pu = draw_uniform_pair(a, chain, it32, 1, (i0 + w) >> 1);
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+          zn[w] = pz.a; zn[w + 1] = pz.b; lb[w] = logu_bracket(pu.a); lb[w + 1] = logu_bracket(pu.b);
+#elif MCU_SEEDS_LOGU
           zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = log_uniform(pu.a); uu[w + 1] = log_uniform(pu.b);
 #else
           zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = pu.a; uu[w + 1] = pu.b;
@@ -342,7 +353,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
           en[w] = fast_exp(pick(g, cfg.grp[ir]) + bn[w]);                  // fresh e_i: also resets the drift of the alpha updates
           ln[w] = fast_log(1.0 + en[w]);
           const double dl = fma(cfg.r[ir], bn[w] - bi[w], -cfg.n[ix[w]] * (ln[w] - SLL(ix[w]))) - half_inv_s2 * fma(bn[w], bn[w], -bi[w] * bi[w]);
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+          acc[w] = i0 + w < NPL && logu_less(lb[w], dl);
+#elif MCU_SEEDS_LOGU
           acc[w] = i0 + w < NPL && uu[w] < dl;
 #else
           acc[w] = i0 + w < NPL && mh_accept_nb(uu[w], dl);
@@ -352,7 +365,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; ++w)
           if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) SAC(ix[w]) = ac[w] + 1.0; }
       };
-#if MCU_SEEDS_PIPE && MCU_SEEDS_LOGU
+#if MCU_SEEDS_PIPE && MCU_SEEDS_LOGU == 1
       // Software-pipelined form (two plates per trip): the normals and log-uniforms of trip t + 1 depend on nothing but the counters, so
       // they are generated DURING trip t — four independent dependency chains (two updates, Philox + Box-Muller, Philox + two logs) for
       // the scheduler to interleave, and the exp -> log -> compare chain of a trip no longer waits for its own draws.
@@ -406,7 +419,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       if (adapt) m2 += 1.0;
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+      const LogU lus = logu_bracket(draw_uniform_pair(a, chain, it32, 2, 0).a);
+#elif MCU_SEEDS_LOGU
       const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
 #endif
       const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
@@ -416,7 +431,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       const double dx = xn - x;
       const double dinv = 1.0 / s2n - 1.0 / s2;
       const double delta = -(0.001 + 1.0) * dx - 0.001 * dinv + dx - 0.5 * S * dinv - (double)NPL * 0.5 * dx;
-#if MCU_SEEDS_LOGU
+#if MCU_SEEDS_LOGU == 2
+      if (logu_less(lus, delta)) { x = xn; s2 = s2n; if (adapt) acs += 1; }
+#elif MCU_SEEDS_LOGU
       if (lus < delta) { x = xn; s2 = s2n; if (adapt) acs += 1; }
 #else
       const double u = draw_uniform_pair(a, chain, it32, 2, 0).a;
