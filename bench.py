@@ -148,8 +148,9 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": "chain_iters_per_sec", "value": value, "unit": "chain-iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "seeds random-effects logistic (21 plates), AMWG x3 blocks, 2000 iters (burnin 1000, thin 10)",
-                   "chains": n_chains, "note": "Julia reference not runnable (no julia in image); CPU restatement of its algorithm (oracle/) timed instead"},
+        "config": {"workload": "seeds random-effects logistic regression (21 plates, doc/examples/seeds.jl), AMWG(alpha0..alpha12)+AMWG(b)+AMWG(s2)",
+                   "chains_per_gpu": 125000, "chains_total": 125000 * args.gpus, "iters": ITERS, "burnin": BURNIN, "thin": THIN,
+                   "sample_chains": n_chains, "note": "Julia reference not runnable (no julia in image); CPU restatement of its algorithm (oracle/) timed instead"},
         "cpu_baseline": {"value": value, "unit": "chain-iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "chain-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
