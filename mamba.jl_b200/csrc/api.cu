@@ -154,6 +154,12 @@ void default_inputs(mcu_ctx* h) {
       in["group"] = {1, 1, 2, 2, 2, 1, 1, 1, 2, 2};
       in["y"] = {1.40, 1.64, 1.44, 1.36, 1.65, 1.08, 1.09, 1.25, 1.25, 1.30, 1.65, 1.57, 1.58, 1.68, 1.69, 1.31, 1.43, 1.44, 1.39, 1.52};
       break;
+    case MCU_TPL_BLOCKER:  // doc/examples/blocker.jl:4-18
+      in["rt"] = {3, 7, 5, 102, 28, 4, 98, 60, 25, 138, 64, 45, 9, 57, 25, 33, 28, 8, 6, 32, 27, 22};
+      in["nt"] = {38, 114, 69, 1533, 355, 59, 945, 632, 278, 1916, 873, 263, 291, 858, 154, 207, 251, 151, 174, 209, 391, 680};
+      in["rc"] = {3, 14, 11, 127, 27, 6, 152, 48, 37, 188, 52, 47, 16, 45, 31, 38, 12, 6, 3, 40, 43, 39};
+      in["nc"] = {39, 116, 93, 1520, 365, 52, 939, 471, 282, 1921, 583, 266, 293, 883, 147, 213, 122, 154, 134, 218, 364, 674};
+      break;
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -173,6 +179,7 @@ int upload_inputs(mcu_ctx* h) {
   if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
   auto in = h->inputs;   // derived arrays
   if (h->tpl == MCU_TPL_SEEDS || h->tpl == MCU_TPL_SURGICAL) in["lc"] = lchoose_vec(in["n"], in["r"]);
+  if (h->tpl == MCU_TPL_BLOCKER) { in["lcc"] = lchoose_vec(in["nc"], in["rc"]); in["lct"] = lchoose_vec(in["nt"], in["rt"]); }
   if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
     if (kv.second.empty()) continue;
@@ -216,6 +223,11 @@ template <> struct Host<SalmModel> {
 template <> struct Host<EquivModel> {
   static EquivModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["group"], (int)h->inputs["group"].size()}; }
 };
+template <> struct Host<BlockerModel> {
+  static BlockerModel::Data data(mcu_ctx* h) {
+    return {h->d_inputs["rc"], h->d_inputs["nc"], h->d_inputs["rt"], h->d_inputs["nt"], h->d_inputs["lcc"], h->d_inputs["lct"], (int)h->inputs["rc"].size()};
+  }
+};
 template <> struct Host<SurgicalModel> {
   static SurgicalModel::Data data(mcu_ctx* h) { return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["lc"], (int)h->inputs["r"].size()}; }
 };
@@ -238,6 +250,7 @@ template <> struct Host<GlmM> {
     case MCU_TPL_SURGICAL: { typedef SurgicalModel M; BODY; break; }               \
     case MCU_TPL_DYES: { typedef DyesModel M; BODY; break; }                       \
     case MCU_TPL_SALM: { typedef SalmModel M; BODY; break; }                       \
+    case MCU_TPL_BLOCKER: { typedef BlockerModel M; BODY; break; }                 \
     case MCU_TPL_EQUIV: { typedef EquivModel M; BODY; break; }                     \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
@@ -259,6 +272,7 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_SURGICAL: return tpl_info_fixed<SurgicalModel>();
     case MCU_TPL_DYES: return tpl_info_fixed<DyesModel>();
     case MCU_TPL_SALM: return tpl_info_fixed<SalmModel>();
+    case MCU_TPL_BLOCKER: return tpl_info_fixed<BlockerModel>();
     case MCU_TPL_EQUIV: return tpl_info_fixed<EquivModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
@@ -283,6 +297,7 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_SURGICAL: return SurgicalModel::monitor_names();
       case MCU_TPL_DYES: return DyesModel::monitor_names();
       case MCU_TPL_SALM: return SalmModel::monitor_names();
+      case MCU_TPL_BLOCKER: return BlockerModel::monitor_names();
       case MCU_TPL_EQUIV: return EquivModel::monitor_names();
       default: break;
     }
@@ -581,6 +596,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
     if (h->tpl == MCU_TPL_SURGICAL && n != (size_t)SurgicalModel::NH) return fail(h, MCU_ERR_DIM, "surgical inputs have 12 entries");
     if (h->tpl == MCU_TPL_DYES && n != 30) return fail(h, MCU_ERR_DIM, "dyes inputs have 30 entries");
+    if (h->tpl == MCU_TPL_BLOCKER && n != (size_t)BlockerModel::NT) return fail(h, MCU_ERR_DIM, "blocker inputs have 22 entries");
     if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
     if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");

@@ -518,6 +518,60 @@ struct EquivModel {
   MCU_D static int out_dist(const Data& d, const double* s, int e, double& a, double& b) { a = mean(d, s, e); b = sqrt(s[1]); return OUT_NORMAL; }
 };
 
+// =============================================================================== blocker
+// doc/examples/blocker.jl:22-69 (data :4-18): meta-analysis of 22 beta-blocker trials, two observed Binomial nodes (control and treated
+// arms), trial baselines mu[22], trial effects delta[22] ~ Normal(d, sqrt(s2)) and a predictive effect delta_new.
+// State: s2, d, delta_new, mu[22], delta[22]; monitored s2, d, delta_new (the order of doc/examples/blocker.rst).
+struct BlockerModel {
+  static constexpr int D = 47, NN = 5, NF = 7, P = 3, NT = 22;
+  struct Data { const double* rc; const double* nc; const double* rt; const double* nt; const double* lcc; const double* lct; int N; };
+  MCU_HD static int node_off(int n) { return n < 3 ? n : (n == 3 ? 3 : 3 + NT); }
+  MCU_HD static int node_len(int n) { return n < 3 ? 1 : NT; }
+  MCU_HD static int node_link(int n) { return n == 0 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) {
+    return (f == 2 || f == 4) ? 0x3u /* s2, d */ : f == 5 ? 0x8u /* mu */ : f == 6 ? 0x18u /* mu, delta */ : 0u;
+  }
+  MCU_HD static int mon_link(int j) { return j == 0 ? LINK_LOG : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"s2", "d", "delta_new", "mu", "delta"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "s2\nd\ndelta_new"; }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_invgamma(s[0], 0.001, 0.001, ig001_c0(), transform);
+    if (f == 1) return lp_normal(s[1], 0.0, 1000.0);
+    if (f == 2) return lp_normal(s[2], s[1], sqrt(s[0]));
+    if (f == 3) { double lp = 0.0; for (int i = 0; i < NT; ++i) lp += lp_normal(s[3 + i], 0.0, 1000.0); return lp; }
+    if (f == 4) { const double sg = sqrt(s[0]); double lp = 0.0; for (int i = 0; i < NT; ++i) lp += lp_normal(s[3 + NT + i], s[1], sg); return lp; }
+    double lp = 0.0;
+    if (f == 5) { for (int i = 0; i < NT; ++i) lp += lp_binomial_logit(d.rc[i], d.nc[i], d.lcc[i], s[3 + i]); return lp; }          // rc ~ Binomial(nc, invlogit(mu))
+    for (int i = 0; i < NT; ++i) lp += lp_binomial_logit(d.rt[i], d.nt[i], d.lct[i], s[3 + i] + s[3 + NT + i]);                      // rt ~ Binomial(nt, invlogit(mu + delta))
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double s2 = s[0], dd = s[1];
+    double sd = s[2] - dd, sdd = sd * sd;
+    g[2] = -(s[2] - dd) / s2;
+    for (int i = 0; i < NT; ++i) {
+      const double mu = s[3 + i], dl = s[3 + NT + i];
+      const double pc = 1.0 / (exp(-mu) + 1.0), pt = 1.0 / (exp(-(mu + dl)) + 1.0);
+      const double rt = d.rt[i] - d.nt[i] * pt;
+      g[3 + i] = (d.rc[i] - d.nc[i] * pc) + rt - mu / 1e6;
+      g[3 + NT + i] = rt - (dl - dd) / s2;
+      sd += dl - dd; sdd += (dl - dd) * (dl - dd);
+    }
+    g[1] = sd / s2 - dd / 1e6;
+    g[0] = -0.5 * (double)(NT + 1) / s2 + 0.5 * sdd / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
+  MCU_HD static int out_len(const Data&) { return 2 * NT; }   // rc[22] then rt[22]
+  MCU_D static int out_dist(const Data& d, const double* s, int e, double& a, double& b) {
+    if (e < NT) { a = d.nc[e]; b = 1.0 / (exp(-s[3 + e]) + 1.0); }
+    else { const int i = e - NT; a = d.nt[i]; b = 1.0 / (exp(-(s[3 + i] + s[3 + NT + i])) + 1.0); }
+    return OUT_BINOMIAL;
+  }
+};
+
 // =============================================================================== glm (CUDA-core form)
 // y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
 // small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.

@@ -45,6 +45,8 @@ _TEMPLATES = {
     "dyes": dict(nodes=[("s2_between", 1), ("theta", 1), ("s2_within", 1), ("mu", 6)], inputs=["y", "batch"], outputs=["y"]),
     "salm": dict(nodes=[("s2", 1), ("gamma", 1), ("beta", 1), ("alpha", 1), ("lambda", 18)], inputs=["y", "x"], outputs=["y"]),
     "equiv": dict(nodes=[("s2_2", 1), ("s2_1", 1), ("pi", 1), ("phi", 1), ("mu", 1), ("delta", 20)], inputs=["y", "group"], outputs=["y"]),
+    "blocker": dict(nodes=[("s2", 1), ("d", 1), ("delta_new", 1), ("mu", 22), ("delta", 22)], inputs=["rc", "nc", "rt", "nt"], outputs=["rc", "rt"],
+                    output_lens=[22, 22]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 
@@ -209,7 +211,7 @@ def _inits_matrix(model, inits):
         for nm, _ in _TEMPLATES[model.template]["nodes"]:
             if nm not in d:
                 raise ArgumentError(f"missing initial value for node : {nm}")   # initialization.jl:9-10
-            v = np.atleast_1d(np.asarray(d[nm], dtype=float)).ravel()
+            v = np.atleast_1d(np.asarray(d[nm], dtype=float)).ravel(order="F")   # matrices flatten column-major, as unlist does
             if v.size != model.node_len(nm):
                 raise DimensionMismatch(f"incompatible initial value for node : {nm}")
             rec.extend(v.tolist())
@@ -792,10 +794,16 @@ def predict(mc, nodekeys=None, stream_id=0):
     _, need = _factor_mask(mc, eng, nodekeys)
     st, _ = _states_from_chains(mc, eng, need)
     n, _, m = mc.value.shape
-    draws = eng.predict(st, stream_id)                                   # [n * m x L], rows chain-major
+    draws = eng.predict(st, stream_id)                                   # [n * m x L], rows chain-major; all observed nodes in order
+    lens = _TEMPLATES[mc.model.template].get("output_lens", [draws.shape[1]])
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    cols, names = [], []
+    for key in nodekeys:
+        q = outputs.index(key)
+        cols += list(range(offs[q], offs[q + 1])); names += [f"{key}[{i + 1}]" for i in range(lens[q])]
+    draws = draws[:, cols]
     L = draws.shape[1]
     value = draws.reshape(m, n, L).transpose(1, 2, 0)
-    names = [f"{nodekeys[0]}[{i + 1}]" for i in range(L)]
     return ModelChains(value, mc.model, engine=None, start=mc.first, thin=mc.step, names=names, chains=mc.chains)
 
 

@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -491,6 +491,63 @@ inline Model make_equiv() {
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// blocker: doc/examples/blocker.jl:22-69 (data :4-18).  Node order s2, d, delta_new, mu, delta, rc, rt (topological; monitored columns
+// in the order of doc/examples/blocker.rst).  Two observed nodes.
+inline Model make_blocker() {
+  Model m; m.template_id = TPL_BLOCKER;
+  m.inputs["rt"] = {3, 7, 5, 102, 28, 4, 98, 60, 25, 138, 64, 45, 9, 57, 25, 33, 28, 8, 6, 32, 27, 22};
+  m.inputs["nt"] = {38, 114, 69, 1533, 355, 59, 945, 632, 278, 1916, 873, 263, 291, 858, 154, 207, 251, 151, 174, 209, 391, 680};
+  m.inputs["rc"] = {3, 14, 11, 127, 27, 6, 152, 48, 37, 188, 52, 47, 16, 45, 31, 38, 12, 6, 3, 40, 43, 39};
+  m.inputs["nc"] = {39, 116, 93, 1520, 365, 52, 939, 471, 282, 1921, 583, 266, 293, 883, 147, 213, 122, 154, 134, 218, 364, 674};
+  { Node n = make_node("s2", true, 1, true, true);                                                             // 0
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("d", true, 1, true, true);                                                              // 1
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+    m.nodes.push_back(n); }
+  auto effect = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, mm.val(1)[0], std::sqrt(mm.val(0)[0])}; };
+  { Node n = make_node("delta_new", true, 1, true, true); n.sources = {1, 0}; n.eval = effect; m.nodes.push_back(n); }   // 2
+  { Node n = make_node("mu", true, 22, false, false);                                                          // 3
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("delta", true, 22, false, false); n.sources = {1, 0}; n.eval = effect; m.nodes.push_back(n); }    // 4
+  { Node n = make_node("rc", true, 22, false, false, true);                                                    // 5: Binomial(nc[i], invlogit(mu[i]))
+    n.sources = {3};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& nc = mm.in("nc"); const auto& mu = mm.val(3);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(nc.size());
+      for (size_t i = 0; i < nc.size(); ++i) s.distr.arr[i] = {D_BINOMIAL, nc[i], invlogit(mu[i])};
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("rt", true, 22, false, false, true);                                                    // 6: Binomial(nt[i], invlogit(mu[i] + delta[i]))
+    n.sources = {3, 4};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& nt = mm.in("nt"); const auto& mu = mm.val(3); const auto& dl = mm.val(4);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(nt.size());
+      for (size_t i = 0; i < nt.size(); ++i) s.distr.arr[i] = {D_BINOMIAL, nt[i], invlogit(mu[i] + dl[i])};
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: s2, d, delta_new, mu[22], delta[22]
+    const auto& rc = mm.in("rc"); const auto& nc = mm.in("nc"); const auto& rt = mm.in("rt"); const auto& nt = mm.in("nt");
+    const auto& mu = mm.val(3); const auto& dl = mm.val(4);
+    const double s2 = mm.val(0)[0], d = mm.val(1)[0], dn = mm.val(2)[0];
+    double sd = dn - d, sdd = sd * sd;
+    g[2] = -(dn - d) / s2;
+    for (int i = 0; i < 22; ++i) {
+      const double pc = invlogit(mu[i]), pt = invlogit(mu[i] + dl[i]);
+      const double r = rt[i] - nt[i] * pt;
+      g[3 + i] = (rc[i] - nc[i] * pc) + r - mu[i] / 1e6;
+      g[25 + i] = r - (dl[i] - d) / s2;
+      sd += dl[i] - d; sdd += (dl[i] - d) * (dl[i] - d);
+    }
+    g[1] = sd / s2 - d / 1e6;
+    g[0] = -11.5 / s2 + 0.5 * sdd / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
 inline Model make_template(int id, int glm_d = 0) {
   switch (id) {
     case TPL_LINE: return make_line();
@@ -501,6 +558,7 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_SURGICAL: return make_surgical();
     case TPL_DYES: return make_dyes();
     case TPL_SALM: return make_salm();
+    case TPL_BLOCKER: return make_blocker();
     case TPL_EQUIV: return make_equiv();
     default: throw std::runtime_error("unknown template");
   }

@@ -1,5 +1,5 @@
 """Writes tests/golden/block_logpdf_more.json: formula-level golden vectors (scipy.stats, no oracle, no engine) for the templates
-added after block_logpdf{,_extra}.json — salm (doc/examples/salm.jl) and equiv (doc/examples/equiv.jl).  Same construction as
+added after block_logpdf{,_extra}.json — salm, equiv and blocker (doc/examples/{salm,equiv,blocker}.jl).  Same construction as
 make_golden.py: data parsed from the reference's own scripts, logpdf!(m, x, block, transform) (src/model/simulation.jl:77-90) per
 sampling block of the scripts' schemes, plus the observed-node log density (the deviance term of dic, src/output/modelstats.jl:3-13).
 Run in the build container (reads /root/reference):  python tests/golden/make_golden_more.py"""
@@ -64,18 +64,38 @@ def equiv_blocks(D, s):     # state: s2_2, s2_1, pi, phi, mu, delta[20]
             "y": lik}
 
 
+def blocker_data():
+    src = open(f"{REF}/doc/examples/blocker.jl").read()
+    return {k: np.array(nums(re.search(r":" + k + r" =>\s*\[(.*?)\]", src, re.S).group(1))) for k in ("rt", "nt", "rc", "nc")}
+
+
+def blocker_blocks(D, s):   # state: s2, d, delta_new, mu[22], delta[22]
+    s2, d, dn, mu, dl = s[0], s[1], s[2], s[3:25], s[25:47]
+    invlogit = lambda e: 1.0 / (np.exp(-e) + 1.0)
+    lc = st.binom.logpmf(D["rc"], D["nc"], invlogit(mu)).sum()
+    lt = st.binom.logpmf(D["rt"], D["nt"], invlogit(mu + dl)).sum()
+    pmu = normal(mu, 0, 1000.0).sum(); pdl = normal(dl, d, np.sqrt(s2)).sum(); pdn = normal(dn, d, np.sqrt(s2))
+    return {"amwg_mu": pmu + lc + lt,                                              # AMWG(:mu, 0.1): blocker.jl:84
+            "amwg_delta_delta_new": pdl + pdn + lt,                                # AMWG([:delta, :delta_new], 0.1): blocker.jl:85
+            "slice_d_s2": normal(d, 0, 1000.0) + invgamma(s2, 0.001, 0.001) + pdn + pdl,   # Slice([:d, :s2], 1.0): blocker.jl:86
+            "rc": lc, "rt": lt}
+
+
 def main():
     rng = np.random.default_rng(20261020)
-    D = {"salm": salm_data(), "equiv": equiv_data()}
+    D = {"salm": salm_data(), "equiv": equiv_data(), "blocker": blocker_data()}
     n = 12
     S = {"salm": np.column_stack([rng.gamma(2, 0.05, n), rng.normal(-0.001, 0.0005, n), rng.normal(0.35, 0.1, n), rng.normal(2.0, 0.3, n),
                                   rng.normal(0, 0.25, (n, 18))]),
          "equiv": np.column_stack([rng.gamma(2, 0.01, n), rng.gamma(2, 0.01, n), rng.normal(-0.2, 0.1, n), rng.normal(0, 0.1, n),
                                    rng.normal(1.44, 0.05, n), rng.normal(0, 0.1, (n, 20))])}
-    fn = {"salm": salm_blocks, "equiv": equiv_blocks}
+    rng_b = np.random.default_rng(20261021)
+    S["blocker"] = np.column_stack([rng_b.gamma(2, 0.01, n), rng_b.normal(-0.25, 0.06, n), rng_b.normal(-0.25, 0.15, n), rng_b.normal(-2.2, 0.4, (n, 22)),
+                                    rng_b.normal(-0.25, 0.15, (n, 22))])
+    fn = {"salm": salm_blocks, "equiv": equiv_blocks, "blocker": blocker_blocks}
     out = {"_about": "block_logpdf fixtures for salm and equiv; see make_golden_more.py",
            "data": {k: {kk: vv.tolist() for kk, vv in v.items()} for k, v in D.items()}, "blocks": {}}
-    for tpl in ("salm", "equiv"):
+    for tpl in ("salm", "equiv", "blocker"):
         vals = [fn[tpl](D[tpl], s) for s in S[tpl]]
         out["blocks"][tpl] = {"states": S[tpl].tolist(), "logpdf": {k: [float(v[k]) for v in vals] for k in vals[0]}}
     with open(os.path.join(HERE, "block_logpdf_more.json"), "w") as f:

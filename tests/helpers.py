@@ -22,6 +22,9 @@ SALM_INITS = np.array([[10.0, 0.0, 0.0, 0.0] + [0.0] * 18, [1.0, 0.01, 1.0, 1.0]
 EQUIV_INITS = np.array([[1.0, 1.0, 0.0, 0.0, 0.0] + [0.0] * 20, [10.0, 10.0, 10.0, 10.0, 10.0] + [0.0] * 20])   # doc/examples/equiv.jl:79-84 (s2_2, s2_1, pi, phi, mu, delta)
 
 
+BLOCKER_INITS = np.array([[1.0, 0.0, 0.0] + [0.0] * 44, [10.0, 2.0, 2.0] + [2.0] * 44])                 # doc/examples/blocker.jl:73-78 (s2, d, delta_new, mu, delta)
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -72,6 +75,10 @@ SCHEMES = {
                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     # doc/examples/salm.jl:63-64: Slice([:alpha, :beta, :gamma], [1.0, 1.0, 0.1]), AMWG([:lambda, :s2], 0.1)
     "salm_slice_amwg": ("salm", [dict(kind="slice_multi", nodes=[3, 2, 1], scale=[1.0, 1.0, 0.1]), dict(kind="amwg", nodes=[4, 0], scale=0.1)], SALM_INITS),
+    # doc/examples/blocker.jl:84-86: AMWG(:mu, 0.1), AMWG([:delta, :delta_new], 0.1), Slice([:d, :s2], 1.0)
+    "blocker_amwg_slice": ("blocker", [dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1),
+                                       dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], BLOCKER_INITS),
+    "blocker_nuts_slice": ("blocker", [dict(kind="nuts", nodes=[3, 4, 2]), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], BLOCKER_INITS),
     # doc/examples/equiv.jl:89-91: NUTS(:delta), Slice([:mu, :phi, :pi], 1.0), Slice([:s2_1, :s2_2], 1.0, Univariate)
     "equiv_nuts_slice": ("equiv", [dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0),
                                    dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], EQUIV_INITS),

@@ -52,6 +52,11 @@ BLOCKS = {
         "slice_mu_phi_pi": ([dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0), dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], 1),
         "slice_s2_1_s2_2": ([dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0), dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], 2),
     },
+    "blocker": {
+        "amwg_mu": ([dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], 0),
+        "amwg_delta_delta_new": ([dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], 1),
+        "slice_d_s2": ([dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], 2),
+    },
     "pumps": {
         "alpha_beta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 0),
         "theta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 1),
@@ -113,7 +118,7 @@ def test_oracle_extra_template_block_densities_match_golden(oracle, gold_extra, 
         np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
 
 
-@pytest.mark.parametrize("tpl", ["salm", "equiv"])
+@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker"])
 def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
     S = np.array(gold_more["blocks"][tpl]["states"])
     for key, (blocks, bi) in BLOCKS[tpl].items():
@@ -121,8 +126,9 @@ def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
         o.set_scheme(_oracle_blocks(blocks))
         np.testing.assert_allclose(o.logpdf(bi, S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
     o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(next(iter(BLOCKS[tpl].values()))[0]))
-    nn = {"salm": 5, "equiv": 6}[tpl]
-    np.testing.assert_allclose(o.logpdf_nodes(1 << nn, S), gold_more["blocks"][tpl]["logpdf"]["y"], rtol=1e-11)   # observed node only
+    nn = {"salm": 5, "equiv": 6, "blocker": 5}[tpl]
+    for q, key in enumerate(["rc", "rt"] if tpl == "blocker" else ["y"]):                                          # observed nodes, one at a time
+        np.testing.assert_allclose(o.logpdf_nodes(1 << (nn + q), S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11)
     # analytic gradient of the joint against central differences of the block density that holds every parameter node
     allb = [dict(kind="nuts", nodes=list(range(nn)))]
     o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(allb))
@@ -231,7 +237,7 @@ def test_gpu_extra_template_block_densities_match_golden(gold_extra, tpl):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tpl", ["salm", "equiv"])
+@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker"])
 def test_gpu_salm_equiv_block_densities_match_golden(gold_more, tpl):
     from mambacuda.engine import Engine
     S = np.array(gold_more["blocks"][tpl]["states"])
@@ -240,7 +246,8 @@ def test_gpu_salm_equiv_block_densities_match_golden(gold_more, tpl):
         eng.set_scheme(blocks)
         np.testing.assert_allclose(eng.logpdf(bi, S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
         nn, nf = eng.factor_counts()
-        np.testing.assert_allclose(eng.logpdf_nodes(1 << nn, S), gold_more["blocks"][tpl]["logpdf"]["y"], rtol=1e-11)
+        for q, okey in enumerate(["rc", "rt"] if tpl == "blocker" else ["y"]):
+            np.testing.assert_allclose(eng.logpdf_nodes(1 << (nn + q), S), gold_more["blocks"][tpl]["logpdf"][okey], rtol=1e-11)
         eng.close()
 
 

@@ -34,12 +34,12 @@ def random_states(inits, B, rng, D_pos):
     return st
 
 
-POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}, "salm": {0}, "equiv": {0, 1}}
+POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}, "salm": {0}, "equiv": {0, 1}, "blocker": {0}}
 
 
 @pytest.mark.parametrize("name", ["line_amwg_slice", "line_nuts_all", "seeds_amwg", "seeds_amm", "rats_slice_amwg",
                                   "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg", "dyes_nuts_slice", "dyes_mala_slice", "dyes_hmc_slice",
-                                  "salm_slice_amwg", "equiv_nuts_slice", "equiv_amwg"])
+                                  "salm_slice_amwg", "equiv_nuts_slice", "equiv_amwg", "blocker_amwg_slice", "blocker_nuts_slice"])
 def test_logpdf_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -66,7 +66,7 @@ def test_logpdf_out_of_support_is_minus_inf(oracle):
     assert np.all(np.isneginf(eng2.logpdf(0, in2, x))) and np.all(np.isneginf(orc2.logpdf(0, in2, x)))
 
 
-@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice", "equiv_nuts_slice"])
+@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice", "equiv_nuts_slice", "blocker_nuts_slice"])
 def test_gradient_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -141,6 +141,7 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("surgical_amwg", 300, 150, 2),
     ("salm_slice_amwg", 300, 150, 2),
     ("equiv_amwg", 300, 150, 2),
+    ("blocker_amwg_slice", 300, 150, 2),
     ("dyes_rwm_slice", 300, 0, 1),
     ("dyes_hmc_slice", 100, 0, 1),
     ("line_rwm", 500, 0, 1),
@@ -368,15 +369,15 @@ def test_gelman_logit_link_for_logical_columns_in_the_unit_interval(oracle):
     np.testing.assert_allclose(psrf_h, psrf_o, rtol=1e-7)
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice"])
 def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     # logpdf(mc, nodekeys) (modelstats.jl:16-58): observed nodes only (the deviance of dic), every stochastic node, one parameter node
     eng, orc, inits = make_pair(oracle, tpl_scheme, 4)
     tpl = helpers.scheme(tpl_scheme)[0]
     st = random_states(inits, 24, np.random.default_rng(8), POS[tpl])
     nn, nf = eng.factor_counts()
-    assert nf == nn + 1
-    for mask in (1 << nn, (1 << nf) - 1, 1, 1 << (nn - 1)):
+    assert nf == nn + (2 if tpl == "blocker" else 1)   # blocker has two observed nodes (rc, rt)
+    for mask in (1 << nn, (1 << nf) - 1, 1, 1 << (nn - 1), 1 << (nf - 1)):
         np.testing.assert_allclose(eng.logpdf_nodes(mask, st), orc.logpdf_nodes(mask, st), rtol=RTOL_LP, atol=1e-12)
     # the block density is the sum of the block's own node densities and its targets': for a block holding every parameter node
     # this is the joint (simulation.jl:77-90)
@@ -384,7 +385,7 @@ def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     assert np.isfinite(joint).all()
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice"])
 def test_predict_matches_oracle(oracle, tpl_scheme):
     # predict(mc) (modelstats.jl:63-96): rand of the observed node at each state, same Philox stream on both sides
     from mambacuda.engine import Engine
@@ -394,7 +395,7 @@ def test_predict_matches_oracle(oracle, tpl_scheme):
     st = random_states(inits, 40, np.random.default_rng(9), POS[tpl])
     g = eng.predict(st, stream_id=5); o = orc.predict(st, 31, stream_id=5)
     assert g.shape == o.shape and g.shape[0] == 40
-    if tpl in ("seeds", "pumps", "surgical", "salm"):    # counts: identical integers
+    if tpl in ("seeds", "pumps", "surgical", "salm", "blocker"):    # counts: identical integers
         assert (g == np.round(g)).all() and (g >= 0).all()
         assert (g == o).mean() > 0.999           # a uniform within rounding of a CDF step may fall on either side
     else:
@@ -437,6 +438,38 @@ def test_equiv_posterior_matches_published_table(oracle):
     codes = eng.link_codes(True)
     assert codes[names.index("theta")] == 1 and codes[names.index("equiv")] == 0
     assert (psrf[2:, 0] < 1.03).all() and (psrf[:2, 0] < 1.15).all()   # the variances mix slowly under the constrained-scale slice (published ESS 394 / 592 of 10,000)
+
+
+def test_blocker_posterior_dic_and_predict(oracle):
+    # doc/examples/blocker.rst:46-49 through the API mirror; dic / predict with two observed nodes
+    from mambacuda import api
+    m = api.Model("blocker")
+    api.setsamplers(m, [api.AMWG("mu", 0.1), api.AMWG(["delta", "delta_new"], 0.1), api.Slice(["d", "s2"], 1.0)])        # blocker.jl:84-86
+    inits = [dict(d=0.0, delta_new=0.0, s2=1.0, mu=np.zeros(22), delta=np.zeros(22)), dict(d=2.0, delta_new=2.0, s2=10.0, mu=np.full(22, 2.0), delta=np.full(22, 2.0))]
+    sim = api.mcmc(m, {}, inits * 16, 10000, burnin=2500, thin=2, chains=32)
+    assert sim.names == ["s2", "d", "delta_new"]
+    ss, _, _ = api.summarystats(sim)
+    ref = {"s2": (0.01822186, 0.0014150714, 0.021121265), "d": (-0.25563567, 0.0040205781, 0.061841945), "delta_new": (-0.25005767, 0.0050219145, 0.150325282)}
+    for j, nm in enumerate(sim.names):
+        assert abs(ss[j, 0] - ref[nm][0]) < 3 * np.hypot(ref[nm][1], ss[j, 3]) + 0.02 * ref[nm][2], (nm, ss[j], ref[nm])
+    with pytest.raises(api.ArgumentError, match="chain values are missing for nodes : mu, delta"):     # the arms depend on unmonitored nodes
+        api.dic(sim)
+    with pytest.raises(api.ArgumentError, match="chain values are missing for nodes"):
+        api.predict(sim, "rt")
+    # with every node available (a ModelChains over the full state) both run: deviance = -2 (logpdf(rc) + logpdf(rt))
+    eng = sim.engine
+    vals, _, _ = eng.get_state()
+    full = api.ModelChains(vals.T[None, :, :].copy(), sim.model, engine=None, names=eng.names(0), start=10000, thin=2)
+    full.engine = eng; full._streaming = False
+    d, rows, cols = api.dic(full)
+    lp = api.logpdf(full, ["rc", "rt"]).value[0, 0, :]
+    assert d.shape == (2, 2) and np.isfinite(d).all()
+    np.testing.assert_allclose(-2.0 * lp.mean() , d[0, 0] - d[0, 1], rtol=1e-12)                        # DIC - pD = mean deviance
+    pp = api.predict(full)
+    assert pp.names[0] == "rc[1]" and pp.names[22] == "rt[1]" and pp.value.shape == (1, 44, 32)
+    assert api.predict(full, "rt").names == [f"rt[{i + 1}]" for i in range(22)]
+    nt = np.array([38, 114, 69, 1533, 355, 59, 945, 632, 278, 1916, 873, 263, 291, 858, 154, 207, 251, 151, 174, 209, 391, 680])
+    assert (pp.value[0, 22:, :] <= nt[:, None]).all() and (pp.value >= 0).all()
 
 
 def test_salm_posterior(oracle):

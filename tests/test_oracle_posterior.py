@@ -113,6 +113,16 @@ def test_equiv_reference_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_blocker_reference_scheme(oracle):
+    # doc/examples/blocker.jl:84-92 (AMWG(mu) + AMWG([delta, delta_new]) + Slice([d, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2),
+    # table doc/examples/blocker.rst:46-49
+    ref = {"s2": (0.01822186, 0.0014150714), "d": (-0.25563567, 0.0040205781), "delta_new": (-0.25005767, 0.0050219145)}
+    tpl, blocks, inits = helpers.scheme("blocker_amwg_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=8, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_surgical_reference_scheme(oracle):
     # doc/examples/surgical.jl:54-60 (NUTS(b) + Slice([mu, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/surgical.rst
     ref = {"mu": (-2.550263247, 0.00352027397), "pop_mean": (0.073062651, 0.00022880854), "s2": (0.183080212, 0.00629499754),
