@@ -44,8 +44,13 @@ const TEMPLATES = Dict(
   0 => [:beta, :s2],                                                      # doc/tutorial/line.jl
   1 => [:alpha0, :alpha1, :alpha2, :alpha12, :s2, :b],                    # doc/examples/seeds.jl
   2 => [:mu_alpha, :mu_beta, :s2_alpha, :s2_beta, :s2_c, :alpha, :beta],  # doc/examples/rats.jl
-  3 => [:alpha, :beta, :theta]                                            # doc/examples/pumps.jl
-)
+  3 => [:alpha, :beta, :theta],                                           # doc/examples/pumps.jl
+  5 => [:mu, :s2, :b],                                                    # doc/examples/surgical.jl
+  6 => [:s2_between, :theta, :s2_within, :mu],                            # doc/examples/dyes.jl
+  7 => [:s2, :gamma, :beta, :alpha, :lambda],                             # doc/examples/salm.jl
+  8 => [:s2_2, :s2_1, :pi, :phi, :mu, :delta],                            # doc/examples/equiv.jl
+  9 => [:s2, :d, :delta_new, :mu, :delta]                                 # doc/examples/blocker.jl
+)                                                                         # (4 = the GLM family: pass template=4 and inputs X, y)
 
 function check(h::Ptr{Void}, rc::Cint)
   if rc != 0
