@@ -192,11 +192,12 @@ def setsamplers(model, scheme):
 
 def setinputs(model, inputs):
     """setinputs!(m, inputs): src/model/initialization.jl:30-40"""
-    need = [k for k in _TEMPLATES[model.template]["inputs"] if model.template == "glm"]
+    need = ["X", "y"] if model.template == "glm" else []       # the example templates carry the data of their scripts as defaults
     for key in need:
         if key not in inputs:
             raise ArgumentError(f"missing inputs for node : {key}")
-    model.inputs = {k: np.asarray(v, dtype=float) for k, v in inputs.items() if k in _TEMPLATES[model.template]["inputs"]}
+    allowed = list(_TEMPLATES[model.template]["inputs"]) + (["family", "sigma"] if model.template == "glm" else [])
+    model.inputs = {k: np.atleast_1d(np.asarray(v, dtype=float)) for k, v in inputs.items() if k in allowed}
     if model.template == "glm":
         model.glm_d = int(model.inputs["X"].shape[1])
     model.hasinputs = True
