@@ -82,7 +82,8 @@ enum {
 };
 
 enum { MCU_ADAPT_ALL = 0, MCU_ADAPT_BURNIN = 1, MCU_ADAPT_NONE = 2 }; /* amwg.jl:47-56, amm.jl:45-55 */
-enum { MCU_PROP_NORMAL = 0, MCU_PROP_SYMUNIFORM = 1, MCU_PROP_SYMTRIANGULAR = 2 }; /* rwm.jl:12-13, distributions/extensions.jl:43-53 */
+enum { MCU_PROP_NORMAL = 0, MCU_PROP_SYMUNIFORM = 1, MCU_PROP_SYMTRIANGULAR = 2, MCU_PROP_COSINE = 3, MCU_PROP_EPANECHNIKOV = 4,
+       MCU_PROP_BIWEIGHT = 5, MCU_PROP_TRIWEIGHT = 6 }; /* rwm.jl:12-13, distributions/extensions.jl:43-53 (SymDistributionType) */
 enum { MCU_GRAD_ANALYTIC = 0, MCU_GRAD_FORWARD = 1, MCU_GRAD_CENTRAL = 2 };       /* nuts.jl:47 dtype; simulation.jl:47-51 */
 enum { MCU_RNG_PHILOX = 0, MCU_RNG_EXTERNAL = 1 };
 enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1, MCU_ETYPE_IPSE = 2 };                                    /* src/output/mcse.jl:3-8 */

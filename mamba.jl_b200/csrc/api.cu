@@ -688,7 +688,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
     }
     if (d.kind == MCU_HMC && (d.L < 1 || !(d.epsilon > 0))) return fail(h, MCU_ERR_ARG, "HMC needs epsilon > 0 and L >= 1");
     if (d.kind == MCU_MALA && !(d.epsilon > 0)) return fail(h, MCU_ERR_ARG, "MALA needs epsilon > 0");
-    if (d.kind == MCU_RWM && (d.proposal < 0 || d.proposal > 2)) return fail(h, MCU_ERR_UNSUPPORTED, "RWM proposal not available on the device");
+    if (d.kind == MCU_RWM && (d.proposal < 0 || d.proposal > MCU_PROP_TRIWEIGHT)) return fail(h, MCU_ERR_UNSUPPORTED, "RWM proposal not available on the device");
     if (d.grad < 0 || d.grad > 2) return fail(h, MCU_ERR_ARG, "unknown gradient mode");
     int *de = nullptr, *dl = nullptr; double *ds = nullptr, *dS = nullptr;
     CK(cudaMalloc(&de, sizeof(int) * k)); h->scheme_allocs.push_back(de);

@@ -139,17 +139,40 @@ static MCU_NOINL double rgamma_mt(double a, Draws& rng) {
 }
 
 // -------------------------------------------------------------------------------- RWM
+// rand(proposal(0.0, 1.0)) for the symmetric kernels of src/distributions/extensions.jl:51-53.  The reference calls Distributions.rand;
+// the engine's draw order per component (shared with the oracle): Normal one normal; SymUniform, Cosine one uniform; SymTriangularDist two
+// uniforms; Epanechnikov three uniforms (the middle-of-three rule, Devroye 1986 p. 236); Biweight / Triweight two Gamma(3) / Gamma(4) draws
+// (z = 2 B - 1 with B ~ Beta(3, 3) / Beta(4, 4), since (1 - z^2)^k = (4 B (1 - B))^k).
+static MCU_NOINL double rwm_draw(int proposal, Draws& rng) {
+  switch (proposal) {
+    case 1: return -1.0 + 2.0 * rng.uniform();                                   // SymUniform(0,1) = Uniform(-1,1)
+    case 2: { const double a = rng.uniform(); return a - rng.uniform(); }        // SymTriangularDist(0,1)
+    case 3: {                                                                     // Cosine(0,1): F(z) = (1 + z + sin(pi z) / pi) / 2 on [-1, 1], inverted by bisection
+      const double u = rng.uniform();
+      double lo = -1.0, hi = 1.0;
+      for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (0.5 * (1.0 + mid + sinpi(mid) * 0.31830988618379067154) < u) lo = mid; else hi = mid;
+      }
+      return 0.5 * (lo + hi);
+    }
+    case 4: {                                                                     // Epanechnikov(0,1)
+      const double u1 = -1.0 + 2.0 * rng.uniform(), u2 = -1.0 + 2.0 * rng.uniform(), u3 = -1.0 + 2.0 * rng.uniform();
+      return (fabs(u3) >= fabs(u2) && fabs(u3) >= fabs(u1)) ? u2 : u3;
+    }
+    case 5: case 6: {                                                             // Biweight(0,1) / Triweight(0,1)
+      const double a = proposal == 5 ? 3.0 : 4.0;
+      const double g1 = rgamma_mt(a, rng), g2 = rgamma_mt(a, rng);
+      return 2.0 * (g1 / (g1 + g2)) - 1.0;
+    }
+    default: return rng.normal();
+  }
+}
 template <int K, class T>
 MCU_NOINL void rwm_sample(double* v, const DevBlock& b, T& tgt, Draws& rng) {   // rwm.jl:65-71
   const int k = b.k;
   double x[K];
-  for (int i = 0; i < k; ++i) {
-    double e;
-    if (b.proposal == 1) e = -1.0 + 2.0 * rng.uniform();                                // SymUniform(0,1) = Uniform(-1,1)
-    else if (b.proposal == 2) { const double a = rng.uniform(); e = a - rng.uniform(); } // SymTriangularDist(0,1)
-    else e = rng.normal();
-    x[i] = v[i] + b.scale[i] * e;
-  }
+  for (int i = 0; i < k; ++i) x[i] = v[i] + b.scale[i] * rwm_draw(b.proposal, rng);
   const double u = rng.uniform();
   const double lx = tgt.logf(x);
   const double lv = tgt.logf(v);

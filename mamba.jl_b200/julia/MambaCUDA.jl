@@ -128,6 +128,7 @@ end
 function RWM(params, scale; proposal=Normal)
   s = Mamba.RWM(params, scale, proposal=proposal)
   code = proposal == Normal ? 0 : proposal == SymUniform ? 1 : proposal == SymTriangularDist ? 2 :
+         proposal == Cosine ? 3 : proposal == Epanechnikov ? 4 : proposal == Biweight ? 5 : proposal == Triweight ? 6 :
          throw(ArgumentError("proposal $proposal has no device implementation"))
   shimargs[s] = Dict(:scale => scale, :proposal => code); s
 end

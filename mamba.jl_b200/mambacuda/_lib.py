@@ -14,7 +14,7 @@ OK, ERR_ARG, ERR_DIM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, 
 TPL = {"line": 0, "seeds": 1, "rats": 2, "pumps": 3, "glm": 4, "surgical": 5, "dyes": 6, "salm": 7, "equiv": 8, "blocker": 9}
 KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc": 5, "amm": 6, "gibbs": 7, "mala": 8}
 ADAPT = {"all": 0, "burnin": 1, "none": 2}
-PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2}
+PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2, "cosine": 3, "epanechnikov": 4, "biweight": 5, "triweight": 6}
 GRAD = {"analytic": 0, "forward": 1, "central": 2}
 RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE = 1, 2, 4
 

@@ -84,7 +84,7 @@ def Slice(params, width, form=Multivariate, transform=False):      # src/sampler
 
 def RWM(params, scale, proposal="normal"):                         # src/samplers/rwm.jl:49-58
     if proposal not in _lib.PROPOSAL:
-        raise ArgumentError(f"proposal {proposal} has no device implementation (normal, symuniform, symtriangular)")
+        raise ArgumentError(f"proposal {proposal} is not a SymDistributionType ({', '.join(_lib.PROPOSAL)})")   # extensions.jl:51-53
     return Sampler(params, "rwm", scale=scale, proposal=proposal)
 
 

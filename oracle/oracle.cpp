@@ -264,6 +264,11 @@ int orc_predict(void* h, uint64_t seed, uint32_t stream_id, int64_t B, const dou
     return 0;
   } catch (std::exception& e) { c->err = e.what(); return -1; }
 }
+// n draws of rand(proposal(0, 1)) from one Philox stream (tests: moments and CDF of the RWM proposal kernels)
+void orc_rwm_draws(int proposal, uint64_t seed, int64_t n, double* out) {
+  PhiloxRng rng(seed, 0); rng.seek(1, 0, 3);
+  for (int64_t i = 0; i < n; ++i) out[i] = rwm_draw(proposal, rng);
+}
 int orc_gradlogpdf(void* h, int block, int grad_mode, int64_t B, const double* state, const double* x, double* lp, double* g) {
   Ctx* c = (Ctx*)h;
   try {

@@ -229,6 +229,14 @@ def summarystats(chains, etype=0, batch=100):
     return out
 
 
+def rwm_draws(proposal, seed, n):
+    L = lib()
+    out = np.empty(n)
+    L.orc_rwm_draws.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_double)]
+    L.orc_rwm_draws(int(proposal), int(seed), int(n), _dp(out))
+    return out
+
+
 def philox(ctr, key):
     L = lib()
     c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()

@@ -126,10 +126,31 @@ inline void slice_multi_sample(Vec& v, const Vec& width, const LogF& logf, Rng& 
 // ---------------------------------------------------------------------------- RWM
 // proposal(0,1) draws: Normal → randn; SymUniform(0,1) = Uniform(-1,1) (extensions.jl:43-46);
 // SymTriangularDist(0,1): rand = mu + sigma * (rand() - rand())  (Distributions.jl)
+// Cosine / Epanechnikov / Biweight / Triweight (extensions.jl:51-53): Distributions.jl's samplers are not in the tree; the engine contract
+// (mamba.jl_b200/csrc/samplers.cuh) is one uniform + CDF inversion (Cosine), the middle-of-three rule (Epanechnikov), 2 Beta(3,3) - 1 and
+// 2 Beta(4,4) - 1 through two Gamma draws (Biweight, Triweight).
 inline double rwm_draw(int proposal, Rng& rng) {
   switch (proposal) {
     case 1: return runif(-1.0, 1.0, rng);
     case 2: { double a = rng.uniform(); double b = rng.uniform(); return a - b; }
+    case 3: {
+      const double u = rng.uniform();
+      double lo = -1.0, hi = 1.0;
+      for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (0.5 * (1.0 + mid + std::sin(M_PI * mid) * 0.31830988618379067154) < u) lo = mid; else hi = mid;
+      }
+      return 0.5 * (lo + hi);
+    }
+    case 4: {
+      const double u1 = -1.0 + 2.0 * rng.uniform(), u2 = -1.0 + 2.0 * rng.uniform(), u3 = -1.0 + 2.0 * rng.uniform();
+      return (std::fabs(u3) >= std::fabs(u2) && std::fabs(u3) >= std::fabs(u1)) ? u2 : u3;
+    }
+    case 5: case 6: {
+      const double a = proposal == 5 ? 3.0 : 4.0;
+      const double g1 = rgamma_mt(a, rng), g2 = rgamma_mt(a, rng);
+      return 2.0 * (g1 / (g1 + g2)) - 1.0;
+    }
     default: return rng.normal();
   }
 }

@@ -42,6 +42,10 @@ SCHEMES = {
     "line_rwm": ("line", [dict(kind="rwm", nodes=[0, 1], scale=[0.5, 0.2, 0.8])], LINE_INITS),
     "line_rwm_unif": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symuniform")], LINE_INITS),
     "line_rwm_tri": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symtriangular")], LINE_INITS),
+    "line_rwm_cos": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.8, proposal="cosine")], LINE_INITS),
+    "line_rwm_epa": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.8, proposal="epanechnikov")], LINE_INITS),
+    "line_rwm_biw": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.9, proposal="biweight")], LINE_INITS),
+    "line_rwm_trw": ("line", [dict(kind="rwm", nodes=[0, 1], scale=1.0, proposal="triweight")], LINE_INITS),
     "line_mala": ("line", [dict(kind="mala", nodes=[0, 1], epsilon=0.08)], LINE_INITS),
     "line_mala_sigma": ("line", [dict(kind="mala", nodes=[0, 1], epsilon=0.08,
                                       scale=np.array([[1.0, 0.2, 0.0], [0.2, 0.5, 0.1], [0.0, 0.1, 2.0]]))], LINE_INITS),
@@ -65,13 +69,13 @@ SCHEMES = {
                                  dict(kind="slice_uni", nodes=[1, 3], scale=1.0)], RATS_INITS),
     # NUTS(alpha, beta, mu_alpha, mu_beta) + Slice(s2_c, s2_alpha, s2_beta; univariate)
     "rats_nuts_slice": ("rats", [dict(kind="nuts", nodes=[5, 6, 0, 1]), dict(kind="slice_uni", nodes=[4, 2, 3], scale=[10.0, 10.0, 1.0])], RATS_INITS),
-    # doc/examples/dyes.jl:60-73: four schemes on one model (scheme4's Cosine proposal has no device implementation: Normal is used)
+    # doc/examples/dyes.jl:60-73: four schemes on one model (scheme4: RWM(theta) with a Cosine proposal)
     "dyes_nuts_slice": ("dyes", [dict(kind="nuts", nodes=[3, 1]), dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     "dyes_mala_slice": ("dyes", [dict(kind="mala", nodes=[1], epsilon=50.0), dict(kind="mala", nodes=[3], epsilon=50.0, scale=np.eye(6)),
                                  dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     "dyes_hmc_slice": ("dyes", [dict(kind="hmc", nodes=[1], epsilon=10.0, L=5), dict(kind="hmc", nodes=[3], epsilon=10.0, L=5, scale=np.eye(6)),
                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
-    "dyes_rwm_slice": ("dyes", [dict(kind="rwm", nodes=[1], scale=50.0), dict(kind="rwm", nodes=[3], scale=50.0),
+    "dyes_rwm_slice": ("dyes", [dict(kind="rwm", nodes=[1], scale=50.0, proposal="cosine"), dict(kind="rwm", nodes=[3], scale=50.0),
                                 dict(kind="slice_multi", nodes=[2, 0], scale=1000.0)], DYES_INITS),
     # doc/examples/salm.jl:63-64: Slice([:alpha, :beta, :gamma], [1.0, 1.0, 0.1]), AMWG([:lambda, :s2], 0.1)
     "salm_slice_amwg": ("salm", [dict(kind="slice_multi", nodes=[3, 2, 1], scale=[1.0, 1.0, 0.1]), dict(kind="amwg", nodes=[4, 0], scale=0.1)], SALM_INITS),

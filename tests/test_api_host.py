@@ -15,7 +15,7 @@ def test_sampler_constructors_mirror_the_reference(mcu_built):
     assert api.NUTS("beta").desc["target"] == 0.6                                                                    # nuts.jl:22
     assert api.AMM(["a"], 0.01 * np.eye(1)).desc["beta"] == 0.05                                                     # amm.jl:21-22
     with pytest.raises(api.ArgumentError):
-        api.RWM("beta", 1.0, proposal="cosine")
+        api.RWM("beta", 1.0, proposal="laplace")
 
 
 def test_setsamplers_and_block_descs(mcu_built):

@@ -84,7 +84,7 @@ def test_dyes_example_all_four_schemes():
     schemes = {"nuts": [api.NUTS(["mu", "theta"]), sl],
                "mala": [api.MALA("theta", 50.0), api.MALA("mu", 50.0, np.eye(6)), sl],
                "hmc": [api.HMC("theta", 10.0, 5), api.HMC("mu", 10.0, 5, np.eye(6)), sl],
-               "rwm": [api.RWM("theta", 50.0), api.RWM("mu", 50.0), sl]}        # scheme4's Cosine proposal has no device form: Normal
+               "rwm": [api.RWM("theta", 50.0, proposal="cosine"), api.RWM("mu", 50.0), sl]}
     ref = {"theta": (1526.7186, 0.37724897, 24.5), "s2_within": (2887.5853, 76.89117959, 1075.0), "mu[1]": (1511.4798, 0.52158448, 21.0),
            "mu[5]": (1578.6636, 1.29216105, 25.0), "mu[6]": (1487.1934, 1.23710390, 25.0)}
     for name, scheme in schemes.items():
@@ -98,7 +98,7 @@ def test_dyes_example_all_four_schemes():
         else:
             check_table(sim, ref, extra_sd=0.05)
     with pytest.raises(api.ArgumentError):
-        api.RWM("theta", 50.0, proposal="cosine")
+        api.RWM("theta", 50.0, proposal="laplace")        # not a SymDistributionType (src/distributions/extensions.jl:51-53)
 
 
 def test_salm_and_equiv_examples():

@@ -147,6 +147,10 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("line_rwm", 500, 0, 1),
     ("line_rwm_unif", 500, 0, 1),
     ("line_rwm_tri", 500, 0, 1),
+    ("line_rwm_cos", 500, 0, 1),
+    ("line_rwm_epa", 500, 0, 1),
+    ("line_rwm_biw", 500, 0, 1),
+    ("line_rwm_trw", 500, 0, 1),
     ("line_slice_uni", 400, 100, 1),
     ("line_amm", 500, 250, 1),
     ("line_hmc", 300, 0, 1),

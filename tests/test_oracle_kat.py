@@ -308,3 +308,20 @@ def test_node_logpdf_is_the_sum_of_scipy_densities(oracle):
     want_all = want_y + np.array([st.expon.logpdf(s[0], scale=1.0) + st.gamma.logpdf(s[1], 0.1, scale=1.0)
                                   + st.gamma.logpdf(s[2:], s[0], scale=1.0 / s[1]).sum() for s in S])
     np.testing.assert_allclose(o.logpdf_nodes(0b1111, S), want_all, rtol=1e-11)
+
+
+def test_rwm_proposal_kernels_have_the_right_distribution(oracle):
+    """RWM proposals (src/samplers/rwm.jl:65-71 draws rand(proposal(0, 1)); SymDistributionType, src/distributions/extensions.jl:51-53):
+    support [-1, 1], variance and CDF of the Cosine, Epanechnikov, Biweight and Triweight kernels (Kolmogorov-Smirnov against the closed forms)."""
+    import scipy.stats as st
+    cdf = {3: lambda z: 0.5 * (1 + z + np.sin(np.pi * z) / np.pi),
+           4: lambda z: 0.5 + 0.75 * (z - z ** 3 / 3),
+           5: lambda z: 0.5 + (15.0 / 16.0) * (z - 2 * z ** 3 / 3 + z ** 5 / 5),
+           6: lambda z: 0.5 + (35.0 / 32.0) * (z - z ** 3 + 3 * z ** 5 / 5 - z ** 7 / 7)}
+    var = {3: 1.0 / 3.0 - 2.0 / np.pi ** 2, 4: 0.2, 5: 1.0 / 7.0, 6: 1.0 / 9.0}
+    for code in (3, 4, 5, 6):
+        z = oracle.rwm_draws(code, 99, 200000)
+        assert z.min() >= -1.0 and z.max() <= 1.0
+        assert abs(z.mean()) < 4 * np.sqrt(var[code] / z.size)
+        np.testing.assert_allclose(z.var(), var[code], rtol=0.02)
+        assert st.kstest(z, cdf[code]).pvalue > 1e-3
