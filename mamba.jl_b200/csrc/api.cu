@@ -160,6 +160,11 @@ void default_inputs(mcu_ctx* h) {
       in["rc"] = {3, 14, 11, 127, 27, 6, 152, 48, 37, 188, 52, 47, 16, 45, 31, 38, 12, 6, 3, 40, 43, 39};
       in["nc"] = {39, 116, 93, 1520, 365, 52, 939, 471, 282, 1921, 583, 266, 293, 883, 147, 213, 122, 154, 134, 218, 364, 674};
       break;
+    case MCU_TPL_STACKS:  // doc/examples/stacks.jl:4-30 (x: 21 x 3, row-major)
+      in["y"] = {42, 37, 37, 28, 18, 18, 19, 20, 15, 14, 14, 13, 11, 12, 8, 7, 8, 8, 9, 15, 15};
+      in["x"] = {80, 27, 89, 80, 27, 88, 75, 25, 90, 62, 24, 87, 62, 22, 87, 62, 23, 87, 62, 24, 93, 62, 24, 93, 58, 23, 87, 58, 18, 80, 58, 18, 89,
+                 58, 17, 88, 58, 18, 82, 58, 19, 93, 50, 18, 89, 50, 18, 86, 50, 19, 72, 50, 19, 79, 50, 20, 80, 56, 20, 82, 70, 20, 91};
+      break;
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -179,6 +184,14 @@ int upload_inputs(mcu_ctx* h) {
   if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
   auto in = h->inputs;   // derived arrays
   if (h->tpl == MCU_TPL_SEEDS || h->tpl == MCU_TPL_SURGICAL) in["lc"] = lchoose_vec(in["n"], in["r"]);
+  if (h->tpl == MCU_TPL_STACKS) {   // meanx, sdx (sample sd), z = (x - meanx) / sdx: stacks.jl:32-37
+    const auto& x = in["x"]; const int N = (int)in["y"].size();
+    std::vector<double> mean(3, 0.0), sd(3, 0.0), z((size_t)N * 3);
+    for (int j = 0; j < 3; ++j) { for (int i = 0; i < N; ++i) mean[j] += x[i * 3 + j]; mean[j] /= N; }
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int i = 0; i < N; ++i) { const double e = x[i * 3 + j] - mean[j]; s += e * e; } sd[j] = std::sqrt(s / (N - 1)); }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) z[i * 3 + j] = (x[i * 3 + j] - mean[j]) / sd[j];
+    in["meanx"] = mean; in["sdx"] = sd; in["z"] = z;
+  }
   if (h->tpl == MCU_TPL_BLOCKER) { in["lcc"] = lchoose_vec(in["nc"], in["rc"]); in["lct"] = lchoose_vec(in["nt"], in["rt"]); }
   if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
@@ -228,6 +241,9 @@ template <> struct Host<BlockerModel> {
     return {h->d_inputs["rc"], h->d_inputs["nc"], h->d_inputs["rt"], h->d_inputs["nt"], h->d_inputs["lcc"], h->d_inputs["lct"], (int)h->inputs["rc"].size()};
   }
 };
+template <> struct Host<StacksModel> {
+  static StacksModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["z"], h->d_inputs["meanx"], h->d_inputs["sdx"], (int)h->inputs["y"].size()}; }
+};
 template <> struct Host<SurgicalModel> {
   static SurgicalModel::Data data(mcu_ctx* h) { return {h->d_inputs["r"], h->d_inputs["n"], h->d_inputs["lc"], (int)h->inputs["r"].size()}; }
 };
@@ -251,6 +267,7 @@ template <> struct Host<GlmM> {
     case MCU_TPL_DYES: { typedef DyesModel M; BODY; break; }                       \
     case MCU_TPL_SALM: { typedef SalmModel M; BODY; break; }                       \
     case MCU_TPL_BLOCKER: { typedef BlockerModel M; BODY; break; }                 \
+    case MCU_TPL_STACKS: { typedef StacksModel M; BODY; break; }                   \
     case MCU_TPL_EQUIV: { typedef EquivModel M; BODY; break; }                     \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
@@ -273,6 +290,7 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_DYES: return tpl_info_fixed<DyesModel>();
     case MCU_TPL_SALM: return tpl_info_fixed<SalmModel>();
     case MCU_TPL_BLOCKER: return tpl_info_fixed<BlockerModel>();
+    case MCU_TPL_STACKS: return tpl_info_fixed<StacksModel>();
     case MCU_TPL_EQUIV: return tpl_info_fixed<EquivModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
@@ -298,6 +316,7 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_DYES: return DyesModel::monitor_names();
       case MCU_TPL_SALM: return SalmModel::monitor_names();
       case MCU_TPL_BLOCKER: return BlockerModel::monitor_names();
+      case MCU_TPL_STACKS: return StacksModel::monitor_names();
       case MCU_TPL_EQUIV: return EquivModel::monitor_names();
       default: break;
     }
@@ -596,6 +615,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_PUMPS && n != (size_t)PumpsModel::NPUMP) return fail(h, MCU_ERR_DIM, "pumps inputs have 10 entries");
     if (h->tpl == MCU_TPL_SURGICAL && n != (size_t)SurgicalModel::NH) return fail(h, MCU_ERR_DIM, "surgical inputs have 12 entries");
     if (h->tpl == MCU_TPL_DYES && n != 30) return fail(h, MCU_ERR_DIM, "dyes inputs have 30 entries");
+    if (h->tpl == MCU_TPL_STACKS && n != (nm == "x" ? 63u : 21u)) return fail(h, MCU_ERR_DIM, "stacks inputs: y has 21 entries, x 21 x 3");
     if (h->tpl == MCU_TPL_BLOCKER && n != (size_t)BlockerModel::NT) return fail(h, MCU_ERR_DIM, "blocker inputs have 22 entries");
     if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
     if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");

@@ -228,6 +228,7 @@ static MCU_NOINL double rand_out(int kind, double a, double b, Draws& rng) {
   if (kind == OUT_NORMAL) return a + b * rng.normal();
   const double u = rng.uniform();
   if (kind == OUT_BERNOULLI) return u < a ? 1.0 : 0.0;
+  if (kind == OUT_LAPLACE) { const double c = u - 0.5; return a - b * (c < 0 ? -1.0 : 1.0) * log(1.0 - 2.0 * fabs(c)); }   // inverse CDF
   if (kind == OUT_BINOMIAL) {
     const double n = a, p = b, q = 1.0 - p;
     if (!(p > 0.0)) return 0.0;

@@ -27,6 +27,7 @@ MCU_DECLARE_TPL(DyesModel)
 MCU_DECLARE_TPL(SalmModel)
 MCU_DECLARE_TPL(EquivModel)
 MCU_DECLARE_TPL(BlockerModel)
+MCU_DECLARE_TPL(StacksModel)
 
 // fewer chains than one wave at the default occupancy (148 SMs x 4 blocks x 128 threads): the low-latency instantiation
 #ifdef MCU_GENERIC_MINB

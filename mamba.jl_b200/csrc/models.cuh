@@ -34,7 +34,7 @@ namespace mcu {
 
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 constexpr int LINK_IDENT = 0, LINK_LOG = 1, LINK_HEUR = -1;
-constexpr int OUT_NORMAL = 0, OUT_BINOMIAL = 1, OUT_POISSON = 2, OUT_BERNOULLI = 3;
+constexpr int OUT_NORMAL = 0, OUT_BINOMIAL = 1, OUT_POISSON = 2, OUT_BERNOULLI = 3, OUT_LAPLACE = 4;
 
 MCU_D double neg_inf() { return -CUDART_INF; }
 
@@ -81,6 +81,8 @@ MCU_D double lp_poisson(double y, double lgy1 /* lgamma(y+1) */, double lam) {
   if (lam == 0.0) return y == 0.0 ? 0.0 : neg_inf();
   return y * log(lam) - lam - lgy1;
 }
+// Laplace(location mu, scale theta): -(|x - mu| / theta + log(2 theta))
+MCU_D double lp_laplace(double x, double mu, double theta) { return -(fabs(x - mu) / theta + log(2.0 * theta)); }
 MCU_D double lp_bernoulli_logit(double y, double eta) {
   const double p = 1.0 / (exp(-eta) + 1.0);
   return y == 0.0 ? log(1.0 - p) : log(p);
@@ -570,6 +572,57 @@ struct BlockerModel {
     else { const int i = e - NT; a = d.nt[i]; b = 1.0 / (exp(-(s[3 + i] + s[3 + NT + i])) + 1.0); }
     return OUT_BINOMIAL;
   }
+};
+
+// =============================================================================== stacks
+// doc/examples/stacks.jl:41-94 (data :4-38): stack-loss regression on standardised covariates z with a Laplace likelihood,
+// y[i] ~ Laplace(beta0 + z[i,:] . beta, s2).  Every monitored quantity is a Logical node: b = beta ./ sdx, b0 = beta0 - b . meanx,
+// sigma = sqrt(2) s2, outlier[i] = |y[i] - mu[i]| / sigma > 2.5 for i in (1, 3, 4, 21).  State: beta0, beta[3], s2.
+struct StacksModel {
+  static constexpr int D = 5, NN = 3, NF = 4, P = 9, NOBS = 21;
+  struct Data { const double* y; const double* z; const double* meanx; const double* sdx; int N; };
+  MCU_HD static int node_off(int n) { return n == 0 ? 0 : (n == 1 ? 1 : 4); }
+  MCU_HD static int node_len(int n) { return n == 1 ? 3 : 1; }
+  MCU_HD static int node_link(int n) { return n == 2 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 3 ? 0x7u : 0u; }
+  MCU_HD static int mon_link(int) { return LINK_HEUR; }   // no monitored stochastic node
+  static const char* node_name(int n) { static const char* nm[] = {"beta0", "beta", "s2"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "b[1]\nb[2]\nb[3]\nb0\nsigma\noutlier[1]\noutlier[3]\noutlier[4]\noutlier[21]"; }
+  MCU_D static double mu(const Data& d, const double* s, int i) { return s[0] + (d.z[i * 3] * s[1] + d.z[i * 3 + 1] * s[2] + d.z[i * 3 + 2] * s[3]); }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f == 0) return lp_normal(s[0], 0.0, 1000.0);
+    if (f == 1) { double lp = 0.0; for (int j = 0; j < 3; ++j) lp += lp_normal(s[1 + j], 0.0, 1000.0); return lp; }
+    if (f == 2) return lp_invgamma(s[4], 0.001, 0.001, ig001_c0(), transform);
+    double lp = 0.0;
+    for (int i = 0; i < d.N; ++i) lp += lp_laplace(d.y[i], mu(d, s, i), s[4]);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double th = s[4];
+    double g0 = 0, g1 = 0, g2 = 0, g3 = 0, sabs = 0;
+    for (int i = 0; i < d.N; ++i) {
+      const double e = d.y[i] - mu(d, s, i);
+      const double sgn = e > 0 ? 1.0 : (e < 0 ? -1.0 : 0.0);
+      g0 += sgn; g1 += sgn * d.z[i * 3]; g2 += sgn * d.z[i * 3 + 1]; g3 += sgn * d.z[i * 3 + 2];
+      sabs += fabs(e);
+    }
+    g[0] = g0 / th - s[0] / 1e6; g[1] = g1 / th - s[1] / 1e6; g[2] = g2 / th - s[2] / 1e6; g[3] = g3 / th - s[3] / 1e6;
+    g[4] = -(double)d.N / th + sabs / (th * th) + d_invgamma(th, 0.001, 0.001);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data& d, const double* s, double* out) {
+    double dot = 0.0;
+    for (int j = 0; j < 3; ++j) { out[j] = s[1 + j] / d.sdx[j]; dot += out[j] * d.meanx[j]; }
+    out[3] = s[0] - dot;
+    const double sigma = sqrt(2.0) * s[4];
+    out[4] = sigma;
+    const int idx[4] = {0, 2, 3, 20};
+    for (int q = 0; q < 4; ++q) out[5 + q] = fabs((d.y[idx[q]] - mu(d, s, idx[q])) / sigma) > 2.5 ? 1.0 : 0.0;
+  }
+  MCU_HD static int out_len(const Data& d) { return d.N; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = mu(d, s, i); b = s[4]; return OUT_LAPLACE; }
 };
 
 // =============================================================================== glm (CUDA-core form)

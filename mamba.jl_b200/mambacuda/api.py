@@ -47,6 +47,7 @@ _TEMPLATES = {
     "equiv": dict(nodes=[("s2_2", 1), ("s2_1", 1), ("pi", 1), ("phi", 1), ("mu", 1), ("delta", 20)], inputs=["y", "group"], outputs=["y"]),
     "blocker": dict(nodes=[("s2", 1), ("d", 1), ("delta_new", 1), ("mu", 22), ("delta", 22)], inputs=["rc", "nc", "rt", "nt"], outputs=["rc", "rt"],
                     output_lens=[22, 22]),
+    "stacks": dict(nodes=[("beta0", 1), ("beta", 3), ("s2", 1)], inputs=["y", "x"], outputs=["y"]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 

@@ -35,17 +35,17 @@ inline double digamma(double x) {
   return r + std::log(x) - 0.5 / x + t;
 }
 
-enum DKind { D_NULL = 0, D_NORMAL, D_INVGAMMA, D_GAMMA, D_EXPONENTIAL, D_BINOMIAL, D_POISSON, D_BERNOULLI };
+enum DKind { D_NULL = 0, D_NORMAL, D_INVGAMMA, D_GAMMA, D_EXPONENTIAL, D_BINOMIAL, D_POISSON, D_BERNOULLI, D_LAPLACE };
 
 struct UDist {
   DKind k = D_NULL;
   double a = 0, b = 0;  // Normal(mu, sigma); InverseGamma(shape, scale); Gamma(shape, scale);
-                        // Exponential(scale); Binomial(n, p); Poisson(lambda); Bernoulli(p)
+                        // Exponential(scale); Binomial(n, p); Poisson(lambda); Bernoulli(p); Laplace(location, scale)
 };
 
 // @distr_support bounds of Distributions.jl
 inline double dmin(const UDist& d) {
-  switch (d.k) { case D_NORMAL: return NEG_INF; default: return 0.0; }
+  switch (d.k) { case D_NORMAL: case D_LAPLACE: return NEG_INF; default: return 0.0; }
 }
 inline double dmax(const UDist& d) {
   switch (d.k) {
@@ -93,6 +93,8 @@ inline double logpdf(const UDist& d, double x) {
     }
     case D_BERNOULLI:
       return x == 0.0 ? std::log(1.0 - d.a) : (x == 1.0 ? std::log(d.a) : NEG_INF);
+    case D_LAPLACE:   // Distributions/univariate/continuous/laplace.jl: -(|x - mu| / theta + log(2 theta))
+      return -(std::fabs(x - d.a) / d.b + std::log(2.0 * d.b));
     default: return 0.0;
   }
 }

@@ -219,6 +219,7 @@ static double rand_udist(const UDist& d, Rng& rng) {
   if (d.k == D_NORMAL) return d.a + d.b * rng.normal();
   const double u = rng.uniform();
   if (d.k == D_BERNOULLI) return u < d.a ? 1.0 : 0.0;
+  if (d.k == D_LAPLACE) { const double c = u - 0.5; return d.a - d.b * (c < 0 ? -1.0 : 1.0) * std::log(1.0 - 2.0 * std::fabs(c)); }   // inverse CDF
   if (d.k == D_BINOMIAL) {
     const double n = d.a, p = d.b, q = 1.0 - p;
     if (!(p > 0.0)) return 0.0;

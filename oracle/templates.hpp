@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9, TPL_STACKS = 10 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -548,6 +548,86 @@ inline Model make_blocker() {
   return m;
 }
 
+// ------------------------------------------------------------------------------------------
+// stacks: doc/examples/stacks.jl:41-94 (data :4-38): stack-loss regression on standardised covariates with a Laplace likelihood; every
+// monitored quantity is a Logical node (b, b0, sigma, outlier[1, 3, 4, 21]).  Node order beta0, beta, s2, b, b0, sigma, mu, outlier, y.
+inline std::vector<double> stacks_x() {   // 21 x 3, row-major
+  return {80, 27, 89, 80, 27, 88, 75, 25, 90, 62, 24, 87, 62, 22, 87, 62, 23, 87, 62, 24, 93, 62, 24, 93, 58, 23, 87, 58, 18, 80, 58, 18, 89,
+          58, 17, 88, 58, 18, 82, 58, 19, 93, 50, 18, 89, 50, 18, 86, 50, 19, 72, 50, 19, 79, 50, 20, 80, 56, 20, 82, 70, 20, 91};
+}
+inline Model make_stacks() {
+  Model m; m.template_id = TPL_STACKS;
+  m.inputs["y"] = {42, 37, 37, 28, 18, 18, 19, 20, 15, 14, 14, 13, 11, 12, 8, 7, 8, 8, 9, 15, 15};
+  m.inputs["x"] = stacks_x();
+  {   // meanx, sdx (sample sd), z = (x - meanx) / sdx: stacks.jl:32-37
+    const auto& x = m.inputs["x"]; const int N = 21;
+    std::vector<double> mean(3, 0.0), sd(3, 0.0), z(N * 3);
+    for (int j = 0; j < 3; ++j) { for (int i = 0; i < N; ++i) mean[j] += x[i * 3 + j]; mean[j] /= N; }
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int i = 0; i < N; ++i) { const double e = x[i * 3 + j] - mean[j]; s += e * e; } sd[j] = std::sqrt(s / (N - 1)); }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) z[i * 3 + j] = (x[i * 3 + j] - mean[j]) / sd[j];
+    m.inputs["meanx"] = mean; m.inputs["sdx"] = sd; m.inputs["z"] = z;
+  }
+  auto prior_n = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+  { Node n = make_node("beta0", true, 1, true, false); n.eval = prior_n; m.nodes.push_back(n); }              // 0
+  { Node n = make_node("beta", true, 3, false, false); n.eval = prior_n; m.nodes.push_back(n); }              // 1
+  { Node n = make_node("s2", true, 1, true, false);                                                            // 2
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b", false, 3, false, true);                                                            // 3: beta ./ sdx
+    n.sources = {1};
+    n.eval = [](const Model& mm, Node& l) { const auto& be = mm.val(1); const auto& sd = mm.in("sdx"); l.value.resize(3); for (int j = 0; j < 3; ++j) l.value[j] = be[j] / sd[j]; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b0", false, 1, true, true);                                                            // 4: beta0 - dot(b, meanx)
+    n.sources = {0, 3};
+    n.eval = [](const Model& mm, Node& l) { const auto& b = mm.val(3); const auto& mx = mm.in("meanx"); double s = 0; for (int j = 0; j < 3; ++j) s += b[j] * mx[j]; l.value.assign(1, mm.val(0)[0] - s); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("sigma", false, 1, true, true);                                                         // 5: sqrt(2) * s2
+    n.sources = {2};
+    n.eval = [](const Model& mm, Node& l) { l.value.assign(1, std::sqrt(2.0) * mm.val(2)[0]); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("mu", false, 21, false, false);                                                         // 6: beta0 + z * beta
+    n.sources = {0, 1};
+    n.eval = [](const Model& mm, Node& l) {
+      const auto& z = mm.in("z"); const auto& be = mm.val(1); const double b0 = mm.val(0)[0];
+      l.value.resize(21);
+      for (int i = 0; i < 21; ++i) { double s = 0; for (int j = 0; j < 3; ++j) s += z[i * 3 + j] * be[j]; l.value[i] = b0 + s; }
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("outlier", false, 21, false, false);                                                    // 7: |y - mu| / sigma > 2.5, monitor [1, 3, 4, 21]
+    n.monitor = {0, 2, 3, 20};
+    n.sources = {6, 5};
+    n.eval = [](const Model& mm, Node& l) {
+      const auto& y = mm.in("y"); const auto& mu = mm.val(6); const double sg = mm.val(5)[0];
+      l.value.resize(21);
+      for (int i = 0; i < 21; ++i) l.value[i] = std::fabs((y[i] - mu[i]) / sg) > 2.5 ? 1.0 : 0.0;
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 21, false, false, true);                                                     // 8: Laplace(mu[i], s2)
+    n.sources = {6, 2};
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& mu = mm.val(6); const double th = mm.val(2)[0];
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(21);
+      for (int i = 0; i < 21; ++i) s.distr.arr[i] = {D_LAPLACE, mu[i], th};
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: beta0, beta[3], s2
+    const auto& y = mm.in("y"); const auto& z = mm.in("z"); const auto& mu = mm.val(6); const auto& be = mm.val(1);
+    const double b0 = mm.val(0)[0], th = mm.val(2)[0];
+    double g0 = 0, gb[3] = {0, 0, 0}, sabs = 0;
+    for (int i = 0; i < 21; ++i) {
+      const double e = y[i] - mu[i];
+      const double sgn = e > 0 ? 1.0 : (e < 0 ? -1.0 : 0.0);
+      g0 += sgn; for (int j = 0; j < 3; ++j) gb[j] += sgn * z[i * 3 + j];
+      sabs += std::fabs(e);
+    }
+    g[0] = g0 / th - b0 / 1e6;
+    for (int j = 0; j < 3; ++j) g[1 + j] = gb[j] / th - be[j] / 1e6;
+    g[4] = -21.0 / th + sabs / (th * th) + ig_dlogpdf(0.001, 0.001, th);
+  };
+  m.finalize();
+  return m;
+}
+
 inline Model make_template(int id, int glm_d = 0) {
   switch (id) {
     case TPL_LINE: return make_line();
@@ -559,6 +639,7 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_DYES: return make_dyes();
     case TPL_SALM: return make_salm();
     case TPL_BLOCKER: return make_blocker();
+    case TPL_STACKS: return make_stacks();
     case TPL_EQUIV: return make_equiv();
     default: throw std::runtime_error("unknown template");
   }

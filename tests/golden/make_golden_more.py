@@ -81,9 +81,35 @@ def blocker_blocks(D, s):   # state: s2, d, delta_new, mu[22], delta[22]
             "rc": lc, "rt": lt}
 
 
+def stacks_data():
+    src = open(f"{REF}/doc/examples/stacks.jl").read()
+    y = np.array(nums(re.search(r":y => \[(.*?)\]", src, re.S).group(1)))
+    x = np.array(nums(re.search(r":x =>\s*\[(.*?)\]", src, re.S).group(1))).reshape(21, 3)
+    return {"y": y, "x": x}
+
+
+def stacks_blocks(D, s):    # state: beta0, beta[3], s2
+    b0, be, s2 = s[0], s[1:4], s[4]
+    z = (D["x"] - D["x"].mean(axis=0)) / D["x"].std(axis=0, ddof=1)                # stacks.jl:32-37
+    lik = st.laplace.logpdf(D["y"], b0 + z @ be, s2).sum()                          # Laplace(mu[i], s2): stacks.jl:45
+    pb = normal(np.concatenate([[b0], be]), 0, 1000.0).sum()
+    ps2 = invgamma(s2, 0.001, 0.001)
+    return {"nuts_beta0_beta": pb + lik, "slice_s2": ps2 + lik, "y": lik}            # NUTS([:beta0, :beta]), Slice(:s2, 1.0): stacks.jl:104-105
+
+
+def stacks_monitor(D, s):   # b[3], b0, sigma, outlier[1, 3, 4, 21]: stacks.jl:68-88
+    b0, be, s2 = s[0], s[1:4], s[4]
+    mx, sx = D["x"].mean(axis=0), D["x"].std(axis=0, ddof=1)
+    z = (D["x"] - mx) / sx
+    b = be / sx
+    sigma = np.sqrt(2.0) * s2
+    out = (np.abs((D["y"] - (b0 + z @ be)) / sigma) > 2.5).astype(float)
+    return np.concatenate([b, [b0 - b @ mx, sigma], out[[0, 2, 3, 20]]])
+
+
 def main():
     rng = np.random.default_rng(20261020)
-    D = {"salm": salm_data(), "equiv": equiv_data(), "blocker": blocker_data()}
+    D = {"salm": salm_data(), "equiv": equiv_data(), "blocker": blocker_data(), "stacks": stacks_data()}
     n = 12
     S = {"salm": np.column_stack([rng.gamma(2, 0.05, n), rng.normal(-0.001, 0.0005, n), rng.normal(0.35, 0.1, n), rng.normal(2.0, 0.3, n),
                                   rng.normal(0, 0.25, (n, 18))]),
@@ -92,12 +118,15 @@ def main():
     rng_b = np.random.default_rng(20261021)
     S["blocker"] = np.column_stack([rng_b.gamma(2, 0.01, n), rng_b.normal(-0.25, 0.06, n), rng_b.normal(-0.25, 0.15, n), rng_b.normal(-2.2, 0.4, (n, 22)),
                                     rng_b.normal(-0.25, 0.15, (n, 22))])
-    fn = {"salm": salm_blocks, "equiv": equiv_blocks, "blocker": blocker_blocks}
+    rng_s = np.random.default_rng(20261022)
+    S["stacks"] = np.column_stack([rng_s.normal(17.5, 1.0, n), rng_s.normal(0, 2.0, (n, 3)) + [7.7, 2.4, -1.0], rng_s.gamma(6, 0.45, n)])
+    fn = {"salm": salm_blocks, "equiv": equiv_blocks, "blocker": blocker_blocks, "stacks": stacks_blocks}
     out = {"_about": "block_logpdf fixtures for salm and equiv; see make_golden_more.py",
            "data": {k: {kk: vv.tolist() for kk, vv in v.items()} for k, v in D.items()}, "blocks": {}}
-    for tpl in ("salm", "equiv", "blocker"):
+    for tpl in ("salm", "equiv", "blocker", "stacks"):
         vals = [fn[tpl](D[tpl], s) for s in S[tpl]]
         out["blocks"][tpl] = {"states": S[tpl].tolist(), "logpdf": {k: [float(v[k]) for v in vals] for k in vals[0]}}
+    out["blocks"]["stacks"]["monitor"] = [stacks_monitor(D["stacks"], s).tolist() for s in S["stacks"]]
     with open(os.path.join(HERE, "block_logpdf_more.json"), "w") as f:
         json.dump(out, f)
     print("wrote block_logpdf_more.json")

@@ -25,6 +25,9 @@ EQUIV_INITS = np.array([[1.0, 1.0, 0.0, 0.0, 0.0] + [0.0] * 20, [10.0, 10.0, 10.
 BLOCKER_INITS = np.array([[1.0, 0.0, 0.0] + [0.0] * 44, [10.0, 2.0, 2.0] + [2.0] * 44])                 # doc/examples/blocker.jl:73-78 (s2, d, delta_new, mu, delta)
 
 
+STACKS_INITS = np.array([[10.0, 0.0, 0.0, 0.0, 10.0], [1.0, 1.0, 1.0, 1.0, 1.0]])                       # doc/examples/stacks.jl:98-101 (beta0, beta[3], s2)
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -83,6 +86,9 @@ SCHEMES = {
     "blocker_amwg_slice": ("blocker", [dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1),
                                        dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], BLOCKER_INITS),
     "blocker_nuts_slice": ("blocker", [dict(kind="nuts", nodes=[3, 4, 2]), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], BLOCKER_INITS),
+    # doc/examples/stacks.jl:104-105: NUTS([:beta0, :beta]), Slice(:s2, 1.0)
+    "stacks_nuts_slice": ("stacks", [dict(kind="nuts", nodes=[0, 1]), dict(kind="slice_multi", nodes=[2], scale=1.0)], STACKS_INITS),
+    "stacks_amwg": ("stacks", [dict(kind="amwg", nodes=[0, 1], scale=1.0), dict(kind="amwg", nodes=[2], scale=0.5)], STACKS_INITS),
     # doc/examples/equiv.jl:89-91: NUTS(:delta), Slice([:mu, :phi, :pi], 1.0), Slice([:s2_1, :s2_2], 1.0, Univariate)
     "equiv_nuts_slice": ("equiv", [dict(kind="nuts", nodes=[5]), dict(kind="slice_multi", nodes=[4, 3, 2], scale=1.0),
                                    dict(kind="slice_uni", nodes=[1, 0], scale=1.0)], EQUIV_INITS),

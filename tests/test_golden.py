@@ -57,6 +57,10 @@ BLOCKS = {
         "amwg_delta_delta_new": ([dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], 1),
         "slice_d_s2": ([dict(kind="amwg", nodes=[3], scale=0.1), dict(kind="amwg", nodes=[4, 2], scale=0.1), dict(kind="slice_multi", nodes=[1, 0], scale=1.0)], 2),
     },
+    "stacks": {
+        "nuts_beta0_beta": ([dict(kind="nuts", nodes=[0, 1]), dict(kind="slice_multi", nodes=[2], scale=1.0)], 0),
+        "slice_s2": ([dict(kind="nuts", nodes=[0, 1]), dict(kind="slice_multi", nodes=[2], scale=1.0)], 1),
+    },
     "pumps": {
         "alpha_beta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 0),
         "theta_constrained": ([dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], 1),
@@ -118,7 +122,7 @@ def test_oracle_extra_template_block_densities_match_golden(oracle, gold_extra, 
         np.testing.assert_allclose(o.logpdf(bi, S), gold_extra["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
 
 
-@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker"])
+@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker", "stacks"])
 def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
     S = np.array(gold_more["blocks"][tpl]["states"])
     for key, (blocks, bi) in BLOCKS[tpl].items():
@@ -126,7 +130,7 @@ def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
         o.set_scheme(_oracle_blocks(blocks))
         np.testing.assert_allclose(o.logpdf(bi, S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
     o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(next(iter(BLOCKS[tpl].values()))[0]))
-    nn = {"salm": 5, "equiv": 6, "blocker": 5}[tpl]
+    nn = {"salm": 5, "equiv": 6, "blocker": 5, "stacks": 3}[tpl]
     for q, key in enumerate(["rc", "rt"] if tpl == "blocker" else ["y"]):                                          # observed nodes, one at a time
         np.testing.assert_allclose(o.logpdf_nodes(1 << (nn + q), S), gold_more["blocks"][tpl]["logpdf"][key], rtol=1e-11)
     # analytic gradient of the joint against central differences of the block density that holds every parameter node
@@ -134,7 +138,14 @@ def test_oracle_salm_equiv_block_densities_match_golden(oracle, gold_more, tpl):
     o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(allb))
     lp_a, g_a = o.gradlogpdf(0, S, mode=0)
     lp_c, g_c = o.gradlogpdf(0, S, mode=2)
-    np.testing.assert_allclose(g_a, g_c, rtol=2e-5, atol=1e-4 * np.abs(g_c).max())
+    np.testing.assert_allclose(g_a, g_c, rtol=2e-5, atol=1e-4 * np.abs(g_c).max())   # (stacks: |y - mu| is piecewise linear, no kink within 6e-6 of these states)
+    if tpl == "stacks":   # the monitored columns are all Logical nodes: b, b0, sigma, outlier[1, 3, 4, 21]
+        still = [dict(kind="rwm", nodes=[0, 1, 2], scale=0.0)]          # a random walk of step 0: one "iteration" records unlist(m, true) at S
+        o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(still))
+        out, st, _ = o.run(len(S), S, 1, burnin=0, thin=1, seed=1)
+        assert o.names() == ["b[1]", "b[2]", "b[3]", "b0", "sigma", "outlier[1]", "outlier[3]", "outlier[4]", "outlier[21]"]
+        np.testing.assert_array_equal(st, S)
+        np.testing.assert_allclose(out[0].T, gold_more["blocks"]["stacks"]["monitor"], rtol=1e-12)
 
 
 def test_oracle_glm_density_and_gradient_match_golden(oracle, gold):
@@ -237,7 +248,7 @@ def test_gpu_extra_template_block_densities_match_golden(gold_extra, tpl):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker"])
+@pytest.mark.parametrize("tpl", ["salm", "equiv", "blocker", "stacks"])
 def test_gpu_salm_equiv_block_densities_match_golden(gold_more, tpl):
     from mambacuda.engine import Engine
     S = np.array(gold_more["blocks"][tpl]["states"])
@@ -248,6 +259,12 @@ def test_gpu_salm_equiv_block_densities_match_golden(gold_more, tpl):
         nn, nf = eng.factor_counts()
         for q, okey in enumerate(["rc", "rt"] if tpl == "blocker" else ["y"]):
             np.testing.assert_allclose(eng.logpdf_nodes(1 << (nn + q), S), gold_more["blocks"][tpl]["logpdf"][okey], rtol=1e-11)
+        eng.close()
+    if tpl == "stacks":   # Logical monitored columns at fixed states (a random walk of step 0 records unlist(m, true))
+        eng = Engine(tpl, len(S))
+        eng.set_scheme([dict(kind="rwm", nodes=[0, 1, 2], scale=0.0)]); eng.set_inits(S)
+        out = eng.run(1, burnin=0, thin=1)
+        np.testing.assert_allclose(out[0].T, gold_more["blocks"]["stacks"]["monitor"], rtol=1e-12)
         eng.close()
 
 

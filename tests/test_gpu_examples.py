@@ -123,6 +123,24 @@ def test_salm_and_equiv_examples():
     assert sim.indiscretesupport((0, 1))[sim.names.index("equiv")] and not sim.indiscretesupport()[0]
 
 
+def test_stacks_example():
+    # doc/examples/stacks.jl:96-111 → doc/examples/stacks.rst:42-51: Laplace likelihood, every monitored column a Logical node
+    from mambacuda import api
+    model = api.Model("stacks")
+    api.setsamplers(model, [api.NUTS(["beta0", "beta"]), api.Slice("s2", 1.0)])
+    inits = [dict(beta0=10, beta=[0, 0, 0], s2=10), dict(beta0=1, beta=[1, 1, 1], s2=1)]
+    sim = api.mcmc(model, {}, inits * 8, 10000, burnin=2500, thin=2, chains=16)
+    assert sim.names == ["b[1]", "b[2]", "b[3]", "b0", "sigma", "outlier[1]", "outlier[3]", "outlier[4]", "outlier[21]"]
+    check_table(sim, {"b[1]": (0.836863707, 0.0027601754, 0.1309), "b[2]": (0.744454449, 0.0065756939, 0.3348), "b[3]": (-0.116648437, 0.0015143922, 0.1221),
+                      "b0": (-38.776564595, 0.0979006137, 8.819), "sigma": (3.487643717, 0.0279025494, 0.8761), "outlier[1]": (0.042666667, 0.0029490162, 0.2021),
+                      "outlier[3]": (0.0548, 0.0034398827, 0.2276), "outlier[4]": (0.298, 0.0089200654, 0.4574), "outlier[21]": (0.6064, 0.0113877443, 0.4886)}, extra_sd=0.03)
+    assert sim.indiscretesupport((0, 1))[5:].all()                       # the outlier indicators
+    codes = sim.link_codes()                                             # link(c): sigma > 0 -> log; b[3] changes sign, indicators contain zeros -> identity
+    assert codes[4] == 1 and codes[2] == 0 and (codes[5:] == 0).all()
+    with pytest.raises(api.ArgumentError, match="chain values are missing for nodes : beta0, beta, s2"):
+        api.dic(sim)                                                     # the stochastic nodes are not monitored in this script
+
+
 def test_glm_through_the_api():
     # BASELINE.json configs[3] in miniature: Bernoulli-logit regression, NUTS(beta); the data go in through setinputs! (X, y)
     from mambacuda import api

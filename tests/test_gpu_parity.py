@@ -34,12 +34,12 @@ def random_states(inits, B, rng, D_pos):
     return st
 
 
-POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}, "salm": {0}, "equiv": {0, 1}, "blocker": {0}}
+POS = {"line": {2}, "seeds": {4}, "rats": {2, 3, 4}, "pumps": set(range(12)), "surgical": {1}, "dyes": {0, 2}, "salm": {0}, "equiv": {0, 1}, "blocker": {0}, "stacks": {4}}
 
 
 @pytest.mark.parametrize("name", ["line_amwg_slice", "line_nuts_all", "seeds_amwg", "seeds_amm", "rats_slice_amwg",
                                   "rats_nuts_slice", "pumps_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "surgical_amwg", "dyes_nuts_slice", "dyes_mala_slice", "dyes_hmc_slice",
-                                  "salm_slice_amwg", "equiv_nuts_slice", "equiv_amwg", "blocker_amwg_slice", "blocker_nuts_slice"])
+                                  "salm_slice_amwg", "equiv_nuts_slice", "equiv_amwg", "blocker_amwg_slice", "blocker_nuts_slice", "stacks_nuts_slice", "stacks_amwg"])
 def test_logpdf_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -66,7 +66,7 @@ def test_logpdf_out_of_support_is_minus_inf(oracle):
     assert np.all(np.isneginf(eng2.logpdf(0, in2, x))) and np.all(np.isneginf(orc2.logpdf(0, in2, x)))
 
 
-@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice", "equiv_nuts_slice", "blocker_nuts_slice"])
+@pytest.mark.parametrize("name", ["line_nuts_all", "line_nuts_slice", "rats_nuts_slice", "pumps_amwg_nuts", "seeds_amwg", "surgical_nuts_slice", "dyes_nuts_slice", "equiv_nuts_slice", "blocker_nuts_slice", "stacks_nuts_slice"])
 def test_gradient_matches_oracle(oracle, name):
     eng, orc, inits = make_pair(oracle, name, 4)
     tpl = helpers.SCHEMES[name][0]
@@ -142,6 +142,7 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("salm_slice_amwg", 300, 150, 2),
     ("equiv_amwg", 300, 150, 2),
     ("blocker_amwg_slice", 300, 150, 2),
+    ("stacks_amwg", 300, 150, 2),
     ("dyes_rwm_slice", 300, 0, 1),
     ("dyes_hmc_slice", 100, 0, 1),
     ("line_rwm", 500, 0, 1),
@@ -373,7 +374,7 @@ def test_gelman_logit_link_for_logical_columns_in_the_unit_interval(oracle):
     np.testing.assert_allclose(psrf_h, psrf_o, rtol=1e-7)
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice", "stacks_amwg"])
 def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     # logpdf(mc, nodekeys) (modelstats.jl:16-58): observed nodes only (the deviance of dic), every stochastic node, one parameter node
     eng, orc, inits = make_pair(oracle, tpl_scheme, 4)
@@ -389,7 +390,7 @@ def test_node_logpdf_matches_oracle(oracle, tpl_scheme):
     assert np.isfinite(joint).all()
 
 
-@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice"])
+@pytest.mark.parametrize("tpl_scheme", ["line_amwg_slice", "seeds_amwg", "rats_slice_amwg", "pumps_slice", "surgical_amwg", "dyes_nuts_slice", "salm_slice_amwg", "equiv_amwg", "blocker_amwg_slice", "stacks_amwg"])
 def test_predict_matches_oracle(oracle, tpl_scheme):
     # predict(mc) (modelstats.jl:63-96): rand of the observed node at each state, same Philox stream on both sides
     from mambacuda.engine import Engine

@@ -123,6 +123,18 @@ def test_blocker_reference_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_stacks_reference_scheme(oracle):
+    # doc/examples/stacks.jl:104-110 (NUTS([beta0, beta]) + Slice(s2, 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/stacks.rst:42-51
+    ref = {"b[1]": (0.836863707, 0.0027601754), "b[2]": (0.744454449, 0.0065756939), "b[3]": (-0.116648437, 0.0015143922),
+           "b0": (-38.776564595, 0.0979006137), "sigma": (3.487643717, 0.0279025494), "outlier[1]": (0.042666667, 0.0029490162),
+           "outlier[4]": (0.298, 0.0089200654), "outlier[21]": (0.6064, 0.0113877443)}
+    tpl, blocks, inits = helpers.scheme("stacks_nuts_slice")
+    ob = [helpers.oracle_block(b) for b in blocks]; ob[0]["max_depth"] = 10
+    o = oracle.Oracle(tpl); o.set_scheme(ob)
+    out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=9, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_surgical_reference_scheme(oracle):
     # doc/examples/surgical.jl:54-60 (NUTS(b) + Slice([mu, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/surgical.rst
     ref = {"mu": (-2.550263247, 0.00352027397), "pop_mean": (0.073062651, 0.00022880854), "s2": (0.183080212, 0.00629499754),
