@@ -51,6 +51,23 @@ struct BlockTarget {
     return lp;
   }
   MCU_D double logf(const double* x) const { relist(x); return eval(); }
+  MCU_D double inv(int i, double x) const { return (b.transform && b.elink[i] == LINK_LOG) ? exp(x) : x; }
+  MCU_D void put(int i, double x) const { s[b.elem[i]] = inv(i, x); }
+  // logpdf!(block, v) when v differs in component i only from the vector evaluated last (whose value is `cur` and which the state record
+  // still holds).  Where the template marks the element as local, only the terms that read it are re-evaluated:
+  //   logf(v') = logf(v) - terms(v) + terms(v')   — the reference re-evaluates the whole block (amwg.jl:100-106, slice.jl:80-88); every
+  // term that reads the element is the element's own prior term or belongs to a target of the block, so nothing else changes.
+  MCU_D double logf_comp(const double* v, int i, double cur) const {
+    const int e = b.elem[i];
+    if (M::elem_local(e) && isfinite(cur)) {
+      const bool tr = b.transform != 0;
+      const double t_old = M::elem_terms(d, s, e, tr);
+      s[e] = inv(i, v[i]);
+      const double t_new = M::elem_terms(d, s, e, tr);
+      return isnan(t_new) ? neg_inf() : (cur - t_old) + t_new;
+    }
+    return logf(v);
+  }
   MCU_NOINL void grad_analytic(const double* x, double* g) const {
     relist(x);
     double gj[M::D];

@@ -139,6 +139,8 @@ struct LineModel {
     g[1] = sxr / s[2] - s[1] / 1000.0;
     g[2] = -0.5 * (double)d.N / s[2] + 0.5 * srr / (s[2] * s[2]) + d_invgamma(s[2], 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int) { return false; }   // no element whose move touches only a few terms
+  MCU_D static double elem_terms(const Data&, const double*, int, bool) { return 0.0; }
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
@@ -190,6 +192,14 @@ struct SeedsModel {
     }
     g[0] = g0 - s[0] / 1e6; g[1] = g1 - s[1] / 1e6; g[2] = g2 - s[2] / 1e6; g[3] = g12 - s[3] / 1e6;
     g[4] = -0.5 * (double)d.N / s2 + 0.5 * sbb / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  // elem_local(e): a move of state element e changes only a few terms of the joint density; elem_terms = their sum at the current state
+  // (own prior term, with the log-Jacobian when the block samples on the transformed scale, + the likelihood terms that read e).
+  // The generic AMWG / univariate-slice samplers then form logf(v') = logf(v) - terms(v) + terms(v') instead of a full block evaluation.
+  MCU_HD static bool elem_local(int e) { return e >= 5; }
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e - 5;
+    return lp_normal(s[e], 0.0, sqrt(s[4])) + lp_binomial_logit(d.r[i], d.n[i], d.lc[i], eta(d, s, i));
   }
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
@@ -251,6 +261,14 @@ struct RatsModel {
     g[3] = -0.5 * NR / s2b + 0.5 * sbb / (s2b * s2b) + d_invgamma(s2b, 0.001, 0.001);
     g[4] = -0.5 * (double)d.N / s2c + 0.5 * see / (s2c * s2c) + d_invgamma(s2c, 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int e) { return e >= 5; }   // alpha_i, beta_i: own Normal term + rat i's five observations
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e < 35 ? e - 5 : e - 35;
+    const double own = e < 35 ? lp_normal(s[e], s[0], sqrt(s[2])) : lp_normal(s[e], s[1], sqrt(s[3]));
+    double sq = 0.0;
+    for (int k = 0; k < d.N; ++k) if (d.rat[k] == i) { const double r = d.y[k] - (s[5 + i] + s[35 + i] * d.Xm[k]); sq += r * r; }
+    return own - (sq / s[4]) / 2.0;
+  }
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
@@ -306,6 +324,13 @@ struct PumpsModel {
   }
   MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 12; ++j) out[j] = s[j]; }
   // conjugate full conditionals (MCU_GIBBS): theta_i | . ~ Gamma(alpha + y_i, 1/(beta + t_i)); beta | . ~ Gamma(0.1 + N alpha, 1/(1 + sum theta))
+  MCU_HD static bool elem_local(int e) { return e >= 2; }   // theta_i: its Gamma term + its Poisson term
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool transform) {
+    const int i = e - 2;
+    const double own = lp_gamma(s[e], s[0], 1.0 / s[1], transform);
+    if (!isfinite(own)) return own;                       // outside the support: the reference stops at the first non-finite partial sum
+    return own + lp_poisson(d.y[i], d.lgy1[i], s[e] * d.t[i]);
+  }
   MCU_HD static bool has_gibbs(int node) { return node == 1 || node == 2; }
   template <class R, class G>
   MCU_D static void gibbs(const Data& d, double* s, int node, R& rng, G rgamma) {
@@ -360,6 +385,11 @@ struct SurgicalModel {
     g[0] = sd / s2 - mu / 1e6;
     g[1] = -0.5 * (double)d.N / s2 + 0.5 * sdd / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int e) { return e >= 2; }   // b_i: its Normal term + its Binomial term
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e - 2;
+    return lp_normal(s[e], s[0], sqrt(s[1])) + lp_binomial_logit(d.r[i], d.n[i], d.lc[i], s[e]);
+  }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
@@ -404,6 +434,13 @@ struct DyesModel {
     g[1] = sd / s2b - th / 1e6;
     g[0] = -0.5 * NB / s2b + 0.5 * sdd / (s2b * s2b) + d_invgamma(s2b, 0.001, 0.001);
     g[2] = -0.5 * (double)d.N / s2w + 0.5 * see / (s2w * s2w) + d_invgamma(s2w, 0.001, 0.001);
+  }
+  MCU_HD static bool elem_local(int e) { return e >= 3; }   // mu_i: its Normal term + the five samples of batch i
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e - 3;
+    double sq = 0.0;
+    for (int k = 0; k < d.N; ++k) if (d.batch[k] == i) { const double r = d.y[k] - s[e]; sq += r * r; }
+    return lp_normal(s[e], s[1], sqrt(s[0])) - (sq / s[2]) / 2.0;
   }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
@@ -458,6 +495,11 @@ struct SalmModel {
     g[3] = ga - s[3] / 1e6; g[2] = gb - s[2] / 1e6; g[1] = gg - s[1] / 1e6;
     g[0] = -0.5 * (double)NY / s2 + 0.5 * sll / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int e) { return e >= 4; }   // lambda_ij: its Normal term + its Poisson term
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e - 4;
+    return lp_normal(s[e], 0.0, sqrt(s[0])) + lp_poisson(d.y[i], d.lgy1[i], mu(d, s, i));
+  }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 4; ++j) out[j] = s[j]; }
@@ -509,6 +551,11 @@ struct EquivModel {
     g[4] = gm - s[4] / 1e6; g[3] = gp - s[3] / 1e6; g[2] = gq - s[2] / 1e6;
     g[1] = -0.5 * (double)NY / s21 + 0.5 * see / (s21 * s21) + d_invgamma(s21, 0.001, 0.001);
     g[0] = -0.5 * (double)NY / s22 + 0.5 * sdd / (s22 * s22) + d_invgamma(s22, 0.001, 0.001);
+  }
+  MCU_HD static bool elem_local(int e) { return e >= 5; }   // delta_ij: its Normal term + its observation
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    const int i = e - 5;
+    return lp_normal(s[e], 0.0, sqrt(s[0])) + lp_normal(d.y[i], mean(d, s, i), sqrt(s[1]));
   }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
@@ -563,6 +610,16 @@ struct BlockerModel {
     g[1] = sd / s2 - dd / 1e6;
     g[0] = -0.5 * (double)(NT + 1) / s2 + 0.5 * sdd / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int e) { return e >= 2; }   // delta_new: one Normal; mu_i: prior + both arms of trial i; delta_i: prior + treated arm
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    if (e == 2) return lp_normal(s[2], s[1], sqrt(s[0]));
+    if (e < 3 + NT) {
+      const int i = e - 3;
+      return lp_normal(s[e], 0.0, 1000.0) + lp_binomial_logit(d.rc[i], d.nc[i], d.lcc[i], s[e]) + lp_binomial_logit(d.rt[i], d.nt[i], d.lct[i], s[e] + s[e + NT]);
+    }
+    const int i = e - 3 - NT;
+    return lp_normal(s[e], s[1], sqrt(s[0])) + lp_binomial_logit(d.rt[i], d.nt[i], d.lct[i], s[3 + i] + s[e]);
+  }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
@@ -610,6 +667,8 @@ struct StacksModel {
     g[0] = g0 / th - s[0] / 1e6; g[1] = g1 / th - s[1] / 1e6; g[2] = g2 / th - s[2] / 1e6; g[3] = g3 / th - s[3] / 1e6;
     g[4] = -(double)d.N / th + sabs / (th * th) + d_invgamma(th, 0.001, 0.001);
   }
+  MCU_HD static bool elem_local(int) { return false; }   // no element whose move touches only a few terms
+  MCU_D static double elem_terms(const Data&, const double*, int, bool) { return 0.0; }
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
@@ -661,6 +720,8 @@ struct GlmModel {
       for (int j = 0; j < d.d; ++j) g[j] += r * d.X[(size_t)i * d.d + j];
     }
   }
+  MCU_HD static bool elem_local(int) { return false; }   // no element whose move touches only a few terms
+  MCU_D static double elem_terms(const Data&, const double*, int, bool) { return 0.0; }
   MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) { for (int j = 0; j < d.d; ++j) out[j] = s[j]; }

@@ -62,12 +62,13 @@ MCU_NOINL void amwg_sample(double* v, const DevBlock& b, TuneRef tn, T& tgt, Dra
   for (int i = 0; i < k; ++i) {
     const double x = v[i];
     v[i] += z[i];
-    const double logfprime = tgt.logf(v);
+    const double logfprime = tgt.logf_comp(v, i, logf0);   // one component moved: local terms only where the template provides them
     if (rng.uniform() < exp(logfprime - logf0)) {
       logf0 = logfprime;
       if (adapt) tn[2 + k + i] += 1.0;
     } else {
       v[i] = x;
+      tgt.put(i, x);
     }
   }
   if (adapt) {
@@ -95,7 +96,7 @@ MCU_NOINL void slice_uni_sample(double* v, const DevBlock& b, T& tgt, Draws& rng
     const double x = v[i];
     v[i] = lower[i] + (upper[i] - lower[i]) * rng.uniform();
     while (true) {
-      logf0 = tgt.logf(v);
+      logf0 = tgt.logf_comp(v, i, logf0);   // logf0 is always the value at the vector the state record holds
       if (!(logf0 < p0)) break;
       const double value = v[i];
       if (value < x) lower[i] = value; else upper[i] = value;
