@@ -17,6 +17,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fastfn.cuh"
+
 namespace mcu {
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -48,12 +50,14 @@ __device__ __forceinline__ double box_muller_sin(double ua, double ub) {
 
 struct Draws {
   uint32_t k0, k1, chain, iter, blockkind, ku, kn;
+  uint32_t z_blk, u_blk;      // Philox block whose second draw is held in z_next / u_next (0xffffffff: none)
+  double z_next, u_next;
   const double* ext;          // EXTERNAL mode: this chain's stream, or nullptr
   unsigned long long ext_n;
   unsigned long long* ext_pos;  // this chain's cursor (persists across block updates and launches)
 
   __device__ __forceinline__ void seek(uint32_t it, uint32_t block, uint32_t kind) {
-    iter = it; blockkind = block | (kind << 16); ku = 0; kn = 0;
+    iter = it; blockkind = block | (kind << 16); ku = 0; kn = 0; z_blk = 0xffffffffu; u_blk = 0xffffffffu;
   }
   __device__ __forceinline__ double next_ext() {
     unsigned long long p = *ext_pos;
@@ -63,18 +67,24 @@ struct Draws {
   }
   __device__ __noinline__ double uniform() {
     if (ext) return next_ext();
+    if ((ku & 1u) && u_blk == (ku >> 1)) { ++ku; return u_next; }   // second half of the block drawn a call ago
     uint32_t w[4];
     philox4x32_10(ku >> 1, iter, chain, blockkind, k0, k1, w);
-    const double u = (ku & 1u) ? u53(w[2], w[3]) : u53(w[0], w[1]);
+    u_next = u53(w[2], w[3]); u_blk = ku >> 1;
+    const double u = (ku & 1u) ? u_next : u53(w[0], w[1]);
     ++ku;
     return u;
   }
   __device__ __noinline__ double normal() {
     if (ext) { const double a = next_ext(); const double b = next_ext(); return box_muller(a, b); }
+    if ((kn & 1u) && z_blk == (kn >> 1)) { ++kn; return z_next; }   // second draw of the block evaluated a call ago
     uint32_t w[4];
     philox4x32_10(kn >> 1, iter, chain, blockkind | (1u << 24), k0, k1, w);
-    const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
-    const double z = (kn & 1u) ? box_muller_sin(ua, ub) : box_muller(ua, ub);
+    // both Box-Muller branches from one log / sqrt / sin-cos evaluation (the same arithmetic as the fused kernels' draw_normal_pair)
+    const double rad = sqrt(-2.0 * fast_log(1.0 - u53(w[0], w[1])));
+    const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
+    z_next = rad * sc.a; z_blk = kn >> 1;
+    const double z = (kn & 1u) ? z_next : rad * sc.b;
     ++kn;
     return z;
   }
