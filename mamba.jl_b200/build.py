@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart"])
     return OUT
 
 

@@ -53,10 +53,6 @@ struct UStream {
   }
 };
 
-MCU_D double ig_term(double v, double c0) {   // InverseGamma(0.001, 0.001) on the constrained scale, -Inf outside the support
-  if (!(v >= 0.0)) return -CUDART_INF;
-  return c0 - 1.001 * fast_log(v) - 0.001 / v;
-}
 
 template <int BS>
 __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __grid_constant__ RatsFastCfg cfg, const __grid_constant__ RunArgs a) {

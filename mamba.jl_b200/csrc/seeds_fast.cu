@@ -30,6 +30,10 @@
 // FP64 throughout (the reference is Float64; a decision taken in FP32 would flip ~1e-7 of the time).
 #include <type_traits>
 
+#ifndef MCU_SEEDS_ESTRIN
+#define MCU_SEEDS_ESTRIN 0
+#endif
+#define MCU_FASTMATH_ESTRIN MCU_SEEDS_ESTRIN   // before the first include: fastfn.cuh comes in through launch.hpp
 #include "launch.hpp"
 
 #ifndef MCU_SEEDS_BW
@@ -42,9 +46,6 @@
 #ifndef MCU_SEEDS_PIPE
 #define MCU_SEEDS_PIPE 0   // b block: draws of trip t + 1 generated during trip t — measured 10 % SLOWER (profiles/r1_seeds_fast_summary.md), kept for the record
 #endif
-#ifndef MCU_SEEDS_ESTRIN
-#define MCU_SEEDS_ESTRIN 0
-#endif
 #ifndef MCU_SEEDS_BS
 #define MCU_SEEDS_BS 96
 #endif
@@ -52,7 +53,6 @@
 #define MCU_SEEDS_MINB 3
 #endif
 
-#define MCU_FASTMATH_ESTRIN MCU_SEEDS_ESTRIN
 #include "fastmath.cuh"
 
 namespace mcu {
@@ -78,12 +78,7 @@ struct FastCfg {
   double amm_SL[16], amm_beta, amm_scale;
 };
 
-// r log p + (n - r) log(1 - p) with p = invlogit(eta), written as r eta - n softplus(eta)
-MCU_D double binlogit_term(double r, double n, double eta) {
-  const double e = exp(-fabs(eta));
-  return r * eta - n * (fmax(eta, 0.0) + log1p(e));
-}
-
+#if !MCU_SEEDS_LOGU   // the u < exp(delta) form of the MH test (MCU_SEEDS_LOGU = 0)
 MCU_D bool mh_accept(double u, double delta) {   // rand() < exp(logfprime - logf0): amwg.jl:107
   if (delta >= 0.0) return true;                  // u < 1 <= exp(delta)
   if (!(delta > -700.0)) return false;            // exp underflows (or delta is NaN): u < 0 never holds
@@ -95,6 +90,7 @@ MCU_D bool mh_accept_nb(double u, double delta) {
   const double ex = fast_exp(fmax(fmin(delta, 0.0), -700.0));
   return delta >= 0.0 ? true : (delta > -700.0 && u < ex);
 }
+#endif
 
 struct Bases { double g0, g1, g2, g3; };
 MCU_D Bases group_bases(double a0, double a1, double a2, double a12) {
