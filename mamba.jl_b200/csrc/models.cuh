@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "fastfn.cuh"
+
 namespace mcu {
 
 #define MCU_HD __host__ __device__ __forceinline__
@@ -38,59 +40,72 @@ constexpr int OUT_NORMAL = 0, OUT_BINOMIAL = 1, OUT_POISSON = 2, OUT_BERNOULLI =
 
 MCU_D double neg_inf() { return -CUDART_INF; }
 
+// log / exp of the density formulas: the constant-bank fdlibm kernels of fastfn.cuh (< 1 ulp, no 64-bit immediates to materialise) on
+// their domain, libm outside it (zero, subnormal, infinite or NaN arguments; |x| >= 700 for exp)
+// Inlined by default (loop-invariant logs hoist out of the term loops: stacks 2x); a translation unit may define MCU_DENSITY_MATH_NOINLINE
+// to call them instead, which is faster where the inlined bodies push the kernel out of its register / instruction-cache budget
+// (measured per template, profiles/r1_templates_bench.json: surgical, blocker, equiv).
+#ifdef MCU_DENSITY_MATH_NOINLINE
+#define MCU_DMATH static __device__ __noinline__
+#else
+#define MCU_DMATH MCU_D
+#endif
+MCU_DMATH double flog(double x) { return (x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308) ? fast_log(x) : log(x); }
+MCU_DMATH double fexp(double x) { return (x > -700.0 && x < 700.0) ? fast_exp(x) : exp(x); }
+
 // ---- univariate log densities (Distributions.jl formulas) -------------------
 MCU_D double lp_normal(double x, double mu, double sigma) {
   if (isnan(x)) return neg_inf();
   const double z = (x - mu) / sigma;
-  return -(z * z + kLog2Pi) / 2.0 - log(sigma);
+  return -(z * z + kLog2Pi) / 2.0 - flog(sigma);
 }
-// InverseGamma(shape a, scale th), with lgamma(a) and a*log(th) folded into c0 = a*log(th) - lgamma(a)
+// InverseGamma(shape a, scale th), with lgamma(a) and a*flog(th) folded into c0 = a*flog(th) - lgamma(a)
 MCU_D double lp_invgamma(double x, double a, double th, double c0, bool transform) {
   if (!(x >= 0.0)) return neg_inf();
-  const double lx = log(x);
+  const double lx = flog(x);
   double lp = c0 - (a + 1.0) * lx - th / x;
   if (transform) lp += lx;
   return lp;
 }
 MCU_D double lp_gamma(double x, double a, double th, bool transform) {   // Gamma(shape a, scale th)
   if (!(x >= 0.0)) return neg_inf();
-  const double lx = log(x);
-  double lp = -lgamma(a) - a * log(th) + (a - 1.0) * lx - x / th;
+  const double lx = flog(x);
+  double lp = -lgamma(a) - a * flog(th) + (a - 1.0) * lx - x / th;
   if (transform) lp += lx;
   return lp;
 }
 MCU_D double lp_exponential(double x, double th, bool transform) {       // Exponential(scale th)
   if (!(x >= 0.0)) return neg_inf();
   const double lambda = 1.0 / th;
-  double lp = log(lambda) - lambda * x;
-  if (transform) lp += log(x);
+  double lp = flog(lambda) - lambda * x;
+  if (transform) lp += flog(x);
   return lp;
 }
 // Binomial(n, p = invlogit(eta)) at integer r, lc = lchoose(n, r) precomputed on the host
 MCU_D double lp_binomial_logit(double r, double n, double lc, double eta) {
-  const double p = 1.0 / (exp(-eta) + 1.0);      // invlogit: src/utils.jl:64
+  const double p = 1.0 / (fexp(-eta) + 1.0);      // invlogit: src/utils.jl:64
   const double q = 1.0 - p;
   if (p == 0.0) return r == 0.0 ? 0.0 : neg_inf();
   if (q == 0.0) return r == n ? 0.0 : neg_inf();
   double lp = lc;
-  if (r > 0.0) lp += r * log(p);
-  if (n - r > 0.0) lp += (n - r) * log(q);
+  if (r > 0.0) lp += r * flog(p);
+  if (n - r > 0.0) lp += (n - r) * flog(q);
   return lp;
 }
 MCU_D double lp_poisson(double y, double lgy1 /* lgamma(y+1) */, double lam) {
   if (lam == 0.0) return y == 0.0 ? 0.0 : neg_inf();
-  return y * log(lam) - lam - lgy1;
+  return y * flog(lam) - lam - lgy1;
 }
-// Laplace(location mu, scale theta): -(|x - mu| / theta + log(2 theta))
-MCU_D double lp_laplace(double x, double mu, double theta) { return -(fabs(x - mu) / theta + log(2.0 * theta)); }
+// Laplace(location mu, scale theta): -(|x - mu| / theta + flog(2 theta))
+MCU_D double lp_laplace(double x, double mu, double theta) { return -(fabs(x - mu) / theta + flog(2.0 * theta)); }
 MCU_D double lp_bernoulli_logit(double y, double eta) {
-  const double p = 1.0 / (exp(-eta) + 1.0);
-  return y == 0.0 ? log(1.0 - p) : log(p);
+  const double p = 1.0 / (fexp(-eta) + 1.0);
+  return y == 0.0 ? flog(1.0 - p) : flog(p);
 }
 // MvNormal(mu, sigma) isotropic: -(d log 2pi + d log sigma^2)/2 - (|x-mu|^2 / sigma^2)/2
 MCU_D double lp_isonormal(double sq, double d, double sigma) {
   const double v = sigma * sigma;
-  return -(d * kLog2Pi + d * log(v)) / 2.0 - (sq / v) / 2.0;
+  return -(d * kLog2Pi + d * flog(v)) / 2.0 - (sq / v) / 2.0;
 }
 MCU_D double d_invgamma(double x, double a, double th) { return -(a + 1.0) / x + th / (x * x); }
 
@@ -100,11 +115,11 @@ MCU_D double digamma_d(double x) {
   const double f = 1.0 / (x * x);
   const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 +
                    f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
-  return r + log(x) - 0.5 / x + t;
+  return r + flog(x) - 0.5 / x + t;
 }
 
-// c0 of InverseGamma(0.001, 0.001): 0.001*log(0.001) - lgamma(0.001)
-MCU_D double ig001_c0() { return 0.001 * log(0.001) - lgamma(0.001); }
+// c0 of InverseGamma(0.001, 0.001): 0.001*flog(0.001) - lgamma(0.001)
+MCU_D double ig001_c0() { return 0.001 * flog(0.001) - lgamma(0.001); }
 
 // =============================================================================== line
 struct LineModel {
@@ -184,7 +199,7 @@ struct SeedsModel {
     double g0 = 0, g1 = 0, g2 = 0, g12 = 0, sbb = 0;
     const double s2 = s[4];
     for (int i = 0; i < d.N; ++i) {
-      const double p = 1.0 / (exp(-eta(d, s, i)) + 1.0);
+      const double p = 1.0 / (fexp(-eta(d, s, i)) + 1.0);
       const double de = d.r[i] - d.n[i] * p;
       g0 += de; g1 += d.x1[i] * de; g2 += d.x2[i] * de; g12 += d.x1[i] * d.x2[i] * de;
       g[5 + i] = de - s[5 + i] / s2;
@@ -207,7 +222,7 @@ struct SeedsModel {
     for (int j = 0; j < 5; ++j) out[j] = s[j];
   }
   MCU_HD static int out_len(const Data& d) { return d.N; }
-  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (exp(-eta(d, s, i)) + 1.0); return OUT_BINOMIAL; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (fexp(-eta(d, s, i)) + 1.0); return OUT_BINOMIAL; }
 };
 
 // =============================================================================== rats
@@ -295,12 +310,12 @@ struct PumpsModel {
     if (f == 1) return lp_gamma(s[1], 0.1, 1.0, transform);
     if (f == 2) {  // theta ~ Gamma(alpha, 1 / beta), one distribution for the 10-vector
       const double a = s[0], th = 1.0 / s[1];
-      const double c = -lgamma(a) - a * log(th);
+      const double c = -lgamma(a) - a * flog(th);
       double lp = 0.0;
       for (int i = 0; i < d.N; ++i) {
         const double x = s[2 + i];
         if (!(x >= 0.0)) { lp += neg_inf(); continue; }
-        const double lx = log(x);
+        const double lx = flog(x);
         double t = c + (a - 1.0) * lx - x / th;
         if (transform) t += lx;
         lp += t;
@@ -317,9 +332,9 @@ struct PumpsModel {
     for (int i = 0; i < d.N; ++i) {
       const double th = s[2 + i];
       g[2 + i] = d.y[i] / th - d.t[i] + (al - 1.0) / th - be;
-      slog += log(th); sth += th;
+      slog += flog(th); sth += th;
     }
-    g[0] = N * log(be) + slog - N * digamma_d(al) - 1.0;
+    g[0] = N * flog(be) + slog - N * digamma_d(al) - 1.0;
     g[1] = N * al / be - sth + (0.1 - 1.0) / be - 1.0;
   }
   MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 12; ++j) out[j] = s[j]; }
@@ -378,7 +393,7 @@ struct SurgicalModel {
     const double mu = s[0], s2 = s[1];
     double sd = 0.0, sdd = 0.0;
     for (int i = 0; i < d.N; ++i) {
-      const double p = 1.0 / (exp(-s[2 + i]) + 1.0), db = s[2 + i] - mu;
+      const double p = 1.0 / (fexp(-s[2 + i]) + 1.0), db = s[2 + i] - mu;
       g[2 + i] = (d.r[i] - d.n[i] * p) - db / s2;
       sd += db; sdd += db * db;
     }
@@ -393,11 +408,11 @@ struct SurgicalModel {
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data& d, const double* s, double* out) {
-    out[0] = s[0]; out[1] = 1.0 / (exp(-s[0]) + 1.0); out[2] = s[1];   // pop_mean = invlogit(mu): surgical.jl:34-36
-    for (int i = 0; i < d.N; ++i) out[3 + i] = 1.0 / (exp(-s[2 + i]) + 1.0);   // p = invlogit(b): surgical.jl:19-21
+    out[0] = s[0]; out[1] = 1.0 / (fexp(-s[0]) + 1.0); out[2] = s[1];   // pop_mean = invlogit(mu): surgical.jl:34-36
+    for (int i = 0; i < d.N; ++i) out[3 + i] = 1.0 / (fexp(-s[2 + i]) + 1.0);   // p = invlogit(b): surgical.jl:19-21
   }
   MCU_HD static int out_len(const Data& d) { return d.N; }
-  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (exp(-s[2 + i]) + 1.0); return OUT_BINOMIAL; }
+  MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = d.n[i]; b = 1.0 / (fexp(-s[2 + i]) + 1.0); return OUT_BINOMIAL; }
 };
 
 // =============================================================================== dyes
@@ -465,9 +480,9 @@ struct SalmModel {
   static const char* node_name(int n) { static const char* nm[] = {"s2", "gamma", "beta", "alpha", "lambda"}; return nm[n]; }
   static const char* state_names() { return nullptr; }
   static const char* monitor_names() { return "s2\ngamma\nbeta\nalpha"; }
-  MCU_D static double mu(const Data& d, const double* s, int e) {   // exp(alpha + beta log(x_j + 10) + gamma x_j + lambda_ij): salm.jl:22
+  MCU_D static double mu(const Data& d, const double* s, int e) {   // fexp(alpha + beta flog(x_j + 10) + gamma x_j + lambda_ij): salm.jl:22
     const double x = d.x[e / NPLATE];
-    return exp(s[3] + s[2] * log(x + 10.0) + s[1] * x + s[4 + e]);
+    return fexp(s[3] + s[2] * flog(x + 10.0) + s[1] * x + s[4 + e]);
   }
   MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
     if (f == 0) return lp_invgamma(s[0], 0.001, 0.001, ig001_c0(), transform);
@@ -488,7 +503,7 @@ struct SalmModel {
     for (int e = 0; e < NY; ++e) {
       const double x = d.x[e / NPLATE];
       const double r = d.y[e] - mu(d, s, e);
-      ga += r; gb += r * log(x + 10.0); gg += r * x;
+      ga += r; gb += r * flog(x + 10.0); gg += r * x;
       g[4 + e] = r - s[4 + e] / s2;
       sll += s[4 + e] * s[4 + e];
     }
@@ -509,7 +524,7 @@ struct SalmModel {
 
 // =============================================================================== equiv
 // doc/examples/equiv.jl:25-75 (data :4-22): two-period crossover bioequivalence trial, 10 subjects x 2 periods, Normal responses with
-// treatment (phi), period (pi) and subject-by-period (delta) effects; theta = exp(phi) and equiv = 1{0.8 < theta < 1.2} are Logical.
+// treatment (phi), period (pi) and subject-by-period (delta) effects; theta = fexp(phi) and equiv = 1{0.8 < theta < 1.2} are Logical.
 // Matrices column-major (e = subject + 10 period).  State: s2_2, s2_1, pi, phi, mu, delta[20]; monitored s2_2, s2_1, pi, phi, theta,
 // equiv, mu (the order of doc/examples/equiv.rst).
 struct EquivModel {
@@ -560,7 +575,7 @@ struct EquivModel {
   MCU_HD static bool has_gibbs(int) { return false; }
   template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
   MCU_D static void monitor(const Data&, const double* s, double* out) {
-    const double theta = exp(s[3]);
+    const double theta = fexp(s[3]);
     out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; out[4] = theta; out[5] = (0.8 < theta && theta < 1.2) ? 1.0 : 0.0; out[6] = s[4];
   }
   MCU_HD static int out_len(const Data&) { return NY; }
@@ -601,7 +616,7 @@ struct BlockerModel {
     g[2] = -(s[2] - dd) / s2;
     for (int i = 0; i < NT; ++i) {
       const double mu = s[3 + i], dl = s[3 + NT + i];
-      const double pc = 1.0 / (exp(-mu) + 1.0), pt = 1.0 / (exp(-(mu + dl)) + 1.0);
+      const double pc = 1.0 / (fexp(-mu) + 1.0), pt = 1.0 / (fexp(-(mu + dl)) + 1.0);
       const double rt = d.rt[i] - d.nt[i] * pt;
       g[3 + i] = (d.rc[i] - d.nc[i] * pc) + rt - mu / 1e6;
       g[3 + NT + i] = rt - (dl - dd) / s2;
@@ -625,8 +640,8 @@ struct BlockerModel {
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
   MCU_HD static int out_len(const Data&) { return 2 * NT; }   // rc[22] then rt[22]
   MCU_D static int out_dist(const Data& d, const double* s, int e, double& a, double& b) {
-    if (e < NT) { a = d.nc[e]; b = 1.0 / (exp(-s[3 + e]) + 1.0); }
-    else { const int i = e - NT; a = d.nt[i]; b = 1.0 / (exp(-(s[3 + i] + s[3 + NT + i])) + 1.0); }
+    if (e < NT) { a = d.nc[e]; b = 1.0 / (fexp(-s[3 + e]) + 1.0); }
+    else { const int i = e - NT; a = d.nt[i]; b = 1.0 / (fexp(-(s[3 + i] + s[3 + NT + i])) + 1.0); }
     return OUT_BINOMIAL;
   }
 };
@@ -708,7 +723,7 @@ struct GlmModel {
     double lp = 0.0;
     for (int i = 0; i < d.N; ++i) {
       double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
-      lp += d.family == 1 ? lp_poisson(d.y[i], lgamma(d.y[i] + 1.0), exp(eta)) : d.family == 2 ? lp_normal(d.y[i], eta, d.sigma) : lp_bernoulli_logit(d.y[i], eta);
+      lp += d.family == 1 ? lp_poisson(d.y[i], lgamma(d.y[i] + 1.0), fexp(eta)) : d.family == 2 ? lp_normal(d.y[i], eta, d.sigma) : lp_bernoulli_logit(d.y[i], eta);
     }
     return lp;
   }
@@ -716,7 +731,7 @@ struct GlmModel {
     for (int j = 0; j < d.d; ++j) g[j] = -s[j] / 1000.0;
     for (int i = 0; i < d.N; ++i) {
       double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
-      const double r = d.family == 1 ? d.y[i] - exp(eta) : d.family == 2 ? (d.y[i] - eta) / (d.sigma * d.sigma) : d.y[i] - 1.0 / (exp(-eta) + 1.0);
+      const double r = d.family == 1 ? d.y[i] - fexp(eta) : d.family == 2 ? (d.y[i] - eta) / (d.sigma * d.sigma) : d.y[i] - 1.0 / (fexp(-eta) + 1.0);
       for (int j = 0; j < d.d; ++j) g[j] += r * d.X[(size_t)i * d.d + j];
     }
   }
@@ -728,9 +743,9 @@ struct GlmModel {
   MCU_HD static int out_len(const Data& d) { return d.N; }
   MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) {
     double eta = 0; for (int j = 0; j < d.d; ++j) eta += d.X[(size_t)i * d.d + j] * s[j];
-    if (d.family == 1) { a = exp(eta); b = 0.0; return OUT_POISSON; }
+    if (d.family == 1) { a = fexp(eta); b = 0.0; return OUT_POISSON; }
     if (d.family == 2) { a = eta; b = d.sigma; return OUT_NORMAL; }
-    a = 1.0 / (exp(-eta) + 1.0); b = 0.0; return OUT_BERNOULLI;
+    a = 1.0 / (fexp(-eta) + 1.0); b = 0.0; return OUT_BERNOULLI;
   }
 };
 
