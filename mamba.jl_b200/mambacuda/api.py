@@ -236,6 +236,16 @@ class Chains:
 
     def __init__(self, value, start=1, thin=1, names=None, chains=None):
         value = np.asarray(value, dtype=float)
+        if value.ndim == 2:                    # Chains(value::Matrix; ...): one chain (chains.jl:34-41)
+            value = value[:, :, None]
+            if isinstance(chains, (int, np.integer)):
+                chains = [int(chains)]
+        elif value.ndim == 1:                  # Chains(value::Vector; names = "Param1"): one parameter, one chain (chains.jl:43-49)
+            value = value[:, None, None]
+            if isinstance(names, str):
+                names = [names]
+            if isinstance(chains, (int, np.integer)):
+                chains = [int(chains)]
         if value.ndim != 3:
             raise DimensionMismatch("value must be iterations x parameters x chains")
         n, p, m = value.shape

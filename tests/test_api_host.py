@@ -56,6 +56,10 @@ def test_chains_container(mcu_built):
     assert (c.first, c.step, c.last) == (252, 2, 270) and c.chains == [1, 2, 3]     # chains.jl:14-32
     with pytest.raises(api.DimensionMismatch, match="names length differ"):
         api.Chains(np.zeros((10, 2, 3)), names=["a"])
+    m = api.Chains(np.zeros((10, 2)), start=5, names=["a", "b"], chains=4)            # matrix form: chains.jl:34-41
+    assert m.value.shape == (10, 2, 1) and m.chains == [4] and m.first == 5
+    v = api.Chains(np.arange(6.0), names="theta")                                       # vector form: chains.jl:43-49
+    assert v.value.shape == (6, 1, 1) and v.names == ["theta"] and v.chains == [1]
 
 
 def _toy_chains(n=40, p=3, m=2, start=11, thin=2, seed=0):
