@@ -270,7 +270,7 @@ def small_model_bench(args, rank, local_rank, world):
             line = {"metric": "chain_iters_per_sec", "value": world * C * iters / dt, "unit": "chain-iterations/s", "n_gpus": world, "steps": 1,
                     "warmup": 1, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                     "data": "reference data set", "config": {"workload": name, "chains_per_gpu": C, "iters": iters, "burnin": burnin, "thin": thin,
-                                                             "kernel": {"rats_nuts_slice": "rats_warp_kernel (one warp per chain)", "rats_slice_amwg": "rats_fast_kernel (fused)", "pumps_slice": "pumps_fast_kernel (fused)"}.get(name, "run_generic_kernel"), "kernel_ms": kms,
+                                                             "kernel": {"rats_nuts_slice": "rats_warp_kernel (one warp per chain)", "rats_slice_amwg": "rats_fast_kernel (fused)", "pumps_slice": "pumps_fast_kernel (fused)", "pumps_gibbs_amwg": "pumps_gibbs_kernel (fused)"}.get(name, "run_generic_kernel"), "kernel_ms": kms,
                                                              "psrf_max": None if psrf is None else float(np.nanmax(psrf[:, 0])),
                                                              "names": eng.names(1)[:12],
                                                              "posterior_mean": None if summ is None else [float(v) for v in summ[:12, 0]],

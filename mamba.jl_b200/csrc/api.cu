@@ -59,6 +59,7 @@ struct mcu_ctx {
   long long launches = 0;
   double last_ms = 0.0;
   bool seeds_fast_ok = false;
+  bool pumps_gibbs_ok = false;                                              // fused pumps Gibbs + AMWG kernel (pumps_fast.cu)
   bool pumps_fast_ok = false;                                               // fused pumps Slice kernel (pumps_fast.cu)
   bool rats_fast_ok = false;                                                // fused rats Slice + AMWG kernel (rats_fast.cu)
   bool rats_warp_ok = false; double* r_scratch = nullptr; int r_grid = 0;   // warp-per-chain rats kernel (rats_warp.cu)
@@ -400,6 +401,14 @@ bool scheme_is_pumps_fast(const mcu_ctx* h) {
   const DevBlock& a = h->h_blocks[0]; const DevBlock& b = h->h_blocks[1];
   return a.kind == MCU_SLICE_UNI && a.transform == 0 && a.n_own == 2 && a.own[0] == 0 && a.own[1] == 1 &&
          b.kind == MCU_SLICE_UNI && b.transform == 0 && b.n_own == 1 && b.own[0] == 2;
+}
+
+bool scheme_is_pumps_gibbs(const mcu_ctx* h) {
+  // Gibbs(theta), Gibbs(beta), AMWG(alpha): BASELINE.json configs[4] / SURVEY.md §8d config 5
+  if (h->tpl != MCU_TPL_PUMPS || h->h_blocks.size() != 3) return false;
+  const DevBlock* b = h->h_blocks.data();
+  return b[0].kind == MCU_GIBBS && b[0].n_own == 1 && b[0].own[0] == 2 && b[1].kind == MCU_GIBBS && b[1].n_own == 1 && b[1].own[0] == 1 &&
+         b[2].kind == MCU_AMWG && b[2].n_own == 1 && b[2].own[0] == 0;
 }
 
 bool scheme_is_rats_fast(const mcu_ctx* h) {
@@ -744,6 +753,7 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   h->rats_warp_ok = scheme_is_rats_warp(h);
   h->rats_fast_ok = scheme_is_rats_fast(h);
   h->pumps_fast_ok = scheme_is_pumps_fast(h);
+  h->pumps_gibbs_ok = scheme_is_pumps_gibbs(h);
   return MCU_OK;
 }
 
@@ -836,7 +846,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   }
   bool rats_fast = h->rats_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   const bool pumps_fast = h->pumps_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
-  if (fast || rats_warp || rats_fast || pumps_fast) chunk = iters;   // the fused kernels keep everything on chip for the whole call
+  const bool pumps_gibbs = h->pumps_gibbs_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  if (fast || rats_warp || rats_fast || pumps_fast || pumps_gibbs) chunk = iters;   // the fused kernels keep everything on chip for the whole call
   CK(cudaEventRecord(h->ev0, h->stream));
   long long done = 0;
   if (glm_tick) {
@@ -852,6 +863,9 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
       rc = seeds_fast_launch(h->inputs["r"].data(), h->inputs["n"].data(), h->inputs["x1"].data(), h->inputs["x2"].data(), a, h->h_blocks.data(),
                              h->h_scales, h->h_SigmaL.empty() || h->h_SigmaL[0].empty() ? nullptr : h->h_SigmaL[0].data(), h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
+    } else if (pumps_gibbs) {
+      rc = pumps_gibbs_launch(h->inputs["y"].data(), h->inputs["t"].data(), (int)h->inputs["y"].size(), a, h->h_blocks[2], h->h_scales[2][0], h->stream);
+      if (rc) return fail(h, MCU_ERR_CUDA, "pumps_gibbs launch failed");
     } else if (pumps_fast) {
       rc = pumps_fast_launch(h->inputs["y"].data(), h->inputs["t"].data(), (int)h->inputs["y"].size(), a, h->h_scales, h->stream);
       if (rc) return fail(h, MCU_ERR_CUDA, "pumps_fast launch failed");

@@ -78,6 +78,8 @@ int seeds_fast_launch(const double* r, const double* n, const double* x1, const 
 
 // fused pumps kernel for the reference's Slice scheme (pumps_fast.cu); returns 0 on success
 int pumps_fast_launch(const double* y, const double* t, int N, const RunArgs& a, const std::vector<std::vector<double>>& h_scales, cudaStream_t st);
+// fused pumps kernel for [Gibbs(theta), Gibbs(beta), AMWG(alpha)] (BASELINE.json configs[4]); `amwg` is the host copy of block 2
+int pumps_gibbs_launch(const double* y, const double* t, int N, const RunArgs& a, const DevBlock& amwg, double scale, cudaStream_t st);
 
 // fused rats kernel for the reference's Slice + AMWG scheme (rats_fast.cu); returns 0 on success, -2 if the data layout is not 30 x 5
 int rats_fast_launch(const double* y, const double* Xm, const double* rat, int N, double xbar, const RunArgs& a, const DevBlock* h_blocks,

@@ -136,7 +136,105 @@ __global__ void __launch_bounds__(BS, 8) pumps_fast_kernel(const __grid_constant
 #undef TH
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// BASELINE.json configs[4] / SURVEY.md §8d config 5: [Gibbs(theta), Gibbs(beta), AMWG(alpha)] — the conjugate full conditionals
+//   theta_i | . ~ Gamma(alpha + y_i, 1 / (beta + t_i)),  beta | . ~ Gamma(0.1 + 10 alpha, 1 / (1 + sum theta))      (models.cuh, PumpsModel::gibbs)
+// and a one-component AMWG update of alpha on x = log alpha (amwg.jl:99-115).  The draws are those of the generic kernel — the same
+// Draws cursor per block, the same Marsaglia-Tsang routine — so the Gibbs values are bit-identical; what changes is the AMWG target: the
+// ten Gamma(theta_i | alpha, 1/beta) terms enter through SL = sum log theta_i,
+//   logf(x') - logf(x) = -(a' - a) + (x' - x) + 10 ((a' - a) log beta - (lgamma(a') - lgamma(a))) + (a' - a) SL,      a = exp(x),
+// with lgamma(a) carried from the previous iteration (one lgamma per iteration instead of two block evaluations of ten terms each).
+struct PumpsGibbsCfg {
+  double y[NP], t[NP];
+  double scale, target;
+  int adapt, batchsize, tune_off;
+};
+
+#ifndef MCU_PUMPSG_MINB
+#define MCU_PUMPSG_MINB 12   // resident blocks per SM (measured 4 / 6 / 8 / 10 / 12 / 14 / 16: 2.6 / 2.9 / 3.0 / 3.1 / 3.4 / 3.3 / 3.3e9 chain-iterations/s at 1e7 chains)
+#endif
+template <int BS>
+__global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const __grid_constant__ PumpsGibbsCfg cfg, const __grid_constant__ RunArgs a) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const long long c = (long long)blockIdx.x * BS + tid;
+  if (c >= a.n_chains) return;
+  const size_t C = (size_t)a.n_chains;
+#define TH(i) smem[(i) * BS + tid]
+  double al = a.state[0 * C + c], be = a.state[1 * C + c];
+  for (int i = 0; i < NP; ++i) TH(i) = a.state[(size_t)(2 + i) * C + c];
+  // AMWG tune record of block 2: m, adapt flag, sigma, accept count (samplers.cuh, amwg_sample)
+  double* tn = a.tune + (size_t)cfg.tune_off * C + c;
+  double m = tn[0 * C], sigma = tn[2 * C], acc = tn[3 * C];
+  bool was = tn[1 * C] != 0.0;
+  double lg_al = lgamma(al);
+  Draws rng;
+  rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
+  rng.ext = nullptr; rng.ext_n = 0; rng.ext_pos = nullptr;
+
+  for (long long it = 1; it <= a.iters; ++it) {
+    const long long iter = a.iter0 + it;
+    const uint32_t it32 = (uint32_t)iter;
+    // ---- block 0: Gibbs(theta)
+    rng.seek(it32, 0, 0);
+#pragma unroll 1
+    for (int i = 0; i < NP; ++i) TH(i) = rgamma_mt(al + cfg.y[i], rng) / (be + cfg.t[i]);
+    // ---- block 1: Gibbs(beta)
+    rng.seek(it32, 1, 0);
+    double sth = 0.0, SL = 0.0;
+    for (int i = 0; i < NP; ++i) { const double th = TH(i); sth += th; SL += fast_log(th); }
+    be = rgamma_mt(0.1 + (double)NP * al, rng) / (1.0 + sth);
+    // ---- block 2: AMWG(alpha) on x = log alpha
+    rng.seek(it32, 2, 0);
+    const bool adapt = cfg.adapt == 1 ? iter <= a.burnin : cfg.adapt == 0;
+    if (iter == 1) { m = 0.0; was = false; sigma = cfg.scale; acc = 0.0; }      // AMWGTune(x, sigma): fresh at the first iteration
+    if (adapt && !was) { acc = 0.0; m = 0.0; }                                     // setadapt!: amwg.jl:88-96
+    was = adapt;
+    if (adapt) m += 1.0;
+    const double x = log(al);                                                      // unlist on the link scale ...
+    const double a0 = exp(x);                                                      // ... and relist: the generic kernel's round trip, kept bit for bit
+    const double z = sigma * rng.normal();
+    const double xn = x + z;
+    const double an = exp(xn);
+    const double lg_an = lgamma(an);
+    const double da = an - a0;
+    const double delta = -da + (xn - x) + (double)NP * (da * fast_log(be) - (lg_an - lg_al)) + da * SL;
+    if (rng.uniform() < exp(delta)) { al = an; lg_al = lg_an; if (adapt) acc += 1.0; }
+    else al = a0;
+    if (adapt && ((long long)m % cfg.batchsize) == 0) {                            // amwg.jl:74-80
+      const double dl = amwg_delta(m, cfg.batchsize);
+      sigma *= exp(acc / m < cfg.target ? -dl : dl);
+    }
+    // ---- thinning + streaming moments (mcmc.jl:76-78)
+    if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {
+      double mon[PumpsModel::P];
+      mon[0] = al; mon[1] = be;
+      for (int i = 0; i < NP; ++i) mon[2 + i] = TH(i);
+      if (a.samples) {
+        const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
+        for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
+      }
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
+    }
+  }
+  a.state[0 * C + c] = al; a.state[1 * C + c] = be;
+  for (int i = 0; i < NP; ++i) a.state[(size_t)(2 + i) * C + c] = TH(i);
+  tn[0 * C] = m; tn[1 * C] = was ? 1.0 : 0.0; tn[2 * C] = sigma; tn[3 * C] = acc;
+#undef TH
+}
+
 }  // namespace
+
+int pumps_gibbs_launch(const double* y, const double* t, int N, const RunArgs& a, const DevBlock& amwg, double scale, cudaStream_t st) {
+  if (N != NP) return -2;
+  PumpsGibbsCfg cfg;
+  for (int i = 0; i < NP; ++i) { cfg.y[i] = y[i]; cfg.t[i] = t[i]; }
+  cfg.scale = scale; cfg.target = amwg.target; cfg.adapt = amwg.adapt; cfg.batchsize = amwg.batchsize; cfg.tune_off = amwg.tune_off;
+  constexpr int BS = 128;
+  const size_t smem = (size_t)BS * NP * sizeof(double);
+  pumps_gibbs_kernel<BS><<<(unsigned)((a.n_chains + BS - 1) / BS), BS, smem, st>>>(cfg, a);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 int pumps_fast_launch(const double* y, const double* t, int N, const RunArgs& a, const std::vector<std::vector<double>>& h_scales, cudaStream_t st) {
   if (N != NP) return -2;

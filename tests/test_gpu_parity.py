@@ -507,6 +507,23 @@ def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):
         eng2.set_scheme([dict(kind="gibbs", nodes=[5])])
 
 
+def test_pumps_gibbs_kernel_matches_oracle_and_generic_and_restarts(oracle):
+    # fused [Gibbs(theta), Gibbs(beta), AMWG(alpha)] kernel (pumps_fast.cu): the Gibbs draws are the generic kernel's bit for bit, the AMWG
+    # target is evaluated on sufficient statistics
+    g, o, eng, _ = run_pair(oracle, "pumps_gibbs_amwg", 64, 300, 100, 2, force_generic=False)
+    assert_same_run(g, o, min_frac=0.9)
+    tpl, blocks, inits = helpers.scheme("pumps_gibbs_amwg")
+    gen = Engine_(tpl, 64, blocks, inits, seed=99)
+    out_gen = gen.run(300, burnin=100, thin=2, force_generic=True)
+    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-9, atol=1e-12) for c in range(64)])
+    assert ok.mean() >= 0.9
+    two = Engine_(tpl, 64, blocks, inits, seed=99)        # mcmc(mc, iters): 130 + 170 iterations in two calls
+    a = two.run(130, burnin=100, thin=2); b = two.run(170, burnin=100, thin=2)
+    np.testing.assert_array_equal(np.concatenate([a, b], axis=0), g[0])
+    st2, tune2, _ = two.get_state()
+    np.testing.assert_array_equal(st2, g[1]); np.testing.assert_array_equal(tune2, g[2])
+
+
 def test_pumps_gibbs_amwg_posterior_and_psrf(oracle):
     # doc/examples/pumps.rst:43-56: beta 0.9304, alpha 0.6968, theta[1] 0.0599, theta[10] 1.9848
     from mambacuda.engine import Engine
