@@ -156,8 +156,32 @@ struct LineModel {
   }
   MCU_HD static bool elem_local(int) { return false; }   // no element whose move touches only a few terms
   MCU_D static double elem_terms(const Data&, const double*, int, bool) { return 0.0; }
-  MCU_HD static bool has_gibbs(int) { return false; }   // no conjugate full conditional registered for this template (MCU_GIBBS)
-  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  // The tutorial's user-defined Gibbs samplers (doc/tutorial/line.jl:27-45, scheme3):
+  //   beta | . ~ MvNormal(mu, Sigma),  Sigma = inv(X'X / s2 + I / 1000),  mu = Sigma X'y / s2        (Gibbs_beta; prior mean 0, invcov I / 1000)
+  //   s2 | .   ~ InverseGamma(N / 2 + 0.001, sum (y - mu)^2 / 2 + 0.001)                               (Gibbs_s2)
+  // Draw order: two normals (z1, z2; beta = mu + L z with L the lower Cholesky factor of Sigma); one Gamma(shape) variate, s2 = scale / G.
+  MCU_HD static bool has_gibbs(int node) { return node == 0 || node == 1; }
+  template <class R, class G> MCU_D static void gibbs(const Data& d, double* s, int node, R& rng, G rgamma) {
+    if (node == 0) {
+      double sx = 0, sxx = 0, sy = 0, sxy = 0;
+      for (int i = 0; i < d.N; ++i) { sx += d.x[i]; sxx += d.x[i] * d.x[i]; sy += d.y[i]; sxy += d.x[i] * d.y[i]; }
+      const double s2 = s[2];
+      const double a11 = (double)d.N / s2 + 1.0 / 1000.0, a12 = sx / s2, a22 = sxx / s2 + 1.0 / 1000.0;
+      const double det = a11 * a22 - a12 * a12;
+      const double S11 = a22 / det, S12 = -a12 / det, S22 = a11 / det;
+      const double r1 = sy / s2, r2 = sxy / s2;
+      const double m1 = S11 * r1 + S12 * r2, m2 = S12 * r1 + S22 * r2;
+      const double l11 = sqrt(S11), l21 = S12 / l11, l22 = sqrt(S22 - l21 * l21);
+      const double z1 = rng.normal(), z2 = rng.normal();
+      s[0] = m1 + l11 * z1;
+      s[1] = m2 + l21 * z1 + l22 * z2;
+    } else {
+      double ss = 0.0;
+      for (int i = 0; i < d.N; ++i) { const double r = d.y[i] - (1.0 * s[0] + d.x[i] * s[1]); ss += r * r; }
+      const double a = (double)d.N / 2.0 + 0.001, b = ss / 2.0 + 0.001;
+      s[2] = b / rgamma(a, rng);
+    }
+  }
   MCU_D static void monitor(const Data&, const double* s, double* out) { out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; }
   // distribution of observed element i given the state (predict, src/output/modelstats.jl:63-96):
   // returns OUT_NORMAL (a = mean, b = sd), OUT_BINOMIAL (a = n, b = p), OUT_POISSON (a = rate) or OUT_BERNOULLI (a = p)

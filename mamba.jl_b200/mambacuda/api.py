@@ -121,7 +121,8 @@ def AMM(params, Sigma, adapt="all", beta=0.05, scale=2.38):        # src/sampler
 def Gibbs(params):
     """The device counterpart of a user-defined Gibbs sampler `Sampler(params, (args...) -> rand(full conditional))`
     (src/samplers/sampler.jl:20-24; tutorial's Gibbs_beta / Gibbs_s2): an exact draw from the block's full conditional, for the
-    node sets the template registers a conjugate form for (pumps: [:theta], [:beta]); anything else raises at setsamplers time."""
+    node sets the template registers a conjugate form for (pumps: [:theta], [:beta]; line: [:beta], [:s2] — the tutorial's Gibbs_beta / Gibbs_s2);
+    anything else raises at setsamplers time."""
     return Sampler(params, "gibbs")
 
 

@@ -65,6 +65,35 @@ inline Model make_line() {
     g[1] = sxr / s2 - b[1] / 1000.0;
     g[2] = -0.5 * (double)x.size() / s2 + 0.5 * srr / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
   };
+  // the tutorial's Gibbs_beta / Gibbs_s2 (doc/tutorial/line.jl:27-45): conjugate full conditionals; same draw order as the device template
+  m.gibbs = [](Model& mm, int node, Rng& rng) {
+    const auto& x = mm.in("x"); const auto& y = mm.in("y");
+    const size_t N = y.size();
+    if (node == 0) {
+      double sx = 0, sxx = 0, sy = 0, sxy = 0;
+      for (size_t i = 0; i < N; ++i) { sx += x[i]; sxx += x[i] * x[i]; sy += y[i]; sxy += x[i] * y[i]; }
+      const double s2 = mm.val(1)[0];
+      const double a11 = (double)N / s2 + 1.0 / 1000.0, a12 = sx / s2, a22 = sxx / s2 + 1.0 / 1000.0;
+      const double det = a11 * a22 - a12 * a12;
+      const double S11 = a22 / det, S12 = -a12 / det, S22 = a11 / det;
+      const double r1 = sy / s2, r2 = sxy / s2;
+      const double m1 = S11 * r1 + S12 * r2, m2 = S12 * r1 + S22 * r2;
+      const double l11 = std::sqrt(S11), l21 = S12 / l11, l22 = std::sqrt(S22 - l21 * l21);
+      const double z1 = rng.normal(), z2 = rng.normal();
+      mm.nodes[0].value[0] = m1 + l11 * z1;
+      mm.nodes[0].value[1] = m2 + l21 * z1 + l22 * z2;
+      return true;
+    }
+    if (node == 1) {
+      const auto& be = mm.val(0);
+      double ss = 0.0;
+      for (size_t i = 0; i < N; ++i) { const double r = y[i] - (1.0 * be[0] + x[i] * be[1]); ss += r * r; }
+      const double a = (double)N / 2.0 + 0.001, b = ss / 2.0 + 0.001;
+      mm.nodes[1].value[0] = b / rgamma_mt(a, rng);
+      return true;
+    }
+    return false;
+  };
   m.finalize();
   return m;
 }

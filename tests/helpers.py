@@ -45,6 +45,8 @@ SCHEMES = {
     "line_rwm": ("line", [dict(kind="rwm", nodes=[0, 1], scale=[0.5, 0.2, 0.8])], LINE_INITS),
     "line_rwm_unif": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symuniform")], LINE_INITS),
     "line_rwm_tri": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.6, proposal="symtriangular")], LINE_INITS),
+    # doc/tutorial/line.jl:54 scheme3 = [Gibbs_beta, Gibbs_s2]: the tutorial's user-defined conjugate samplers
+    "line_gibbs": ("line", [dict(kind="gibbs", nodes=[0]), dict(kind="gibbs", nodes=[1])], LINE_INITS),
     "line_rwm_cos": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.8, proposal="cosine")], LINE_INITS),
     "line_rwm_epa": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.8, proposal="epanechnikov")], LINE_INITS),
     "line_rwm_biw": ("line", [dict(kind="rwm", nodes=[0, 1], scale=0.9, proposal="biweight")], LINE_INITS),

@@ -138,6 +138,7 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("rats_slice_amwg", 200, 100, 2),
     ("pumps_slice", 300, 100, 2),
     ("pumps_gibbs_amwg", 300, 100, 2),
+    ("line_gibbs", 500, 100, 1),
     ("surgical_amwg", 300, 150, 2),
     ("salm_slice_amwg", 300, 150, 2),
     ("equiv_amwg", 300, 150, 2),

@@ -125,6 +125,22 @@ def test_tutorial_file_io_and_restart(sim1, tmp_path):
         api.mcmc(sim1[range(252, 9001), None, None], 100)
 
 
+def test_tutorial_schemes_2_and_3():
+    # line.jl:51-54, 97-102: scheme2 = [NUTS([:beta, :s2])], scheme3 = [Gibbs_beta, Gibbs_s2] — the user-defined conjugate samplers, which
+    # the device engine provides as registered full conditionals (api.Gibbs); same posterior as scheme1 (tutorial.rst:432-436)
+    from mambacuda import api
+    rng = np.random.default_rng(123)
+    inits = [dict(beta=rng.normal(0, 1, 2), s2=rng.gamma(1.0, 1.0)) for _ in range(3)]
+    for scheme in ([api.NUTS(["beta", "s2"])], [api.Gibbs("beta"), api.Gibbs("s2")]):
+        model = api.Model("line")
+        api.setsamplers(model, scheme)
+        sim = api.mcmc(model, LINE, inits, 10000, burnin=250, thin=2, chains=3)
+        ss, names, _ = api.summarystats(sim)
+        assert abs(ss[0, 0] - 0.5971183) < 4 * np.hypot(0.016925598, ss[0, 3]) and abs(ss[1, 0] - 0.8017036) < 4 * np.hypot(0.004793345, ss[1, 3])
+        assert abs(ss[2, 0] - 1.2203777) < 4 * np.hypot(0.101798287, ss[2, 3]) + 0.1
+    assert api.changerate(sim)[0][3] == 1.0          # a Gibbs sweep always moves
+
+
 def test_store_false_keeps_only_streaming_moments():
     from mambacuda import api
     model = api.Model("line")

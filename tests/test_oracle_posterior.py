@@ -135,6 +135,15 @@ def test_stacks_reference_scheme(oracle):
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
 
 
+def test_line_gibbs_scheme(oracle):
+    # doc/tutorial/line.jl:54,101-102: scheme3 = [Gibbs_beta, Gibbs_s2] targets the tutorial posterior (doc/tutorial.rst:432-436)
+    ref = {"beta[1]": (0.5971183, 0.016925598), "beta[2]": (0.8017036, 0.004793345), "s2": (1.2203777, 0.101798287)}
+    tpl, blocks, inits = helpers.scheme("line_gibbs")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(6, inits, 10000, burnin=250, thin=2, seed=12, nthreads=6)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
 def test_surgical_reference_scheme(oracle):
     # doc/examples/surgical.jl:54-60 (NUTS(b) + Slice([mu, s2], 1.0), 2 x 10,000, burnin 2,500, thin 2), table doc/examples/surgical.rst
     ref = {"mu": (-2.550263247, 0.00352027397), "pop_mean": (0.073062651, 0.00022880854), "s2": (0.183080212, 0.00629499754),
