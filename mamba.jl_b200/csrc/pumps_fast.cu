@@ -40,8 +40,11 @@ struct UStreamP {
   }
 };
 
+#ifndef MCU_PUMPSF_MINB
+#define MCU_PUMPSF_MINB 6    // resident blocks per SM (measured 3 / 4 / 5 / 6 / 8 / 10 / 12 / 16: 1.57 / 1.57 / 1.69 / 1.70 / 1.63 / 1.58 / 1.53 / 1.37e9 at 1e6 chains)
+#endif
 template <int BS>
-__global__ void __launch_bounds__(BS, 8) pumps_fast_kernel(const __grid_constant__ PumpsFastCfg cfg, const __grid_constant__ RunArgs a) {
+__global__ void __launch_bounds__(BS, MCU_PUMPSF_MINB) pumps_fast_kernel(const __grid_constant__ PumpsFastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const long long c = (long long)blockIdx.x * BS + tid;
