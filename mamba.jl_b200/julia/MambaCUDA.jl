@@ -150,7 +150,7 @@ function MALA(params, epsilon::Real, Sigma=nothing; dtype::Symbol=:forward)
   shimargs[s] = d; s
 end
 ## A user-defined Gibbs sampler Sampler(params, f) has no device equivalent in general (f is a Julia closure); for the
-## node sets a template registers a conjugate full conditional for (pumps: [:theta], [:beta]) the shim tags the sampler so
+## node sets a template registers a conjugate full conditional for (pumps: [:theta], [:beta]; line: [:beta], [:s2]) the shim tags the sampler so
 ## that the block runs as MCU_GIBBS; `f` stays attached for the CPU path of stock Mamba.
 function Gibbs(params, f::Function)
   s = Mamba.Sampler(params, f)
@@ -161,6 +161,58 @@ function AMM(params, Sigma; adapt::Symbol=:all, beta::Real=0.05, scale::Real=2.3
   shimargs[s] = Dict(:scale => Sigma, :adapt => adapt, :beta => beta, :amm_scale => scale); s
 end
 
+## What a restart needs to rebuild the device handle: template id, the inputs that were uploaded, the block descriptors (the constructor
+## arguments live in `shimargs` under the ORIGINAL Sampler objects, so the descriptors are built before the model is deep-copied) and the
+## seed.  Keyed by the model object stored in the ModelChains that mcmc returns.
+type RunInfo
+  tid::Int
+  inputs::Dict{Symbol, Any}
+  descs::Vector{BlockDesc}
+  keep::Vector{Any}
+  seed::UInt64
+  device::Int
+end
+const shiminfo = ObjectIdDict()
+
+function openhandle(info::RunInfo, chains::Integer)
+  h = Ref{Ptr{Void}}(C_NULL)
+  rc = ccall((:mcu_create, libmambacuda), Cint, (Cint, Int64, Int64, Cint, UInt64, Ptr{Ptr{Void}}),
+             info.tid, chains, 0, info.device, info.seed, h)
+  rc == 0 || error(unsafe_string(ccall((:mcu_last_error, libmambacuda), Cstring, (Ptr{Void},), C_NULL)))
+  ## inputs (setinputs!, src/model/initialization.jl:30-40); integer data travel as Float64
+  for (key, value) in info.inputs
+    isa(value, AbstractArray) || continue
+    x = convert(Array{Float64}, value)
+    dims = Int64[size(x)...]
+    check(h[], ccall((:mcu_set_data, libmambacuda), Cint, (Ptr{Void}, Cstring, Cint, Ptr{Int64}, Ptr{Float64}),
+                     h[], string(key), length(dims), dims, x))
+  end
+  check(h[], ccall((:mcu_set_scheme, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{BlockDesc}), h[], length(info.descs), info.descs))
+  h[]
+end
+
+## run `iters` more iterations on an initialised handle and wrap the result exactly as mcmc_master! does (mcmc.jl:54-58)
+function runhandle(h::Ptr{Void}, mm::Model, first::Integer, iters::Integer, thin::Integer, chains::Integer)
+  D = Ref{Cint}(0); P = Ref{Cint}(0); NN = Ref{Cint}(0)
+  check(h, ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), h, D, P, NN))
+  kept = ccall((:mcu_kept, libmambacuda), Int64, (Int64, Int64, Int64, Int64), mm.iter, iters, mm.burnin, thin)
+  value = Array{Float64}(kept, P[], chains)            # == ModelChains.value layout, filled in place
+  check(h, ccall((:mcu_run, libmambacuda), Cint, (Ptr{Void}, Int64, Int64, Int64, Ptr{Float64}, UInt32),
+                 h, iters, mm.burnin, thin, value, 0))
+  ## final ModelStates (mcmc.jl:56,82): values + tune records
+  nt = Ref{Int64}(0)
+  check(h, ccall((:mcu_tune_size, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), h, nt))
+  vals = Array{Float64}(D[], chains); tune = Array{Float64}(max(nt[], 1), chains); it = Ref{Int64}(0)
+  check(h, ccall((:mcu_get_state, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                 h, vals, tune, it))
+  mm.iter = it[]
+  mm.states = ModelState[ModelState(vals[:, k], Any[tune[:, k]]) for k in 1:chains]
+  buf = Vector{UInt8}(1 << 16)
+  ccall((:mcu_names, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{UInt8}, Csize_t), h, 1, buf, length(buf))
+  pnames = split(unsafe_string(pointer(buf)), '\n')
+  ModelChains(Chains(value, start=first, thin=thin, names=AbstractString[pnames...]), mm)
+end
+
 ## mcmc(model, inputs, inits, iters; burnin, thin, chains): same signature, checks and result as
 ## src/model/mcmc.jl:19-33; the chains x iterations loop is ONE call into the library.
 function mcmc(m::Model, inputs::Dict{Symbol}, inits::Vector{Dict{Symbol, Any}}, iters::Integer;
@@ -169,62 +221,54 @@ function mcmc(m::Model, inputs::Dict{Symbol}, inits::Vector{Dict{Symbol, Any}}, 
   iters > burnin || throw(ArgumentError("burnin is greater than or equal to iters"))
   length(inits) >= chains || throw(ArgumentError("fewer initial values than chains"))
 
+  tid = template >= 0 ? template : matchtemplate(m)
+  nodes = TEMPLATES[tid]
+  nodeids = Dict{Symbol, Int}([nodes[i] => i - 1 for i in 1:length(nodes)])
+  keep = Any[]
+  descs = BlockDesc[blockdesc(m, s, nodeids, keep) for s in m.samplers]   # on the caller's Sampler objects: see RunInfo
+
   mm = deepcopy(m)
   setinputs!(mm, inputs)
   setinits!(mm, inits[1:chains])          # validates the Dicts exactly as the reference does
   mm.burnin = burnin
+  mm.iter = 0
+  info = RunInfo(tid, inputs, descs, keep, UInt64(seed), device)
 
-  tid = template >= 0 ? template : matchtemplate(mm)
-  nodes = TEMPLATES[tid]
-  nodeids = Dict{Symbol, Int}([nodes[i] => i - 1 for i in 1:length(nodes)])
-
-  h = Ref{Ptr{Void}}(C_NULL)
-  rc = ccall((:mcu_create, libmambacuda), Cint, (Cint, Int64, Int64, Cint, UInt64, Ptr{Ptr{Void}}),
-             tid, chains, 0, device, seed, h)
-  rc == 0 || error(unsafe_string(ccall((:mcu_last_error, libmambacuda), Cstring, (Ptr{Void},), C_NULL)))
+  h = openhandle(info, chains)
   try
-    ## inputs (setinputs!, src/model/initialization.jl:30-40); integer data travel as Float64
-    for (key, value) in inputs
-      isa(value, AbstractArray) || continue
-      x = convert(Array{Float64}, value)
-      dims = Int64[size(x)...]
-      check(h[], ccall((:mcu_set_data, libmambacuda), Cint, (Ptr{Void}, Cstring, Cint, Ptr{Int64}, Ptr{Float64}),
-                       h[], string(key), length(dims), dims, x))
-    end
-    keep = Any[]
-    descs = BlockDesc[blockdesc(mm, s, nodeids, keep) for s in mm.samplers]
-    check(h[], ccall((:mcu_set_scheme, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{BlockDesc}), h[], length(descs), descs))
-
-    ## initial values → [D × chains] (record contiguous == column-major D × n)
-    D = Ref{Cint}(0); P = Ref{Cint}(0); NN = Ref{Cint}(0)
-    check(h[], ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), h[], D, P, NN))
-    x0 = Array{Float64}(D[], chains)
-    for k in 1:chains
-      x0[:, k] = vcat([vec(Float64[inits[k][key]...]) for key in nodes]...)
-    end
-    check(h[], ccall((:mcu_set_inits, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Int64, Float64), h[], x0, chains, 0.0))
-
-    kept = ccall((:mcu_kept, libmambacuda), Int64, (Int64, Int64, Int64, Int64), 0, iters, burnin, thin)
-    value = Array{Float64}(kept, P[], chains)          # == ModelChains.value layout, filled in place
-    check(h[], ccall((:mcu_run, libmambacuda), Cint, (Ptr{Void}, Int64, Int64, Int64, Ptr{Float64}, UInt32),
-                     h[], iters, burnin, thin, value, 0))
-
-    ## final ModelStates (mcmc.jl:56,82): values + tune records
-    nt = Ref{Int64}(0)
-    check(h[], ccall((:mcu_tune_size, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), h[], nt))
-    vals = Array{Float64}(D[], chains); tune = Array{Float64}(max(nt[], 1), chains); it = Ref{Int64}(0)
-    check(h[], ccall((:mcu_get_state, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
-                     h[], vals, tune, it))
-    mm.iter = it[]
-    mm.states = ModelState[ModelState(vals[:, k], Any[tune[:, k]]) for k in 1:chains]
-
-    buf = Vector{UInt8}(1 << 16)
-    ccall((:mcu_names, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{UInt8}, Csize_t), h[], 1, buf, length(buf))
-    pnames = split(unsafe_string(pointer(buf)), '\n')
-    sim = Chains(value, start=burnin + thin, thin=thin, names=AbstractString[pnames...])
-    return ModelChains(sim, mm)
+    ## initial values → [D × chains] (record contiguous == column-major D × n); matrices flatten column-major, as unlist does
+    x0 = hcat([vcat([vec(Float64[inits[k][key]...]) for key in nodes]...) for k in 1:chains]...)
+    check(h, ccall((:mcu_set_inits, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Int64, Float64), h, x0, chains, 0.0))
+    mc = runhandle(h, mm, burnin + thin, iters, thin, chains)
+    shiminfo[mc.model] = info
+    return mc
   finally
-    ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h[])
+    ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h)
+  end
+end
+
+## mcmc(mc, iters): restart (src/model/mcmc.jl:3-16) — the handle is rebuilt at the stored ModelStates (values, tune records, iteration
+## counter); the Philox counters are functions of the iteration number, so the continuation equals an uninterrupted run.
+function mcmc(mc::ModelChains, iters::Integer; verbose::Bool=true)
+  thin = step(mc)
+  last(mc) == div(mc.model.iter, thin) * thin || throw(ArgumentError("chain is missing its last iteration"))
+  haskey(shiminfo, mc.model) || throw(ArgumentError("this ModelChains was not produced by MambaCUDA.mcmc"))
+  info = shiminfo[mc.model]
+  mm = deepcopy(mc.model)
+  chains = length(mc.chains)
+  h = openhandle(info, chains)
+  try
+    vals = hcat([st.value for st in mm.states]...)
+    tune = hcat([st.tune[1] for st in mm.states]...)
+    check(h, ccall((:mcu_set_state, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Ptr{Float64}, Int64), h, vals, tune, mm.iter))
+    mc2 = runhandle(h, mm, last(mc) + thin, iters, thin, chains)
+    shiminfo[mc2.model] = info
+    if mc2.names != mc.names
+      mc2 = mc2[:, mc.names, :]
+    end
+    return ModelChains(vcat(mc, mc2), mc2.model)
+  finally
+    ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h)
   end
 end
 
