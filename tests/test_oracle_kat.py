@@ -325,3 +325,52 @@ def test_rwm_proposal_kernels_have_the_right_distribution(oracle):
         assert abs(z.mean()) < 4 * np.sqrt(var[code] / z.size)
         np.testing.assert_allclose(z.var(), var[code], rtol=0.02)
         assert st.kstest(z, cdf[code]).pvalue > 1e-3
+
+
+def test_predict_draws_are_the_quantile_functions_of_the_observed_nodes(oracle):
+    """predict(mc) (src/output/modelstats.jl:63-96) on the engine's stream contract (seed, chain = stream id, iteration = record index,
+    block 0, kind 15): a discrete element is the inverse CDF of ONE uniform (sequential search from 0 == scipy's ppf), a Laplace element
+    its closed-form quantile, a Normal element mu + sigma z with z from the normal stream."""
+    import helpers
+    import scipy.stats as st
+    rng = np.random.default_rng(21)
+    seed, stream = 77, 3
+    # pumps: y[i] ~ Poisson(theta[i] t[i])
+    tpl, blocks, inits = helpers.scheme("pumps_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    S = np.column_stack([rng.gamma(2.0, 0.5, size=6), rng.gamma(2.0, 0.5, size=6), rng.gamma(2.0, 0.4, size=(6, 10))])
+    t = np.array([94.3, 15.7, 62.9, 126, 5.24, 31.4, 1.05, 1.05, 2.1, 10.5])
+    got = o.predict(S, seed, stream_id=stream)
+    for i in range(6):
+        u = oracle.draws(seed, stream, i, 0, [0] * 10, kind=15)
+        np.testing.assert_array_equal(got[i], st.poisson.ppf(u, S[i, 2:] * t))
+    # surgical: r[i] ~ Binomial(n[i], invlogit(b[i]))
+    tpl, blocks, inits = helpers.scheme("surgical_amwg")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    S = np.column_stack([rng.normal(-2.5, 0.2, 5), rng.gamma(2.0, 0.1, 5), rng.normal(-2.5, 0.5, (5, 12))])
+    n = np.array([47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360])
+    got = o.predict(S, seed, stream_id=stream)
+    for i in range(5):
+        u = oracle.draws(seed, stream, i, 0, [0] * 12, kind=15)
+        want = st.binom.ppf(u, n, 1 / (1 + np.exp(-S[i, 2:])))
+        assert (got[i] == want).mean() >= 11 / 12          # a uniform within rounding of a CDF step may fall on either side
+    # stacks: y[i] ~ Laplace(mu[i], s2)
+    tpl, blocks, inits = helpers.scheme("stacks_amwg")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    S = np.column_stack([rng.normal(17.5, 1, 4), rng.normal(0, 2, (4, 3)), rng.gamma(6, 0.45, 4)])
+    got = o.predict(S, seed, stream_id=stream)
+    for i in range(4):
+        u = oracle.draws(seed, stream, i, 0, [0] * 21, kind=15)
+        resid = st.laplace.ppf(u, 0.0, S[i, 4])
+        # y_rep - resid = mu[i] = beta0 + z . beta: the same vector for any stream
+        other = o.predict(S[i:i + 1], seed, stream_id=stream + 1)[0] - st.laplace.ppf(oracle.draws(seed, stream + 1, 0, 0, [0] * 21, kind=15), 0.0, S[i, 4])
+        np.testing.assert_allclose(got[i] - resid, other, rtol=1e-10, atol=1e-10)
+    # line: y[i] ~ Normal(beta1 + beta2 x[i], sqrt(s2)) through the normal stream
+    tpl, blocks, inits = helpers.scheme("line_amwg_slice")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    S = np.column_stack([rng.normal(size=(3, 2)), rng.gamma(2.0, 1.0, 3)])
+    got = o.predict(S, seed, stream_id=stream)
+    x = np.arange(1.0, 6.0)
+    for i in range(3):
+        z = oracle.draws(seed, stream, i, 0, [1] * 5, kind=15)
+        np.testing.assert_allclose(got[i], S[i, 0] + S[i, 1] * x + np.sqrt(S[i, 2]) * z, rtol=1e-13)
