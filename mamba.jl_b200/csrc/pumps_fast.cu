@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
           v = v * v * v;
           const double u = rng.uniform();
           const double x2 = xn * xn;
-          if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
+          if (u < 1.0 - 0.0331 * x2 * x2 || flog(u) < 0.5 * x2 + d * (1.0 - v + flog(v))) {
             TH(i) = boost * d * v / (be + st[i]);
             ++i; setup = true;
           }

@@ -135,7 +135,7 @@ static MCU_NOINL double rgamma_mt(double a, Draws& rng) {
     const double u = rng.uniform();
     const double x2 = x * x;
     if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    if (flog(u) < 0.5 * x2 + d * (1.0 - v + flog(v))) return boost * d * v;
   }
 }
 
