@@ -870,6 +870,39 @@ def rafterydiag(c, q=0.025, r=0.005, s=0.95, eps=0.001):
     return out, c.names, ["Thinning", "Burn-in", "Total", "Nmin", "Dependence Factor"]
 
 
+def format_summary(value, rownames, colnames):
+    """Text layout of show(io, s::ChainSummary) (src/output/chainsummary.jl:50-84): right-aligned columns, one common fixed-point format
+    per column (the reference delegates the digits to Showoff.showoff; here 8 significant digits of the column's largest entry), column
+    names centred on the column widths, row names right-aligned."""
+    v = np.atleast_2d(np.asarray(value, dtype=float))
+    cols = []
+    for j in range(v.shape[1]):
+        col = v[:, j]
+        fin = np.abs(col[np.isfinite(col)])
+        big = fin.max() if fin.size else 0.0
+        if big != 0.0 and (big >= 1e9 or big < 1e-5):
+            cols.append([f"{x:.7e}" for x in col])
+        else:
+            dec = int(min(12, max(0, 8 - (int(np.floor(np.log10(big))) + 1 if big > 0 else 1))))
+            cols.append(["NaN" if np.isnan(x) else f"{x:.{dec}f}" for x in col])
+    rn = max(len(r) for r in rownames)
+    wid = [1 + max(len(cn), max(len(s) for s in cstr)) for cn, cstr in zip(colnames, cols)]
+    out = [" " * rn]
+    for cn, w in zip(colnames, wid):
+        nspace = w - len(cn) - 1
+        nright = nspace >> 1
+        out[0] += " " * (1 + nspace - nright) + cn + " " * nright
+    for i, r in enumerate(rownames):
+        out.append(" " * (rn - len(r)) + r + "".join(" " * (w - len(cstr[i])) + cstr[i] for w, cstr in zip(wid, cols)))
+    return "\n".join(out) + "\n"
+
+
+def describe_text(c, q=(0.025, 0.25, 0.5, 0.75, 0.975), etype="bm"):
+    """What describe(io, c) prints (src/output/stats.jl:43-52): header, "Empirical Posterior Estimates:", "Quantiles:"."""
+    (ss, names, cols), (qq, _, qcols) = describe(c, q=q, etype=etype)
+    return (c.header() + "\nEmpirical Posterior Estimates:\n" + format_summary(ss, names, cols) + "\nQuantiles:\n" + format_summary(qq, names, qcols) + "\n")
+
+
 def describe(c, q=(0.025, 0.25, 0.5, 0.75, 0.975), etype="bm"):
     """describe(c): src/output/stats.jl:41-52 — summarystats + quantiles."""
     return summarystats(c, etype=etype), quantile(c, q=q)

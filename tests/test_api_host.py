@@ -193,6 +193,26 @@ def test_diagnostics_on_plain_chains_use_the_host_entry_points(mcu_built, oracle
     np.testing.assert_allclose(psrf_m[:3], np.round(oracle.gelmandiag(x, 0.05, None), 3), atol=1e-12)
 
 
+def test_describe_text_has_the_layout_of_the_reference(mcu_built):
+    # doc/tutorial.rst:427-442: header, "Empirical Posterior Estimates:" and "Quantiles:" tables with right-aligned columns
+    from mambacuda import api
+    rng = np.random.default_rng(4)
+    c = api.Chains(np.stack([rng.normal(0.6, 1.1, (300, 2)), rng.normal(0.8, 0.3, (300, 2)), rng.gamma(1.0, 1.2, (300, 2))], axis=1),
+                   start=252, thin=2, names=["beta[1]", "beta[2]", "s2"])
+    txt = api.describe_text(c)
+    lines = txt.splitlines()
+    assert lines[0] == "Iterations = 252:850" and lines[1] == "Thinning interval = 2" and lines[2] == "Chains = 1,2" and lines[3] == "Samples per chain = 300"
+    i = lines.index("Empirical Posterior Estimates:")
+    assert lines[i + 1].split() == ["Mean", "SD", "Naive", "SE", "MCSE", "ESS"]
+    rows = lines[i + 2:i + 5]
+    assert [r.split()[0] for r in rows] == ["beta[1]", "beta[2]", "s2"] and len({len(r) for r in rows}) == 1      # right-aligned: equal line lengths
+    assert rows[2].startswith("     s2 ")                                                                          # row names right-aligned
+    ss, _, _ = api.summarystats(c)
+    np.testing.assert_allclose([float(x) for x in rows[0].split()[1:]], ss[0], rtol=1e-6)
+    j = lines.index("Quantiles:")
+    assert lines[j + 1].split() == ["2.5%", "25.0%", "50.0%", "75.0%", "97.5%"] and lines[j + 2].split()[0] == "beta[1]"
+
+
 def test_write_and_read_round_trip(mcu_built, tmp_path):
     from mambacuda import api
     c = _toy_chains()
