@@ -101,6 +101,17 @@ int stage(mcu_ctx* h, size_t bytes, void** out) {
   return MCU_OK;
 }
 
+// device scratch that lives for one API call: freed on every return path (the CK macro returns early on a CUDA error)
+struct DevScratch {
+  void* p = nullptr;
+  DevScratch() = default;
+  DevScratch(const DevScratch&) = delete;
+  DevScratch& operator=(const DevScratch&) = delete;
+  ~DevScratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  double* f64() const { return static_cast<double*>(p); }
+};
+
 inline unsigned grid_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // ---- template metadata on the host ---------------------------------------------------------------
@@ -957,18 +968,21 @@ static int density_call(mcu_handle h, int block, int grad_mode, int64_t B, const
   CK(cudaSetDevice(h->device));
   int rc = upload_inputs(h); if (rc) return rc;
   const int k = h->h_blocks[block].k, D = h->D;
-  double *d_rec = nullptr, *d_state = nullptr, *d_x = nullptr, *d_lp = nullptr, *d_g = nullptr, *d_tmp = nullptr;
-  CK(cudaMalloc(&d_rec, sizeof(double) * B * std::max(D, k)));
-  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
+  DevScratch b_rec, b_state, b_x, b_lp, b_g, b_tmp;
+  double *d_x = nullptr, *d_g = nullptr, *d_tmp = nullptr;
+  CK(b_rec.alloc(sizeof(double) * B * std::max(D, k)));
+  CK(b_state.alloc(sizeof(double) * B * D));
+  double *d_rec = b_rec.f64(), *d_state = b_state.f64();
   CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
   launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
   if (x) {
-    CK(cudaMalloc(&d_x, sizeof(double) * B * k));
+    CK(b_x.alloc(sizeof(double) * B * k)); d_x = b_x.f64();
     CK(cudaMemcpyAsync(d_rec, x, sizeof(double) * B * k, cudaMemcpyHostToDevice, h->stream));
     launch_records_to_soa(d_rec, d_x, B, k, h->stream); h->launches++;
   }
-  CK(cudaMalloc(&d_lp, sizeof(double) * B));
-  if (g) { CK(cudaMalloc(&d_g, sizeof(double) * B * k)); CK(cudaMalloc(&d_tmp, sizeof(double) * B * k)); }
+  CK(b_lp.alloc(sizeof(double) * B));
+  double* d_lp = b_lp.f64();
+  if (g) { CK(b_g.alloc(sizeof(double) * B * k)); CK(b_tmp.alloc(sizeof(double) * B * k)); d_g = b_g.f64(); d_tmp = b_tmp.f64(); }
   MCU_DISPATCH(h, launch_logpdf(Host<M>::data(h), h->d_blocks, block, B, D, d_state, d_x, d_lp, d_g, grad_mode, h->stream));
   h->launches++;
   if (lp) CK(cudaMemcpyAsync(lp, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
@@ -977,7 +991,6 @@ static int density_call(mcu_handle h, int block, int grad_mode, int64_t B, const
     CK(cudaMemcpyAsync(g, d_tmp, sizeof(double) * B * k, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_x); cudaFree(d_lp); cudaFree(d_g); cudaFree(d_tmp);
   CK(cudaGetLastError());
   return MCU_OK;
 }
@@ -1005,17 +1018,17 @@ int mcu_logpdf_nodes(mcu_handle h, uint32_t factor_mask, int64_t B, const double
   CK(cudaSetDevice(h->device));
   int rc = upload_inputs(h); if (rc) return rc;
   const int D = h->D;
-  double *d_rec = nullptr, *d_state = nullptr, *d_lp = nullptr;
-  CK(cudaMalloc(&d_rec, sizeof(double) * B * D));
-  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
-  CK(cudaMalloc(&d_lp, sizeof(double) * B));
+  DevScratch rec, soa, out;
+  CK(rec.alloc(sizeof(double) * B * D));
+  CK(soa.alloc(sizeof(double) * B * D));
+  CK(out.alloc(sizeof(double) * B));
+  double *d_rec = rec.f64(), *d_state = soa.f64(), *d_lp = out.f64();
   CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
   launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
   MCU_DISPATCH(h, launch_factors(Host<M>::data(h), factor_mask, B, D, d_state, d_lp, h->stream));
   h->launches++;
   CK(cudaMemcpyAsync(lp, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_lp);
   CK(cudaGetLastError());
   return MCU_OK;
 }
@@ -1030,11 +1043,12 @@ int mcu_predict(mcu_handle h, int64_t B, const double* state, uint32_t stream_id
   if (!out) return MCU_OK;   // size query
   if (!state || B < 1) return fail(h, MCU_ERR_ARG, "bad argument");
   const int D = h->D;
-  double *d_rec = nullptr, *d_state = nullptr, *d_out = nullptr, *d_tmp = nullptr;
-  CK(cudaMalloc(&d_rec, sizeof(double) * B * D));
-  CK(cudaMalloc(&d_state, sizeof(double) * B * D));
-  CK(cudaMalloc(&d_out, sizeof(double) * B * L));
-  CK(cudaMalloc(&d_tmp, sizeof(double) * B * L));
+  DevScratch rec, soa, draws, tmp;
+  CK(rec.alloc(sizeof(double) * B * D));
+  CK(soa.alloc(sizeof(double) * B * D));
+  CK(draws.alloc(sizeof(double) * B * L));
+  CK(tmp.alloc(sizeof(double) * B * L));
+  double *d_rec = rec.f64(), *d_state = soa.f64(), *d_out = draws.f64(), *d_tmp = tmp.f64();
   CK(cudaMemcpyAsync(d_rec, state, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
   launch_records_to_soa(d_rec, d_state, B, D, h->stream); h->launches++;
   MCU_DISPATCH(h, launch_predict(Host<M>::data(h), B, D, d_state, h->seed, stream_id, d_out, h->stream));
@@ -1042,7 +1056,6 @@ int mcu_predict(mcu_handle h, int64_t B, const double* state, uint32_t stream_id
   launch_soa_to_records(d_out, d_tmp, B, L, h->stream); h->launches++;
   CK(cudaMemcpyAsync(out, d_tmp, sizeof(double) * B * L, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_rec); cudaFree(d_state); cudaFree(d_out); cudaFree(d_tmp);
   CK(cudaGetLastError());
   return MCU_OK;
 }
