@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -83,3 +84,37 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"pyoracle|liboracle|oracle/|orc_[a-z]", txt):
                         bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_block_descriptor_layout_is_the_same_in_all_three_bindings():
+    """mcu_block_desc (include/mambacuda.h), the ctypes mirror (mambacuda/_lib.py, pyoracle.py) and the Julia `immutable BlockDesc`
+    (julia/MambaCUDA.jl) must list the same fields in the same order with the same widths: the struct crosses the ABI by pointer."""
+    import ctypes as C
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "mamba.jl_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from mambacuda import _lib
+    import pyoracle
+    h = open(os.path.join(ROOT, "include", "mambacuda.h")).read()
+    body = re.search(r"typedef struct mcu_block_desc \{(.*?)\} mcu_block_desc;", h, re.S).group(1)
+    fields = []
+    for line in body.splitlines():
+        m = re.match(r"\s*(const double\*|int32_t|double)\s+(\w+)(\[\w+\])?;", line)
+        if m:
+            fields.append((m.group(2), m.group(1), bool(m.group(3))))
+    assert [f[0] for f in fields] == ["kind", "n_nodes", "nodes", "transform", "adapt", "batchsize", "proposal", "L", "grad", "max_depth", "n_scale",
+                                      "target", "epsilon", "beta", "amm_scale", "scale"]
+    width = {"int32_t": 4, "double": 8, "const double*": 8}
+    for cls in (_lib.BlockDesc, pyoracle.BlockDesc):
+        assert [n for n, _ in cls._fields_] == [f[0] for f in fields]
+        for (n, t), (_, ctype, is_arr) in zip(cls._fields_, fields):
+            assert C.sizeof(t) == width[ctype] * (8 if is_arr else 1), n
+        assert C.sizeof(cls) == 112                      # 11 x int32 + 8 x int32 nodes = 76 → padded to 80, + 4 doubles + 1 pointer
+    jl = open(os.path.join(ROOT, "mamba.jl_b200", "julia", "MambaCUDA.jl")).read()
+    jbody = re.search(r"immutable BlockDesc\n(.*?)\nend", jl, re.S).group(1)
+    jfields = [tuple(x.strip() for x in ln.split("::")) for ln in jbody.splitlines() if "::" in ln]
+    assert [f[0] for f in jfields] == [f[0] for f in fields]
+    jt = {"int32_t": "Int32", "double": "Float64", "const double*": "Ptr{Float64}"}
+    for (n, t), (_, ctype, is_arr) in zip(jfields, fields):
+        assert t == ("NTuple{8, Int32}" if is_arr else jt[ctype]), (n, t)
+    assert "MCU_MAX_BLOCK_NODES = 8" in jl and re.search(r"#define MCU_MAX_BLOCK_NODES\s+8", h)
