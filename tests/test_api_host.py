@@ -244,3 +244,23 @@ def test_write_and_read_round_trip(mcu_built, tmp_path):
     assert sub.names == ["beta[1]", "beta[2]"] and isinstance(sub, api.ModelChains)
     with pytest.raises(api.ArgumentError, match="chain values are missing for nodes : gamma"):
         r[:, "gamma", :]
+
+
+def test_template_node_tables_agree_with_the_oracle(mcu_built, oracle):
+    # the API mirror lays out initial values by its own node table (api._TEMPLATES); the state record order of the engine is the oracle's
+    # (GPU parity tests): a mismatch would silently permute initial values
+    from mambacuda import api, _lib
+    import pyoracle
+    assert set(api._TEMPLATES) == set(_lib.TPL) == set(pyoracle.TPL)
+    assert _lib.TPL == pyoracle.TPL
+    for tpl, t in api._TEMPLATES.items():
+        if tpl == "glm":
+            continue
+        want = []
+        for nm, ln in t["nodes"]:
+            want += [nm] if ln == 1 else [f"{nm}[{i + 1}]" for i in range(ln)]
+        o = oracle.Oracle(tpl)
+        got = o.names(monitoronly=False)
+        # the oracle lists every node (Logical and observed ones too): keep the unobserved stochastic elements = the state record
+        state = [g for g in got if g.split("[")[0] in {nm for nm, _ in t["nodes"]}]
+        assert state == want, (tpl, state[:6], want[:6])
