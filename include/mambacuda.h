@@ -93,6 +93,8 @@ enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1, MCU_ETYPE_IPSE = 2 };              
 #define MCU_RUN_NO_STORE 1u     /* do not keep thinned samples on the device, only streaming moments */
 #define MCU_RUN_FORCE_GENERIC 2u /* never dispatch to a specialised (fused) kernel */
 #define MCU_RUN_GLM_REFERENCE 4u /* GLM/NUTS tick engine: use the FP64 CUDA-core gradient kernel instead of the tensor-core one */
+#define MCU_RUN_PARTIAL 8u       /* this call is one segment of a longer mcmc() run driven by the caller (burn-in may extend past it):
+                                    skips the "burnin is greater than or equal to iters" check of mcmc.jl:22-23 */
 
 #define MCU_MAX_BLOCK_NODES 8
 
@@ -134,7 +136,9 @@ int mcu_abi_version(void);
 /* ---- model inputs: setinputs!  src/model/initialization.jl:30-40 --------------------------- */
 /* Named input arrays of the template (e.g. "x","y" for line; "r","n","x1","x2" for seeds;
  * "y","Xm","rat" for rats; "y","t" for pumps; "X" [N×d row-major],"y" for the GLM).
- * Integer-valued inputs are passed as doubles.  Every template has the reference's dataset as
+ * Integer-valued inputs are passed as doubles.  Index inputs ("rat" of rats, "batch" of dyes) are 0-BASED
+ * (the Julia shim subtracts 1 from the scripts' 1-based vectors) and range-checked: MCU_ERR_ARG otherwise.
+ * Inputs that must agree in length (line x / y, GLM X rows / y) are checked when they are uploaded: MCU_ERR_DIM.  Every template has the reference's dataset as
  * default, so this is optional except for the GLM.                                            */
 int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, const double* ptr);
 

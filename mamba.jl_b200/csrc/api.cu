@@ -189,8 +189,13 @@ void default_inputs(mcu_ctx* h) {
   }
 }
 
+bool scheme_is_seeds_fast(const mcu_ctx* h);
 int upload_inputs(mcu_ctx* h) {
   if (!h->data_dirty) return MCU_OK;
+  // inputs that must agree in length (DimensionMismatch in the reference: simulation.jl:20-23)
+  if (h->tpl == MCU_TPL_LINE && h->inputs["x"].size() != h->inputs["y"].size()) { h->err = "line: x and y differ in length"; return MCU_ERR_DIM; }
+  if (h->tpl == MCU_TPL_GLM_LOGIT && h->glm_d > 0 && h->inputs["X"].size() != h->inputs["y"].size() * (size_t)h->glm_d) { h->err = "GLM: y must have one entry per row of X"; return MCU_ERR_DIM; }
+  if (!h->h_blocks.empty()) h->seeds_fast_ok = scheme_is_seeds_fast(h);   // the fused-kernel eligibility depends on the data (0/1 design)
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
   h->d_inputs.clear();
   if (h->d_rat) { cudaFree(h->d_rat); h->d_rat = nullptr; }
@@ -453,7 +458,8 @@ int ensure_glm_buffers(mcu_ctx* h) {
   if (h->g_sc) return MCU_OK;
   const size_t C = (size_t)h->C, d = (size_t)h->D;
   const size_t nsc = glm_tick_scalar_slots(), nv = glm_tick_vector_slots();
-  long long nslab = (148LL * 512 + h->C - 1) / h->C;
+  int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+  long long nslab = ((long long)n_sm * 512 + h->C - 1) / h->C;
   const long long N = (long long)h->inputs["y"].size();
   if (nslab > (N + 63) / 64) nslab = (N + 63) / 64;
   if (nslab < 1) nslab = 1;
@@ -464,7 +470,7 @@ int ensure_glm_buffers(mcu_ctx* h) {
     // instead of 4 slabs = 128 CTAs on 148 SMs)
     const long long groups = (h->C + 127) / 128;
     const long long NT = glm_tc_num_tiles(N);
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int sms = n_sm;
     long long ns = 1; double best = 1e300;
     for (long long cand = 1; cand <= NT && cand * groups <= 8LL * sms; ++cand) {
       const long long waves = (cand * groups + sms - 1) / sms, tps = (NT + cand - 1) / cand;
@@ -640,6 +646,9 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
     if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
+    // index inputs are 0-based offsets into the state record (the Julia shim converts the scripts' 1-based rat / batch: rats.jl:42, dyes.jl:16)
+    if (h->tpl == MCU_TPL_RATS && nm == "rat") for (size_t i = 0; i < n; ++i) if (!(ptr[i] >= 0.0 && ptr[i] < 30.0 && ptr[i] == std::floor(ptr[i]))) return fail(h, MCU_ERR_ARG, "rat must hold 0-based integer indices in [0, 30)");
+    if (h->tpl == MCU_TPL_DYES && nm == "batch") for (size_t i = 0; i < n; ++i) if (!(ptr[i] >= 0.0 && ptr[i] < 6.0 && ptr[i] == std::floor(ptr[i]))) return fail(h, MCU_ERR_ARG, "batch must hold 0-based integer indices in [0, 6)");
   }
   if (h->tpl == MCU_TPL_GLM_LOGIT && nm == "family" && (n != 1 || !(ptr[0] == 0.0 || ptr[0] == 1.0 || ptr[0] == 2.0)))
     return fail(h, MCU_ERR_ARG, "family must be 0 (Bernoulli / logit), 1 (Poisson / log) or 2 (Normal / identity)");
@@ -818,7 +827,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   if (!h) return MCU_ERR_ARG;
   if (iters < 1) return fail(h, MCU_ERR_ARG, "iters must be positive");
   if (thin < 1) return fail(h, MCU_ERR_ARG, "thin must be positive");
-  if (h->iter == 0 && iters <= burnin) return fail(h, MCU_ERR_ARG, "burnin is greater than or equal to iters");   // mcmc.jl:22-23
+  if (h->iter == 0 && iters <= burnin && !(flags & MCU_RUN_PARTIAL)) return fail(h, MCU_ERR_ARG, "burnin is greater than or equal to iters");   // mcmc.jl:22-23
   if (!h->has_inits) return fail(h, MCU_ERR_STATE, "initial values must be set before mcu_run");
   CK(cudaSetDevice(h->device));
   int rc = upload_inputs(h); if (rc) return rc;
@@ -844,7 +853,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.logit_mask = 0ull;
   { const TplInfo ti = tpl_info(h); for (int j = 0; j < h->P && j < 64; ++j) if (ti.monlink[j] == LINK_HEUR) a.logit_mask |= 1ull << j; }
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
-  const bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
+  bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   long long chunk = 256;
   if (const char* e = std::getenv("MCU_CHUNK_ITERS")) { long long v = std::atoll(e); if (v > 0) chunk = v; }
@@ -873,6 +882,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     if (fast) {
       rc = seeds_fast_launch(h->inputs["r"].data(), h->inputs["n"].data(), h->inputs["x1"].data(), h->inputs["x2"].data(), a, h->h_blocks.data(),
                              h->h_scales, h->h_SigmaL.empty() || h->h_SigmaL[0].empty() ? nullptr : h->h_SigmaL[0].data(), h->stream);
+      if (rc == -2) { fast = false; chunk = 256; continue; }   // design is not 0/1 indicators: the generic kernel takes over
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
     } else if (pumps_gibbs) {
       rc = pumps_gibbs_launch(h->inputs["y"].data(), h->inputs["t"].data(), (int)h->inputs["y"].size(), a, h->h_blocks[2], h->h_scales[2][0], h->stream);
@@ -901,15 +911,19 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   CK(cudaGetLastError());
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
   h->iter += iters;
+  if (h->rng_mode == MCU_RNG_EXTERNAL) {   // a shim stream that ran dry would silently feed constant draws: report it
+    std::vector<unsigned long long> pos(C);
+    CK(cudaMemcpy(pos.data(), h->d_ext_pos, sizeof(unsigned long long) * C, cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < C; ++c) if (pos[c] == ~0ull) return fail(h, MCU_ERR_STATE, "external uniform stream exhausted (chain " + std::to_string(c) + "): supply more draws per chain");
+  }
   if (out && kept > 0) {
-    double* d_out = nullptr;
+    double* d_out = nullptr;   // handle-lifetime staging buffer: no cudaMalloc / cudaFree on the hot call
     const size_t total = (size_t)kept * h->P * C;
-    CK(cudaMalloc(&d_out, sizeof(double) * total));
+    rc = stage(h, sizeof(double) * total, (void**)&d_out); if (rc) return rc;
     launch_samples_to_julia(h->d_samples, d_out, kept, h->P, h->C, h->stream);
     h->launches++;
     CK(cudaMemcpyAsync(out, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_out);
     CK(cudaGetLastError());
   }
   return MCU_OK;
@@ -940,24 +954,33 @@ int mcu_get_state(mcu_handle h, double* values, double* tune, int64_t* iter) {
 int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_t iter) {
   if (!h || !values) return h ? fail(h, MCU_ERR_ARG, "values is NULL") : MCU_ERR_ARG;
   if (h->h_blocks.empty()) return fail(h, MCU_ERR_STATE, "set the sampling scheme before the state");
+  // the tune records are (re)created only at iteration 1 (sampler.jl:40-45): a chain resumed later needs the ones it had
+  if (!tune && h->tune_size > 0 && iter > 0) return fail(h, MCU_ERR_ARG, "a state at iteration > 0 needs its sampler tune records");
   CK(cudaSetDevice(h->device));
   int rc = upload_inputs(h); if (rc) return rc;
   rc = ensure_chain_buffers(h); if (rc) return rc;
   const size_t C = (size_t)h->C;
   {
-    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->D));
+    double* tmp = nullptr; rc = stage(h, sizeof(double) * C * h->D, (void**)&tmp); if (rc) return rc;
     CK(cudaMemcpyAsync(tmp, values, sizeof(double) * C * h->D, cudaMemcpyHostToDevice, h->stream));
     launch_records_to_soa(tmp, h->d_state, h->C, h->D, h->stream); h->launches++;
-    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+    CK(cudaStreamSynchronize(h->stream));
   }
   if (tune && h->tune_size > 0) {
-    double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * h->tune_size));
+    double* tmp = nullptr; rc = stage(h, sizeof(double) * C * h->tune_size, (void**)&tmp); if (rc) return rc;
     CK(cudaMemcpyAsync(tmp, tune, sizeof(double) * C * h->tune_size, cudaMemcpyHostToDevice, h->stream));
     launch_records_to_soa(tmp, h->d_tune, h->C, (int)h->tune_size, h->stream); h->launches++;
-    CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp);
+    CK(cudaStreamSynchronize(h->stream));
+  } else if (h->tune_size > 0) {
+    CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)h->tune_size, h->stream));
   }
+  // a state set from outside starts a new history: the streaming moments and the stored samples of the previous one are dropped
+  CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
+  CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  h->iter = iter; h->has_inits = true;
+  h->iter = iter; h->has_inits = true; h->samples_kept = 0;
   free_glm_buffers(h);
   return MCU_OK;
 }

@@ -61,7 +61,7 @@ struct Draws {
   }
   __device__ __forceinline__ double next_ext() {
     unsigned long long p = *ext_pos;
-    if (p >= ext_n) return 0.5;
+    if (p >= ext_n) { *ext_pos = ~0ull; return 0.5; }   // exhausted: the cursor becomes a sentinel that mcu_run turns into MCU_ERR_STATE
     *ext_pos = p + 1;
     return ext[p];
   }

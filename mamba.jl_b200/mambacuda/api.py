@@ -613,24 +613,36 @@ def _wrap(mm, eng, value, start, thin, chains):
 
 
 def _restart(mc, iters):
+    import copy
     thin = mc.step
     if mc.last != (mc.model.iter // thin) * thin:
         raise ArgumentError("chain is missing its last iteration")          # mcmc.jl:5-6
+    mm = copy.deepcopy(mc.model)                                            # mm = deepcopy(mc.model): mcmc.jl:8
     eng = mc.engine
     streaming = eng is not None and getattr(mc, "_streaming", False)
+    seed = getattr(mc, "_seed", eng.seed if eng is not None else 123)
+    if eng is not None and eng.iter() != mm.iter:
+        # the live handle has been advanced by an earlier mcmc(mc, n) from this same object: put it back at mc's own ModelStates
+        eng.set_state(np.stack([st.value for st in mm.states]), np.stack([st.tune for st in mm.states]), mm.iter)
+        streaming = False
     if eng is None:   # a ModelChains that came back from read(): rebuild the device handle at the stored ModelStates
-        mm = mc.model
         if not mm.states:
             raise ArgumentError("chain is missing its last iteration")
-        eng = Engine(mm.template, len(mc.chains), seed=getattr(mc, "_seed", 123))
+        eng = Engine(mm.template, len(mc.chains), seed=seed)
         for k, v in mm.inputs.items():
             eng.set_data(k, v)
         eng.set_scheme(_block_descs(mm))
         eng.set_state(np.stack([st.value for st in mm.states]), np.stack([st.tune for st in mm.states]), mm.iter)
-    value = eng.run(iters, burnin=mc.model.burnin, thin=thin)
-    mc2 = _wrap(mc.model, eng, value, mc.last + thin, thin, len(mc.chains))
-    return ModelChains(np.concatenate([mc.value, mc2.value], axis=0), mc2.model, engine=eng, nodelinks=mc2._nodelinks, streaming=streaming,
-                       start=mc.first, thin=thin, names=mc.names, chains=mc.chains)
+    value = eng.run(iters, burnin=mm.burnin, thin=thin)
+    mc2 = _wrap(mm, eng, value, mc.last + thin, thin, len(mc.chains))
+    # the handle's streaming moments now cover the new draws as well: only the returned object may read them; the source keeps
+    # the handle for density calls (dic / predict) but its diagnostics go back to its own materialised array
+    mc._streaming = False
+    mc._seed = seed
+    out = ModelChains(np.concatenate([mc.value, mc2.value], axis=0), mc2.model, engine=eng, nodelinks=mc2._nodelinks, streaming=streaming,
+                      start=mc.first, thin=thin, names=mc.names, chains=mc.chains)
+    out._seed = seed
+    return out
 
 
 def gelmandiag(c, alpha=0.05, mpsrf=False, transform=False):

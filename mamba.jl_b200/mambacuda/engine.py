@@ -117,13 +117,14 @@ class Engine:
     def kept(self, first_iter, iters, burnin, thin):
         return self.L.mcu_kept(first_iter, iters, burnin, thin)
 
-    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False):
-        """Returns the [kept × p × chains] block (Fortran order) or None when out=False."""
+    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False, partial=False):
+        """Returns the [kept × p × chains] block (Fortran order) or None when out=False.
+        partial=True: this call is one segment of a longer run (MCU_RUN_PARTIAL)."""
         _, p, _ = self.dims()
         it0 = self.iter()
         kept = self.kept(it0, iters, burnin, thin)
         flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0) | \
-            (_lib.RUN_GLM_REFERENCE if glm_reference else 0)
+            (_lib.RUN_GLM_REFERENCE if glm_reference else 0) | (_lib.RUN_PARTIAL if partial else 0)
         arr = None
         if out:
             arr = np.full((kept, p, self.n_chains), np.nan, order="F")

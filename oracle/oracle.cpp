@@ -338,25 +338,62 @@ static void write_tune(const Model& m, double* o) {
 
 int64_t orc_tune_size(void* h) { return tune_size(((Ctx*)h)->model); }
 int64_t orc_kept(int64_t iters, int64_t burnin, int64_t thin) { return iters > burnin ? (iters - burnin) / thin : 0; }
+// number of i in (first, first + iters] with i > burnin and (i - burnin) % thin == 0 (restart segments, mcmc.jl:3-16)
+int64_t orc_kept2(int64_t first, int64_t iters, int64_t burnin, int64_t thin) {
+  auto upto = [&](int64_t i) { return i > burnin ? (i - burnin) / thin : 0; };
+  return upto(first + iters) - upto(first);
+}
+
+// inverse of write_tune: the tune records of a restarted chain (mcmc(mc, iters) keeps the Sampler.tune objects: mcmc.jl:8, sampler.jl:40-45);
+// the fields that are not part of the blob are the constructor constants the fresh branch of block_update sets
+static void read_tune(Model& m, const double* o) {
+  for (size_t b = 0; b < m.samplers.size(); ++b) {
+    SamplerSpec& sp = m.samplers[b]; Tune& t = sp.tune; const size_t k = (size_t)m.block_dim((int)b);
+    switch (sp.kind) {
+      case S_AMWG:
+        t = Tune(); t.init = true; t.batchsize = sp.batchsize > 0 ? sp.batchsize : 50; t.target = sp.target > 0 ? sp.target : 0.44;
+        t.m = (long)*o++; t.adapt = *o++ != 0.0;
+        t.sigma.assign(o, o + k); o += k;
+        t.accept.resize(k); for (size_t i = 0; i < k; ++i) t.accept[i] = (long)*o++;
+        break;
+      case S_NUTS:
+        t = Tune(); t.init = true; t.target = sp.target > 0 ? sp.target : 0.6;
+        t.adapt = *o++ != 0.0; t.alpha = *o++; t.epsilon = *o++; t.epsilonbar = *o++; t.Hbar = *o++; t.m = (long)*o++; t.mu = *o++; t.nalpha = (long)*o++;
+        break;
+      case S_AMM:
+        t = Tune(); t.init = true; t.beta = sp.beta > 0 ? sp.beta : 0.05; t.scale = sp.amm_scale > 0 ? sp.amm_scale : 2.38;
+        chol_lower(sp.scale, k, t.SigmaL);
+        t.adapt = *o++ != 0.0; t.m = (long)*o++;
+        t.Mv.assign(o, o + k); o += k; t.Mvv.assign(o, o + k * k); o += k * k; t.SigmaLm.assign(o, o + k * k); o += k * k;
+        break;
+      default: break;
+    }
+  }
+}
 
 // mcmc(model, data, inits, iters; burnin, thin, chains): mcmc.jl:19-83.
-//  inits [n_inits × D]; chain c (global id g = chain_offset + c) starts from record g % n_inits,
+//  inits [n_inits × D]; chain c (global id g = chain_ids ? chain_ids[c] : chain_offset + c) starts from record g % n_inits,
 //  plus optional N(0, jitter_sd²) jitter on the unconstrained scale (Philox stream kind 1, iter 0,
 //  block 0, draw j = state element index).
-//  out [kept × p × n_chains] column-major (may be NULL); final_state [n_chains × D] (may be NULL);
-//  tune_out [n_chains × orc_tune_size] (may be NULL);
+//  Restart (mcmc(mc, iters): mcmc.jl:3-16) when iter0 > 0: inits is [n_chains × D] (record c = state of chain c after iteration
+//  iter0), tune_in [n_chains × orc_tune_size] the tune records written by an earlier call; iterations iter0 + 1 .. iter0 + iters run.
+//  out [kept × p × n_chains] column-major (may be NULL), kept = orc_kept2(iter0, iters, burnin, thin); final_state [n_chains × D]
+//  (may be NULL); tune_out [n_chains × orc_tune_size] (may be NULL);
+//  margins [n_chains × iters] (may be NULL): the smallest decision margin of each iteration (samplers.hpp note_margin);
 //  ext_u: NULL for Philox mode, else [n_chains × n_per_chain] uniforms consumed sequentially.
 //  nthreads: chains are distributed over this many std::threads (the reference would use pmap
 //  over worker processes, utils.jl:91-98 — disabled in this version).
-int orc_run(void* h, int64_t n_chains, int64_t chain_offset, uint64_t seed, const double* inits, int64_t n_inits,
-            double jitter_sd, int64_t iters, int64_t burnin, int64_t thin, double* out, double* final_state,
-            double* tune_out, const double* ext_u, int64_t n_per_chain, int nthreads) {
+int orc_run2(void* h, int64_t n_chains, int64_t chain_offset, const int64_t* chain_ids, uint64_t seed, const double* inits, int64_t n_inits,
+             double jitter_sd, int64_t iter0, const double* tune_in, int64_t iters, int64_t burnin, int64_t thin, double* out,
+             double* final_state, double* tune_out, double* margins, const double* ext_u, int64_t n_per_chain, int nthreads) {
   Ctx* c = (Ctx*)h;
-  if (iters <= burnin) { c->err = "burnin is greater than or equal to iters"; return MCU_ERR_ARG; }   // mcmc.jl:22-23
+  if (iter0 == 0 && iters <= burnin) { c->err = "burnin is greater than or equal to iters"; return MCU_ERR_ARG; }   // mcmc.jl:22-23
   if (n_inits < 1) { c->err = "fewer initial values than chains"; return MCU_ERR_ARG; }              // mcmc.jl:24-25
   if (thin < 1) { c->err = "thin must be positive"; return MCU_ERR_ARG; }
+  if (iter0 > 0 && n_inits != n_chains) { c->err = "a restart needs one state record per chain"; return MCU_ERR_ARG; }
   const int D = c->model.state_dim(); const int p = c->model.n_monitor();
-  const int64_t kept = orc_kept(iters, burnin, thin);
+  const int64_t kept = orc_kept2(iter0, iters, burnin, thin);
+  const int64_t row0 = iter0 > burnin ? (iter0 - burnin) / thin : 0;
   const int64_t nt = tune_size(c->model);
   if (nthreads < 1) nthreads = 1;
   std::vector<std::string> errs(nthreads);
@@ -365,38 +402,43 @@ int orc_run(void* h, int64_t n_chains, int64_t chain_offset, uint64_t seed, cons
       for (int64_t k = tid; k < n_chains; k += nthreads) {   // mcmc_worker!: mcmc.jl:62-83
         Model m = c->model;                                    // deepcopy(m)
         m.burnin = burnin;
-        int64_t g = chain_offset + k;
+        int64_t g = chain_ids ? chain_ids[k] : chain_offset + k;
         std::unique_ptr<Rng> rng;
         if (ext_u) rng.reset(new ExternalRng(ext_u + k * n_per_chain, (size_t)n_per_chain));
         else rng.reset(new PhiloxRng(seed, (uint32_t)g));
-        std::vector<double> x0(inits + (g % n_inits) * D, inits + (g % n_inits + 1) * D);
+        const int64_t rec = iter0 > 0 ? k : g % n_inits;
+        std::vector<double> x0(inits + rec * D, inits + (rec + 1) * D);
         m.setinits(x0.data());
-        if (jitter_sd > 0) {
+        if (jitter_sd > 0 && iter0 == 0) {
           PhiloxRng jr(seed, (uint32_t)g); jr.seek(0, 0, 1);
-          int o = 0;
           for (int i : m.state_nodes()) {
             Node& n = m.nodes[i]; Vec y, z;
             link_sub(n.distr, n.value, y);
-            for (double& yi : y) { yi += jitter_sd * jr.normal(); (void)o; }
+            for (double& yi : y) yi += jitter_sd * jr.normal();
             invlink_sub(n.distr, y.data(), y.size(), z);
             n.value = z;
           }
           std::vector<double> xs(D); m.get_state(xs.data()); m.setinits(xs.data());
         }
         for (auto& sp : m.samplers) sp.tune = Tune();
+        if (iter0 > 0) { m.iter = (long)iter0; if (tune_in && nt > 0) read_tune(m, tune_in + k * nt); }
         std::vector<double> mon(p);
-        for (int64_t i = 1; i <= iters; ++i) {
+        for (int64_t i = iter0 + 1; i <= iter0 + iters; ++i) {
+          double margin = INFINITY;
+          g_margin_slot = margins ? &margin : nullptr;
           sweep(m, *rng);
+          g_margin_slot = nullptr;
+          if (margins) margins[k * iters + (i - iter0 - 1)] = margin;
           if (i > burnin && (i - burnin) % thin == 0 && out) {          // mcmc.jl:76-78
             m.get_monitor(mon.data());
-            int64_t row = (i - (burnin + thin)) / thin;                  // iters2inds: chains.jl:66-69,81-87
+            int64_t row = (i - burnin) / thin - 1 - row0;                // iters2inds: chains.jl:66-69,81-87
             for (int j = 0; j < p; ++j) out[row + kept * (j + (int64_t)p * k)] = mon[j];
           }
         }
         if (final_state) m.get_state(final_state + k * D);
         if (tune_out) write_tune(m, tune_out + k * nt);
       }
-    } catch (std::exception& e) { errs[tid] = e.what(); }
+    } catch (std::exception& e) { errs[tid] = e.what(); g_margin_slot = nullptr; }
   };
   if (nthreads == 1) worker(0);
   else {
@@ -406,6 +448,12 @@ int orc_run(void* h, int64_t n_chains, int64_t chain_offset, uint64_t seed, cons
   }
   for (auto& e : errs) if (!e.empty()) { c->err = e; return -1; }
   return 0;
+}
+int orc_run(void* h, int64_t n_chains, int64_t chain_offset, uint64_t seed, const double* inits, int64_t n_inits,
+            double jitter_sd, int64_t iters, int64_t burnin, int64_t thin, double* out, double* final_state,
+            double* tune_out, const double* ext_u, int64_t n_per_chain, int nthreads) {
+  return orc_run2(h, n_chains, chain_offset, nullptr, seed, inits, n_inits, jitter_sd, 0, nullptr, iters, burnin, thin, out, final_state,
+                  tune_out, nullptr, ext_u, n_per_chain, nthreads);
 }
 
 // gelmandiag(c; alpha, transform): linkcode per column (-1 heuristic / 0 identity / 1 log) or NULL = no transform

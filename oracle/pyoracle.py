@@ -85,6 +85,10 @@ def lib():
         L.orc_kept.argtypes = [C.c_int64] * 3
         L.orc_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, dp, C.c_int64, C.c_double,
                               C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, C.c_int64, C.c_int]
+        L.orc_kept2.restype = C.c_int64
+        L.orc_kept2.argtypes = [C.c_int64] * 4
+        L.orc_run2.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_uint64, dp, C.c_int64, C.c_double,
+                               C.c_int64, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.c_int64, C.c_int]
         L.orc_gelmandiag.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_int), dp]
         L.orc_summarystats.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64, dp]
         L.orc_fquantile.restype = C.c_double
@@ -188,21 +192,34 @@ class Oracle:
         return self.L.orc_tune_size(self.h)
 
     def run(self, n_chains, inits, iters, burnin=0, thin=1, seed=123, chain_offset=0, jitter_sd=0.0,
-            ext_u=None, nthreads=1, store=True):
+            ext_u=None, nthreads=1, store=True, chain_ids=None, iter0=0, tune_in=None, margins=False):
+        """mcmc() for n_chains chains.  chain_ids: explicit global chain ids (scattered samples of a large run);
+        iter0 > 0: restart — inits holds one state record per chain and tune_in their tune records;
+        margins=True also returns [n_chains x iters], the smallest decision margin of every iteration (samplers.hpp)."""
         inits = _f64(np.atleast_2d(inits))
         D, p = self.dims()
         assert inits.shape[1] == D
-        kept = self.L.orc_kept(iters, burnin, thin)
+        if chain_ids is not None:
+            chain_ids = np.ascontiguousarray(chain_ids, dtype=np.int64)
+            n_chains = chain_ids.size
+        kept = self.L.orc_kept2(iter0, iters, burnin, thin)
         out = np.full((kept, p, n_chains), np.nan, order="F") if store else None
         final = np.empty((n_chains, D))
         nt = self.tune_size()
         tune = np.zeros((n_chains, max(nt, 1)))
+        tin = None
+        if tune_in is not None and nt > 0:
+            tin = _f64(np.atleast_2d(tune_in)); assert tin.shape == (n_chains, nt)
+        marg = np.full((n_chains, iters), np.inf) if margins else None
         npc = 0
         if ext_u is not None:
             ext_u = _f64(np.atleast_2d(ext_u)); npc = ext_u.shape[1]
-        rc = self.L.orc_run(self.h, n_chains, chain_offset, seed, _dp(inits), inits.shape[0], jitter_sd,
-                            iters, burnin, thin, _dp(out), _dp(final), _dp(tune), _dp(ext_u), npc, nthreads)
+        ids = None if chain_ids is None else chain_ids.ctypes.data_as(C.POINTER(C.c_int64))
+        rc = self.L.orc_run2(self.h, n_chains, chain_offset, ids, seed, _dp(inits), inits.shape[0], jitter_sd, iter0, _dp(tin),
+                             iters, burnin, thin, _dp(out), _dp(final), _dp(tune), _dp(marg), _dp(ext_u), npc, nthreads)
         self._chk(rc)
+        if margins:
+            return out, final, tune[:, :nt], marg
         return out, final, tune[:, :nt]
 
 

@@ -23,6 +23,22 @@ typedef std::vector<double> Vec;
 typedef std::function<double(const Vec&)> LogF;
 typedef std::function<double(const Vec&, Vec&)> LogFGrad;   // returns logf, fills grad
 
+// Decision audit (tests/helpers.py::audit_divergence): every comparison that steers a sampler notes how close it came to its
+// threshold, relative to max(1, |threshold|); the engine keeps the minimum per chain and iteration.  A device chain may part from
+// the oracle's ONLY in an iteration where this minimum is at rounding level (the two sides evaluate the same density in a
+// different floating-point order) — anything else is a real difference in draw order or arithmetic.
+inline thread_local double* g_margin_slot = nullptr;
+inline void note_margin(double lhs, double rhs, double scale = 1.0) {
+  if (!g_margin_slot || !std::isfinite(lhs) || !std::isfinite(rhs)) return;
+  const double m = std::fabs(lhs - rhs) / std::fmax(scale, std::fabs(rhs));
+  if (m < *g_margin_slot) *g_margin_slot = m;
+}
+// rand() < exp(delta), the Metropolis-Hastings test of every sampler file (e.g. amwg.jl:107); noted on the log scale
+inline bool mh_test(double u, double delta) {
+  note_margin(std::log(u), delta);
+  return u < std::exp(delta);
+}
+
 inline double dotv(const Vec& a, const Vec& b) { double s = 0; for (size_t i = 0; i < a.size(); ++i) s += a[i] * b[i]; return s; }
 inline double dotv(const Vec& a) { return dotv(a, a); }   // utils.jl:62
 
@@ -40,7 +56,7 @@ inline void amwg_sub(Vec& v, Tune& t, const LogF& logf, Rng& rng) {   // amwg.jl
     double x = v[i];
     v[i] += z[i];
     double logfprime = logf(v);
-    if (rng.uniform() < std::exp(logfprime - logf0)) {
+    if (mh_test(rng.uniform(), logfprime - logf0)) {
       logf0 = logfprime;
       t.accept[i] += t.adapt ? 1 : 0;
     } else {
@@ -78,11 +94,13 @@ inline double rgamma_mt(double a, Rng& rng) {
   const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
   for (;;) {
     double x, v;
-    do { x = rng.normal(); v = 1.0 + c * x; } while (v <= 0.0);
+    do { x = rng.normal(); v = 1.0 + c * x; note_margin(v, 0.0); } while (v <= 0.0);
     v = v * v * v;
     const double u = rng.uniform();
     const double x2 = x * x;
+    note_margin(u, 1.0 - 0.0331 * x2 * x2);
     if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+    note_margin(std::log(u), 0.5 * x2 + d * (1.0 - v + std::log(v)));
     if (std::log(u) < 0.5 * x2 + d * (1.0 - v + std::log(v))) return boost * d * v;
   }
 }
@@ -99,6 +117,7 @@ inline void slice_uni_sample(Vec& v, const Vec& width, const LogF& logf, Rng& rn
     v[i] = runif(lower[i], upper[i], rng);
     while (true) {
       logf0 = logf(v);
+      note_margin(logf0, p0);
       if (!(logf0 < p0)) break;
       double value = v[i];
       if (value < x) lower[i] = value; else upper[i] = value;
@@ -113,7 +132,10 @@ inline void slice_multi_sample(Vec& v, const Vec& width, const LogF& logf, Rng& 
   for (size_t i = 0; i < n; ++i) lower[i] = v[i] - width[i] * rng.uniform();
   for (size_t i = 0; i < n; ++i) upper[i] = lower[i] + width[i];
   for (size_t i = 0; i < n; ++i) x[i] = width[i] * rng.uniform() + lower[i];
-  while (logf(x) < p0) {
+  while (true) {
+    const double lx = logf(x);
+    note_margin(lx, p0);
+    if (!(lx < p0)) break;
     for (size_t i = 0; i < n; ++i) {
       double value = x[i];
       if (value < v[i]) lower[i] = value; else upper[i] = value;
@@ -161,7 +183,7 @@ inline void rwm_sample(Vec& v, const Vec& scale, int proposal, const LogF& logf,
   double u = rng.uniform();
   double lx = logf(x);          // logf(x) is evaluated first, then logf(v): the model is left at v
   double lv = logf(v);
-  if (u < std::exp(lx - lv)) v = x;
+  if (mh_test(u, lx - lv)) v = x;
 }
 
 // ---------------------------------------------------------------------------- NUTS
@@ -176,8 +198,10 @@ inline Leap leapfrog(const Vec& x, const Vec& r, const Vec& grad, double epsilon
   return o;
 }
 inline bool nouturn(const Vec& xminus, const Vec& xplus, const Vec& rminus, const Vec& rplus) {  // nuts.jl:183-187
-  size_t n = xminus.size(); double a = 0, b = 0;
-  for (size_t i = 0; i < n; ++i) { double d = xplus[i] - xminus[i]; a += d * rminus[i]; b += d * rplus[i]; }
+  size_t n = xminus.size(); double a = 0, b = 0, sa = 0, sb = 0;
+  for (size_t i = 0; i < n; ++i) { double d = xplus[i] - xminus[i]; a += d * rminus[i]; b += d * rplus[i]; sa += std::fabs(d * rminus[i]); sb += std::fabs(d * rplus[i]); }
+  if (sa > 0) note_margin(a, 0.0, sa);
+  if (sb > 0) note_margin(b, 0.0, sb);
   return a >= 0 && b >= 0;
 }
 struct Tree {
@@ -190,6 +214,7 @@ inline Tree buildtree(const Vec& x, const Vec& r, const Vec& grad, int pm, int j
   if (j == 0) {
     Leap l = leapfrog(x, r, grad, pm * epsilon, f);
     double logpprime = l.logf - 0.5 * dotv(l.r);
+    note_margin(logu0, logpprime);
     t.nprime = logu0 < logpprime ? 1 : 0;
     t.sprime = logu0 < logpprime + 1000.0;
     t.xminus = t.xplus = l.x; t.rminus = t.rplus = l.r; t.gradminus = t.gradplus = l.grad;
@@ -207,7 +232,9 @@ inline Tree buildtree(const Vec& x, const Vec& r, const Vec& grad, int pm, int j
         t2 = buildtree(t.xplus, t.rplus, t.gradplus, pm, j - 1, epsilon, f, logp0, logu0, rng);
         t.xplus = t2.xplus; t.rplus = t2.rplus; t.gradplus = t2.gradplus;
       }
-      if (rng.uniform() < (double)t2.nprime / (double)(t.nprime + t2.nprime)) t.xprime = t2.xprime;
+      const double um = rng.uniform(), ratio = (double)t2.nprime / (double)(t.nprime + t2.nprime);
+      note_margin(um, ratio);
+      if (um < ratio) t.xprime = t2.xprime;
       t.nprime += t2.nprime;
       t.sprime = t2.sprime && nouturn(t.xminus, t.xplus, t.rminus, t.rplus);
       t.alphaprime += t2.alphaprime;
@@ -228,7 +255,9 @@ inline void nuts_sub(Vec& v, Tune& tune, double epsilon, const LogFGrad& f, Rng&
   Vec xminus = l.x, xplus = l.x, rminus = l.r, rplus = l.r, gradminus = l.grad, gradplus = l.grad;
   int j = 0; long nn = 1; bool s = true;
   while (s) {
-    int pm = 2 * (rng.uniform() > 0.5 ? 1 : 0) - 1;
+    const double ud = rng.uniform();
+    note_margin(ud, 0.5);
+    int pm = 2 * (ud > 0.5 ? 1 : 0) - 1;
     Tree t;
     if (pm == -1) {
       t = buildtree(xminus, rminus, gradminus, pm, j, epsilon, f, logp0, logu0, rng);
@@ -237,7 +266,11 @@ inline void nuts_sub(Vec& v, Tune& tune, double epsilon, const LogFGrad& f, Rng&
       t = buildtree(xplus, rplus, gradplus, pm, j, epsilon, f, logp0, logu0, rng);
       xplus = t.xplus; rplus = t.rplus; gradplus = t.gradplus;
     }
-    if (t.sprime && rng.uniform() < (double)t.nprime / (double)nn) v = t.xprime;
+    if (t.sprime) {
+      const double um = rng.uniform(), ratio = (double)t.nprime / (double)nn;
+      note_margin(um, ratio);
+      if (um < ratio) v = t.xprime;
+    }
     j += 1;
     nn += t.nprime;
     s = t.sprime && nouturn(xminus, xplus, rminus, rplus);
@@ -253,12 +286,14 @@ inline double nutsepsilon(const Vec& x, const LogFGrad& f, Rng& rng) {   // nuts
   double epsilon = 1.0;
   Leap l1 = leapfrog(x, l0.r, l0.grad, epsilon, f);
   double prob = std::exp(l1.logf - l0.logf - 0.5 * (dotv(l1.r) - dotv(l0.r)));
+  note_margin(prob, 0.5);
   int pm = 2 * (prob > 0.5 ? 1 : 0) - 1;
   int guard = 0;
   while (std::pow(prob, pm) > std::pow(0.5, pm)) {
     epsilon *= std::pow(2.0, pm);
     l1 = leapfrog(x, l0.r, l0.grad, epsilon, f);
     prob = std::exp(l1.logf - l0.logf - 0.5 * (dotv(l1.r) - dotv(l0.r)));
+    note_margin(prob, 0.5);
     if (++guard > 2000) break;   // not in the reference; guards the oracle against NaN loops
   }
   return epsilon;
@@ -318,7 +353,7 @@ inline void mala_sample(Vec& v, double epsilon, const Vec& SigmaL, const LogFGra
   const double q0 = -0.5 * dotv(Linv(w));
   for (size_t i = 0; i < n; ++i) w[i] = y[i] - v[i] - m0[i];
   const double q1 = -0.5 * dotv(Linv(w));
-  if (rng.uniform() < std::exp((logf1 - q1) - (logf0 - q0))) v = y;
+  if (mh_test(rng.uniform(), (logf1 - q1) - (logf0 - q0))) v = y;
 }
 
 // ---------------------------------------------------------------------------- HMC
@@ -347,7 +382,7 @@ inline void hmc_sample(Vec& v, double epsilon, int L, const Vec& SigmaL, const L
     return 0.5 * dotv(w);
   };
   double Kp0 = kinetic(p0), Kp1 = kinetic(p1);
-  if (rng.uniform() < std::exp((logf1 - Kp1) - (logf0 - Kp0))) v = x1;
+  if (mh_test(rng.uniform(), (logf1 - Kp1) - (logf0 - Kp0))) v = x1;
 }
 
 // ---------------------------------------------------------------------------- AMM
@@ -432,7 +467,7 @@ inline void amm_sample(Vec& v, Tune& t, const LogF& logf, bool adapt, Rng& rng) 
   for (size_t i = 0; i < n; ++i) x[i] += v[i];
   double u = rng.uniform();
   double lx = logf(x), lv = logf(v);
-  if (u < std::exp(lx - lv)) v = x;
+  if (mh_test(u, lx - lv)) v = x;
   if (t.adapt) {
     t.m += 1;
     double p = (double)t.m / ((double)t.m + 1.0);

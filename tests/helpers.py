@@ -132,3 +132,84 @@ def glm_data(N=200, d=8, seed=1):
     beta = rng.normal(size=d) / np.sqrt(d)
     y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(float)
     return X, y, beta
+
+
+# ---- audited comparison of a device run with the oracle's (no tolerated fraction of diverging chains) -------------------------
+TIE = 1e-9   # a decision is a "threshold tie" when |lhs - rhs| < TIE * max(1, |rhs|) (oracle/samplers.hpp note_margin)
+
+
+def audit_divergence(g, o, margins, kept_iters, iter0, rtol=1e-8, atol=1e-10, tune_rtol=1e-6, tie=TIE, int_tune_cols=()):
+    """g, o = (out [kept x p x C], state [C x D], tune [C x T]) of the device and of the oracle on the same stream;
+    margins [C x iters] = the oracle's smallest decision margin of iterations iter0 + 1 .. iter0 + iters;
+    kept_iters = the (absolute, 1-based) iteration of every row of `out`.
+
+    Every chain must reproduce the oracle to `rtol`.  A chain that does not is accepted ONLY if the oracle took a decision within
+    `tie` of its threshold inside the window of iterations in which the first difference appears (the two sides evaluate the same
+    density in a different floating-point order, so only such a decision can legitimately go the other way); from there on the two
+    trajectories are different realisations and are not compared.  Integer tune columns (accept counters, m) of agreeing chains
+    must be equal.  Returns (number of chains that agree throughout, list of (chain, first differing iteration window, margin))."""
+    out_g, st_g, tune_g = g
+    out_o, st_o, tune_o = o
+    C = st_g.shape[0]
+    iters = margins.shape[1]
+    kept_iters = np.asarray(kept_iters, dtype=np.int64)
+    assert out_g.shape == out_o.shape and out_g.shape[0] == kept_iters.size
+    assert not np.isnan(out_g).any() and not np.isnan(st_g).any()
+    ties, bad = [], []
+    for c in range(C):
+        rows_ok = np.all(np.isclose(out_g[:, :, c], out_o[:, :, c], rtol=rtol, atol=atol), axis=1) if kept_iters.size else np.ones(0, bool)
+        end_ok = np.allclose(st_g[c], st_o[c], rtol=rtol, atol=atol) and \
+            np.allclose(tune_g[c], tune_o[c], rtol=tune_rtol, atol=tune_rtol * 1e-2, equal_nan=True)
+        if rows_ok.all() and end_ok:
+            for j in int_tune_cols:
+                assert tune_g[c, j] == tune_o[c, j], f"chain {c}: integer tune column {j} differs ({tune_g[c, j]} vs {tune_o[c, j]})"
+            continue
+        if not rows_ok.all():
+            r = int(np.argmin(rows_ok))
+            lo = kept_iters[r - 1] if r > 0 else iter0
+            hi = kept_iters[r]
+        else:
+            lo = kept_iters[-1] if kept_iters.size else iter0
+            hi = iter0 + iters
+        w = margins[c, lo - iter0:hi - iter0]
+        m = float(w.min()) if w.size else np.inf
+        (ties if m < tie else bad).append((c, (int(lo) + 1, int(hi)), m))
+    assert not bad, (f"{len(bad)} of {C} chains part from the oracle where no decision was within {tie:g} of its threshold "
+                     f"(chain, iterations, smallest margin): {bad[:8]}")
+    return C - len(ties), ties
+
+
+def resync_audit(eng, orc, ids, inits, iters, burnin, seed, jitter_sd, rtol, tie, run_kw=None, nthreads=None):
+    """Per-step parity (north_star: same state + same stream => same decisions and the same next state).  At every iteration the
+    sampled device chains `ids` are put at the oracle's state / tune records, both sides take ONE iteration, and the results must
+    agree to `rtol` unless the oracle's smallest decision margin of that iteration is below `tie`.  The other chains of the launch
+    simply keep running from their own states.  Returns (steps compared, [(chain, iteration, margin) of the ties])."""
+    import os
+    run_kw = run_kw or {}
+    nthreads = nthreads or os.cpu_count() or 4
+    ids = np.asarray(ids, dtype=np.int64)
+    ties, compared = [], 0
+    prev_o = prev_t = st = tune = None
+    for i in range(1, iters + 1):
+        if i == 1:      # iteration 1 starts from the (jittered) inits on both sides; the tune records are created there (sampler.jl:40-45)
+            eng.set_inits(inits, jitter_sd=jitter_sd)
+            _, st_o, tune_o, marg = orc.run(0, inits, 1, burnin=burnin, thin=1, seed=seed, jitter_sd=jitter_sd, chain_ids=ids,
+                                            nthreads=nthreads, margins=True, store=False)
+        else:
+            st[ids] = prev_o; tune[ids] = prev_t
+            eng.set_state(st, tune, i - 1)
+            _, st_o, tune_o, marg = orc.run(0, prev_o, 1, burnin=burnin, thin=1, seed=seed, chain_ids=ids, iter0=i - 1, tune_in=prev_t,
+                                            nthreads=nthreads, margins=True, store=False)
+        eng.run(1, burnin=burnin, thin=1, store=False, out=False, partial=True, **run_kw)
+        st, tune, it = eng.get_state()
+        assert it == i
+        for k, c in enumerate(ids):
+            same = np.allclose(st[c], st_o[k], rtol=rtol, atol=1e-9) and np.allclose(tune[c], tune_o[k], rtol=rtol * 10, atol=1e-9, equal_nan=True)
+            if not same:
+                assert marg[k, 0] < tie, (f"iteration {i}, chain {c}: device and oracle differ after one step from a common state and no "
+                                          f"decision was within {tie:g} of its threshold (smallest margin {marg[k, 0]:.3g}; "
+                                          f"max state diff {np.max(np.abs(st[c] - st_o[k])):.3g})")
+                ties.append((int(c), i, float(marg[k, 0])))
+        compared += len(ids)
+        prev_o, prev_t = st_o, tune_o
+    return compared, ties

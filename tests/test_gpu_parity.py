@@ -107,28 +107,50 @@ def test_glm_density_and_gradient(oracle):
 
 
 def run_pair(oracle, name, n_chains, iters, burnin, thin, seed=99, force_generic=True):
+    """The same mcmc() on the device and on the oracle; the oracle also reports its smallest decision margin per iteration."""
     eng, orc, inits = make_pair(oracle, name, n_chains, seed=seed)
     eng.set_inits(inits)
     out_g = eng.run(iters, burnin=burnin, thin=thin, force_generic=force_generic)
     st_g, tune_g, it = eng.get_state()
-    out_o, st_o, tune_o = orc.run(n_chains, inits, iters, burnin=burnin, thin=thin, seed=seed, nthreads=4)
+    out_o, st_o, tune_o, marg = orc.run(n_chains, inits, iters, burnin=burnin, thin=thin, seed=seed, nthreads=4, margins=True)
     assert it == iters
-    return (out_g, st_g, tune_g), (out_o, st_o, tune_o), eng, orc
+    return (out_g, st_g, tune_g), (out_o, st_o, tune_o, marg), eng, orc
 
 
-def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
-    """Chains that took identical decisions agree to rounding.  `min_frac` < 1 tolerates the rare chain
-    whose accept/reject comparison sits within rounding of the threshold (then everything after differs)."""
-    out_g, st_g, tune_g = g
-    out_o, st_o, tune_o = o
-    C = st_g.shape[0]
-    ok_state = np.array([np.allclose(st_g[c], st_o[c], rtol=rtol, atol=1e-10) for c in range(C)])
-    ok_out = np.array([np.allclose(out_g[:, :, c], out_o[:, :, c], rtol=rtol, atol=1e-10) for c in range(C)])
-    ok_tune = np.array([np.allclose(tune_g[c], tune_o[c], rtol=tune_rtol, atol=tune_rtol * 1e-2, equal_nan=True) for c in range(C)])
-    ok = ok_state & ok_out & ok_tune
-    assert ok.mean() >= min_frac, (f"only {ok.sum()}/{C} chains reproduce the oracle trajectory "
-                                   f"(state {ok_state.sum()}, samples {ok_out.sum()}, tune {ok_tune.sum()})")
-    assert not np.isnan(out_g).any()
+def kept_iterations(iters, burnin, thin, iter0=0):
+    return [i for i in range(iter0 + 1, iter0 + iters + 1) if i > burnin and (i - burnin) % thin == 0]
+
+
+def assert_same_run(g, o, iters, burnin, thin, rtol=1e-8, tune_rtol=1e-6):
+    """Every chain reproduces the oracle to rounding, or parts from it in an iteration where the oracle's own decision sat within
+    1e-9 of its threshold (helpers.audit_divergence) — no fraction of unexplained chains is tolerated.  Returns the tied chains."""
+    n_same, ties = helpers.audit_divergence(g, o[:3], o[3], kept_iterations(iters, burnin, thin), 0, rtol=rtol, tune_rtol=tune_rtol)
+    assert len(ties) <= max(1, g[1].shape[0] // 16), f"implausibly many threshold ties: {ties}"
+    return [t[0] for t in ties]
+
+
+def assert_same_chains(a, b, skip=(), rtol=1e-9, atol=1e-12):
+    """Two device runs of the same scheme (fused kernel / generic kernel / restarted) chain by chain, except chains in `skip`."""
+    for c in range(a.shape[2]):
+        if c not in skip:
+            np.testing.assert_allclose(a[:, :, c], b[:, :, c], rtol=rtol, atol=atol, err_msg=f"chain {c}")
+
+
+def resync(oracle, name, n_chains, iters, burnin, seed, rtol, tie=helpers.TIE, force_generic=True, run_kw=None):
+    """Gradient-based samplers (NUTS, HMC, MALA) amplify rounding along a trajectory, and dual averaging amplifies it from one
+    iteration to the next, so whole runs cannot be compared to a fixed tolerance; every single step from a common state can."""
+    eng, orc, inits = make_pair(oracle, name, n_chains, seed=seed)
+    tpl, blocks, _ = helpers.scheme(name)
+    ob = [helpers.oracle_block(b) for b in blocks]
+    for b in ob:
+        if b["kind"] == "nuts":
+            b["max_depth"] = 10           # the device stops doubling after 10 doublings (documented deviation)
+    orc.set_scheme(ob)
+    kw = dict(force_generic=force_generic); kw.update(run_kw or {})
+    compared, ties = helpers.resync_audit(eng, orc, np.arange(n_chains), inits, iters, burnin, seed, 0.0, rtol, tie, run_kw=kw, nthreads=4)
+    assert len(ties) <= max(1, compared // 200), f"implausibly many threshold ties: {ties}"
+    _, tune, _ = eng.get_state()
+    return eng, tune
 
 
 @pytest.mark.parametrize("name,iters,burnin,thin", [
@@ -145,7 +167,6 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("blocker_amwg_slice", 300, 150, 2),
     ("stacks_amwg", 300, 150, 2),
     ("dyes_rwm_slice", 300, 0, 1),
-    ("dyes_hmc_slice", 100, 0, 1),
     ("line_rwm", 500, 0, 1),
     ("line_rwm_unif", 500, 0, 1),
     ("line_rwm_tri", 500, 0, 1),
@@ -155,22 +176,16 @@ def assert_same_run(g, o, rtol=1e-8, min_frac=1.0, tune_rtol=1e-6):
     ("line_rwm_trw", 500, 0, 1),
     ("line_slice_uni", 400, 100, 1),
     ("line_amm", 500, 250, 1),
-    ("line_hmc", 300, 0, 1),
-    ("line_hmc_sigma", 300, 0, 1),
 ])
 def test_trajectories_match_oracle(oracle, name, iters, burnin, thin):
     g, o, _, _ = run_pair(oracle, name, 16, iters, burnin, thin)
     # AMM's SigmaLm comes from Mvv - Mv Mv' (cancellation): its entries agree to fewer digits than the chain does
-    assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4 if "amm" in name else 1e-6)
+    assert_same_run(g, o, iters, burnin, thin, tune_rtol=1e-4 if "amm" in name else 1e-6)
 
 
-@pytest.mark.parametrize("name", ["line_mala", "line_mala_sigma"])
-def test_mala_trajectories_match_oracle(oracle, name):
-    # The Langevin drift x + (epsilon/2) Sigma grad has Jacobian I + (epsilon/2) Sigma H; in the small-s2 region of the line model
-    # |epsilon H / 2| ~ 10, so rounding differences between the two machines grow ~10x per accepted step (first differences of
-    # 1e-8 appear after 100-300 iterations): step-wise agreement is observable over a short horizon, as for NUTS.
-    g, o, _, _ = run_pair(oracle, name, 32, 60, 0, 1)
-    assert_same_run(g, o, rtol=1e-5, min_frac=0.8)
+@pytest.mark.parametrize("name,iters", [("line_hmc", 120), ("line_hmc_sigma", 120), ("dyes_hmc_slice", 60), ("line_mala", 120), ("line_mala_sigma", 120)])
+def test_hmc_and_mala_steps_match_oracle(oracle, name, iters):
+    resync(oracle, name, 16, iters, 0, seed=99, rtol=1e-8)
 
 
 def test_mala_is_statistically_equivalent_to_the_published_posterior(oracle):
@@ -183,52 +198,28 @@ def test_mala_is_statistically_equivalent_to_the_published_posterior(oracle):
     assert abs(summ[0, 0] - 0.5971) < 0.05 and abs(summ[1, 0] - 0.8017) < 0.02   # doc/tutorial.rst:432-436
 
 
-def nuts_pair(oracle, name, n_chains, iters, burnin, seed, force_generic=True):
-    """The oracle runs the reference's recursive buildtree (nuts.jl:139-180), the device the unrolled
-    leaf-by-leaf form; both stop doubling after 10 doublings."""
-    eng, orc, inits = make_pair(oracle, name, n_chains, seed=seed)
-    tpl, blocks, _ = helpers.scheme(name)
-    ob = [helpers.oracle_block(b) for b in blocks]
-    for b in ob:
-        if b["kind"] == "nuts":
-            b["max_depth"] = 10
-    orc.set_scheme(ob)
-    eng.set_inits(inits)
-    out_g = eng.run(iters, burnin=burnin, thin=1, force_generic=force_generic)
-    st_g, tune_g, _ = eng.get_state()
-    out_o, st_o, tune_o = orc.run(n_chains, inits, iters, burnin=burnin, thin=1, seed=seed, nthreads=4)
-    return (out_g, st_g, tune_g), (out_o, st_o, tune_o)
-
-
 @pytest.mark.parametrize("name", ["line_nuts_slice", "line_nuts_all", "rats_nuts_slice", "pumps_amwg_nuts", "surgical_nuts_slice", "equiv_nuts_slice"])
-def test_nuts_adaptive_trajectories_match_oracle(oracle, name):
-    # Dual averaging multiplies a perturbation of the acceptance statistic by sqrt(m)/gamma/(m+t0) ~ 2-10x per
-    # adaptive iteration (nuts.jl:70-75), so libm-level rounding differences between two machines grow
-    # exponentially while adapting: step-wise agreement is only observable over a short horizon.
-    # 64 chains x 12 adaptive + 4 non-adaptive iterations exercise trees of several depths and both directions.
-    g, o = nuts_pair(oracle, name, 64, 16, 12, seed=5)
-    assert_same_run(g, o, rtol=1e-5, min_frac=0.9)
-    depth_proxy = g[2][:, -1] if name != "pumps_amwg_nuts" else g[2][:, -1]
-    assert depth_proxy.max() >= 4          # nalpha of the last doubling: trees deeper than one doubling were built
+def test_nuts_adaptive_steps_match_oracle(oracle, name):
+    # The oracle runs the reference's recursive buildtree (nuts.jl:139-180), the device the unrolled leaf-by-leaf form.  Every step of
+    # 30 adaptive (nutsepsilon at iteration 1, dual averaging) + 10 non-adaptive iterations of 32 chains, each from the oracle's state
+    eng, tune = resync(oracle, name, 32, 40, 30, seed=5, rtol=1e-7, tie=1e-7)
+    assert tune[:, -1].max() >= 4          # nalpha of the last doubling: trees deeper than one doubling were built
 
 
 @pytest.mark.parametrize("name,iters", [("line_nuts_slice", 100), ("line_nuts_all", 50), ("rats_nuts_slice", 40), ("pumps_amwg_nuts", 100)])
-def test_nuts_fixed_stepsize_trajectories_match_oracle(oracle, name, iters):
+def test_nuts_fixed_stepsize_steps_match_oracle(oracle, name, iters):
     # burnin = 0: model-based NUTS adapts only while iter <= burnin (nuts.jl:52), epsilon stays at nutsepsilon()
-    g, o = nuts_pair(oracle, name, 16, iters, 0, seed=6)
-    # long Hamiltonian trajectories in the (beta, log s2) funnel amplify rounding: allow a few chains to flip a decision
-    assert_same_run(g, o, rtol=1e-6, min_frac=0.75)
+    resync(oracle, name, 16, iters, 0, seed=6, rtol=1e-7, tie=1e-7)
 
 
 def test_seeds_fast_kernel_with_amm_block_matches_oracle_and_generic(oracle):
     # the reference's own seeds scheme (AMM + AMWG + AMWG, doc/examples/seeds.jl:69-71) through the fused kernel
     g, o, eng, _ = run_pair(oracle, "seeds_amm", 32, 300, 150, 3, force_generic=False)
-    assert_same_run(g, o, min_frac=0.9, tune_rtol=1e-4)
+    tied = assert_same_run(g, o, 300, 150, 3, tune_rtol=1e-4)
     tpl, blocks, inits = helpers.scheme("seeds_amm")
     e2 = Engine_(tpl, 32, blocks, inits, seed=99)
     out_gen = e2.run(300, burnin=150, thin=3, force_generic=True)
-    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
-    assert ok.mean() >= 0.9
+    assert_same_chains(g[0], out_gen, skip=tied, rtol=1e-8, atol=1e-10)
     # restart through the fused kernel
     e3 = Engine_(tpl, 8, blocks, inits, seed=5); full = e3.run(90, burnin=30, thin=3)
     e4 = Engine_(tpl, 8, blocks, inits, seed=5); a = e4.run(45, burnin=30, thin=3); b = e4.run(45, burnin=30, thin=3)
@@ -238,12 +229,11 @@ def test_seeds_fast_kernel_with_amm_block_matches_oracle_and_generic(oracle):
 # ---- fused pumps Slice kernel (mamba.jl_b200/csrc/pumps_fast.cu) ---------------------------------------------
 def test_pumps_fast_kernel_matches_oracle_generic_and_published_table(oracle):
     g, o, _, _ = run_pair(oracle, "pumps_slice", 32, 300, 100, 2, force_generic=False)
-    assert_same_run(g, o, min_frac=0.9)
+    tied = assert_same_run(g, o, 300, 100, 2)
     tpl, blocks, inits = helpers.scheme("pumps_slice")
     e2 = Engine_(tpl, 32, blocks, inits, seed=99)
     out_gen = e2.run(300, burnin=100, thin=2, force_generic=True)
-    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
-    assert ok.mean() >= 0.9
+    assert_same_chains(g[0], out_gen, skip=tied, rtol=1e-8, atol=1e-10)
     from mambacuda.engine import Engine
     eng = Engine(tpl, 2048, seed=8); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
     eng.run(3000, burnin=1500, thin=1, store=False, out=False)
@@ -255,12 +245,11 @@ def test_pumps_fast_kernel_matches_oracle_generic_and_published_table(oracle):
 # ---- fused rats Slice + AMWG kernel (mamba.jl_b200/csrc/rats_fast.cu) -------------------------------------
 def test_rats_fast_kernel_trajectories_match_oracle_and_generic(oracle):
     g, o, eng, _ = run_pair(oracle, "rats_slice_amwg", 32, 200, 100, 2, force_generic=False)
-    assert_same_run(g, o, min_frac=0.9)
+    tied = assert_same_run(g, o, 200, 100, 2)
     tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
     eng2 = Engine_(tpl, 32, blocks, inits, seed=99)
     out_gen = eng2.run(200, burnin=100, thin=2, force_generic=True)
-    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-8, atol=1e-10) for c in range(32)])
-    assert ok.mean() >= 0.9
+    assert_same_chains(g[0], out_gen, skip=tied, rtol=1e-8, atol=1e-10)
 
 
 def test_rats_fast_kernel_restart_and_posterior(oracle):
@@ -285,28 +274,34 @@ def Engine_(tpl, n, blocks, inits, seed):
 
 
 # ---- warp-per-chain rats kernel (mamba.jl_b200/csrc/rats_warp.cu) ------------------------------------------
-@pytest.mark.parametrize("iters,burnin,min_frac", [(16, 12, 0.9), (40, 0, 0.75)])
-def test_rats_warp_kernel_trajectories_match_oracle(oracle, iters, burnin, min_frac):
+@pytest.mark.parametrize("iters,burnin", [(40, 30), (40, 0)])
+def test_rats_warp_kernel_steps_match_oracle(oracle, iters, burnin):
     # the same draws in the same order as the reference's recursion: adaptive (dual averaging + nutsepsilon) and fixed step size
-    g, o = nuts_pair(oracle, "rats_nuts_slice", 64, iters, burnin, seed=5, force_generic=False)
-    assert_same_run(g, o, rtol=1e-5, min_frac=min_frac)
-    assert g[2][:, -1].max() >= 4
+    eng, tune = resync(oracle, "rats_nuts_slice", 64, iters, burnin, seed=5, rtol=1e-7, tie=1e-7, force_generic=False)
+    assert tune[:, -1].max() >= 4
 
 
 def test_rats_warp_kernel_matches_generic_kernel_and_restarts(oracle):
+    # warp-per-chain kernel against the one-chain-per-thread kernel, step by step from common states (the two evaluate the same
+    # leapfrogs in a different floating-point order), and mcmc(mc, iters) restart (mcmc.jl:3-16) through the warp kernel
     from mambacuda.engine import Engine
     tpl, blocks, inits = helpers.scheme("rats_nuts_slice")
-    outs = []
-    for generic in (True, False):
-        eng = Engine(tpl, 96, seed=21)
-        eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
-        if generic:
-            outs.append(eng.run(30, burnin=10, thin=2, force_generic=True))
-        else:   # 12 + 18 iterations in two calls = mcmc(mc, iters) restart (mcmc.jl:3-16) through the warp kernel
-            a = eng.run(12, burnin=10, thin=2); b = eng.run(18, burnin=10, thin=2)
-            outs.append(np.concatenate([a, b], axis=0))
-    ok = np.array([np.allclose(outs[0][:, :, c], outs[1][:, :, c], rtol=1e-5, atol=1e-9) for c in range(96)])
-    assert ok.mean() >= 0.85, f"{ok.sum()}/96 chains agree between the warp kernel and the generic kernel"
+    a = Engine(tpl, 96, seed=21); a.set_scheme(blocks); a.set_inits(inits, jitter_sd=0.05)
+    b = Engine(tpl, 96, seed=21); b.set_scheme(blocks); b.set_inits(inits, jitter_sd=0.05)
+    n_diff = 0
+    for i in range(1, 31):
+        a.run(1, burnin=10, thin=1, store=False, out=False, partial=True, force_generic=True)
+        b.run(1, burnin=10, thin=1, store=False, out=False, partial=True)
+        sa, ta, _ = a.get_state(); sb, tb, _ = b.get_state()
+        same = np.array([np.allclose(sa[c], sb[c], rtol=1e-7, atol=1e-9) for c in range(96)])
+        n_diff += int((~same).sum())
+        b.set_state(sa, ta, i)           # both continue from the generic kernel's state
+    assert n_diff <= 3, f"{n_diff} of 2,880 single steps differ between the warp kernel and the generic kernel"
+    e1 = Engine(tpl, 64, seed=22); e1.set_scheme(blocks); e1.set_inits(inits, jitter_sd=0.05)
+    full = e1.run(30, burnin=10, thin=2)
+    e2 = Engine(tpl, 64, seed=22); e2.set_scheme(blocks); e2.set_inits(inits, jitter_sd=0.05)
+    p1 = e2.run(12, burnin=10, thin=2); p2 = e2.run(18, burnin=10, thin=2)
+    np.testing.assert_array_equal(np.concatenate([p1, p2], axis=0), full)
 
 
 def test_rats_warp_kernel_posterior_matches_published_table(oracle):
@@ -512,12 +507,11 @@ def test_pumps_gibbs_kernel_matches_oracle_and_generic_and_restarts(oracle):
     # fused [Gibbs(theta), Gibbs(beta), AMWG(alpha)] kernel (pumps_fast.cu): the Gibbs draws are the generic kernel's bit for bit, the AMWG
     # target is evaluated on sufficient statistics
     g, o, eng, _ = run_pair(oracle, "pumps_gibbs_amwg", 64, 300, 100, 2, force_generic=False)
-    assert_same_run(g, o, min_frac=0.9)
+    tied = assert_same_run(g, o, 300, 100, 2)
     tpl, blocks, inits = helpers.scheme("pumps_gibbs_amwg")
     gen = Engine_(tpl, 64, blocks, inits, seed=99)
     out_gen = gen.run(300, burnin=100, thin=2, force_generic=True)
-    ok = np.array([np.allclose(g[0][:, :, c], out_gen[:, :, c], rtol=1e-9, atol=1e-12) for c in range(64)])
-    assert ok.mean() >= 0.9
+    assert_same_chains(g[0], out_gen, skip=tied)
     two = Engine_(tpl, 64, blocks, inits, seed=99)        # mcmc(mc, iters): 130 + 170 iterations in two calls
     a = two.run(130, burnin=100, thin=2); b = two.run(170, burnin=100, thin=2)
     np.testing.assert_array_equal(np.concatenate([a, b], axis=0), g[0])
@@ -560,8 +554,8 @@ def test_external_stream_matches_oracle(oracle):
     eng.set_inits(inits)
     out_g = eng.run(200, burnin=50, thin=1, force_generic=True)
     st_g, tune_g, _ = eng.get_state()
-    out_o, st_o, tune_o = orc.run(8, inits, 200, burnin=50, thin=1, ext_u=u)
-    assert_same_run((out_g, st_g, tune_g), (out_o, st_o, tune_o))
+    out_o, st_o, tune_o, marg = orc.run(8, inits, 200, burnin=50, thin=1, ext_u=u, margins=True)
+    assert_same_run((out_g, st_g, tune_g), (out_o, st_o, tune_o, marg), 200, 50, 1)
 
 
 def test_restart_continues_the_chain(oracle):
@@ -641,11 +635,13 @@ def test_error_codes(oracle):
 def test_seeds_fast_matches_oracle_and_generic(oracle):
     # dispatch happens inside mcu_run when the scheme is [AMWG(alphas), AMWG(b), AMWG(s2)] on the seeds template
     g, o, eng, _ = run_pair(oracle, "seeds_amwg", 64, 400, 200, 4, seed=21, force_generic=False)
-    assert_same_run(g, o, rtol=1e-8, min_frac=0.95)
+    tied = assert_same_run(g, o, 400, 200, 4)
     assert (g[2][:, 0] == 400).all() and (o[2][:, 0] == 400).all()           # m of block 0 (adapt=:all)
-    np.testing.assert_array_equal(g[2][:, 6:10], o[2][:, 6:10])              # alpha accept counters are integers
-    g2, _, _, _ = run_pair(oracle, "seeds_amwg", 64, 400, 200, 4, seed=21, force_generic=True)
-    np.testing.assert_allclose(g[0], g2[0], rtol=1e-9, atol=1e-12)
+    keep = [c for c in range(64) if c not in tied]
+    np.testing.assert_array_equal(g[2][keep, 6:10], o[2][keep, 6:10])        # alpha accept counters are integers
+    g2, o2, _, _ = run_pair(oracle, "seeds_amwg", 64, 400, 200, 4, seed=21, force_generic=True)
+    tied2 = assert_same_run(g2, o2, 400, 200, 4)
+    assert_same_chains(g[0], g2[0], skip=set(tied) | set(tied2))
 
 
 def test_seeds_fast_burnin_adaptation_and_restart(oracle):
@@ -659,10 +655,9 @@ def test_seeds_fast_burnin_adaptation_and_restart(oracle):
     assert p1.shape[0] == 3
     np.testing.assert_array_equal(np.concatenate([p1, p2], axis=0), full)
     orc = oracle.Oracle(tpl); orc.set_scheme([helpers.oracle_block(x) for x in blocks])
-    out_o, st_o, tune_o = orc.run(32, inits, 300, burnin=120, thin=3, seed=9, jitter_sd=0.1, nthreads=4)
+    out_o, st_o, tune_o, marg = orc.run(32, inits, 300, burnin=120, thin=3, seed=9, jitter_sd=0.1, nthreads=4, margins=True)
     st, tune, _ = a.get_state()
-    ok = [np.allclose(full[:, :, c], out_o[:, :, c], rtol=1e-8) and np.allclose(tune[c], tune_o[c], rtol=1e-7) for c in range(32)]
-    assert np.mean(ok) >= 0.95
+    assert_same_run((full, st, tune), (out_o, st_o, tune_o, marg), 300, 120, 3)
     assert (tune[:, 0] == 120).all() and (tune[:, 1] == 0).all()             # adaptation stopped after burn-in
 
 
@@ -700,29 +695,28 @@ def glm_pair(oracle, N, d, n_chains, seed):
     return eng, orc, inits
 
 
+def glm_resync(oracle, N, d, n_chains, seed, iters, burnin, run_kw):
+    eng, orc, inits = glm_pair(oracle, N, d, n_chains, seed)
+    compared, ties = helpers.resync_audit(eng, orc, np.arange(n_chains), inits, iters, burnin, seed, 0.0, 1e-7, 1e-7, run_kw=run_kw, nthreads=4)
+    assert len(ties) <= max(1, compared // 200), ties
+    return eng
+
+
 def test_glm_tick_engine_matches_generic_kernel_and_oracle(oracle):
     # every chain is a resumable state machine fed by a shared gradient pass; it must request exactly the
-    # gradients the reference's recursion does (same draws, same post-order merges, same dual averaging)
-    eng, orc, inits = glm_pair(oracle, 400, 8, 32, seed=13)
-    eng.set_inits(inits)
-    out_t = eng.run(16, burnin=12, thin=1, glm_reference=True)   # tick engine, FP64 gradient kernel
-    st_t, tune_t, _ = eng.get_state()
-    eng.set_inits(inits)
-    out_g = eng.run(16, burnin=12, thin=1, force_generic=True)   # one chain per thread
-    st_g, tune_g, _ = eng.get_state()
-    out_o, st_o, tune_o = orc.run(32, inits, 16, burnin=12, thin=1, seed=13, nthreads=4)
-    assert_same_run((out_t, st_t, tune_t), (out_g, st_g, tune_g), rtol=1e-6, min_frac=0.9)
-    assert_same_run((out_t, st_t, tune_t), (out_o, st_o, tune_o), rtol=1e-5, min_frac=0.9)
-    assert tune_t[:, 7].max() >= 4                               # trees deeper than one doubling
+    # gradients the reference's recursion does (same draws, same post-order merges, same dual averaging):
+    # every step of 20 adaptive + 8 non-adaptive iterations from the oracle's state, tick engine (FP64 gradient kernel) and generic kernel
+    eng = glm_resync(oracle, 400, 8, 32, 13, 28, 20, dict(glm_reference=True))
+    _, tune, _ = eng.get_state()
+    assert tune[:, 7].max() >= 4                                 # trees deeper than one doubling
+    glm_resync(oracle, 400, 8, 32, 13, 28, 20, dict(force_generic=True))
 
 
 def test_glm_tick_engine_fixed_stepsize_and_restart(oracle):
+    glm_resync(oracle, 300, 6, 16, 17, 40, 0, dict(glm_reference=True))
     eng, orc, inits = glm_pair(oracle, 300, 6, 16, seed=17)
     eng.set_inits(inits)
     full = eng.run(40, burnin=0, thin=2, glm_reference=True)
-    out_o, st_o, tune_o = orc.run(16, inits, 40, burnin=0, thin=2, seed=17, nthreads=4)
-    st, tune, _ = eng.get_state()
-    assert_same_run((full, st, tune), (out_o, st_o, tune_o), rtol=1e-6, min_frac=0.85)
     eng.set_inits(inits)
     p1 = eng.run(14, burnin=0, thin=2, glm_reference=True); p2 = eng.run(26, burnin=0, thin=2, glm_reference=True)
     np.testing.assert_allclose(np.concatenate([p1, p2], axis=0), full, rtol=1e-12)
