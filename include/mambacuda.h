@@ -60,7 +60,9 @@ enum {
   MCU_TPL_EQUIV = 8,     /* doc/examples/equiv.jl:25-75    nodes: s2_2, s2_1, pi, phi, mu, delta[10x2]; monitored s2_2, s2_1, pi, phi, theta, equiv, mu */
   MCU_TPL_BLOCKER = 9,   /* doc/examples/blocker.jl:22-69  nodes: s2, d, delta_new, mu[22], delta[22]; two observed nodes rc, rt; monitored s2, d, delta_new */
   MCU_TPL_STACKS = 10,   /* doc/examples/stacks.jl:41-94   nodes: beta0, beta[3], s2; Laplace likelihood; monitored (all Logical) b[3], b0, sigma, outlier[1,3,4,21] */
-  MCU_N_TEMPLATES = 11
+  MCU_TPL_MAGNESIUM = 11, /* doc/examples/magnesium.jl:21-82 nodes: priors[6], mu[6], theta[6x8], pc[6x8]; bounded (Uniform / truncated) priors: mu is sampled on
+                             the two-sided link logit((x-a)/(b-a)) (src/distributions/transformdistribution.jl:6-48); monitored (Logical) tau[6], OR[6] */
+  MCU_N_TEMPLATES = 12
 };
 
 /* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */

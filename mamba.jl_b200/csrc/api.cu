@@ -42,6 +42,7 @@ struct mcu_ctx {
   int D = 0, P = 0, NN = 0, glm_d = 0;
   std::vector<int> elink_state;   // link code per state element
   int* d_elink_state = nullptr;
+  double* d_ebound_state = nullptr;   // (lo, hi) per state element (LINK_BOUNDED elements)
   // scheme
   std::vector<DevBlock> h_blocks;
   DevBlock* d_blocks = nullptr;
@@ -177,6 +178,12 @@ void default_inputs(mcu_ctx* h) {
       in["x"] = {80, 27, 89, 80, 27, 88, 75, 25, 90, 62, 24, 87, 62, 22, 87, 62, 23, 87, 62, 24, 93, 62, 24, 93, 58, 23, 87, 58, 18, 80, 58, 18, 89,
                  58, 17, 88, 58, 18, 82, 58, 19, 93, 50, 18, 89, 50, 18, 86, 50, 19, 72, 50, 19, 79, 50, 20, 80, 56, 20, 82, 70, 20, 91};
       break;
+    case MCU_TPL_MAGNESIUM:  // doc/examples/magnesium.jl:4-9
+      in["rt"] = {1, 9, 2, 1, 10, 1, 1, 90};
+      in["nt"] = {40, 135, 200, 48, 150, 59, 25, 1159};
+      in["rc"] = {2, 23, 7, 1, 8, 9, 3, 118};
+      in["nc"] = {36, 135, 200, 46, 148, 56, 23, 1157};
+      break;
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -209,7 +216,7 @@ int upload_inputs(mcu_ctx* h) {
     for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) z[i * 3 + j] = (x[i * 3 + j] - mean[j]) / sd[j];
     in["meanx"] = mean; in["sdx"] = sd; in["z"] = z;
   }
-  if (h->tpl == MCU_TPL_BLOCKER) { in["lcc"] = lchoose_vec(in["nc"], in["rc"]); in["lct"] = lchoose_vec(in["nt"], in["rt"]); }
+  if (h->tpl == MCU_TPL_BLOCKER || h->tpl == MCU_TPL_MAGNESIUM) { in["lcc"] = lchoose_vec(in["nc"], in["rc"]); in["lct"] = lchoose_vec(in["nt"], in["rt"]); }
   if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
     if (kv.second.empty()) continue;
@@ -258,6 +265,16 @@ template <> struct Host<BlockerModel> {
     return {h->d_inputs["rc"], h->d_inputs["nc"], h->d_inputs["rt"], h->d_inputs["nt"], h->d_inputs["lcc"], h->d_inputs["lct"], (int)h->inputs["rc"].size()};
   }
 };
+template <> struct Host<MagnesiumModel> {
+  static MagnesiumModel::Data data(mcu_ctx* h) {
+    // s2 = 1 / (rt + 0.5) + 1 / (nt - rt + 0.5) + 1 / (rc + 0.5) + 1 / (nc - rc + 0.5), s2_0 = 1 / mean(1 / s2): magnesium.jl:13-17
+    const auto &rt = h->inputs["rt"], &nt = h->inputs["nt"], &rc = h->inputs["rc"], &nc = h->inputs["nc"];
+    double sinv = 0.0;
+    for (size_t j = 0; j < rt.size(); ++j) sinv += 1.0 / (1.0 / (rt[j] + 0.5) + 1.0 / (nt[j] - rt[j] + 0.5) + 1.0 / (rc[j] + 0.5) + 1.0 / (nc[j] - rc[j] + 0.5));
+    const double s2_0 = 1.0 / (sinv / (double)rt.size());
+    return {h->d_inputs["rc"], h->d_inputs["nc"], h->d_inputs["rt"], h->d_inputs["nt"], h->d_inputs["lcc"], h->d_inputs["lct"], s2_0, std::sqrt(s2_0 / std::erf(0.75))};
+  }
+};
 template <> struct Host<StacksModel> {
   static StacksModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["z"], h->d_inputs["meanx"], h->d_inputs["sdx"], (int)h->inputs["y"].size()}; }
 };
@@ -286,15 +303,25 @@ template <> struct Host<GlmM> {
     case MCU_TPL_BLOCKER: { typedef BlockerModel M; BODY; break; }                 \
     case MCU_TPL_STACKS: { typedef StacksModel M; BODY; break; }                   \
     case MCU_TPL_EQUIV: { typedef EquivModel M; BODY; break; }                     \
+    case MCU_TPL_MAGNESIUM: { typedef MagnesiumModel M; BODY; break; }             \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
 
-struct TplInfo { int D, P, NN; std::vector<int> off, len, link, monlink; std::vector<std::string> node_names; };
+struct TplInfo {
+  int D, P, NN; std::vector<int> off, len, link, monlink; std::vector<std::string> node_names;
+  std::vector<int> elink;        // link code of every state element (the node's, unless the node is an array of different distributions)
+  std::vector<double> ebound;    // (lo, hi) of every state element; read for LINK_BOUNDED elements only
+};
 
 template <class M> TplInfo tpl_info_fixed() {
   TplInfo t; t.D = M::D; t.P = M::P; t.NN = M::NN;
   for (int n = 0; n < M::NN; ++n) { t.off.push_back(M::node_off(n)); t.len.push_back(M::node_len(n)); t.link.push_back(M::node_link(n)); t.node_names.push_back(M::node_name(n)); }
   for (int j = 0; j < M::P; ++j) t.monlink.push_back(M::mon_link(j));
+  t.elink.assign(M::D, LINK_IDENT); t.ebound.assign(2 * (size_t)M::D, 0.0);
+  for (int n = 0; n < M::NN; ++n) for (int e = M::node_off(n); e < M::node_off(n) + M::node_len(n); ++e) {
+    t.elink[e] = M::elem_link(e, M::node_link(n));
+    M::elem_bounds(e, t.ebound[2 * e], t.ebound[2 * e + 1]);
+  }
   return t;
 }
 TplInfo tpl_info(const mcu_ctx* h) {
@@ -309,10 +336,12 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_BLOCKER: return tpl_info_fixed<BlockerModel>();
     case MCU_TPL_STACKS: return tpl_info_fixed<StacksModel>();
     case MCU_TPL_EQUIV: return tpl_info_fixed<EquivModel>();
+    case MCU_TPL_MAGNESIUM: return tpl_info_fixed<MagnesiumModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
       t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
       t.monlink.assign(h->glm_d, LINK_IDENT);
+      t.elink.assign(h->glm_d, LINK_IDENT); t.ebound.assign(2 * (size_t)h->glm_d, 0.0);
       return t;
     }
   }
@@ -335,6 +364,7 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_BLOCKER: return BlockerModel::monitor_names();
       case MCU_TPL_STACKS: return StacksModel::monitor_names();
       case MCU_TPL_EQUIV: return EquivModel::monitor_names();
+      case MCU_TPL_MAGNESIUM: return MagnesiumModel::monitor_names();
       default: break;
     }
   }
@@ -620,7 +650,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
-  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->d_diag); cudaFree(h->r_scratch); free_glm_data(h);
+  cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ebound_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->d_diag); cudaFree(h->r_scratch); free_glm_data(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
   return MCU_OK;
@@ -643,6 +673,7 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_DYES && n != 30) return fail(h, MCU_ERR_DIM, "dyes inputs have 30 entries");
     if (h->tpl == MCU_TPL_STACKS && n != (nm == "x" ? 63u : 21u)) return fail(h, MCU_ERR_DIM, "stacks inputs: y has 21 entries, x 21 x 3");
     if (h->tpl == MCU_TPL_BLOCKER && n != (size_t)BlockerModel::NT) return fail(h, MCU_ERR_DIM, "blocker inputs have 22 entries");
+    if (h->tpl == MCU_TPL_MAGNESIUM && n != (size_t)MagnesiumModel::NTR) return fail(h, MCU_ERR_DIM, "magnesium inputs have 8 entries");
     if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
     if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
@@ -710,13 +741,17 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
     b.proposal = d.proposal; b.L = d.L; b.grad = d.grad; b.max_depth = d.max_depth;
     b.target = d.target > 0 ? d.target : (d.kind == MCU_NUTS ? 0.6 : 0.44);
     b.epsilon = d.epsilon; b.beta = d.beta > 0 ? d.beta : 0.05; b.amm_scale = d.amm_scale > 0 ? d.amm_scale : 2.38;
-    std::vector<int> elem, elink;
+    std::vector<int> elem, elink; std::vector<double> ebound; bool any_bounded = false;
     for (int i = 0; i < d.n_nodes; ++i) {
       const int n = d.nodes[i];
       if (n < 0 || n >= t.NN) return fail(h, MCU_ERR_ARG, "node id out of range");
       if (b.mask & (1u << n)) return fail(h, MCU_ERR_ARG, "node listed twice in a block");
       b.mask |= 1u << n; b.own[i] = n;
-      for (int e = 0; e < t.len[n]; ++e) { elem.push_back(t.off[n] + e); elink.push_back(t.link[n]); }
+      for (int e = 0; e < t.len[n]; ++e) {
+        const int se = t.off[n] + e;
+        elem.push_back(se); elink.push_back(t.elink[se]); ebound.push_back(t.ebound[2 * se]); ebound.push_back(t.ebound[2 * se + 1]);
+        any_bounded = any_bounded || t.elink[se] == LINK_BOUNDED;
+      }
     }
     b.n_own = d.n_nodes; b.k = (int)elem.size();
     const int k = b.k;
@@ -744,9 +779,11 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
     CK(cudaMalloc(&dl, sizeof(int) * k)); h->scheme_allocs.push_back(dl);
     CK(cudaMemcpy(de, elem.data(), sizeof(int) * k, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dl, elink.data(), sizeof(int) * k, cudaMemcpyHostToDevice));
+    double* db = nullptr;
+    if (any_bounded) { CK(cudaMalloc(&db, sizeof(double) * 2 * k)); h->scheme_allocs.push_back(db); CK(cudaMemcpy(db, ebound.data(), sizeof(double) * 2 * k, cudaMemcpyHostToDevice)); }
     if (!sc.empty()) { CK(cudaMalloc(&ds, sizeof(double) * k)); h->scheme_allocs.push_back(ds); CK(cudaMemcpy(ds, sc.data(), sizeof(double) * k, cudaMemcpyHostToDevice)); }
     if (!SL.empty()) { CK(cudaMalloc(&dS, sizeof(double) * k * k)); h->scheme_allocs.push_back(dS); CK(cudaMemcpy(dS, SL.data(), sizeof(double) * k * k, cudaMemcpyHostToDevice)); }
-    b.elem = de; b.elink = dl; b.scale = ds; b.SigmaL = dS;
+    b.elem = de; b.elink = dl; b.ebound = db; b.scale = ds; b.SigmaL = dS;
     h_scales.push_back(sc);
     h_SigmaL.push_back(SL);
     b.tune_off = (int)toff;
@@ -763,11 +800,12 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   CK(cudaMalloc(&h->d_blocks, sizeof(DevBlock) * hb.size()));
   CK(cudaMemcpy(h->d_blocks, hb.data(), sizeof(DevBlock) * hb.size(), cudaMemcpyHostToDevice));
   // link code of every state element (for init jitter)
-  h->elink_state.assign(h->D, LINK_IDENT);
-  for (int n = 0; n < t.NN; ++n) for (int e = 0; e < t.len[n]; ++e) h->elink_state[t.off[n] + e] = t.link[n];
-  cudaFree(h->d_elink_state); h->d_elink_state = nullptr;
+  h->elink_state = t.elink;
+  cudaFree(h->d_elink_state); h->d_elink_state = nullptr; cudaFree(h->d_ebound_state); h->d_ebound_state = nullptr;
   CK(cudaMalloc(&h->d_elink_state, sizeof(int) * h->D));
   CK(cudaMemcpy(h->d_elink_state, h->elink_state.data(), sizeof(int) * h->D, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_ebound_state, sizeof(double) * 2 * h->D));
+  CK(cudaMemcpy(h->d_ebound_state, t.ebound.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice));
   h->h_scales = h_scales; h->h_SigmaL = h_SigmaL;
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
   h->rats_warp_ok = scheme_is_rats_warp(h);
@@ -787,7 +825,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   double* d_in = nullptr;
   rc = stage(h, sizeof(double) * (size_t)n_inits * h->D, (void**)&d_in); if (rc) return rc;
   CK(cudaMemcpyAsync(d_in, x, sizeof(double) * (size_t)n_inits * h->D, cudaMemcpyHostToDevice, h->stream));
-  launch_init(h->C, h->chain_offset, h->seed, h->D, d_in, n_inits, h->d_elink_state, jitter_sd, h->d_state, h->stream);
+  launch_init(h->C, h->chain_offset, h->seed, h->D, d_in, n_inits, h->d_elink_state, h->d_ebound_state, jitter_sd, h->d_state, h->stream);
   h->launches++;
   const size_t C = (size_t)h->C;
   CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size), h->stream));

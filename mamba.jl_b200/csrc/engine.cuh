@@ -27,12 +27,24 @@ struct BlockTarget {
   double* s;
   const DevBlock& b;
 
-  MCU_D void relist(const double* x) const {
-    for (int i = 0; i < b.k; ++i) s[b.elem[i]] = (b.transform && b.elink[i] == LINK_LOG) ? exp(x[i]) : x[i];
+  // invlink / link of block element i (transformdistribution.jl:6-32): identity, exp / log, or the two-sided (b - a) invlogit(x) + a /
+  // logit((v - a) / (b - a)) with invlogit, logit as in src/utils.jl:64-68
+  MCU_D double inv(int i, double x) const {
+    if (!b.transform) return x;
+    const int lk = b.elink[i];
+    if (lk == LINK_LOG) return exp(x);
+    if (lk == LINK_BOUNDED) { const double lo = b.ebound[2 * i], hi = b.ebound[2 * i + 1]; return (hi - lo) * (1.0 / (exp(-x) + 1.0)) + lo; }
+    return x;
   }
-  MCU_D void unlist(double* x) const {
-    for (int i = 0; i < b.k; ++i) { const double v = s[b.elem[i]]; x[i] = (b.transform && b.elink[i] == LINK_LOG) ? log(v) : v; }
+  MCU_D double fwd(int i, double v) const {
+    if (!b.transform) return v;
+    const int lk = b.elink[i];
+    if (lk == LINK_LOG) return log(v);
+    if (lk == LINK_BOUNDED) { const double lo = b.ebound[2 * i], hi = b.ebound[2 * i + 1]; const double p = (v - lo) / (hi - lo); return log(p / (1.0 - p)); }
+    return v;
   }
+  MCU_D void relist(const double* x) const { for (int i = 0; i < b.k; ++i) s[b.elem[i]] = inv(i, x[i]); }
+  MCU_D void unlist(double* x) const { for (int i = 0; i < b.k; ++i) x[i] = fwd(i, s[b.elem[i]]); }
   MCU_NOINL double eval() const {
     double lp = 0.0;
     const bool tr = b.transform != 0;
@@ -51,7 +63,6 @@ struct BlockTarget {
     return lp;
   }
   MCU_D double logf(const double* x) const { relist(x); return eval(); }
-  MCU_D double inv(int i, double x) const { return (b.transform && b.elink[i] == LINK_LOG) ? exp(x) : x; }
   MCU_D void put(int i, double x) const { s[b.elem[i]] = inv(i, x); }
   // logpdf!(block, v) when v differs in component i only from the vector evaluated last (whose value is `cur` and which the state record
   // still holds).  Where the template marks the element as local, only the terms that read it are re-evaluated:
@@ -72,9 +83,14 @@ struct BlockTarget {
     relist(x);
     double gj[M::D];
     M::joint_grad(d, s, gj);
-    for (int i = 0; i < b.k; ++i) {
+    for (int i = 0; i < b.k; ++i) {   // theta = invlink(x): d/dx [lp(theta) + log |dtheta/dx|] = dlp/dtheta * dtheta/dx + d(log-Jacobian)/dx
       const int e = b.elem[i];
-      g[i] = (b.transform && b.elink[i] == LINK_LOG) ? gj[e] * s[e] + 1.0 : gj[e];
+      const int lk = b.transform ? b.elink[i] : LINK_IDENT;
+      if (lk == LINK_LOG) g[i] = gj[e] * s[e] + 1.0;
+      else if (lk == LINK_BOUNDED) {
+        const double lo = b.ebound[2 * i], hi = b.ebound[2 * i + 1];
+        g[i] = gj[e] * ((s[e] - lo) * (hi - s[e]) / (hi - lo)) + ((hi - s[e]) - (s[e] - lo)) / (hi - lo);
+      } else g[i] = gj[e];
     }
   }
   // Calculus.gradient(f, x, :forward / :central): src/model/simulation.jl:47-51

@@ -5,7 +5,7 @@ namespace mcu {
 
 // setinits! for all chains: state[e][c] = inits[(g % n_inits)][e] (+ jitter on the link scale).
 __global__ void init_kernel(long long n_chains, long long chain_offset, unsigned long long seed, int D,
-                            const double* inits, long long n_inits, const int* elink, double jitter_sd, double* state) {
+                            const double* inits, long long n_inits, const int* elink, const double* ebound, double jitter_sd, double* state) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chains) return;
   const long long gidx = chain_offset + c;
@@ -17,7 +17,11 @@ __global__ void init_kernel(long long n_chains, long long chain_offset, unsigned
     double v = rec[e];
     if (jitter_sd > 0.0) {
       const double z = jitter_sd * rng.normal();
-      v = elink[e] == LINK_LOG ? exp(log(v) + z) : v + z;
+      if (elink[e] == LINK_LOG) v = exp(log(v) + z);
+      else if (elink[e] == LINK_BOUNDED) {   // jitter on the two-sided link scale: transformdistribution.jl:9-10, 24-25
+        const double lo = ebound[2 * e], hi = ebound[2 * e + 1], p = (v - lo) / (hi - lo);
+        v = (hi - lo) * (1.0 / (exp(-(log(p / (1.0 - p)) + z)) + 1.0)) + lo;
+      } else v = v + z;
     }
     state[(size_t)e * n_chains + c] = v;
   }
@@ -158,8 +162,8 @@ double measure_fp64_peak_tflops(cudaStream_t st) {
 static inline unsigned gridf(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 void launch_init(long long n_chains, long long chain_offset, unsigned long long seed, int D, const double* inits,
-                 long long n_inits, const int* elink, double jitter_sd, double* state, cudaStream_t st) {
-  init_kernel<<<gridf(n_chains, 256), 256, 0, st>>>(n_chains, chain_offset, seed, D, inits, n_inits, elink, jitter_sd, state);
+                 long long n_inits, const int* elink, const double* ebound, double jitter_sd, double* state, cudaStream_t st) {
+  init_kernel<<<gridf(n_chains, 256), 256, 0, st>>>(n_chains, chain_offset, seed, D, inits, n_inits, elink, ebound, jitter_sd, state);
 }
 void launch_soa_to_records(const double* soa, double* rec, long long C, int rows, cudaStream_t st) {
   soa_to_records<<<gridf(C, 256), 256, 0, st>>>(soa, rec, C, rows);

@@ -28,6 +28,7 @@ MCU_DECLARE_TPL(SalmModel)
 MCU_DECLARE_TPL(EquivModel)
 MCU_DECLARE_TPL(BlockerModel)
 MCU_DECLARE_TPL(StacksModel)
+MCU_DECLARE_TPL(MagnesiumModel)
 
 // fewer chains than one wave at the default occupancy (148 SMs x 4 blocks x 128 threads): the low-latency instantiation
 #ifdef MCU_GENERIC_MINB
@@ -58,7 +59,7 @@ MCU_DECLARE_TPL(StacksModel)
 
 // misc kernels (kern_misc.cu)
 void launch_init(long long n_chains, long long chain_offset, unsigned long long seed, int D, const double* inits,
-                 long long n_inits, const int* elink, double jitter_sd, double* state, cudaStream_t st);
+                 long long n_inits, const int* elink, const double* ebound, double jitter_sd, double* state, cudaStream_t st);
 void launch_soa_to_records(const double* soa, double* rec, long long C, int rows, cudaStream_t st);
 void launch_records_to_soa(const double* rec, double* soa, long long C, int rows, cudaStream_t st);
 void launch_samples_to_julia(const double* smp, double* out, long long kept, int P, long long C, cudaStream_t st);

@@ -35,7 +35,10 @@ namespace mcu {
 #define MCU_NOINL __device__ __noinline__
 
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
-constexpr int LINK_IDENT = 0, LINK_LOG = 1, LINK_HEUR = -1;
+// link codes of a state element (src/distributions/transformdistribution.jl): identity (:53-61), log (lower bound 0: :66-78),
+// two-sided logit((x - a) / (b - a)) with log-Jacobian log((x - a)(b - x) / (b - a)) (:6-48; the unit interval of :83-93 is (a, b) = (0, 1));
+// LINK_HEUR marks a monitored Logical column whose link(c) is data-dependent (src/output/chains.jl:237-246)
+constexpr int LINK_IDENT = 0, LINK_LOG = 1, LINK_BOUNDED = 2, LINK_HEUR = -1;
 constexpr int OUT_NORMAL = 0, OUT_BINOMIAL = 1, OUT_POISSON = 2, OUT_BERNOULLI = 3, OUT_LAPLACE = 4;
 
 MCU_D double neg_inf() { return -CUDART_INF; }
@@ -121,8 +124,32 @@ MCU_D double digamma_d(double x) {
 // c0 of InverseGamma(0.001, 0.001): 0.001*flog(0.001) - lgamma(0.001)
 MCU_D double ig001_c0() { return 0.001 * flog(0.001) - lgamma(0.001); }
 
+// Defaults every template inherits: an element takes its node's link (arrays of different distributions override elem_link), bounded
+// links take their interval from elem_bounds.
+struct TplBase {
+  MCU_HD static int elem_link(int /*e*/, int node_link) { return node_link; }
+  MCU_HD static void elem_bounds(int /*e*/, double& lo, double& hi) { lo = 0.0; hi = 1.0; }
+};
+// Uniform(a, b) (Distributions.jl: -log(b - a) on [a, b]) with the two-sided link's log-Jacobian when the block samples on the link scale
+MCU_D double lp_uniform(double x, double a, double b, bool transform) {
+  if (!(x >= a && x <= b)) return neg_inf();
+  double lp = -flog(b - a);
+  if (transform) lp += flog((x - a) * (b - x) / (b - a));      // transformdistribution.jl:39-40
+  return lp;
+}
+// Binomial(n, p) at integer r, lc = lchoose(n, r) precomputed on the host (closed form of dbinom, as lp_binomial_logit)
+MCU_D double lp_binomial_p(double r, double n, double lc, double p) {
+  const double q = 1.0 - p;
+  if (p == 0.0) return r == 0.0 ? 0.0 : neg_inf();
+  if (q == 0.0) return r == n ? 0.0 : neg_inf();
+  double lp = lc;
+  if (r > 0.0) lp += r * flog(p);
+  if (n - r > 0.0) lp += (n - r) * flog(q);
+  return lp;
+}
+
 // =============================================================================== line
-struct LineModel {
+struct LineModel : TplBase {
   static constexpr int D = 3, NN = 2, NF = 3, P = 3, MAXN = 64;
   struct Data { const double* x; const double* y; int N; };
   MCU_HD static int node_off(int n) { return n == 0 ? 0 : 2; }
@@ -190,7 +217,7 @@ struct LineModel {
 };
 
 // =============================================================================== seeds
-struct SeedsModel {
+struct SeedsModel : TplBase {
   static constexpr int D = 26, NN = 6, NF = 7, P = 5, NP = 21;
   struct Data { const double* r; const double* n; const double* x1; const double* x2; const double* lc; int N; };
   MCU_HD static int node_off(int n) { return n <= 4 ? n : 5; }
@@ -250,7 +277,7 @@ struct SeedsModel {
 };
 
 // =============================================================================== rats
-struct RatsModel {
+struct RatsModel : TplBase {
   // state: mu_alpha, mu_beta, s2_alpha, s2_beta, s2_c, alpha[30], beta[30]
   static constexpr int D = 65, NN = 7, NF = 8, P = 3, NR = 30;
   struct Data { const double* y; const double* Xm; const int* rat; int N; double xbar; };
@@ -318,7 +345,7 @@ struct RatsModel {
 };
 
 // =============================================================================== pumps
-struct PumpsModel {
+struct PumpsModel : TplBase {
   static constexpr int D = 12, NN = 3, NF = 4, P = 12, NPUMP = 10;
   struct Data { const double* y; const double* t; const double* lgy1; int N; };
   MCU_HD static int node_off(int n) { return n; }
@@ -388,7 +415,7 @@ struct PumpsModel {
 // =============================================================================== surgical
 // doc/examples/surgical.jl:11-43: r_i ~ Binomial(n_i, invlogit(b_i)), b_i ~ Normal(mu, sqrt(s2)), mu ~ Normal(0, 1000),
 // s2 ~ InverseGamma(0.001, 0.001); Logical p = invlogit(b), pop_mean = invlogit(mu).  State: mu, s2, b[12].
-struct SurgicalModel {
+struct SurgicalModel : TplBase {
   static constexpr int D = 14, NN = 3, NF = 4, P = 15, NH = 12;
   struct Data { const double* r; const double* n; const double* lc; int N; };
   MCU_HD static int node_off(int n) { return n; }
@@ -443,7 +470,7 @@ struct SurgicalModel {
 // doc/examples/dyes.jl:22-47: y_k ~ MvNormal(mu[batch_k], sqrt(s2_within)) (30-dim iso), mu_i ~ Normal(theta, sqrt(s2_between)) (6 batches),
 // theta ~ Normal(0, 1000), s2_within, s2_between ~ InverseGamma(0.001, 0.001).  State / monitors (order of doc/examples/dyes.rst):
 // s2_between, theta, s2_within, mu[6].
-struct DyesModel {
+struct DyesModel : TplBase {
   static constexpr int D = 9, NN = 4, NF = 5, P = 9, NB = 6;
   struct Data { const double* y; const int* batch; int N; };
   MCU_HD static int node_off(int n) { return n; }
@@ -493,7 +520,7 @@ struct DyesModel {
 // response and an extra-Poisson random effect per plate/dose.  Matrices are flattened column-major (e = plate + 3 dose), as unlist
 // does (src/model/dependent.jl:192-195).  State: s2, gamma, beta, alpha, lambda[18] (the first four are the monitored columns, in the
 // order of doc/examples/salm.rst).
-struct SalmModel {
+struct SalmModel : TplBase {
   static constexpr int D = 22, NN = 5, NF = 6, P = 4, NY = 18, NPLATE = 3;
   struct Data { const double* y; const double* x; const double* lgy1; int N; };
   MCU_HD static int node_off(int n) { return n; }
@@ -551,7 +578,7 @@ struct SalmModel {
 // treatment (phi), period (pi) and subject-by-period (delta) effects; theta = fexp(phi) and equiv = 1{0.8 < theta < 1.2} are Logical.
 // Matrices column-major (e = subject + 10 period).  State: s2_2, s2_1, pi, phi, mu, delta[20]; monitored s2_2, s2_1, pi, phi, theta,
 // equiv, mu (the order of doc/examples/equiv.rst).
-struct EquivModel {
+struct EquivModel : TplBase {
   static constexpr int D = 25, NN = 6, NF = 7, P = 7, NS = 10, NY = 20;
   struct Data { const double* y; const double* group; int N; };
   MCU_HD static int node_off(int n) { return n; }
@@ -610,7 +637,7 @@ struct EquivModel {
 // doc/examples/blocker.jl:22-69 (data :4-18): meta-analysis of 22 beta-blocker trials, two observed Binomial nodes (control and treated
 // arms), trial baselines mu[22], trial effects delta[22] ~ Normal(d, sqrt(s2)) and a predictive effect delta_new.
 // State: s2, d, delta_new, mu[22], delta[22]; monitored s2, d, delta_new (the order of doc/examples/blocker.rst).
-struct BlockerModel {
+struct BlockerModel : TplBase {
   static constexpr int D = 47, NN = 5, NF = 7, P = 3, NT = 22;
   struct Data { const double* rc; const double* nc; const double* rt; const double* nt; const double* lcc; const double* lct; int N; };
   MCU_HD static int node_off(int n) { return n < 3 ? n : (n == 3 ? 3 : 3 + NT); }
@@ -674,7 +701,7 @@ struct BlockerModel {
 // doc/examples/stacks.jl:41-94 (data :4-38): stack-loss regression on standardised covariates z with a Laplace likelihood,
 // y[i] ~ Laplace(beta0 + z[i,:] . beta, s2).  Every monitored quantity is a Logical node: b = beta ./ sdx, b0 = beta0 - b . meanx,
 // sigma = sqrt(2) s2, outlier[i] = |y[i] - mu[i]| / sigma > 2.5 for i in (1, 3, 4, 21).  State: beta0, beta[3], s2.
-struct StacksModel {
+struct StacksModel : TplBase {
   static constexpr int D = 5, NN = 3, NF = 4, P = 9, NOBS = 21;
   struct Data { const double* y; const double* z; const double* meanx; const double* sdx; int N; };
   MCU_HD static int node_off(int n) { return n == 0 ? 0 : (n == 1 ? 1 : 4); }
@@ -723,11 +750,133 @@ struct StacksModel {
   MCU_D static int out_dist(const Data& d, const double* s, int i, double& a, double& b) { a = mu(d, s, i); b = s[4]; return OUT_LAPLACE; }
 };
 
+// =============================================================================== magnesium
+// doc/examples/magnesium.jl:21-82 (data :4-17): meta-analysis of 8 trials under six priors for the between-trial sd tau.  The example
+// whose parameter nodes carry bounded distributions: pc ~ Uniform(0, 1), mu ~ Uniform(-10, 10) — sampled by AMWG on the two-sided link
+// (transformdistribution.jl:6-48) — and priors = [InverseGamma(.001, .001), Uniform(0, 50) x 2, Uniform(0, 1) x 2,
+// Truncated(Normal(0, sqrt(s2_0 / erf(0.75))), 0, Inf)].  6 x 8 matrices are column-major (prior index i fastest), as in Julia.
+// State: priors[6], mu[6], theta[48], pc[48]; monitored (both Logical): tau[6], OR[6] = exp(mu).
+struct MagnesiumModel : TplBase {
+  static constexpr int D = 108, NN = 4, NF = 6, P = 12, NPR = 6, NTR = 8, NE = 48;
+  struct Data { const double* rc; const double* nc; const double* rt; const double* nt; const double* lcc; const double* lct; double s2_0; double sd6; };
+  MCU_HD static int node_off(int n) { return n == 0 ? 0 : n == 1 ? 6 : n == 2 ? 12 : 60; }
+  MCU_HD static int node_len(int n) { return n < 2 ? NPR : NE; }
+  MCU_HD static int node_link(int n) { return n == 2 ? LINK_IDENT : LINK_BOUNDED; }
+  MCU_HD static int elem_link(int e, int node_link) { return (e == 0 || e == 5) ? LINK_LOG : node_link; }   // InverseGamma / Normal truncated to [0, Inf)
+  MCU_HD static void elem_bounds(int e, double& lo, double& hi) {
+    if (e == 1 || e == 2) { lo = 0.0; hi = 50.0; }
+    else if (e >= 6 && e < 12) { lo = -10.0; hi = 10.0; }
+    else { lo = 0.0; hi = 1.0; }
+  }
+  MCU_HD static uint32_t parents(int f) { return f == 2 ? 0x3u /* priors (through tau), mu */ : f == 4 ? 0x8u /* pc */ : f == 5 ? 0xCu /* theta, pc */ : 0u; }
+  MCU_HD static int mon_link(int) { return LINK_HEUR; }
+  static const char* node_name(int n) { static const char* nm[] = {"priors", "mu", "theta", "pc"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "tau[1]\ntau[2]\ntau[3]\ntau[4]\ntau[5]\ntau[6]\nOR[1]\nOR[2]\nOR[3]\nOR[4]\nOR[5]\nOR[6]"; }
+  // tau = Logical(priors, s2_0): magnesium.jl:60-70
+  MCU_D static double tau(const Data& d, const double* s, int i) {
+    switch (i) {
+      case 0: return sqrt(s[0]);
+      case 1: return sqrt(s[1]);
+      case 2: return s[2];
+      case 3: return sqrt(d.s2_0 * (1.0 / s[3] - 1.0));
+      case 4: return sqrt(d.s2_0) * (1.0 / s[4] - 1.0);
+      default: return sqrt(s[5]);
+    }
+  }
+  MCU_D static double prior_term(const Data& d, const double* s, int k, bool transform) {
+    const double x = s[k];
+    switch (k) {
+      case 0: return lp_invgamma(x, 0.001, 0.001, ig001_c0(), transform);
+      case 1: case 2: return lp_uniform(x, 0.0, 50.0, transform);
+      case 3: case 4: return lp_uniform(x, 0.0, 1.0, transform);
+      default: {   // Truncated(Normal(0, sd6), 0, Inf): logpdf(Normal) - log(1/2) on [0, Inf) (Distributions/truncate.jl)
+        if (!(x >= 0.0)) return neg_inf();
+        double lp = lp_normal(x, 0.0, d.sd6) - flog(0.5);
+        if (transform) lp += flog(x);
+        return lp;
+      }
+    }
+  }
+  MCU_D static double rt_term(const Data& d, const double* s, int e) {   // rtx[i, j] ~ Binomial(nt[j], invlogit(theta + logit(pc))): magnesium.jl:37-49
+    const int j = e / NPR;
+    const double pc = s[60 + e], phi = flog(pc / (1.0 - pc));
+    const double pt = 1.0 / (fexp(-(s[12 + e] + phi)) + 1.0);
+    return lp_binomial_p(d.rt[j], d.nt[j], d.lct[j], pt);
+  }
+  MCU_D static double rc_term(const Data& d, const double* s, int e) { const int j = e / NPR; return lp_binomial_p(d.rc[j], d.nc[j], d.lcc[j], s[60 + e]); }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    double lp = 0.0;
+    if (f == 0) { for (int k = 0; k < NPR; ++k) lp += prior_term(d, s, k, transform); return lp; }
+    if (f == 1) { for (int i = 0; i < NPR; ++i) lp += lp_uniform(s[6 + i], -10.0, 10.0, transform); return lp; }
+    if (f == 2) {   // theta[i, j] ~ Normal(mu[i], tau[i])
+      double t[NPR]; for (int i = 0; i < NPR; ++i) t[i] = tau(d, s, i);
+      for (int e = 0; e < NE; ++e) lp += lp_normal(s[12 + e], s[6 + e % NPR], t[e % NPR]);
+      return lp;
+    }
+    if (f == 3) { for (int e = 0; e < NE; ++e) lp += lp_uniform(s[60 + e], 0.0, 1.0, transform); return lp; }
+    if (f == 4) { for (int e = 0; e < NE; ++e) lp += rc_term(d, s, e); return lp; }
+    for (int e = 0; e < NE; ++e) lp += rt_term(d, s, e);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    double dmu[NPR] = {0, 0, 0, 0, 0, 0}, dtau[NPR] = {0, 0, 0, 0, 0, 0}, t[NPR];
+    for (int i = 0; i < NPR; ++i) t[i] = tau(d, s, i);
+    for (int e = 0; e < NE; ++e) {
+      const int i = e % NPR, j = e / NPR;
+      const double pc = s[60 + e], th = s[12 + e];
+      const double pt = 1.0 / (fexp(-(th + flog(pc / (1.0 - pc)))) + 1.0);
+      const double r = d.rt[j] - d.nt[j] * pt, dev = th - s[6 + i], t2 = t[i] * t[i];
+      g[12 + e] = -dev / t2 + r;
+      g[60 + e] = d.rc[j] / pc - (d.nc[j] - d.rc[j]) / (1.0 - pc) + r / (pc * (1.0 - pc));
+      dmu[i] += dev / t2;
+      dtau[i] += -1.0 / t[i] + dev * dev / (t2 * t[i]);
+    }
+    for (int i = 0; i < NPR; ++i) g[6 + i] = dmu[i];
+    g[0] = dtau[0] / (2.0 * t[0]) + d_invgamma(s[0], 0.001, 0.001);
+    g[1] = dtau[1] / (2.0 * t[1]);
+    g[2] = dtau[2];
+    g[3] = dtau[3] * (-d.s2_0 / (s[3] * s[3])) / (2.0 * t[3]);
+    g[4] = dtau[4] * (-sqrt(d.s2_0) / (s[4] * s[4]));
+    g[5] = dtau[5] / (2.0 * t[5]) - s[5] / (d.sd6 * d.sd6);
+  }
+  // every element is local: priors[k] / mu[i]: own prior + the 8 Normal terms of row k / i; theta[e]: its Normal term + its treated arm;
+  // pc[e]: its Uniform term + both arms of cell e
+  MCU_HD static bool elem_local(int) { return true; }
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool transform) {
+    if (e < 12) {
+      const int i = e < 6 ? e : e - 6;
+      const double own = e < 6 ? prior_term(d, s, e, transform) : lp_uniform(s[e], -10.0, 10.0, transform);
+      if (!(own > neg_inf())) return neg_inf();
+      const double ti = tau(d, s, i);
+      double lp = own;
+      for (int j = 0; j < NTR; ++j) lp += lp_normal(s[12 + i + NPR * j], s[6 + i], ti);
+      return lp;
+    }
+    if (e < 60) { const int q = e - 12; return lp_normal(s[e], s[6 + q % NPR], tau(d, s, q % NPR)) + rt_term(d, s, q); }
+    const int q = e - 60;
+    const double own = lp_uniform(s[e], 0.0, 1.0, transform);
+    if (!(own > neg_inf())) return neg_inf();
+    return own + rc_term(d, s, q) + rt_term(d, s, q);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data& d, const double* s, double* out) {
+    for (int i = 0; i < NPR; ++i) { out[i] = tau(d, s, i); out[NPR + i] = fexp(s[6 + i]); }   // OR = exp(mu): magnesium.jl:56-58
+  }
+  MCU_HD static int out_len(const Data&) { return 2 * NE; }   // rcx[48] then rtx[48]
+  MCU_D static int out_dist(const Data& d, const double* s, int o, double& a, double& b) {
+    if (o < NE) { a = d.nc[o / NPR]; b = s[60 + o]; }
+    else { const int e = o - NE; const double pc = s[60 + e]; a = d.nt[e / NPR]; b = 1.0 / (fexp(-(s[12 + e] + flog(pc / (1.0 - pc)))) + 1.0); }
+    return OUT_BINOMIAL;
+  }
+};
+
 // =============================================================================== glm (CUDA-core form)
 // y_i ~ Bernoulli(invlogit(X[i,:] . beta)), beta ~ MvNormal(d, sqrt(1000)).  This per-chain form is the
 // small-N path used by the generic kernel; the large-N path is the fused tensor-core kernel.
 template <int DMAX>
-struct GlmModel {
+struct GlmModel : TplBase {
   static constexpr int D = DMAX, NN = 1, NF = 2, P = DMAX;
   // family: 0 Bernoulli / logit, 1 Poisson / log, 2 Normal / identity with known sd sigma
   struct Data { const double* X; const double* y; int N; int d; int family; double sigma; };

@@ -37,6 +37,7 @@ struct DevBlock {
   double target, epsilon, beta, amm_scale;
   const int* elem;                     // [k] state index of each block element
   const int* elink;                    // [k] link code of each block element
+  const double* ebound;                // [2k] (lo, hi) of each block element with a LINK_BOUNDED link, or nullptr when the block has none
   const double* scale;                 // [k] sigma / width / scale, expanded
   const double* SigmaL;                // [k*k] column-major lower Cholesky factor (HMC with Sigma, AMM) or nullptr
 };

@@ -50,7 +50,8 @@ const TEMPLATES = Dict(
   7 => [:s2, :gamma, :beta, :alpha, :lambda],                             # doc/examples/salm.jl
   8 => [:s2_2, :s2_1, :pi, :phi, :mu, :delta],                            # doc/examples/equiv.jl
   9 => [:s2, :d, :delta_new, :mu, :delta],                                # doc/examples/blocker.jl
-  10 => [:beta0, :beta, :s2]                                              # doc/examples/stacks.jl
+  10 => [:beta0, :beta, :s2],                                             # doc/examples/stacks.jl
+  11 => [:priors, :mu, :theta, :pc]                                       # doc/examples/magnesium.jl (6 x 8 matrices column-major)
 )                                                                         # (4 = the GLM family: pass template=4 and inputs X, y)
 
 function check(h::Ptr{Void}, rc::Cint)

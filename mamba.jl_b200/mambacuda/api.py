@@ -48,6 +48,8 @@ _TEMPLATES = {
     "blocker": dict(nodes=[("s2", 1), ("d", 1), ("delta_new", 1), ("mu", 22), ("delta", 22)], inputs=["rc", "nc", "rt", "nt"], outputs=["rc", "rt"],
                     output_lens=[22, 22]),
     "stacks": dict(nodes=[("beta0", 1), ("beta", 3), ("s2", 1)], inputs=["y", "x"], outputs=["y"]),
+    "magnesium": dict(nodes=[("priors", 6), ("mu", 6), ("theta", 48), ("pc", 48)], inputs=["rc", "nc", "rt", "nt"], outputs=["rcx", "rtx"],
+                      output_lens=[48, 48]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 

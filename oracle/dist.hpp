@@ -35,22 +35,31 @@ inline double digamma(double x) {
   return r + std::log(x) - 0.5 / x + t;
 }
 
-enum DKind { D_NULL = 0, D_NORMAL, D_INVGAMMA, D_GAMMA, D_EXPONENTIAL, D_BINOMIAL, D_POISSON, D_BERNOULLI, D_LAPLACE };
+enum DKind { D_NULL = 0, D_NORMAL, D_INVGAMMA, D_GAMMA, D_EXPONENTIAL, D_BINOMIAL, D_POISSON, D_BERNOULLI, D_LAPLACE, D_UNIFORM, D_BETA, D_TRUNCNORMAL };
 
 struct UDist {
   DKind k = D_NULL;
   double a = 0, b = 0;  // Normal(mu, sigma); InverseGamma(shape, scale); Gamma(shape, scale);
-                        // Exponential(scale); Binomial(n, p); Poisson(lambda); Bernoulli(p); Laplace(location, scale)
+                        // Exponential(scale); Binomial(n, p); Poisson(lambda); Bernoulli(p); Laplace(location, scale);
+                        // Uniform(a, b); Beta(alpha, beta); Truncated(Normal(mu = a, sigma = b), lo, hi)
+  double lo = 0, hi = 0;  // truncation bounds (D_TRUNCNORMAL only; +-Inf for a one-sided truncation)
 };
 
-// @distr_support bounds of Distributions.jl
+// @distr_support bounds of Distributions.jl (minimum(d), maximum(d))
 inline double dmin(const UDist& d) {
-  switch (d.k) { case D_NORMAL: case D_LAPLACE: return NEG_INF; default: return 0.0; }
+  switch (d.k) {
+    case D_NORMAL: case D_LAPLACE: return NEG_INF;
+    case D_UNIFORM: return d.a;
+    case D_TRUNCNORMAL: return d.lo;
+    default: return 0.0;
+  }
 }
 inline double dmax(const UDist& d) {
   switch (d.k) {
     case D_BINOMIAL: return d.a;
-    case D_BERNOULLI: return 1.0;
+    case D_BERNOULLI: case D_BETA: return 1.0;
+    case D_UNIFORM: return d.b;
+    case D_TRUNCNORMAL: return d.hi;
     default: return -NEG_INF;
   }
 }
@@ -95,25 +104,70 @@ inline double logpdf(const UDist& d, double x) {
       return x == 0.0 ? std::log(1.0 - d.a) : (x == 1.0 ? std::log(d.a) : NEG_INF);
     case D_LAPLACE:   // Distributions/univariate/continuous/laplace.jl: -(|x - mu| / theta + log(2 theta))
       return -(std::fabs(x - d.a) / d.b + std::log(2.0 * d.b));
+    case D_UNIFORM:   // Distributions/univariate/continuous/uniform.jl: insupport ? -log(b - a) : -Inf
+      return (x >= d.a && x <= d.b) ? -std::log(d.b - d.a) : NEG_INF;
+    case D_BETA:      // (alpha - 1) log x + (beta - 1) log1p(-x) - lbeta(alpha, beta)
+      return (d.a - 1.0) * std::log(x) + (d.b - 1.0) * std::log1p(-x) - (lgam(d.a) + lgam(d.b) - lgam(d.a + d.b));
+    case D_TRUNCNORMAL: {  // Distributions/truncate.jl: logpdf(untruncated, x) - logtp inside [lo, hi], tp = cdf(hi) - cdf(lo)
+      if (!(x >= d.lo && x <= d.hi)) return NEG_INF;
+      auto Phi = [&](double t) { return std::isinf(t) ? (t > 0 ? 1.0 : 0.0) : 0.5 * std::erfc(-(t - d.a) / d.b * M_SQRT1_2); };
+      const double z = (x - d.a) / d.b;
+      return -(z * z + LOG2PI) / 2.0 - std::log(d.b) - std::log(Phi(d.hi) - Phi(d.lo));
+    }
     default: return 0.0;
   }
 }
 
-// Membership in the unions of transformdistribution.jl:53-93.  Discrete distributions fall to
-// the `link(d::Distribution, x) = x` fallbacks of distributionstruct.jl:84,104,136.
-enum LinkKind { LK_IDENT = 0, LK_LOG = 1 };
+// link / invlink / transformed logpdf: transformdistribution.jl:6-93.  The generic TransformDistribution methods (:6-48) decide from
+// (minimum(d), maximum(d)): both finite -> logit((x - a) / (b - a)); lower only -> log(x - a); upper only -> log(b - x); neither -> x.
+// The Real / Positive / Unit unions (:53-93) are the special cases (a, b) = (-Inf, Inf), (0, Inf), (0, 1) of the same maps.
+// Discrete distributions fall to the `link(d::Distribution, x) = x` fallbacks of distributionstruct.jl:84,104,136.
+enum LinkKind { LK_IDENT = 0, LK_LOG = 1, LK_BOUNDED = 2, LK_UPPER = 3 };
 inline LinkKind linkkind(const UDist& d) {
-  switch (d.k) {
-    case D_INVGAMMA: case D_GAMMA: case D_EXPONENTIAL: return LK_LOG;  // PositiveDistribution :66-78
-    default: return LK_IDENT;                                           // RealDistribution :53-61 / fallbacks
+  if (is_discrete(d) || d.k == D_NULL) return LK_IDENT;
+  const bool lower = std::isfinite(dmin(d)), upper = std::isfinite(dmax(d));
+  return lower && upper ? LK_BOUNDED : lower ? LK_LOG : upper ? LK_UPPER : LK_IDENT;
+}
+inline double link(const UDist& d, double x) {
+  const double a = dmin(d), b = dmax(d);
+  switch (linkkind(d)) {
+    case LK_BOUNDED: return logit((x - a) / (b - a));
+    case LK_LOG: return std::log(x - a);
+    case LK_UPPER: return std::log(b - x);
+    default: return x;
   }
 }
-inline double link(const UDist& d, double x) { return linkkind(d) == LK_LOG ? std::log(x) : x; }
-inline double invlink(const UDist& d, double x) { return linkkind(d) == LK_LOG ? std::exp(x) : x; }
+inline double invlink(const UDist& d, double x) {
+  const double a = dmin(d), b = dmax(d);
+  switch (linkkind(d)) {
+    case LK_BOUNDED: return (b - a) * invlogit(x) + a;
+    case LK_LOG: return std::exp(x) + a;
+    case LK_UPPER: return b - std::exp(x);
+    default: return x;
+  }
+}
 inline double logpdf(const UDist& d, double x, bool transform) {
   double lp = logpdf(d, x);
-  if (transform && linkkind(d) == LK_LOG) lp += std::log(x);  // :75-78
+  if (transform) {
+    const double a = dmin(d), b = dmax(d);
+    switch (linkkind(d)) {
+      case LK_BOUNDED: lp += std::log((x - a) * (b - x) / (b - a)); break;   // :39-40
+      case LK_LOG: lp += std::log(x - a); break;                              // :41-42, :75-78
+      case LK_UPPER: lp += std::log(b - x); break;                            // :43-44
+      default: break;
+    }
+  }
   return lp;
+}
+// d(constrained value)/d(link value) and d(log-Jacobian)/d(link value) at the constrained value x: chain rule of the analytic gradient
+inline void link_chain(const UDist& d, double x, double& dtheta, double& djac) {
+  const double a = dmin(d), b = dmax(d);
+  switch (linkkind(d)) {
+    case LK_BOUNDED: dtheta = (x - a) * (b - x) / (b - a); djac = ((b - x) - (x - a)) / (b - a); break;
+    case LK_LOG: dtheta = x - a; djac = 1.0; break;
+    case LK_UPPER: dtheta = -(b - x); djac = 1.0; break;
+    default: dtheta = 1.0; djac = 0.0; break;
+  }
 }
 // distributionstruct.jl:138-140
 inline double logpdf_sub(const UDist& d, double x, bool transform) {

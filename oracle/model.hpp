@@ -275,9 +275,11 @@ struct Model {
       int so = state_offset(p);
       for (int e = 0; e < n.len; ++e, ++o) {
         const UDist& d = n.distr.form == Distr::UNI_ARRAY ? n.distr.arr[e] : n.distr.u;
-        bool lg = transform && n.distr.form != Distr::MVNORMAL_ISO && linkkind(d) == LK_LOG;
-        // theta = exp(x): d/dx [lp(theta) + log theta] = theta * dlp/dtheta + 1
-        g[o] = lg ? gj[so + e] * n.value[e] + 1.0 : gj[so + e];
+        // theta = invlink(x): d/dx [lp(theta) + log|dtheta/dx|] = dlp/dtheta * dtheta/dx + d(log-Jacobian)/dx
+        if (transform && n.distr.form != Distr::MVNORMAL_ISO) {
+          double dth, dj; link_chain(d, n.value[e], dth, dj);
+          g[o] = gj[so + e] * dth + dj;
+        } else g[o] = gj[so + e];
       }
     }
     return g;

@@ -385,9 +385,10 @@ static void read_tune(Model& m, const double* o) {
 //  over worker processes, utils.jl:91-98 — disabled in this version).
 int orc_run2(void* h, int64_t n_chains, int64_t chain_offset, const int64_t* chain_ids, uint64_t seed, const double* inits, int64_t n_inits,
              double jitter_sd, int64_t iter0, const double* tune_in, int64_t iters, int64_t burnin, int64_t thin, double* out,
-             double* final_state, double* tune_out, double* margins, const double* ext_u, int64_t n_per_chain, int nthreads) {
+             double* final_state, double* tune_out, double* margins, const double* ext_u, int64_t n_per_chain, int nthreads, int partial) {
   Ctx* c = (Ctx*)h;
-  if (iter0 == 0 && iters <= burnin) { c->err = "burnin is greater than or equal to iters"; return MCU_ERR_ARG; }   // mcmc.jl:22-23
+  // partial != 0: the call is one segment of a longer run whose burn-in may extend past it (the caller continues with iter0 > 0)
+  if (iter0 == 0 && !partial && iters <= burnin) { c->err = "burnin is greater than or equal to iters"; return MCU_ERR_ARG; }   // mcmc.jl:22-23
   if (n_inits < 1) { c->err = "fewer initial values than chains"; return MCU_ERR_ARG; }              // mcmc.jl:24-25
   if (thin < 1) { c->err = "thin must be positive"; return MCU_ERR_ARG; }
   if (iter0 > 0 && n_inits != n_chains) { c->err = "a restart needs one state record per chain"; return MCU_ERR_ARG; }
@@ -453,7 +454,7 @@ int orc_run(void* h, int64_t n_chains, int64_t chain_offset, uint64_t seed, cons
             double jitter_sd, int64_t iters, int64_t burnin, int64_t thin, double* out, double* final_state,
             double* tune_out, const double* ext_u, int64_t n_per_chain, int nthreads) {
   return orc_run2(h, n_chains, chain_offset, nullptr, seed, inits, n_inits, jitter_sd, 0, nullptr, iters, burnin, thin, out, final_state,
-                  tune_out, nullptr, ext_u, n_per_chain, nthreads);
+                  tune_out, nullptr, ext_u, n_per_chain, nthreads, 0);
 }
 
 // gelmandiag(c; alpha, transform): linkcode per column (-1 heuristic / 0 identity / 1 log) or NULL = no transform
@@ -469,6 +470,16 @@ int orc_gelmandiag(const double* chains, int64_t n, int64_t p, int64_t m, double
 int orc_summarystats(const double* chains, int64_t n, int64_t p, int64_t m, int etype, int64_t batch, double* out) {
   summarystats(chains, (size_t)n, (size_t)p, (size_t)m, etype, (size_t)batch, out);
   return 0;
+}
+// link layer probe (transformdistribution.jl:6-93) for one univariate distribution: out = { link(x), invlink(link(x)), logpdf(x, true) - logpdf(x, false) }
+// kind: DKind of dist.hpp (9 Uniform(a, b), 10 Beta(a, b), 11 Truncated(Normal(a, b), lo, hi), 2 InverseGamma, ...)
+void orc_link(int kind, double a, double b, double lo, double hi, double x, double* out) {
+  UDist d; d.k = (DKind)kind; d.a = a; d.b = b; d.lo = lo; d.hi = hi;
+  out[0] = link(d, x); out[1] = invlink(d, out[0]); out[2] = logpdf(d, x, true) - logpdf(d, x, false);
+}
+double orc_udist_logpdf(int kind, double a, double b, double lo, double hi, double x) {
+  UDist d; d.k = (DKind)kind; d.a = a; d.b = b; d.lo = lo; d.hi = hi;
+  return logpdf_sub(d, x, false);
 }
 double orc_fquantile(double q, double d1, double d2) { return fquantile(q, d1, d2); }
 double orc_digamma(double x) { return digamma(x); }

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-TPL = {"line": 0, "seeds": 1, "rats": 2, "pumps": 3, "glm": 4, "surgical": 5, "dyes": 6, "salm": 7, "equiv": 8, "blocker": 9, "stacks": 10}
+TPL = {"line": 0, "seeds": 1, "rats": 2, "pumps": 3, "glm": 4, "surgical": 5, "dyes": 6, "salm": 7, "equiv": 8, "blocker": 9, "stacks": 10, "magnesium": 11}
 KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc": 5, "amm": 6, "gibbs": 7, "mala": 8}
 MAX_BLOCK_NODES = 8
 
@@ -88,7 +88,7 @@ def lib():
         L.orc_kept2.restype = C.c_int64
         L.orc_kept2.argtypes = [C.c_int64] * 4
         L.orc_run2.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_uint64, dp, C.c_int64, C.c_double,
-                               C.c_int64, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.c_int64, C.c_int]
+                               C.c_int64, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.c_int64, C.c_int, C.c_int]
         L.orc_gelmandiag.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_int), dp]
         L.orc_summarystats.argtypes = [dp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64, dp]
         L.orc_fquantile.restype = C.c_double
@@ -192,10 +192,11 @@ class Oracle:
         return self.L.orc_tune_size(self.h)
 
     def run(self, n_chains, inits, iters, burnin=0, thin=1, seed=123, chain_offset=0, jitter_sd=0.0,
-            ext_u=None, nthreads=1, store=True, chain_ids=None, iter0=0, tune_in=None, margins=False):
+            ext_u=None, nthreads=1, store=True, chain_ids=None, iter0=0, tune_in=None, margins=False, partial=False):
         """mcmc() for n_chains chains.  chain_ids: explicit global chain ids (scattered samples of a large run);
         iter0 > 0: restart — inits holds one state record per chain and tune_in their tune records;
-        margins=True also returns [n_chains x iters], the smallest decision margin of every iteration (samplers.hpp)."""
+        margins=True also returns [n_chains x iters], the smallest decision margin of every iteration (samplers.hpp);
+        partial=True: one segment of a longer run (burn-in may extend past it)."""
         inits = _f64(np.atleast_2d(inits))
         D, p = self.dims()
         assert inits.shape[1] == D
@@ -216,7 +217,7 @@ class Oracle:
             ext_u = _f64(np.atleast_2d(ext_u)); npc = ext_u.shape[1]
         ids = None if chain_ids is None else chain_ids.ctypes.data_as(C.POINTER(C.c_int64))
         rc = self.L.orc_run2(self.h, n_chains, chain_offset, ids, seed, _dp(inits), inits.shape[0], jitter_sd, iter0, _dp(tin),
-                             iters, burnin, thin, _dp(out), _dp(final), _dp(tune), _dp(marg), _dp(ext_u), npc, nthreads)
+                             iters, burnin, thin, _dp(out), _dp(final), _dp(tune), _dp(marg), _dp(ext_u), npc, nthreads, int(partial))
         self._chk(rc)
         if margins:
             return out, final, tune[:, :nt], marg
@@ -244,6 +245,25 @@ def summarystats(chains, etype=0, batch=100):
     out = np.empty((p, 5))
     L.orc_summarystats(_dp(c), n, p, m, etype, batch, _dp(out))
     return out
+
+
+DKIND = {"normal": 1, "invgamma": 2, "gamma": 3, "exponential": 4, "binomial": 5, "poisson": 6, "bernoulli": 7, "laplace": 8, "uniform": 9, "beta": 10, "truncnormal": 11}
+
+
+def link(kind, a, b, x, lo=0.0, hi=0.0):
+    """(link(x), invlink(link(x)), log-Jacobian) of one univariate distribution: transformdistribution.jl:6-93."""
+    L = lib()
+    L.orc_link.argtypes = [C.c_int] + [C.c_double] * 5 + [C.POINTER(C.c_double)]
+    out = np.empty(3)
+    L.orc_link(DKIND[kind], a, b, lo, hi, x, _dp(out))
+    return out
+
+
+def udist_logpdf(kind, a, b, x, lo=0.0, hi=0.0):
+    L = lib()
+    L.orc_udist_logpdf.restype = C.c_double
+    L.orc_udist_logpdf.argtypes = [C.c_int] + [C.c_double] * 5
+    return L.orc_udist_logpdf(DKIND[kind], a, b, lo, hi, x)
 
 
 def rwm_draws(proposal, seed, n):

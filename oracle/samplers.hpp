@@ -418,8 +418,10 @@ inline size_t pivoted_chol_PL(const Vec& A_in, size_t n, Vec& PL) {
     size_t pvt = j; double best = -1;
     for (size_t i = j; i < n; ++i) {
       double d = A[i + i * n] - dots[i];
+      if (i > j) note_margin(d, best, amax);            // pivot choice: two candidates within rounding of each other
       if (d > best) { best = d; pvt = i; }
     }
+    note_margin(best, tol, amax);                        // rank decision on a (near-)singular Schur complement
     if (best <= tol || std::isnan(best)) { rank = j; break; }
     if (pvt != j) {
       // symmetric swap of rows/cols j and pvt in A, and of the computed rows of L

@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9, TPL_STACKS = 10 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9, TPL_STACKS = 10, TPL_MAGNESIUM = 11 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -319,6 +319,109 @@ inline Model make_glm(int d) {
       double r = fam == 1 ? y[i] - std::exp(eta) : fam == 2 ? (y[i] - eta) / (sg * sg) : y[i] - invlogit(eta);
       for (int j = 0; j < d; ++j) g[j] += r * X[i * d + j];
     }
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// magnesium: doc/examples/magnesium.jl:21-82 (data :4-17) — meta-analysis of 8 trials under six priors for the between-trial sd tau.
+// The one example whose parameter nodes carry BOUNDED distributions: pc ~ Uniform(0, 1), mu ~ Uniform(-10, 10) (sampled by AMWG on the
+// two-sided link logit((x - a) / (b - a)), transformdistribution.jl:6-48), priors = [InverseGamma, Uniform(0, 50) x 2, Uniform(0, 1) x 2,
+// Truncated(Normal(0, sqrt(s2_0 / erf(0.75))), 0, Inf)].  6 x 8 matrices are stored column-major (prior index i fastest), as Julia does.
+// Node order: priors, mu, tau (Logical), OR (Logical), theta, pc, rcx (observed), rtx (observed); monitored: tau[6], OR[6].
+inline Model make_magnesium() {
+  Model m; m.template_id = TPL_MAGNESIUM;
+  m.inputs["rt"] = {1, 9, 2, 1, 10, 1, 1, 90};
+  m.inputs["nt"] = {40, 135, 200, 48, 150, 59, 25, 1159};
+  m.inputs["rc"] = {2, 23, 7, 1, 8, 9, 3, 118};
+  m.inputs["nc"] = {36, 135, 200, 46, 148, 56, 23, 1157};
+  {
+    const auto &rt = m.inputs["rt"], &nt = m.inputs["nt"], &rc = m.inputs["rc"], &nc = m.inputs["nc"];
+    std::vector<double> rtx(48), rcx(48);
+    double sinv = 0.0;
+    for (int j = 0; j < 8; ++j) {
+      for (int i = 0; i < 6; ++i) { rtx[i + 6 * j] = rt[j]; rcx[i + 6 * j] = rc[j]; }                      // magnesium.jl:11-12
+      const double s2 = 1.0 / (rt[j] + 0.5) + 1.0 / (nt[j] - rt[j] + 0.5) + 1.0 / (rc[j] + 0.5) + 1.0 / (nc[j] - rc[j] + 0.5);   // :13-16
+      sinv += 1.0 / s2;
+    }
+    m.inputs["rtx"] = rtx; m.inputs["rcx"] = rcx;
+    m.inputs["s2_0"] = {1.0 / (sinv / 8.0)};                                                               // :17
+  }
+  { Node n = make_node("priors", true, 6, false, false);                                                   // 0
+    n.eval = [](const Model& mm, Node& s) {
+      const double s2_0 = mm.in("s2_0")[0];
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(6);
+      s.distr.arr[0] = {D_INVGAMMA, 0.001, 0.001};
+      s.distr.arr[1] = {D_UNIFORM, 0.0, 50.0}; s.distr.arr[2] = {D_UNIFORM, 0.0, 50.0};
+      s.distr.arr[3] = {D_UNIFORM, 0.0, 1.0}; s.distr.arr[4] = {D_UNIFORM, 0.0, 1.0};
+      UDist t; t.k = D_TRUNCNORMAL; t.a = 0.0; t.b = std::sqrt(s2_0 / std::erf(0.75)); t.lo = 0.0; t.hi = INFINITY;
+      s.distr.arr[5] = t;
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("mu", true, 6, false, false);                                                       // 1
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_UNIFORM, -10.0, 10.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("tau", false, 6, false, true);                                                      // 2: Logical
+    n.sources = {0};
+    n.eval = [](const Model& mm, Node& l) {
+      const auto& p = mm.val(0); const double s2_0 = mm.in("s2_0")[0];
+      l.value = {std::sqrt(p[0]), std::sqrt(p[1]), p[2], std::sqrt(s2_0 * (1.0 / p[3] - 1.0)), std::sqrt(s2_0) * (1.0 / p[4] - 1.0), std::sqrt(p[5])};
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("OR", false, 6, false, true);                                                       // 3: Logical, exp(mu)
+    n.sources = {1};
+    n.eval = [](const Model& mm, Node& l) { l.value.resize(6); for (int i = 0; i < 6; ++i) l.value[i] = std::exp(mm.val(1)[i]); };
+    m.nodes.push_back(n); }
+  { Node n = make_node("theta", true, 48, false, false);                                                   // 4: Normal(mu[i], tau[i])
+    n.sources = {1, 2};
+    n.eval = [](const Model& mm, Node& s) {
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(48);
+      for (int j = 0; j < 8; ++j) for (int i = 0; i < 6; ++i) s.distr.arr[i + 6 * j] = {D_NORMAL, mm.val(1)[i], mm.val(2)[i]};
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("pc", true, 48, false, false);                                                      // 5
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_UNIFORM, 0.0, 1.0}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("rcx", true, 48, false, false, true);                                               // 6: Binomial(nc[j], pc[i, j])
+    n.sources = {5};
+    n.eval = [](const Model& mm, Node& s) {
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(48);
+      for (int j = 0; j < 8; ++j) for (int i = 0; i < 6; ++i) s.distr.arr[i + 6 * j] = {D_BINOMIAL, mm.in("nc")[j], mm.val(5)[i + 6 * j]};
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("rtx", true, 48, false, false, true);                                               // 7: Binomial(nt[j], invlogit(theta + logit(pc)))
+    n.sources = {5, 4};
+    n.eval = [](const Model& mm, Node& s) {
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(48);
+      for (int e = 0; e < 48; ++e) {
+        const double phi = logit(mm.val(5)[e]);
+        s.distr.arr[e] = {D_BINOMIAL, mm.in("nt")[e / 6], invlogit(mm.val(4)[e] + phi)};
+      }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: priors[6], mu[6], theta[48], pc[48]
+    const auto &rt = mm.in("rt"), &nt = mm.in("nt"), &rc = mm.in("rc"), &nc = mm.in("nc");
+    const auto &p = mm.val(0), &mu = mm.val(1), &tau = mm.val(2), &th = mm.val(4), &pc = mm.val(5);
+    const double s2_0 = mm.in("s2_0")[0];
+    double dmu[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < 48; ++e) {
+      const int i = e % 6, j = e / 6;
+      const double pt = invlogit(th[e] + logit(pc[e]));
+      const double r = rt[j] - nt[j] * pt, dev = th[e] - mu[i], t2 = tau[i] * tau[i];
+      g[12 + e] = -dev / t2 + r;
+      g[60 + e] = rc[j] / pc[e] - (nc[j] - rc[j]) / (1.0 - pc[e]) + r / (pc[e] * (1.0 - pc[e]));
+      dmu[i] += dev / t2;
+      dtau[i] += -1.0 / tau[i] + dev * dev / (t2 * tau[i]);
+    }
+    for (int i = 0; i < 6; ++i) g[6 + i] = dmu[i];
+    const double sg5 = std::sqrt(s2_0 / std::erf(0.75));
+    g[0] = dtau[0] / (2.0 * tau[0]) + ig_dlogpdf(0.001, 0.001, p[0]);
+    g[1] = dtau[1] / (2.0 * tau[1]);
+    g[2] = dtau[2];
+    g[3] = dtau[3] * (-s2_0 / (p[3] * p[3])) / (2.0 * tau[3]);
+    g[4] = dtau[4] * (-std::sqrt(s2_0) / (p[4] * p[4]));
+    g[5] = dtau[5] / (2.0 * tau[5]) - p[5] / (sg5 * sg5);
   };
   m.finalize();
   return m;
@@ -668,6 +771,7 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_DYES: return make_dyes();
     case TPL_SALM: return make_salm();
     case TPL_BLOCKER: return make_blocker();
+    case TPL_MAGNESIUM: return make_magnesium();
     case TPL_STACKS: return make_stacks();
     case TPL_EQUIV: return make_equiv();
     default: throw std::runtime_error("unknown template");

@@ -28,6 +28,10 @@ BLOCKER_INITS = np.array([[1.0, 0.0, 0.0] + [0.0] * 44, [10.0, 2.0, 2.0] + [2.0]
 STACKS_INITS = np.array([[10.0, 0.0, 0.0, 0.0, 10.0], [1.0, 1.0, 1.0, 1.0, 1.0]])                       # doc/examples/stacks.jl:98-101 (beta0, beta[3], s2)
 
 
+# doc/examples/magnesium.jl:86-95 (state order priors[6], mu[6], theta[6 x 8], pc[6 x 8])
+MAGNESIUM_INITS = np.array([[1, 1, 1, 0.5, 0.5, 1] + [-0.5] * 6 + [0.0] * 48 + [0.5] * 48, [1, 1, 1, 0.5, 0.5, 1] + [0.5] * 6 + [0.0] * 48 + [0.5] * 48], dtype=float)
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -98,6 +102,13 @@ SCHEMES = {
     # doc/examples/surgical.jl:54-55: NUTS(:b), Slice([:mu, :s2], 1.0)
     "surgical_nuts_slice": ("surgical", [dict(kind="nuts", nodes=[2]), dict(kind="slice_multi", nodes=[0, 1], scale=1.0)], SURGICAL_INITS),
     "surgical_amwg": ("surgical", [dict(kind="amwg", nodes=[2], scale=0.3), dict(kind="amwg", nodes=[0, 1], scale=0.3)], SURGICAL_INITS),
+    # doc/examples/magnesium.jl:99-102: AMWG(:theta, 0.1), AMWG(:mu, 0.1) [Uniform(-10, 10): two-sided link], Slice(:pc, 0.25, Univariate),
+    # Slice(:priors, [1.0, 5.0, 5.0, 0.25, 0.25, 5.0], Univariate)
+    "magnesium": ("magnesium", [dict(kind="amwg", nodes=[2], scale=0.1), dict(kind="amwg", nodes=[1], scale=0.1), dict(kind="slice_uni", nodes=[3], scale=0.25),
+                                dict(kind="slice_uni", nodes=[0], scale=[1.0, 5.0, 5.0, 0.25, 0.25, 5.0])], MAGNESIUM_INITS),
+    # every block on the link scale: log for priors[1] / priors[6], two-sided logit for the Uniform priors, mu and pc
+    "magnesium_transformed": ("magnesium", [dict(kind="amwg", nodes=[2], scale=0.1), dict(kind="amwg", nodes=[1, 0], scale=0.2),
+                                            dict(kind="slice_uni", nodes=[3], scale=1.0, transform=1), dict(kind="nuts", nodes=[0, 1])], MAGNESIUM_INITS),
     # doc/examples/pumps.jl:52-53
     "pumps_slice": ("pumps", [dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], None),
     "pumps_amwg_nuts": ("pumps", [dict(kind="amwg", nodes=[0, 1], scale=0.5), dict(kind="nuts", nodes=[2])], None),
@@ -179,7 +190,7 @@ def audit_divergence(g, o, margins, kept_iters, iter0, rtol=1e-8, atol=1e-10, tu
     return C - len(ties), ties
 
 
-def resync_audit(eng, orc, ids, inits, iters, burnin, seed, jitter_sd, rtol, tie, run_kw=None, nthreads=None):
+def resync_audit(eng, orc, ids, inits, iters, burnin, seed, jitter_sd, rtol, tie, run_kw=None, nthreads=None, tune_rtol=None):
     """Per-step parity (north_star: same state + same stream => same decisions and the same next state).  At every iteration the
     sampled device chains `ids` are put at the oracle's state / tune records, both sides take ONE iteration, and the results must
     agree to `rtol` unless the oracle's smallest decision margin of that iteration is below `tie`.  The other chains of the launch
@@ -188,13 +199,14 @@ def resync_audit(eng, orc, ids, inits, iters, burnin, seed, jitter_sd, rtol, tie
     run_kw = run_kw or {}
     nthreads = nthreads or os.cpu_count() or 4
     ids = np.asarray(ids, dtype=np.int64)
+    tune_rtol = tune_rtol or rtol * 10
     ties, compared = [], 0
     prev_o = prev_t = st = tune = None
     for i in range(1, iters + 1):
         if i == 1:      # iteration 1 starts from the (jittered) inits on both sides; the tune records are created there (sampler.jl:40-45)
             eng.set_inits(inits, jitter_sd=jitter_sd)
             _, st_o, tune_o, marg = orc.run(0, inits, 1, burnin=burnin, thin=1, seed=seed, jitter_sd=jitter_sd, chain_ids=ids,
-                                            nthreads=nthreads, margins=True, store=False)
+                                            nthreads=nthreads, margins=True, store=False, partial=True)
         else:
             st[ids] = prev_o; tune[ids] = prev_t
             eng.set_state(st, tune, i - 1)
@@ -204,7 +216,7 @@ def resync_audit(eng, orc, ids, inits, iters, burnin, seed, jitter_sd, rtol, tie
         st, tune, it = eng.get_state()
         assert it == i
         for k, c in enumerate(ids):
-            same = np.allclose(st[c], st_o[k], rtol=rtol, atol=1e-9) and np.allclose(tune[c], tune_o[k], rtol=rtol * 10, atol=1e-9, equal_nan=True)
+            same = np.allclose(st[c], st_o[k], rtol=rtol, atol=1e-9) and np.allclose(tune[c], tune_o[k], rtol=tune_rtol, atol=1e-9, equal_nan=True)
             if not same:
                 assert marg[k, 0] < tie, (f"iteration {i}, chain {c}: device and oracle differ after one step from a common state and no "
                                           f"decision was within {tie:g} of its threshold (smallest margin {marg[k, 0]:.3g}; "

@@ -8,6 +8,8 @@ import os
 import numpy as np
 import pytest
 
+import helpers
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # golden key -> (scheme blocks that expose the block, index of the block inside that scheme)
@@ -527,3 +529,108 @@ def test_abi_convergence_diagnostics_match_numpy(mcu_built, gold_diag):
     assert r[1, 0, 0] >= r[0, 0, 0]                       # the strongly autocorrelated column needs more thinning
     short, _, _ = api.rafterydiag(api.Chains(z[:500]))     # fewer than nmin samples: NaN rows, nmin reported
     assert np.isnan(short[0, 0, 0]) and short[0, 3, 0] == 3746
+
+
+# ---- link layer (src/distributions/transformdistribution.jl:6-93) and the magnesium template that exercises it -----------------------
+MAG_BLOCKS = {   # golden key -> (scheme, block index)
+    "amwg_theta": ("magnesium", 0), "amwg_mu_transformed": ("magnesium", 1), "slice_pc": ("magnesium", 2), "slice_priors": ("magnesium", 3),
+    "slice_pc_transformed": ("magnesium_transformed", 2), "priors_mu_transformed": ("magnesium_transformed", 3),
+}
+
+
+@pytest.fixture(scope="module")
+def gold_links():
+    with open(os.path.join(GOLD, "links.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_link_functions_match_golden(oracle, gold_links):
+    for a, b, x, lk, jac in gold_links["links"]:
+        if b is not None:      # two-sided: Uniform(a, b); the unit interval also through Beta (UnitDistribution, :83-93)
+            kinds = [("uniform", a, b, 0.0, 0.0)] + ([("beta", 2.0, 3.0, 0.0, 0.0)] if (a, b) == (0.0, 1.0) else [])
+        else:                  # lower bound only: a Normal truncated to [a, Inf); a = 0 also through the PositiveDistribution union (:66-78)
+            kinds = [("truncnormal", 0.3, 2.0, a, np.inf)] + ([("invgamma", 0.001, 0.001, 0.0, 0.0), ("gamma", 2.0, 3.0, 0.0, 0.0), ("exponential", 1.0, 0.0, 0.0, 0.0)] if a == 0.0 else [])
+        for kind, p1, p2, lo, hi in kinds:
+            got = oracle.link(kind, p1, p2, x, lo, hi)
+            np.testing.assert_allclose(got[0], lk, rtol=1e-12, atol=1e-14, err_msg=f"link {kind} {a} {b} {x}")
+            np.testing.assert_allclose(got[1], x, rtol=1e-9, atol=1e-12 * max(1.0, abs(a)), err_msg=f"invlink {kind} {a} {b} {x}")
+            np.testing.assert_allclose(got[2], jac, rtol=1e-12, atol=1e-14, err_msg=f"jacobian {kind} {a} {b} {x}")
+    # unbounded and discrete distributions: identity, no Jacobian (RealDistribution :53-61, fallbacks distributionstruct.jl:84,104,136)
+    for kind, p1, p2 in (("normal", 0.0, 2.0), ("laplace", 1.0, 2.0), ("binomial", 10.0, 0.3), ("poisson", 3.0, 0.0)):
+        np.testing.assert_array_equal(oracle.link(kind, p1, p2, 3.0), [3.0, 3.0, 0.0])
+    # the densities the new links come with, against scipy
+    import scipy.stats as st
+    for x in (0.0, 0.2, 7.0, 50.0, 50.1, -0.1):
+        np.testing.assert_allclose(oracle.udist_logpdf("uniform", 0.0, 50.0, x), st.uniform.logpdf(x, 0, 50), rtol=1e-14)
+    for x in (0.01, 0.4, 0.99):
+        np.testing.assert_allclose(oracle.udist_logpdf("beta", 2.5, 0.7, x), st.beta.logpdf(x, 2.5, 0.7), rtol=1e-12)
+    for x in (-0.5, 0.0, 0.3, 4.0):
+        np.testing.assert_allclose(oracle.udist_logpdf("truncnormal", 0.0, 1.3, x, 0.0, np.inf), st.truncnorm.logpdf(x, 0, np.inf, loc=0, scale=1.3), rtol=1e-13)
+        np.testing.assert_allclose(oracle.udist_logpdf("truncnormal", 1.0, 2.0, x, -0.25, 3.0), st.truncnorm.logpdf(x, (-0.25 - 1) / 2, (3 - 1) / 2, loc=1, scale=2), rtol=1e-13)
+
+
+def test_oracle_magnesium_block_densities_match_golden(oracle, gold_links):
+    S = np.array(gold_links["states"])
+    for key, (scheme, bi) in MAG_BLOCKS.items():
+        tpl, blocks, _ = helpers.scheme(scheme)
+        o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(blocks))
+        np.testing.assert_allclose(o.logpdf(bi, S), gold_links["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+    tpl, blocks, _ = helpers.scheme("magnesium_transformed")
+    o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(blocks))
+    for q, key in enumerate(["rcx", "rtx"]):
+        np.testing.assert_allclose(o.logpdf_nodes(1 << (4 + q), S), gold_links["logpdf"][key], rtol=1e-11)
+    # unlist(block, true): priors and mu on their link scales (log / two-sided logit), and the way back
+    np.testing.assert_allclose(np.stack([o.unlist(3, s) for s in S]), gold_links["unlist_priors_mu"], rtol=1e-11, atol=1e-13)
+    # monitored Logical columns tau[6], OR[6] at fixed states (a random walk of step 0 records unlist(m, true))
+    o2 = oracle.Oracle(tpl); o2.set_scheme(_oracle_blocks([dict(kind="rwm", nodes=[2], scale=0.0)]))
+    out, st_, _ = o2.run(len(S), S, 1, burnin=0, thin=1, seed=1)
+    assert o2.names() == [f"tau[{i}]" for i in range(1, 7)] + [f"OR[{i}]" for i in range(1, 7)]
+    np.testing.assert_allclose(out[0].T, gold_links["monitor"], rtol=1e-12)
+    # analytic gradient on the link scale (chain rule through the two-sided link) against central differences of the transformed density
+    for bi in (1, 3):
+        lp_a, g_a = o.gradlogpdf(bi, S, mode=0)
+        lp_c, g_c = o.gradlogpdf(bi, S, mode=2)
+        np.testing.assert_allclose(g_a, g_c, rtol=2e-5, atol=1e-5 * np.abs(g_c).max())
+    # out of the support: -Inf on the constrained scale (distributionstruct.jl:138-140)
+    tplc, blocksc, _ = helpers.scheme("magnesium")
+    oc = oracle.Oracle(tplc); oc.set_scheme(_oracle_blocks(blocksc))
+    x = np.array(S[0][:6]); x[1] = 50.5
+    assert np.isneginf(oc.logpdf(3, S[:1], x[None, :]))
+    x = np.array(S[0][60:]); x[7] = -0.01
+    assert np.isneginf(oc.logpdf(2, S[:1], x[None, :]))
+
+
+@pytest.mark.gpu
+def test_gpu_magnesium_block_densities_links_and_gradients_match_golden(oracle, gold_links):
+    from mambacuda.engine import Engine
+    S = np.array(gold_links["states"])
+    for key, (scheme, bi) in MAG_BLOCKS.items():
+        tpl, blocks, _ = helpers.scheme(scheme)
+        eng = Engine(tpl, 4); eng.set_scheme(blocks)
+        np.testing.assert_allclose(eng.logpdf(bi, S), gold_links["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        eng.close()
+    tpl, blocks, _ = helpers.scheme("magnesium_transformed")
+    eng = Engine(tpl, len(S)); eng.set_scheme(blocks)
+    nn, nf = eng.factor_counts()
+    assert (nn, nf) == (4, 6)
+    for q, key in enumerate(["rcx", "rtx"]):
+        np.testing.assert_allclose(eng.logpdf_nodes(1 << (nn + q), S), gold_links["logpdf"][key], rtol=1e-11)
+    # explicit block vectors on the link scale: invlink on the device must land on the golden states' densities
+    x = np.array(gold_links["unlist_priors_mu"])
+    np.testing.assert_allclose(eng.logpdf(3, S, x), gold_links["logpdf"]["priors_mu_transformed"], rtol=1e-10, atol=1e-9)
+    o = oracle.Oracle(tpl); o.set_scheme(_oracle_blocks(blocks))
+    for bi, k in ((1, 12), (3, 12), (2, 48)):
+        if blocks[bi]["kind"] == "slice_uni":
+            continue
+        lp_g, g_g = eng.gradlogpdf(bi, S, k)
+        lp_o, g_o = o.gradlogpdf(bi, S, mode=0)
+        np.testing.assert_allclose(lp_g, lp_o, rtol=1e-12)
+        np.testing.assert_allclose(g_g, g_o, rtol=1e-10, atol=1e-10)
+    eng2 = Engine(tpl, len(S)); eng2.set_scheme([dict(kind="rwm", nodes=[2], scale=0.0)]); eng2.set_inits(S)
+    out = eng2.run(1, burnin=0, thin=1)
+    np.testing.assert_allclose(out[0].T, gold_links["monitor"], rtol=1e-12)
+    # jitter on the link scale stays inside every support (two-sided links map back into (a, b))
+    eng2.set_inits(S, jitter_sd=2.0)
+    st_, _, _ = eng2.get_state()
+    assert (st_[:, 1:3] > 0).all() and (st_[:, 1:3] < 50).all() and (st_[:, 3:5] > 0).all() and (st_[:, 3:5] < 1).all()
+    assert (np.abs(st_[:, 6:12]) < 10).all() and (st_[:, 60:] > 0).all() and (st_[:, 60:] < 1).all() and (st_[:, [0, 5]] > 0).all()

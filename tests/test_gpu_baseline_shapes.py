@@ -63,13 +63,21 @@ def test_seeds_fused_kernel_at_the_baseline_shape(oracle):
 
 
 def test_seeds_reference_scheme_amm_at_the_baseline_shape(oracle):
-    # the reference's own scheme (AMM + AMWG + AMWG, doc/examples/seeds.jl:69-71) through the fused kernel, 125,000 chains
-    C, iters, burnin, thin = 125_000, 600, 300, 10
-    g, o, marg, _ = run_full_and_sample(oracle, "seeds_amm", C, iters, burnin, thin, 96, seed=7, jitter_sd=0.1)
-    # AMM's SigmaLm comes from Mvv - Mv Mv' (cancellation): its entries agree to fewer digits than the chain does
-    n_same, ties = helpers.audit_divergence(g, o, marg, kept_iterations(0, iters, burnin, thin), 0, tune_rtol=1e-4)
-    print(f"seeds AMM 125,000 x 600: {n_same}/96 reproduce the oracle; ties: {ties}")
-    assert n_same >= 92
+    # the reference's own scheme (AMM + AMWG + AMWG, doc/examples/seeds.jl:69-71) through the fused kernel, 125,000 chains.
+    # AMM's proposal at iteration t uses the factor cholfact(Sigma, Val{true}) computed at the end of an EARLIER iteration, and while a
+    # chain has hardly moved its running covariance is singular, so the rank / pivot decisions (amm.jl:88-91) are taken on rounding
+    # noise in the reference itself.  Hence per-step parity: state AND tune record (Mv, Mvv, SigmaLm) after every single step from the
+    # oracle's state; a differing step needs one of the oracle's decisions of THAT step — MH test, pivot choice or rank test, all
+    # noted as margins (samplers.hpp) — at rounding distance from its threshold.
+    from mambacuda.engine import Engine
+    C, seed = 125_000, 7
+    tpl, blocks, inits = helpers.scheme("seeds_amm")
+    eng = Engine(tpl, C, seed=seed); eng.set_scheme(blocks)
+    orc = oracle.Oracle(tpl); orc.set_scheme([helpers.oracle_block(b) for b in blocks])
+    ids = scattered_ids(C, 96)
+    compared, ties = helpers.resync_audit(eng, orc, ids, inits, 60, 0, seed, 0.1, rtol=1e-7, tie=1e-9, tune_rtol=1e-4)   # SigmaLm: Mvv - Mv Mv' cancels
+    print(f"seeds AMM 125,000 chains: {compared} single steps compared, {len(ties)} threshold ties: {ties[:6]}")
+    assert len(ties) <= 0.02 * compared
 
 
 def test_rats_fused_slice_amwg_kernel_at_the_baseline_shape(oracle):

@@ -771,3 +771,55 @@ def test_glm_tick_engine_with_tensor_core_gradient_is_statistically_equivalent(o
     a, b = res
     assert np.all(np.abs(a[:, 0] - b[:, 0]) < 4 * np.hypot(a[:, 3], b[:, 3]) + 1e-3)     # means within MCSE
     np.testing.assert_allclose(a[:, 1], b[:, 1], rtol=0.1)                                # posterior SDs
+
+
+# ---- magnesium: bounded (Uniform / truncated) priors and the two-sided link (transformdistribution.jl:6-48) ---------------------------
+def test_magnesium_trajectories_match_oracle(oracle):
+    # the script's own scheme (doc/examples/magnesium.jl:99-102): AMWG(mu) proposes on logit((mu + 10) / 20); the Slice blocks work on the
+    # constrained scale where proposals outside [0, 1] / [0, 50] have density -Inf and shrink the interval
+    g, o, _, _ = run_pair(oracle, "magnesium", 16, 300, 150, 2)
+    assert_same_run(g, o, 300, 150, 2)
+    out = g[0]
+    assert out.shape[1] == 12 and (out[:, :6, :] > 0).all() and (out[:, 6:, :] > 0).all()
+
+
+def test_magnesium_steps_on_the_link_scale_match_oracle(oracle):
+    # every block on the link scale, incl. NUTS over (priors, mu): log links, two-sided links and their Jacobians in the gradient
+    resync(oracle, "magnesium_transformed", 16, 40, 30, seed=5, rtol=1e-7, tie=1e-7)
+
+
+def test_magnesium_densities_and_predict_match_oracle(oracle):
+    from mambacuda.engine import Engine
+    tpl, blocks, inits = helpers.scheme("magnesium_transformed")
+    eng = Engine(tpl, 64, seed=3); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.5)
+    st, _, _ = eng.get_state()                                   # jittered on the link scale: inside every support
+    orc = oracle.Oracle(tpl); orc.set_scheme([helpers.oracle_block(b) for b in blocks])
+    _, st_o, _ = orc.run(64, inits, 1, burnin=0, thin=1, seed=3, jitter_sd=0.5, partial=True)
+    rng = np.random.default_rng(2)
+    for b in range(4):
+        np.testing.assert_allclose(eng.logpdf(b, st), orc.logpdf(b, st), rtol=RTOL_LP, atol=1e-12)
+        x = np.stack([orc.unlist(b, s) for s in st]) + rng.normal(scale=0.1, size=(64, orc.unlist(b, st[0]).size))
+        np.testing.assert_allclose(eng.logpdf(b, st, x), orc.logpdf(b, st, x), rtol=RTOL_LP, atol=1e-12)
+    nn, nf = eng.factor_counts()
+    for mask in (1 << nn, 1 << (nn + 1), (1 << nf) - 1, 1, 2, 8):
+        np.testing.assert_allclose(eng.logpdf_nodes(mask, st), orc.logpdf_nodes(mask, st), rtol=RTOL_LP, atol=1e-12)
+    g = eng.predict(st, stream_id=5); o = orc.predict(st, 3, stream_id=5)
+    assert g.shape == o.shape == (64, 96) and (g == o).mean() > 0.999
+
+
+def test_magnesium_posterior_matches_published_table(oracle):
+    # doc/examples/magnesium.rst:45-57 (2 x 12,500, burnin 2,500, thin 2): mean, MCSE, SD
+    from mambacuda.engine import Engine
+    ref = {"tau[1]": (0.55098858, 0.0221, 0.358), "tau[2]": (1.11557619, 0.0238, 0.589), "tau[3]": (0.83211110, 0.0223, 0.491), "tau[4]": (0.47864203, 0.0136, 0.263),
+           "tau[5]": (0.48624861, 0.0215, 0.354), "tau[6]": (0.56841884, 0.0059, 0.189), "OR[1]": (0.47784058, 0.0067, 0.154), "OR[2]": (0.42895913, 0.0081, 0.322),
+           "OR[3]": (0.43118350, 0.0064, 0.183), "OR[4]": (0.47587697, 0.0065, 0.139), "OR[5]": (0.48545299, 0.0084, 0.146), "OR[6]": (0.44554385, 0.0054, 0.141)}
+    tpl, blocks, inits = helpers.scheme("magnesium")
+    eng = Engine(tpl, 512, seed=14); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.02)
+    eng.run(12500, burnin=2500, thin=2, store=False, out=False)
+    summ = eng.summary_streaming(); names = eng.names(1)
+    for nm, (mean, mcse_ref, sd) in ref.items():
+        j = names.index(nm)
+        assert abs(summ[j, 0] - mean) < 3 * np.hypot(mcse_ref, summ[j, 3]) + 0.02 * sd, (nm, summ[j, 0], mean)
+    codes = eng.link_codes(True)        # tau, OR are Logical columns > 0 (tau[4..6] and the ORs also exceed 1 somewhere): log link
+    assert (codes[:3] == 1).all()
+    assert (eng.gelman(0.05, True)[:, 0] < 1.1).all()

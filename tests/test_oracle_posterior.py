@@ -175,3 +175,18 @@ def test_pumps_reference_scheme(oracle):
     o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
     out, _, _ = o.run(8, inits, 10000, burnin=2500, thin=2, seed=3, nthreads=8)
     within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), ref)
+
+
+MAGNESIUM_TABLE = {   # doc/examples/magnesium.rst:45-57: mean, MCSE
+    "tau[1]": (0.55098858, 0.0221132365), "tau[2]": (1.11557619, 0.0237788755), "tau[3]": (0.83211110, 0.0222839957), "tau[4]": (0.47864203, 0.0135868530),
+    "tau[5]": (0.48624861, 0.0215005369), "tau[6]": (0.56841884, 0.0058505056), "OR[1]": (0.47784058, 0.0066922017), "OR[2]": (0.42895913, 0.0081170895),
+    "OR[3]": (0.43118350, 0.0064385836), "OR[4]": (0.47587697, 0.0064893426), "OR[5]": (0.48545299, 0.0083912319), "OR[6]": (0.44554385, 0.0053818401)}
+
+
+def test_magnesium_reference_scheme(oracle):
+    # doc/examples/magnesium.jl:99-107 (AMWG(theta) + AMWG(mu) [Uniform(-10, 10) on the two-sided link] + Slice(pc) + Slice(priors), 2 x 12,500,
+    # burnin 2,500, thin 2), table doc/examples/magnesium.rst:45-57; here 8 chains x 5,000 (the interpreted 108-element model is slow)
+    tpl, blocks, inits = helpers.scheme("magnesium")
+    o = oracle.Oracle(tpl); o.set_scheme([helpers.oracle_block(b) for b in blocks])
+    out, _, _ = o.run(8, inits, 5000, burnin=1500, thin=2, seed=21, nthreads=8)
+    within_3_mcse(oracle.summarystats(out, 0, 100), o.names(), MAGNESIUM_TABLE)
