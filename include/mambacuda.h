@@ -98,6 +98,10 @@ enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1, MCU_ETYPE_IPSE = 2 };              
 #define MCU_RUN_PARTIAL 8u       /* this call is one segment of a longer mcmc() run driven by the caller (burn-in may extend past it):
                                     skips the "burnin is greater than or equal to iters" check of mcmc.jl:22-23 */
 
+#define MCU_RUN_ASYNC 16u        /* queue the run on the handle's stream and return (out must be NULL); complete it with mcu_wait.  One host thread can
+                                    then drive a handle per GPU concurrently, as pmap2 drives a worker per chain (src/model/mcmc.jl:48-52, src/utils.jl:91-98).
+                                    (The GLM / NUTS tick engine is host-driven and returns only when done.) */
+
 #define MCU_MAX_BLOCK_NODES 8
 
 /*
@@ -169,6 +173,11 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
  * kept = number of kept iterations inside this call.                                          */
 int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* out, uint32_t flags);
 int64_t mcu_kept(int64_t first_iter, int64_t iters, int64_t burnin, int64_t thin);
+/* Completes an MCU_RUN_ASYNC run (no-op otherwise): blocks until the handle's stream is idle; device-side failures are reported here. */
+int mcu_wait(mcu_handle h);
+/* ModelChains.value of the last mcu_run, [kept × n_monitor × n_chains] column-major (src/Mamba.jl:172-185), for callers that passed
+ * out = NULL (asynchronous runs; pinned destination buffers: the copy then runs at full PCIe rate without a bounce buffer).        */
+int mcu_get_samples(mcu_handle h, double* out);
 
 /* ---- ModelState round trip (src/Mamba.jl:152-155; mcmc.jl:56,82) --------------------------- */
 /* values [n_chains × D], tune [n_chains × tune_size] (may be NULL), iter = model.iter.        */
@@ -272,6 +281,33 @@ int mcu_chains_summarystats(const double* value, int64_t n, int p, int64_t m, in
 int mcu_chains_geweke(const double* value, int64_t n, int p, int64_t m, double first, double last, int etype, int batch_size, double* out);
 int mcu_chains_heidel(const double* value, int64_t n, int p, int64_t m, double alpha, double eps, int etype, int batch_size, int64_t start, double* out);
 int mcu_chains_raftery(const double* value, int64_t n, int p, int64_t m, double q, double r, double s, double eps, int64_t range_start, int64_t range_step, double* out);
+
+/* ---- diagnostics over chains that live on several handles / GPUs -------------------------------------
+ * The reference farms chains out to workers and gathers every sample (pmap2(mcmc_worker!, lsts), src/model/mcmc.jl:48-59) before
+ * gelmandiag (src/output/gelmandiag.jl:3-60) and summarystats (src/output/stats.jl:85-94) run on the gathered array.  Here every
+ * handle reduces its own chains on the device and a packed two-round protocol carries O(p) doubles between handles
+ * (mamba.jl_b200/csrc/diagproto.hpp):
+ *   round 1 buffer [min p | max p | sum 9p]  — all-reduce the three parts with MIN / MAX / SUM;
+ *   round 2 buffer [15p]                     — all-reduce with SUM (centred gelman sums + centred summary sums per column).
+ * ANY transport can carry the buffers (mcu_diag_round1 → reduce → mcu_diag_round2 → reduce → mcu_diag_finish: Julia worker messaging,
+ * MPI, torch.distributed); the built-in transport is NCCL over NVLink: mcu_comm_unique_id on rank 0, the 128-byte id handed to the other
+ * ranks by the host language, mcu_comm_init on every rank's handle, then mcu_diag_global does both rounds on the device (reductions,
+ * all-reduces and the plan kernel queued back to back on the handle's stream, one synchronisation).  NCCL is bound at run time
+ * (dlopen of libnccl.so.2, or $MCU_NCCL_LIB): a process that never asks for a communicator does not need it.
+ * Without a communicator mcu_diag_global covers this handle's chains (one call instead of mcu_gelman + mcu_summary_streaming).      */
+typedef struct mcu_nccl_id { char internal[128]; } mcu_nccl_id;     /* == ncclUniqueId */
+int mcu_diag_sizes(int p, int* n_round1, int* n_round2);
+int mcu_monitor_links(mcu_handle h, int* monlink /* [p]: 0 identity, 1 log, -1 Logical column (data-dependent heuristic) */);
+int mcu_n_kept(mcu_handle h, int64_t* n_kept);
+int mcu_diag_round1(mcu_handle h, double* buf /* [11p] */);
+int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1 /* [11p] */, double* buf2 /* [15p] */);
+/* psrf [p × 2] (not rounded), summary [p × 5] = mean, SD, naive SE, MCSE (batch means of 100), ESS; codes [p] = link code used; each may be NULL */
+int mcu_diag_finish(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* reduced1,
+                    const double* reduced2, double* psrf, double* summary, int* codes);
+int mcu_comm_unique_id(mcu_nccl_id* id);
+int mcu_comm_init(mcu_handle h, int rank, int nranks, const mcu_nccl_id* id);
+int mcu_comm_size(mcu_handle h, int* rank, int* nranks);
+int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes);
 
 /* ---- RNG contract ----------------------------------------------------- */
 /* PHILOX: Philox4x32-10, key = seed, counter = (k >> 1, iteration, global chain, block | kind << 16 | stream << 24).

@@ -14,7 +14,10 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/mambacuda.h"
+#include "diagproto.hpp"
 #include "hostdiag.hpp"
 #include "launch.hpp"
 
@@ -74,6 +77,11 @@ struct mcu_ctx {
   double g_lp_const = 0.0;
   unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
+  bool pending = false;   // an mcu_run(..., MCU_RUN_ASYNC) has not been waited for yet
+  // cross-GPU diagnostics (mcu_comm_init / mcu_diag_global): NCCL communicator of this handle's rank, monitored-column links on the device
+  void* comm = nullptr; int comm_rank = 0, comm_nranks = 1;
+  int* d_monlink = nullptr; std::vector<int> h_monlink;
+  unsigned long long logit_mask = 0ull;
 };
 
 namespace {
@@ -603,6 +611,88 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
   return MCU_OK;
 }
 
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------------------------------
+// libmambacuda.so has no link-time dependency on NCCL: the library is looked up when a communicator is first asked for
+// (dlopen finds the copy the host process already loaded, e.g. torch's, else the system one), so single-GPU users need no NCCL at all.
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, mcu_nccl_id, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;   // ncclDataType_t / ncclRedOp_t values of nccl.h (stable ABI)
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) return &api;
+  const char* names[] = {std::getenv("MCU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) { api.err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return &api; }
+  auto sym = [&](const char* n) { void* f = dlsym(api.lib, n); if (!f && api.err.empty()) api.err = std::string("NCCL symbol missing: ") + n; return f; };
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, mcu_nccl_id, int)>(sym("ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclAllReduce"));
+  api.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+  if (!api.err.empty()) { dlclose(api.lib); api.lib = nullptr; }
+  return &api;
+}
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    const int r_ = (call);                                                                         \
+    if (r_ != 0) {                                                                                 \
+      h->err = std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "NCCL error"); \
+      return MCU_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+// device scratch of the two-round protocol: [partials | round-1 buffer 11P | plan 5P | round-2 buffer 15P]
+struct DiagBufs { double* partial; double* r1; double* plan; double* r2; };
+int diag_bufs(mcu_ctx* h, DiagBufs* b) {
+  const long long nblk = grid_for(h->C, 128);
+  const size_t P = (size_t)h->P;
+  const size_t need = sizeof(double) * ((size_t)nblk * P * kDiag2 + P * (kDiag1 + 5 + kDiag2)) + 64;
+  if (need > h->diag_cap) {
+    if (h->d_diag) cudaFree(h->d_diag);
+    h->d_diag = nullptr; h->diag_cap = 0;
+    if (cudaMalloc(&h->d_diag, need) != cudaSuccess) return fail(h, MCU_ERR_CUDA, "cudaMalloc(diagnostics scratch) failed");
+    h->diag_cap = need;
+  }
+  b->partial = static_cast<double*>(h->d_diag);
+  b->r1 = b->partial + (size_t)nblk * P * kDiag2;
+  b->plan = b->r1 + P * kDiag1;
+  b->r2 = b->plan + P * 5;
+  return MCU_OK;
+}
+int diag_finish_host(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* r1, const double* r2,
+                     double* psrf, double* summary, int* codes_out) {
+  for (int j = 0; j < p; ++j) {
+    double ctr[4];
+    const int code = diag_plan_column(p, j, monlink[j], transform, r1, ctr);
+    if (code == 2 && j >= 64) return MCU_ERR_UNSUPPORTED;   // logit moments are streamed for the first 64 columns only
+    if (codes_out) codes_out[j] = code;
+    const double* s = r2 + (size_t)j * kDiag2;
+    if (psrf) {
+      if (s[0] < 2.0) return MCU_ERR_ARG;                    // "less than 2 chains supplied to gelman diagnostic": gelmandiag.jl:6-7
+      hostdiag::gelman_column((double)n_kept, ctr[0], ctr[1], s, alpha, psrf + j * 2);
+    }
+    if (summary) hostdiag::summary_column((double)n_kept, ctr[2], ctr[3], s + 7, summary + j * 5);
+  }
+  return MCU_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -649,6 +739,8 @@ int mcu_destroy(mcu_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
+  if (h->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(h->comm);
+  cudaFree(h->d_monlink);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
   cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ebound_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->d_diag); cudaFree(h->r_scratch); free_glm_data(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
@@ -807,6 +899,11 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   CK(cudaMalloc(&h->d_ebound_state, sizeof(double) * 2 * h->D));
   CK(cudaMemcpy(h->d_ebound_state, t.ebound.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice));
   h->h_scales = h_scales; h->h_SigmaL = h_SigmaL;
+  h->h_monlink = t.monlink; h->logit_mask = 0ull;
+  for (int j = 0; j < h->P && j < 64; ++j) if (t.monlink[j] == LINK_HEUR) h->logit_mask |= 1ull << j;
+  cudaFree(h->d_monlink); h->d_monlink = nullptr;
+  CK(cudaMalloc(&h->d_monlink, sizeof(int) * std::max(1, h->P)));
+  CK(cudaMemcpy(h->d_monlink, t.monlink.data(), sizeof(int) * h->P, cudaMemcpyHostToDevice));
   h->seeds_fast_ok = scheme_is_seeds_fast(h);
   h->rats_warp_ok = scheme_is_rats_warp(h);
   h->rats_fast_ok = scheme_is_rats_fast(h);
@@ -888,8 +985,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.n_blocks = (int)h->h_blocks.size(); a.D = h->D; a.P = h->P; a.blocks = h->d_blocks;
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
-  a.logit_mask = 0ull;
-  { const TplInfo ti = tpl_info(h); for (int j = 0; j < h->P && j < 64; ++j) if (ti.monlink[j] == LINK_HEUR) a.logit_mask |= 1ull << j; }
+  a.logit_mask = h->logit_mask;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
   bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
@@ -945,25 +1041,50 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     done += n;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
+  h->iter += iters;
+  h->pending = true;
+  if (flags & MCU_RUN_ASYNC) {
+    if (out) return fail(h, MCU_ERR_ARG, "MCU_RUN_ASYNC returns before the samples exist: pass out = NULL and fetch them with mcu_get_samples");
+    return MCU_OK;
+  }
+  rc = mcu_wait(h); if (rc) return rc;
+  if (out && kept > 0) return mcu_get_samples(h, out);
+  return MCU_OK;
+}
+
+// Completes an mcu_run(..., MCU_RUN_ASYNC): blocks until the handle's stream is idle and reports what the run left behind.
+int mcu_wait(mcu_handle h) {
+  if (!h) return MCU_ERR_ARG;
+  if (!h->pending) return MCU_OK;
+  CK(cudaSetDevice(h->device));
+  h->pending = false;
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
-  h->iter += iters;
   if (h->rng_mode == MCU_RNG_EXTERNAL) {   // a shim stream that ran dry would silently feed constant draws: report it
+    const size_t C = (size_t)h->C;
     std::vector<unsigned long long> pos(C);
     CK(cudaMemcpy(pos.data(), h->d_ext_pos, sizeof(unsigned long long) * C, cudaMemcpyDeviceToHost));
     for (size_t c = 0; c < C; ++c) if (pos[c] == ~0ull) return fail(h, MCU_ERR_STATE, "external uniform stream exhausted (chain " + std::to_string(c) + "): supply more draws per chain");
   }
-  if (out && kept > 0) {
-    double* d_out = nullptr;   // handle-lifetime staging buffer: no cudaMalloc / cudaFree on the hot call
-    const size_t total = (size_t)kept * h->P * C;
-    rc = stage(h, sizeof(double) * total, (void**)&d_out); if (rc) return rc;
-    launch_samples_to_julia(h->d_samples, d_out, kept, h->P, h->C, h->stream);
-    h->launches++;
-    CK(cudaMemcpyAsync(out, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaGetLastError());
-  }
+  return MCU_OK;
+}
+
+// ModelChains.value of the last mcu_run ([kept x n_monitor x n_chains], column-major): device transpose into the handle's staging
+// buffer (no allocation on the hot call) and one D2H copy — give it pinned memory for an asynchronous, full-rate transfer.
+int mcu_get_samples(mcu_handle h, double* out) {
+  if (!h || !out) return MCU_ERR_ARG;
+  int rc = mcu_wait(h); if (rc) return rc;
+  if (h->samples_kept < 1 || !h->d_samples) return fail(h, MCU_ERR_STATE, "no stored samples (run without MCU_RUN_NO_STORE)");
+  CK(cudaSetDevice(h->device));
+  double* d_out = nullptr;
+  const size_t total = (size_t)h->samples_kept * h->P * (size_t)h->C;
+  rc = stage(h, sizeof(double) * total, (void**)&d_out); if (rc) return rc;
+  launch_samples_to_julia(h->d_samples, d_out, h->samples_kept, h->P, h->C, h->stream);
+  h->launches++;
+  CK(cudaMemcpyAsync(out, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
   return MCU_OK;
 }
 
@@ -1332,6 +1453,115 @@ int mcu_chains_summarystats(const double* value, int64_t n, int p, int64_t m, in
   if (!value || !out || n < 1 || p < 1 || m < 1 || etype < MCU_ETYPE_BM || etype > MCU_ETYPE_IPSE) return MCU_ERR_ARG;
   if (batch_size < 1) batch_size = 100;
   return hostdiag::chains_summarystats(value, n, p, m, etype, batch_size, out) ? MCU_ERR_ARG : MCU_OK;
+}
+
+// ---- cross-handle diagnostics: the packed two-round protocol (diagproto.hpp) ---------------------------------------------------------
+int mcu_diag_sizes(int p, int* n_round1, int* n_round2) {
+  if (p < 1) return MCU_ERR_ARG;
+  if (n_round1) *n_round1 = p * kDiag1;
+  if (n_round2) *n_round2 = p * kDiag2;
+  return MCU_OK;
+}
+int mcu_monitor_links(mcu_handle h, int* monlink) {
+  if (!h || !monlink) return MCU_ERR_ARG;
+  if (h->h_monlink.empty()) return fail(h, MCU_ERR_STATE, "set the sampling scheme first");
+  for (int j = 0; j < h->P; ++j) monlink[j] = h->h_monlink[j];
+  return MCU_OK;
+}
+int mcu_diag_round1(mcu_handle h, double* buf) {
+  if (!h || !buf) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  DiagBufs b; int rc = diag_bufs(h, &b); if (rc) return rc;
+  launch_diag1(h->d_mom, h->d_momn, h->C, h->P, h->logit_mask, b.partial, b.r1, h->stream); h->launches += 2;
+  CK(cudaMemcpyAsync(buf, b.r1, sizeof(double) * h->P * kDiag1, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1, double* buf2) {
+  if (!h || !reduced1 || !buf2) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  DiagBufs b; int rc = diag_bufs(h, &b); if (rc) return rc;
+  CK(cudaMemcpyAsync(b.r1, reduced1, sizeof(double) * h->P * kDiag1, cudaMemcpyHostToDevice, h->stream));
+  launch_diag_plan(b.r1, h->d_monlink, transform, h->P, b.plan, h->stream);
+  launch_diag2(h->d_mom, h->d_momn, h->C, h->P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
+  CK(cudaMemcpyAsync(buf2, b.r2, sizeof(double) * h->P * kDiag2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return MCU_OK;
+}
+int mcu_diag_finish(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* reduced1, const double* reduced2,
+                    double* psrf, double* summary, int* codes) {
+  if (p < 1 || !monlink || !reduced1 || !reduced2) return MCU_ERR_ARG;
+  return diag_finish_host(n_kept, p, alpha, monlink, transform, reduced1, reduced2, psrf, summary, codes);
+}
+int mcu_n_kept(mcu_handle h, int64_t* n_kept) {
+  if (!h || !n_kept) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  double n0 = 0; CK(cudaMemcpy(&n0, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost));
+  *n_kept = (int64_t)n0;
+  return MCU_OK;
+}
+
+// ---- built-in transport: NCCL over NVLink (one rank per handle; replaces the gather of pmap2(mcmc_worker!, ...), mcmc.jl:48-59) ------
+int mcu_comm_unique_id(mcu_nccl_id* id) {
+  if (!id) return MCU_ERR_ARG;
+  NcclApi* n = nccl_api();
+  if (!n->lib) { g_create_err = n->err; return MCU_ERR_UNSUPPORTED; }
+  return n->GetUniqueId(id) == 0 ? MCU_OK : MCU_ERR_CUDA;
+}
+int mcu_comm_init(mcu_handle h, int rank, int nranks, const mcu_nccl_id* id) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return h ? fail(h, MCU_ERR_ARG, "bad rank / nranks / id") : MCU_ERR_ARG;
+  NcclApi* n = nccl_api();
+  if (!n->lib) return fail(h, MCU_ERR_UNSUPPORTED, n->err);
+  CK(cudaSetDevice(h->device));
+  if (h->comm) { n->CommDestroy(h->comm); h->comm = nullptr; }
+  NK(n->CommInitRank(&h->comm, nranks, *id, rank));
+  h->comm_rank = rank; h->comm_nranks = nranks;
+  return MCU_OK;
+}
+int mcu_comm_size(mcu_handle h, int* rank, int* nranks) {
+  if (!h) return MCU_ERR_ARG;
+  if (rank) *rank = h->comm_rank;
+  if (nranks) *nranks = h->comm ? h->comm_nranks : 1;
+  return MCU_OK;
+}
+// gelmandiag + summarystats over the chains of EVERY rank of the communicator (of this handle alone without one): both protocol rounds
+// stay on the device — reductions, NCCL all-reduces (round 1: MIN / MAX / SUM in one group; round 2: SUM) and the plan kernel are queued
+// on the handle's stream back to back; one synchronisation, then O(p) host arithmetic (F quantile etc., hostdiag.hpp).
+int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes) {
+  if (!h || (!psrf && !summary && !codes)) return MCU_ERR_ARG;
+  if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
+  CK(cudaSetDevice(h->device));
+  const int P = h->P;
+  DiagBufs b; int rc = diag_bufs(h, &b); if (rc) return rc;
+  launch_diag1(h->d_mom, h->d_momn, h->C, P, h->logit_mask, b.partial, b.r1, h->stream); h->launches += 2;
+  NcclApi* n = h->comm ? nccl_api() : nullptr;
+  if (n) {
+    NK(n->GroupStart());
+    NK(n->AllReduce(b.r1, b.r1, (size_t)P, kNcclFloat64, kNcclMin, h->comm, h->stream));
+    NK(n->AllReduce(b.r1 + P, b.r1 + P, (size_t)P, kNcclFloat64, kNcclMax, h->comm, h->stream));
+    NK(n->AllReduce(b.r1 + 2 * P, b.r1 + 2 * P, (size_t)P * kDiagSum1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    NK(n->GroupEnd());
+  }
+  launch_diag_plan(b.r1, h->d_monlink, transform, P, b.plan, h->stream);
+  launch_diag2(h->d_mom, h->d_momn, h->C, P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
+  if (n) NK(n->AllReduce(b.r2, b.r2, (size_t)P * kDiag2, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  std::vector<double> host((size_t)P * (kDiag1 + kDiag2) + 1);
+  CK(cudaMemcpyAsync(host.data(), b.r1, sizeof(double) * P * kDiag1, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(host.data() + (size_t)P * kDiag1, b.r2, sizeof(double) * P * kDiag2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(host.data() + (size_t)P * (kDiag1 + kDiag2), h->d_momn, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  const int64_t n_kept = (int64_t)host[(size_t)P * (kDiag1 + kDiag2)];
+  if (psrf && n_kept < 2) return fail(h, MCU_ERR_STATE, "fewer than 2 kept samples per chain");
+  rc = diag_finish_host(n_kept, P, alpha, h->h_monlink.data(), transform, host.data(), host.data() + (size_t)P * kDiag1, psrf, summary, codes);
+  if (rc == MCU_ERR_UNSUPPORTED) return fail(h, rc, "logit link beyond monitored column 64 needs stored samples");
+  if (rc == MCU_ERR_ARG) return fail(h, rc, "less than 2 chains supplied to gelman diagnostic");
+  return rc;
 }
 
 double mcu_fp64_peak_tflops(mcu_handle h) {

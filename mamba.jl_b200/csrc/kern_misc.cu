@@ -1,5 +1,6 @@
 // kern_misc.cu — initialisation, layout transposes and the cross-chain reduction kernels.
 #include "launch.hpp"
+#include "diagproto.hpp"
 
 namespace mcu {
 
@@ -124,6 +125,105 @@ __global__ void summary_partial_kernel(const double* mom, const double* momn, lo
       __syncthreads();
     }
   }
+}
+
+// ---- packed two-round diagnostics protocol (diagproto.hpp) ---------------------------------------------
+// block-level reduction of one value per thread (128 threads): op 0 = sum, 1 = min, 2 = max
+__device__ __forceinline__ double block_reduce128(double v, int op, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const double a = sh[threadIdx.x], b = sh[threadIdx.x + off];
+      sh[threadIdx.x] = op == 0 ? a + b : op == 1 ? fmin(a, b) : fmax(a, b);
+    }
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__global__ void diag1_partial_kernel(const double* mom, const double* momn, long long C, int P, unsigned long long logit_mask,
+                                     double* partial /*[grid][P][11]*/) {
+  __shared__ double sh[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = c < C;
+  const double n = on ? momn[c] : 2.0, nb = on ? momn[2 * C + c] : 0.0;
+  for (int j = 0; j < P; ++j) {
+    const double* q = mom + (size_t)j * kMomPerCol * C + c;
+    double v[kDiag1];
+    v[0] = on ? q[4 * C] : CUDART_INF; v[1] = on ? q[5 * C] : -CUDART_INF;
+    const bool lg = j < 64 && ((logit_mask >> j) & 1ull);
+    v[2] = on ? 1.0 : 0.0;
+    v[3] = on ? q[0 * C] : 0.0; v[4] = on ? q[1 * C] / (n - 1.0) : 0.0;
+    v[5] = on ? q[2 * C] : 0.0; v[6] = on ? q[3 * C] / (n - 1.0) : 0.0;
+    v[7] = (on && lg) ? q[9 * C] : 0.0; v[8] = (on && lg) ? q[10 * C] / (n - 1.0) : 0.0;
+    v[9] = nb; v[10] = on ? nb * q[7 * C] : 0.0;
+    for (int k = 0; k < kDiag1; ++k) {
+      const double r = block_reduce128(v[k], k == 0 ? 1 : k == 1 ? 2 : 0, sh);
+      if (threadIdx.x == 0) partial[((size_t)blockIdx.x * P + j) * kDiag1 + k] = r;
+    }
+  }
+}
+// fold of the round-1 partials into the protocol layout [min P | max P | sum 9P]
+__global__ void diag1_fold_kernel(const double* partial, long long nblocks, int P, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * kDiag1) return;
+  const int j = i / kDiag1, k = i % kDiag1;
+  double r = k == 0 ? CUDART_INF : k == 1 ? -CUDART_INF : 0.0;
+  for (long long b = 0; b < nblocks; ++b) {
+    const double x = partial[(size_t)b * P * kDiag1 + i];
+    r = k == 0 ? fmin(r, x) : k == 1 ? fmax(r, x) : r + x;
+  }
+  out[k == 0 ? j : k == 1 ? P + j : 2 * P + j * kDiagSum1 + (k - 2)] = r;
+}
+// plan[j] = { code, c1, c2, k1, k2 } from the all-reduced round-1 buffer
+__global__ void diag_plan_kernel(const double* r1, const int* monlink, int transform, int P, double* plan) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  double ctr[4];
+  const int code = diag_plan_column(P, j, monlink[j], transform, r1, ctr);
+  plan[j * 5 + 0] = (double)code; plan[j * 5 + 1] = ctr[0]; plan[j * 5 + 2] = ctr[1]; plan[j * 5 + 3] = ctr[2]; plan[j * 5 + 4] = ctr[3];
+}
+__global__ void diag2_partial_kernel(const double* mom, const double* momn, long long C, int P, const double* plan,
+                                     double* partial /*[grid][P][15]*/) {
+  __shared__ double sh[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = c < C;
+  const double n = on ? momn[c] : 2.0, nb = on ? momn[2 * C + c] : 0.0;
+  for (int j = 0; j < P; ++j) {
+    const double* q = mom + (size_t)j * kMomPerCol * C + c;
+    const int code = (int)plan[j * 5];
+    const double c1 = plan[j * 5 + 1], c2 = plan[j * 5 + 2], k1 = plan[j * 5 + 3], k2 = plan[j * 5 + 4];
+    double v[kDiag2];
+    for (int k = 0; k < kDiag2; ++k) v[k] = 0.0;
+    if (on) {
+      const double psibar = code == 2 ? q[9 * C] : code == 1 ? q[2 * C] : q[0 * C];
+      const double s2 = (code == 2 ? q[10 * C] : code == 1 ? q[3 * C] : q[1 * C]) / (n - 1.0);
+      const double d = psibar - c1, e = s2 - c2;
+      v[0] = 1.0; v[1] = d; v[2] = d * d; v[3] = e; v[4] = e * e; v[5] = e * d; v[6] = e * d * d;
+      const double mean = q[0 * C], bmean = q[7 * C];
+      v[7] = 1.0; v[8] = mean; v[9] = q[1 * C]; v[10] = (mean - k1) * (mean - k1);
+      v[11] = nb; v[12] = nb * bmean; v[13] = q[8 * C]; v[14] = nb * (bmean - k2) * (bmean - k2);
+    }
+    for (int k = 0; k < kDiag2; ++k) {
+      const double r = block_reduce128(v[k], 0, sh);
+      if (threadIdx.x == 0) partial[((size_t)blockIdx.x * P + j) * kDiag2 + k] = r;
+    }
+  }
+}
+void launch_diag1(const double* mom, const double* momn, long long C, int P, unsigned long long logit_mask, double* partial, double* out, cudaStream_t st) {
+  const long long nblk = (C + 127) / 128;
+  diag1_partial_kernel<<<(unsigned)nblk, 128, 0, st>>>(mom, momn, C, P, logit_mask, partial);
+  diag1_fold_kernel<<<(unsigned)((P * kDiag1 + 127) / 128), 128, 0, st>>>(partial, nblk, P, out);
+}
+void launch_diag_plan(const double* r1, const int* monlink, int transform, int P, double* plan, cudaStream_t st) {
+  diag_plan_kernel<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(r1, monlink, transform, P, plan);
+}
+void launch_diag2(const double* mom, const double* momn, long long C, int P, const double* plan, double* partial, double* out, cudaStream_t st) {
+  const long long nblk = (C + 127) / 128;
+  diag2_partial_kernel<<<(unsigned)nblk, 128, 0, st>>>(mom, momn, C, P, plan, partial);
+  fold_kernel<<<(unsigned)((P * kDiag2 + 127) / 128), 128, 0, st>>>(partial, nblk, P * kDiag2, out);
 }
 
 

@@ -70,6 +70,11 @@ void launch_minmax_partial(const double* mom, long long C, int P, double* partia
 void launch_summary_partial(const double* mom, const double* momn, long long C, int P, const double* center,
                             double* partial, cudaStream_t st);
 
+// packed two-round diagnostics protocol (diagproto.hpp): round-1 reductions into [min P | max P | sum 9P], plan, round-2 reductions (15 P)
+void launch_diag1(const double* mom, const double* momn, long long C, int P, unsigned long long logit_mask, double* partial, double* out, cudaStream_t st);
+void launch_diag_plan(const double* r1, const int* monlink, int transform, int P, double* plan, cudaStream_t st);
+void launch_diag2(const double* mom, const double* momn, long long C, int P, const double* plan, double* partial, double* out, cudaStream_t st);
+
 double measure_fp64_peak_tflops(cudaStream_t st);
 
 // fused seeds/AMWG kernel (seeds_fast.cu); returns 0 on success

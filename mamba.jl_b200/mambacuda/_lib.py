@@ -16,7 +16,7 @@ KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc":
 ADAPT = {"all": 0, "burnin": 1, "none": 2}
 PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2, "cosine": 3, "epanechnikov": 4, "biweight": 5, "triweight": 6}
 GRAD = {"analytic": 0, "forward": 1, "central": 2}
-RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE, RUN_PARTIAL = 1, 2, 4, 8
+RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE, RUN_PARTIAL, RUN_ASYNC = 1, 2, 4, 8, 16
 
 
 class BlockDesc(C.Structure):
@@ -49,6 +49,8 @@ SYMBOLS = [
     "mcu_launch_count", "mcu_last_kernel_ms", "mcu_fp64_peak_tflops",
     "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
     "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery", "mcu_chains_summarystats", "mcu_factor_counts", "mcu_factor_parents", "mcu_logpdf_nodes", "mcu_predict",
+    "mcu_diag_sizes", "mcu_monitor_links", "mcu_n_kept", "mcu_diag_round1", "mcu_diag_round2", "mcu_diag_finish",
+    "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_size", "mcu_diag_global", "mcu_wait", "mcu_get_samples",
 ]
 
 
@@ -110,5 +112,17 @@ def lib():
     L.mcu_logpdf_nodes.argtypes = [C.c_void_p, C.c_uint32, i64, dp, dp]
     L.mcu_predict.argtypes = [C.c_void_p, i64, dp, C.c_uint32, dp, C.POINTER(i64)]
     L.mcu_chains_summarystats.argtypes = [dp, i64, C.c_int, i64, C.c_int, C.c_int, dp]
+    L.mcu_diag_sizes.argtypes = [C.c_int, ip, ip]
+    L.mcu_monitor_links.argtypes = [vp, ip]
+    L.mcu_n_kept.argtypes = [vp, C.POINTER(i64)]
+    L.mcu_diag_round1.argtypes = [vp, dp]
+    L.mcu_diag_round2.argtypes = [vp, C.c_int, dp, dp]
+    L.mcu_diag_finish.argtypes = [i64, C.c_int, C.c_double, ip, C.c_int, dp, dp, dp, dp, ip]
+    L.mcu_comm_unique_id.argtypes = [C.c_char_p]
+    L.mcu_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.mcu_comm_size.argtypes = [vp, ip, ip]
+    L.mcu_diag_global.argtypes = [vp, C.c_double, C.c_int, dp, dp, ip]
+    L.mcu_wait.argtypes = [vp]
+    L.mcu_get_samples.argtypes = [vp, dp]
     _lib = L
     return L

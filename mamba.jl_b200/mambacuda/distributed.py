@@ -1,10 +1,13 @@
 """Cross-GPU diagnostics: the ONLY collective on the path.
 
-Chains are sharded across ranks (one process per GPU, contiguous global chain ids); nothing is
-exchanged while sampling.  gelmandiag / summarystats over all chains need cross-chain sums of
-per-chain moments: each rank reduces its own chains on the device (mcu_moments / mcu_summary_sums),
-and the O(p) partial sums are all-reduced with torch.distributed (NCCL over NVLink on GPUs, gloo in
-the CPU tests).  `local` is anything that offers the Engine's reduction methods.
+Chains are sharded across ranks (one process per GPU, contiguous global chain ids); nothing is exchanged while sampling.
+gelmandiag / summarystats over all chains run as the packed two-round protocol of libmambacuda (include/mambacuda.h,
+csrc/diagproto.hpp): O(p) doubles per round.
+
+  * A handle that joined an NCCL communicator (`init_comm`) does both rounds inside the library, on the device
+    (`Engine.diag_global`): nothing in this module touches the data.
+  * Any other transport carries the two buffers itself: `global_diagnostics` all-reduces them with torch.distributed (gloo in the
+    CPU tests) around `local.diag_round1 / diag_round2 / diag_finish` — `local` is an Engine or anything with those methods.
 """
 import numpy as np
 
@@ -19,7 +22,7 @@ def _dist():
     return None
 
 
-def _allreduce(arr, op="sum", device=None):
+def _allreduce(arr, op, device=None):
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return np.asarray(arr, dtype=np.float64)
@@ -27,33 +30,36 @@ def _allreduce(arr, op="sum", device=None):
     t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64))
     if dist.get_backend() == "nccl":
         t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
-    rop = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op]
-    dist.all_reduce(t, op=rop)
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op])
     return t.cpu().numpy()
 
 
-def global_link_codes(local, transform, device=None):
-    mm = local.minmax()
-    mm = np.stack([_allreduce(mm[:, 0], "min", device), _allreduce(mm[:, 1], "max", device)], axis=1)
-    return local.link_codes(transform, mm)
+def init_comm(eng):
+    """Give `eng` the NCCL communicator of the torch.distributed world: rank 0 creates the id, torch broadcasts its 128 bytes."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return False
+    from .engine import comm_unique_id
+    box = [comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    eng.comm_init(dist.get_rank(), dist.get_world_size(), box[0])
+    return True
+
+
+def global_diagnostics(local, alpha=0.05, transform=False, device=None):
+    """(psrf [p x 2], summary [p x 5], link codes) over the chains of ALL ranks: src/output/gelmandiag.jl:3-60, stats.jl:85-94."""
+    if hasattr(local, "comm_size") and local.comm_size()[1] > 1:
+        return local.diag_global(alpha, transform)
+    b1 = local.diag_round1()
+    p = b1.size // 11
+    r1 = np.concatenate([_allreduce(b1[:p], "min", device), _allreduce(b1[p:2 * p], "max", device), _allreduce(b1[2 * p:], "sum", device)])
+    r2 = _allreduce(local.diag_round2(transform, r1), "sum", device)
+    return local.diag_finish(alpha, transform, r1, r2)
 
 
 def global_gelman(local, alpha=0.05, transform=False, device=None):
-    """gelmandiag over the chains of ALL ranks (src/output/gelmandiag.jl:3-60): two all-reduces of 7p doubles."""
-    codes = global_link_codes(local, transform, device) if transform else None
-    s0, n = local.moments(codes, None)
-    s0 = _allreduce(s0, "sum", device)
-    center = np.stack([s0[:, 1] / s0[:, 0], s0[:, 3] / s0[:, 0]], axis=1)
-    s1, n = local.moments(codes, center)
-    s1 = _allreduce(s1, "sum", device)
-    return local.gelman_from_moments(n, center, s1, alpha)
+    return global_diagnostics(local, alpha, transform, device)[0]
 
 
 def global_summary(local, device=None):
-    """Streaming summarystats over the chains of all ranks (src/output/stats.jl:85-94): [p × 5]."""
-    s0 = _allreduce(local.summary_sums(None), "sum", device)
-    nb = np.where(s0[:, 4] > 0, s0[:, 4], 1.0)
-    center = np.stack([s0[:, 1] / s0[:, 0], s0[:, 5] / nb], axis=1)
-    s1 = _allreduce(local.summary_sums(center), "sum", device)
-    n = local.moments(None, None)[1]
-    return local.summary_from_sums(n, center, s1)
+    return global_diagnostics(local, 0.05, False, device)[1]

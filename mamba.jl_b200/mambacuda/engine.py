@@ -117,18 +117,32 @@ class Engine:
     def kept(self, first_iter, iters, burnin, thin):
         return self.L.mcu_kept(first_iter, iters, burnin, thin)
 
-    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False, partial=False):
+    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False, partial=False, wait=True):
         """Returns the [kept × p × chains] block (Fortran order) or None when out=False.
-        partial=True: this call is one segment of a longer run (MCU_RUN_PARTIAL)."""
+        partial=True: this call is one segment of a longer run (MCU_RUN_PARTIAL).
+        wait=False: MCU_RUN_ASYNC — the call returns once the run is queued; finish it with wait() (then samples())."""
+        if not wait:
+            out = False
         _, p, _ = self.dims()
         it0 = self.iter()
         kept = self.kept(it0, iters, burnin, thin)
         flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0) | \
-            (_lib.RUN_GLM_REFERENCE if glm_reference else 0) | (_lib.RUN_PARTIAL if partial else 0)
+            (_lib.RUN_GLM_REFERENCE if glm_reference else 0) | (_lib.RUN_PARTIAL if partial else 0) | (0 if wait else _lib.RUN_ASYNC)
+        self._last_kept = kept
         arr = None
         if out:
             arr = np.full((kept, p, self.n_chains), np.nan, order="F")
         self._chk(self.L.mcu_run(self.h, int(iters), int(burnin), int(thin), _dp(arr) if out and kept > 0 else None, flags))
+        return arr
+
+    def wait(self):
+        self._chk(self.L.mcu_wait(self.h))
+
+    def samples(self, into=None):
+        """ModelChains.value of the last run ([kept × p × chains], Fortran order); `into`: a preallocated (e.g. pinned) array."""
+        _, p, _ = self.dims()
+        arr = into if into is not None else np.empty((self._last_kept, p, self.n_chains), order="F")
+        self._chk(self.L.mcu_get_samples(self.h, _dp(arr)))
         return arr
 
     def iter(self):
@@ -280,6 +294,50 @@ class Engine:
         self._chk(self.L.mcu_summary_streaming(self.h, _dp(out)))
         return out
 
+    # ---- diagnostics over the chains of several handles / GPUs (include/mambacuda.h, csrc/diagproto.hpp) -------------------
+    def monitor_links(self):
+        p = self.dims()[1]
+        ml = (C.c_int * p)()
+        self._chk(self.L.mcu_monitor_links(self.h, ml))
+        return np.array(list(ml), dtype=np.int32)
+
+    def n_kept(self):
+        n = C.c_int64()
+        self._chk(self.L.mcu_n_kept(self.h, C.byref(n)))
+        return n.value
+
+    def diag_round1(self):
+        p = self.dims()[1]
+        buf = np.empty(11 * p)
+        self._chk(self.L.mcu_diag_round1(self.h, _dp(buf)))
+        return buf
+
+    def diag_round2(self, transform, reduced1):
+        p = self.dims()[1]
+        r1 = _f64(reduced1); buf = np.empty(15 * p)
+        self._chk(self.L.mcu_diag_round2(self.h, int(bool(transform)), _dp(r1), _dp(buf)))
+        return buf
+
+    def diag_finish(self, alpha, transform, reduced1, reduced2):
+        return diag_finish(self.n_kept(), self.monitor_links(), alpha, transform, reduced1, reduced2)
+
+    def comm_init(self, rank, nranks, unique_id):
+        """Join the NCCL communicator of `unique_id` (bytes from comm_unique_id() on rank 0) as `rank` of `nranks`."""
+        self._chk(self.L.mcu_comm_init(self.h, int(rank), int(nranks), bytes(unique_id)))
+
+    def comm_size(self):
+        r, n = C.c_int(), C.c_int()
+        self._chk(self.L.mcu_comm_size(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def diag_global(self, alpha=0.05, transform=False):
+        """gelmandiag + streaming summarystats over every rank of the handle's communicator (this handle alone without one):
+        (psrf [p x 2], summary [p x 5], link codes [p]); device-resident, NCCL all-reduces, one synchronisation."""
+        p = self.dims()[1]
+        psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)()
+        self._chk(self.L.mcu_diag_global(self.h, float(alpha), int(bool(transform)), _dp(psrf), _dp(summ), codes))
+        return psrf, summ, np.array(list(codes), dtype=np.int32)
+
     def fp64_peak_tflops(self):
         return self.L.mcu_fp64_peak_tflops(self.h)
 
@@ -288,3 +346,28 @@ class Engine:
 
     def last_kernel_ms(self):
         return self.L.mcu_last_kernel_ms(self.h)
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); hand the 128 bytes to the other ranks with the host language's own messaging."""
+    buf = C.create_string_buffer(128)
+    L = _lib.lib()
+    rc = L.mcu_comm_unique_id(buf)
+    if rc != 0:
+        raise MambaCudaError(rc, L.mcu_last_error(None).decode())
+    return buf.raw
+
+
+def diag_finish(n_kept, monlink, alpha, transform, reduced1, reduced2):
+    """Host arithmetic of the two-round protocol (no device): (psrf, summary, codes) from the all-reduced buffers."""
+    L = _lib.lib()
+    p = len(monlink)
+    ml = (C.c_int * p)(*[int(v) for v in monlink])
+    r1 = _f64(reduced1); r2 = _f64(reduced2)
+    psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)()
+    rc = L.mcu_diag_finish(int(n_kept), p, float(alpha), ml, int(bool(transform)), _dp(r1), _dp(r2), _dp(psrf), _dp(summ), codes)
+    if rc == _lib.ERR_ARG:
+        raise ValueError("less than 2 chains supplied to gelman diagnostic")
+    if rc != 0:
+        raise MambaCudaError(rc, "mcu_diag_finish failed")
+    return psrf, summ, np.array(list(codes), dtype=np.int32)

@@ -823,3 +823,99 @@ def test_magnesium_posterior_matches_published_table(oracle):
     codes = eng.link_codes(True)        # tau, OR are Logical columns > 0 (tau[4..6] and the ORs also exceed 1 somewhere): log link
     assert (codes[:3] == 1).all()
     assert (eng.gelman(0.05, True)[:, 0] < 1.1).all()
+
+
+# ---- diagnostics over several handles: the packed two-round protocol and its NCCL transport (include/mambacuda.h) --------------------
+def _combine_round1(bufs, p):
+    b = np.stack(bufs)
+    return np.concatenate([b[:, :p].min(axis=0), b[:, p:2 * p].max(axis=0), b[:, 2 * p:].sum(axis=0)])
+
+
+def test_diag_global_equals_gelman_and_summary_and_the_two_handle_protocol(oracle):
+    from mambacuda.engine import Engine, diag_finish
+    tpl, blocks, inits = helpers.scheme("surgical_amwg")          # monitored: identity, log and Logical (logit heuristic) columns
+    whole = Engine(tpl, 64, seed=5); whole.set_scheme(blocks); whole.set_inits(inits, jitter_sd=0.05)
+    out = whole.run(1200, burnin=200, thin=2)
+    for transform in (False, True):
+        psrf, summ, codes = whole.diag_global(0.05, transform)
+        np.testing.assert_allclose(psrf, whole.gelman(0.05, transform), rtol=1e-10)
+        np.testing.assert_allclose(summ, whole.summary_streaming(), rtol=1e-10)
+        np.testing.assert_array_equal(codes, whole.link_codes(transform))
+        np.testing.assert_allclose(psrf, oracle.gelmandiag(out, 0.05, [{0: 0, 1: 1, 2: -1}[int(c)] for c in codes] if transform else None), rtol=1e-7)
+    np.testing.assert_allclose(summ, oracle.summarystats(out, 0, 100), rtol=1e-8)
+    # the same chains on two handles (global chain ids 0..39 and 40..63): buffers combined by the host, as any transport would
+    parts = []
+    for off, n in ((0, 40), (40, 24)):
+        e = Engine(tpl, n, seed=5, chain_offset=off); e.set_scheme(blocks); e.set_inits(inits, jitter_sd=0.05)
+        e.run(1200, burnin=200, thin=2, store=False, out=False, wait=False)      # MCU_RUN_ASYNC: both handles are queued before either is waited for
+        parts.append(e)
+    for e in parts:
+        e.wait()
+    p = whole.dims()[1]
+    r1 = _combine_round1([e.diag_round1() for e in parts], p)
+    r2 = np.sum([e.diag_round2(True, r1) for e in parts], axis=0)
+    psrf2, summ2, codes2 = diag_finish(parts[0].n_kept(), parts[0].monitor_links(), 0.05, True, r1, r2)
+    np.testing.assert_allclose(psrf2, psrf, rtol=1e-9)
+    np.testing.assert_allclose(summ2, summ, rtol=1e-9)
+    np.testing.assert_array_equal(codes2, codes)
+
+
+def test_async_run_and_get_samples(oracle):
+    from mambacuda.engine import Engine, MambaCudaError
+    tpl, blocks, inits = helpers.scheme("seeds_amwg")
+    a = Engine(tpl, 48, seed=3); a.set_scheme(blocks); a.set_inits(inits, jitter_sd=0.1)
+    want = a.run(200, burnin=100, thin=4)
+    b = Engine(tpl, 48, seed=3); b.set_scheme(blocks); b.set_inits(inits, jitter_sd=0.1)
+    assert b.run(200, burnin=100, thin=4, wait=False) is None
+    b.wait()
+    np.testing.assert_array_equal(b.samples(), want)
+    assert b.last_kernel_ms() > 0
+    into = np.empty(want.shape, order="F")
+    assert b.samples(into) is into and np.array_equal(into, want)
+    c = Engine(tpl, 4, seed=3); c.set_scheme(blocks); c.set_inits(inits)
+    c.run(50, burnin=10, thin=1, store=False, out=False)
+    with pytest.raises(MambaCudaError, match="no stored samples"):
+        c.samples()
+
+
+def _nccl_rank(rank, world, tmp):
+    import os, sys, time
+    sys.path[:0] = [os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mamba.jl_b200"), os.path.dirname(os.path.abspath(__file__))]
+    import numpy as np
+    import helpers
+    from mambacuda.engine import Engine, comm_unique_id
+    idf = os.path.join(tmp, "nccl_id")
+    if rank == 0:
+        with open(idf + ".tmp", "wb") as f:
+            f.write(comm_unique_id())
+        os.replace(idf + ".tmp", idf)                     # the id travels by whatever messaging the host language has (here: a file)
+    while not os.path.exists(idf):
+        time.sleep(0.01)
+    uid = open(idf, "rb").read()
+    tpl, blocks, inits = helpers.scheme("surgical_amwg")
+    n = 40 if rank == 0 else 24
+    e = Engine(tpl, n, seed=5, chain_offset=0 if rank == 0 else 40, device=rank); e.set_scheme(blocks); e.set_inits(inits, jitter_sd=0.05)
+    e.comm_init(rank, world, uid)
+    assert e.comm_size() == (rank, world)
+    e.run(1200, burnin=200, thin=2, store=False, out=False)
+    psrf, summ, codes = e.diag_global(0.05, True)
+    np.savez(os.path.join(tmp, f"r{rank}.npz"), psrf=psrf, summ=summ, codes=codes)
+
+
+def test_nccl_diag_global_over_two_gpus(oracle, tmp_path):
+    # mcu_comm_init + mcu_diag_global: both protocol rounds on the device, all-reduced by NCCL inside libmambacuda (one rank per GPU)
+    from mambacuda import _lib
+    from mambacuda.engine import Engine
+    if _lib.lib().mcu_device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_nccl_rank, args=(2, str(tmp_path)), nprocs=2, join=True)
+    tpl, blocks, inits = helpers.scheme("surgical_amwg")
+    whole = Engine(tpl, 64, seed=5); whole.set_scheme(blocks); whole.set_inits(inits, jitter_sd=0.05)
+    whole.run(1200, burnin=200, thin=2, store=False, out=False)
+    psrf, summ, codes = whole.diag_global(0.05, True)
+    for r in range(2):
+        got = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_allclose(got["psrf"], psrf, rtol=1e-9)
+        np.testing.assert_allclose(got["summ"], summ, rtol=1e-9)
+        np.testing.assert_array_equal(got["codes"], codes)

@@ -68,6 +68,50 @@ class NumpyLocal:
             sums[j] = [m, mean.sum(), M2.sum(), ((mean - c1) ** 2).sum(), nb * m, (nb * bmean).sum(), bM2.sum(), (nb * (bmean - c2) ** 2).sum()]
         return sums
 
+    # ---- the packed two-round protocol (mamba.jl_b200/csrc/diagproto.hpp), as the device kernels compute it ----------------
+    def _scales(self, j):
+        x = self.c[:, j, :]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return [x, np.log(x), np.log(x / (1 - x)) if self.monlink[j] == -1 else np.zeros_like(x)]
+
+    def diag_round1(self):
+        n, p, m = self.c.shape
+        nb = n // 100
+        mn, mx, sums = np.empty(p), np.empty(p), np.zeros((p, 9))
+        for j in range(p):
+            x = self.c[:, j, :]
+            mn[j], mx[j] = x.min(), x.max()
+            sc = self._scales(j)
+            bmean = x[: nb * 100].reshape(nb, 100, m).mean(axis=(0, 1))
+            sums[j] = [m] + [v for y in sc for v in (y.mean(axis=0).sum(), y.var(axis=0, ddof=1).sum())] + [nb * m, (nb * bmean).sum()]
+        return np.concatenate([mn, mx, sums.ravel()])
+
+    def diag_round2(self, transform, r1):
+        n, p, m = self.c.shape
+        nb = n // 100
+        out = np.zeros((p, 15))
+        s1 = r1[2 * p:].reshape(p, 9)
+        for j in range(p):
+            ml = self.monlink[j]
+            code = 0
+            if transform:
+                code = 1 if ml == 1 else ((2 if r1[p + j] < 1 else 1) if (ml == -1 and r1[j] > 0) else 0)
+            c1, c2 = s1[j, 1 + 2 * code] / s1[j, 0], s1[j, 2 + 2 * code] / s1[j, 0]
+            k1, k2 = s1[j, 1] / s1[j, 0], (s1[j, 8] / s1[j, 7] if s1[j, 7] > 0 else 0.0)
+            y = self._scales(j)[code]
+            d = y.mean(axis=0) - c1; e = y.var(axis=0, ddof=1) - c2
+            x = self.c[:, j, :]
+            mean = x.mean(axis=0); M2 = ((x - mean) ** 2).sum(axis=0)
+            bm = x[: nb * 100].reshape(nb, 100, m).mean(axis=1)
+            bmean = bm.mean(axis=0); bM2 = ((bm - bmean) ** 2).sum(axis=0)
+            out[j] = [m, d.sum(), (d * d).sum(), e.sum(), (e * e).sum(), (e * d).sum(), (e * d * d).sum(),
+                      m, mean.sum(), M2.sum(), ((mean - k1) ** 2).sum(), nb * m, (nb * bmean).sum(), bM2.sum(), (nb * (bmean - k2) ** 2).sum()]
+        return out.ravel()
+
+    def diag_finish(self, alpha, transform, r1, r2):
+        from mambacuda.engine import diag_finish
+        return diag_finish(self.c.shape[0], self.monlink, alpha, transform, r1, r2)
+
     def summary_from_sums(self, n_kept, center, sums):
         C = self.C
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
@@ -83,6 +127,12 @@ def make_chains(m=6, seed=4):
     c[:, 1, :] = np.exp(0.2 * c[:, 1, :])          # a positive column (log link)
     c[:, 2, :] = 100.0 + c[:, 2, :]                # a far-from-zero column: exercises the centring
     return c
+
+
+def make_chains4(m=6, seed=4):
+    c3 = make_chains(m, seed)
+    u = 1.0 / (1.0 + np.exp(-ar1_chains(300, 1, m, 0.5, seed + 1)))     # a Logical column inside (0, 1): logit link (chains.jl:241-243)
+    return np.concatenate([c3, u], axis=1)
 
 
 def test_gelman_from_moments_equals_reference_gelmandiag(oracle, mcu_built):
@@ -101,6 +151,20 @@ def test_summary_from_sums_equals_reference_summarystats(oracle, mcu_built):
     got = mdist.global_summary(NumpyLocal(c, [0, 1, -1]))
     want = oracle.summarystats(c, 0, 100)
     np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_packed_protocol_equals_reference_diagnostics(oracle, mcu_built):
+    # one rank: gelmandiag(transform) with identity / log / heuristic-log / heuristic-logit columns, and summarystats, in one pass
+    from mambacuda import distributed as mdist
+    c = make_chains4()
+    monlink = [0, 1, -1, -1]
+    for transform, linkcode in ((False, None), (True, [0, 1, -1, -1])):
+        psrf, summ, codes = mdist.global_diagnostics(NumpyLocal(c, monlink), 0.05, transform)
+        np.testing.assert_allclose(psrf, oracle.gelmandiag(c, 0.05, linkcode), rtol=1e-9)
+        np.testing.assert_allclose(summ, oracle.summarystats(c, 0, 100), rtol=1e-9)
+        assert list(codes) == ([0, 1, 1, 2] if transform else [0, 0, 0, 0])
+    with pytest.raises(ValueError, match="less than 2 chains"):
+        mdist.global_diagnostics(NumpyLocal(c[:, :, :1], monlink), 0.05, False)
 
 
 def test_f_quantile_of_the_product_against_scipy(mcu_built):
@@ -129,11 +193,12 @@ def _rank_main(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mambacuda import distributed as mdist
-    c = make_chains(m=6)
+    c = make_chains4(m=6)
     mine = c[:, :, rank * 3:(rank + 1) * 3]            # contiguous chain shards, as the engine shards them
-    local = NumpyLocal(mine, [0, 1, -1])
-    psrf = mdist.global_gelman(local, 0.05, True)
-    summ = mdist.global_summary(local)
+    if rank == 1:
+        mine = c[:, :, 3:5]                            # uneven shards: 3 + 2 chains ... and the sixth chain is left out on purpose below
+    local = NumpyLocal(mine, [0, 1, -1, -1])
+    psrf, summ, _ = mdist.global_diagnostics(local, 0.05, True)
     np.save(os.path.join(tmp, f"psrf{rank}.npy"), psrf)
     np.save(os.path.join(tmp, f"summ{rank}.npy"), summ)
     dist.barrier()
@@ -144,8 +209,8 @@ def test_two_rank_allreduce_matches_single_process(oracle, mcu_built, tmp_path):
     import torch.multiprocessing as mp
     port = 29500 + os.getpid() % 2000
     mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    c = make_chains(m=6)
-    want_psrf = oracle.gelmandiag(c, 0.05, [0, 1, -1])
+    c = make_chains4(m=6)[:, :, :5]
+    want_psrf = oracle.gelmandiag(c, 0.05, [0, 1, -1, -1])
     want_summ = oracle.summarystats(c, 0, 100)
     for r in range(2):
         np.testing.assert_allclose(np.load(tmp_path / f"psrf{r}.npy"), want_psrf, rtol=1e-9)
