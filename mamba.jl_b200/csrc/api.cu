@@ -77,6 +77,7 @@ struct mcu_ctx {
   double g_lp_const = 0.0;
   unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
+  unsigned long long* d_work = nullptr;   // device counter of gradient evaluations (rats_warp leapfrogs, GLM useful chain-gradients)
   bool pending = false;   // an mcu_run(..., MCU_RUN_ASYNC) has not been waited for yet
   // cross-GPU diagnostics (mcu_comm_init / mcu_diag_global): NCCL communicator of this handle's rank, monitored-column links on the device
   void* comm = nullptr; int comm_rank = 0, comm_nranks = 1;
@@ -586,7 +587,7 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
   t.max_depth = b.max_depth > 0 ? (b.max_depth < kMaxDepth ? b.max_depth : kMaxDepth) : kMaxDepth;
   t.target = b.target; t.eps_desc = b.epsilon;
   t.state = h->d_state; t.tune = h->d_tune + (size_t)b.tune_off * h->C; t.sc = h->g_sc; t.vec = h->g_vec; t.req = h->g_req;
-  t.lp = h->g_lp; t.grad = h->g_grad; t.samples = a.samples; t.mom = h->d_mom; t.momn = h->d_momn; t.n_active = h->g_nactive;
+  t.lp = h->g_lp; t.grad = h->g_grad; t.samples = a.samples; t.mom = h->d_mom; t.momn = h->d_momn; t.n_active = h->g_nactive; t.work = h->d_work;
   const int N = (int)h->inputs["y"].size();
   // A tick = advance every chain to its next gradient request, then one gradient pass.  The host only looks at
   // the running-chain counter every kCheck ticks (finished chains idle; at most kCheck - 1 passes are wasted at the end).
@@ -740,7 +741,7 @@ int mcu_destroy(mcu_handle h) {
   cudaStreamSynchronize(h->stream);
   free_scheme(h); free_chain_buffers(h);
   if (h->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(h->comm);
-  cudaFree(h->d_monlink);
+  cudaFree(h->d_monlink); cudaFree(h->d_work);
   for (auto& kv : h->d_inputs) cudaFree(kv.second);
   cudaFree(h->d_rat); cudaFree(h->d_elink_state); cudaFree(h->d_ebound_state); cudaFree(h->d_ext); cudaFree(h->d_ext_pos); cudaFree(h->d_stage); cudaFree(h->d_diag); cudaFree(h->r_scratch); free_glm_data(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
@@ -986,6 +987,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
   a.logit_mask = h->logit_mask;
+  if (!h->d_work) { CK(cudaMalloc(&h->d_work, sizeof(unsigned long long))); CK(cudaMemset(h->d_work, 0, sizeof(unsigned long long))); }
+  a.work = h->d_work;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
   bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
   const bool glm_tick = scheme_is_glm_tick(h) && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
@@ -1598,6 +1601,14 @@ int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, dou
 }
 
 int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
+int mcu_work_count(mcu_handle h, uint64_t* gradients, int64_t* glm_ticks) {
+  if (!h) return MCU_ERR_ARG;
+  unsigned long long w = 0;
+  if (h->d_work) { CK(cudaSetDevice(h->device)); CK(cudaMemcpy(&w, h->d_work, sizeof(w), cudaMemcpyDeviceToHost)); }
+  if (gradients) *gradients = w;
+  if (glm_ticks) *glm_ticks = h->ticks;
+  return MCU_OK;
+}
 double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }
 
 }  // extern "C"

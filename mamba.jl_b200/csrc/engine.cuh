@@ -133,6 +133,7 @@ struct RunArgs {
   const DevBlock* blocks;
   double* state; double* tune; double* samples; double* mom; double* momn;
   const double* ext_u; unsigned long long ext_n; unsigned long long* ext_pos;
+  unsigned long long* work;               // device counter of gradient evaluations (leapfrogs) the kernels add to, or nullptr
   unsigned long long logit_mask;          // monitored columns (bit j) whose link(c) may be the logit: Logical nodes in (0, 1), chains.jl:237-246
 };
 

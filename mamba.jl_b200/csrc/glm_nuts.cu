@@ -50,6 +50,7 @@ struct GlmTickArgs {
   const double* grad;// [d][C] likelihood gradient
   double* samples; double* mom; double* momn;
   int* n_active;     // [2] ring: slot (tick & 1) counts chains still running after this tick
+  unsigned long long* work;   // useful chain-gradients: incremented once per chain that still wants the gradient of this tick's pass
   int tick;
 };
 
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
     a.sc[(size_t)SL_PHASE * C + c] = (double)phase; a.sc[(size_t)SL_ITER * C + c] = (double)iter; a.sc[(size_t)SL_JDRAW * C + c] = (double)jdraw; a.sc[(size_t)SL_KN * C + c] = (double)kn;
     a.tune[0 * C + c] = t_adapt; a.tune[1 * C + c] = t_alpha; a.tune[2 * C + c] = t_eps; a.tune[3 * C + c] = t_epsbar;
     a.tune[4 * C + c] = t_Hbar; a.tune[5 * C + c] = t_m; a.tune[6 * C + c] = t_mu; a.tune[7 * C + c] = t_nalpha;
-    if (phase != PH_DONE) atomicAdd(&a.n_active[a.tick & 1], 1);
+    if (phase != PH_DONE) { atomicAdd(&a.n_active[a.tick & 1], 1); if (a.work) atomicAdd(a.work, 1ull); }
   }
 #undef SC
 #undef SCW
@@ -451,7 +452,7 @@ void glm_advance(const GlmTick& t, cudaStream_t st) {
   a.C = t.C; a.chain_offset = t.chain_offset; a.seed = t.seed; a.target_iter = t.target_iter; a.burnin = t.burnin; a.thin = t.thin;
   a.row0 = t.row0; a.d = t.d; a.max_depth = t.max_depth; a.target = t.target; a.eps_desc = t.eps_desc;
   a.state = t.state; a.tune = t.tune; a.sc = t.sc; a.vec = t.vec; a.req = t.req; a.lp = t.lp; a.grad = t.grad;
-  a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active; a.tick = t.tick;
+  a.samples = t.samples; a.mom = t.mom; a.momn = t.momn; a.n_active = t.n_active; a.work = t.work; a.tick = t.tick;
   glm_advance_kernel<<<(unsigned)((t.C + 3) / 4), 128, 0, st>>>(a);   // one warp per chain, 4 chains per block
 }
 

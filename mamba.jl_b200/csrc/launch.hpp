@@ -107,6 +107,7 @@ struct GlmTick {
   double* state; double* tune; double* sc; double* vec; double* req; const double* lp; const double* grad;
   double* samples; double* mom; double* momn;
   int* n_active;   // [2]
+  unsigned long long* work;
   int tick;
 };
 size_t glm_tick_scalar_slots();

@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
 #pragma unroll
   for (int k = 0; k < NOBS; ++k) { ch.y[k] = cfg.y[k][lane]; ch.xo[k] = cfg.x[k][lane]; }
 
+  unsigned long long n_leap = 0;      // leapfrogs of this warp's chains (warp-uniform): the work unit of the roofline (mcu_work_count)
   for (long long c = gw; c < a.n_chains; c += GW) {
     WRng rng;
     rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
           alpha = 0.0; nalpha = 0.0;
           for (unsigned t = 0; t < nleaf; ++t) {
             const double logpp = ch.leapfrog_inl(cx, cr, cg, pm * eps);
+            ++n_leap;
             Tn = logu0 < logpp ? 1.0 : 0.0;
             Ts = logu0 < logpp + 1000.0;
             alpha += exp_nonpos(fmin(logpp - logp0, 0.0));                   // min(1, exp(logp' - logp0))
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
     if (lane < NR) { a.state[(size_t)(5 + lane) * C + c] = x.a; a.state[(size_t)(5 + NR + lane) * C + c] = x.b; }
     __syncwarp();
   }
+  if (lane == 0 && a.work && n_leap) atomicAdd(a.work, n_leap);
 }
 
 }  // namespace

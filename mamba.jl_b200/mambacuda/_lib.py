@@ -50,7 +50,7 @@ SYMBOLS = [
     "mcu_chains_quantile", "mcu_chains_hpd", "mcu_chains_autocor", "mcu_chains_changerate", "mcu_chains_gelman",
     "mcu_chains_geweke", "mcu_chains_heidel", "mcu_chains_raftery", "mcu_chains_summarystats", "mcu_factor_counts", "mcu_factor_parents", "mcu_logpdf_nodes", "mcu_predict",
     "mcu_diag_sizes", "mcu_monitor_links", "mcu_n_kept", "mcu_diag_round1", "mcu_diag_round2", "mcu_diag_finish",
-    "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_size", "mcu_diag_global", "mcu_wait", "mcu_get_samples",
+    "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_size", "mcu_diag_global", "mcu_wait", "mcu_get_samples", "mcu_work_count",
 ]
 
 
@@ -123,6 +123,7 @@ def lib():
     L.mcu_comm_size.argtypes = [vp, ip, ip]
     L.mcu_diag_global.argtypes = [vp, C.c_double, C.c_int, dp, dp, ip]
     L.mcu_wait.argtypes = [vp]
+    L.mcu_work_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(i64)]
     L.mcu_get_samples.argtypes = [vp, dp]
     _lib = L
     return L

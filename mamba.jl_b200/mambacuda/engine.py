@@ -341,6 +341,12 @@ class Engine:
     def fp64_peak_tflops(self):
         return self.L.mcu_fp64_peak_tflops(self.h)
 
+    def work_count(self):
+        """(gradient evaluations of the fused gradient-based paths, GLM ticks) since the handle was created."""
+        w, t = C.c_uint64(), C.c_int64()
+        self._chk(self.L.mcu_work_count(self.h, C.byref(w), C.byref(t)))
+        return w.value, t.value
+
     def launch_count(self):
         return self.L.mcu_launch_count(self.h)
 
