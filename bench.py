@@ -372,7 +372,7 @@ def glm_config(ctx, args):
     keep_out, host_out = ctx.pinned((C, d))
     import ctypes as Ct
     sampler = ClockSampler(ctx.local_rank).start()
-    w0, k0 = eng.work_count(); l0 = eng.launch_count()
+    w0, k0 = eng.work_count(); s0 = eng.glm_pass_slots; l0 = eng.launch_count()
     ctx.sync_all(); t0 = time.perf_counter()
     eng.set_inits(host_in)
     eng.run(iters, burnin=iters // 2, thin=1, store=False, out=False)
@@ -382,7 +382,7 @@ def glm_config(ctx, args):
     eng._chk(eng.L.mcu_get_state(eng.h, host_out.ctypes.data_as(Ct.POINTER(Ct.c_double)), None, Ct.byref(it)))
     ctx.sync_all(); dt = time.perf_counter() - t0
     clocks = sampler.stop()
-    w1, k1 = eng.work_count(); launches = eng.launch_count() - l0
+    w1, k1 = eng.work_count(); s1 = eng.glm_pass_slots; launches = eng.launch_count() - l0
     dt, kms = ctx.max_over_ranks(dt, kms)
     out = None
     if ctx.rank == 0:
@@ -395,7 +395,8 @@ def glm_config(ctx, args):
             "ms_per_step": kms, "scaling": "weak", "dtype": "f16x2-split tensor (f32 accumulate) + f64 NUTS state", "data": "synthetic",
             "config": {"workload": f"Bayesian {args.glm_family} regression N={N}, d={d}, NUTS(beta), {C} chains/GPU (configs[3])", "chains_per_gpu": C,
                        "iters": iters, "burnin": iters // 2, "gradient_passes": int(ticks), "tick_ms": kms / max(ticks, 1), "pass_ms": pass_ms,
-                       "useful_chain_gradients": int(w1 - w0), "useful_fraction": (w1 - w0) / max(1, ticks * C),
+                       "useful_chain_gradients": int(w1 - w0), "pass_chain_slots": int(s1 - s0), "useful_fraction": (w1 - w0) / max(1, s1 - s0),
+                       "useful_fraction_without_compaction": (w1 - w0) / max(1, ticks * C),
                        "l2": "X (449 MB packed) exceeds L2; every pass streams it from HBM",
                        "psrf_max": float(np.nanmax(psrf[:, 0])), "posterior_mean_abs_err_vs_truth": float(np.mean(np.abs(summ[:, 0] - beta_true)))},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -412,7 +413,7 @@ def glm_config(ctx, args):
         # forward differences (d + 2 density evaluations per gradient, src/model/simulation.jl:47-51)
         cores = os.cpu_count() or 1
         base = {}
-        for mode, Ns, its in [] if args.no_cpu_baseline else (("analytic", 20000, 6), ("forward", 2000, 4)):
+        for mode, Ns, its in [] if args.no_cpu_baseline else (("analytic", 100000, 10), ("forward", 10000, 6)):
             Xs, ys = X[:Ns], y[:Ns]
             blocks = [dict(kind="nuts", nodes=[0], grad=mode)]
             v, secs = oracle_rate("glm", blocks, 0.1 * np.random.default_rng(9).standard_normal((cores, d)), cores, its, its // 2, 1, cores, glm=(Xs, ys))
@@ -647,17 +648,17 @@ def main():
     if "rats" in want:      # configs[2]: 65,536 chains per GPU
         cfgs["rats_nuts_slice"] = small_config(ctx, "configs[2] rats hierarchical normal growth model (30 x 5), NUTS(alpha, beta, mu_alpha, mu_beta) + Slice(s2_c, s2_alpha, s2_beta), 65,536 chains x 2,000",
                                                "rats_nuts_slice", 65536, 2000, 1000, 5, RATS_FLOP_PER_LEAPFROG, True, "rats_warp_kernel (one warp per chain)",
-                                               (os.cpu_count() or 1) if cpu else 0, 150,
+                                               4 * (os.cpu_count() or 1) if cpu else 0, 1500,
                                                note="one chain per warp, 30 of 32 lanes own a rat: bound by shuffle / dependent-issue latency of the leapfrog butterflies, not by the FP64 pipe")
         cfgs["rats_slice_amwg"] = small_config(ctx, "configs[2] rats, the reference's own scheme (doc/examples/rats.jl:112-116): Slice + AMWG, 65,536 chains x 2,000",
                                                "rats_slice_amwg", 65536, 2000, 1000, 5, RATS_FAST_FLOP_PER_ITER, False, "rats_fast_kernel (fused)",
-                                               4 * (os.cpu_count() or 1) if cpu else 0, 400, note="RNG / dependent-issue latency bound (as seeds_fast_kernel)")
+                                               16 * (os.cpu_count() or 1) if cpu else 0, 2000, note="RNG / dependent-issue latency bound (as seeds_fast_kernel)")
     if "glm" in want:
         cfgs["glm_nuts"] = glm_config(ctx, args)
     if "pumps" in want:     # configs[4]: 10^7 chains in total, split over the GPUs (strong scaling), on-device PSRF
         cfgs["pumps_gibbs_amwg"] = small_config(ctx, f"configs[4] pumps gamma-Poisson hierarchy, Gibbs(theta) + Gibbs(beta) + AMWG(alpha), {args.pumps_chains:.0e} chains x 2,000, on-device Gelman-Rubin",
                                                 "pumps_gibbs_amwg", args.pumps_chains, 2000, 1000, 10, PUMPS_FLOP_PER_ITER, False, "pumps_gibbs_kernel (fused)",
-                                                64 * (os.cpu_count() or 1) if cpu else 0, 2000, strong=True, note="issue-slot bound: 11 Gamma variates per iteration")
+                                                512 * (os.cpu_count() or 1) if cpu else 0, 2000, strong=True, note="issue-slot bound: 11 Gamma variates per iteration")
     if rank == 0:
         if cfgs:
             line["configs"] = cfgs

@@ -74,6 +74,8 @@ struct mcu_ctx {
   // GLM / NUTS tick engine buffers (glm_nuts.cu)
   double *g_sc = nullptr, *g_vec = nullptr, *g_req = nullptr, *g_lp = nullptr, *g_grad = nullptr, *g_part_lp = nullptr, *g_part_g = nullptr;
   int* g_nactive = nullptr; int g_nslab = 0;
+  int* g_map = nullptr; long long g_pass_C = 0; int g_pass_nslab = 0;   // tick-engine compaction: pass slot k = chain g_map[k] (g_pass_C = 0: every chain, no map)
+  long long compactions = 0; unsigned long long pass_slots = 0;   // chain slots the gradient passes of the tick engine carried (sum over ticks)
   double g_lp_const = 0.0;
   unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
@@ -397,7 +399,7 @@ void free_glm_data(mcu_ctx* h) {
 // tick-engine state of the chains
 void free_glm_buffers(mcu_ctx* h) {
   cudaFree(h->g_sc); cudaFree(h->g_vec); cudaFree(h->g_req); cudaFree(h->g_lp); cudaFree(h->g_grad); cudaFree(h->g_part_lp); cudaFree(h->g_part_g);
-  cudaFree(h->g_nactive);
+  cudaFree(h->g_nactive); cudaFree(h->g_map); h->g_map = nullptr; h->g_pass_C = 0;
   h->g_sc = h->g_vec = h->g_req = h->g_lp = h->g_grad = h->g_part_lp = h->g_part_g = nullptr; h->g_nactive = nullptr;
 }
 void free_chain_buffers(mcu_ctx* h) {
@@ -493,6 +495,21 @@ bool scheme_is_glm_tick(const mcu_ctx* h) {
   return b.kind == MCU_NUTS && b.grad == MCU_GRAD_ANALYTIC && b.n_own == 1;
 }
 
+// one CTA per SM (tensor memory and shared memory are both fully used): pick the number of row slabs that minimises
+// waves x tiles-per-slab, i.e. the idle SMs of the last wave (4,096 chains = 32 groups: 9 slabs = 288 CTAs = 1.95 waves
+// instead of 4 slabs = 128 CTAs on 148 SMs)
+int glm_tc_choose_nslab(long long N, long long C, int sms) {
+  const long long groups = (C + 127) / 128;
+  const long long NT = glm_tc_num_tiles(N);
+  long long ns = 1; double best = 1e300;
+  for (long long cand = 1; cand <= NT && cand * groups <= 8LL * sms; ++cand) {
+    const long long waves = (cand * groups + sms - 1) / sms, tps = (NT + cand - 1) / cand;
+    const double cost = (double)waves * ((double)tps + 6.0);   // + ~6 tiles of prologue / epilogue per CTA
+    if (cost < best - 1e-9) { best = cost; ns = cand; }
+  }
+  return (int)ns;
+}
+
 int ensure_glm_buffers(mcu_ctx* h) {
   if (h->g_sc) return MCU_OK;
   const size_t C = (size_t)h->C, d = (size_t)h->D;
@@ -503,22 +520,13 @@ int ensure_glm_buffers(mcu_ctx* h) {
   if (nslab > (N + 63) / 64) nslab = (N + 63) / 64;
   if (nslab < 1) nslab = 1;
   const long long nslab_ref = nslab; h->g_nslab = (int)nslab_ref;
+  h->g_nslab_tc = glm_tc_choose_nslab(N, h->C, n_sm);
   {
-    // one CTA per SM (tensor memory and shared memory are both fully used): pick the number of row slabs that minimises
-    // waves x tiles-per-slab, i.e. the idle SMs of the last wave (4,096 chains = 32 groups: 9 slabs = 288 CTAs = 1.95 waves
-    // instead of 4 slabs = 128 CTAs on 148 SMs)
-    const long long groups = (h->C + 127) / 128;
-    const long long NT = glm_tc_num_tiles(N);
-    const int sms = n_sm;
-    long long ns = 1; double best = 1e300;
-    for (long long cand = 1; cand <= NT && cand * groups <= 8LL * sms; ++cand) {
-      const long long waves = (cand * groups + sms - 1) / sms, tps = (NT + cand - 1) / cand;
-      const double cost = (double)waves * ((double)tps + 6.0);   // + ~6 tiles of prologue / epilogue per CTA
-      if (cost < best - 1e-9) { best = cost; ns = cand; }
-    }
-    h->g_nslab_tc = (int)ns;
-    const long long npart = ns * glm_tc_nsub(N, (int)ns);   // FP64 gradient partials: one per (slab, flush interval)
+    // FP64 / FP32 partials: one per (slab, chain slot); a compacted pass has fewer 128-chain groups and more slabs, slabs x groups <= 8 SMs
+    const long long npart = (long long)h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc);
     if (npart > nslab) nslab = npart;
+    const long long cap = (8LL * n_sm * 128 + h->C - 1) / h->C;   // slabs x 128-chain groups of any compacted pass, in units of C slots
+    if (cap > nslab) nslab = cap;
   }
   if (const char* e = std::getenv("MCU_GLM_IMPL")) h->glm_impl = std::atoi(e);
   CK(cudaMalloc(&h->g_sc, sizeof(double) * nsc * C));
@@ -528,8 +536,10 @@ int ensure_glm_buffers(mcu_ctx* h) {
   CK(cudaMalloc(&h->g_grad, sizeof(double) * d * C));
   CK(cudaMalloc(&h->g_part_lp, sizeof(double) * nslab * C));
   CK(cudaMalloc(&h->g_part_g, sizeof(double) * nslab * d * C));
-  CK(cudaMalloc(&h->g_nactive, 2 * sizeof(int)));
-  CK(cudaMemsetAsync(h->g_nactive, 0, 2 * sizeof(int), h->stream));
+  CK(cudaMalloc(&h->g_nactive, 4 * sizeof(int)));
+  CK(cudaMalloc(&h->g_map, sizeof(int) * C));
+  h->g_pass_C = 0;
+  CK(cudaMemsetAsync(h->g_nactive, 0, 4 * sizeof(int), h->stream));
   if (!h->g_blob) {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
@@ -565,10 +575,13 @@ int ensure_glm_buffers(mcu_ctx* h) {
 
 int glm_gradient_dispatch(mcu_ctx* h, int N) {
   if (h->glm_impl == 1) {
-    if (glm_tc_launch(h->g_blob, N, h->D, h->C, h->g_req, h->g_nslab_tc, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), glm_family(h), glm_sigma(h), h->stream) != 0)
+    const bool cmp = h->g_pass_C > 0;                                   // compacted pass: only the chains that are still running
+    const long long Cp = cmp ? h->g_pass_C : h->C; const int ns = cmp ? h->g_pass_nslab : h->g_nslab_tc;
+    const int* map = cmp ? h->g_map : nullptr;
+    if (glm_tc_launch(h->g_blob, N, h->D, Cp, h->g_req, ns, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), glm_family(h), glm_sigma(h), h->stream, map, h->C) != 0)
       return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
-    glm_fold_tc(h->g_part_lp, reinterpret_cast<const float*>(h->g_part_g), h->g_nslab_tc, h->g_nslab_tc * glm_tc_nsub(N, h->g_nslab_tc), h->D, h->C,
-                h->g_req, h->g_xty, h->g_lp_const, h->g_lp, h->g_grad, h->stream);
+    glm_fold_tc(h->g_part_lp, reinterpret_cast<const float*>(h->g_part_g), ns, ns * glm_tc_nsub(N, ns), h->D, Cp,
+                h->g_req, h->g_xty, h->g_lp_const, h->g_lp, h->g_grad, h->stream, map, h->C);
   } else {
     glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
                        h->g_lp, h->g_grad, glm_family(h), glm_sigma(h), h->stream);
@@ -594,6 +607,10 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
   int kCheck = 8;
   if (const char* e = std::getenv("MCU_GLM_CHECK")) { const int v = std::atoi(e); if (v > 0) kCheck = v; }
   int tick = 0;
+  h->g_pass_C = 0;                                   // every chain runs again
+  bool compact = h->glm_impl_run == 1 && h->glm_impl == 1;
+  if (const char* e = std::getenv("MCU_GLM_COMPACT")) compact = compact && std::atoi(e) != 0;
+  int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
   while (true) {
     int slot = 0;
     for (int k = 0; k < kCheck; ++k, ++tick) {
@@ -602,13 +619,24 @@ int run_glm_tick(mcu_ctx* h, long long iters, long long burnin, long long thin, 
       const int saved = h->glm_impl; if (h->glm_impl_run == 0) h->glm_impl = 0;
       rc = glm_gradient_dispatch(h, N); h->glm_impl = saved;
       if (rc) return rc;
-      h->ticks++;
+      h->ticks++; h->pass_slots += (unsigned long long)(h->g_pass_C > 0 ? h->g_pass_C : h->C);
     }
     int active = 0;
     CK(cudaMemcpyAsync(&active, h->g_nactive + slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (active == 0) break;
+    // Chains finish at very different ticks (NUTS trees differ in depth by up to 2^10 leaves): once a whole 128-chain group of the
+    // current pass has gone idle, the running chains are compacted into the leading pass slots and the tensor-core pass shrinks with them
+    const long long cur = h->g_pass_C > 0 ? h->g_pass_C : h->C;
+    if (compact && (active + 127) / 128 < (cur + 127) / 128) {
+      glm_compact(h->g_sc, h->C, h->g_map, h->g_nactive + 2, h->stream); h->launches++;
+      int cnt = 0;
+      CK(cudaMemcpyAsync(&cnt, h->g_nactive + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (cnt > 0) { h->g_pass_C = cnt; h->g_pass_nslab = glm_tc_choose_nslab(N, cnt, n_sm); h->compactions++; }
+    }
   }
+  h->g_pass_C = 0;
   return MCU_OK;
 }
 
@@ -1584,7 +1612,7 @@ int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, dou
   double* tmp = nullptr; CK(cudaMalloc(&tmp, sizeof(double) * C * d));
   CK(cudaMemcpyAsync(tmp, beta, sizeof(double) * C * d, cudaMemcpyHostToDevice, h->stream));
   launch_records_to_soa(tmp, h->g_req, h->C, d, h->stream); h->launches++;
-  const int saved = h->glm_impl; h->glm_impl = impl;
+  const int saved = h->glm_impl; h->glm_impl = impl; h->g_pass_C = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
   rc = glm_gradient_dispatch(h, N);
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -1601,12 +1629,13 @@ int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, dou
 }
 
 int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
-int mcu_work_count(mcu_handle h, uint64_t* gradients, int64_t* glm_ticks) {
+int mcu_work_count(mcu_handle h, uint64_t* gradients, int64_t* glm_ticks, uint64_t* glm_pass_slots) {
   if (!h) return MCU_ERR_ARG;
   unsigned long long w = 0;
   if (h->d_work) { CK(cudaSetDevice(h->device)); CK(cudaMemcpy(&w, h->d_work, sizeof(w), cudaMemcpyDeviceToHost)); }
   if (gradients) *gradients = w;
   if (glm_ticks) *glm_ticks = h->ticks;
+  if (glm_pass_slots) *glm_pass_slots = h->pass_slots;
   return MCU_OK;
 }
 double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }

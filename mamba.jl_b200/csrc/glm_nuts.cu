@@ -414,10 +414,11 @@ __global__ void glm_fold2_kernel(const double* __restrict__ part_lp, const doubl
     lp[c] = s;
   }
 }
-// tensor-core path: FP32 gradient partials; lp[c] = lp_const + beta_c . xty + sum_s part_lp[s][c] (xty, lp_const: the family's linear / constant part)
+// tensor-core path: FP32 gradient partials; lp[c] = lp_const + beta_c . xty + sum_s part_lp[s][c] (xty, lp_const: the family's linear / constant part).
+// The partials are indexed by PASS slot k (C slots); with a compaction map the results go to chain map[k] of the Cfull-strided lp / grad / req.
 __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const float* __restrict__ part_g, int nslab_lp, int nslab_g,
                                    long long C, int d, const double* __restrict__ req, const double* __restrict__ xty, double lp_const,
-                                   double* __restrict__ lp, double* __restrict__ grad) {
+                                   double* __restrict__ lp, double* __restrict__ grad, const int* __restrict__ map, long long Cfull) {
   const long long dC = (long long)d * C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < dC) {
@@ -428,19 +429,43 @@ __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const flo
       s2 += (double)part_g[(size_t)(k + 2) * dC + i]; s3 += (double)part_g[(size_t)(k + 3) * dC + i];
     }
     for (; k < nslab_g; ++k) s0 += (double)part_g[(size_t)k * dC + i];
-    grad[i] = (s0 + s1) + (s2 + s3);
+    const long long j = i / C, slot = i % C;
+    grad[(size_t)j * Cfull + (map ? (long long)map[slot] : slot)] = (s0 + s1) + (s2 + s3);
   } else if (i < dC + C) {
-    const long long c = i - dC;
+    const long long slot = i - dC;
+    const long long c = map ? (long long)map[slot] : slot;
     double s = lp_const;
-    for (int k = 0; k < nslab_lp; ++k) s += part_lp[(size_t)k * C + c];
-    for (int j = 0; j < d; ++j) s += req[(size_t)j * C + c] * xty[j];
+    for (int k = 0; k < nslab_lp; ++k) s += part_lp[(size_t)k * C + slot];
+    for (int j = 0; j < d; ++j) s += req[(size_t)j * Cfull + c] * xty[j];
     lp[c] = s;
   }
 }
+// Compaction of the tick engine: slot k of the next passes = the k-th chain (in chain order) that is still running.  Chains finish their
+// iterations at very different ticks (tree depths differ by up to 2^10), so late passes would otherwise carry mostly idle rows.
+// One block; count[0] = number of running chains.
+__global__ void __launch_bounds__(1024) glm_compact_kernel(const double* __restrict__ sc, long long C, int* __restrict__ map, int* __restrict__ count) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const long long per = (C + 1023) / 1024, lo = t * per, hi = lo + per < C ? lo + per : C;
+  int n = 0;
+  for (long long c = lo; c < hi; ++c) n += (int)sc[(size_t)SL_PHASE * C + c] != PH_DONE;
+  part[t] = n;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {           // inclusive scan
+    const int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int k = part[t] - n;
+  for (long long c = lo; c < hi; ++c) if ((int)sc[(size_t)SL_PHASE * C + c] != PH_DONE) map[k++] = (int)c;
+  if (t == 1023) count[0] = part[1023];
+}
+void glm_compact(const double* sc, long long C, int* map, int* count, cudaStream_t st) { glm_compact_kernel<<<1, 1024, 0, st>>>(sc, C, map, count); }
 void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
-                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st) {
+                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st, const int* map, long long Cfull) {
   const long long dC = (long long)d * C;
-  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp_const, lp, grad);
+  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp_const, lp, grad, map, map ? Cfull : C);
 }
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st) {
   const long long dC = (long long)d * C;

@@ -147,8 +147,10 @@ __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __re
 struct TcArgs {
   const unsigned char* blob; size_t tile_bytes;
   int NT, tiles_per_slab, d, DP;
-  long long C;
-  const double* req;         // [d][C]
+  long long C;               // chains of this pass (after compaction: the chains still running, mapped through `map`)
+  long long Cfull;           // chains of the handle = stride of req
+  const int* map;            // [C] chain index of pass slot k, or nullptr (identity)
+  const double* req;         // [d][Cfull]
   double* part_lp;           // [nslab][C]   -ln2 * sum_i [ |s_i| / 2 + log2(1 + 2^-|s_i|) ],  s = eta * log2(e)
   float* part_g;             // [nslab][d][C]  FP32 running sum of the TMEM accumulator flushes (folded over slabs in FP64)
   int n_pad;                 // zero rows appended to the last tile
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
   if (tid < kEpiThreads) {
     const int q = warp & 3, cq = warp >> 2;
     const long long c = (long long)blockIdx.x * TM + q * 32 + (tid & 31);
+    const long long csrc = (c < a.C && a.map) ? (long long)a.map[c] : c;   // compacted pass: slot c holds chain map[c]
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     for (int ck = cq; ck < DP / 16; ck += 4) {
       uint32_t vh[8], vl[8];
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int col = ck * 16 + e + u;
-          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.C + c] * a.theta_scale) : 0.0f;
+          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.Cfull + csrc] * a.theta_scale) : 0.0f;
         }
         const __half2 h = __floats2half2_rn(x[0], x[1]);
         const float2 hb = __half22float2(h);
@@ -483,12 +486,12 @@ int glm_tc_nsub(long long, int) { return 1; }   // one FP32 gradient partial per
 
 // Returns 0 on success.  part_lp [nslab][C] (FP64), part_g [nslab][d][C] (FP32), to be folded over slabs (glm_fold_tc).
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st) {
+                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st, const int* map, long long Cfull) {
   TcArgs a;
   a.DP = (d + 15) / 16 * 16;
   if (a.DP > 128) return -2;   // TMEM budget: G (DP columns) + Theta hi/lo (DP/2 each) next to the two D1 buffers
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);
-  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
+  a.tiles_per_slab = (a.NT + nslab - 1) / nslab; a.n_pad = (int)(glm_tc_num_tiles(N) * TR - N); a.d = d; a.C = C; a.Cfull = map ? Cfull : C; a.map = map; a.req = req; a.part_lp = part_lp; a.part_g = part_g;
   a.theta_scale = family == 2 ? 1.0 : 1.4426950408889634; a.r_scale = (float)(1.0 / (sigma * sigma));
   const size_t smem = kStages * a.tile_bytes + 8 * (B_COUNT + 2) + 3 * 128 * sizeof(double);
   static thread_local size_t smem_set[3][64] = {{0}};   // per family and device: the attribute call is slow, do it once per size

@@ -343,8 +343,9 @@ class Engine:
 
     def work_count(self):
         """(gradient evaluations of the fused gradient-based paths, GLM ticks) since the handle was created."""
-        w, t = C.c_uint64(), C.c_int64()
-        self._chk(self.L.mcu_work_count(self.h, C.byref(w), C.byref(t)))
+        w, t, sl = C.c_uint64(), C.c_int64(), C.c_uint64()
+        self._chk(self.L.mcu_work_count(self.h, C.byref(w), C.byref(t), C.byref(sl)))
+        self.glm_pass_slots = sl.value
         return w.value, t.value
 
     def launch_count(self):
