@@ -82,6 +82,10 @@ int seeds_fast_launch(const double* r, const double* n, const double* x1, const 
                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st);
 
 
+// the same with two threads per chain (seeds_fast2.cu): twice the warps per SM for the same shared-memory footprint
+int seeds_fast2_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
+                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st);
+
 // fused pumps kernel for the reference's Slice scheme (pumps_fast.cu); returns 0 on success
 int pumps_fast_launch(const double* y, const double* t, int N, const RunArgs& a, const std::vector<std::vector<double>>& h_scales, cudaStream_t st);
 // fused pumps kernel for [Gibbs(theta), Gibbs(beta), AMWG(alpha)] (BASELINE.json configs[4]); `amwg` is the host copy of block 2

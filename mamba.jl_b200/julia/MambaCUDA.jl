@@ -175,15 +175,19 @@ type RunInfo
 end
 const shiminfo = ObjectIdDict()
 
-function openhandle(info::RunInfo, chains::Integer)
+function openhandle(info::RunInfo, chains::Integer; offset::Integer=0, device::Integer=info.device)
   h = Ref{Ptr{Void}}(C_NULL)
   rc = ccall((:mcu_create, libmambacuda), Cint, (Cint, Int64, Int64, Cint, UInt64, Ptr{Ptr{Void}}),
-             info.tid, chains, 0, info.device, info.seed, h)
+             info.tid, chains, offset, device, info.seed, h)
   rc == 0 || error(unsafe_string(ccall((:mcu_last_error, libmambacuda), Cstring, (Ptr{Void},), C_NULL)))
   ## inputs (setinputs!, src/model/initialization.jl:30-40); integer data travel as Float64
   for (key, value) in info.inputs
     isa(value, AbstractArray) || continue
     x = convert(Array{Float64}, value)
+    ## index inputs are 0-based offsets on the device (include/mambacuda.h); the scripts hold Julia's 1-based indices (rats.jl:42, dyes.jl:16)
+    if (info.tid == 2 && key == :rat) || (info.tid == 6 && key == :batch)
+      x = x - 1.0
+    end
     dims = Int64[size(x)...]
     check(h[], ccall((:mcu_set_data, libmambacuda), Cint, (Ptr{Void}, Cstring, Cint, Ptr{Int64}, Ptr{Float64}),
                      h[], string(key), length(dims), dims, x))
@@ -246,6 +250,94 @@ function mcmc(m::Model, inputs::Dict{Symbol}, inits::Vector{Dict{Symbol, Any}}, 
   finally
     ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h)
   end
+end
+
+## mcmc over several GPUs of the box from ONE Julia process (the reference farms chains out with pmap2(mcmc_worker!, lsts),
+## src/model/mcmc.jl:48-52): chains are cut into contiguous shards, shard k runs on devices[k] with global chain ids
+## offset .. offset + n - 1 (the Philox key is the global id: the samples do not depend on the sharding), every run is queued with
+## MCU_RUN_ASYNC before any is waited for, and the shards' samples land side by side in ModelChains.value.
+const MCU_RUN_NO_STORE = UInt32(1)
+const MCU_RUN_ASYNC = UInt32(16)
+
+function mcmc(m::Model, inputs::Dict{Symbol}, inits::Vector{Dict{Symbol, Any}}, iters::Integer, devices::Vector{Int};
+              burnin::Integer=0, thin::Integer=1, chains::Integer=1, verbose::Bool=true, seed::Integer=123, template::Integer=-1)
+  iters > burnin || throw(ArgumentError("burnin is greater than or equal to iters"))
+  length(inits) >= chains || throw(ArgumentError("fewer initial values than chains"))
+  tid = template >= 0 ? template : matchtemplate(m)
+  nodes = TEMPLATES[tid]
+  nodeids = Dict{Symbol, Int}([nodes[i] => i - 1 for i in 1:length(nodes)])
+  keep = Any[]
+  descs = BlockDesc[blockdesc(m, s, nodeids, keep) for s in m.samplers]
+  mm = deepcopy(m)
+  setinputs!(mm, inputs); setinits!(mm, inits[1:chains]); mm.burnin = burnin; mm.iter = 0
+  info = RunInfo(tid, inputs, descs, keep, UInt64(seed), devices[1])
+  G = length(devices)
+  cuts = [div(k * chains, G) for k in 0:G]                       # chain c lives on GPU floor(c G / chains): SURVEY.md §8e
+  x0 = hcat([vcat([vec(Float64[inits[k][key]...]) for key in nodes]...) for k in 1:chains]...)
+  hs = Ptr{Void}[]
+  try
+    for k in 1:G
+      n = cuts[k + 1] - cuts[k]
+      h = openhandle(info, n, offset=cuts[k], device=devices[k]); push!(hs, h)
+      check(h, ccall((:mcu_set_inits, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Int64, Float64), h, pointer(x0, size(x0, 1) * cuts[k] + 1), n, 0.0))
+      check(h, ccall((:mcu_run, libmambacuda), Cint, (Ptr{Void}, Int64, Int64, Int64, Ptr{Float64}, UInt32), h, iters, burnin, thin, C_NULL, MCU_RUN_ASYNC))
+    end
+    D = Ref{Cint}(0); P = Ref{Cint}(0); NN = Ref{Cint}(0)
+    check(hs[1], ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), hs[1], D, P, NN))
+    kept = ccall((:mcu_kept, libmambacuda), Int64, (Int64, Int64, Int64, Int64), 0, iters, burnin, thin)
+    value = Array{Float64}(kept, P[], chains)
+    nt = Ref{Int64}(0)
+    check(hs[1], ccall((:mcu_tune_size, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), hs[1], nt))
+    vals = Array{Float64}(D[], chains); tune = Array{Float64}(max(nt[], 1), chains); it = Ref{Int64}(0)
+    for k in 1:G
+      h = hs[k]
+      check(h, ccall((:mcu_wait, libmambacuda), Cint, (Ptr{Void},), h))
+      check(h, ccall((:mcu_get_samples, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}), h, pointer(value, kept * P[] * cuts[k] + 1)))
+      check(h, ccall((:mcu_get_state, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                     h, pointer(vals, D[] * cuts[k] + 1), pointer(tune, size(tune, 1) * cuts[k] + 1), it))
+    end
+    mm.iter = it[]
+    mm.states = ModelState[ModelState(vals[:, k], Any[tune[:, k]]) for k in 1:chains]
+    buf = Vector{UInt8}(1 << 16)
+    ccall((:mcu_names, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{UInt8}, Csize_t), hs[1], 1, buf, length(buf))
+    pnames = split(unsafe_string(pointer(buf)), '\n')
+    mc = ModelChains(Chains(value, start=burnin + thin, thin=thin, names=AbstractString[pnames...]), mm)
+    shiminfo[mc.model] = info
+    return mc
+  finally
+    for h in hs
+      ccall((:mcu_destroy, libmambacuda), Cint, (Ptr{Void},), h)
+    end
+  end
+end
+
+## gelmandiag / summarystats over the chains of several live handles WITHOUT gathering the samples (10^6 chains do not fit a Chains
+## array): the packed two-round protocol of include/mambacuda.h, the O(p) buffers combined here in Julia.  Worker processes
+## (addprocs, one per GPU) can instead join an NCCL communicator: mcu_comm_unique_id on one, the 128 bytes sent with remotecall,
+## mcu_comm_init on each, then mcu_diag_global does both rounds on the devices.
+function devicediagnostics(hs::Vector{Ptr{Void}}; alpha::Real=0.05, transform::Bool=false)
+  P = Ref{Cint}(0)
+  check(hs[1], ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), hs[1], C_NULL, P, C_NULL))
+  p = Int(P[])
+  r1 = Array{Float64}(11p, length(hs))
+  for (k, h) in enumerate(hs)
+    check(h, ccall((:mcu_diag_round1, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}), h, pointer(r1, 11p * (k - 1) + 1)))
+  end
+  red1 = vcat(minimum(r1[1:p, :], 2), maximum(r1[p+1:2p, :], 2), sum(r1[2p+1:end, :], 2))[:]
+  r2 = Array{Float64}(15p, length(hs))
+  for (k, h) in enumerate(hs)
+    check(h, ccall((:mcu_diag_round2, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{Float64}, Ptr{Float64}), h, transform, red1, pointer(r2, 15p * (k - 1) + 1)))
+  end
+  red2 = sum(r2, 2)[:]
+  monlink = Array{Cint}(p); nkept = Ref{Int64}(0)
+  check(hs[1], ccall((:mcu_monitor_links, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}), hs[1], monlink))
+  check(hs[1], ccall((:mcu_n_kept, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), hs[1], nkept))
+  psrf = Array{Float64}(2, p); summ = Array{Float64}(5, p); codes = Array{Cint}(p)
+  rc = ccall((:mcu_diag_finish, libmambacuda), Cint,
+             (Int64, Cint, Float64, Ptr{Cint}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+             nkept[], p, alpha, monlink, transform, red1, red2, psrf, summ, codes)
+  rc == 0 || throw(ArgumentError("less than 2 chains supplied to gelman diagnostic"))
+  round(psrf', 3), summ'          # gelmandiag rounds to 3 dp (gelmandiag.jl:59); summary columns: Mean, SD, Naive SE, MCSE, ESS
 end
 
 ## mcmc(mc, iters): restart (src/model/mcmc.jl:3-16) — the handle is rebuilt at the stored ModelStates (values, tune records, iteration
