@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "mambacuda", "libmambacuda.so")
-SOURCES = ["api.cu", "kern_misc.cu", "seeds_fast.cu", "seeds_fast2.cu", "rats_warp.cu", "rats_fast.cu", "pumps_fast.cu", "glm_nuts.cu", "glm_tc.cu", "tpl_line.cu", "tpl_seeds.cu", "tpl_rats.cu", "tpl_pumps.cu", "tpl_glm.cu", "tpl_surgical.cu", "tpl_dyes.cu", "tpl_salm.cu", "tpl_equiv.cu", "tpl_blocker.cu", "tpl_stacks.cu", "tpl_magnesium.cu"]
+SOURCES = ["api.cu", "kern_misc.cu", "seeds_fast.cu", "rats_warp.cu", "rats_fast.cu", "pumps_fast.cu", "glm_nuts.cu", "glm_tc.cu", "tpl_line.cu", "tpl_seeds.cu", "tpl_rats.cu", "tpl_pumps.cu", "tpl_glm.cu", "tpl_surgical.cu", "tpl_dyes.cu", "tpl_salm.cu", "tpl_equiv.cu", "tpl_blocker.cu", "tpl_stacks.cu", "tpl_magnesium.cu", "tpl_oxford.cu", "tpl_epil.cu"]
 COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

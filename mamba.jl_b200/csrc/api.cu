@@ -1045,11 +1045,8 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
     const long long n = std::min(chunk, iters - done);
     a.iter0 = h->iter + done; a.iters = n;
     if (fast) {
-      // two threads per chain (seeds_fast2.cu) unless MCU_SEEDS_TPC=1 asks for the one-thread-per-chain kernel (seeds_fast.cu)
-      static const int seeds_tpc = [] { const char* e = std::getenv("MCU_SEEDS_TPC"); return e ? std::atoi(e) : 2; }();
-      auto launch = seeds_tpc == 1 ? seeds_fast_launch : seeds_fast2_launch;
-      rc = launch(h->inputs["r"].data(), h->inputs["n"].data(), h->inputs["x1"].data(), h->inputs["x2"].data(), a, h->h_blocks.data(),
-                  h->h_scales, h->h_SigmaL.empty() || h->h_SigmaL[0].empty() ? nullptr : h->h_SigmaL[0].data(), h->stream);
+      rc = seeds_fast_launch(h->inputs["r"].data(), h->inputs["n"].data(), h->inputs["x1"].data(), h->inputs["x2"].data(), a, h->h_blocks.data(),
+                             h->h_scales, h->h_SigmaL.empty() || h->h_SigmaL[0].empty() ? nullptr : h->h_SigmaL[0].data(), h->stream);
       if (rc == -2) { fast = false; chunk = 256; continue; }   // design is not 0/1 indicators: the generic kernel takes over
       if (rc) return fail(h, MCU_ERR_CUDA, "seeds_fast launch failed");
     } else if (pumps_gibbs) {

@@ -203,10 +203,10 @@ __device__ __forceinline__ void generic_kernel_body(const typename M::Data& data
         case 1: slice_uni_sample<M::D>(v, b, tgt, rng); break;
         case 2: slice_multi_sample<M::D>(v, b, tgt, rng); break;
         case 3: rwm_sample<M::D>(v, b, tgt, rng); break;
-        case 4: nuts_sample<M::D>(v, b, tn, tgt, rng, fresh, iter <= a.burnin); break;
-        case 5: hmc_sample<M::D>(v, b, tgt, rng); break;
-        case 6: amm_sample<M::D>(v, b, tn, tgt, rng, fresh, isadapt); break;
-        case 8: mala_sample<M::D>(v, b, tgt, rng); break;
+        case 4: if constexpr (M::kGradSamplers) nuts_sample<M::D>(v, b, tn, tgt, rng, fresh, iter <= a.burnin); break;
+        case 5: if constexpr (M::kGradSamplers) hmc_sample<M::D>(v, b, tgt, rng); break;
+        case 6: if constexpr (M::kGradSamplers) amm_sample<M::D>(v, b, tn, tgt, rng, fresh, isadapt); break;
+        case 8: if constexpr (M::kGradSamplers) mala_sample<M::D>(v, b, tgt, rng); break;
         case 7: M::gibbs(data, s, b.own[0], rng, [](double shape, Draws& r) { return rgamma_mt(shape, r); }); tgt.unlist(v); break;   // MCU_GIBBS
       }
       tgt.relist(v);                                           // m[sampler.params] = relist(block, v)

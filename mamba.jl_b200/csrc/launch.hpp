@@ -29,6 +29,8 @@ MCU_DECLARE_TPL(EquivModel)
 MCU_DECLARE_TPL(BlockerModel)
 MCU_DECLARE_TPL(StacksModel)
 MCU_DECLARE_TPL(MagnesiumModel)
+MCU_DECLARE_TPL(OxfordModel)
+MCU_DECLARE_TPL(EpilModel)
 
 // fewer chains than one wave at the default occupancy (148 SMs x 4 blocks x 128 threads): the low-latency instantiation
 #ifdef MCU_GENERIC_MINB
@@ -81,10 +83,6 @@ double measure_fp64_peak_tflops(cudaStream_t st);
 int seeds_fast_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st);
 
-
-// the same with two threads per chain (seeds_fast2.cu): twice the warps per SM for the same shared-memory footprint
-int seeds_fast2_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
-                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st);
 
 // fused pumps kernel for the reference's Slice scheme (pumps_fast.cu); returns 0 on success
 int pumps_fast_launch(const double* y, const double* t, int N, const RunArgs& a, const std::vector<std::vector<double>>& h_scales, cudaStream_t st);

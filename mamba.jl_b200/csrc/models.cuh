@@ -127,6 +127,8 @@ MCU_D double ig001_c0() { return 0.001 * flog(0.001) - lgamma(0.001); }
 // Defaults every template inherits: an element takes its node's link (arrays of different distributions override elem_link), bounded
 // links take their interval from elem_bounds.
 struct TplBase {
+  static constexpr bool kGradSamplers = true;   // false: NUTS / HMC / MALA / AMM are compiled out of the generic kernel (templates whose state is too
+                                                // large for ~40 block-sized per-thread vectors); mcu_set_scheme answers MCU_ERR_UNSUPPORTED for them
   MCU_HD static int elem_link(int /*e*/, int node_link) { return node_link; }
   MCU_HD static void elem_bounds(int /*e*/, double& lo, double& hi) { lo = 0.0; hi = 1.0; }
 };
@@ -870,6 +872,143 @@ struct MagnesiumModel : TplBase {
     else { const int e = o - NE; const double pc = s[60 + e]; a = d.nt[e / NPR]; b = 1.0 / (fexp(-(s[12 + e] + flog(pc / (1.0 - pc)))) + 1.0); }
     return OUT_BINOMIAL;
   }
+};
+
+// =============================================================================== oxford
+// doc/examples/oxford.jl:31-82 (data :4-28): 120 strata of a case-control study — 244 unobserved elements per chain, the largest state of
+// the example corpus next to epil.  alpha, beta1, beta2 ~ Normal(0, 1000), s2 ~ InverseGamma(.001, .001), b[120] ~ Normal(0, sqrt(s2)),
+// mu[120] ~ Normal(0, 1000); r0[i] ~ Binomial(n0[i], invlogit(mu[i])), r1[i] ~ Binomial(n1[i], invlogit(mu[i] + alpha + beta1 year[i] +
+// beta2 (year[i]^2 - 22) + b[i])).  State: alpha, beta1, beta2, s2, b[120], mu[120]; monitored alpha, beta1, beta2, s2.
+// kGradSamplers = false: the gradient-based samplers keep ~40 block-sized vectors per thread (NUTS tree stack), which at this state size
+// needs the warp-per-chain layout of rats_warp.cu; the script's own scheme (AMWG + three multivariate Slice blocks) runs on the generic kernel.
+struct OxfordModel : TplBase {
+  static constexpr int D = 244, NN = 6, NF = 8, P = 4, K = 120;
+  static constexpr bool kGradSamplers = false;
+  struct Data { const double* r1; const double* n1; const double* r0; const double* n0; const double* year; const double* lc1; const double* lc0; };
+  MCU_HD static int node_off(int n) { return n < 4 ? n : (n == 4 ? 4 : 4 + K); }
+  MCU_HD static int node_len(int n) { return n < 4 ? 1 : K; }
+  MCU_HD static int node_link(int n) { return n == 3 ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 4 ? 0x08u /* s2 */ : f == 6 ? 0x20u /* mu */ : f == 7 ? 0x37u /* alpha, beta1, beta2, b, mu */ : 0u; }
+  MCU_HD static int mon_link(int j) { return j == 3 ? LINK_LOG : LINK_IDENT; }
+  static const char* node_name(int n) { static const char* nm[] = {"alpha", "beta1", "beta2", "s2", "b", "mu"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "alpha\nbeta1\nbeta2\ns2"; }
+  MCU_D static double eta1(const Data& d, const double* s, int i) {
+    const double yr = d.year[i];
+    return s[4 + K + i] + s[0] + s[1] * yr + s[2] * (yr * yr - 22.0) + s[4 + i];
+  }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f < 3) return lp_normal(s[f], 0.0, 1000.0);
+    if (f == 3) return lp_invgamma(s[3], 0.001, 0.001, ig001_c0(), transform);
+    double lp = 0.0;
+    if (f == 4) { const double sg = sqrt(s[3]); for (int i = 0; i < K; ++i) lp += lp_normal(s[4 + i], 0.0, sg); return lp; }
+    if (f == 5) { for (int i = 0; i < K; ++i) lp += lp_normal(s[4 + K + i], 0.0, 1000.0); return lp; }
+    if (f == 6) { for (int i = 0; i < K; ++i) lp += lp_binomial_logit(d.r0[i], d.n0[i], d.lc0[i], s[4 + K + i]); return lp; }
+    for (int i = 0; i < K; ++i) lp += lp_binomial_logit(d.r1[i], d.n1[i], d.lc1[i], eta1(d, s, i));
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double s2 = s[3];
+    double ga = 0, g1 = 0, g2 = 0, sbb = 0;
+    for (int i = 0; i < K; ++i) {
+      const double yr = d.year[i], q = yr * yr - 22.0;
+      const double res1 = d.r1[i] - d.n1[i] * (1.0 / (fexp(-eta1(d, s, i)) + 1.0));
+      const double res0 = d.r0[i] - d.n0[i] * (1.0 / (fexp(-s[4 + K + i]) + 1.0));
+      ga += res1; g1 += res1 * yr; g2 += res1 * q;
+      g[4 + i] = res1 - s[4 + i] / s2;
+      g[4 + K + i] = res0 + res1 - s[4 + K + i] / 1e6;
+      sbb += s[4 + i] * s[4 + i];
+    }
+    g[0] = ga - s[0] / 1e6; g[1] = g1 - s[1] / 1e6; g[2] = g2 - s[2] / 1e6;
+    g[3] = -0.5 * (double)K / s2 + 0.5 * sbb / (s2 * s2) + d_invgamma(s2, 0.001, 0.001);
+  }
+  MCU_HD static bool elem_local(int e) { return e >= 4; }   // b_i: its Normal term + case term i; mu_i: its Normal term + both arms of stratum i
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    if (e < 4 + K) { const int i = e - 4; return lp_normal(s[e], 0.0, sqrt(s[3])) + lp_binomial_logit(d.r1[i], d.n1[i], d.lc1[i], eta1(d, s, i)); }
+    const int i = e - 4 - K;
+    return lp_normal(s[e], 0.0, 1000.0) + lp_binomial_logit(d.r0[i], d.n0[i], d.lc0[i], s[e]) + lp_binomial_logit(d.r1[i], d.n1[i], d.lc1[i], eta1(d, s, i));
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data&, const double* s, double* out) { for (int j = 0; j < 4; ++j) out[j] = s[j]; }
+  MCU_HD static int out_len(const Data&) { return 2 * K; }   // r0[120] then r1[120]
+  MCU_D static int out_dist(const Data& d, const double* s, int o, double& a, double& b) {
+    if (o < K) { a = d.n0[o]; b = 1.0 / (fexp(-s[4 + K + o]) + 1.0); }
+    else { const int i = o - K; a = d.n1[i]; b = 1.0 / (fexp(-eta1(d, s, i)) + 1.0); }
+    return OUT_BINOMIAL;
+  }
+};
+
+// =============================================================================== epil
+// doc/examples/epil.jl:33-111 (data :4-30): Poisson GLMM of seizure counts, 59 patients x 4 visits — 303 unobserved elements per chain.
+// a0 and the five coefficients ~ Normal(0, 100), s2_b1, s2_b ~ InverseGamma(.001, .001), b1[59] ~ Normal(0, sqrt(s2_b1)),
+// b[59 x 4] ~ Normal(0, sqrt(s2_b)) (column-major, patient fastest), y[i, j] ~ Poisson(exp(eta_ij)) with centred covariates (epil.jl:25-30).
+// State: a0, alpha_Base, alpha_Trt, alpha_BT, alpha_Age, alpha_V4, s2_b1, s2_b, b1[59], b[236]; monitored: the five coefficients,
+// alpha0 (Logical, epil.jl:85-91), s2_b1, s2_b.  cov = [x1[59] | x2[59] | x3[59] | x4[59] | x5[4] | the five covariate means] (host-derived).
+struct EpilModel : TplBase {
+  static constexpr int D = 303, NN = 10, NF = 11, P = 8, NPAT = 59, NV = 4, NOBS = 236;
+  static constexpr bool kGradSamplers = false;
+  struct Data { const double* y; const double* lgy1; const double* cov; };
+  MCU_HD static int node_off(int n) { return n < 8 ? n : (n == 8 ? 8 : 8 + NPAT); }
+  MCU_HD static int node_len(int n) { return n < 8 ? 1 : (n == 8 ? NPAT : NOBS); }
+  MCU_HD static int node_link(int n) { return (n == 6 || n == 7) ? LINK_LOG : LINK_IDENT; }
+  MCU_HD static uint32_t parents(int f) { return f == 8 ? 0x040u /* s2_b1 */ : f == 9 ? 0x080u /* s2_b */ : f == 10 ? 0x33Fu /* a0, coefficients, b1, b */ : 0u; }
+  MCU_HD static int mon_link(int j) { return j < 5 ? LINK_IDENT : (j == 5 ? LINK_HEUR : LINK_LOG); }
+  static const char* node_name(int n) { static const char* nm[] = {"a0", "alpha_Base", "alpha_Trt", "alpha_BT", "alpha_Age", "alpha_V4", "s2_b1", "s2_b", "b1", "b"}; return nm[n]; }
+  static const char* state_names() { return nullptr; }
+  static const char* monitor_names() { return "alpha_Base\nalpha_Trt\nalpha_BT\nalpha_Age\nalpha_V4\nalpha0\ns2_b1\ns2_b"; }
+  MCU_D static double eta(const Data& d, const double* s, int i, int j) {
+    const double* c = d.cov;
+    return s[0] + s[1] * c[i] + s[2] * c[NPAT + i] + s[3] * c[2 * NPAT + i] + s[4] * c[3 * NPAT + i] + s[5] * c[4 * NPAT + j] + s[8 + i] + s[8 + NPAT + i + NPAT * j];
+  }
+  MCU_D static double y_term(const Data& d, const double* s, int i, int j) { const int o = i + NPAT * j; return lp_poisson(d.y[o], d.lgy1[o], fexp(eta(d, s, i, j))); }
+  MCU_NOINL static double factor(const Data& d, const double* s, int f, bool transform) {
+    if (f < 6) return lp_normal(s[f], 0.0, 100.0);
+    if (f < 8) return lp_invgamma(s[f], 0.001, 0.001, ig001_c0(), transform);
+    double lp = 0.0;
+    if (f == 8) { const double sg = sqrt(s[6]); for (int i = 0; i < NPAT; ++i) lp += lp_normal(s[8 + i], 0.0, sg); return lp; }
+    if (f == 9) { const double sg = sqrt(s[7]); for (int o = 0; o < NOBS; ++o) lp += lp_normal(s[8 + NPAT + o], 0.0, sg); return lp; }
+    for (int j = 0; j < NV; ++j) for (int i = 0; i < NPAT; ++i) lp += y_term(d, s, i, j);
+    return lp;
+  }
+  MCU_NOINL static void joint_grad(const Data& d, const double* s, double* g) {
+    const double* c = d.cov;
+    double ga[6] = {0, 0, 0, 0, 0, 0}, sb1 = 0, sb = 0;
+    for (int i = 0; i < NPAT; ++i) g[8 + i] = 0.0;
+    for (int j = 0; j < NV; ++j) for (int i = 0; i < NPAT; ++i) {
+      const int o = i + NPAT * j;
+      const double res = d.y[o] - fexp(eta(d, s, i, j));
+      ga[0] += res; ga[1] += res * c[i]; ga[2] += res * c[NPAT + i]; ga[3] += res * c[2 * NPAT + i]; ga[4] += res * c[3 * NPAT + i]; ga[5] += res * c[4 * NPAT + j];
+      g[8 + i] += res;
+      g[8 + NPAT + o] = res - s[8 + NPAT + o] / s[7];
+      sb += s[8 + NPAT + o] * s[8 + NPAT + o];
+    }
+    for (int i = 0; i < NPAT; ++i) { g[8 + i] -= s[8 + i] / s[6]; sb1 += s[8 + i] * s[8 + i]; }
+    for (int k = 0; k < 6; ++k) g[k] = ga[k] - s[k] / 1e4;
+    g[6] = -0.5 * (double)NPAT / s[6] + 0.5 * sb1 / (s[6] * s[6]) + d_invgamma(s[6], 0.001, 0.001);
+    g[7] = -0.5 * (double)NOBS / s[7] + 0.5 * sb / (s[7] * s[7]) + d_invgamma(s[7], 0.001, 0.001);
+  }
+  MCU_HD static bool elem_local(int e) { return e >= 8; }   // b1_i: its Normal term + patient i's four visits; b_ij: its Normal term + one visit
+  MCU_D static double elem_terms(const Data& d, const double* s, int e, bool) {
+    if (e < 8 + NPAT) {
+      const int i = e - 8;
+      double lp = lp_normal(s[e], 0.0, sqrt(s[6]));
+      for (int j = 0; j < NV; ++j) lp += y_term(d, s, i, j);
+      return lp;
+    }
+    const int o = e - 8 - NPAT;
+    return lp_normal(s[e], 0.0, sqrt(s[7])) + y_term(d, s, o % NPAT, o / NPAT);
+  }
+  MCU_HD static bool has_gibbs(int) { return false; }
+  template <class R, class G> MCU_D static void gibbs(const Data&, double*, int, R&, G) {}
+  MCU_D static void monitor(const Data& d, const double* s, double* out) {
+    const double* bar = d.cov + 4 * NPAT + NV;
+    for (int k = 0; k < 5; ++k) out[k] = s[1 + k];
+    out[5] = s[0] - s[1] * bar[0] - s[2] * bar[1] - s[3] * bar[2] - s[4] * bar[3] - s[5] * bar[4];   // alpha0: epil.jl:85-91
+    out[6] = s[6]; out[7] = s[7];
+  }
+  MCU_HD static int out_len(const Data&) { return NOBS; }
+  MCU_D static int out_dist(const Data& d, const double* s, int o, double& a, double& b) { a = fexp(eta(d, s, o % NPAT, o / NPAT)); b = 0.0; return OUT_POISSON; }
 };
 
 // =============================================================================== glm (CUDA-core form)

@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9, TPL_STACKS = 10, TPL_MAGNESIUM = 11 };
+enum { TPL_LINE = 0, TPL_SEEDS = 1, TPL_RATS = 2, TPL_PUMPS = 3, TPL_GLM = 4, TPL_SURGICAL = 5, TPL_DYES = 6, TPL_SALM = 7, TPL_EQUIV = 8, TPL_BLOCKER = 9, TPL_STACKS = 10, TPL_MAGNESIUM = 11, TPL_OXFORD = 12, TPL_EPIL = 13 };
 
 inline Node make_node(const std::string& name, bool stochastic, int len, bool scalar, bool monitored,
                       bool observed = false) {
@@ -428,6 +428,176 @@ inline Model make_magnesium() {
 }
 
 // ------------------------------------------------------------------------------------------
+// oxford: doc/examples/oxford.jl:31-82 (data :4-28) — 120 strata of a case-control study.  244 unobserved elements:
+// alpha, beta1, beta2 ~ Normal(0, 1000), s2 ~ InverseGamma(.001, .001), b[120] ~ Normal(0, sqrt(s2)), mu[120] ~ Normal(0, 1000);
+// r0[i] ~ Binomial(n0[i], invlogit(mu[i])), r1[i] ~ Binomial(n1[i], invlogit(mu[i] + alpha + beta1 year[i] + beta2 (year[i]^2 - 22) + b[i])).
+// Monitored: alpha, beta1, beta2, s2.
+inline Model make_oxford() {
+  Model m; m.template_id = TPL_OXFORD;
+  m.inputs["r1"] = {3, 5, 2, 7, 7, 2, 5, 3, 5, 11, 6, 6, 11, 4, 4, 2, 8, 8, 6, 5, 15, 4, 9, 9, 4, 12, 8, 8, 6, 8,
+      12, 4, 7, 16, 12, 9, 4, 7, 8, 11, 5, 12, 8, 17, 9, 3, 2, 7, 6, 5, 11, 14, 13, 8, 6, 4, 8, 4, 8, 7,
+      15, 15, 9, 9, 5, 6, 3, 9, 12, 14, 16, 17, 8, 8, 9, 5, 9, 11, 6, 14, 21, 16, 6, 9, 8, 9, 8, 4, 11, 11,
+      6, 9, 4, 4, 9, 9, 10, 14, 6, 3, 4, 6, 10, 4, 3, 3, 10, 4, 10, 5, 4, 3, 13, 1, 7, 5, 7, 6, 3, 7};
+  m.inputs["n1"] = {28, 21, 32, 35, 35, 38, 30, 43, 49, 53, 31, 35, 46, 53, 61, 40, 29, 44, 52, 55, 61, 31, 48, 44, 42, 53, 56, 71, 43, 43,
+      43, 40, 44, 70, 75, 71, 37, 31, 42, 46, 47, 55, 63, 91, 43, 39, 35, 32, 53, 49, 75, 64, 69, 64, 49, 29, 40, 27, 48, 43,
+      61, 77, 55, 60, 46, 28, 33, 32, 46, 57, 56, 78, 58, 52, 31, 28, 46, 42, 45, 63, 71, 69, 43, 50, 31, 34, 54, 46, 58, 62,
+      52, 41, 34, 52, 63, 59, 88, 62, 47, 53, 57, 74, 68, 61, 45, 45, 62, 73, 53, 39, 45, 51, 55, 41, 53, 51, 42, 46, 54, 32};
+  m.inputs["r0"] = {0, 2, 2, 1, 2, 0, 1, 1, 1, 2, 4, 4, 2, 1, 7, 4, 3, 5, 3, 2, 4, 1, 4, 5, 2, 7, 5, 8, 2, 3,
+      5, 4, 1, 6, 5, 11, 5, 2, 5, 8, 5, 6, 6, 10, 7, 5, 5, 2, 8, 1, 13, 9, 11, 9, 4, 4, 8, 6, 8, 6,
+      8, 14, 6, 5, 5, 2, 4, 2, 9, 5, 6, 7, 5, 10, 3, 2, 1, 7, 9, 13, 9, 11, 4, 8, 2, 3, 7, 4, 7, 5,
+      6, 6, 5, 6, 9, 7, 7, 7, 4, 2, 3, 4, 10, 3, 4, 2, 10, 5, 4, 5, 4, 6, 5, 3, 2, 2, 4, 6, 4, 1};
+  m.inputs["n0"] = {28, 21, 32, 35, 35, 38, 30, 43, 49, 53, 31, 35, 46, 53, 61, 40, 29, 44, 52, 55, 61, 31, 48, 44, 42, 53, 56, 71, 43, 43,
+      43, 40, 44, 70, 75, 71, 37, 31, 42, 46, 47, 55, 63, 91, 43, 39, 35, 32, 53, 49, 75, 64, 69, 64, 49, 29, 40, 27, 48, 43,
+      61, 77, 55, 60, 46, 28, 33, 32, 46, 57, 56, 78, 58, 52, 31, 28, 46, 42, 45, 63, 71, 69, 43, 50, 31, 34, 54, 46, 58, 62,
+      52, 41, 34, 52, 63, 59, 88, 62, 47, 53, 57, 74, 68, 61, 45, 45, 62, 73, 53, 39, 45, 51, 55, 41, 53, 51, 42, 46, 54, 32};
+  m.inputs["year"] = {-10, -9, -9, -8, -8, -8, -7, -7, -7, -7, -6, -6, -6, -6, -6, -5, -5, -5, -5, -5, -5, -4, -4, -4, -4, -4, -4, -4, -3, -3,
+      -3, -3, -3, -3, -3, -3, -2, -2, -2, -2, -2, -2, -2, -2, -2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0,
+      0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3,
+      3, 3, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8, 9, 9, 10};
+  auto vague = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 1000.0}; };
+  { Node n = make_node("alpha", true, 1, true, true); n.eval = vague; m.nodes.push_back(n); }              // 0
+  { Node n = make_node("beta1", true, 1, true, true); n.eval = vague; m.nodes.push_back(n); }              // 1
+  { Node n = make_node("beta2", true, 1, true, true); n.eval = vague; m.nodes.push_back(n); }              // 2
+  { Node n = make_node("s2", true, 1, true, true);                                                         // 3
+    n.eval = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b", true, 120, false, false); n.sources = {3};                                     // 4
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(3)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("mu", true, 120, false, false); n.eval = vague; m.nodes.push_back(n); }             // 5
+  { Node n = make_node("r0", true, 120, false, false, true); n.sources = {5};                              // 6
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& n0 = mm.in("n0"); const auto& mu = mm.val(5);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(n0.size());
+      for (size_t i = 0; i < n0.size(); ++i) s.distr.arr[i] = {D_BINOMIAL, n0[i], invlogit(mu[i])};
+    };
+    m.nodes.push_back(n); }
+  { Node n = make_node("r1", true, 120, false, false, true); n.sources = {5, 0, 1, 2, 4};                  // 7
+    n.eval = [](const Model& mm, Node& s) {
+      const auto& n1 = mm.in("n1"); const auto& yr = mm.in("year"); const auto& mu = mm.val(5); const auto& b = mm.val(4);
+      const double al = mm.val(0)[0], b1 = mm.val(1)[0], b2 = mm.val(2)[0];
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(n1.size());
+      for (size_t i = 0; i < n1.size(); ++i)
+        s.distr.arr[i] = {D_BINOMIAL, n1[i], invlogit(mu[i] + al + b1 * yr[i] + b2 * (yr[i] * yr[i] - 22.0) + b[i])};
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: alpha, beta1, beta2, s2, b[120], mu[120]
+    const auto &r0 = mm.in("r0"), &n0 = mm.in("n0"), &r1 = mm.in("r1"), &n1 = mm.in("n1"), &yr = mm.in("year");
+    const auto &b = mm.val(4), &mu = mm.val(5);
+    const double al = mm.val(0)[0], b1 = mm.val(1)[0], b2 = mm.val(2)[0], s2 = mm.val(3)[0];
+    double ga = 0, g1 = 0, g2 = 0, sbb = 0;
+    for (int i = 0; i < 120; ++i) {
+      const double q = yr[i] * yr[i] - 22.0;
+      const double res1 = r1[i] - n1[i] * invlogit(mu[i] + al + b1 * yr[i] + b2 * q + b[i]);
+      const double res0 = r0[i] - n0[i] * invlogit(mu[i]);
+      ga += res1; g1 += res1 * yr[i]; g2 += res1 * q;
+      g[4 + i] = res1 - b[i] / s2;
+      g[124 + i] = res0 + res1 - mu[i] / 1e6;
+      sbb += b[i] * b[i];
+    }
+    g[0] = ga - al / 1e6; g[1] = g1 - b1 / 1e6; g[2] = g2 - b2 / 1e6;
+    g[3] = -60.0 / s2 + 0.5 * sbb / (s2 * s2) + ig_dlogpdf(0.001, 0.001, s2);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// epil: doc/examples/epil.jl:33-111 (data :4-30) — Poisson GLMM of seizure counts, 59 patients x 4 visits.  303 unobserved elements:
+// a0, alpha_Base, alpha_Trt, alpha_BT, alpha_Age, alpha_V4 ~ Normal(0, 100), s2_b1, s2_b ~ InverseGamma(.001, .001),
+// b1[59] ~ Normal(0, sqrt(s2_b1)), b[59 x 4] ~ Normal(0, sqrt(s2_b)) (column-major, patient fastest);
+// y[i, j] ~ Poisson(exp(a0 + alpha_Base (logBase4_i - mean) + alpha_Trt (Trt_i - mean) + alpha_BT (BT_i - mean) + alpha_Age (logAge_i - mean)
+//                       + alpha_V4 (V4_j - mean) + b1[i] + b[i, j])).
+// Monitored: alpha_Base, alpha_Trt, alpha_BT, alpha_Age, alpha_V4, alpha0 (Logical), s2_b1, s2_b.
+struct EpilCov { std::vector<double> lb, trt, bt, la; double v4[4]; double lbbar, trtbar, btbar, labar, v4bar; };
+inline EpilCov epil_cov(const Model& mm) {     // epil.jl:25-30
+  const auto &Base = mm.in("Base"), &Trt = mm.in("Trt"), &Age = mm.in("Age"), &V4 = mm.in("V4");
+  EpilCov c; const size_t N = Base.size();
+  c.lb.resize(N); c.trt = Trt; c.bt.resize(N); c.la.resize(N);
+  double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  for (size_t i = 0; i < N; ++i) { c.lb[i] = std::log(Base[i] / 4.0); c.bt[i] = c.lb[i] * Trt[i]; c.la[i] = std::log(Age[i]); s1 += c.lb[i]; s2 += Trt[i]; s3 += c.bt[i]; s4 += c.la[i]; }
+  c.lbbar = s1 / N; c.trtbar = s2 / N; c.btbar = s3 / N; c.labar = s4 / N;
+  double sv = 0; for (int j = 0; j < 4; ++j) { c.v4[j] = V4[j]; sv += V4[j]; }
+  c.v4bar = sv / 4.0;
+  return c;
+}
+inline Model make_epil() {
+  Model m; m.template_id = TPL_EPIL;
+  m.inputs["y"] = {5, 3, 2, 4, 7, 5, 6, 40, 5, 14, 26, 12, 4, 7, 16, 11, 0, 37, 3, 3, 3, 3, 2, 8, 18, 2, 3, 13, 11, 8,
+      0, 3, 2, 4, 22, 5, 2, 3, 4, 2, 0, 5, 11, 10, 19, 1, 6, 2, 102, 4, 8, 1, 18, 6, 3, 1, 2, 0, 1, 3,
+      5, 4, 4, 18, 2, 4, 20, 6, 13, 12, 6, 4, 9, 24, 0, 0, 29, 5, 0, 4, 4, 3, 12, 24, 1, 1, 15, 14, 7, 4,
+      6, 6, 3, 17, 4, 4, 7, 18, 1, 2, 4, 14, 5, 7, 1, 10, 1, 65, 3, 6, 3, 11, 3, 5, 23, 3, 0, 4, 3, 3,
+      0, 1, 9, 8, 0, 21, 6, 6, 6, 8, 6, 12, 10, 0, 3, 28, 2, 6, 3, 3, 3, 2, 76, 2, 4, 13, 9, 9, 3, 1,
+      7, 1, 19, 7, 0, 7, 2, 1, 4, 0, 25, 3, 6, 2, 8, 0, 72, 2, 5, 1, 28, 4, 4, 19, 0, 0, 3, 3, 3, 5,
+      4, 21, 7, 2, 12, 5, 0, 22, 4, 2, 14, 9, 5, 3, 29, 5, 7, 4, 4, 5, 8, 25, 1, 2, 12, 8, 4, 0, 3, 4,
+      3, 16, 4, 4, 7, 5, 0, 0, 3, 15, 8, 7, 3, 8, 0, 63, 4, 7, 5, 13, 0, 3, 8, 1, 0, 2};   // 59 x 4, column-major (patient fastest)
+  m.inputs["Trt"] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1,
+      1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+  m.inputs["Base"] = {11, 11, 6, 8, 66, 27, 12, 52, 23, 10, 52, 33, 18, 42, 87, 50, 18, 111, 18, 20, 12, 9, 17, 28, 55, 9, 10, 47, 76, 38,
+      19, 10, 19, 24, 31, 14, 11, 67, 41, 7, 22, 13, 46, 36, 38, 7, 36, 11, 151, 22, 41, 32, 56, 24, 16, 22, 25, 13, 12};
+  m.inputs["Age"] = {31, 30, 25, 36, 22, 29, 31, 42, 37, 28, 36, 24, 23, 36, 26, 26, 28, 31, 32, 21, 29, 21, 32, 25, 30, 40, 19, 22, 18, 32,
+      20, 30, 18, 24, 30, 35, 27, 20, 22, 28, 23, 40, 33, 21, 35, 25, 26, 25, 22, 32, 25, 35, 21, 41, 32, 26, 21, 36, 37};
+  m.inputs["V4"] = {0, 0, 0, 1};
+  auto coef = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, 100.0}; };
+  { Node n = make_node("a0", true, 1, true, false); n.eval = coef; m.nodes.push_back(n); }                  // 0
+  const char* names[5] = {"alpha_Base", "alpha_Trt", "alpha_BT", "alpha_Age", "alpha_V4"};
+  for (int k = 0; k < 5; ++k) { Node n = make_node(names[k], true, 1, true, true); n.eval = coef; m.nodes.push_back(n); }   // 1..5
+  { Node n = make_node("alpha0", false, 1, true, true); n.sources = {0, 1, 2, 3, 4, 5};                     // 6: Logical, epil.jl:85-91
+    n.eval = [](const Model& mm, Node& l) {
+      const EpilCov c = epil_cov(mm);
+      l.value.assign(1, mm.val(0)[0] - mm.val(1)[0] * c.lbbar - mm.val(2)[0] * c.trtbar - mm.val(3)[0] * c.btbar - mm.val(4)[0] * c.labar - mm.val(5)[0] * c.v4bar);
+    };
+    m.nodes.push_back(n); }
+  auto ig = [](const Model&, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_INVGAMMA, 0.001, 0.001}; };
+  { Node n = make_node("s2_b1", true, 1, true, true); n.eval = ig; m.nodes.push_back(n); }                 // 7
+  { Node n = make_node("s2_b", true, 1, true, true); n.eval = ig; m.nodes.push_back(n); }                  // 8
+  { Node n = make_node("b1", true, 59, false, false); n.sources = {7};                                     // 9
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(7)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("b", true, 236, false, false); n.sources = {8};                                     // 10
+    n.eval = [](const Model& mm, Node& s) { s.distr.form = Distr::UNI; s.distr.u = {D_NORMAL, 0.0, std::sqrt(mm.val(8)[0])}; };
+    m.nodes.push_back(n); }
+  { Node n = make_node("y", true, 236, false, false, true); n.sources = {0, 1, 2, 3, 4, 5, 9, 10};         // 11
+    n.eval = [](const Model& mm, Node& s) {
+      const EpilCov c = epil_cov(mm);
+      const double a0 = mm.val(0)[0], aB = mm.val(1)[0], aT = mm.val(2)[0], aBT = mm.val(3)[0], aA = mm.val(4)[0], aV = mm.val(5)[0];
+      const auto &b1 = mm.val(9), &b = mm.val(10);
+      s.distr.form = Distr::UNI_ARRAY; s.distr.arr.resize(236);
+      for (int j = 0; j < 4; ++j) for (int i = 0; i < 59; ++i) {
+        const double eta = a0 + aB * (c.lb[i] - c.lbbar) + aT * (c.trt[i] - c.trtbar) + aBT * (c.bt[i] - c.btbar) + aA * (c.la[i] - c.labar) +
+                           aV * (c.v4[j] - c.v4bar) + b1[i] + b[i + 59 * j];
+        s.distr.arr[i + 59 * j] = {D_POISSON, std::exp(eta), 0.0};
+      }
+    };
+    m.nodes.push_back(n); }
+  m.joint_grad = [](const Model& mm, std::vector<double>& g) {   // state order: a0, alpha_Base, alpha_Trt, alpha_BT, alpha_Age, alpha_V4, s2_b1, s2_b, b1[59], b[236]
+    const EpilCov c = epil_cov(mm);
+    const auto& y = mm.in("y");
+    const double a0 = mm.val(0)[0], aB = mm.val(1)[0], aT = mm.val(2)[0], aBT = mm.val(3)[0], aA = mm.val(4)[0], aV = mm.val(5)[0];
+    const double s2b1 = mm.val(7)[0], s2b = mm.val(8)[0];
+    const auto &b1 = mm.val(9), &b = mm.val(10);
+    double ga[6] = {0, 0, 0, 0, 0, 0}, sb1 = 0, sb = 0;
+    for (int i = 0; i < 59; ++i) g[8 + i] = 0.0;
+    for (int j = 0; j < 4; ++j) for (int i = 0; i < 59; ++i) {
+      const double x1 = c.lb[i] - c.lbbar, x2 = c.trt[i] - c.trtbar, x3 = c.bt[i] - c.btbar, x4 = c.la[i] - c.labar, x5 = c.v4[j] - c.v4bar;
+      const double eta = a0 + aB * x1 + aT * x2 + aBT * x3 + aA * x4 + aV * x5 + b1[i] + b[i + 59 * j];
+      const double res = y[i + 59 * j] - std::exp(eta);
+      ga[0] += res; ga[1] += res * x1; ga[2] += res * x2; ga[3] += res * x3; ga[4] += res * x4; ga[5] += res * x5;
+      g[8 + i] += res;
+      g[67 + i + 59 * j] = res - b[i + 59 * j] / s2b;
+      sb += b[i + 59 * j] * b[i + 59 * j];
+    }
+    for (int i = 0; i < 59; ++i) { g[8 + i] -= b1[i] / s2b1; sb1 += b1[i] * b1[i]; }
+    const double co[6] = {a0, aB, aT, aBT, aA, aV};
+    for (int k = 0; k < 6; ++k) g[k] = ga[k] - co[k] / 1e4;
+    g[6] = -29.5 / s2b1 + 0.5 * sb1 / (s2b1 * s2b1) + ig_dlogpdf(0.001, 0.001, s2b1);
+    g[7] = -118.0 / s2b + 0.5 * sb / (s2b * s2b) + ig_dlogpdf(0.001, 0.001, s2b);
+  };
+  m.finalize();
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------
 // surgical: doc/examples/surgical.jl:11-43 (data :4-8).  Node order = topological order: mu, pop_mean, s2, b, p, r.
 inline Model make_surgical() {
   Model m; m.template_id = TPL_SURGICAL;
@@ -772,6 +942,8 @@ inline Model make_template(int id, int glm_d = 0) {
     case TPL_SALM: return make_salm();
     case TPL_BLOCKER: return make_blocker();
     case TPL_MAGNESIUM: return make_magnesium();
+    case TPL_OXFORD: return make_oxford();
+    case TPL_EPIL: return make_epil();
     case TPL_STACKS: return make_stacks();
     case TPL_EQUIV: return make_equiv();
     default: throw std::runtime_error("unknown template");
