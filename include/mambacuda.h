@@ -62,7 +62,10 @@ enum {
   MCU_TPL_STACKS = 10,   /* doc/examples/stacks.jl:41-94   nodes: beta0, beta[3], s2; Laplace likelihood; monitored (all Logical) b[3], b0, sigma, outlier[1,3,4,21] */
   MCU_TPL_MAGNESIUM = 11, /* doc/examples/magnesium.jl:21-82 nodes: priors[6], mu[6], theta[6x8], pc[6x8]; bounded (Uniform / truncated) priors: mu is sampled on
                              the two-sided link logit((x-a)/(b-a)) (src/distributions/transformdistribution.jl:6-48); monitored (Logical) tau[6], OR[6] */
-  MCU_N_TEMPLATES = 12
+  MCU_TPL_OXFORD = 12,    /* doc/examples/oxford.jl:31-82   nodes: alpha, beta1, beta2, s2, b[120], mu[120] (244 elements; AMWG / Slice / RWM blocks only) */
+  MCU_TPL_EPIL = 13,      /* doc/examples/epil.jl:33-111    nodes: a0, alpha_Base, alpha_Trt, alpha_BT, alpha_Age, alpha_V4, s2_b1, s2_b, b1[59], b[59x4] (303 elements;
+                             AMWG / Slice / RWM blocks only); monitored: the five coefficients, alpha0 (Logical), s2_b1, s2_b */
+  MCU_N_TEMPLATES = 14
 };
 
 /* ---- sampler kinds (src/samplers/) ---------------------------------------------------------- */

@@ -195,6 +195,45 @@ void default_inputs(mcu_ctx* h) {
       in["rc"] = {2, 23, 7, 1, 8, 9, 3, 118};
       in["nc"] = {36, 135, 200, 46, 148, 56, 23, 1157};
       break;
+    case MCU_TPL_OXFORD:  // doc/examples/oxford.jl:4-28
+      in["r1"] = {3, 5, 2, 7, 7, 2, 5, 3, 5, 11, 6, 6, 11, 4, 4, 2, 8, 8, 6, 5, 15, 4, 9, 9, 4, 12, 8, 8, 6, 8,
+          12, 4, 7, 16, 12, 9, 4, 7, 8, 11, 5, 12, 8, 17, 9, 3, 2, 7, 6, 5, 11, 14, 13, 8, 6, 4, 8, 4, 8, 7,
+          15, 15, 9, 9, 5, 6, 3, 9, 12, 14, 16, 17, 8, 8, 9, 5, 9, 11, 6, 14, 21, 16, 6, 9, 8, 9, 8, 4, 11, 11,
+          6, 9, 4, 4, 9, 9, 10, 14, 6, 3, 4, 6, 10, 4, 3, 3, 10, 4, 10, 5, 4, 3, 13, 1, 7, 5, 7, 6, 3, 7};
+      in["n1"] = {28, 21, 32, 35, 35, 38, 30, 43, 49, 53, 31, 35, 46, 53, 61, 40, 29, 44, 52, 55, 61, 31, 48, 44, 42, 53, 56, 71, 43, 43,
+          43, 40, 44, 70, 75, 71, 37, 31, 42, 46, 47, 55, 63, 91, 43, 39, 35, 32, 53, 49, 75, 64, 69, 64, 49, 29, 40, 27, 48, 43,
+          61, 77, 55, 60, 46, 28, 33, 32, 46, 57, 56, 78, 58, 52, 31, 28, 46, 42, 45, 63, 71, 69, 43, 50, 31, 34, 54, 46, 58, 62,
+          52, 41, 34, 52, 63, 59, 88, 62, 47, 53, 57, 74, 68, 61, 45, 45, 62, 73, 53, 39, 45, 51, 55, 41, 53, 51, 42, 46, 54, 32};
+      in["r0"] = {0, 2, 2, 1, 2, 0, 1, 1, 1, 2, 4, 4, 2, 1, 7, 4, 3, 5, 3, 2, 4, 1, 4, 5, 2, 7, 5, 8, 2, 3,
+          5, 4, 1, 6, 5, 11, 5, 2, 5, 8, 5, 6, 6, 10, 7, 5, 5, 2, 8, 1, 13, 9, 11, 9, 4, 4, 8, 6, 8, 6,
+          8, 14, 6, 5, 5, 2, 4, 2, 9, 5, 6, 7, 5, 10, 3, 2, 1, 7, 9, 13, 9, 11, 4, 8, 2, 3, 7, 4, 7, 5,
+          6, 6, 5, 6, 9, 7, 7, 7, 4, 2, 3, 4, 10, 3, 4, 2, 10, 5, 4, 5, 4, 6, 5, 3, 2, 2, 4, 6, 4, 1};
+      in["n0"] = {28, 21, 32, 35, 35, 38, 30, 43, 49, 53, 31, 35, 46, 53, 61, 40, 29, 44, 52, 55, 61, 31, 48, 44, 42, 53, 56, 71, 43, 43,
+          43, 40, 44, 70, 75, 71, 37, 31, 42, 46, 47, 55, 63, 91, 43, 39, 35, 32, 53, 49, 75, 64, 69, 64, 49, 29, 40, 27, 48, 43,
+          61, 77, 55, 60, 46, 28, 33, 32, 46, 57, 56, 78, 58, 52, 31, 28, 46, 42, 45, 63, 71, 69, 43, 50, 31, 34, 54, 46, 58, 62,
+          52, 41, 34, 52, 63, 59, 88, 62, 47, 53, 57, 74, 68, 61, 45, 45, 62, 73, 53, 39, 45, 51, 55, 41, 53, 51, 42, 46, 54, 32};
+      in["year"] = {-10, -9, -9, -8, -8, -8, -7, -7, -7, -7, -6, -6, -6, -6, -6, -5, -5, -5, -5, -5, -5, -4, -4, -4, -4, -4, -4, -4, -3, -3,
+          -3, -3, -3, -3, -3, -3, -2, -2, -2, -2, -2, -2, -2, -2, -2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 0,
+          0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3,
+          3, 3, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8, 9, 9, 10};
+      break;
+    case MCU_TPL_EPIL:  // doc/examples/epil.jl:4-24
+      in["y"] = {5, 3, 2, 4, 7, 5, 6, 40, 5, 14, 26, 12, 4, 7, 16, 11, 0, 37, 3, 3, 3, 3, 2, 8, 18, 2, 3, 13, 11, 8,
+          0, 3, 2, 4, 22, 5, 2, 3, 4, 2, 0, 5, 11, 10, 19, 1, 6, 2, 102, 4, 8, 1, 18, 6, 3, 1, 2, 0, 1, 3,
+          5, 4, 4, 18, 2, 4, 20, 6, 13, 12, 6, 4, 9, 24, 0, 0, 29, 5, 0, 4, 4, 3, 12, 24, 1, 1, 15, 14, 7, 4,
+          6, 6, 3, 17, 4, 4, 7, 18, 1, 2, 4, 14, 5, 7, 1, 10, 1, 65, 3, 6, 3, 11, 3, 5, 23, 3, 0, 4, 3, 3,
+          0, 1, 9, 8, 0, 21, 6, 6, 6, 8, 6, 12, 10, 0, 3, 28, 2, 6, 3, 3, 3, 2, 76, 2, 4, 13, 9, 9, 3, 1,
+          7, 1, 19, 7, 0, 7, 2, 1, 4, 0, 25, 3, 6, 2, 8, 0, 72, 2, 5, 1, 28, 4, 4, 19, 0, 0, 3, 3, 3, 5,
+          4, 21, 7, 2, 12, 5, 0, 22, 4, 2, 14, 9, 5, 3, 29, 5, 7, 4, 4, 5, 8, 25, 1, 2, 12, 8, 4, 0, 3, 4,
+          3, 16, 4, 4, 7, 5, 0, 0, 3, 15, 8, 7, 3, 8, 0, 63, 4, 7, 5, 13, 0, 3, 8, 1, 0, 2};   // 59 x 4, column-major (patient fastest)
+      in["Trt"] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1,
+          1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+      in["Base"] = {11, 11, 6, 8, 66, 27, 12, 52, 23, 10, 52, 33, 18, 42, 87, 50, 18, 111, 18, 20, 12, 9, 17, 28, 55, 9, 10, 47, 76, 38,
+          19, 10, 19, 24, 31, 14, 11, 67, 41, 7, 22, 13, 46, 36, 38, 7, 36, 11, 151, 22, 41, 32, 56, 24, 16, 22, 25, 13, 12};
+      in["Age"] = {31, 30, 25, 36, 22, 29, 31, 42, 37, 28, 36, 24, 23, 36, 26, 26, 28, 31, 32, 21, 29, 21, 32, 25, 30, 40, 19, 22, 18, 32,
+          20, 30, 18, 24, 30, 35, 27, 20, 22, 28, 23, 40, 33, 21, 35, 25, 26, 25, 22, 32, 25, 35, 21, 41, 32, 26, 21, 36, 37};
+      in["V4"] = {0, 0, 0, 1};
+      break;
     case MCU_TPL_SURGICAL:  // doc/examples/surgical.jl:4-8
       in["r"] = {0, 18, 8, 46, 8, 13, 9, 31, 14, 8, 29, 24};
       in["n"] = {47, 148, 119, 810, 211, 196, 148, 215, 207, 97, 256, 360};
@@ -228,7 +267,23 @@ int upload_inputs(mcu_ctx* h) {
     in["meanx"] = mean; in["sdx"] = sd; in["z"] = z;
   }
   if (h->tpl == MCU_TPL_BLOCKER || h->tpl == MCU_TPL_MAGNESIUM) { in["lcc"] = lchoose_vec(in["nc"], in["rc"]); in["lct"] = lchoose_vec(in["nt"], in["rt"]); }
-  if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
+  if (h->tpl == MCU_TPL_OXFORD) { in["lc1"] = lchoose_vec(in["n1"], in["r1"]); in["lc0"] = lchoose_vec(in["n0"], in["r0"]); }
+  if (h->tpl == MCU_TPL_EPIL) {
+    // centred covariates logBase4 = log(Base / 4), Trt, BT = logBase4 .* Trt, logAge = log(Age), V4 and their means: epil.jl:25-30
+    const auto &Base = in["Base"], &Trt = in["Trt"], &Age = in["Age"], &V4 = in["V4"];
+    const int NPT = EpilModel::NPAT, NV = EpilModel::NV;
+    std::vector<double> cov((size_t)4 * NPT + NV + 5, 0.0), lb(NPT), bt(NPT), la(NPT);
+    double m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+    for (int i = 0; i < NPT; ++i) { lb[i] = std::log(Base[i] / 4.0); bt[i] = lb[i] * Trt[i]; la[i] = std::log(Age[i]); m1 += lb[i]; m2 += Trt[i]; m3 += bt[i]; m4 += la[i]; }
+    for (int j = 0; j < NV; ++j) m5 += V4[j];
+    m1 /= NPT; m2 /= NPT; m3 /= NPT; m4 /= NPT; m5 /= NV;
+    for (int i = 0; i < NPT; ++i) { cov[i] = lb[i] - m1; cov[NPT + i] = Trt[i] - m2; cov[2 * NPT + i] = bt[i] - m3; cov[3 * NPT + i] = la[i] - m4; }
+    for (int j = 0; j < NV; ++j) cov[4 * NPT + j] = V4[j] - m5;
+    const double bars[5] = {m1, m2, m3, m4, m5};
+    for (int k = 0; k < 5; ++k) cov[4 * NPT + NV + k] = bars[k];
+    in["cov"] = cov;
+  }
+  if (h->tpl == MCU_TPL_PUMPS || h->tpl == MCU_TPL_SALM || h->tpl == MCU_TPL_EPIL) { std::vector<double> l; for (double y : in["y"]) l.push_back(std::lgamma(y + 1.0)); in["lgy1"] = l; }
   for (auto& kv : in) {
     if (kv.second.empty()) continue;
     double* p = nullptr;
@@ -286,6 +341,14 @@ template <> struct Host<MagnesiumModel> {
     return {h->d_inputs["rc"], h->d_inputs["nc"], h->d_inputs["rt"], h->d_inputs["nt"], h->d_inputs["lcc"], h->d_inputs["lct"], s2_0, std::sqrt(s2_0 / std::erf(0.75))};
   }
 };
+template <> struct Host<OxfordModel> {
+  static OxfordModel::Data data(mcu_ctx* h) {
+    return {h->d_inputs["r1"], h->d_inputs["n1"], h->d_inputs["r0"], h->d_inputs["n0"], h->d_inputs["year"], h->d_inputs["lc1"], h->d_inputs["lc0"]};
+  }
+};
+template <> struct Host<EpilModel> {
+  static EpilModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["lgy1"], h->d_inputs["cov"]}; }
+};
 template <> struct Host<StacksModel> {
   static StacksModel::Data data(mcu_ctx* h) { return {h->d_inputs["y"], h->d_inputs["z"], h->d_inputs["meanx"], h->d_inputs["sdx"], (int)h->inputs["y"].size()}; }
 };
@@ -315,6 +378,8 @@ template <> struct Host<GlmM> {
     case MCU_TPL_STACKS: { typedef StacksModel M; BODY; break; }                   \
     case MCU_TPL_EQUIV: { typedef EquivModel M; BODY; break; }                     \
     case MCU_TPL_MAGNESIUM: { typedef MagnesiumModel M; BODY; break; }             \
+    case MCU_TPL_OXFORD: { typedef OxfordModel M; BODY; break; }                   \
+    case MCU_TPL_EPIL: { typedef EpilModel M; BODY; break; }                       \
     default: return fail(h, MCU_ERR_ARG, "unknown template");                      \
   }
 
@@ -348,6 +413,8 @@ TplInfo tpl_info(const mcu_ctx* h) {
     case MCU_TPL_STACKS: return tpl_info_fixed<StacksModel>();
     case MCU_TPL_EQUIV: return tpl_info_fixed<EquivModel>();
     case MCU_TPL_MAGNESIUM: return tpl_info_fixed<MagnesiumModel>();
+    case MCU_TPL_OXFORD: return tpl_info_fixed<OxfordModel>();
+    case MCU_TPL_EPIL: return tpl_info_fixed<EpilModel>();
     default: {
       TplInfo t; t.D = h->glm_d; t.P = h->glm_d; t.NN = 1;
       t.off = {0}; t.len = {h->glm_d}; t.link = {LINK_IDENT}; t.node_names = {"beta"};
@@ -376,6 +443,8 @@ std::string names_of(const mcu_ctx* h, int which) {
       case MCU_TPL_STACKS: return StacksModel::monitor_names();
       case MCU_TPL_EQUIV: return EquivModel::monitor_names();
       case MCU_TPL_MAGNESIUM: return MagnesiumModel::monitor_names();
+      case MCU_TPL_OXFORD: return OxfordModel::monitor_names();
+      case MCU_TPL_EPIL: return EpilModel::monitor_names();
       default: break;
     }
   }
@@ -795,6 +864,8 @@ int mcu_set_data(mcu_handle h, const char* name, int ndim, const int64_t* dims, 
     if (h->tpl == MCU_TPL_STACKS && n != (nm == "x" ? 63u : 21u)) return fail(h, MCU_ERR_DIM, "stacks inputs: y has 21 entries, x 21 x 3");
     if (h->tpl == MCU_TPL_BLOCKER && n != (size_t)BlockerModel::NT) return fail(h, MCU_ERR_DIM, "blocker inputs have 22 entries");
     if (h->tpl == MCU_TPL_MAGNESIUM && n != (size_t)MagnesiumModel::NTR) return fail(h, MCU_ERR_DIM, "magnesium inputs have 8 entries");
+    if (h->tpl == MCU_TPL_OXFORD && n != (size_t)OxfordModel::K) return fail(h, MCU_ERR_DIM, "oxford inputs have 120 entries");
+    if (h->tpl == MCU_TPL_EPIL && n != (nm == "y" ? 236u : nm == "V4" ? 4u : 59u)) return fail(h, MCU_ERR_DIM, "epil inputs: y has 236 entries (59 x 4), V4 has 4, Trt / Base / Age have 59");
     if (h->tpl == MCU_TPL_SALM && n != (nm == "x" ? 6u : 18u)) return fail(h, MCU_ERR_DIM, "salm inputs: y has 18 entries (3 x 6), x has 6");
     if (h->tpl == MCU_TPL_EQUIV && n != (nm == "group" ? 10u : 20u)) return fail(h, MCU_ERR_DIM, "equiv inputs: y has 20 entries (10 x 2), group has 10");
     if (h->tpl == MCU_TPL_RATS && nm != "xbar" && n != 150) return fail(h, MCU_ERR_DIM, "rats inputs have 150 entries");
@@ -853,6 +924,11 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
       if (!ok) return fail(h, MCU_ERR_UNSUPPORTED, "no conjugate full conditional for this node on the device (user-defined samplers have no device equivalent)");
     }
     if (d.n_nodes < 1 || d.n_nodes > MCU_MAX_BLOCK_NODES) return fail(h, MCU_ERR_ARG, "block must name 1..8 nodes");
+    if (d.kind == MCU_NUTS || d.kind == MCU_HMC || d.kind == MCU_MALA || d.kind == MCU_AMM) {
+      bool grad_ok = true;
+      MCU_DISPATCH(h, grad_ok = M::kGradSamplers);
+      if (!grad_ok) return fail(h, MCU_ERR_UNSUPPORTED, "NUTS / HMC / MALA / AMM are not compiled for this template (240+ state elements per chain): use AMWG / Slice / RWM blocks");
+    }
     DevBlock b; std::memset(&b, 0, sizeof(b));
     b.kind = d.kind;
     b.transform = (d.kind == MCU_SLICE_UNI || d.kind == MCU_SLICE_MULTI) ? (d.transform != 0) : (d.kind == MCU_GIBBS ? 0 : 1);   // slice.jl:47-50; others sampler files :53

@@ -79,6 +79,17 @@ struct BlockTarget {
     }
     return logf(v);
   }
+  // The same for a sequence of candidates of component i around ONE base vector (univariate slice: slice.jl:80-88): terms_at(i) is taken
+  // once at the base, every candidate costs one evaluation of the element's own terms.  A candidate outside the support gives -Inf
+  // without disturbing the base, so the shrinkage loop never falls back to full block evaluations (it did: a Uniform(0, 1) element
+  // whose interval reaches below 0 made every later evaluation of that coordinate a full one).
+  MCU_D bool comp_is_local(int i, double base_lp) const { return M::elem_local(b.elem[i]) && isfinite(base_lp); }
+  MCU_D double terms_at(int i) const { return M::elem_terms(d, s, b.elem[i], b.transform != 0); }
+  MCU_D double logf_comp_base(const double* v, int i, double base_lp, double t_base) const {
+    s[b.elem[i]] = inv(i, v[i]);
+    const double t_new = M::elem_terms(d, s, b.elem[i], b.transform != 0);
+    return isnan(t_new) ? neg_inf() : (base_lp - t_base) + t_new;
+  }
   MCU_NOINL void grad_analytic(const double* x, double* g) const {
     relist(x);
     double gj[M::D];

@@ -95,9 +95,13 @@ MCU_NOINL void slice_uni_sample(double* v, const DevBlock& b, T& tgt, Draws& rng
   for (int i = 0; i < k; ++i) {
     const double p0 = logf0 + log(rng.uniform());
     const double x = v[i];
+    // the coordinate's candidates are all evaluated against the vector the loop starts from (value logf0, component x)
+    const double base_lp = logf0;
+    const bool local = tgt.comp_is_local(i, base_lp);
+    const double t_base = local ? tgt.terms_at(i) : 0.0;
     v[i] = lower[i] + (upper[i] - lower[i]) * rng.uniform();
     while (true) {
-      logf0 = tgt.logf_comp(v, i, logf0);   // logf0 is always the value at the vector the state record holds
+      logf0 = local ? tgt.logf_comp_base(v, i, base_lp, t_base) : tgt.logf(v);
       if (!(logf0 < p0)) break;
       const double value = v[i];
       if (value < x) lower[i] = value; else upper[i] = value;

@@ -51,7 +51,9 @@ const TEMPLATES = Dict(
   8 => [:s2_2, :s2_1, :pi, :phi, :mu, :delta],                            # doc/examples/equiv.jl
   9 => [:s2, :d, :delta_new, :mu, :delta],                                # doc/examples/blocker.jl
   10 => [:beta0, :beta, :s2],                                             # doc/examples/stacks.jl
-  11 => [:priors, :mu, :theta, :pc]                                       # doc/examples/magnesium.jl (6 x 8 matrices column-major)
+  11 => [:priors, :mu, :theta, :pc],                                      # doc/examples/magnesium.jl (6 x 8 matrices column-major)
+  12 => [:alpha, :beta1, :beta2, :s2, :b, :mu],                           # doc/examples/oxford.jl
+  13 => [:a0, :alpha_Base, :alpha_Trt, :alpha_BT, :alpha_Age, :alpha_V4, :s2_b1, :s2_b, :b1, :b]   # doc/examples/epil.jl
 )                                                                         # (4 = the GLM family: pass template=4 and inputs X, y)
 
 function check(h::Ptr{Void}, rc::Cint)

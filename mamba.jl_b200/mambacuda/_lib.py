@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MCU_LIB_PATH") or os.path.join(_HERE, "libmambacuda.s
 MAX_BLOCK_NODES = 8
 
 OK, ERR_ARG, ERR_DIM, ERR_STATE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-TPL = {"line": 0, "seeds": 1, "rats": 2, "pumps": 3, "glm": 4, "surgical": 5, "dyes": 6, "salm": 7, "equiv": 8, "blocker": 9, "stacks": 10, "magnesium": 11}
+TPL = {"line": 0, "seeds": 1, "rats": 2, "pumps": 3, "glm": 4, "surgical": 5, "dyes": 6, "salm": 7, "equiv": 8, "blocker": 9, "stacks": 10, "magnesium": 11, "oxford": 12, "epil": 13}
 KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc": 5, "amm": 6, "gibbs": 7, "mala": 8}
 ADAPT = {"all": 0, "burnin": 1, "none": 2}
 PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2, "cosine": 3, "epanechnikov": 4, "biweight": 5, "triweight": 6}

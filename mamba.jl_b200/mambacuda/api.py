@@ -50,6 +50,10 @@ _TEMPLATES = {
     "stacks": dict(nodes=[("beta0", 1), ("beta", 3), ("s2", 1)], inputs=["y", "x"], outputs=["y"]),
     "magnesium": dict(nodes=[("priors", 6), ("mu", 6), ("theta", 48), ("pc", 48)], inputs=["rc", "nc", "rt", "nt"], outputs=["rcx", "rtx"],
                       output_lens=[48, 48]),
+    "oxford": dict(nodes=[("alpha", 1), ("beta1", 1), ("beta2", 1), ("s2", 1), ("b", 120), ("mu", 120)], inputs=["r1", "n1", "r0", "n0", "year"], outputs=["r0", "r1"],
+                   output_lens=[120, 120]),
+    "epil": dict(nodes=[("a0", 1), ("alpha_Base", 1), ("alpha_Trt", 1), ("alpha_BT", 1), ("alpha_Age", 1), ("alpha_V4", 1), ("s2_b1", 1), ("s2_b", 1), ("b1", 59), ("b", 236)],
+                 inputs=["y", "Trt", "Base", "Age", "V4"], outputs=["y"]),
     "glm": dict(nodes=[("beta", None)], inputs=["X", "y"], outputs=["y"]),
 }
 

@@ -32,6 +32,10 @@ STACKS_INITS = np.array([[10.0, 0.0, 0.0, 0.0, 10.0], [1.0, 1.0, 1.0, 1.0, 1.0]]
 MAGNESIUM_INITS = np.array([[1, 1, 1, 0.5, 0.5, 1] + [-0.5] * 6 + [0.0] * 48 + [0.5] * 48, [1, 1, 1, 0.5, 0.5, 1] + [0.5] * 6 + [0.0] * 48 + [0.5] * 48], dtype=float)
 
 
+OXFORD_INITS = np.array([[0, 0, 0, 1] + [0] * 240, [1, 1, 1, 10] + [0] * 240], dtype=float)       # doc/examples/oxford.jl:86-93 (alpha, beta1, beta2, s2, b[120], mu[120])
+EPIL_INITS = np.array([[0] * 6 + [1, 1] + [0] * 295, [1] * 6 + [10, 10] + [0] * 295], dtype=float)  # doc/examples/epil.jl:115-122 (a0, coefficients, s2_b1, s2_b, b1[59], b[236])
+
+
 def pumps_inits(seed=1):
     rng = np.random.default_rng(seed)   # doc/examples/pumps.jl:43-49 draws theta from Gamma
     return np.array([[1.0, 1.0] + list(rng.gamma(1.0, 1.0, 10)), [10.0, 10.0] + list(rng.gamma(10.0, 0.1, 10))])
@@ -109,6 +113,16 @@ SCHEMES = {
     # every block on the link scale: log for priors[1] / priors[6], two-sided logit for the Uniform priors, mu and pc
     "magnesium_transformed": ("magnesium", [dict(kind="amwg", nodes=[2], scale=0.1), dict(kind="amwg", nodes=[1, 0], scale=0.2),
                                             dict(kind="slice_uni", nodes=[3], scale=1.0, transform=1), dict(kind="nuts", nodes=[0, 1])], MAGNESIUM_INITS),
+    # doc/examples/oxford.jl:97-100: AMWG([:alpha, :beta1, :beta2], 1.0), Slice(:s2, 1.0), Slice(:mu, 1.0), Slice(:b, 1.0) — 120-dimensional multivariate slices
+    "oxford": ("oxford", [dict(kind="amwg", nodes=[0, 1, 2], scale=1.0), dict(kind="slice_multi", nodes=[3], scale=1.0), dict(kind="slice_multi", nodes=[5], scale=1.0),
+                          dict(kind="slice_multi", nodes=[4], scale=1.0)], OXFORD_INITS),
+    "oxford_componentwise": ("oxford", [dict(kind="amwg", nodes=[0, 1, 2], scale=0.5), dict(kind="slice_uni", nodes=[3], scale=1.0, transform=1), dict(kind="amwg", nodes=[5], scale=0.5),
+                                        dict(kind="slice_uni", nodes=[4], scale=1.0)], OXFORD_INITS),
+    # doc/examples/epil.jl:126-130: AMWG([:a0, :alpha_Base, :alpha_Trt, :alpha_BT, :alpha_Age, :alpha_V4], 0.1), Slice(:b1, 0.5), Slice(:b, 0.5), Slice([:s2_b1, :s2_b], 1.0)
+    "epil": ("epil", [dict(kind="amwg", nodes=[0, 1, 2, 3, 4, 5], scale=0.1), dict(kind="slice_multi", nodes=[8], scale=0.5), dict(kind="slice_multi", nodes=[9], scale=0.5),
+                      dict(kind="slice_multi", nodes=[6, 7], scale=1.0)], EPIL_INITS),
+    "epil_componentwise": ("epil", [dict(kind="amwg", nodes=[0, 1, 2, 3, 4, 5], scale=0.1), dict(kind="amwg", nodes=[8], scale=0.3), dict(kind="slice_uni", nodes=[9], scale=0.5),
+                                    dict(kind="amwg", nodes=[6, 7], scale=0.5)], EPIL_INITS),
     # doc/examples/pumps.jl:52-53
     "pumps_slice": ("pumps", [dict(kind="slice_uni", nodes=[0, 1], scale=1.0), dict(kind="slice_uni", nodes=[2], scale=1.0)], None),
     "pumps_amwg_nuts": ("pumps", [dict(kind="amwg", nodes=[0, 1], scale=0.5), dict(kind="nuts", nodes=[2])], None),

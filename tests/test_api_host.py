@@ -30,7 +30,7 @@ def test_setsamplers_and_block_descs(mcu_built):
     with pytest.raises(api.ArgumentError, match="no device equivalent"):
         api.setsamplers(m, [lambda model, block: None])      # Sampler([:beta], closure): src/samplers/sampler.jl:20-24
     with pytest.raises(api.ArgumentError, match="no device template"):
-        api.Model("epil")                                    # doc/examples/epil.jl has no compiled template
+        api.Model("kidney")                                  # doc/examples/kidney.jl has no compiled template
 
 
 def test_mcmc_argument_checks(mcu_built):

@@ -634,3 +634,76 @@ def test_gpu_magnesium_block_densities_links_and_gradients_match_golden(oracle, 
     st_, _, _ = eng2.get_state()
     assert (st_[:, 1:3] > 0).all() and (st_[:, 1:3] < 50).all() and (st_[:, 3:5] > 0).all() and (st_[:, 3:5] < 1).all()
     assert (np.abs(st_[:, 6:12]) < 10).all() and (st_[:, 60:] > 0).all() and (st_[:, 60:] < 1).all() and (st_[:, [0, 5]] > 0).all()
+
+
+# ---- oxford and epil: 244 / 303 unobserved elements per chain (doc/examples/oxford.jl, doc/examples/epil.jl) -------------------------
+LARGE_BLOCKS = {
+    "oxford": {"amwg_alpha_beta1_beta2": ("oxford", 0), "slice_s2": ("oxford", 1), "slice_mu": ("oxford", 2), "slice_b": ("oxford", 3),
+               "s2_transformed": ("oxford_componentwise", 1)},
+    "epil": {"amwg_coefficients": ("epil", 0), "slice_b1": ("epil", 1), "slice_b": ("epil", 2), "slice_s2_b1_s2_b": ("epil", 3)},
+}
+LARGE_OBS = {"oxford": ["r0", "r1"], "epil": ["y"]}
+
+
+@pytest.fixture(scope="module")
+def gold_large():
+    with open(os.path.join(GOLD, "block_logpdf_large.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("tpl", ["oxford", "epil"])
+def test_oracle_oxford_epil_block_densities_match_golden(oracle, gold_large, tpl):
+    S = np.array(gold_large[tpl]["states"])
+    for key, (scheme, bi) in LARGE_BLOCKS[tpl].items():
+        t, blocks, _ = helpers.scheme(scheme)
+        o = oracle.Oracle(t); o.set_scheme(_oracle_blocks(blocks))
+        np.testing.assert_allclose(o.logpdf(bi, S), gold_large[tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+    t, blocks, _ = helpers.scheme(tpl)
+    o = oracle.Oracle(t); o.set_scheme(_oracle_blocks(blocks))
+    nn = {"oxford": 6, "epil": 10}[tpl]
+    for q, key in enumerate(LARGE_OBS[tpl]):
+        np.testing.assert_allclose(o.logpdf_nodes(1 << (nn + q), S), gold_large[tpl]["logpdf"][key], rtol=1e-11)
+    # analytic gradient of the joint against central differences of the density of one block that holds every parameter node
+    o = oracle.Oracle(t); o.set_scheme(_oracle_blocks([dict(kind="nuts", nodes=list(range(min(nn, 8))))] if nn <= 8 else
+                                                      [dict(kind="nuts", nodes=list(range(8))), dict(kind="nuts", nodes=[8, 9])]))
+    for bi in range(1 if nn <= 8 else 2):
+        _, g_a = o.gradlogpdf(bi, S, mode=0)
+        _, g_c = o.gradlogpdf(bi, S, mode=2)
+        np.testing.assert_allclose(g_a, g_c, rtol=2e-5, atol=1e-5 * np.abs(g_c).max())
+    if tpl == "epil":   # monitored Logical column alpha0 (epil.jl:85-91) at fixed states
+        o2 = oracle.Oracle(t); o2.set_scheme(_oracle_blocks([dict(kind="rwm", nodes=[0], scale=0.0)]))
+        out, _, _ = o2.run(len(S), S, 1, burnin=0, thin=1, seed=1)
+        assert o2.names() == ["alpha_Base", "alpha_Trt", "alpha_BT", "alpha_Age", "alpha_V4", "alpha0", "s2_b1", "s2_b"]
+        np.testing.assert_allclose(out[0, 5, :], gold_large["epil"]["logpdf"]["alpha0"], rtol=1e-12)
+        np.testing.assert_allclose(out[0, :5, :].T, S[:, 1:6], rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tpl", ["oxford", "epil"])
+def test_gpu_oxford_epil_block_densities_match_golden(oracle, gold_large, tpl):
+    from mambacuda.engine import Engine, MambaCudaError
+    S = np.array(gold_large[tpl]["states"])
+    for key, (scheme, bi) in LARGE_BLOCKS[tpl].items():
+        t, blocks, _ = helpers.scheme(scheme)
+        eng = Engine(t, 4); eng.set_scheme(blocks)
+        np.testing.assert_allclose(eng.logpdf(bi, S), gold_large[tpl]["logpdf"][key], rtol=1e-11, atol=1e-9, err_msg=key)
+        eng.close()
+    t, blocks, _ = helpers.scheme(tpl)
+    eng = Engine(t, len(S)); eng.set_scheme(blocks)
+    nn, nf = eng.factor_counts()
+    for q, key in enumerate(LARGE_OBS[tpl]):
+        np.testing.assert_allclose(eng.logpdf_nodes(1 << (nn + q), S), gold_large[tpl]["logpdf"][key], rtol=1e-11)
+    # the analytic gradient entry point works at this state size too (a batched density call, not a sampler)
+    o = oracle.Oracle(t); o.set_scheme(_oracle_blocks(blocks))
+    k = o.unlist(0, S[0]).size
+    lp_g, g_g = eng.gradlogpdf(0, S, k)
+    lp_o, g_o = o.gradlogpdf(0, S, mode=0)
+    np.testing.assert_allclose(lp_g, lp_o, rtol=1e-12)
+    np.testing.assert_allclose(g_g, g_o, rtol=1e-10, atol=1e-9)
+    if tpl == "epil":
+        e2 = Engine(t, len(S)); e2.set_scheme([dict(kind="rwm", nodes=[0], scale=0.0)]); e2.set_inits(S)
+        out = e2.run(1, burnin=0, thin=1)
+        np.testing.assert_allclose(out[0, 5, :], gold_large["epil"]["logpdf"]["alpha0"], rtol=1e-12)
+    # gradient-based samplers are not compiled for templates of this size: a clear error, no silent fallback
+    with pytest.raises(MambaCudaError, match="not compiled for this template"):
+        eng.set_scheme([dict(kind="nuts", nodes=[0])])
