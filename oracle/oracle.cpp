@@ -514,6 +514,8 @@ double orc_line_logf(const double* x, double* grad) {
 // which: 0 AMWG(1.0) [doc/samplers/amwg.jl:28-35], 1 NUTS [doc/samplers/nuts.jl:34-43],
 //        2 SliceUnivariate(width 1,1,2), 3 SliceMultivariate [doc/samplers/slice.jl:31-40],
 //        4 AMWG(beta)+SliceMultivariate(log s2; 5.0) [doc/examples/line_amwg_slice.jl:35-43]
+//        5 AMM(eye(3)) [doc/samplers/amm.jl:28-35], 6 / 7 HMC(0.1, 50) without / with Sigma = eye(3) [doc/samplers/hmc.jl:37-51],
+//        8 / 9 MALA(0.1) without / with Sigma = eye(3) [doc/samplers/mala.jl:37-50], 10 RWM([0.5, 0.25, 1.0], SymUniform) [doc/samplers/rwm.jl:28-35]
 // out [n × 3] column-major, columns b0, b1, s2 = exp(theta3).
 int orc_standalone_line(int which, uint64_t seed, int64_t n, int64_t burnin, double* out) {
   PhiloxRng rng(seed, 0);
@@ -524,6 +526,9 @@ int orc_standalone_line(int which, uint64_t seed, int64_t n, int64_t burnin, dou
   Tune tn;
   if (which == 1) { rng.seek(0, 0, 0); tn.epsilon = nutsepsilon(theta, lfg, rng); tn.target = 0.6; }
   Tune tb; tb.accept.assign(2, 0); tb.sigma.assign(2, 1.0);
+  Tune tm; tm.beta = 0.05; tm.scale = 2.38; chol_lower({1, 0, 0, 0, 1, 0, 0, 0, 1}, 3, tm.SigmaL);   // AMMVariate(x, eye(3), logf)
+  const Vec eye3 = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  Vec eyeL; chol_lower(eye3, 3, eyeL);
   for (int64_t i = 1; i <= n; ++i) {
     rng.seek((uint32_t)i, 0, 0);
     switch (which) {
@@ -540,6 +545,12 @@ int orc_standalone_line(int which, uint64_t seed, int64_t n, int64_t burnin, dou
         theta = {beta[0], beta[1], l[0]};
         break;
       }
+      case 5: amm_sample(theta, tm, logf, i <= burnin, rng); break;
+      case 6: hmc_sample(theta, 0.1, 50, Vec(), lfg, rng); break;
+      case 7: hmc_sample(theta, 0.1, 50, eyeL, lfg, rng); break;
+      case 8: mala_sample(theta, 0.1, Vec(), lfg, rng); break;
+      case 9: mala_sample(theta, 0.1, eyeL, lfg, rng); break;
+      case 10: rwm_sample(theta, {0.5, 0.25, 1.0}, 1, logf, rng); break;
       default: return -1;
     }
     out[(i - 1)] = theta[0]; out[(i - 1) + n] = theta[1]; out[(i - 1) + 2 * n] = std::exp(theta[2]);

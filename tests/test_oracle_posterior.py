@@ -31,6 +31,17 @@ def test_line_standalone_nuts_and_slice(oracle):
         within_3_mcse(oracle.summarystats(c, 0, 100), ["b0", "b1", "s2"], ref)
 
 
+def test_line_standalone_amm_hmc_mala_rwm(oracle):
+    # the remaining stand-alone sampler demos of the reference, with the scripts' own settings, on the closed-form log posterior they all share
+    # (doc/samplers/amm.jl:28-35 AMMVariate(eye(3)), hmc.jl:37-51 HMC(0.1, 50) without / with Sigma = eye(3), mala.jl:37-50 MALA(0.1) without / with
+    # Sigma, rwm.jl:28-35 RWM([0.5, 0.25, 1.0], SymUniform)): the .rst pages publish no output, so they are pinned to the tutorial table of the same
+    # posterior (doc/tutorial.rst:432-436)
+    ref = {"b0": (0.5971183, 0.016925598), "b1": (0.8017036, 0.004793345), "s2": (1.2203777, 0.101798287)}
+    for which, n, burn, drop in ((5, 5000, 1000, 1000), (6, 5000, 0, 200), (7, 5000, 0, 200), (8, 20000, 0, 2000), (9, 20000, 0, 2000), (10, 20000, 0, 2000)):
+        c = np.stack([oracle.standalone_line(which, n, burn, seed=100 + s)[drop:] for s in range(6)], axis=2)
+        within_3_mcse(oracle.summarystats(c, 0, 100), ["b0", "b1", "s2"], ref)
+
+
 def test_line_model_based_nuts_slice(oracle):
     # doc/tutorial/line.jl:48-49,99: scheme1 = [NUTS(:beta), Slice(:s2, 3.0)], 3 x 10,000, burnin 250, thin 2
     ref = {"beta[1]": (0.5971183, 0.016925598), "beta[2]": (0.8017036, 0.004793345), "s2": (1.2203777, 0.101798287)}
