@@ -280,6 +280,8 @@ def small_config(ctx, name, scheme_name, C_total, iters, burnin, thin, flop_per_
     # warm-up launch (module load, attribute calls), then per-chain host inits: the script's records cycled + jitter, materialised on the device once
     eng.set_inits(inits, jitter_sd=jitter if C > 16 else 0.0)
     eng.run(min(iters, 20), burnin=min(burnin, 10), thin=1, store=False, out=False)
+    if ctx.world * C >= 2:
+        eng.diag_global(0.05, True)               # first collective of this handle's communicator: NCCL sets its connections up here, not in the timed call
     eng.set_inits(inits, jitter_sd=jitter if C > 16 else 0.0)
     st0, _, _ = eng.get_state()
     keep_in, host_in = ctx.pinned((C, D)); host_in[:] = st0
@@ -287,7 +289,7 @@ def small_config(ctx, name, scheme_name, C_total, iters, burnin, thin, flop_per_
     import ctypes as Ct
     ctx.l2_flush.fill_(1)
     sampler = ClockSampler(ctx.local_rank).start()
-    w0, _ = eng.work_count()
+    w0, _ = eng.work_count(); cap0 = eng.nuts_cap_hits
     ctx.sync_all(); t0 = time.perf_counter()
     eng.set_inits(host_in)                                                         # H2D
     eng.run(iters, burnin=burnin, thin=thin, store=False, out=False)
@@ -299,7 +301,7 @@ def small_config(ctx, name, scheme_name, C_total, iters, burnin, thin, flop_per_
     eng._chk(eng.L.mcu_get_state(eng.h, host_out.ctypes.data_as(Ct.POINTER(Ct.c_double)), None, Ct.byref(it)))   # D2H
     ctx.sync_all(); dt = time.perf_counter() - t0
     clocks = sampler.stop()
-    w1, _ = eng.work_count()
+    w1, _ = eng.work_count(); cap1 = eng.nuts_cap_hits
     dt, kms, diag_s = ctx.max_over_ranks(dt, kms, t2 - t1)
     (leap,) = ctx.sum_over_ranks(w1 - w0)
     chains_total = C * ctx.world
@@ -326,6 +328,7 @@ def small_config(ctx, name, scheme_name, C_total, iters, burnin, thin, flop_per_
         if unit_is_leapfrog:
             out["config"]["leapfrogs_all_gpus"] = int(leap)
             out["config"]["leapfrogs_per_chain_iter"] = leap / (chains_total * iters)
+            out["config"]["nuts_depth_cap_hits_per_chain_iter"] = (cap1 - cap0) / (C * iters)     # reference: no cap (nuts.jl:106-124); device: 10 doublings
         if ess_all is not None:
             out["ess"] = {"ess_per_sec_min": float(np.nanmin(ess_all) / dt), "ess_min": float(np.nanmin(ess_all)),
                           "definition": "(SD/MCSE_bm)^2 over the kept draws of all chains, batch size 100 (batches never straddle chains), uncapped; per second of the end-to-end call"}
@@ -368,11 +371,14 @@ def glm_config(ctx, args):
     if ref is not eng:
         ref.close()
     # NUTS run, end to end: per-chain initial positions from pinned host memory, diagnostics over all GPUs, final states back
+    eng.set_inits(np.zeros((1, d)), jitter_sd=0.1)
+    eng.run(2, burnin=1, thin=1, store=False, out=False)      # warm-up: tick-engine buffers, and the first collective of the communicator
+    eng.diag_global(0.05, False)
     keep_in, host_in = ctx.pinned((C, d)); host_in[:] = 0.1 * np.random.default_rng(7 + ctx.rank).standard_normal((C, d))
     keep_out, host_out = ctx.pinned((C, d))
     import ctypes as Ct
     sampler = ClockSampler(ctx.local_rank).start()
-    w0, k0 = eng.work_count(); s0 = eng.glm_pass_slots; l0 = eng.launch_count()
+    w0, k0 = eng.work_count(); s0 = eng.glm_pass_slots; cap0 = eng.nuts_cap_hits; l0 = eng.launch_count()
     ctx.sync_all(); t0 = time.perf_counter()
     eng.set_inits(host_in)
     eng.run(iters, burnin=iters // 2, thin=1, store=False, out=False)
@@ -382,7 +388,7 @@ def glm_config(ctx, args):
     eng._chk(eng.L.mcu_get_state(eng.h, host_out.ctypes.data_as(Ct.POINTER(Ct.c_double)), None, Ct.byref(it)))
     ctx.sync_all(); dt = time.perf_counter() - t0
     clocks = sampler.stop()
-    w1, k1 = eng.work_count(); s1 = eng.glm_pass_slots; launches = eng.launch_count() - l0
+    w1, k1 = eng.work_count(); s1 = eng.glm_pass_slots; cap1 = eng.nuts_cap_hits; launches = eng.launch_count() - l0
     dt, kms = ctx.max_over_ranks(dt, kms)
     out = None
     if ctx.rank == 0:
@@ -397,6 +403,7 @@ def glm_config(ctx, args):
                        "iters": iters, "burnin": iters // 2, "gradient_passes": int(ticks), "tick_ms": kms / max(ticks, 1), "pass_ms": pass_ms,
                        "useful_chain_gradients": int(w1 - w0), "pass_chain_slots": int(s1 - s0), "useful_fraction": (w1 - w0) / max(1, s1 - s0),
                        "useful_fraction_without_compaction": (w1 - w0) / max(1, ticks * C),
+                       "nuts_depth_cap_hits_per_chain_iter": (cap1 - cap0) / (C * iters),
                        "l2": "X (449 MB packed) exceeds L2; every pass streams it from HBM",
                        "psrf_max": float(np.nanmax(psrf[:, 0])), "posterior_mean_abs_err_vs_truth": float(np.mean(np.abs(summ[:, 0] - beta_true)))},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

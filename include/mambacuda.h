@@ -328,10 +328,12 @@ int mcu_device_count(void);
 double mcu_fp64_peak_tflops(mcu_handle h);
 /* Number of kernel launches issued by this handle since creation (bench "gpu_launches").      */
 int64_t mcu_launch_count(mcu_handle h);
-/* Work done by the gradient-based fused paths since the handle was created: leapfrog steps of the warp-per-chain rats kernel / chain-gradients
- * the GLM tick engine actually consumed (a finished chain idles until its 128-chain group is compacted away), the number of GLM ticks
- * (gradient passes) and the chain slots those passes carried in total: gradients / glm_pass_slots = the useful fraction of the tensor-core work. */
-int mcu_work_count(mcu_handle h, uint64_t* gradients, int64_t* glm_ticks, uint64_t* glm_pass_slots);
+/* Work counters of the gradient-based fused paths since the handle was created, out[4]:
+ *   [0] gradient evaluations: leapfrog steps of the warp-per-chain rats kernel / chain-gradients the GLM tick engine actually consumed
+ *   [1] GLM ticks (gradient passes)   [2] chain slots those passes carried in total ([0] / [2] = useful fraction of the tensor-core work; a
+ *       finished chain idles until its 128-chain group is compacted away)
+ *   [3] NUTS iterations that stopped at the tree-depth cap (max_depth doublings; the reference has no cap, src/samplers/nuts.jl:106-124)  */
+int mcu_work_count(mcu_handle h, uint64_t* out);
 /* Device time in ms of the sampler kernels of the last mcu_run (CUDA events on the launching stream). */
 double mcu_last_kernel_ms(mcu_handle h);
 

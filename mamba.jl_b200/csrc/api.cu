@@ -80,6 +80,7 @@ struct mcu_ctx {
   unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
   unsigned long long* d_work = nullptr;   // device counter of gradient evaluations (rats_warp leapfrogs, GLM useful chain-gradients)
+  bool g_reset = false;   // the GLM tick-engine records must be re-initialised before the next run (new inits / state)
   bool pending = false;   // an mcu_run(..., MCU_RUN_ASYNC) has not been waited for yet
   // cross-GPU diagnostics (mcu_comm_init / mcu_diag_global): NCCL communicator of this handle's rank, monitored-column links on the device
   void* comm = nullptr; int comm_rank = 0, comm_nranks = 1;
@@ -579,8 +580,27 @@ int glm_tc_choose_nslab(long long N, long long C, int sms) {
   return (int)ns;
 }
 
+int reset_glm_records(mcu_ctx* h) {
+  const size_t C = (size_t)h->C, d = (size_t)h->D;
+  const size_t nsc = glm_tick_scalar_slots(), nv = glm_tick_vector_slots();
+  CK(cudaMemsetAsync(h->g_sc, 0, sizeof(double) * nsc * C, h->stream));
+  CK(cudaMemsetAsync(h->g_vec, 0, sizeof(double) * nv * d * C, h->stream));
+  CK(cudaMemsetAsync(h->g_req, 0, sizeof(double) * d * C, h->stream));
+  CK(cudaMemsetAsync(h->g_lp, 0, sizeof(double) * C, h->stream));
+  CK(cudaMemsetAsync(h->g_grad, 0, sizeof(double) * d * C, h->stream));
+  CK(cudaMemsetAsync(h->g_nactive, 0, 4 * sizeof(int), h->stream));
+  // resume point: every chain's own iteration counter starts at the handle's
+  if (h->iter > 0) {
+    std::vector<double> it(C, (double)h->iter);
+    CK(cudaMemcpyAsync(h->g_sc + 1 * C, it.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));   // slot 1 = SL_ITER
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->g_reset = false;
+  return MCU_OK;
+}
+
 int ensure_glm_buffers(mcu_ctx* h) {
-  if (h->g_sc) return MCU_OK;
+  if (h->g_sc) return h->g_reset ? reset_glm_records(h) : MCU_OK;
   const size_t C = (size_t)h->C, d = (size_t)h->D;
   const size_t nsc = glm_tick_scalar_slots(), nv = glm_tick_vector_slots();
   int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
@@ -628,17 +648,7 @@ int ensure_glm_buffers(mcu_ctx* h) {
     CK(cudaMemcpyAsync(h->g_xty, xty.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
-  CK(cudaMemsetAsync(h->g_sc, 0, sizeof(double) * nsc * C, h->stream));
-  CK(cudaMemsetAsync(h->g_vec, 0, sizeof(double) * nv * d * C, h->stream));
-  CK(cudaMemsetAsync(h->g_req, 0, sizeof(double) * d * C, h->stream));
-  CK(cudaMemsetAsync(h->g_lp, 0, sizeof(double) * C, h->stream));
-  CK(cudaMemsetAsync(h->g_grad, 0, sizeof(double) * d * C, h->stream));
-  // resume point: every chain's own iteration counter starts at the handle's
-  if (h->iter > 0) {
-    std::vector<double> it(C, (double)h->iter);
-    CK(cudaMemcpyAsync(h->g_sc + 1 * C, it.data(), sizeof(double) * C, cudaMemcpyHostToDevice, h->stream));   // slot 1 = SL_ITER
-    CK(cudaStreamSynchronize(h->stream));
-  }
+  { const int rc = reset_glm_records(h); if (rc) return rc; }
   return MCU_OK;
 }
 
@@ -1037,7 +1047,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   h->iter = 0; h->has_inits = true; h->samples_kept = 0;
-  free_glm_buffers(h);
+  h->g_reset = true;   // the tick engine's chain records start over (buffers are kept: no cudaMalloc / cudaFree per mcmc() call)
   return MCU_OK;
 }
 
@@ -1091,7 +1101,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
   a.logit_mask = h->logit_mask;
-  if (!h->d_work) { CK(cudaMalloc(&h->d_work, sizeof(unsigned long long))); CK(cudaMemset(h->d_work, 0, sizeof(unsigned long long))); }
+  if (!h->d_work) { CK(cudaMalloc(&h->d_work, 2 * sizeof(unsigned long long))); CK(cudaMemset(h->d_work, 0, 2 * sizeof(unsigned long long))); }
   a.work = h->d_work;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
   bool fast = h->seeds_fast_ok && !(flags & MCU_RUN_FORCE_GENERIC) && h->rng_mode == MCU_RNG_PHILOX;
@@ -1247,7 +1257,7 @@ int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   h->iter = iter; h->has_inits = true; h->samples_kept = 0;
-  free_glm_buffers(h);
+  h->g_reset = true;
   return MCU_OK;
 }
 
@@ -1705,13 +1715,11 @@ int mcu_glm_gradient(mcu_handle h, int impl, const double* beta, double* lp, dou
 }
 
 int64_t mcu_launch_count(mcu_handle h) { return h ? h->launches : 0; }
-int mcu_work_count(mcu_handle h, uint64_t* gradients, int64_t* glm_ticks, uint64_t* glm_pass_slots) {
-  if (!h) return MCU_ERR_ARG;
-  unsigned long long w = 0;
-  if (h->d_work) { CK(cudaSetDevice(h->device)); CK(cudaMemcpy(&w, h->d_work, sizeof(w), cudaMemcpyDeviceToHost)); }
-  if (gradients) *gradients = w;
-  if (glm_ticks) *glm_ticks = h->ticks;
-  if (glm_pass_slots) *glm_pass_slots = h->pass_slots;
+int mcu_work_count(mcu_handle h, uint64_t* out) {
+  if (!h || !out) return MCU_ERR_ARG;
+  unsigned long long w[2] = {0, 0};
+  if (h->d_work) { CK(cudaSetDevice(h->device)); CK(cudaMemcpy(w, h->d_work, sizeof(w), cudaMemcpyDeviceToHost)); }
+  out[0] = w[0]; out[1] = (uint64_t)h->ticks; out[2] = h->pass_slots; out[3] = w[1];
   return MCU_OK;
 }
 double mcu_last_kernel_ms(mcu_handle h) { return h ? h->last_ms : 0.0; }

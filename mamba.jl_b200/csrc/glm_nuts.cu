@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) glm_advance_kernel(GlmTickArgs a) {
         const int jn = j + 1;
         n += Tn;
         bool s = Ts && nouturn(V_XM, V_XP, V_RM, V_RP);
-        if (jn >= a.max_depth) s = false;
+        if (s && jn >= a.max_depth) { s = false; if (lane == 0 && a.work) atomicAdd(a.work + 1, 1ull); }   // depth cap bound (reference: no cap, nuts.jl:106-124)
         t_alpha = alpha; t_nalpha = nalpha;
         SCW(SL_N, n); SCW(SL_J, (double)jn);
         if (s) {           // next doubling

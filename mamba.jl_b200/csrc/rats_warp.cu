@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
 #pragma unroll
   for (int k = 0; k < NOBS; ++k) { ch.y[k] = cfg.y[k][lane]; ch.xo[k] = cfg.x[k][lane]; }
 
-  unsigned long long n_leap = 0;      // leapfrogs of this warp's chains (warp-uniform): the work unit of the roofline (mcu_work_count)
+  unsigned long long n_leap = 0, n_cap = 0;      // leapfrogs of this warp's chains (warp-uniform): the work unit of the roofline (mcu_work_count)
   for (long long c = gw; c < a.n_chains; c += GW) {
     WRng rng;
     rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
           } else {
             s = false;
           }
-          if (j >= cfg.max_depth) s = false;
+          if (s && j >= cfg.max_depth) { s = false; ++n_cap; }   // the reference would keep doubling (nuts.jl:106-124): counted, mcu_work_count
         }
         t_alpha = alpha; t_nalpha = nalpha;
         x = vld(e_v, lane);
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
     if (lane < NR) { a.state[(size_t)(5 + lane) * C + c] = x.a; a.state[(size_t)(5 + NR + lane) * C + c] = x.b; }
     __syncwarp();
   }
-  if (lane == 0 && a.work && n_leap) atomicAdd(a.work, n_leap);
+  if (lane == 0 && a.work && n_leap) { atomicAdd(a.work, n_leap); if (n_cap) atomicAdd(a.work + 1, n_cap); }
 }
 
 }  // namespace

@@ -123,7 +123,7 @@ def lib():
     L.mcu_comm_size.argtypes = [vp, ip, ip]
     L.mcu_diag_global.argtypes = [vp, C.c_double, C.c_int, dp, dp, ip]
     L.mcu_wait.argtypes = [vp]
-    L.mcu_work_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(i64), C.POINTER(C.c_uint64)]
+    L.mcu_work_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mcu_get_samples.argtypes = [vp, dp]
     _lib = L
     return L

@@ -342,11 +342,12 @@ class Engine:
         return self.L.mcu_fp64_peak_tflops(self.h)
 
     def work_count(self):
-        """(gradient evaluations of the fused gradient-based paths, GLM ticks) since the handle was created."""
-        w, t, sl = C.c_uint64(), C.c_int64(), C.c_uint64()
-        self._chk(self.L.mcu_work_count(self.h, C.byref(w), C.byref(t), C.byref(sl)))
-        self.glm_pass_slots = sl.value
-        return w.value, t.value
+        """(gradient evaluations of the fused gradient-based paths, GLM ticks) since the handle was created; also sets
+        self.glm_pass_slots and self.nuts_cap_hits (mcu_work_count)."""
+        out = (C.c_uint64 * 4)()
+        self._chk(self.L.mcu_work_count(self.h, out))
+        self.glm_pass_slots = int(out[2]); self.nuts_cap_hits = int(out[3])
+        return int(out[0]), int(out[1])
 
     def launch_count(self):
         return self.L.mcu_launch_count(self.h)

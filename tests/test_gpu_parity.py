@@ -947,3 +947,40 @@ def test_oxford_and_epil_posteriors_are_close_to_the_published_tables(oracle, na
         j = names.index(nm)
         assert abs(summ[j, 0] - mean) < (2.0 if nm.startswith("s2") else 1.0) * sd, (nm, summ[j, 0], mean, sd)
     assert np.isfinite(eng.gelman(0.05, True)).all()
+
+
+# ---- the north_star shim on the BASELINE models: both sides consume the same host-supplied uniform stream ----------------------------
+@pytest.mark.parametrize("name,iters,burnin,per_iter", [("seeds_amwg", 150, 75, 90), ("seeds_amm", 120, 60, 90), ("rats_slice_amwg", 60, 30, 400), ("pumps_gibbs_amwg", 150, 75, 120)])
+def test_external_stream_on_the_baseline_models(oracle, name, iters, burnin, per_iter):
+    # mcu_set_rng_mode(EXTERNAL): draws are read sequentially from u[chain][...] (a normal takes two, cosine branch) in the order the
+    # reference's sampler consumes rand() / randn() — what a Julia shim that overrides rand / randn hands over.  Schemes with a fused
+    # kernel run on the generic kernel in this mode (the fused kernels address the counter-based stream by position).
+    eng, orc, inits = make_pair(oracle, name, 8)
+    u = np.random.default_rng(7).uniform(size=(8, per_iter * iters))
+    eng.set_external_stream(u)
+    eng.set_inits(inits)
+    out_g = eng.run(iters, burnin=burnin, thin=1)
+    st_g, tune_g, _ = eng.get_state()
+    out_o, st_o, tune_o, marg = orc.run(8, inits, iters, burnin=burnin, thin=1, ext_u=u, margins=True)
+    assert_same_run((out_g, st_g, tune_g), (out_o, st_o, tune_o, marg), iters, burnin, 1, tune_rtol=1e-4 if "amm" in name else 1e-6)
+
+
+def test_external_stream_nuts_steps_and_exhaustion(oracle):
+    # NUTS on the shim stream (rats, 62-dimensional block; the number of draws per iteration depends on the tree): step-by-step decisions and
+    # trajectories agree over a short horizon (dual averaging amplifies rounding from one iteration to the next: see resync tests), and a stream
+    # that runs dry is an error, not a silently degenerate chain
+    from mambacuda.engine import MambaCudaError
+    eng, orc, inits = make_pair(oracle, "rats_nuts_slice", 8)
+    tpl, blocks, _ = helpers.scheme("rats_nuts_slice")
+    ob = [helpers.oracle_block(b) for b in blocks]; ob[0]["max_depth"] = 10
+    orc.set_scheme(ob)
+    u = np.random.default_rng(9).uniform(size=(8, 60000))
+    eng.set_external_stream(u); eng.set_inits(inits)
+    out_g = eng.run(6, burnin=4, thin=1)
+    out_o, st_o, tune_o = orc.run(8, inits, 6, burnin=4, thin=1, ext_u=u)
+    ok = [np.allclose(out_g[:, :, c], out_o[:, :, c], rtol=1e-5, atol=1e-8) for c in range(8)]
+    assert sum(ok) >= 7, ok
+    short = np.random.default_rng(9).uniform(size=(8, 50))
+    eng.set_external_stream(short); eng.set_inits(inits)
+    with pytest.raises(MambaCudaError, match="external uniform stream exhausted"):
+        eng.run(6, burnin=4, thin=1)
