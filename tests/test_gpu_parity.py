@@ -966,9 +966,10 @@ def test_external_stream_on_the_baseline_models(oracle, name, iters, burnin, per
 
 
 def test_external_stream_nuts_steps_and_exhaustion(oracle):
-    # NUTS on the shim stream (rats, 62-dimensional block; the number of draws per iteration depends on the tree): step-by-step decisions and
-    # trajectories agree over a short horizon (dual averaging amplifies rounding from one iteration to the next: see resync tests), and a stream
-    # that runs dry is an error, not a silently degenerate chain
+    # NUTS on the shim stream (rats, 62-dimensional block; the number of draws per iteration depends on the tree): decisions and trajectories of
+    # the first iterations agree (nutsepsilon, two adaptive and two non-adaptive iterations; longer horizons are covered step by step by the resync
+    # tests because dual averaging amplifies rounding from one iteration to the next), and a stream that runs dry is an error, not a silently
+    # degenerate chain
     from mambacuda.engine import MambaCudaError
     eng, orc, inits = make_pair(oracle, "rats_nuts_slice", 8)
     tpl, blocks, _ = helpers.scheme("rats_nuts_slice")
@@ -976,10 +977,10 @@ def test_external_stream_nuts_steps_and_exhaustion(oracle):
     orc.set_scheme(ob)
     u = np.random.default_rng(9).uniform(size=(8, 60000))
     eng.set_external_stream(u); eng.set_inits(inits)
-    out_g = eng.run(6, burnin=4, thin=1)
-    out_o, st_o, tune_o = orc.run(8, inits, 6, burnin=4, thin=1, ext_u=u)
-    ok = [np.allclose(out_g[:, :, c], out_o[:, :, c], rtol=1e-5, atol=1e-8) for c in range(8)]
-    assert sum(ok) >= 7, ok
+    out_g = eng.run(4, burnin=2, thin=1)
+    st_g, tune_g, _ = eng.get_state()
+    out_o, st_o, tune_o, marg = orc.run(8, inits, 4, burnin=2, thin=1, ext_u=u, margins=True)
+    assert_same_run((out_g, st_g, tune_g), (out_o, st_o, tune_o, marg), 4, 2, 1, rtol=1e-6, tune_rtol=1e-5)
     short = np.random.default_rng(9).uniform(size=(8, 50))
     eng.set_external_stream(short); eng.set_inits(inits)
     with pytest.raises(MambaCudaError, match="external uniform stream exhausted"):
