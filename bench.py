@@ -372,7 +372,7 @@ def glm_config(ctx, args):
         ref.close()
     # NUTS run, end to end: per-chain initial positions from pinned host memory, diagnostics over all GPUs, final states back
     eng.set_inits(np.zeros((1, d)), jitter_sd=0.1)
-    eng.run(2, burnin=1, thin=1, store=False, out=False)      # warm-up: tick-engine buffers, and the first collective of the communicator
+    eng.run(4, burnin=1, thin=1, store=False, out=False)      # warm-up: tick-engine buffers, and the first collective of the communicator
     eng.diag_global(0.05, False)
     keep_in, host_in = ctx.pinned((C, d)); host_in[:] = 0.1 * np.random.default_rng(7 + ctx.rank).standard_normal((C, d))
     keep_out, host_out = ctx.pinned((C, d))

@@ -291,7 +291,8 @@ int mcu_chains_raftery(const double* value, int64_t n, int p, int64_t m, double 
  * handle reduces its own chains on the device and a packed two-round protocol carries O(p) doubles between handles
  * (mamba.jl_b200/csrc/diagproto.hpp):
  *   round 1 buffer [min p | max p | sum 9p]  — all-reduce the three parts with MIN / MAX / SUM;
- *   round 2 buffer [15p]                     — all-reduce with SUM (centred gelman sums + centred summary sums per column).
+ *   round 2 buffer [15p + p(p-1) for p <= 12] — all-reduce with SUM (centred gelman sums + centred summary sums per column, then two sums per
+ *                                              column pair for the multivariate PSRF, gelmandiag.jl:49-55).
  * ANY transport can carry the buffers (mcu_diag_round1 → reduce → mcu_diag_round2 → reduce → mcu_diag_finish: Julia worker messaging,
  * MPI, torch.distributed); the built-in transport is NCCL over NVLink: mcu_comm_unique_id on rank 0, the 128-byte id handed to the other
  * ranks by the host language, mcu_comm_init on every rank's handle, then mcu_diag_global does both rounds on the device (reductions,
@@ -303,14 +304,17 @@ int mcu_diag_sizes(int p, int* n_round1, int* n_round2);
 int mcu_monitor_links(mcu_handle h, int* monlink /* [p]: 0 identity, 1 log, -1 Logical column (data-dependent heuristic) */);
 int mcu_n_kept(mcu_handle h, int64_t* n_kept);
 int mcu_diag_round1(mcu_handle h, double* buf /* [11p] */);
-int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1 /* [11p] */, double* buf2 /* [15p] */);
-/* psrf [p × 2] (not rounded), summary [p × 5] = mean, SD, naive SE, MCSE (batch means of 100), ESS; codes [p] = link code used; each may be NULL */
+int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1 /* [11p] */, double* buf2 /* [n_round2 of mcu_diag_sizes] */);
+/* psrf [p × 2] (not rounded), summary [p × 5] = mean, SD, naive SE, MCSE (batch means of 100), ESS; codes [p] = link code used;
+ * mpsrf = the multivariate PSRF of gelmandiag(c; mpsrf = true) from the streamed within-chain covariances (NaN when p > 12, when W is not positive
+ * definite, or when a Logical column's link is resolved by the data-dependent heuristic to log / logit: those need the stored draws, mcu_chains_gelman);
+ * each output may be NULL */
 int mcu_diag_finish(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* reduced1,
-                    const double* reduced2, double* psrf, double* summary, int* codes);
+                    const double* reduced2, double* psrf, double* summary, int* codes, double* mpsrf);
 int mcu_comm_unique_id(mcu_nccl_id* id);
 int mcu_comm_init(mcu_handle h, int rank, int nranks, const mcu_nccl_id* id);
 int mcu_comm_size(mcu_handle h, int* rank, int* nranks);
-int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes);
+int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes, double* mpsrf);
 
 /* ---- RNG contract ----------------------------------------------------- */
 /* PHILOX: Philox4x32-10, key = seed, counter = (k >> 1, iteration, global chain, block | kind << 16 | stream << 24).

@@ -53,6 +53,8 @@ struct mcu_ctx {
   long long tune_size = 0;
   // chain state
   double *d_state = nullptr, *d_tune = nullptr, *d_samples = nullptr, *d_mom = nullptr, *d_momn = nullptr;
+  double* d_comom = nullptr;   // [2][P (P - 1) / 2][C] streaming within-chain co-moments (P <= 12), for the multivariate PSRF
+  unsigned long long log_mask = 0ull;
   size_t samples_cap = 0; long long samples_kept = 0;
   long long iter = 0;
   bool has_inits = false;
@@ -474,8 +476,8 @@ void free_glm_buffers(mcu_ctx* h) {
 }
 void free_chain_buffers(mcu_ctx* h) {
   free_glm_buffers(h);
-  cudaFree(h->d_state); cudaFree(h->d_tune); cudaFree(h->d_samples); cudaFree(h->d_mom); cudaFree(h->d_momn);
-  h->d_state = h->d_tune = h->d_samples = h->d_mom = h->d_momn = nullptr;
+  cudaFree(h->d_state); cudaFree(h->d_tune); cudaFree(h->d_samples); cudaFree(h->d_mom); cudaFree(h->d_momn); cudaFree(h->d_comom);
+  h->d_state = h->d_tune = h->d_samples = h->d_mom = h->d_momn = h->d_comom = nullptr;
   h->samples_cap = 0; h->samples_kept = 0;
 }
 
@@ -505,6 +507,10 @@ int ensure_chain_buffers(mcu_ctx* h) {
   CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size), h->stream));
   CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
   CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  if (diag_npair(h->P) > 0) {
+    CK(cudaMalloc(&h->d_comom, sizeof(double) * C * 2 * (size_t)diag_npair(h->P)));
+    CK(cudaMemsetAsync(h->d_comom, 0, sizeof(double) * C * 2 * (size_t)diag_npair(h->P), h->stream));
+  }
   return MCU_OK;
 }
 
@@ -771,7 +777,8 @@ struct DiagBufs { double* partial; double* r1; double* plan; double* r2; };
 int diag_bufs(mcu_ctx* h, DiagBufs* b) {
   const long long nblk = grid_for(h->C, 128);
   const size_t P = (size_t)h->P;
-  const size_t need = sizeof(double) * ((size_t)nblk * P * kDiag2 + P * (kDiag1 + 5 + kDiag2)) + 64;
+  const size_t npair = (size_t)diag_npair(h->P);
+  const size_t need = sizeof(double) * ((size_t)nblk * std::max(P * kDiag2, 2 * npair) + P * (kDiag1 + 5 + kDiag2) + 2 * npair) + 64;
   if (need > h->diag_cap) {
     if (h->d_diag) cudaFree(h->d_diag);
     h->d_diag = nullptr; h->diag_cap = 0;
@@ -779,17 +786,19 @@ int diag_bufs(mcu_ctx* h, DiagBufs* b) {
     h->diag_cap = need;
   }
   b->partial = static_cast<double*>(h->d_diag);
-  b->r1 = b->partial + (size_t)nblk * P * kDiag2;
+  b->r1 = b->partial + (size_t)nblk * std::max(P * kDiag2, 2 * npair);
   b->plan = b->r1 + P * kDiag1;
   b->r2 = b->plan + P * 5;
   return MCU_OK;
 }
 int diag_finish_host(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* r1, const double* r2,
-                     double* psrf, double* summary, int* codes_out) {
+                     double* psrf, double* summary, int* codes_out, double* mpsrf) {
+  std::vector<int> codes(p); std::vector<double> ctrs((size_t)p * 4);
   for (int j = 0; j < p; ++j) {
-    double ctr[4];
+    double* ctr = ctrs.data() + (size_t)j * 4;
     const int code = diag_plan_column(p, j, monlink[j], transform, r1, ctr);
     if (code == 2 && j >= 64) return MCU_ERR_UNSUPPORTED;   // logit moments are streamed for the first 64 columns only
+    codes[j] = code;
     if (codes_out) codes_out[j] = code;
     const double* s = r2 + (size_t)j * kDiag2;
     if (psrf) {
@@ -797,6 +806,30 @@ int diag_finish_host(int64_t n_kept, int p, double alpha, const int* monlink, in
       hostdiag::gelman_column((double)n_kept, ctr[0], ctr[1], s, alpha, psrf + j * 2);
     }
     if (summary) hostdiag::summary_column((double)n_kept, ctr[2], ctr[3], s + 7, summary + j * 5);
+  }
+  if (mpsrf) {   // gelmandiag.jl:49-55 from the streamed within-chain co-moments: W = mean_k S_k, B = n cov_k(chain means)
+    *mpsrf = NAN;
+    const int npair = diag_npair(p);
+    bool ok = npair > 0;
+    for (int j = 0; j < p && ok; ++j) ok = codes[j] == (transform && monlink[j] == kPlanLinkLog ? 1 : 0);   // co-moments exist on the raw and the node-link scale only
+    if (ok) {
+      const double m = r2[0], n = (double)n_kept;
+      std::vector<double> W((size_t)p * p), B((size_t)p * p);
+      for (int j = 0; j < p; ++j) {
+        const double* s = r2 + (size_t)j * kDiag2;
+        W[j * p + j] = ctrs[(size_t)j * 4 + 1] + s[3] / m;
+        B[j * p + j] = n * (s[2] - s[1] * s[1] / m) / (m - 1.0);
+      }
+      const double* pr = r2 + (size_t)p * kDiag2;
+      int k = 0;
+      for (int i = 0; i < p; ++i)
+        for (int j = i + 1; j < p; ++j, ++k) {
+          const double di = r2[(size_t)i * kDiag2 + 1], dj = r2[(size_t)j * kDiag2 + 1];
+          W[i * p + j] = W[j * p + i] = pr[2 * k] / m;
+          B[i * p + j] = B[j * p + i] = n * (pr[2 * k + 1] - di * dj / m) / (m - 1.0);
+        }
+      *mpsrf = hostdiag::mpsrf_from_WB(W, B, (long long)n_kept, (long long)m, p);
+    }
   }
   return MCU_OK;
 }
@@ -1014,8 +1047,8 @@ int mcu_set_scheme(mcu_handle h, int n_blocks, const mcu_block_desc* blocks) {
   CK(cudaMalloc(&h->d_ebound_state, sizeof(double) * 2 * h->D));
   CK(cudaMemcpy(h->d_ebound_state, t.ebound.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice));
   h->h_scales = h_scales; h->h_SigmaL = h_SigmaL;
-  h->h_monlink = t.monlink; h->logit_mask = 0ull;
-  for (int j = 0; j < h->P && j < 64; ++j) if (t.monlink[j] == LINK_HEUR) h->logit_mask |= 1ull << j;
+  h->h_monlink = t.monlink; h->logit_mask = 0ull; h->log_mask = 0ull;
+  for (int j = 0; j < h->P && j < 64; ++j) { if (t.monlink[j] == LINK_HEUR) h->logit_mask |= 1ull << j; if (t.monlink[j] == LINK_LOG) h->log_mask |= 1ull << j; }
   cudaFree(h->d_monlink); h->d_monlink = nullptr;
   CK(cudaMalloc(&h->d_monlink, sizeof(int) * std::max(1, h->P)));
   CK(cudaMemcpy(h->d_monlink, t.monlink.data(), sizeof(int) * h->P, cudaMemcpyHostToDevice));
@@ -1043,6 +1076,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   CK(cudaMemsetAsync(h->d_tune, 0, sizeof(double) * C * (size_t)std::max(1LL, h->tune_size), h->stream));
   CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
   CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  if (h->d_comom) CK(cudaMemsetAsync(h->d_comom, 0, sizeof(double) * C * 2 * (size_t)diag_npair(h->P), h->stream));
   if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1100,7 +1134,7 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.n_blocks = (int)h->h_blocks.size(); a.D = h->D; a.P = h->P; a.blocks = h->d_blocks;
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
-  a.logit_mask = h->logit_mask;
+  a.logit_mask = h->logit_mask; a.comom = h->d_comom; a.log_mask = h->log_mask;
   if (!h->d_work) { CK(cudaMalloc(&h->d_work, 2 * sizeof(unsigned long long))); CK(cudaMemset(h->d_work, 0, 2 * sizeof(unsigned long long))); }
   a.work = h->d_work;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
@@ -1253,6 +1287,7 @@ int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_
   // a state set from outside starts a new history: the streaming moments and the stored samples of the previous one are dropped
   CK(cudaMemsetAsync(h->d_mom, 0, sizeof(double) * C * (size_t)h->P * kMomPerCol, h->stream));
   CK(cudaMemsetAsync(h->d_momn, 0, sizeof(double) * C * 3, h->stream));
+  if (h->d_comom) CK(cudaMemsetAsync(h->d_comom, 0, sizeof(double) * C * 2 * (size_t)diag_npair(h->P), h->stream));
   if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1576,7 +1611,7 @@ int mcu_chains_summarystats(const double* value, int64_t n, int p, int64_t m, in
 int mcu_diag_sizes(int p, int* n_round1, int* n_round2) {
   if (p < 1) return MCU_ERR_ARG;
   if (n_round1) *n_round1 = p * kDiag1;
-  if (n_round2) *n_round2 = p * kDiag2;
+  if (n_round2) *n_round2 = p * kDiag2 + 2 * diag_npair(p);
   return MCU_OK;
 }
 int mcu_monitor_links(mcu_handle h, int* monlink) {
@@ -1604,15 +1639,17 @@ int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1, double*
   CK(cudaMemcpyAsync(b.r1, reduced1, sizeof(double) * h->P * kDiag1, cudaMemcpyHostToDevice, h->stream));
   launch_diag_plan(b.r1, h->d_monlink, transform, h->P, b.plan, h->stream);
   launch_diag2(h->d_mom, h->d_momn, h->C, h->P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
-  CK(cudaMemcpyAsync(buf2, b.r2, sizeof(double) * h->P * kDiag2, cudaMemcpyDeviceToHost, h->stream));
+  const int npair = h->d_comom ? diag_npair(h->P) : 0;
+  if (npair > 0) { launch_diag_pairs(h->d_mom, h->d_momn, h->d_comom, h->C, h->P, b.plan, transform ? 1 : 0, b.partial, b.r2 + (size_t)h->P * kDiag2, h->stream); h->launches += 2; }
+  CK(cudaMemcpyAsync(buf2, b.r2, sizeof(double) * ((size_t)h->P * kDiag2 + 2 * (size_t)npair), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   return MCU_OK;
 }
 int mcu_diag_finish(int64_t n_kept, int p, double alpha, const int* monlink, int transform, const double* reduced1, const double* reduced2,
-                    double* psrf, double* summary, int* codes) {
+                    double* psrf, double* summary, int* codes, double* mpsrf) {
   if (p < 1 || !monlink || !reduced1 || !reduced2) return MCU_ERR_ARG;
-  return diag_finish_host(n_kept, p, alpha, monlink, transform, reduced1, reduced2, psrf, summary, codes);
+  return diag_finish_host(n_kept, p, alpha, monlink, transform, reduced1, reduced2, psrf, summary, codes, mpsrf);
 }
 int mcu_n_kept(mcu_handle h, int64_t* n_kept) {
   if (!h || !n_kept) return MCU_ERR_ARG;
@@ -1649,8 +1686,8 @@ int mcu_comm_size(mcu_handle h, int* rank, int* nranks) {
 // gelmandiag + summarystats over the chains of EVERY rank of the communicator (of this handle alone without one): both protocol rounds
 // stay on the device — reductions, NCCL all-reduces (round 1: MIN / MAX / SUM in one group; round 2: SUM) and the plan kernel are queued
 // on the handle's stream back to back; one synchronisation, then O(p) host arithmetic (F quantile etc., hostdiag.hpp).
-int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes) {
-  if (!h || (!psrf && !summary && !codes)) return MCU_ERR_ARG;
+int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, double* summary, int* codes, double* mpsrf) {
+  if (!h || (!psrf && !summary && !codes && !mpsrf)) return MCU_ERR_ARG;
   if (!h->has_inits) return fail(h, MCU_ERR_STATE, "no samples yet");
   CK(cudaSetDevice(h->device));
   const int P = h->P;
@@ -1666,16 +1703,20 @@ int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, dou
   }
   launch_diag_plan(b.r1, h->d_monlink, transform, P, b.plan, h->stream);
   launch_diag2(h->d_mom, h->d_momn, h->C, P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
-  if (n) NK(n->AllReduce(b.r2, b.r2, (size_t)P * kDiag2, kNcclFloat64, kNcclSum, h->comm, h->stream));
-  std::vector<double> host((size_t)P * (kDiag1 + kDiag2) + 1);
+  const int npair = h->d_comom ? diag_npair(P) : 0;
+  if (npair > 0) { launch_diag_pairs(h->d_mom, h->d_momn, h->d_comom, h->C, P, b.plan, transform ? 1 : 0, b.partial, b.r2 + (size_t)P * kDiag2, h->stream); h->launches += 2; }
+  const size_t n2 = (size_t)P * kDiag2 + 2 * (size_t)npair;
+  if (n) NK(n->AllReduce(b.r2, b.r2, n2, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  std::vector<double> host((size_t)P * kDiag1 + n2 + 1);
   CK(cudaMemcpyAsync(host.data(), b.r1, sizeof(double) * P * kDiag1, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(host.data() + (size_t)P * kDiag1, b.r2, sizeof(double) * P * kDiag2, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(host.data() + (size_t)P * (kDiag1 + kDiag2), h->d_momn, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(host.data() + (size_t)P * kDiag1, b.r2, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(host.data() + (size_t)P * kDiag1 + n2, h->d_momn, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  const int64_t n_kept = (int64_t)host[(size_t)P * (kDiag1 + kDiag2)];
+  const int64_t n_kept = (int64_t)host[(size_t)P * kDiag1 + n2];
   if (psrf && n_kept < 2) return fail(h, MCU_ERR_STATE, "fewer than 2 kept samples per chain");
-  rc = diag_finish_host(n_kept, P, alpha, h->h_monlink.data(), transform, host.data(), host.data() + (size_t)P * kDiag1, psrf, summary, codes);
+  rc = diag_finish_host(n_kept, P, alpha, h->h_monlink.data(), transform, host.data(), host.data() + (size_t)P * kDiag1, psrf, summary, codes, npair > 0 ? mpsrf : nullptr);
+  if (mpsrf && npair == 0) *mpsrf = NAN;
   if (rc == MCU_ERR_UNSUPPORTED) return fail(h, rc, "logit link beyond monitored column 64 needs stored samples");
   if (rc == MCU_ERR_ARG) return fail(h, rc, "less than 2 chains supplied to gelman diagnostic");
   return rc;

@@ -12,6 +12,11 @@
 //   round 2  sum2 (15 p), all-reduced with SUM.  Per column j:
 //            { m, Σd, Σd², Σe, Σe², Σed, Σed² }  with d = ψ̄ - c1, e = s² - c2 on the planned scale   (gelmandiag.jl:12-29)
 //            { C, Σ mean, Σ M2, Σ (mean - k1)², Σ nb, Σ nb·bmean, Σ bM2, Σ nb (bmean - k2)² }          (stats.jl:85-94, mcse.jl:10-19)
+//            followed, when p <= 12, by two sums per column pair i < j (p (p - 1) / 2 pairs, in the order (0,1), (0,2), ..., (1,2), ...):
+//            { Σ cov_k(i, j), Σ d_i d_j }  — the off-diagonals of W = mean of the within-chain covariances and of B / n = cov of the chain
+//            means, for the multivariate PSRF (gelmandiag.jl:49-55) without the draws.  The within-chain co-moments are streamed on the raw
+//            scale and on the nodes' own link scale; a column whose link(c) is resolved by the data-dependent heuristic to log / logit has
+//            no streamed co-moments on that scale, and the MPSRF is then reported as NaN (it needs the stored draws).
 //   The centring keeps the variances free of cancellation; any transport may carry the buffers (NCCL inside libmambacuda,
 //   torch.distributed / gloo in the CPU tests, Julia's own worker messaging).
 #pragma once
@@ -27,6 +32,8 @@ namespace mcu {
 constexpr int kDiag1 = 11;       // values per column produced by a handle in round 1: min, max, 9 sums
 constexpr int kDiagSum1 = 9;
 constexpr int kDiag2 = 15;       // values per column in round 2
+constexpr int kDiagCoMaxP = 12;  // == kCoMaxP of engine.cuh
+MCU_PROTO_HD int diag_npair(int p) { return (p > 1 && p <= kDiagCoMaxP) ? p * (p - 1) / 2 : 0; }
 constexpr int kPlanLinkLog = 1, kPlanLinkHeur = -1;   // == LINK_LOG / LINK_HEUR of models.cuh
 
 // link code (0 identity, 1 log, 2 logit) and round-2 centres { c1, c2, k1, k2 } of column j from the all-reduced round-1 buffer

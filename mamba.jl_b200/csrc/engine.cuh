@@ -16,6 +16,7 @@ namespace mcu {
 
 constexpr int kMomPerCol = 11;  // mean, M2, lmean, lM2, min, max, bsum, bmean, bM2, logit mean, logit M2 (Logical columns only)
 constexpr int kBatch = 100;     // mcse_bm default batch size (src/output/mcse.jl:10)
+constexpr int kCoMaxP = 12;     // streaming within-chain covariances (for the multivariate PSRF, gelmandiag.jl:49-55) are kept for up to 12 monitored columns
 
 // logpdf!(block, x) / logpdfgrad!(block, x) for one chain: relist x into the state record
 // (invlink when the block samples on the transformed scale), then sum the block's own prior
@@ -145,26 +146,33 @@ struct RunArgs {
   double* state; double* tune; double* samples; double* mom; double* momn;
   const double* ext_u; unsigned long long ext_n; unsigned long long* ext_pos;
   unsigned long long* work;               // device counter of gradient evaluations (leapfrogs) the kernels add to, or nullptr
+  double* comom;                          // [2][P (P - 1) / 2][C] streaming within-chain co-moments (raw scale | node-link scale), or nullptr
+  unsigned long long log_mask;            // monitored columns (bit j) whose node link is the log (co-moment set 1 uses log x for them)
   unsigned long long logit_mask;          // monitored columns (bit j) whose link(c) may be the logit: Logical nodes in (0, 1), chains.jl:237-246
 };
 
-static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon, unsigned long long logit_mask = 0ull) {
+static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon, unsigned long long logit_mask = 0ull,
+                                     double* comom = nullptr, unsigned long long log_mask = 0ull) {
   const double n = momn[0 * C + c] + 1.0; momn[0 * C + c] = n;
   double bc = momn[1 * C + c] + 1.0;
   const bool bdone = bc >= (double)kBatch;
   double nb = momn[2 * C + c];
   if (bdone) { bc = 0.0; nb += 1.0; momn[2 * C + c] = nb; }
   momn[1 * C + c] = bc;
+  const bool co = comom != nullptr && P <= kCoMaxP && P > 1;
+  double d_old[kCoMaxP], r_new[kCoMaxP], dl_old[kCoMaxP], rl_new[kCoMaxP];   // Welford co-moments: C_ij += (x_i - mean_i^old)(x_j - mean_j^new)
   for (int j = 0; j < P; ++j) {
     double* q = mom + (size_t)j * kMomPerCol * C + c;
     const double x = mon[j];
     double mean = q[0 * C], M2 = q[1 * C];
     double dl = x - mean; mean += dl / n; M2 += dl * (x - mean);
     q[0 * C] = mean; q[1 * C] = M2;
+    if (co) { d_old[j] = dl; r_new[j] = x - mean; }
     const double lx = log(x);
     double lmean = q[2 * C], lM2 = q[3 * C];
     dl = lx - lmean; lmean += dl / n; lM2 += dl * (lx - lmean);
     q[2 * C] = lmean; q[3 * C] = lM2;
+    if (co) { const bool lg = (log_mask >> j) & 1ull; dl_old[j] = lg ? dl : d_old[j]; rl_new[j] = lg ? lx - lmean : r_new[j]; }
     q[4 * C] = n == 1.0 ? x : fmin(q[4 * C], x);
     q[5 * C] = n == 1.0 ? x : fmax(q[5 * C], x);
     if (j < 64 && ((logit_mask >> j) & 1ull)) {
@@ -181,6 +189,15 @@ static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t
       q[7 * C] = bmean; q[8 * C] = bM2;
     }
     q[6 * C] = bsum;
+  }
+  if (co) {
+    const size_t npair = (size_t)P * (P - 1) / 2;
+    size_t k = 0;
+    for (int i = 0; i < P; ++i)
+      for (int j = i + 1; j < P; ++j, ++k) {
+        comom[k * C + c] += d_old[i] * r_new[j];
+        comom[(npair + k) * C + c] += dl_old[i] * rl_new[j];
+      }
   }
 }
 
@@ -228,7 +245,7 @@ __device__ __forceinline__ void generic_kernel_body(const typename M::Data& data
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;   // iters2inds: src/output/chains.jl:66-87
         for (int j = 0; j < a.P; ++j) a.samples[((size_t)row * a.P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon, a.logit_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon, a.logit_mask, a.comom, a.log_mask);
     }
   }
   for (int e = 0; e < a.D; ++e) a.state[(size_t)e * C + c] = s[e];

@@ -430,6 +430,22 @@ inline double sym_eigmax(std::vector<double> A, int p) {
   double mx = A[0]; for (int a = 1; a < p; ++a) mx = std::fmax(mx, A[a * p + a]);
   return mx;
 }
+// multivariate PSRF (gelmandiag.jl:49-55): isposdef(W) ? R_fixed + R_random_scale * eigmax(inv(cholfact(W)) * B) : NaN, with
+// W = mean within-chain covariance, B = n cov(chain means) (p x p, row-major) — W^-1 B is similar to L^-1 B L^-T (W = L L')
+inline double mpsrf_from_WB(const std::vector<double>& W, const std::vector<double>& B, long long n, long long m, int p) {
+  std::vector<double> L((size_t)p * p, 0.0); bool pd = true;
+  for (int a = 0; a < p && pd; ++a)
+    for (int b = 0; b <= a; ++b) {
+      double s = W[a * p + b]; for (int k = 0; k < b; ++k) s -= L[a * p + k] * L[b * p + k];
+      if (a == b) { if (!(s > 0)) { pd = false; break; } L[a * p + a] = std::sqrt(s); } else L[a * p + b] = s / L[b * p + b];
+    }
+  if (!pd) return NAN;
+  std::vector<double> Y((size_t)p * p), S((size_t)p * p);
+  for (int c = 0; c < p; ++c) for (int a = 0; a < p; ++a) { double s = B[a * p + c]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * Y[k * p + c]; Y[a * p + c] = s / L[a * p + a]; }   // Y = L^-1 B
+  for (int r = 0; r < p; ++r) for (int a = 0; a < p; ++a) { double s = Y[r * p + a]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * S[r * p + k]; S[r * p + a] = s / L[a * p + a]; }   // S = Y L^-T
+  for (int a = 0; a < p; ++a) for (int b = a + 1; b < p; ++b) { const double t = 0.5 * (S[a * p + b] + S[b * p + a]); S[a * p + b] = S[b * p + a] = t; }
+  return (double)(n - 1) / (double)n + (double)(m + 1) / ((double)m * (double)n) * sym_eigmax(S, p);
+}
 // gelmandiag(c; alpha, mpsrf, transform) on a materialised array: gelmandiag.jl:3-60.  codes[j] = 1: log scale, 2: logit scale (link(c)).
 // out [(p + mpsrf) x 2] row-major, NOT rounded; the multivariate row is (R_fixed + R_random_scale eigmax(W^-1 B), NaN), NaN when W is
 // not positive definite.  Returns 1 for fewer than 2 chains.
@@ -460,21 +476,7 @@ inline int chains_gelman(const double* v, long long n, int p, long long m, doubl
     gelman_column((double)n, gm[j], c2, s, alpha, out + 2 * j);
   }
   if (mpsrf) {
-    // isposdef(W) ? R_fixed + R_random_scale * eigmax(inv(cholfact(W)) * B) : NaN — W^-1 B is similar to L^-1 B L^-T (W = L L')
-    std::vector<double> L((size_t)p * p, 0.0); bool pd = true;
-    for (int a = 0; a < p && pd; ++a)
-      for (int b = 0; b <= a; ++b) {
-        double s = W[a * p + b]; for (int k = 0; k < b; ++k) s -= L[a * p + k] * L[b * p + k];
-        if (a == b) { if (!(s > 0)) { pd = false; break; } L[a * p + a] = std::sqrt(s); } else L[a * p + b] = s / L[b * p + b];
-      }
-    double x = NAN;
-    if (pd) {
-      std::vector<double> Y((size_t)p * p), S((size_t)p * p);
-      for (int c = 0; c < p; ++c) for (int a = 0; a < p; ++a) { double s = B[a * p + c]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * Y[k * p + c]; Y[a * p + c] = s / L[a * p + a]; }   // Y = L^-1 B
-      for (int r = 0; r < p; ++r) for (int a = 0; a < p; ++a) { double s = Y[r * p + a]; for (int k = 0; k < a; ++k) s -= L[a * p + k] * S[r * p + k]; S[r * p + a] = s / L[a * p + a]; }   // S = Y L^-T
-      for (int a = 0; a < p; ++a) for (int b = a + 1; b < p; ++b) { const double t = 0.5 * (S[a * p + b] + S[b * p + a]); S[a * p + b] = S[b * p + a] = t; }
-      x = (double)(n - 1) / (double)n + (double)(m + 1) / ((double)m * (double)n) * sym_eigmax(S, p);
-    }
+    const double x = mpsrf_from_WB(W, B, n, m, p);
     out[2 * p] = x; out[2 * p + 1] = NAN;
   }
   return 0;

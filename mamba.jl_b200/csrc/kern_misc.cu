@@ -212,6 +212,35 @@ __global__ void diag2_partial_kernel(const double* mom, const double* momn, long
     }
   }
 }
+// round 2, pair part: partial[grid][npair][2] = { Σ cov_k(i, j), Σ d_i d_j } over the block's chains (co-moment set `set`: 0 raw, 1 node-link scale)
+__global__ void diag_pairs_partial_kernel(const double* mom, const double* momn, const double* comom, long long C, int P, const double* plan, int set,
+                                          double* partial) {
+  __shared__ double sh[128];
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = c < C;
+  const double n = on ? momn[c] : 2.0;
+  const int npair = P * (P - 1) / 2;
+  double d[kCoMaxP];
+  for (int j = 0; j < P; ++j) {
+    const double* q = mom + (size_t)j * kMomPerCol * C + c;
+    const int code = (int)plan[j * 5];
+    d[j] = on ? (code == 2 ? q[9 * C] : code == 1 ? q[2 * C] : q[0 * C]) - plan[j * 5 + 1] : 0.0;
+  }
+  int k = 0;
+  for (int i = 0; i < P; ++i)
+    for (int j = i + 1; j < P; ++j, ++k) {
+      const double cov = on ? comom[((size_t)set * npair + k) * C + c] / (n - 1.0) : 0.0;
+      const double r0 = block_reduce128(cov, 0, sh), r1 = block_reduce128(on ? d[i] * d[j] : 0.0, 0, sh);
+      if (threadIdx.x == 0) { partial[((size_t)blockIdx.x * npair + k) * 2] = r0; partial[((size_t)blockIdx.x * npair + k) * 2 + 1] = r1; }
+    }
+}
+void launch_diag_pairs(const double* mom, const double* momn, const double* comom, long long C, int P, const double* plan, int set, double* partial, double* out,
+                       cudaStream_t st) {
+  const long long nblk = (C + 127) / 128;
+  const int npair = P * (P - 1) / 2;
+  diag_pairs_partial_kernel<<<(unsigned)nblk, 128, 0, st>>>(mom, momn, comom, C, P, plan, set, partial);
+  fold_kernel<<<(unsigned)((npair * 2 + 127) / 128), 128, 0, st>>>(partial, nblk, npair * 2, out);
+}
 void launch_diag1(const double* mom, const double* momn, long long C, int P, unsigned long long logit_mask, double* partial, double* out, cudaStream_t st) {
   const long long nblk = (C + 127) / 128;
   diag1_partial_kernel<<<(unsigned)nblk, 128, 0, st>>>(mom, momn, C, P, logit_mask, partial);

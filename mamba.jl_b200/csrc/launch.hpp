@@ -76,6 +76,8 @@ void launch_summary_partial(const double* mom, const double* momn, long long C, 
 void launch_diag1(const double* mom, const double* momn, long long C, int P, unsigned long long logit_mask, double* partial, double* out, cudaStream_t st);
 void launch_diag_plan(const double* r1, const int* monlink, int transform, int P, double* plan, cudaStream_t st);
 void launch_diag2(const double* mom, const double* momn, long long C, int P, const double* plan, double* partial, double* out, cudaStream_t st);
+void launch_diag_pairs(const double* mom, const double* momn, const double* comom, long long C, int P, const double* plan, int set, double* partial, double* out,
+                       cudaStream_t st);
 
 double measure_fp64_peak_tflops(cudaStream_t st);
 

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSF_MINB) pumps_fast_kernel(const _
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon, 0ull, a.comom, a.log_mask);
     }
   }
   a.state[0 * C + c] = al; a.state[1 * C + c] = be;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon, 0ull, a.comom, a.log_mask);
     }
   }
   a.state[0 * C + c] = al; a.state[1 * C + c] = be;

@@ -117,11 +117,11 @@ def lib():
     L.mcu_n_kept.argtypes = [vp, C.POINTER(i64)]
     L.mcu_diag_round1.argtypes = [vp, dp]
     L.mcu_diag_round2.argtypes = [vp, C.c_int, dp, dp]
-    L.mcu_diag_finish.argtypes = [i64, C.c_int, C.c_double, ip, C.c_int, dp, dp, dp, dp, ip]
+    L.mcu_diag_finish.argtypes = [i64, C.c_int, C.c_double, ip, C.c_int, dp, dp, dp, dp, ip, C.POINTER(C.c_double)]
     L.mcu_comm_unique_id.argtypes = [C.c_char_p]
     L.mcu_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.mcu_comm_size.argtypes = [vp, ip, ip]
-    L.mcu_diag_global.argtypes = [vp, C.c_double, C.c_int, dp, dp, ip]
+    L.mcu_diag_global.argtypes = [vp, C.c_double, C.c_int, dp, dp, ip, C.POINTER(C.c_double)]
     L.mcu_wait.argtypes = [vp]
     L.mcu_work_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mcu_get_samples.argtypes = [vp, dp]

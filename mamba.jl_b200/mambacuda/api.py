@@ -656,7 +656,11 @@ def gelmandiag(c, alpha=0.05, mpsrf=False, transform=False):
     if len(c.chains) < 2:
         raise ArgumentError("less than 2 chains supplied to gelman diagnostic")   # gelmandiag.jl:6-7
     eng = getattr(c, "engine", None) if getattr(c, "_streaming", False) else None
-    if mpsrf or eng is None:   # MPSRF needs the p x p within / between covariances; subsets / files have no device moments:
+    if mpsrf and eng is not None:   # the within-chain covariances are streamed on the device for up to 12 monitored columns (mcu_diag_global)
+        psrf, _, _, mv = eng.diag_global(alpha, transform, mpsrf=True)
+        if not np.isnan(mv):
+            return np.round(np.vstack([psrf, [mv, np.nan]]), 3), c.names + ["Multivariate"], ["PSRF", f"{100 * (1 - alpha / 2)}%"]
+    if mpsrf or eng is None:   # subsets / files have no device moments, and a heuristic log / logit link has no streamed co-moments:
         codes = None           # both are computed on the materialised array (mcu_chains_gelman)
         if transform:
             codes = eng.link_codes(True) if eng is not None else c.link_codes()

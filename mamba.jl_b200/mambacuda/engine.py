@@ -314,12 +314,14 @@ class Engine:
 
     def diag_round2(self, transform, reduced1):
         p = self.dims()[1]
-        r1 = _f64(reduced1); buf = np.empty(15 * p)
+        n1, n2 = C.c_int(), C.c_int()
+        self.L.mcu_diag_sizes(p, C.byref(n1), C.byref(n2))
+        r1 = _f64(reduced1); buf = np.empty(n2.value)
         self._chk(self.L.mcu_diag_round2(self.h, int(bool(transform)), _dp(r1), _dp(buf)))
         return buf
 
-    def diag_finish(self, alpha, transform, reduced1, reduced2):
-        return diag_finish(self.n_kept(), self.monitor_links(), alpha, transform, reduced1, reduced2)
+    def diag_finish(self, alpha, transform, reduced1, reduced2, mpsrf=False):
+        return diag_finish(self.n_kept(), self.monitor_links(), alpha, transform, reduced1, reduced2, mpsrf=mpsrf)
 
     def comm_init(self, rank, nranks, unique_id):
         """Join the NCCL communicator of `unique_id` (bytes from comm_unique_id() on rank 0) as `rank` of `nranks`."""
@@ -330,13 +332,15 @@ class Engine:
         self._chk(self.L.mcu_comm_size(self.h, C.byref(r), C.byref(n)))
         return r.value, n.value
 
-    def diag_global(self, alpha=0.05, transform=False):
+    def diag_global(self, alpha=0.05, transform=False, mpsrf=False):
         """gelmandiag + streaming summarystats over every rank of the handle's communicator (this handle alone without one):
-        (psrf [p x 2], summary [p x 5], link codes [p]); device-resident, NCCL all-reduces, one synchronisation."""
+        (psrf [p x 2], summary [p x 5], link codes [p]) and, with mpsrf=True, the multivariate PSRF from the streamed within-chain
+        covariances as a fourth element; device-resident, NCCL all-reduces, one synchronisation."""
         p = self.dims()[1]
-        psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)()
-        self._chk(self.L.mcu_diag_global(self.h, float(alpha), int(bool(transform)), _dp(psrf), _dp(summ), codes))
-        return psrf, summ, np.array(list(codes), dtype=np.int32)
+        psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)(); mv = C.c_double(float("nan"))
+        self._chk(self.L.mcu_diag_global(self.h, float(alpha), int(bool(transform)), _dp(psrf), _dp(summ), codes, C.byref(mv) if mpsrf else None))
+        out = (psrf, summ, np.array(list(codes), dtype=np.int32))
+        return out + (mv.value,) if mpsrf else out
 
     def fp64_peak_tflops(self):
         return self.L.mcu_fp64_peak_tflops(self.h)
@@ -366,16 +370,17 @@ def comm_unique_id():
     return buf.raw
 
 
-def diag_finish(n_kept, monlink, alpha, transform, reduced1, reduced2):
-    """Host arithmetic of the two-round protocol (no device): (psrf, summary, codes) from the all-reduced buffers."""
+def diag_finish(n_kept, monlink, alpha, transform, reduced1, reduced2, mpsrf=False):
+    """Host arithmetic of the two-round protocol (no device): (psrf, summary, codes[, mpsrf]) from the all-reduced buffers."""
     L = _lib.lib()
     p = len(monlink)
     ml = (C.c_int * p)(*[int(v) for v in monlink])
     r1 = _f64(reduced1); r2 = _f64(reduced2)
-    psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)()
-    rc = L.mcu_diag_finish(int(n_kept), p, float(alpha), ml, int(bool(transform)), _dp(r1), _dp(r2), _dp(psrf), _dp(summ), codes)
+    psrf = np.empty((p, 2)); summ = np.empty((p, 5)); codes = (C.c_int * p)(); mv = C.c_double(float("nan"))
+    rc = L.mcu_diag_finish(int(n_kept), p, float(alpha), ml, int(bool(transform)), _dp(r1), _dp(r2), _dp(psrf), _dp(summ), codes, C.byref(mv) if mpsrf else None)
     if rc == _lib.ERR_ARG:
         raise ValueError("less than 2 chains supplied to gelman diagnostic")
     if rc != 0:
         raise MambaCudaError(rc, "mcu_diag_finish failed")
-    return psrf, summ, np.array(list(codes), dtype=np.int32)
+    out = (psrf, summ, np.array(list(codes), dtype=np.int32))
+    return out + (mv.value,) if mpsrf else out

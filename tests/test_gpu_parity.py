@@ -985,3 +985,34 @@ def test_external_stream_nuts_steps_and_exhaustion(oracle):
     eng.set_external_stream(short); eng.set_inits(inits)
     with pytest.raises(MambaCudaError, match="external uniform stream exhausted"):
         eng.run(6, burnin=4, thin=1)
+
+
+def test_streaming_mpsrf_equals_gelmandiag_on_the_stored_draws(oracle):
+    # gelmandiag(c; mpsrf = true) (gelmandiag.jl:49-55) without the draws: within-chain covariances are streamed as Welford co-moments (raw scale
+    # and the nodes' own link scale), reduced over chains with the packed protocol; compared with the host-array entry point on the stored draws
+    from mambacuda import api
+    from mambacuda.engine import Engine, diag_finish
+    for name, transform in (("seeds_amwg", False), ("seeds_amwg", True), ("pumps_slice", True), ("rats_slice_amwg", False)):
+        tpl, blocks, inits = helpers.scheme(name)
+        eng = Engine(tpl, 48, seed=6); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+        out = eng.run(900, burnin=300, thin=2, force_generic=(name == "pumps_slice"))
+        psrf, summ, codes, mv = eng.diag_global(0.05, transform, mpsrf=True)
+        want = api._chains_gelman(out, 0.05, codes if transform else None, True)
+        np.testing.assert_allclose(psrf, want[:-1], rtol=1e-7)
+        np.testing.assert_allclose(mv, want[-1, 0], rtol=1e-7)
+        # the same through two handles and the host-carried protocol
+        parts = []
+        for off, n in ((0, 20), (20, 28)):
+            e = Engine(tpl, n, seed=6, chain_offset=off); e.set_scheme(blocks); e.set_inits(inits, jitter_sd=0.05)
+            e.run(900, burnin=300, thin=2, store=False, out=False, force_generic=(name == "pumps_slice"))
+            parts.append(e)
+        p = eng.dims()[1]
+        r1 = _combine_round1([e.diag_round1() for e in parts], p)
+        r2 = np.sum([e.diag_round2(transform, r1) for e in parts], axis=0)
+        _, _, _, mv2 = diag_finish(parts[0].n_kept(), parts[0].monitor_links(), 0.05, transform, r1, r2, mpsrf=True)
+        np.testing.assert_allclose(mv2, mv, rtol=1e-9)
+    # rats with transform: alpha0 is a Logical column whose link is resolved by the heuristic to log — no streamed co-moments on that scale
+    tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
+    eng = Engine(tpl, 16, seed=6); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
+    eng.run(400, burnin=100, thin=2, store=False, out=False)
+    assert np.isnan(eng.diag_global(0.05, True, mpsrf=True)[3])

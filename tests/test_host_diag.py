@@ -106,11 +106,28 @@ class NumpyLocal:
             bmean = bm.mean(axis=0); bM2 = ((bm - bmean) ** 2).sum(axis=0)
             out[j] = [m, d.sum(), (d * d).sum(), e.sum(), (e * e).sum(), (e * d).sum(), (e * d * d).sum(),
                       m, mean.sum(), M2.sum(), ((mean - k1) ** 2).sum(), nb * m, (nb * bmean).sum(), bM2.sum(), (nb * (bmean - k2) ** 2).sum()]
-        return out.ravel()
+        # pair sums for the multivariate PSRF: { Σ cov_k(i, j), Σ d_i d_j } on the raw scale (transform = false) or the nodes' own link scale
+        pairs = []
+        ys = [np.log(self.c[:, j, :]) if (transform and self.monlink[j] == 1) else self.c[:, j, :] for j in range(p)]
+        for i in range(p):
+            for j in range(i + 1, p):
+                ci = ys[i] - ys[i].mean(axis=0); cj = ys[j] - ys[j].mean(axis=0)
+                cov = (ci * cj).sum(axis=0) / (n - 1)
+                pairs += [cov.sum(), (self._d(i, transform, r1) * self._d(j, transform, r1)).sum()]
+        return np.concatenate([out.ravel(), np.array(pairs)])
 
-    def diag_finish(self, alpha, transform, r1, r2):
+    def _d(self, j, transform, r1):
+        p = self.c.shape[1]
+        s1 = r1[2 * p:].reshape(p, 9)
+        ml = self.monlink[j]
+        code = 0
+        if transform:
+            code = 1 if ml == 1 else ((2 if r1[p + j] < 1 else 1) if (ml == -1 and r1[j] > 0) else 0)
+        return self._scales(j)[code].mean(axis=0) - s1[j, 1 + 2 * code] / s1[j, 0]
+
+    def diag_finish(self, alpha, transform, r1, r2, mpsrf=False):
         from mambacuda.engine import diag_finish
-        return diag_finish(self.c.shape[0], self.monlink, alpha, transform, r1, r2)
+        return diag_finish(self.c.shape[0], self.monlink, alpha, transform, r1, r2, mpsrf=mpsrf)
 
     def summary_from_sums(self, n_kept, center, sums):
         C = self.C
@@ -165,6 +182,18 @@ def test_packed_protocol_equals_reference_diagnostics(oracle, mcu_built):
         assert list(codes) == ([0, 1, 1, 2] if transform else [0, 0, 0, 0])
     with pytest.raises(ValueError, match="less than 2 chains"):
         mdist.global_diagnostics(NumpyLocal(c[:, :, :1], monlink), 0.05, False)
+    # multivariate PSRF from the pair sums of round 2 (gelmandiag.jl:49-55) against the host-array entry point on the draws themselves
+    from mambacuda import api
+    local = NumpyLocal(c[:, :3, :], [0, 1, 0])
+    for transform, codes in ((False, None), (True, [0, 1, 0])):
+        b1 = local.diag_round1(); r2 = local.diag_round2(transform, b1)
+        psrf, summ, cd, mv = local.diag_finish(0.05, transform, b1, r2, mpsrf=True)
+        want = api._chains_gelman(c[:, :3, :], 0.05, codes, True)
+        np.testing.assert_allclose(psrf, want[:-1], rtol=1e-9)
+        np.testing.assert_allclose(mv, want[-1, 0], rtol=1e-9)
+    # a Logical column resolved to log / logit by the heuristic has no streamed co-moments: NaN, not a wrong number
+    b1 = NumpyLocal(c, monlink).diag_round1(); r2 = NumpyLocal(c, monlink).diag_round2(True, b1)
+    assert np.isnan(NumpyLocal(c, monlink).diag_finish(0.05, True, b1, r2, mpsrf=True)[3])
 
 
 def test_f_quantile_of_the_product_against_scipy(mcu_built):
