@@ -105,6 +105,11 @@ enum { MCU_ETYPE_BM = 0, MCU_ETYPE_IMSE = 1, MCU_ETYPE_IPSE = 2 };              
                                     then drive a handle per GPU concurrently, as pmap2 drives a worker per chain (src/model/mcmc.jl:48-52, src/utils.jl:91-98).
                                     (The GLM / NUTS tick engine is host-driven and returns only when done.) */
 
+#define MCU_RUN_MPSRF 32u        /* also stream the within-chain covariances of the monitored columns (Welford co-moments, p <= 12), so that the multivariate
+                                    PSRF of gelmandiag(c; mpsrf = true) (src/output/gelmandiag.jl:49-55) is available without the draws (mcu_diag_global /
+                                    mcu_diag_finish: mpsrf).  Off by default: p (p - 1) extra doubles are read and written per chain and kept draw.
+                                    The MPSRF is NaN unless EVERY run since mcu_set_inits / mcu_set_state carried the flag. */
+
 #define MCU_MAX_BLOCK_NODES 8
 
 /*

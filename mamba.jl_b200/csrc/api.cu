@@ -55,6 +55,7 @@ struct mcu_ctx {
   double *d_state = nullptr, *d_tune = nullptr, *d_samples = nullptr, *d_mom = nullptr, *d_momn = nullptr;
   double* d_comom = nullptr;   // [2][P (P - 1) / 2][C] streaming within-chain co-moments (P <= 12), for the multivariate PSRF
   unsigned long long log_mask = 0ull;
+  bool comom_ok = false;       // every kept draw since the last inits / state went into the co-moments (MCU_RUN_MPSRF on every run)
   size_t samples_cap = 0; long long samples_kept = 0;
   long long iter = 0;
   bool has_inits = false;
@@ -1080,7 +1081,7 @@ int mcu_set_inits(mcu_handle h, const double* x, int64_t n_inits, double jitter_
   if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  h->iter = 0; h->has_inits = true; h->samples_kept = 0;
+  h->iter = 0; h->has_inits = true; h->samples_kept = 0; h->comom_ok = h->d_comom != nullptr;
   h->g_reset = true;   // the tick engine's chain records start over (buffers are kept: no cudaMalloc / cudaFree per mcmc() call)
   return MCU_OK;
 }
@@ -1134,7 +1135,9 @@ int mcu_run(mcu_handle h, int64_t iters, int64_t burnin, int64_t thin, double* o
   a.n_blocks = (int)h->h_blocks.size(); a.D = h->D; a.P = h->P; a.blocks = h->d_blocks;
   a.state = h->d_state; a.tune = h->d_tune; a.samples = (store && kept > 0) ? h->d_samples : nullptr;
   a.mom = h->d_mom; a.momn = h->d_momn;
-  a.logit_mask = h->logit_mask; a.comom = h->d_comom; a.log_mask = h->log_mask;
+  a.logit_mask = h->logit_mask; a.log_mask = h->log_mask;
+  a.comom = (flags & MCU_RUN_MPSRF) ? h->d_comom : nullptr;
+  if (kept > 0 && !a.comom) h->comom_ok = false;
   if (!h->d_work) { CK(cudaMalloc(&h->d_work, 2 * sizeof(unsigned long long))); CK(cudaMemset(h->d_work, 0, 2 * sizeof(unsigned long long))); }
   a.work = h->d_work;
   a.ext_u = h->rng_mode == MCU_RNG_EXTERNAL ? h->d_ext : nullptr; a.ext_n = h->ext_n; a.ext_pos = h->d_ext_pos;
@@ -1291,7 +1294,7 @@ int mcu_set_state(mcu_handle h, const double* values, const double* tune, int64_
   if (h->d_ext_pos) CK(cudaMemsetAsync(h->d_ext_pos, 0, sizeof(unsigned long long) * C, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  h->iter = iter; h->has_inits = true; h->samples_kept = 0;
+  h->iter = iter; h->has_inits = true; h->samples_kept = 0; h->comom_ok = h->d_comom != nullptr;
   h->g_reset = true;
   return MCU_OK;
 }
@@ -1639,8 +1642,9 @@ int mcu_diag_round2(mcu_handle h, int transform, const double* reduced1, double*
   CK(cudaMemcpyAsync(b.r1, reduced1, sizeof(double) * h->P * kDiag1, cudaMemcpyHostToDevice, h->stream));
   launch_diag_plan(b.r1, h->d_monlink, transform, h->P, b.plan, h->stream);
   launch_diag2(h->d_mom, h->d_momn, h->C, h->P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
-  const int npair = h->d_comom ? diag_npair(h->P) : 0;
-  if (npair > 0) { launch_diag_pairs(h->d_mom, h->d_momn, h->d_comom, h->C, h->P, b.plan, transform ? 1 : 0, b.partial, b.r2 + (size_t)h->P * kDiag2, h->stream); h->launches += 2; }
+  const int npair = diag_npair(h->P);   // the protocol buffer always carries the pair slots (p <= 12); NaN when the co-moments were not streamed
+  if (npair > 0 && h->d_comom && h->comom_ok) { launch_diag_pairs(h->d_mom, h->d_momn, h->d_comom, h->C, h->P, b.plan, transform ? 1 : 0, b.partial, b.r2 + (size_t)h->P * kDiag2, h->stream); h->launches += 2; }
+  else if (npair > 0) { std::vector<double> nanv(2 * (size_t)npair, NAN); CK(cudaMemcpyAsync(b.r2 + (size_t)h->P * kDiag2, nanv.data(), sizeof(double) * nanv.size(), cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
   CK(cudaMemcpyAsync(buf2, b.r2, sizeof(double) * ((size_t)h->P * kDiag2 + 2 * (size_t)npair), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -1703,7 +1707,7 @@ int mcu_diag_global(mcu_handle h, double alpha, int transform, double* psrf, dou
   }
   launch_diag_plan(b.r1, h->d_monlink, transform, P, b.plan, h->stream);
   launch_diag2(h->d_mom, h->d_momn, h->C, P, b.plan, b.partial, b.r2, h->stream); h->launches += 3;
-  const int npair = h->d_comom ? diag_npair(P) : 0;
+  const int npair = (h->d_comom && h->comom_ok && mpsrf) ? diag_npair(P) : 0;   // every rank of a communicator must agree on this (same flags on every rank)
   if (npair > 0) { launch_diag_pairs(h->d_mom, h->d_momn, h->d_comom, h->C, P, b.plan, transform ? 1 : 0, b.partial, b.r2 + (size_t)P * kDiag2, h->stream); h->launches += 2; }
   const size_t n2 = (size_t)P * kDiag2 + 2 * (size_t)npair;
   if (n) NK(n->AllReduce(b.r2, b.r2, n2, kNcclFloat64, kNcclSum, h->comm, h->stream));

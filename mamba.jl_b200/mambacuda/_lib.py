@@ -16,7 +16,7 @@ KIND = {"amwg": 0, "slice_uni": 1, "slice_multi": 2, "rwm": 3, "nuts": 4, "hmc":
 ADAPT = {"all": 0, "burnin": 1, "none": 2}
 PROPOSAL = {"normal": 0, "symuniform": 1, "symtriangular": 2, "cosine": 3, "epanechnikov": 4, "biweight": 5, "triweight": 6}
 GRAD = {"analytic": 0, "forward": 1, "central": 2}
-RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE, RUN_PARTIAL, RUN_ASYNC = 1, 2, 4, 8, 16
+RUN_NO_STORE, RUN_FORCE_GENERIC, RUN_GLM_REFERENCE, RUN_PARTIAL, RUN_ASYNC, RUN_MPSRF = 1, 2, 4, 8, 16, 32
 
 
 class BlockDesc(C.Structure):

@@ -603,7 +603,7 @@ def mcmc(model, *args, burnin=0, thin=1, chains=1, verbose=False, seed=123, devi
     eng.set_scheme(_block_descs(mm))
     eng.set_inits(x)
     mm.burnin = burnin
-    value = eng.run(iters, burnin=burnin, thin=thin, store=store, out=store)
+    value = eng.run(iters, burnin=burnin, thin=thin, store=store, out=store, mpsrf=True)
     if value is None:   # store=False: only the streaming moments exist (what 1e6 chains allow); diagnostics use them
         value = np.empty((0, eng.dims()[1], chains))
     return _wrap(mm, eng, value, burnin + thin, thin, chains)
@@ -639,7 +639,7 @@ def _restart(mc, iters):
             eng.set_data(k, v)
         eng.set_scheme(_block_descs(mm))
         eng.set_state(np.stack([st.value for st in mm.states]), np.stack([st.tune for st in mm.states]), mm.iter)
-    value = eng.run(iters, burnin=mm.burnin, thin=thin)
+    value = eng.run(iters, burnin=mm.burnin, thin=thin, mpsrf=True)
     mc2 = _wrap(mm, eng, value, mc.last + thin, thin, len(mc.chains))
     # the handle's streaming moments now cover the new draws as well: only the returned object may read them; the source keeps
     # the handle for density calls (dic / predict) but its diagnostics go back to its own materialised array

@@ -117,17 +117,18 @@ class Engine:
     def kept(self, first_iter, iters, burnin, thin):
         return self.L.mcu_kept(first_iter, iters, burnin, thin)
 
-    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False, partial=False, wait=True):
+    def run(self, iters, burnin=0, thin=1, store=True, out=True, force_generic=False, glm_reference=False, partial=False, wait=True, mpsrf=False):
         """Returns the [kept × p × chains] block (Fortran order) or None when out=False.
         partial=True: this call is one segment of a longer run (MCU_RUN_PARTIAL).
-        wait=False: MCU_RUN_ASYNC — the call returns once the run is queued; finish it with wait() (then samples())."""
+        wait=False: MCU_RUN_ASYNC — the call returns once the run is queued; finish it with wait() (then samples()).
+        mpsrf=True: MCU_RUN_MPSRF — also stream the within-chain covariances (multivariate PSRF without the draws)."""
         if not wait:
             out = False
         _, p, _ = self.dims()
         it0 = self.iter()
         kept = self.kept(it0, iters, burnin, thin)
         flags = (0 if store else _lib.RUN_NO_STORE) | (_lib.RUN_FORCE_GENERIC if force_generic else 0) | \
-            (_lib.RUN_GLM_REFERENCE if glm_reference else 0) | (_lib.RUN_PARTIAL if partial else 0) | (0 if wait else _lib.RUN_ASYNC)
+            (_lib.RUN_GLM_REFERENCE if glm_reference else 0) | (_lib.RUN_PARTIAL if partial else 0) | (0 if wait else _lib.RUN_ASYNC) | (_lib.RUN_MPSRF if mpsrf else 0)
         self._last_kept = kept
         arr = None
         if out:

@@ -995,7 +995,7 @@ def test_streaming_mpsrf_equals_gelmandiag_on_the_stored_draws(oracle):
     for name, transform in (("seeds_amwg", False), ("seeds_amwg", True), ("pumps_slice", True), ("rats_slice_amwg", False)):
         tpl, blocks, inits = helpers.scheme(name)
         eng = Engine(tpl, 48, seed=6); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
-        out = eng.run(900, burnin=300, thin=2, force_generic=(name == "pumps_slice"))
+        out = eng.run(900, burnin=300, thin=2, force_generic=(name == "pumps_slice"), mpsrf=True)
         psrf, summ, codes, mv = eng.diag_global(0.05, transform, mpsrf=True)
         want = api._chains_gelman(out, 0.05, codes if transform else None, True)
         np.testing.assert_allclose(psrf, want[:-1], rtol=1e-7)
@@ -1004,7 +1004,7 @@ def test_streaming_mpsrf_equals_gelmandiag_on_the_stored_draws(oracle):
         parts = []
         for off, n in ((0, 20), (20, 28)):
             e = Engine(tpl, n, seed=6, chain_offset=off); e.set_scheme(blocks); e.set_inits(inits, jitter_sd=0.05)
-            e.run(900, burnin=300, thin=2, store=False, out=False, force_generic=(name == "pumps_slice"))
+            e.run(900, burnin=300, thin=2, store=False, out=False, force_generic=(name == "pumps_slice"), mpsrf=True)
             parts.append(e)
         p = eng.dims()[1]
         r1 = _combine_round1([e.diag_round1() for e in parts], p)
@@ -1014,5 +1014,8 @@ def test_streaming_mpsrf_equals_gelmandiag_on_the_stored_draws(oracle):
     # rats with transform: alpha0 is a Logical column whose link is resolved by the heuristic to log — no streamed co-moments on that scale
     tpl, blocks, inits = helpers.scheme("rats_slice_amwg")
     eng = Engine(tpl, 16, seed=6); eng.set_scheme(blocks); eng.set_inits(inits, jitter_sd=0.05)
-    eng.run(400, burnin=100, thin=2, store=False, out=False)
+    eng.run(400, burnin=100, thin=2, store=False, out=False, mpsrf=True)
     assert np.isnan(eng.diag_global(0.05, True, mpsrf=True)[3])
+    assert not np.isnan(eng.diag_global(0.05, False, mpsrf=True)[3])
+    eng.run(100, burnin=100, thin=2, store=False, out=False)              # a run without MCU_RUN_MPSRF: the co-moments no longer cover every kept draw
+    assert np.isnan(eng.diag_global(0.05, False, mpsrf=True)[3])
