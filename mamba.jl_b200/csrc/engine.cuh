@@ -151,28 +151,23 @@ struct RunArgs {
   unsigned long long logit_mask;          // monitored columns (bit j) whose link(c) may be the logit: Logical nodes in (0, 1), chains.jl:237-246
 };
 
-static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon, unsigned long long logit_mask = 0ull,
-                                     double* comom = nullptr, unsigned long long log_mask = 0ull) {
+static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t c, int P, const double* mon, unsigned long long logit_mask = 0ull) {
   const double n = momn[0 * C + c] + 1.0; momn[0 * C + c] = n;
   double bc = momn[1 * C + c] + 1.0;
   const bool bdone = bc >= (double)kBatch;
   double nb = momn[2 * C + c];
   if (bdone) { bc = 0.0; nb += 1.0; momn[2 * C + c] = nb; }
   momn[1 * C + c] = bc;
-  const bool co = comom != nullptr && P <= kCoMaxP && P > 1;
-  double d_old[kCoMaxP], r_new[kCoMaxP], dl_old[kCoMaxP], rl_new[kCoMaxP];   // Welford co-moments: C_ij += (x_i - mean_i^old)(x_j - mean_j^new)
   for (int j = 0; j < P; ++j) {
     double* q = mom + (size_t)j * kMomPerCol * C + c;
     const double x = mon[j];
     double mean = q[0 * C], M2 = q[1 * C];
     double dl = x - mean; mean += dl / n; M2 += dl * (x - mean);
     q[0 * C] = mean; q[1 * C] = M2;
-    if (co) { d_old[j] = dl; r_new[j] = x - mean; }
     const double lx = log(x);
     double lmean = q[2 * C], lM2 = q[3 * C];
     dl = lx - lmean; lmean += dl / n; lM2 += dl * (lx - lmean);
     q[2 * C] = lmean; q[3 * C] = lM2;
-    if (co) { const bool lg = (log_mask >> j) & 1ull; dl_old[j] = lg ? dl : d_old[j]; rl_new[j] = lg ? lx - lmean : r_new[j]; }
     q[4 * C] = n == 1.0 ? x : fmin(q[4 * C], x);
     q[5 * C] = n == 1.0 ? x : fmax(q[5 * C], x);
     if (j < 64 && ((logit_mask >> j) & 1ull)) {
@@ -190,15 +185,32 @@ static MCU_NOINL void moments_update(double* mom, double* momn, size_t C, size_t
     }
     q[6 * C] = bsum;
   }
-  if (co) {
-    const size_t npair = (size_t)P * (P - 1) / 2;
-    size_t k = 0;
-    for (int i = 0; i < P; ++i)
-      for (int j = i + 1; j < P; ++j, ++k) {
-        comom[k * C + c] += d_old[i] * r_new[j];
-        comom[(npair + k) * C + c] += dl_old[i] * rl_new[j];
-      }
+}
+
+// Streaming within-chain co-moments for the multivariate PSRF (MCU_RUN_MPSRF; gelmandiag.jl:49-55): Welford update
+// C_ij += (x_i - mean_i^old)(x_j - mean_j^new) on the raw scale (set 0) and on the nodes' own link scale (set 1: log x for log_mask columns).
+// Called BEFORE moments_update (it reads the old means) and only when the run asked for it: a separate function so that the default path
+// keeps the round-1 code and register allocation (folding it into moments_update cost the fused kernels 3-15 % even when switched off).
+static MCU_NOINL void comoments_update(const double* mom, const double* momn, double* comom, size_t C, size_t c, int P, const double* mon,
+                                       unsigned long long log_mask) {
+  if (P > kCoMaxP || P < 2) return;
+  const double n = momn[0 * C + c] + 1.0;
+  double d_old[kCoMaxP], r_new[kCoMaxP], dl_old[kCoMaxP], rl_new[kCoMaxP];
+  for (int j = 0; j < P; ++j) {
+    const double* q = mom + (size_t)j * kMomPerCol * C + c;
+    const double x = mon[j];
+    const double dl = x - q[0 * C];
+    d_old[j] = dl; r_new[j] = x - (q[0 * C] + dl / n);
+    if ((log_mask >> j) & 1ull) { const double lx = log(x), dll = lx - q[2 * C]; dl_old[j] = dll; rl_new[j] = lx - (q[2 * C] + dll / n); }
+    else { dl_old[j] = d_old[j]; rl_new[j] = r_new[j]; }
   }
+  const size_t npair = (size_t)P * (P - 1) / 2;
+  size_t k = 0;
+  for (int i = 0; i < P; ++i)
+    for (int j = i + 1; j < P; ++j, ++k) {
+      comom[k * C + c] += d_old[i] * r_new[j];
+      comom[(npair + k) * C + c] += dl_old[i] * rl_new[j];
+    }
 }
 
 // The body of the generic kernel; instantiated behind two __global__ wrappers with different launch bounds (below).
@@ -245,7 +257,8 @@ __device__ __forceinline__ void generic_kernel_body(const typename M::Data& data
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;   // iters2inds: src/output/chains.jl:66-87
         for (int j = 0; j < a.P; ++j) a.samples[((size_t)row * a.P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon, a.logit_mask, a.comom, a.log_mask);
+      if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, a.P, mon, a.log_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, a.P, mon, a.logit_mask);
     }
   }
   for (int e = 0; e < a.D; ++e) a.state[(size_t)e * C + c] = s[e];

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSF_MINB) pumps_fast_kernel(const _
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon, 0ull, a.comom, a.log_mask);
+      if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, PumpsModel::P, mon, a.log_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
     }
   }
   a.state[0 * C + c] = al; a.state[1 * C + c] = be;
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < PumpsModel::P; ++j) a.samples[((size_t)row * PumpsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon, 0ull, a.comom, a.log_mask);
+      if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, PumpsModel::P, mon, a.log_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, PumpsModel::P, mon);
     }
   }
   a.state[0 * C + c] = al; a.state[1 * C + c] = be;

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < RatsModel::P; ++j) a.samples[((size_t)row * RatsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, RatsModel::P, mon, 0ull, a.comom, a.log_mask);
+      if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, RatsModel::P, mon, a.log_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, RatsModel::P, mon);
     }
   }
   // ---- store chain state and tune

@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MCU_RATS_MINB) rats_warp_
           const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
           for (int jm = 0; jm < RatsModel::P; ++jm) a.samples[((size_t)row * RatsModel::P + jm) * C + c] = mon[jm];
         }
-        moments_update(a.mom, a.momn, C, (size_t)c, RatsModel::P, mon, 0ull, a.comom, a.log_mask);
+        if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, RatsModel::P, mon, a.log_mask);
+        moments_update(a.mom, a.momn, C, (size_t)c, RatsModel::P, mon);
       }
       __syncwarp();
     }

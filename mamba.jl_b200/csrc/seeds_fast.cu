@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         const long long row = (iter - a.burnin) / a.thin - 1 - a.row0;
         for (int j = 0; j < SeedsModel::P; ++j) a.samples[((size_t)row * SeedsModel::P + j) * C + c] = mon[j];
       }
-      moments_update(a.mom, a.momn, C, (size_t)c, SeedsModel::P, mon, 0ull, a.comom, a.log_mask);
+      if (a.comom) comoments_update(a.mom, a.momn, a.comom, C, (size_t)c, SeedsModel::P, mon, a.log_mask);
+      moments_update(a.mom, a.momn, C, (size_t)c, SeedsModel::P, mon);
     }
   }
   // ---- store chain state ------------------------------------------------------------------------
