@@ -53,7 +53,28 @@
 #define MCU_SEEDS_MINB 3
 #endif
 
+#ifndef MCU_SEEDS_GLN
+#define MCU_SEEDS_GLN 0    // 1: the proposed L[i] of an alpha proposal live in an (L2-resident) global scratch array instead of shared memory
+#endif
+#ifndef MCU_SEEDS_GB
+#define MCU_SEEDS_GB 0     // 1: b[i] is updated in place in the (L2-resident) state array instead of a shared-memory copy
+#endif
+
+#ifndef MCU_SEEDS_DEDUP
+#define MCU_SEEDS_DEDUP 0   // 1: a single loop over the b trips (one copy of the trip body): measured 12 % SLOWER (every trip then carries the dynamic last-plate guards)
+#endif
+#ifndef MCU_SEEDS_PF
+#define MCU_SEEDS_PF (MCU_SEEDS_BW == 2)   // b block: sigma_b / accept counters of trip t + 1 are fetched (L2) at the top of trip t
+#endif
+#ifndef MCU_SEEDS_TAB
+#define MCU_SEEDS_TAB 1    // table-driven log / exp (fasttab_fn.cuh), tables staged in shared memory; 0 = the fdlibm forms of fastfn.cuh
+#endif
+
 #include "fastmath.cuh"
+#if MCU_SEEDS_TAB
+#include "fasttab.cuh"
+#include "fasttab_fn.cuh"
+#endif
 
 namespace mcu {
 
@@ -76,6 +97,7 @@ struct FastCfg {
   double scale_a[4], scale_b[NPL], scale_s;
   // block 0 = AMM(alpha0..alpha12) (doc/examples/seeds.jl:69): lower Cholesky factor of the initial Sigma (column-major), beta, scale
   double amm_SL[16], amm_beta, amm_scale;
+  double* gln;                        // MCU_SEEDS_GLN: [NSL][n_chains] scratch
 };
 
 #if !MCU_SEEDS_LOGU   // the u < exp(delta) form of the MH test (MCU_SEEDS_LOGU = 0)
@@ -111,19 +133,52 @@ MCU_D double pick(const Bases& g, unsigned grp) {   // warp-uniform select, keep
 template <int BS, bool AMM0>
 __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
   extern __shared__ double smem[];
-  double* sb = smem;                        // b[i]
-  double* se = smem + NSL * BS;             // e[i] = exp(eta_i)
-  double* sll = smem + 2 * NSL * BS;        // L[i] = log(1 + e[i])
-  double* sln = smem + 3 * NSL * BS;        // proposed L[i]
+  double* se = smem;                        // e[i] = exp(eta_i)
+  double* sll = smem + NSL * BS;            // L[i] = log(1 + e[i])
+#if !MCU_SEEDS_GB
+  double* sb = smem + 2 * NSL * BS;         // b[i]
+#endif
+#if !MCU_SEEDS_GLN
+  double* sln = smem + (3 - MCU_SEEDS_GB) * NSL * BS;   // proposed L[i]
+#endif
   const int tid = threadIdx.x;
   const long long c = (long long)blockIdx.x * BS + tid;
+#if MCU_SEEDS_TAB
+  double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;   // 128 x (invc, logc), 16-byte aligned
+  double* tex = tlg + 256;                                              // 128 x 2^(j/128)
+  for (int i = tid; i < 256; i += BS) tlg[i] = kLogTabG[i];
+  for (int i = tid; i < 128; i += BS) tex[i] = kExpTabG[i];
+  __syncthreads();
+#define FLOG(x) tab::tlog((x), tlg)
+#define FEXP(x) tab::texp((x), tex)
+#else
+#define FLOG(x) fast_log(x)
+#define FEXP(x) fast_exp(x)
+#endif
   if (c >= a.n_chains) return;
+  // the draws of fastmath.cuh with the kernel's own log (same Philox blocks, same arithmetic otherwise)
+  auto log_uniform = [&](double u) { return u > 0.0 ? FLOG(u) : -CUDART_INF; };
+  auto draw_normal_pair = [&](const RunArgs& aa, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) -> Pair {
+    uint32_t w[4];
+    philox4x32_10(kpair, itn, ch, blk | (1u << 24), (uint32_t)aa.seed, (uint32_t)(aa.seed >> 32), w);
+    const double rad = sqrt(-2.0 * FLOG(1.0 - u53(w[0], w[1])));
+    const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
+    return {rad * sc.b, rad * sc.a};
+  };
   const size_t C = (size_t)a.n_chains;
   const uint32_t chain = (uint32_t)(a.chain_offset + c);
+#if MCU_SEEDS_GB
+#define SB(i) a.state[(size_t)(5 + (i)) * C + c]
+#else
 #define SB(i) sb[(i) * BS + tid]
+#endif
 #define SE(i) se[(i) * BS + tid]
 #define SLL(i) sll[(i) * BS + tid]
+#if MCU_SEEDS_GLN
+#define SLN(i) cfg.gln[(size_t)(i) * C + c]
+#else
 #define SLN(i) sln[(i) * BS + tid]
+#endif
 #define SSG(i) TUNE(1, 2 + (i))
 #define SAC(i) TUNE(1, 2 + NPL + (i))
 #define TUNE(blk, slot) a.tune[(size_t)(cfg.tune_off[blk] + (slot)) * C + c]
@@ -132,7 +187,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   double al0 = a.state[0 * C + c], al1 = a.state[1 * C + c], al2 = a.state[2 * C + c], al3 = a.state[3 * C + c];
   double s2 = a.state[4 * C + c];
   double x = log(s2);
+#if !MCU_SEEDS_GB
   for (int i = 0; i < NPL; ++i) SB(i) = a.state[(size_t)(5 + i) * C + c];
+#endif
   // tune: block 0 [m, adapt, sigma[4], accept[4]]; block 1 [m, adapt, sigma[21], accept[21]]; block 2 [m, adapt, sigma, accept]
   // AMM tune record of block 0 (samplers.cuh): [adapt, m, Mv[4], Mvv[16], SigmaLm[16]] — it stays in the L2-resident tune array
   double m0 = AMM0 ? 0.0 : TUNE(0, 0), m1 = TUNE(1, 0), m2 = TUNE(2, 0);
@@ -142,8 +199,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   double sgs = TUNE(2, 2); int acs = (int)TUNE(2, 3);
 
   Bases g = group_bases(al0, al1, al2, al3);
-  for (int i = 0; i < NPL; ++i) { const double e = fast_exp(pick(g, cfg.grp[i]) + SB(i)); SE(i) = e; SLL(i) = fast_log(1.0 + e); }
-  SB(NPL) = 0.0; SE(NPL) = 0.0; SLL(NPL) = 0.0; SLN(NPL) = 0.0;   // dummy slot: log(1 + 0 * E) = 0, n = 0
+  for (int i = 0; i < NPL; ++i) { const double e = FEXP(pick(g, cfg.grp[i]) + SB(i)); SE(i) = e; SLL(i) = FLOG(1.0 + e); }
+#if !MCU_SEEDS_GB
+  SB(NPL) = 0.0;
+#endif
+  SE(NPL) = 0.0; SLL(NPL) = 0.0; SLN(NPL) = 0.0;   // dummy slot: log(1 + 0 * E) = 0, n = 0
 
   double mon[SeedsModel::P];
   for (long long it = 1; it <= a.iters; ++it) {
@@ -191,7 +251,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       // logf(x) - logf(v): every plate of group q moves by dg[q]; e_i' = e_i exp(dg[grp_i]) (4 exps, 21 logs), priors Normal(0, 1000)
       const Bases gn = group_bases(xp[0], xp[1], xp[2], xp[3]);
       const double dg0 = gn.g0 - g.g0, dg1 = gn.g1 - g.g1, dg2 = gn.g2 - g.g2, dg3 = gn.g3 - g.g3;
-      const double E0 = fast_exp(dg0), E1 = fast_exp(dg1), E2 = fast_exp(dg2), E3 = fast_exp(dg3);
+      const double E0 = FEXP(dg0), E1 = FEXP(dg1), E2 = FEXP(dg2), E3 = FEXP(dg3);
       double delta = 0.0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) delta = fma(-0.5e-6, fma(xp[i], xp[i], -v[i] * v[i]), delta);
@@ -202,7 +262,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         const double Ea = (q0 & 2u) ? ((q0 & 1u) ? E3 : E2) : ((q0 & 1u) ? E1 : E0), da_ = (q0 & 2u) ? ((q0 & 1u) ? dg3 : dg2) : ((q0 & 1u) ? dg1 : dg0);
         const double Eb = (q1 & 2u) ? ((q1 & 1u) ? E3 : E2) : ((q1 & 1u) ? E1 : E0), db_ = (q1 & 2u) ? ((q1 & 1u) ? dg3 : dg2) : ((q1 & 1u) ? dg1 : dg0);
         const double Ec = (q2 & 2u) ? ((q2 & 1u) ? E3 : E2) : ((q2 & 1u) ? E1 : E0), dc_ = (q2 & 2u) ? ((q2 & 1u) ? dg3 : dg2) : ((q2 & 1u) ? dg1 : dg0);
-        const double la = fast_log(fma(SE(i), Ea, 1.0)), lb = fast_log(fma(SE(i + 1), Eb, 1.0)), lc = fast_log(fma(SE(i + 2), Ec, 1.0));
+        const double la = FLOG(fma(SE(i), Ea, 1.0)), lb = FLOG(fma(SE(i + 1), Eb, 1.0)), lc = FLOG(fma(SE(i + 2), Ec, 1.0));
         SLN(i) = la; SLN(i + 1) = lb; SLN(i + 2) = lc;
         dLa += fma(cfg.r[i], da_, -cfg.n[i] * (la - SLL(i)));
         dLb += fma(cfg.r[i + 1], db_, -cfg.n[i + 1] * (lb - SLL(i + 1)));
@@ -262,14 +322,14 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         const double q3 = j == 0 ? al3 : (j == 1 ? al2 : (j == 2 ? al1 : anew));
         const Bases gn = group_bases(q0, q1, q2, q3);
         // every affected plate moves by the same step: e_i' = e_i exp(z); ll_i' - ll_i = r_i z - n_i (L_i' - L_i)
-        const double E = fast_exp(z);
+        const double E = FEXP(z);
         // three plates per trip: their logs are independent, so the scheduler fills one chain's DFMA latency with the others
         double dLa = 0.0, dLb = 0.0, dLc = 0.0;
         const int nt = cfg.atriples[j];
 #pragma unroll 1
         for (int k = 0; k < nt; ++k) {
           const int ia = cfg.alist[j][3 * k], ib = cfg.alist[j][3 * k + 1], ic = cfg.alist[j][3 * k + 2];
-          const double la = fast_log(fma(SE(ia), E, 1.0)), lb = fast_log(fma(SE(ib), E, 1.0)), lc = fast_log(fma(SE(ic), E, 1.0));
+          const double la = FLOG(fma(SE(ia), E, 1.0)), lb = FLOG(fma(SE(ib), E, 1.0)), lc = FLOG(fma(SE(ic), E, 1.0));
           SLN(ia) = la; SLN(ib) = lb; SLN(ic) = lc;
           dLa = fma(cfg.n[ia], la - SLL(ia), dLa);
           dLb = fma(cfg.n[ib], lb - SLL(ib), dLb);
@@ -315,6 +375,20 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       const double half_inv_s2 = 0.5 / s2;                                // b ~ Normal(0, sqrt(s2)): -(b/sigma)^2 / 2 = -b^2 / (2 s2)
       // The b_i are conditionally independent given alpha and s2, so W plates (the draws of W / 2 Philox pairs) are updated
       // per trip in straight-line code: W independent exp → log → exp chains for the scheduler to interleave.
+#if MCU_SEEDS_PF
+      // The tune array is L2-resident (L1 is all shared memory here): ~700 cycles per load.  With the table-driven log / exp a trip is too
+      // short to hide that behind its own draws, so the loads run one trip ahead.
+      double psg[2], pac[2];
+      auto b_fetch = [&](int i0) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const bool real = i0 + w < NPL;
+          psg[w] = real ? SSG(i0 + w) : 0.0;
+          pac[w] = (real && adapt) ? SAC(i0 + w) : 0.0;
+        }
+      };
+      b_fetch(0);
+#endif
       auto b_trip = [&](auto Wc, int i0) {
         constexpr int W = decltype(Wc)::value;
         int ix[W]; double sg[W], bi[W], zn[W], uu[W], ac[W];
@@ -325,10 +399,21 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; ++w) {
           const bool real = i0 + w < NPL;
           ix[w] = real ? i0 + w : NPL;                                     // past the last plate: the dummy slot (never accepted)
-          sg[w] = real ? SSG(ix[w]) : 0.0;                                 // global (L2) loads, issued a whole trip ahead of their use
+#if MCU_SEEDS_PF
+          sg[w] = psg[w]; ac[w] = pac[w];
+#else
+          sg[w] = real ? SSG(ix[w]) : 0.0;                                 // global (L2) loads at the top of the trip
           ac[w] = (real && adapt) ? SAC(ix[w]) : 0.0;
+#endif
+#if MCU_SEEDS_GB
+          bi[w] = real ? SB(ix[w]) : 0.0;
+#else
           bi[w] = SB(ix[w]);
+#endif
         }
+#if MCU_SEEDS_PF
+        b_fetch(i0 + W);
+#endif
 #pragma unroll
         for (int w = 0; w < W; w += 2) {
           const Pair pz = draw_normal_pair(a, chain, it32, 1, (i0 + w) >> 1);
@@ -346,8 +431,8 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; ++w) {
           const int ir = i0 + w < NPL ? i0 + w : 0;                        // constants of a real plate for the dummy chain
           bn[w] = bi[w] + sg[w] * zn[w];
-          en[w] = fast_exp(pick(g, cfg.grp[ir]) + bn[w]);                  // fresh e_i: also resets the drift of the alpha updates
-          ln[w] = fast_log(1.0 + en[w]);
+          en[w] = FEXP(pick(g, cfg.grp[ir]) + bn[w]);                  // fresh e_i: also resets the drift of the alpha updates
+          ln[w] = FLOG(1.0 + en[w]);
           const double dl = fma(cfg.r[ir], bn[w] - bi[w], -cfg.n[ix[w]] * (ln[w] - SLL(ix[w]))) - half_inv_s2 * fma(bn[w], bn[w], -bi[w] * bi[w]);
 #if MCU_SEEDS_LOGU == 2
           acc[w] = i0 + w < NPL && logu_less(lb[w], dl);
@@ -381,9 +466,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
           pz = draw_normal_pair(a, chain, it32, 1, ip + 1);
           { const Pair pu = draw_uniform_pair(a, chain, it32, 1, ip + 1); lu.a = log_uniform(pu.a); lu.b = log_uniform(pu.b); }
           const double bna = bia + sga * za, bnb = bib + sgb * zb;
-          const double ena = fast_exp(pick(g, cfg.grp[i0]) + bna);             // fresh e_i: also resets the drift of the alpha updates
-          const double enb = fast_exp(pick(g, cfg.grp[r1]) + bnb);
-          const double lna = fast_log(1.0 + ena), lnb = fast_log(1.0 + enb);
+          const double ena = FEXP(pick(g, cfg.grp[i0]) + bna);             // fresh e_i: also resets the drift of the alpha updates
+          const double enb = FEXP(pick(g, cfg.grp[r1]) + bnb);
+          const double lna = FLOG(1.0 + ena), lnb = FLOG(1.0 + enb);
           const double da = fma(cfg.r[i0], bna - bia, -cfg.n[i0] * (lna - SLL(i0))) - half_inv_s2 * fma(bna, bna, -bia * bia);
           const double db = fma(cfg.r[r1], bnb - bib, -cfg.n[i1] * (lnb - SLL(i1))) - half_inv_s2 * fma(bnb, bnb, -bib * bib);
           const bool acca = lua < da, accb = two && lub < db;
@@ -395,8 +480,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       {
         constexpr int W = MCU_SEEDS_BW;
         int i0 = 0;
+        if constexpr (W != 2 || !MCU_SEEDS_DEDUP) {   // (W == 2: one loop, one copy of the trip body in the instruction stream)
 #pragma unroll 1
-        for (; i0 + W <= NPL; i0 += W) b_trip(std::integral_constant<int, W>{}, i0);
+          for (; i0 + W <= NPL; i0 += W) b_trip(std::integral_constant<int, W>{}, i0);
+        }
 #pragma unroll 1
         for (; i0 < NPL; i0 += 2) b_trip(std::integral_constant<int, 2>{}, i0);
       }
@@ -421,7 +508,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
 #endif
       const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
-      const double s2n = (xn > -700.0 && xn < 700.0) ? fast_exp(xn) : exp(xn);
+      const double s2n = (xn > -700.0 && xn < 700.0) ? FEXP(xn) : exp(xn);
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
       //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double dx = xn - x;
@@ -454,7 +541,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   // ---- store chain state ------------------------------------------------------------------------
   a.state[0 * C + c] = al0; a.state[1 * C + c] = al1; a.state[2 * C + c] = al2; a.state[3 * C + c] = al3;
   a.state[4 * C + c] = s2;
+#if !MCU_SEEDS_GB
   for (int i = 0; i < NPL; ++i) a.state[(size_t)(5 + i) * C + c] = SB(i);
+#endif
   if (!AMM0) {
     TUNE(0, 0) = m0; TUNE(0, 1) = ad0 ? 1.0 : 0.0;
     TUNE(0, 2) = sg0; TUNE(0, 3) = sg1; TUNE(0, 4) = sg2; TUNE(0, 5) = sg3;
@@ -469,11 +558,13 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #undef SSG
 #undef SAC
 #undef TUNE
+#undef FLOG
+#undef FEXP
 }
 
 template <int BS, bool AMM0>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)BS * 4 * NSL * sizeof(double);
+  const size_t smem = ((size_t)BS * (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL + (MCU_SEEDS_TAB ? 384 : 0)) * sizeof(double);
   static thread_local int attr_dev = -1;   // the attribute call is slow: once per device
   int dev = 0; cudaGetDevice(&dev);
   if (attr_dev != dev) {
@@ -492,6 +583,15 @@ int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
 int seeds_fast_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st) {
   FastCfg cfg;
+  cfg.gln = nullptr;
+#if MCU_SEEDS_GLN
+  {   // experiment: scratch kept per process (one device)
+    static double* buf = nullptr; static size_t cap = 0;
+    const size_t need = (size_t)NSL * (size_t)a.n_chains;
+    if (need > cap) { if (buf) cudaFree(buf); if (cudaMalloc(&buf, need * sizeof(double)) != cudaSuccess) return -1; cap = need; }
+    cfg.gln = buf;
+  }
+#endif
   // plate constants, scales and (AMM) the Cholesky factor come from the handle's host-side copies of what the generic path uses
   const bool amm0 = h_blocks[0].kind == 6;   // MCU_AMM
   double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[NPL], ss[1];
