@@ -81,6 +81,19 @@ MCU_D double fast_log(double x) {
   return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
 }
 
+// sqrt(x) for x >= 0 below ~1e300, branch-free (the library sqrt carries a slow-path call that ends the basic block, so the scheduler cannot
+// interleave two Box-Muller transforms): y ~ 1/sqrt(x) from MUFU.RSQ64H (~2^-22), two Newton steps, then one correction of s = x y with
+// the exact residual x - s^2 (FMA).  <= 1 ulp (tools/check_fasttab.cpp tests the same arithmetic on the host).  x == 0 returns 0.
+MCU_D double fast_sqrt(double x) {
+  double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);                   // y (1 + (1/2 - x y^2 / 2))
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  double sq = x * y;
+  sq = fma(fma(-sq, sq, x), 0.5 * y, sq);                // s + (x - s^2) / (2 s)
+  return x > 0.0 ? sq : 0.0;
+}
+
 // sin and cos of 2 pi u, u in [0, 1): quadrant reduction is exact (u - q/4), then fdlibm's sin/cos kernels on |x| <= pi/4
 __constant__ double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
                                 -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};

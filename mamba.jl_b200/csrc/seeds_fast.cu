@@ -34,14 +34,17 @@
 #define MCU_SEEDS_ESTRIN 0
 #endif
 #define MCU_FASTMATH_ESTRIN MCU_SEEDS_ESTRIN   // before the first include: fastfn.cuh comes in through launch.hpp
+#ifndef MCU_LOGU_DOUBLE
+#define MCU_LOGU_DOUBLE 1                      // fastmath.cuh: the float bracket of log u is widened to doubles next to the draw (1 % faster here)
+#endif
 #include "launch.hpp"
 
 #ifndef MCU_SEEDS_BW
 #define MCU_SEEDS_BW 2      // plates per trip in the b block (even)
 #endif
 #ifndef MCU_SEEDS_LOGU
-#define MCU_SEEDS_LOGU 1   // MH test on the log scale (log u evaluated off the critical path); 2 = float bracket + FP64 log inside the
-                           // rounding band only (same decisions; measured 3-7 % slower, profiles/r1_seeds_fast_summary.md)
+#define MCU_SEEDS_LOGU 2   // MH test on the log scale: 1 = FP64 log u next to the draw (off the critical path); 2 = float bracket of log u + FP64 log inside the
+                           // rounding band only (same decisions; 3-7 % slower than 1 with the fdlibm log in round 1, 3 % faster with the table log)
 #endif
 #ifndef MCU_SEEDS_PIPE
 #define MCU_SEEDS_PIPE 0   // b block: draws of trip t + 1 generated during trip t — measured 10 % SLOWER (profiles/r1_seeds_fast_summary.md), kept for the record
@@ -63,8 +66,22 @@
 #ifndef MCU_SEEDS_DEDUP
 #define MCU_SEEDS_DEDUP 0   // 1: a single loop over the b trips (one copy of the trip body): measured 12 % SLOWER (every trip then carries the dynamic last-plate guards)
 #endif
+#ifndef MCU_SEEDS_FSQRT
+#define MCU_SEEDS_FSQRT 1   // Box-Muller radius through the branch-free fast_sqrt (fastfn.cuh)
+#endif
+#ifndef MCU_SEEDS_UPFRONT
+#define MCU_SEEDS_UPFRONT 0   // every draw of the alpha and s2 blocks (counter-based: no state needed) and exp(z_j) are formed at the top of the
+                              // iteration, six independent Philox / Box-Muller / log / exp chains side by side, instead of pair by pair
+                              // inside the rolled component loop
+#endif
+#ifndef MCU_SEEDS_CALLS
+#define MCU_SEEDS_CALLS 0   // 1: the paired draws (Philox + Box-Muller, Philox + two logs) are out-of-line functions: one copy each in the instruction stream
+#endif
+#ifndef MCU_SEEDS_AW
+#define MCU_SEEDS_AW 3      // plates per trip of an alpha proposal (the plate lists are padded with the dummy slot to a multiple of it)
+#endif
 #ifndef MCU_SEEDS_PF
-#define MCU_SEEDS_PF (MCU_SEEDS_BW == 2)   // b block: sigma_b / accept counters of trip t + 1 are fetched (L2) at the top of trip t
+#define MCU_SEEDS_PF 1   // b block: sigma_b / accept counters of trip t + 1 are fetched (L2) at the top of trip t
 #endif
 #ifndef MCU_SEEDS_TAB
 #define MCU_SEEDS_TAB 1    // table-driven log / exp (fasttab_fn.cuh), tables staged in shared memory; 0 = the fdlibm forms of fastfn.cuh
@@ -86,8 +103,8 @@ constexpr int NSL = NPL + 1;          // shared-memory slots per array: 21 plate
 
 struct FastCfg {
   double r[NPL], n[NSL];
-  unsigned char alist[4][24];         // plates whose eta depends on alpha_j, padded with the dummy slot to a multiple of 3
-  int atriples[4];
+  unsigned char alist[4][24];         // plates whose eta depends on alpha_j, padded with the dummy slot to a multiple of MCU_SEEDS_AW
+  int atriples[4];                    // trips of MCU_SEEDS_AW plates
   double rsum[4];                     // sum of r_i over the plates that depend on alpha_j
   unsigned char grp[NPL];             // 0:(x1=0,x2=0) 1:(0,1) 2:(1,0) 3:(1,1)
   unsigned amask[4];                  // plates whose eta depends on alpha_j
@@ -129,6 +146,28 @@ MCU_D double pick(const Bases& g, unsigned grp) {   // warp-uniform select, keep
   return (grp & 2u) ? hi : lo;
 }
 
+#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
+template <int BS>
+static __device__ __noinline__ Pair seeds_normal_pair_nc(unsigned long long seed, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) {
+  extern __shared__ double smem[];
+  const double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;
+  uint32_t w[4];
+  philox4x32_10(kpair, itn, ch, blk | (1u << 24), (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const double rad = sqrt(-2.0 * tab::tlog(1.0 - u53(w[0], w[1]), tlg));
+  const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
+  return {rad * sc.b, rad * sc.a};
+}
+template <int BS>
+static __device__ __noinline__ Pair seeds_logu_pair_nc(unsigned long long seed, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) {
+  extern __shared__ double smem[];
+  const double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;
+  uint32_t w[4];
+  philox4x32_10(kpair, itn, ch, blk, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
+  return {ua > 0.0 ? tab::tlog(ua, tlg) : -CUDART_INF, ub > 0.0 ? tab::tlog(ub, tlg) : -CUDART_INF};
+}
+#endif
+
 // AMM0: block 0 is AMM(alpha0, alpha1, alpha2, alpha12) (the reference's scheme, doc/examples/seeds.jl:69-71) instead of AMWG
 template <int BS, bool AMM0>
 __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ RunArgs a) {
@@ -156,12 +195,31 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #define FEXP(x) fast_exp(x)
 #endif
   if (c >= a.n_chains) return;
+#if !MCU_SEEDS_LOGU
+  auto mh_accept = [&](double u, double delta) { return delta >= 0.0 ? true : (delta > -700.0 ? u < FEXP(delta) : false); };
+  auto mh_accept_nb = [&](double u, double delta) { const double ex = FEXP(fmax(fmin(delta, 0.0), -700.0)); return delta >= 0.0 ? true : (delta > -700.0 && u < ex); };
+#endif
   // the draws of fastmath.cuh with the kernel's own log (same Philox blocks, same arithmetic otherwise)
   auto log_uniform = [&](double u) { return u > 0.0 ? FLOG(u) : -CUDART_INF; };
+  auto draw_logu_pair = [&](uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) -> Pair {   // logs of both uniforms of a Philox block
+#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
+    return seeds_logu_pair_nc<BS>(a.seed, ch, itn, blk, kpair);
+#else
+    const Pair pu = draw_uniform_pair(a, ch, itn, blk, kpair);
+    return {log_uniform(pu.a), log_uniform(pu.b)};
+#endif
+  };
   auto draw_normal_pair = [&](const RunArgs& aa, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) -> Pair {
+#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
+    return seeds_normal_pair_nc<BS>(aa.seed, ch, itn, blk, kpair);
+#endif
     uint32_t w[4];
     philox4x32_10(kpair, itn, ch, blk | (1u << 24), (uint32_t)aa.seed, (uint32_t)(aa.seed >> 32), w);
+#if MCU_SEEDS_FSQRT
+    const double rad = fast_sqrt(-2.0 * FLOG(1.0 - u53(w[0], w[1])));
+#else
     const double rad = sqrt(-2.0 * FLOG(1.0 - u53(w[0], w[1])));
+#endif
     const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
     return {rad * sc.b, rad * sc.a};
   };
@@ -217,6 +275,15 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       sgs = cfg.scale_s; acs = 0;
       if (AMM0) for (int i = 0; i < 38; ++i) TUNE(0, i) = 0.0;   // AMMTune(x, Sigma): amm.jl:14-24
     }
+#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
+    // Block 2's proposal needs only x = log s2 and its sigma, which no other block changes: it is formed here so that its Philox / Box-Muller /
+    // log / exp chains run beside those of block 0; only sum b_i^2 and the test wait for block 1.
+    const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
+    const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
+    const double s2n = (xn > -700.0 && xn < 700.0) ? FEXP(xn) : exp(xn);
+    const double dx = xn - x;
+    const double dinv = 1.0 / s2n - 1.0 / s2;
+#endif
     // ================================================================== block 0, AMM form (amm.jl:66-108; device generic form: samplers.cuh amm_sample)
     if (AMM0) {
       const bool adapt = cfg.adapt[0] == 1 ? iter <= a.burnin : cfg.adapt[0] == 0;
@@ -300,9 +367,24 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       ad0 = adapt;
       if (adapt) m0 += 1.0;
       // components are rotated through slot 0 so the loop stays rolled with everything in registers
+#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
+      // slot s holds (z, exp z, log u) of component (j + s) % 4, rotated with the alphas
+      double z0, z1, z2, z3, E0, E1, E2, E3, lu0, lu1, lu2, lu3;
+      {
+        const Pair n01 = draw_normal_pair(a, chain, it32, 0, 0), n23 = draw_normal_pair(a, chain, it32, 0, 1);
+        const Pair u01 = draw_logu_pair(chain, it32, 0, 0), u23 = draw_logu_pair(chain, it32, 0, 1);
+        z0 = sg0 * n01.a; z1 = sg1 * n01.b; z2 = sg2 * n23.a; z3 = sg3 * n23.b;   // z = sigma .* randn(n)
+        E0 = FEXP(z0); E1 = FEXP(z1); E2 = FEXP(z2); E3 = FEXP(z3);
+        lu0 = u01.a; lu1 = u01.b; lu2 = u23.a; lu3 = u23.b;
+      }
+#else
       double zc = 0.0, uc = 0.0;   // second draw of the current Philox pair
+#endif
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
+#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
+        const double z = z0, lu = lu0;
+#else
         double zn01;
         if ((j & 1) == 0) { const Pair pr = draw_normal_pair(a, chain, it32, 0, j >> 1); zn01 = pr.a; zc = pr.b; } else zn01 = zc;
 #if MCU_SEEDS_LOGU == 2
@@ -310,9 +392,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); lu = logu_bracket(pr.a); uc = pr.b; } else lu = logu_bracket(uc);
 #elif MCU_SEEDS_LOGU
         double lu;                                                        // log of uniform j of the block, off the critical path
-        if ((j & 1) == 0) { const Pair pr = draw_uniform_pair(a, chain, it32, 0, j >> 1); lu = log_uniform(pr.a); uc = log_uniform(pr.b); } else lu = uc;
+        if ((j & 1) == 0) { const Pair pr = draw_logu_pair(chain, it32, 0, j >> 1); lu = pr.a; uc = pr.b; } else lu = uc;
 #endif
         const double z = sg0 * zn01;                                      // z = sigma .* randn(n): normal j of the block
+#endif
         const double anew = al0 + z;
         const unsigned pm = cfg.amask[j];
         // proposed group bases, again in the reference's summation order (slot s holds alpha_{(j+s)%4})
@@ -322,20 +405,31 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         const double q3 = j == 0 ? al3 : (j == 1 ? al2 : (j == 2 ? al1 : anew));
         const Bases gn = group_bases(q0, q1, q2, q3);
         // every affected plate moves by the same step: e_i' = e_i exp(z); ll_i' - ll_i = r_i z - n_i (L_i' - L_i)
+#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
+        const double E = E0;
+#else
         const double E = FEXP(z);
-        // three plates per trip: their logs are independent, so the scheduler fills one chain's DFMA latency with the others
-        double dLa = 0.0, dLb = 0.0, dLc = 0.0;
+#endif
+        // AW plates per trip: their logs are independent, so the scheduler fills one chain's DFMA latency with the others
+        constexpr int AW = MCU_SEEDS_AW;
+        double dL[AW];
+#pragma unroll
+        for (int w = 0; w < AW; ++w) dL[w] = 0.0;
         const int nt = cfg.atriples[j];
 #pragma unroll 1
         for (int k = 0; k < nt; ++k) {
-          const int ia = cfg.alist[j][3 * k], ib = cfg.alist[j][3 * k + 1], ic = cfg.alist[j][3 * k + 2];
-          const double la = FLOG(fma(SE(ia), E, 1.0)), lb = FLOG(fma(SE(ib), E, 1.0)), lc = FLOG(fma(SE(ic), E, 1.0));
-          SLN(ia) = la; SLN(ib) = lb; SLN(ic) = lc;
-          dLa = fma(cfg.n[ia], la - SLL(ia), dLa);
-          dLb = fma(cfg.n[ib], lb - SLL(ib), dLb);
-          dLc = fma(cfg.n[ic], lc - SLL(ic), dLc);
+          int ii[AW]; double ln[AW];
+#pragma unroll
+          for (int w = 0; w < AW; ++w) ii[w] = cfg.alist[j][AW * k + w];
+#pragma unroll
+          for (int w = 0; w < AW; ++w) ln[w] = FLOG(fma(SE(ii[w]), E, 1.0));
+#pragma unroll
+          for (int w = 0; w < AW; ++w) { SLN(ii[w]) = ln[w]; dL[w] = fma(cfg.n[ii[w]], ln[w] - SLL(ii[w]), dL[w]); }
         }
-        double delta = fma(cfg.rsum[j], z, -((dLa + dLb) + dLc));
+        double dLs = dL[0];
+#pragma unroll
+        for (int w = 1; w < AW; ++w) dLs += dL[w];
+        double delta = fma(cfg.rsum[j], z, -dLs);
         {   // Normal(0, 1000) prior of the component: -(z^2 + log 2pi)/2 - log sigma
           delta = fma(-0.5e-6, fma(anew, anew, -al0 * al0), delta);   // (x / 1000)^2 / 2 without the divisions
         }
@@ -357,6 +451,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         { const double t = al0; al0 = al1; al1 = al2; al2 = al3; al3 = t; }
         { const double t = sg0; sg0 = sg1; sg1 = sg2; sg2 = sg3; sg3 = t; }
         { const int t = ac0; ac0 = ac1; ac1 = ac2; ac2 = ac3; ac3 = t; }
+#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
+        { const double t = z0; z0 = z1; z1 = z2; z2 = z3; z3 = t; }
+        { const double t = E0; E0 = E1; E1 = E2; E2 = E3; E3 = t; }
+        { const double t = lu0; lu0 = lu1; lu1 = lu2; lu2 = lu3; lu3 = t; }
+#endif
       }
       if (adapt && ((long long)m0 % cfg.batchsize[0]) == 0) {
         const double dl = amwg_delta(m0, cfg.batchsize[0]);
@@ -378,10 +477,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #if MCU_SEEDS_PF
       // The tune array is L2-resident (L1 is all shared memory here): ~700 cycles per load.  With the table-driven log / exp a trip is too
       // short to hide that behind its own draws, so the loads run one trip ahead.
-      double psg[2], pac[2];
+      double psg[MCU_SEEDS_BW], pac[MCU_SEEDS_BW];
       auto b_fetch = [&](int i0) {
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < MCU_SEEDS_BW; ++w) {
           const bool real = i0 + w < NPL;
           psg[w] = real ? SSG(i0 + w) : 0.0;
           pac[w] = (real && adapt) ? SAC(i0 + w) : 0.0;
@@ -391,7 +490,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #endif
       auto b_trip = [&](auto Wc, int i0) {
         constexpr int W = decltype(Wc)::value;
-        int ix[W]; double sg[W], bi[W], zn[W], uu[W], ac[W];
+        int ix[W]; double sg[W], bi[W], zn[W], ac[W]; [[maybe_unused]] double uu[W];
 #if MCU_SEEDS_LOGU == 2
         LogU lb[W];
 #endif
@@ -417,11 +516,15 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #pragma unroll
         for (int w = 0; w < W; w += 2) {
           const Pair pz = draw_normal_pair(a, chain, it32, 1, (i0 + w) >> 1);
+#if MCU_SEEDS_LOGU == 1
+          const Pair pu = draw_logu_pair(chain, it32, 1, (i0 + w) >> 1);
+#else
           const Pair pu = draw_uniform_pair(a, chain, it32, 1, (i0 + w) >> 1);
+#endif
 #if MCU_SEEDS_LOGU == 2
           zn[w] = pz.a; zn[w + 1] = pz.b; lb[w] = logu_bracket(pu.a); lb[w + 1] = logu_bracket(pu.b);
 #elif MCU_SEEDS_LOGU
-          zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = log_uniform(pu.a); uu[w + 1] = log_uniform(pu.b);
+          zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = pu.a; uu[w + 1] = pu.b;
 #else
           zn[w] = pz.a; zn[w + 1] = pz.b; uu[w] = pu.a; uu[w + 1] = pu.b;
 #endif
@@ -502,17 +605,23 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       if (adapt) m2 += 1.0;
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
+#if !(MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1)
 #if MCU_SEEDS_LOGU == 2
       const LogU lus = logu_bracket(draw_uniform_pair(a, chain, it32, 2, 0).a);
 #elif MCU_SEEDS_LOGU
+#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
+      const double lus = draw_logu_pair(chain, it32, 2, 0).a;
+#else
       const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
+#endif
 #endif
       const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
       const double s2n = (xn > -700.0 && xn < 700.0) ? FEXP(xn) : exp(xn);
-      // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
-      //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double dx = xn - x;
       const double dinv = 1.0 / s2n - 1.0 / s2;
+#endif
+      // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
+      //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double delta = -(0.001 + 1.0) * dx - 0.001 * dinv + dx - 0.5 * S * dinv - (double)NPL * 0.5 * dx;
 #if MCU_SEEDS_LOGU == 2
       if (logu_less(lus, delta)) { x = xn; s2 = s2n; if (adapt) acs += 1; }
@@ -614,8 +723,8 @@ int seeds_fast_launch(const double* r, const double* n, const double* x1, const 
   for (int j = 0; j < 4; ++j) {
     int cnt = 0;
     for (int i = 0; i < NPL; ++i) if ((cfg.amask[j] >> i) & 1u) cfg.alist[j][cnt++] = (unsigned char)i;
-    while (cnt % 3) cfg.alist[j][cnt++] = (unsigned char)NPL;
-    cfg.atriples[j] = cnt / 3;
+    while (cnt % MCU_SEEDS_AW) cfg.alist[j][cnt++] = (unsigned char)NPL;
+    cfg.atriples[j] = cnt / MCU_SEEDS_AW;
     for (int k = cnt; k < 24; ++k) cfg.alist[j][k] = (unsigned char)NPL;
   }
   cfg.gmask[0] = 0xFu; cfg.gmask[1] = 0xCu; cfg.gmask[2] = 0xAu; cfg.gmask[3] = 0x8u;
