@@ -66,6 +66,9 @@
 #ifndef MCU_SEEDS_DEDUP
 #define MCU_SEEDS_DEDUP 0   // 1: a single loop over the b trips (one copy of the trip body): measured 12 % SLOWER (every trip then carries the dynamic last-plate guards)
 #endif
+#ifndef MCU_SEEDS_SCTAB
+#define MCU_SEEDS_SCTAB 0   // 1: Box-Muller angle through the table-driven sincos (fasttab_fn.cuh): measured 1 % slower than the polynomial form (143.3 vs 142.0 ms)
+#endif
 #ifndef MCU_SEEDS_FSQRT
 #define MCU_SEEDS_FSQRT 1   // Box-Muller radius through the branch-free fast_sqrt (fastfn.cuh)
 #endif
@@ -187,6 +190,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   double* tex = tlg + 256;                                              // 128 x 2^(j/128)
   for (int i = tid; i < 256; i += BS) tlg[i] = kLogTabG[i];
   for (int i = tid; i < 128; i += BS) tex[i] = kExpTabG[i];
+#if MCU_SEEDS_SCTAB
+  double* tsc = tex + 128;                                              // 128 x (sin, cos)(2 pi j / 128), 16-byte aligned
+  for (int i = tid; i < 256; i += BS) tsc[i] = kSinCosTabG[i];
+#endif
   __syncthreads();
 #define FLOG(x) tab::tlog((x), tlg)
 #define FEXP(x) tab::texp((x), tex)
@@ -220,8 +227,13 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #else
     const double rad = sqrt(-2.0 * FLOG(1.0 - u53(w[0], w[1])));
 #endif
+#if MCU_SEEDS_SCTAB
+    const tab::SinCos sc = tab::tsincos2pi(u53(w[2], w[3]), tsc);
+    return {rad * sc.c, rad * sc.s};
+#else
     const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
     return {rad * sc.b, rad * sc.a};
+#endif
   };
   const size_t C = (size_t)a.n_chains;
   const uint32_t chain = (uint32_t)(a.chain_offset + c);
@@ -673,7 +685,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 
 template <int BS, bool AMM0>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)BS * (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL + (MCU_SEEDS_TAB ? 384 : 0)) * sizeof(double);
+  const size_t smem = ((size_t)BS * (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL + (MCU_SEEDS_TAB ? 384 : 0) + (MCU_SEEDS_SCTAB ? 256 : 0)) * sizeof(double);
   static thread_local int attr_dev = -1;   // the attribute call is slow: once per device
   int dev = 0; cudaGetDevice(&dev);
   if (attr_dev != dev) {
