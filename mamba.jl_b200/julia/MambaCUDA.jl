@@ -321,23 +321,25 @@ function devicediagnostics(hs::Vector{Ptr{Void}}; alpha::Real=0.05, transform::B
   P = Ref{Cint}(0)
   check(hs[1], ccall((:mcu_dims, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), hs[1], C_NULL, P, C_NULL))
   p = Int(P[])
-  r1 = Array{Float64}(11p, length(hs))
+  n1 = Ref{Cint}(0); n2 = Ref{Cint}(0)                             # 11p and 15p + p(p-1) (the pair sums of the multivariate PSRF, p <= 12)
+  ccall((:mcu_diag_sizes, libmambacuda), Cint, (Cint, Ptr{Cint}, Ptr{Cint}), p, n1, n2)
+  r1 = Array{Float64}(n1[], length(hs))
   for (k, h) in enumerate(hs)
-    check(h, ccall((:mcu_diag_round1, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}), h, pointer(r1, 11p * (k - 1) + 1)))
+    check(h, ccall((:mcu_diag_round1, libmambacuda), Cint, (Ptr{Void}, Ptr{Float64}), h, pointer(r1, n1[] * (k - 1) + 1)))
   end
   red1 = vcat(minimum(r1[1:p, :], 2), maximum(r1[p+1:2p, :], 2), sum(r1[2p+1:end, :], 2))[:]
-  r2 = Array{Float64}(15p, length(hs))
+  r2 = Array{Float64}(n2[], length(hs))
   for (k, h) in enumerate(hs)
-    check(h, ccall((:mcu_diag_round2, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{Float64}, Ptr{Float64}), h, transform, red1, pointer(r2, 15p * (k - 1) + 1)))
+    check(h, ccall((:mcu_diag_round2, libmambacuda), Cint, (Ptr{Void}, Cint, Ptr{Float64}, Ptr{Float64}), h, transform, red1, pointer(r2, n2[] * (k - 1) + 1)))
   end
   red2 = sum(r2, 2)[:]
   monlink = Array{Cint}(p); nkept = Ref{Int64}(0)
   check(hs[1], ccall((:mcu_monitor_links, libmambacuda), Cint, (Ptr{Void}, Ptr{Cint}), hs[1], monlink))
   check(hs[1], ccall((:mcu_n_kept, libmambacuda), Cint, (Ptr{Void}, Ptr{Int64}), hs[1], nkept))
-  psrf = Array{Float64}(2, p); summ = Array{Float64}(5, p); codes = Array{Cint}(p)
+  psrf = Array{Float64}(2, p); summ = Array{Float64}(5, p); codes = Array{Cint}(p); mpsrf = Ref{Float64}(NaN)
   rc = ccall((:mcu_diag_finish, libmambacuda), Cint,
-             (Int64, Cint, Float64, Ptr{Cint}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
-             nkept[], p, alpha, monlink, transform, red1, red2, psrf, summ, codes)
+             (Int64, Cint, Float64, Ptr{Cint}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}, Ptr{Float64}),
+             nkept[], p, alpha, monlink, transform, red1, red2, psrf, summ, codes, mpsrf)   # mpsrf: NaN unless the runs streamed co-moments (MCU_RUN_MPSRF)
   rc == 0 || throw(ArgumentError("less than 2 chains supplied to gelman diagnostic"))
   round(psrf', 3), summ'          # gelmandiag rounds to 3 dp (gelmandiag.jl:59); summary columns: Mean, SD, Naive SE, MCSE, ESS
 end

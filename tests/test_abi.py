@@ -118,3 +118,51 @@ def test_block_descriptor_layout_is_the_same_in_all_three_bindings():
     for (n, t), (_, ctype, is_arr) in zip(jfields, fields):
         assert t == ("NTuple{8, Int32}" if is_arr else jt[ctype]), (n, t)
     assert "MCU_MAX_BLOCK_NODES = 8" in jl and re.search(r"#define MCU_MAX_BLOCK_NODES\s+8", h)
+
+
+def _split_top(s):
+    """split on commas that are not inside (), {} or []"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_and_ctypes_bindings_pass_as_many_arguments_as_the_header_declares():
+    """Every ccall of the Julia shim and every argtypes list of the ctypes stub has the arity of the prototype in include/mambacuda.h
+    (a call with a missing trailing pointer would still link and then read garbage)."""
+    import re
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "mambacuda.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|double|int64_t|const char\*)\s+(mcu_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(_split_top(args))
+    assert len(protos) > 50
+    jl = open(os.path.join(ROOT, "mamba.jl_b200", "julia", "MambaCUDA.jl")).read()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(mcu_\w+),\s*libmambacuda\),\s*[\w{}]+,\s*\(", jl):
+        name, i = m.group(1), m.end()
+        depth, j = 1, i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jl[j], 0); j += 1
+        types = _split_top(jl[i:j - 1])
+        assert name in protos, name
+        assert len(types) == protos[name], f"{name}: Julia passes {len(types)} arguments, the header declares {protos[name]}"
+        seen += 1
+    assert seen >= 25
+    sys.path.insert(0, os.path.join(ROOT, "mamba.jl_b200"))
+    from mambacuda import _lib
+    src = open(_lib.__file__).read()
+    for m in re.finditer(r"L\.(mcu_\w+)\.argtypes\s*=\s*\[([^\]]*)\]", src):
+        name, n = m.group(1), len(_split_top(m.group(2)))
+        assert name in protos, name
+        assert n == protos[name], f"{name}: ctypes declares {n} arguments, the header {protos[name]}"
