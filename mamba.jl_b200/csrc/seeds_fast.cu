@@ -698,17 +698,6 @@ int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
-}  // namespace mcu
-
-#ifndef MCU_SEEDS_WS
-#define MCU_SEEDS_WS 1     // AMWG scheme: the warp-specialised kernel (seeds_ws.cuh); MCU_SEEDS_WS=0 in the environment selects seeds_fast_kernel at run time
-#endif
-#if MCU_SEEDS_WS && MCU_SEEDS_TAB
-#include <cstdlib>
-#include "seeds_ws.cuh"
-#endif
-
-namespace mcu {
 
 // h_blocks: host copies of the three DevBlocks (scale pointers are device pointers; the scales are
 // re-read from the host-side scale mirror passed in cfg by the caller).
@@ -763,12 +752,6 @@ int seeds_fast_launch(const double* r, const double* n, const double* x1, const 
     cfg.amm_beta = h_blocks[0].beta; cfg.amm_scale = h_blocks[0].amm_scale;
     return launch_bs<MCU_SEEDS_BS, true>(cfg, a, st);
   }
-#if MCU_SEEDS_WS && MCU_SEEDS_TAB
-  {
-    static const bool ws = [] { const char* e = std::getenv("MCU_SEEDS_WS"); return !(e && e[0] == '0'); }();
-    if (ws) return launch_ws<MCU_SEEDS_WS_CW, MCU_SEEDS_WS_PW>(cfg, a, st);
-  }
-#endif
   return launch_bs<MCU_SEEDS_BS, false>(cfg, a, st);
 }
 
