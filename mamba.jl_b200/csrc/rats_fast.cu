@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
         const double ac0 = adapt ? TUNE(WHICH, 2 + NR + i0) : 0.0, ac1 = adapt ? TUNE(WHICH, 2 + NR + i1) : 0.0;
         const Pair pz = draw_normal_pair(a, chain, it32, block, ip);
         const Pair pu = draw_uniform_pair(a, chain, it32, block, ip);
-        const double lu0 = log_uniform(pu.a), lu1 = log_uniform(pu.b);
+        const LogU lu0 = logu_bracket(pu.a), lu1 = logu_bracket(pu.b);   // float bracket of log u; FP64 log only inside the rounding band (same decisions)
         const double z0 = sg0 * pz.a, z1 = sg1 * pz.b;
         const double a0 = AL(i0), b0 = BE(i0), a1 = AL(i1), b1 = BE(i1);
         double S0 = 0.0, S1 = 0.0;                 // A_i (alpha) or B_i (beta) of the two rats
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
         const double dS0 = z0 * fma(q0, z0, -2.0 * S0), dS1 = z1 * fma(q1, z1, -2.0 * S1);   // change of SEE
         const double d0 = (WHICH == 0 ? a0 : b0) - mu, d1 = (WHICH == 0 ? a1 : b1) - mu;
         const double dl0 = -h_c * dS0 - h_p * z0 * fma(2.0, d0, z0), dl1 = -h_c * dS1 - h_p * z1 * fma(2.0, d1, z1);
-        const bool acc0 = lu0 < dl0, acc1 = lu1 < dl1;   // rand() < exp(logf' - logf0): amwg.jl:107
+        const bool acc0 = logu_less(lu0, dl0), acc1 = logu_less(lu1, dl1);   // rand() < exp(logf' - logf0): amwg.jl:107
         if (acc0) { if (WHICH == 0) AL(i0) = a0 + z0; else BE(i0) = b0 + z0; SEE += dS0; if (adapt) TUNE(WHICH, 2 + NR + i0) = ac0 + 1.0; }
         if (acc1) { if (WHICH == 0) AL(i1) = a1 + z1; else BE(i1) = b1 + z1; SEE += dS1; if (adapt) TUNE(WHICH, 2 + NR + i1) = ac1 + 1.0; }
       }
