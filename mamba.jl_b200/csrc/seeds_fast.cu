@@ -46,39 +46,20 @@
 #define MCU_SEEDS_LOGU 2   // MH test on the log scale: 1 = FP64 log u next to the draw (off the critical path); 2 = float bracket of log u + FP64 log inside the
                            // rounding band only (same decisions; 3-7 % slower than 1 with the fdlibm log in round 1, 3 % faster with the table log)
 #endif
-#ifndef MCU_SEEDS_PIPE
-#define MCU_SEEDS_PIPE 0   // b block: draws of trip t + 1 generated during trip t — measured 10 % SLOWER (profiles/r1_seeds_fast_summary.md), kept for the record
-#endif
 #ifndef MCU_SEEDS_BS
 #define MCU_SEEDS_BS 96
 #endif
 #ifndef MCU_SEEDS_MINB
 #define MCU_SEEDS_MINB 3
 #endif
-
-#ifndef MCU_SEEDS_GLN
-#define MCU_SEEDS_GLN 0    // 1: the proposed L[i] of an alpha proposal live in an (L2-resident) global scratch array instead of shared memory
-#endif
-#ifndef MCU_SEEDS_GB
-#define MCU_SEEDS_GB 0     // 1: b[i] is updated in place in the (L2-resident) state array instead of a shared-memory copy
-#endif
-
+// Switches that were measured and removed again (profiles/r2_seeds_fast_summary.md has the numbers; the code is in the history at commit e00a803 / 12620f6):
+// proposal scratch and b in L2 for 14-16 resident warps, draws of the next b trip generated during the current one, all draws of the alpha / s2 blocks up
+// front, out-of-line draw functions, table-driven sincos, two threads per chain, producer / consumer warp specialisation.
 #ifndef MCU_SEEDS_DEDUP
 #define MCU_SEEDS_DEDUP 0   // 1: a single loop over the b trips (one copy of the trip body): measured 12 % SLOWER (every trip then carries the dynamic last-plate guards)
 #endif
-#ifndef MCU_SEEDS_SCTAB
-#define MCU_SEEDS_SCTAB 0   // 1: Box-Muller angle through the table-driven sincos (fasttab_fn.cuh): measured 1 % slower than the polynomial form (143.3 vs 142.0 ms)
-#endif
 #ifndef MCU_SEEDS_FSQRT
 #define MCU_SEEDS_FSQRT 1   // Box-Muller radius through the branch-free fast_sqrt (fastfn.cuh)
-#endif
-#ifndef MCU_SEEDS_UPFRONT
-#define MCU_SEEDS_UPFRONT 0   // every draw of the alpha and s2 blocks (counter-based: no state needed) and exp(z_j) are formed at the top of the
-                              // iteration, six independent Philox / Box-Muller / log / exp chains side by side, instead of pair by pair
-                              // inside the rolled component loop
-#endif
-#ifndef MCU_SEEDS_CALLS
-#define MCU_SEEDS_CALLS 0   // 1: the paired draws (Philox + Box-Muller, Philox + two logs) are out-of-line functions: one copy each in the instruction stream
 #endif
 #ifndef MCU_SEEDS_AW
 #define MCU_SEEDS_AW 3      // plates per trip of an alpha proposal (the plate lists are padded with the dummy slot to a multiple of it)
@@ -117,7 +98,6 @@ struct FastCfg {
   double scale_a[4], scale_b[NPL], scale_s;
   // block 0 = AMM(alpha0..alpha12) (doc/examples/seeds.jl:69): lower Cholesky factor of the initial Sigma (column-major), beta, scale
   double amm_SL[16], amm_beta, amm_scale;
-  double* gln;                        // MCU_SEEDS_GLN: [NSL][n_chains] scratch
 };
 
 #if !MCU_SEEDS_LOGU   // the u < exp(delta) form of the MH test (MCU_SEEDS_LOGU = 0)
@@ -149,27 +129,6 @@ MCU_D double pick(const Bases& g, unsigned grp) {   // warp-uniform select, keep
   return (grp & 2u) ? hi : lo;
 }
 
-#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
-template <int BS>
-static __device__ __noinline__ Pair seeds_normal_pair_nc(unsigned long long seed, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) {
-  extern __shared__ double smem[];
-  const double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;
-  uint32_t w[4];
-  philox4x32_10(kpair, itn, ch, blk | (1u << 24), (uint32_t)seed, (uint32_t)(seed >> 32), w);
-  const double rad = sqrt(-2.0 * tab::tlog(1.0 - u53(w[0], w[1]), tlg));
-  const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
-  return {rad * sc.b, rad * sc.a};
-}
-template <int BS>
-static __device__ __noinline__ Pair seeds_logu_pair_nc(unsigned long long seed, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) {
-  extern __shared__ double smem[];
-  const double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;
-  uint32_t w[4];
-  philox4x32_10(kpair, itn, ch, blk, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-  const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
-  return {ua > 0.0 ? tab::tlog(ua, tlg) : -CUDART_INF, ub > 0.0 ? tab::tlog(ub, tlg) : -CUDART_INF};
-}
-#endif
 
 // AMM0: block 0 is AMM(alpha0, alpha1, alpha2, alpha12) (the reference's scheme, doc/examples/seeds.jl:69-71) instead of AMWG
 template <int BS, bool AMM0>
@@ -177,23 +136,15 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   extern __shared__ double smem[];
   double* se = smem;                        // e[i] = exp(eta_i)
   double* sll = smem + NSL * BS;            // L[i] = log(1 + e[i])
-#if !MCU_SEEDS_GB
   double* sb = smem + 2 * NSL * BS;         // b[i]
-#endif
-#if !MCU_SEEDS_GLN
-  double* sln = smem + (3 - MCU_SEEDS_GB) * NSL * BS;   // proposed L[i]
-#endif
+  double* sln = smem + 3 * NSL * BS;   // proposed L[i]
   const int tid = threadIdx.x;
   const long long c = (long long)blockIdx.x * BS + tid;
 #if MCU_SEEDS_TAB
-  double* tlg = smem + (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL * BS;   // 128 x (invc, logc), 16-byte aligned
+  double* tlg = smem + 4 * NSL * BS;   // 128 x (invc, logc), 16-byte aligned
   double* tex = tlg + 256;                                              // 128 x 2^(j/128)
   for (int i = tid; i < 256; i += BS) tlg[i] = kLogTabG[i];
   for (int i = tid; i < 128; i += BS) tex[i] = kExpTabG[i];
-#if MCU_SEEDS_SCTAB
-  double* tsc = tex + 128;                                              // 128 x (sin, cos)(2 pi j / 128), 16-byte aligned
-  for (int i = tid; i < 256; i += BS) tsc[i] = kSinCosTabG[i];
-#endif
   __syncthreads();
 #define FLOG(x) tab::tlog((x), tlg)
 #define FEXP(x) tab::texp((x), tex)
@@ -209,17 +160,10 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   // the draws of fastmath.cuh with the kernel's own log (same Philox blocks, same arithmetic otherwise)
   auto log_uniform = [&](double u) { return u > 0.0 ? FLOG(u) : -CUDART_INF; };
   auto draw_logu_pair = [&](uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) -> Pair {   // logs of both uniforms of a Philox block
-#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
-    return seeds_logu_pair_nc<BS>(a.seed, ch, itn, blk, kpair);
-#else
     const Pair pu = draw_uniform_pair(a, ch, itn, blk, kpair);
     return {log_uniform(pu.a), log_uniform(pu.b)};
-#endif
   };
   auto draw_normal_pair = [&](const RunArgs& aa, uint32_t ch, uint32_t itn, uint32_t blk, uint32_t kpair) -> Pair {
-#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
-    return seeds_normal_pair_nc<BS>(aa.seed, ch, itn, blk, kpair);
-#endif
     uint32_t w[4];
     philox4x32_10(kpair, itn, ch, blk | (1u << 24), (uint32_t)aa.seed, (uint32_t)(aa.seed >> 32), w);
 #if MCU_SEEDS_FSQRT
@@ -227,28 +171,15 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #else
     const double rad = sqrt(-2.0 * FLOG(1.0 - u53(w[0], w[1])));
 #endif
-#if MCU_SEEDS_SCTAB
-    const tab::SinCos sc = tab::tsincos2pi(u53(w[2], w[3]), tsc);
-    return {rad * sc.c, rad * sc.s};
-#else
     const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
     return {rad * sc.b, rad * sc.a};
-#endif
   };
   const size_t C = (size_t)a.n_chains;
   const uint32_t chain = (uint32_t)(a.chain_offset + c);
-#if MCU_SEEDS_GB
-#define SB(i) a.state[(size_t)(5 + (i)) * C + c]
-#else
 #define SB(i) sb[(i) * BS + tid]
-#endif
 #define SE(i) se[(i) * BS + tid]
 #define SLL(i) sll[(i) * BS + tid]
-#if MCU_SEEDS_GLN
-#define SLN(i) cfg.gln[(size_t)(i) * C + c]
-#else
 #define SLN(i) sln[(i) * BS + tid]
-#endif
 #define SSG(i) TUNE(1, 2 + (i))
 #define SAC(i) TUNE(1, 2 + NPL + (i))
 #define TUNE(blk, slot) a.tune[(size_t)(cfg.tune_off[blk] + (slot)) * C + c]
@@ -257,9 +188,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   double al0 = a.state[0 * C + c], al1 = a.state[1 * C + c], al2 = a.state[2 * C + c], al3 = a.state[3 * C + c];
   double s2 = a.state[4 * C + c];
   double x = log(s2);
-#if !MCU_SEEDS_GB
   for (int i = 0; i < NPL; ++i) SB(i) = a.state[(size_t)(5 + i) * C + c];
-#endif
   // tune: block 0 [m, adapt, sigma[4], accept[4]]; block 1 [m, adapt, sigma[21], accept[21]]; block 2 [m, adapt, sigma, accept]
   // AMM tune record of block 0 (samplers.cuh): [adapt, m, Mv[4], Mvv[16], SigmaLm[16]] — it stays in the L2-resident tune array
   double m0 = AMM0 ? 0.0 : TUNE(0, 0), m1 = TUNE(1, 0), m2 = TUNE(2, 0);
@@ -270,9 +199,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 
   Bases g = group_bases(al0, al1, al2, al3);
   for (int i = 0; i < NPL; ++i) { const double e = FEXP(pick(g, cfg.grp[i]) + SB(i)); SE(i) = e; SLL(i) = FLOG(1.0 + e); }
-#if !MCU_SEEDS_GB
   SB(NPL) = 0.0;
-#endif
   SE(NPL) = 0.0; SLL(NPL) = 0.0; SLN(NPL) = 0.0;   // dummy slot: log(1 + 0 * E) = 0, n = 0
 
   double mon[SeedsModel::P];
@@ -287,15 +214,6 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       sgs = cfg.scale_s; acs = 0;
       if (AMM0) for (int i = 0; i < 38; ++i) TUNE(0, i) = 0.0;   // AMMTune(x, Sigma): amm.jl:14-24
     }
-#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
-    // Block 2's proposal needs only x = log s2 and its sigma, which no other block changes: it is formed here so that its Philox / Box-Muller /
-    // log / exp chains run beside those of block 0; only sum b_i^2 and the test wait for block 1.
-    const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
-    const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
-    const double s2n = (xn > -700.0 && xn < 700.0) ? FEXP(xn) : exp(xn);
-    const double dx = xn - x;
-    const double dinv = 1.0 / s2n - 1.0 / s2;
-#endif
     // ================================================================== block 0, AMM form (amm.jl:66-108; device generic form: samplers.cuh amm_sample)
     if (AMM0) {
       const bool adapt = cfg.adapt[0] == 1 ? iter <= a.burnin : cfg.adapt[0] == 0;
@@ -379,24 +297,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       ad0 = adapt;
       if (adapt) m0 += 1.0;
       // components are rotated through slot 0 so the loop stays rolled with everything in registers
-#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
-      // slot s holds (z, exp z, log u) of component (j + s) % 4, rotated with the alphas
-      double z0, z1, z2, z3, E0, E1, E2, E3, lu0, lu1, lu2, lu3;
-      {
-        const Pair n01 = draw_normal_pair(a, chain, it32, 0, 0), n23 = draw_normal_pair(a, chain, it32, 0, 1);
-        const Pair u01 = draw_logu_pair(chain, it32, 0, 0), u23 = draw_logu_pair(chain, it32, 0, 1);
-        z0 = sg0 * n01.a; z1 = sg1 * n01.b; z2 = sg2 * n23.a; z3 = sg3 * n23.b;   // z = sigma .* randn(n)
-        E0 = FEXP(z0); E1 = FEXP(z1); E2 = FEXP(z2); E3 = FEXP(z3);
-        lu0 = u01.a; lu1 = u01.b; lu2 = u23.a; lu3 = u23.b;
-      }
-#else
       double zc = 0.0, uc = 0.0;   // second draw of the current Philox pair
-#endif
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
-        const double z = z0, lu = lu0;
-#else
         double zn01;
         if ((j & 1) == 0) { const Pair pr = draw_normal_pair(a, chain, it32, 0, j >> 1); zn01 = pr.a; zc = pr.b; } else zn01 = zc;
 #if MCU_SEEDS_LOGU == 2
@@ -407,7 +310,6 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         if ((j & 1) == 0) { const Pair pr = draw_logu_pair(chain, it32, 0, j >> 1); lu = pr.a; uc = pr.b; } else lu = uc;
 #endif
         const double z = sg0 * zn01;                                      // z = sigma .* randn(n): normal j of the block
-#endif
         const double anew = al0 + z;
         const unsigned pm = cfg.amask[j];
         // proposed group bases, again in the reference's summation order (slot s holds alpha_{(j+s)%4})
@@ -417,11 +319,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         const double q3 = j == 0 ? al3 : (j == 1 ? al2 : (j == 2 ? al1 : anew));
         const Bases gn = group_bases(q0, q1, q2, q3);
         // every affected plate moves by the same step: e_i' = e_i exp(z); ll_i' - ll_i = r_i z - n_i (L_i' - L_i)
-#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
-        const double E = E0;
-#else
         const double E = FEXP(z);
-#endif
         // AW plates per trip: their logs are independent, so the scheduler fills one chain's DFMA latency with the others
         constexpr int AW = MCU_SEEDS_AW;
         double dL[AW];
@@ -463,11 +361,6 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         { const double t = al0; al0 = al1; al1 = al2; al2 = al3; al3 = t; }
         { const double t = sg0; sg0 = sg1; sg1 = sg2; sg2 = sg3; sg3 = t; }
         { const int t = ac0; ac0 = ac1; ac1 = ac2; ac2 = ac3; ac3 = t; }
-#if MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1
-        { const double t = z0; z0 = z1; z1 = z2; z2 = z3; z3 = t; }
-        { const double t = E0; E0 = E1; E1 = E2; E2 = E3; E3 = t; }
-        { const double t = lu0; lu0 = lu1; lu1 = lu2; lu2 = lu3; lu3 = t; }
-#endif
       }
       if (adapt && ((long long)m0 % cfg.batchsize[0]) == 0) {
         const double dl = amwg_delta(m0, cfg.batchsize[0]);
@@ -516,11 +409,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
           sg[w] = real ? SSG(ix[w]) : 0.0;                                 // global (L2) loads at the top of the trip
           ac[w] = (real && adapt) ? SAC(ix[w]) : 0.0;
 #endif
-#if MCU_SEEDS_GB
-          bi[w] = real ? SB(ix[w]) : 0.0;
-#else
           bi[w] = SB(ix[w]);
-#endif
         }
 #if MCU_SEEDS_PF
         b_fetch(i0 + W);
@@ -561,37 +450,6 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         for (int w = 0; w < W; ++w)
           if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) SAC(ix[w]) = ac[w] + 1.0; }
       };
-#if MCU_SEEDS_PIPE && MCU_SEEDS_LOGU == 1
-      // Software-pipelined form (two plates per trip): the normals and log-uniforms of trip t + 1 depend on nothing but the counters, so
-      // they are generated DURING trip t — four independent dependency chains (two updates, Philox + Box-Muller, Philox + two logs) for
-      // the scheduler to interleave, and the exp -> log -> compare chain of a trip no longer waits for its own draws.
-      {
-        Pair pz = draw_normal_pair(a, chain, it32, 1, 0);
-        Pair lu; { const Pair pu = draw_uniform_pair(a, chain, it32, 1, 0); lu.a = log_uniform(pu.a); lu.b = log_uniform(pu.b); }
-#pragma unroll 1
-        for (int ip = 0; ip < (NPL + 1) / 2; ++ip) {
-          const int i0 = 2 * ip;
-          const bool two = i0 + 1 < NPL;
-          const int i1 = two ? i0 + 1 : NPL, r1 = two ? i0 + 1 : i0;           // odd plate count: the last trip pairs with the dummy slot
-          const double sga = SSG(i0), sgb = two ? SSG(i1) : 0.0;               // global (L2) loads, issued a whole trip ahead of their use
-          const double aca = adapt ? SAC(i0) : 0.0, acb = (adapt && two) ? SAC(i1) : 0.0;
-          const double bia = SB(i0), bib = SB(i1);
-          const double za = pz.a, zb = pz.b, lua = lu.a, lub = lu.b;
-          // draws of the next trip (one trip past the end is harmless: nothing consumes it)
-          pz = draw_normal_pair(a, chain, it32, 1, ip + 1);
-          { const Pair pu = draw_uniform_pair(a, chain, it32, 1, ip + 1); lu.a = log_uniform(pu.a); lu.b = log_uniform(pu.b); }
-          const double bna = bia + sga * za, bnb = bib + sgb * zb;
-          const double ena = FEXP(pick(g, cfg.grp[i0]) + bna);             // fresh e_i: also resets the drift of the alpha updates
-          const double enb = FEXP(pick(g, cfg.grp[r1]) + bnb);
-          const double lna = FLOG(1.0 + ena), lnb = FLOG(1.0 + enb);
-          const double da = fma(cfg.r[i0], bna - bia, -cfg.n[i0] * (lna - SLL(i0))) - half_inv_s2 * fma(bna, bna, -bia * bia);
-          const double db = fma(cfg.r[r1], bnb - bib, -cfg.n[i1] * (lnb - SLL(i1))) - half_inv_s2 * fma(bnb, bnb, -bib * bib);
-          const bool acca = lua < da, accb = two && lub < db;
-          if (acca) { SB(i0) = bna; SE(i0) = ena; SLL(i0) = lna; if (adapt) SAC(i0) = aca + 1.0; }
-          if (accb) { SB(i1) = bnb; SE(i1) = enb; SLL(i1) = lnb; if (adapt) SAC(i1) = acb + 1.0; }
-        }
-      }
-#else
       {
         constexpr int W = MCU_SEEDS_BW;
         int i0 = 0;
@@ -602,7 +460,6 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #pragma unroll 1
         for (; i0 < NPL; i0 += 2) b_trip(std::integral_constant<int, 2>{}, i0);
       }
-#endif
       if (adapt && ((long long)m1 % cfg.batchsize[1]) == 0) {
         const double dl = amwg_delta(m1, cfg.batchsize[1]);
         const double up = exp(dl), dn = exp(-dl);
@@ -617,21 +474,15 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
       if (adapt) m2 += 1.0;
       double S = 0.0;
       for (int i = 0; i < NPL; ++i) { const double bi = SB(i); S += bi * bi; }
-#if !(MCU_SEEDS_UPFRONT && MCU_SEEDS_LOGU == 1)
 #if MCU_SEEDS_LOGU == 2
       const LogU lus = logu_bracket(draw_uniform_pair(a, chain, it32, 2, 0).a);
 #elif MCU_SEEDS_LOGU
-#if MCU_SEEDS_CALLS && MCU_SEEDS_TAB
-      const double lus = draw_logu_pair(chain, it32, 2, 0).a;
-#else
       const double lus = log_uniform(draw_uniform_pair(a, chain, it32, 2, 0).a);
-#endif
 #endif
       const double xn = x + sgs * draw_normal_pair(a, chain, it32, 2, 0).a;
       const double s2n = (xn > -700.0 && xn < 700.0) ? FEXP(xn) : exp(xn);
       const double dx = xn - x;
       const double dinv = 1.0 / s2n - 1.0 / s2;
-#endif
       // logf(x) = InverseGamma(0.001, 0.001)(s2) + x [log-Jacobian, transformdistribution.jl:75-78]
       //           + sum_i Normal(b_i; 0, sqrt(s2))
       const double delta = -(0.001 + 1.0) * dx - 0.001 * dinv + dx - 0.5 * S * dinv - (double)NPL * 0.5 * dx;
@@ -662,9 +513,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
   // ---- store chain state ------------------------------------------------------------------------
   a.state[0 * C + c] = al0; a.state[1 * C + c] = al1; a.state[2 * C + c] = al2; a.state[3 * C + c] = al3;
   a.state[4 * C + c] = s2;
-#if !MCU_SEEDS_GB
   for (int i = 0; i < NPL; ++i) a.state[(size_t)(5 + i) * C + c] = SB(i);
-#endif
   if (!AMM0) {
     TUNE(0, 0) = m0; TUNE(0, 1) = ad0 ? 1.0 : 0.0;
     TUNE(0, 2) = sg0; TUNE(0, 3) = sg1; TUNE(0, 4) = sg2; TUNE(0, 5) = sg3;
@@ -685,7 +534,7 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 
 template <int BS, bool AMM0>
 int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)BS * (4 - MCU_SEEDS_GLN - MCU_SEEDS_GB) * NSL + (MCU_SEEDS_TAB ? 384 : 0) + (MCU_SEEDS_SCTAB ? 256 : 0)) * sizeof(double);
+  const size_t smem = ((size_t)BS * 4 * NSL + (MCU_SEEDS_TAB ? 384 : 0)) * sizeof(double);
   static thread_local int attr_dev = -1;   // the attribute call is slow: once per device
   int dev = 0; cudaGetDevice(&dev);
   if (attr_dev != dev) {
@@ -704,15 +553,6 @@ int launch_bs(const FastCfg& cfg, const RunArgs& a, cudaStream_t st) {
 int seeds_fast_launch(const double* r, const double* n, const double* x1, const double* x2, const RunArgs& a, const DevBlock* h_blocks,
                       const std::vector<std::vector<double>>& h_scales, const double* h_SigmaL, cudaStream_t st) {
   FastCfg cfg;
-  cfg.gln = nullptr;
-#if MCU_SEEDS_GLN
-  {   // experiment: scratch kept per process (one device)
-    static double* buf = nullptr; static size_t cap = 0;
-    const size_t need = (size_t)NSL * (size_t)a.n_chains;
-    if (need > cap) { if (buf) cudaFree(buf); if (cudaMalloc(&buf, need * sizeof(double)) != cudaSuccess) return -1; cap = need; }
-    cfg.gln = buf;
-  }
-#endif
   // plate constants, scales and (AMM) the Cholesky factor come from the handle's host-side copies of what the generic path uses
   const bool amm0 = h_blocks[0].kind == 6;   // MCU_AMM
   double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[NPL], ss[1];
