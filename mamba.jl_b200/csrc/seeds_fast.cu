@@ -382,16 +382,18 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
 #if MCU_SEEDS_PF
       // The tune array is L2-resident (L1 is all shared memory here): ~700 cycles per load.  With the table-driven log / exp a trip is too
       // short to hide that behind its own draws, so the loads run one trip ahead.
+      // Addresses: one running pointer per chain (plates are C doubles apart, the accept counters NPL plates after the sigmas) instead of a
+      // 64-bit index computation per load.  The fetch for the trip after the last one reads up to three slots past sigma_b / accept of this
+      // block: they are the accept slots of plates 0..2 and the four slots of block 2's record (seeds_fast_launch checks the layout), never used.
+      static_assert(MCU_SEEDS_BW == 2, "the look-ahead fetch stays inside block 2's four tune slots only for two plates per trip");
+      double* tq = &TUNE(1, 2);
+      const size_t acoff = (size_t)NPL * C;
       double psg[MCU_SEEDS_BW], pac[MCU_SEEDS_BW];
-      auto b_fetch = [&](int i0) {
+      auto b_fetch = [&](const double* q) {
 #pragma unroll
-        for (int w = 0; w < MCU_SEEDS_BW; ++w) {
-          const bool real = i0 + w < NPL;
-          psg[w] = real ? SSG(i0 + w) : 0.0;
-          pac[w] = (real && adapt) ? SAC(i0 + w) : 0.0;
-        }
+        for (int w = 0; w < MCU_SEEDS_BW; ++w) { psg[w] = q[(size_t)w * C]; pac[w] = q[acoff + (size_t)w * C]; }
       };
-      b_fetch(0);
+      b_fetch(tq);
 #endif
       auto b_trip = [&](auto Wc, int i0) {
         constexpr int W = decltype(Wc)::value;
@@ -412,7 +414,9 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
           bi[w] = SB(ix[w]);
         }
 #if MCU_SEEDS_PF
-        b_fetch(i0 + W);
+        double* const tc = tq;                                             // this trip's plates
+        tq += (size_t)W * C;
+        b_fetch(tq);
 #endif
 #pragma unroll
         for (int w = 0; w < W; w += 2) {
@@ -448,7 +452,11 @@ __global__ void __launch_bounds__(BS, MCU_SEEDS_MINB) seeds_fast_kernel(const __
         }
 #pragma unroll
         for (int w = 0; w < W; ++w)
+#if MCU_SEEDS_PF
+          if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) tc[acoff + (size_t)w * C] = ac[w] + 1.0; }
+#else
           if (acc[w]) { SB(ix[w]) = bn[w]; SE(ix[w]) = en[w]; SLL(ix[w]) = ln[w]; if (adapt) SAC(ix[w]) = ac[w] + 1.0; }
+#endif
       };
       {
         constexpr int W = MCU_SEEDS_BW;
@@ -581,6 +589,7 @@ int seeds_fast_launch(const double* r, const double* n, const double* x1, const 
   }
   cfg.gmask[0] = 0xFu; cfg.gmask[1] = 0xCu; cfg.gmask[2] = 0xAu; cfg.gmask[3] = 0x8u;
   cfg.scale_s = ss[0];
+  if (h_blocks[2].tune_off != h_blocks[1].tune_off + 2 + 2 * NPL) return -2;   // block 2's record must follow block 1's (the b-block prefetch reads into it): else the generic kernel
   for (int b = 0; b < 3; ++b) {
     cfg.adapt[b] = h_blocks[b].adapt; cfg.batchsize[b] = h_blocks[b].batchsize; cfg.tune_off[b] = h_blocks[b].tune_off;
     cfg.target[b] = h_blocks[b].target;
