@@ -116,11 +116,13 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
       ad = adapt;
       if (adapt) m += 1.0;
       const double h_c = 0.5 / s2c, h_p = 0.5 / s2;
+      double* tq = &TUNE(WHICH, 2);                 // sigma of component 0 of this chain: components are C doubles apart, the accept counters NR further
+      const size_t acoff = (size_t)NR * C;
 #pragma unroll 1
-      for (int ip = 0; ip < NR / 2; ++ip) {       // two components per trip: the two draws of Philox block ip of each stream
+      for (int ip = 0; ip < NR / 2; ++ip, tq += 2 * C) {   // two components per trip: the two draws of Philox block ip of each stream
         const int i0 = 2 * ip, i1 = i0 + 1;
-        const double sg0 = TUNE(WHICH, 2 + i0), sg1 = TUNE(WHICH, 2 + i1);   // L2 loads, consumed after the draws
-        const double ac0 = adapt ? TUNE(WHICH, 2 + NR + i0) : 0.0, ac1 = adapt ? TUNE(WHICH, 2 + NR + i1) : 0.0;
+        const double sg0 = tq[0], sg1 = tq[C];             // L2 loads through a running pointer, consumed after the draws
+        const double ac0 = tq[acoff], ac1 = tq[acoff + C];
         const Pair pz = draw_normal_pair(a, chain, it32, block, ip);
         const Pair pu = draw_uniform_pair(a, chain, it32, block, ip);
         const LogU lu0 = logu_bracket(pu.a), lu1 = logu_bracket(pu.b);   // float bracket of log u; FP64 log only inside the rounding band (same decisions)
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
         const double d0 = (WHICH == 0 ? a0 : b0) - mu, d1 = (WHICH == 0 ? a1 : b1) - mu;
         const double dl0 = -h_c * dS0 - h_p * z0 * fma(2.0, d0, z0), dl1 = -h_c * dS1 - h_p * z1 * fma(2.0, d1, z1);
         const bool acc0 = logu_less(lu0, dl0), acc1 = logu_less(lu1, dl1);   // rand() < exp(logf' - logf0): amwg.jl:107
-        if (acc0) { if (WHICH == 0) AL(i0) = a0 + z0; else BE(i0) = b0 + z0; SEE += dS0; if (adapt) TUNE(WHICH, 2 + NR + i0) = ac0 + 1.0; }
-        if (acc1) { if (WHICH == 0) AL(i1) = a1 + z1; else BE(i1) = b1 + z1; SEE += dS1; if (adapt) TUNE(WHICH, 2 + NR + i1) = ac1 + 1.0; }
+        if (acc0) { if (WHICH == 0) AL(i0) = a0 + z0; else BE(i0) = b0 + z0; SEE += dS0; if (adapt) tq[acoff] = ac0 + 1.0; }
+        if (acc1) { if (WHICH == 0) AL(i1) = a1 + z1; else BE(i1) = b1 + z1; SEE += dS1; if (adapt) tq[acoff + C] = ac1 + 1.0; }
       }
       if (adapt && ((long long)m % cfg.batchsize[WHICH]) == 0) {   // amwg.jl:74-80
         const double dl = amwg_delta(m, cfg.batchsize[WHICH]);
