@@ -154,8 +154,90 @@ struct PumpsGibbsCfg {
   int adapt, batchsize, tune_off;
 };
 
+#ifndef MCU_PUMPSG_PRETEST
+#define MCU_PUMPSG_PRETEST 1
+#endif
+// ---- register-resident block streams for the Gibbs kernel -------------------------------------------------------------------
+// rng.cuh's Draws keeps its cursors and the cached second draw behind `this` of two noinline members, i.e. in local memory: in this
+// kernel that was 115 LDL + 80 STL per chain-iteration and the second-largest stall (long_scoreboard 3.1 per issue, profiles/
+// r2_pumps_gibbs_note.md).  Here the state is a plain struct the compiler keeps in registers; the pair generators stay out of line
+// (one copy in the instruction stream: this kernel's top stall is instruction fetch) and take / return everything by value.
+// Same draws, same arithmetic as Draws::uniform / Draws::normal (PHILOX mode; the fused kernels never run on an EXTERNAL stream).
+static __device__ __noinline__ Pair pg_normal_pair(uint32_t k0, uint32_t k1, uint32_t chain, uint32_t iter, uint32_t blockkind, uint32_t kpair) {
+  uint32_t w[4];
+  philox4x32_10(kpair, iter, chain, blockkind | (1u << 24), k0, k1, w);
+  const double rad = sqrt(-2.0 * fast_log(1.0 - u53(w[0], w[1])));
+  const Pair sc = fast_sincos2pi(u53(w[2], w[3]));
+  return {rad * sc.b, rad * sc.a};   // (even draw of the stream: cosine branch, odd draw: sine branch)
+}
+static __device__ __noinline__ Pair pg_uniform_pair(uint32_t k0, uint32_t k1, uint32_t chain, uint32_t iter, uint32_t blockkind, uint32_t kpair) {
+  uint32_t w[4];
+  philox4x32_10(kpair, iter, chain, blockkind, k0, k1, w);
+  return {u53(w[0], w[1]), u53(w[2], w[3])};
+}
+struct RegDraws {
+  uint32_t k0, k1, chain, iter, blockkind, ku, kn, z_blk, u_blk;
+  double z_next, u_next;
+  MCU_D void seek(uint32_t it, uint32_t block, uint32_t kind) {
+    iter = it; blockkind = block | (kind << 16); ku = 0; kn = 0; z_blk = 0xffffffffu; u_blk = 0xffffffffu;
+  }
+  MCU_D double uniform() {
+    if ((ku & 1u) && u_blk == (ku >> 1)) { ++ku; return u_next; }
+    const Pair p = pg_uniform_pair(k0, k1, chain, iter, blockkind, ku >> 1);
+    u_next = p.b; u_blk = ku >> 1;
+    const double u = (ku & 1u) ? p.b : p.a;
+    ++ku;
+    return u;
+  }
+  MCU_D double normal() {
+    if ((kn & 1u) && z_blk == (kn >> 1)) { ++kn; return z_next; }
+    const Pair p = pg_normal_pair(k0, k1, chain, iter, blockkind, kn >> 1);
+    z_next = p.b; z_blk = kn >> 1;
+    const double z = (kn & 1u) ? p.b : p.a;
+    ++kn;
+    return z;
+  }
+};
+
+// Marsaglia-Tsang acceptance: u < 1 - 0.0331 x^4 (squeeze), else log u < x^2 / 2 + d (1 - v + log v).  The second test needs two FP64 logs
+// and, although only ~8 % of the lanes reach it, a warp almost always has such a lane: it was 16 % of the kernel's instructions.  It is
+// decided on float logs (MUFU.LG2) whenever the two sides differ by more than a band 30x the float error, and in FP64 otherwise — the
+// decisions are those of the FP64 test (samplers.cuh rgamma_mt), so the draws stay the generic kernel's bit for bit.
+MCU_D bool mt_accept(double u, double x2, double d, double v) {
+  if (u < 1.0 - 0.0331 * x2 * x2) return true;
+#if MCU_PUMPSG_PRETEST
+  if (v > 1e-30) {
+    const float lu = __log2f((float)u) * 0.693147181f, lv = __log2f((float)v) * 0.693147181f;
+    const double rhs = 0.5 * x2 + d * ((1.0 - v) + (double)lv);
+    const double band = 1e-5 * (1.0 + fabs((double)lu) + d * (1.0 + fabs((double)lv)));
+    const double diff = (double)lu - rhs;
+    if (diff < -band) return true;
+    if (diff > band) return false;
+  }
+#endif
+  return flog(u) < 0.5 * x2 + d * (1.0 - v + flog(v));
+}
+// samplers.cuh rgamma_mt on a register-resident stream
+template <class R>
+MCU_D double rgamma_mt_reg(double a, R& rng) {
+  double boost = 1.0;
+  if (a < 1.0) { boost = pow(rng.uniform(), 1.0 / a); a += 1.0; }
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    double x, v;
+    do { x = rng.normal(); v = 1.0 + c * x; } while (v <= 0.0);
+    v = v * v * v;
+    const double u = rng.uniform();
+    if (mt_accept(u, x * x, d, v)) return boost * d * v;
+  }
+}
+
+#ifndef MCU_PUMPSG_REGDRAWS
+#define MCU_PUMPSG_REGDRAWS 1
+#endif
 #ifndef MCU_PUMPSG_MINB
-#define MCU_PUMPSG_MINB 12   // resident blocks per SM (measured 4 / 6 / 8 / 10 / 12 / 14 / 16: 2.6 / 2.9 / 3.0 / 3.1 / 3.4 / 3.3 / 3.3e9 chain-iterations/s at 1e7 chains)
+#define MCU_PUMPSG_MINB 10   // resident blocks per SM.  Round 1 (draw state in local memory): 4 / 6 / 8 / 10 / 12 / 14 / 16 gave 2.6 / 2.9 / 3.0 / 3.1 / 3.4 / 3.3 / 3.3e9 chain-iterations/s
+                             // at 1e7 chains; round 2 (register-resident draws + float pre-test, 1e6 chains): 6 / 8 / 10 / 12 give 4.41 / 4.40 / 4.64 / 4.58e9
 #endif
 template <int BS>
 __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const __grid_constant__ PumpsGibbsCfg cfg, const __grid_constant__ RunArgs a) {
@@ -175,9 +257,14 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
   double m = tn[0 * C], sigma = tn[2 * C], acc = tn[3 * C];
   bool was = tn[1 * C] != 0.0;
   double lg_al = lgamma(al);
+#if MCU_PUMPSG_REGDRAWS
+  RegDraws rng;
+  rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
+#else
   Draws rng;
   rng.k0 = (uint32_t)a.seed; rng.k1 = (uint32_t)(a.seed >> 32); rng.chain = (uint32_t)(a.chain_offset + c);
   rng.ext = nullptr; rng.ext_n = 0; rng.ext_pos = nullptr;
+#endif
 
   for (long long it = 1; it <= a.iters; ++it) {
     const long long iter = a.iter0 + it;
@@ -206,7 +293,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
           v = v * v * v;
           const double u = rng.uniform();
           const double x2 = xn * xn;
-          if (u < 1.0 - 0.0331 * x2 * x2 || flog(u) < 0.5 * x2 + d * (1.0 - v + flog(v))) {
+          if (mt_accept(u, x2, d, v)) {
             TH(i) = boost * d * v / (be + st[i]);
             ++i; setup = true;
           }
@@ -217,7 +304,11 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
     rng.seek(it32, 1, 0);
     double sth = 0.0, SL = 0.0;
     for (int i = 0; i < NP; ++i) { const double th = TH(i); sth += th; SL += fast_log(th); }
+#if MCU_PUMPSG_REGDRAWS
+    be = rgamma_mt_reg(0.1 + (double)NP * al, rng) / (1.0 + sth);
+#else
     be = rgamma_mt(0.1 + (double)NP * al, rng) / (1.0 + sth);
+#endif
     // ---- block 2: AMWG(alpha) on x = log alpha
     rng.seek(it32, 2, 0);
     const bool adapt = cfg.adapt == 1 ? iter <= a.burnin : cfg.adapt == 0;
