@@ -202,7 +202,7 @@ struct RegDraws {
 // Marsaglia-Tsang acceptance: u < 1 - 0.0331 x^4 (squeeze), else log u < x^2 / 2 + d (1 - v + log v).  The second test needs two FP64 logs
 // and, although only ~8 % of the lanes reach it, a warp almost always has such a lane: it was 16 % of the kernel's instructions.  It is
 // decided on float logs (MUFU.LG2) whenever the two sides differ by more than a band 30x the float error, and in FP64 otherwise — the
-// decisions are those of the FP64 test (samplers.cuh rgamma_mt), so the draws stay the generic kernel's bit for bit.
+// decisions are those of the FP64 test (samplers.cuh rgamma_mt).
 MCU_D bool mt_accept(double u, double x2, double d, double v) {
   if (u < 1.0 - 0.0331 * x2 * x2) return true;
 #if MCU_PUMPSG_PRETEST
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
           double sh = al + sy[i];
           boost = 1.0;
           if (sh < 1.0) { boost = pow(rng.uniform(), 1.0 / sh); sh += 1.0; }
-          d = sh - 1.0 / 3.0; cc = 1.0 / sqrt(9.0 * d);
+          d = sh - 1.0 / 3.0; cc = fast_rsqrt(9.0 * d);   // (the generic kernel: 1 / sqrt, correctly rounded twice; here <= 2 ulp: the theta draws agree to ~1e-16)
           setup = false;
         }
         const double xn = rng.normal();
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(BS, MCU_PUMPSG_MINB) pumps_gibbs_kernel(const 
           const double u = rng.uniform();
           const double x2 = xn * xn;
           if (mt_accept(u, x2, d, v)) {
-            TH(i) = boost * d * v / (be + st[i]);
+            TH(i) = boost * d * v * fast_rcp(be + st[i]);
             ++i; setup = true;
           }
         }

@@ -504,7 +504,7 @@ def test_gibbs_is_rejected_where_no_conjugate_form_is_registered(oracle):
 
 
 def test_pumps_gibbs_kernel_matches_oracle_and_generic_and_restarts(oracle):
-    # fused [Gibbs(theta), Gibbs(beta), AMWG(alpha)] kernel (pumps_fast.cu): the Gibbs draws are the generic kernel's bit for bit, the AMWG
+    # fused [Gibbs(theta), Gibbs(beta), AMWG(alpha)] kernel (pumps_fast.cu): the Gibbs draws are the generic kernel's to the last bit or two (same accept decisions; reciprocals by Newton steps), the AMWG
     # target is evaluated on sufficient statistics
     g, o, eng, _ = run_pair(oracle, "pumps_gibbs_amwg", 64, 300, 100, 2, force_generic=False)
     tied = assert_same_run(g, o, 300, 100, 2)
