@@ -195,17 +195,10 @@ __global__ void __launch_bounds__(BS, MCU_RATSF_MINB) rats_fast_kernel(const __g
       for (int i = 0; i < NR; ++i) { const double d = arr[i * BS + tid] - cen; v = fma(d, d, v); }
       V = v;
     };
-    // blocks 1-2 (alpha side) and 3-4 (beta side): the two Slice([mu, s2]) updates are one piece of code run twice (a rolled two-trip loop:
-    // the kernel's top stall is instruction fetch, its hot code was 58 KB), the AMWG blocks differ in their arithmetic and stay separate
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-      if (side == 0) amwg_block(std::integral_constant<int, 0>{}, 1u, m1, ad1, mua, s2a);
-      else amwg_block(std::integral_constant<int, 1>{}, 3u, m3, ad3, mub, s2b);
-      double mu = side ? mub : mua, s2 = side ? s2b : s2a, cen, V;
-      centred(side ? sbe : sal, cen, V);
-      slice_mu_s2(2u + 2u * (uint32_t)side, mu, s2, cen, V, side ? cfg.w_b : cfg.w_a);
-      if (side) { mub = mu; s2b = s2; } else { mua = mu; s2a = s2; }
-    }
+    amwg_block(std::integral_constant<int, 0>{}, 1u, m1, ad1, mua, s2a);
+    { double cen, V; centred(sal, cen, V); slice_mu_s2(2u, mua, s2a, cen, V, cfg.w_a); }
+    amwg_block(std::integral_constant<int, 1>{}, 3u, m3, ad3, mub, s2b);
+    { double cen, V; centred(sbe, cen, V); slice_mu_s2(4u, mub, s2b, cen, V, cfg.w_b); }
     // ================================================================== thinning + streaming moments (mcmc.jl:76-78)
     if (iter > a.burnin && (iter - a.burnin) % a.thin == 0) {
       double mon[RatsModel::P];
