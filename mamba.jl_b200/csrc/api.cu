@@ -80,7 +80,7 @@ struct mcu_ctx {
   int* g_map = nullptr; long long g_pass_C = 0; int g_pass_nslab = 0;   // tick-engine compaction: pass slot k = chain g_map[k] (g_pass_C = 0: every chain, no map)
   long long compactions = 0; unsigned long long pass_slots = 0;   // chain slots the gradient passes of the tick engine carried (sum over ticks)
   double g_lp_const = 0.0;
-  unsigned char* g_blob = nullptr; double* g_xty = nullptr; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
+  unsigned char* g_blob = nullptr; double* g_xty = nullptr; double* g_colscale = nullptr /* [2d]: column factors of the packed X and their reciprocals, or null */; int g_nslab_tc = 0; int glm_impl = 1; int glm_impl_run = 1;   // 1 = tensor-core kernel, 0 = FP64 reference kernel
   long long ticks = 0;
   unsigned long long* d_work = nullptr;   // device counter of gradient evaluations (rats_warp leapfrogs, GLM useful chain-gradients)
   bool g_reset = false;   // the GLM tick-engine records must be re-initialised before the next run (new inits / state)
@@ -467,7 +467,7 @@ void free_scheme(mcu_ctx* h) {
 }
 // packed X / y tiles, X'y and the family constants: depend on the data only (they survive mcu_set_inits / mcu_set_state)
 void free_glm_data(mcu_ctx* h) {
-  cudaFree(h->g_blob); h->g_blob = nullptr; cudaFree(h->g_xty); h->g_xty = nullptr;
+  cudaFree(h->g_blob); h->g_blob = nullptr; cudaFree(h->g_xty); h->g_xty = nullptr; cudaFree(h->g_colscale); h->g_colscale = nullptr;
 }
 // tick-engine state of the chains
 void free_glm_buffers(mcu_ctx* h) {
@@ -640,7 +640,24 @@ int ensure_glm_buffers(mcu_ctx* h) {
     const size_t blob_bytes = (size_t)glm_tc_num_tiles(N) * glm_tc_tile_bytes(h->D);
     CK(cudaMalloc(&h->g_blob, blob_bytes));
     const int fam = glm_family(h);
-    glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, fam, h->g_blob, h->stream); h->launches++;
+    {
+      // fp16 hi / lo operands: a column whose largest magnitude is above 2^14 (fp16 overflows at 65,504) or below 2^-6 (the lo term goes
+      // subnormal) is packed times a power of two that brings it into [1, 2); the pass divides Theta and the gradient by the same factor
+      const std::vector<double>& Xs = h->inputs["X"];
+      std::vector<double> cmax(h->D, 0.0), cs(2 * (size_t)h->D, 1.0);
+      for (long long i = 0; i < N; ++i) for (int j = 0; j < h->D; ++j) { const double v = std::fabs(Xs[(size_t)i * h->D + j]); if (v > cmax[j]) cmax[j] = v; }
+      bool any = false;
+      for (int j = 0; j < h->D; ++j) {
+        if (!std::isfinite(cmax[j])) return fail(h, MCU_ERR_ARG, "GLM design matrix holds a non-finite value");
+        if (cmax[j] > 0.0 && (cmax[j] > 16384.0 || cmax[j] < 0.015625)) { int e = 0; std::frexp(cmax[j], &e); cs[j] = std::ldexp(1.0, 1 - e); cs[h->D + j] = std::ldexp(1.0, e - 1); any = true; }
+      }
+      if (any) {
+        CK(cudaMalloc(&h->g_colscale, sizeof(double) * 2 * h->D));
+        CK(cudaMemcpyAsync(h->g_colscale, cs.data(), sizeof(double) * 2 * h->D, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+      }
+    }
+    glm_tc_pack(h->d_inputs["X"], h->d_inputs["y"], (int)N, h->D, fam, h->g_blob, h->stream, h->g_colscale); h->launches++;
     // X'(y - 1/2) (FP64, once): sum_i (y_i - 1/2) eta_i = beta . X'(y - 1/2) is the part of the log-likelihood that is linear in
     // beta (y eta from the Bernoulli term, -eta/2 from softplus(eta) = eta/2 + |eta|/2 + log(1 + e^-|eta|)); the fold adds it
     std::vector<double> xty(h->D, 0.0);
@@ -664,10 +681,10 @@ int glm_gradient_dispatch(mcu_ctx* h, int N) {
     const bool cmp = h->g_pass_C > 0;                                   // compacted pass: only the chains that are still running
     const long long Cp = cmp ? h->g_pass_C : h->C; const int ns = cmp ? h->g_pass_nslab : h->g_nslab_tc;
     const int* map = cmp ? h->g_map : nullptr;
-    if (glm_tc_launch(h->g_blob, N, h->D, Cp, h->g_req, ns, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), glm_family(h), glm_sigma(h), h->stream, map, h->C) != 0)
+    if (glm_tc_launch(h->g_blob, N, h->D, Cp, h->g_req, ns, h->g_part_lp, reinterpret_cast<float*>(h->g_part_g), glm_family(h), glm_sigma(h), h->stream, map, h->C, h->g_colscale ? h->g_colscale + h->D : nullptr) != 0)
       return fail(h, MCU_ERR_CUDA, "glm_tc_kernel launch failed");
     glm_fold_tc(h->g_part_lp, reinterpret_cast<const float*>(h->g_part_g), ns, ns * glm_tc_nsub(N, ns), h->D, Cp,
-                h->g_req, h->g_xty, h->g_lp_const, h->g_lp, h->g_grad, h->stream, map, h->C);
+                h->g_req, h->g_xty, h->g_lp_const, h->g_lp, h->g_grad, h->stream, map, h->C, h->g_colscale ? h->g_colscale + h->D : nullptr);
   } else {
     glm_grad_reference(h->d_inputs["X"], h->d_inputs["y"], N, h->D, h->C, h->g_req, h->g_nslab, h->g_part_lp, h->g_part_g,
                        h->g_lp, h->g_grad, glm_family(h), glm_sigma(h), h->stream);

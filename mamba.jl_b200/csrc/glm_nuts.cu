@@ -418,7 +418,8 @@ __global__ void glm_fold2_kernel(const double* __restrict__ part_lp, const doubl
 // The partials are indexed by PASS slot k (C slots); with a compaction map the results go to chain map[k] of the Cfull-strided lp / grad / req.
 __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const float* __restrict__ part_g, int nslab_lp, int nslab_g,
                                    long long C, int d, const double* __restrict__ req, const double* __restrict__ xty, double lp_const,
-                                   double* __restrict__ lp, double* __restrict__ grad, const int* __restrict__ map, long long Cfull) {
+                                   double* __restrict__ lp, double* __restrict__ grad, const int* __restrict__ map, long long Cfull,
+                                   const double* __restrict__ col_inv) {
   const long long dC = (long long)d * C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < dC) {
@@ -430,7 +431,8 @@ __global__ void glm_fold_tc_kernel(const double* __restrict__ part_lp, const flo
     }
     for (; k < nslab_g; ++k) s0 += (double)part_g[(size_t)k * dC + i];
     const long long j = i / C, slot = i % C;
-    grad[(size_t)j * Cfull + (map ? (long long)map[slot] : slot)] = (s0 + s1) + (s2 + s3);
+    const double gsum = (s0 + s1) + (s2 + s3);
+    grad[(size_t)j * Cfull + (map ? (long long)map[slot] : slot)] = col_inv ? gsum * col_inv[j] : gsum;   // undo the column factor of the packed X (exact: a power of two)
   } else if (i < dC + C) {
     const long long slot = i - dC;
     const long long c = map ? (long long)map[slot] : slot;
@@ -463,9 +465,9 @@ __global__ void __launch_bounds__(1024) glm_compact_kernel(const double* __restr
 }
 void glm_compact(const double* sc, long long C, int* map, int* count, cudaStream_t st) { glm_compact_kernel<<<1, 1024, 0, st>>>(sc, C, map, count); }
 void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
-                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st, const int* map, long long Cfull) {
+                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st, const int* map, long long Cfull, const double* col_inv) {
   const long long dC = (long long)d * C;
-  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp_const, lp, grad, map, map ? Cfull : C);
+  glm_fold_tc_kernel<<<(unsigned)((dC + C + 255) / 256), 256, 0, st>>>(part_lp, part_g, nslab_lp, nslab_g, C, d, req, xty, lp_const, lp, grad, map, map ? Cfull : C, col_inv);
 }
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st) {
   const long long dC = (long long)d * C;

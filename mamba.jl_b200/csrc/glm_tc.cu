@@ -117,7 +117,7 @@ __device__ __forceinline__ uint32_t pack_half2(__half lo, __half hi) {
 // ---- X pre-pack: fp64 [N x d] row-major → per tile [hi | lo | y] ----------------------------------------
 // hi/lo blocks: core matrices (8 rows x 8 cols fp16 = 128 B) ordered [row-block][col-block].
 __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __restrict__ y, int N, int d, int DP, int family,
-                                unsigned char* __restrict__ blob, size_t tile_bytes) {
+                                unsigned char* __restrict__ blob, size_t tile_bytes, const double* __restrict__ colscale) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over tiles * TR * (DP/8) 16-byte chunks
   const int CB = DP / 8;
   const long long chunks_per_tile = (long long)TR * CB;
@@ -130,7 +130,8 @@ __global__ void glm_pack_kernel(const double* __restrict__ X, const double* __re
   __half hi[8], lo[8];
   for (int e = 0; e < 8; ++e) {
     const int col = cb * 8 + e;
-    const float x = (grow < N && col < d) ? (float)X[(size_t)grow * d + col] : 0.0f;
+    // colscale[col] is a power of two (1 for columns inside the fp16 range, see glm_tc_pack): the product is exact
+    const float x = (grow < N && col < d) ? (float)(X[(size_t)grow * d + col] * (colscale ? colscale[col] : 1.0)) : 0.0f;
     hi[e] = __float2half_rn(x);
     lo[e] = __float2half_rn(x - __half2float(hi[e]));
   }
@@ -155,6 +156,7 @@ struct TcArgs {
   float* part_g;             // [nslab][d][C]  FP32 running sum of the TMEM accumulator flushes (folded over slabs in FP64)
   int n_pad;                 // zero rows appended to the last tile
   double theta_scale;        // log2(e) for the logit / log links (eta arrives as an exponent of 2), 1 for the identity link
+  const double* col_inv;     // [d] 1 / colscale (powers of two) or nullptr: X was packed as X diag(colscale), so Theta = beta .* col_inv
   float r_scale;             // Normal: 1 / sigma^2
 };
 
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int col = ck * 16 + e + u;
-          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.Cfull + csrc] * a.theta_scale) : 0.0f;
+          x[u] = (c < a.C && col < a.d) ? (float)(a.req[(size_t)col * a.Cfull + csrc] * (a.col_inv ? a.col_inv[col] * a.theta_scale : a.theta_scale)) : 0.0f;
         }
         const __half2 h = __floats2half2_rn(x[0], x[1]);
         const float2 hb = __half22float2(h);
@@ -476,18 +478,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) glm_tc_kernel(const TcArgs a) {
 size_t glm_tc_tile_bytes(int d) { const int DP = (d + 15) / 16 * 16; return (size_t)2 * TR * DP * 2 + TR * sizeof(float); }
 long long glm_tc_num_tiles(long long N) { return (N + TR - 1) / TR; }
 
-void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st) {
+// colscale (device, [d]) or nullptr: power-of-two column factors that bring a column whose largest magnitude lies outside [2^-6, 2^14] into
+// [1, 2) before the fp16 hi / lo split (fp16 overflows above 65,504 and loses the lo term below ~6e-5); the pass undoes them exactly
+// (Theta = beta / colscale on the way in, gradient / colscale in the fold).
+void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st, const double* colscale) {
   const int DP = (d + 15) / 16 * 16;
   const long long total = glm_tc_num_tiles(N) * TR * (DP / 8);
-  glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, family, blob, glm_tc_tile_bytes(d));
+  glm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, y, N, d, DP, family, blob, glm_tc_tile_bytes(d), colscale);
 }
 
 int glm_tc_nsub(long long, int) { return 1; }   // one FP32 gradient partial per slab (the flush intervals are summed in place)
 
 // Returns 0 on success.  part_lp [nslab][C] (FP64), part_g [nslab][d][C] (FP32), to be folded over slabs (glm_fold_tc).
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st, const int* map, long long Cfull) {
+                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st, const int* map, long long Cfull, const double* col_inv) {
   TcArgs a;
+  a.col_inv = col_inv;
   a.DP = (d + 15) / 16 * 16;
   if (a.DP > 128) return -2;   // TMEM budget: G (DP columns) + Theta hi/lo (DP/2 each) next to the two D1 buffers
   a.blob = blob; a.tile_bytes = glm_tc_tile_bytes(d); a.NT = (int)glm_tc_num_tiles(N);

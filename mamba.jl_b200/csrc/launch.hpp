@@ -124,12 +124,14 @@ void glm_grad_reference(const double* X, const double* y, int N, int d, long lon
 size_t glm_tc_tile_bytes(int d);
 long long glm_tc_num_tiles(long long N);
 int glm_tc_nsub(long long N, int nslab);
-void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st);
+void glm_tc_pack(const double* X, const double* y, int N, int d, int family, unsigned char* blob, cudaStream_t st, const double* colscale = nullptr);
 // C = chains of the pass; with a compaction map (slot k = chain map[k]) req / lp / grad keep the handle's stride Cfull
 int glm_tc_launch(const unsigned char* blob, int N, int d, long long C, const double* req, int nslab,
-                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st, const int* map = nullptr, long long Cfull = 0);
+                  double* part_lp, float* part_g, int family, double sigma, cudaStream_t st, const int* map = nullptr, long long Cfull = 0,
+                  const double* col_inv = nullptr);
 void glm_fold_tc(const double* part_lp, const float* part_g, int nslab_lp, int nslab_g, int d, long long C, const double* req,
-                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st, const int* map = nullptr, long long Cfull = 0);
+                 const double* xty, double lp_const, double* lp, double* grad, cudaStream_t st, const int* map = nullptr, long long Cfull = 0,
+                 const double* col_inv = nullptr);
 void glm_compact(const double* sc, long long C, int* map, int* count, cudaStream_t st);
 void glm_fold(const double* part_lp, const double* part_g, int nslab_lp, int nslab_g, int d, long long C, double* lp, double* grad, cudaStream_t st);
 

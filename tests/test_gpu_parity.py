@@ -757,6 +757,30 @@ def test_glm_tensor_core_gradient_matches_fp64_kernel(oracle, N, d, C):
     assert np.max(np.abs(g1 - g0) / gscale) < 1e-5
 
 
+def test_glm_tensor_core_gradient_with_columns_outside_the_fp16_range(oracle):
+    # The tensor-core pass holds X as fp16 hi + lo pairs: a column in the millions would overflow (65,504) and one around 1e-7 would lose
+    # its lo term.  Such columns are packed times a power of two and the factor is undone exactly on Theta and on the gradient, so the
+    # 1e-5 bound of north_star holds per column whatever the units of the covariates.
+    from mambacuda.engine import Engine
+    N, d, C = 4000, 12, 128
+    X, y, _ = helpers.glm_data(N=N, d=d, seed=11)
+    colfac = np.ones(d); colfac[1] = 3.7e6; colfac[2] = 2.9e-7; colfac[5] = 1.0e5; colfac[7] = 4.4e-4
+    Xs = X * colfac
+    eng = Engine("glm", C, seed=1)
+    eng.set_data("X", Xs); eng.set_data("y", y)
+    eng.set_scheme([dict(kind="nuts", nodes=[0])])
+    beta = np.random.default_rng(12).normal(scale=0.5 / np.sqrt(d), size=(C, d)) / colfac      # eta stays O(1)
+    lp0, g0 = eng.glm_gradient(beta, impl=0)
+    lp1, g1 = eng.glm_gradient(beta, impl=1)
+    eta = beta @ Xs.T
+    np.testing.assert_allclose(lp0, (y * eta - np.logaddexp(0, eta)).sum(axis=1), rtol=1e-12)
+    assert np.all(np.isfinite(lp1)) and np.all(np.isfinite(g1))
+    np.testing.assert_allclose(lp1, lp0, rtol=1e-5)
+    # per column: the gradient of column j carries the units of that column
+    gscale = np.abs(g0 / colfac).max(axis=1, keepdims=True)
+    assert np.max(np.abs((g1 - g0) / colfac) / gscale) < 1e-5
+
+
 def test_glm_tick_engine_with_tensor_core_gradient_is_statistically_equivalent(oracle):
     from mambacuda.engine import Engine
     X, y, beta = helpers.glm_data(N=4000, d=6, seed=5)
