@@ -166,3 +166,13 @@ def test_julia_and_ctypes_bindings_pass_as_many_arguments_as_the_header_declares
         name, n = m.group(1), len(_split_top(m.group(2)))
         assert name in protos, name
         assert n == protos[name], f"{name}: ctypes declares {n} arguments, the header {protos[name]}"
+
+
+def test_measurement_helpers_compile():
+    """tools/*.py (variant timing, ncu drivers, table generator) byte-compile: they are run by hand on the GPU box, so nothing else would notice a typo."""
+    import glob
+    import py_compile
+    files = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py")))
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
