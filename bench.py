@@ -57,7 +57,7 @@ SCHEME = [dict(kind="amwg", nodes=[0, 1, 2, 3], scale=0.1), dict(kind="amwg", no
 SEEDS_WORKLOAD = "seeds random-effects logistic regression (21 plates, doc/examples/seeds.jl), AMWG(alpha0..alpha12)+AMWG(b)+AMWG(s2)"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels (ncu --set full captures, profiles/), keyed by shape
-SEEDS_KERNEL_DRAM_BYTES = {(125000, 2000): 86.63e6 + 117.40e6}
+SEEDS_KERNEL_DRAM_BYTES = {(125000, 2000): 85.71e6 + 117.95e6}   # profiles/r2_seeds_dram_2000.csv (round-2 kernel; round 1: 86.63e6 + 117.40e6)
 GLM_KERNEL_DRAM_BYTES = {512: 453e6 + 5e6, 4096: 546.2e6 + 38.0e6}   # profiles/r1_glm_tc_summary.md, profiles/r2_glm_tc_c4096_ncu.csv
 
 
